@@ -1,0 +1,129 @@
+"""Seeded synthetic references and reordered read sets (BASELINE.json configs).
+
+Pure numpy; no dependency on the oracle or on the CUDA library.  Bases are nt4 codes as the
+reference uses them after conversion (FM_index/bntseq.c:46-63): A,C,G,T -> 0..3, anything else 4.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+NT4 = np.full(256, 4, dtype=np.uint8)
+for _i, _ch in enumerate("ACGT"):
+    NT4[ord(_ch)] = _i
+    NT4[ord(_ch.lower())] = _i
+NT4[ord("-")] = 5  # bntseq.c:49
+CODE2ASCII = np.frombuffer(b"ACGTN", dtype=np.uint8)
+
+
+def random_reference(l_pac: int, seed: int = 20261018) -> np.ndarray:
+    """i.i.d. uniform ACGT reference of l_pac bases (configs 1-3)."""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 4, size=l_pac, dtype=np.uint8)
+
+
+def repeat_rich_reference(l_pac: int, seed: int = 7, n_segdup: int = 100, segdup_len: int = 3000,
+                          n_tandem: int = 200, divergence: float = 0.02) -> np.ndarray:
+    """Random backbone + segmental duplications + tandem repeats (config 4): many mems with
+    x[2] > max_occ and with split_width < x[2] < max_mem_intv."""
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(0, 4, size=l_pac, dtype=np.uint8)
+    # segmental duplications: a few source segments copied many times with 0..divergence substitutions
+    n_src = max(1, n_segdup // 25)
+    for s in range(n_src):
+        seg_len = min(segdup_len, l_pac // 4)
+        src = int(rng.integers(0, l_pac - seg_len))
+        seg = ref[src:src + seg_len].copy()
+        for _ in range(n_segdup // n_src):
+            dst = int(rng.integers(0, l_pac - seg_len))
+            cp = seg.copy()
+            d = float(rng.uniform(0, divergence))
+            mut = rng.random(seg_len) < d
+            cp[mut] = (cp[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+            if rng.random() < 0.5:
+                cp = (3 - cp)[::-1]
+            ref[dst:dst + seg_len] = cp
+    # tandem repeats
+    for _ in range(n_tandem):
+        unit = int(rng.integers(2, 61))
+        copies = int(rng.integers(50, 600))
+        tot = min(unit * copies, l_pac // 8)
+        dst = int(rng.integers(0, l_pac - tot))
+        u = rng.integers(0, 4, size=unit, dtype=np.uint8)
+        ref[dst:dst + tot] = np.resize(u, tot)
+    return ref
+
+
+def simulate_reads(ref: np.ndarray, n_reads: int, read_len=150, sub_rate: float = 0.01, seed: int = 1,
+                   sort_by_pos: bool = True, n_rate: float = 0.0, window: tuple[int, int] | None = None):
+    """Sample reads at uniform start positions, `sub_rate` substitutions per base, 50 % reverse
+    complemented, position-sorted to mimic SPRING reordering (config 1).  `read_len` may be an int
+    or a sequence of lengths to mix.  Returns (bases u8 concatenated, offsets u32[n+1], pos i64[n])."""
+    rng = np.random.default_rng(seed)
+    l_pac = ref.shape[0]
+    lens_choice = np.atleast_1d(np.asarray(read_len, dtype=np.int64))
+    lens = lens_choice[rng.integers(0, lens_choice.size, size=n_reads)]
+    lo, hi = (0, l_pac) if window is None else window
+    pos = rng.integers(lo, np.maximum(lo + 1, hi - lens), size=n_reads)
+    if sort_by_pos:
+        order = np.argsort(pos, kind="stable")
+        pos, lens = pos[order], lens[order]
+    off = np.zeros(n_reads + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    total = int(off[-1])
+    rid = np.repeat(np.arange(n_reads, dtype=np.int64), lens)
+    within = np.arange(total, dtype=np.int64) - off[rid]
+    rev = rng.random(n_reads) < 0.5
+    src = np.where(rev[rid], pos[rid] + lens[rid] - 1 - within, pos[rid] + within)
+    bases = ref[src]
+    bases = np.where(rev[rid], 3 - bases, bases).astype(np.uint8)
+    mut = rng.random(total) < sub_rate
+    bases[mut] = (bases[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+    if n_rate > 0:
+        bases[rng.random(total) < n_rate] = 4
+    return bases, off.astype(np.uint32), pos
+
+
+def shuffle_reads(bases: np.ndarray, off: np.ndarray, seed: int = 3):
+    """Random permutation of a read set (the 'shuffled' arm of config 5)."""
+    rng = np.random.default_rng(seed)
+    n = off.shape[0] - 1
+    perm = rng.permutation(n)
+    lens = np.diff(off.astype(np.int64))[perm]
+    new_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=new_off[1:])
+    rid = np.repeat(np.arange(n, dtype=np.int64), lens)
+    within = np.arange(int(new_off[-1]), dtype=np.int64) - new_off[rid]
+    return bases[off.astype(np.int64)[perm][rid] + within], new_off.astype(np.uint32), perm
+
+
+def write_fasta(path: str, ref: np.ndarray, name: str = "chr1", width: int = 80) -> None:
+    asc = CODE2ASCII[ref]
+    with open(path, "wb") as f:
+        f.write(b">" + name.encode() + b"\n")
+        for i in range(0, asc.shape[0], width * 4096):
+            blk = asc[i:i + width * 4096]
+            n_full = blk.shape[0] // width
+            if n_full:
+                rows = blk[:n_full * width].reshape(n_full, width)
+                out = np.concatenate([rows, np.full((n_full, 1), 10, dtype=np.uint8)], axis=1)
+                f.write(out.tobytes())
+            if blk.shape[0] % width:
+                f.write(blk[n_full * width:].tobytes() + b"\n")
+
+
+def write_reads_txt(path: str, bases: np.ndarray, off: np.ndarray) -> None:
+    """One read per line, every line '\\n'-terminated (main.cpp:36-58 line reader)."""
+    asc = CODE2ASCII[np.minimum(bases, 4)]
+    with open(path, "wb") as f:
+        for r in range(off.shape[0] - 1):
+            f.write(asc[off[r]:off[r + 1]].tobytes() + b"\n")
+
+
+def split_len_bwamem(min_seed_len: int, split_factor: float) -> int:
+    """bwamem.c:223: int * float in float, + .499 promoted to double."""
+    return int(float(np.float32(min_seed_len) * np.float32(split_factor)) + .499)
+
+
+def split_len_compseed(min_seed_len: int, split_factor: float) -> int:
+    """comp_seed.cpp:2279: 1.0 * int * float in double."""
+    return int(1.0 * min_seed_len * float(np.float32(split_factor)) + .499)
