@@ -1,0 +1,10 @@
+"""compseed_b200: B200-native (sm_100a) SMEM seeding path of CompSeed / BWA-MEM behind a C-ABI.
+
+Only the seeding hot path lives here: csrc/ holds the CUDA kernels and the
+C-ABI, seeding.py the ctypes mirror of the reference's interface, synth.py the synthetic inputs.
+"""
+from .seeding import (FMIndex, SeedContext, SeedOpt, SeedResult, CompSeedError, seed_reads, device_count,
+                      probe_random_gather, flush_l2, load_library)
+
+__all__ = ["FMIndex", "SeedContext", "SeedOpt", "SeedResult", "CompSeedError", "seed_reads", "device_count",
+           "probe_random_gather", "flush_l2", "load_library"]

@@ -1,0 +1,708 @@
+// Host side of the C-ABI (include/compseed_b200.h): index upload / re-layout, batch contexts with
+// pinned double-buffered slots, one CUDA stream per slot, kernel launches and result gathering.
+// No CPU compute path exists here: every entry point needs a CUDA device and fails loudly without one.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <vector>
+#include <algorithm>
+#include <cub/device/device_scan.cuh>
+#include "cs_kernels.cuh"
+
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	set_err(CS_E_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); goto fail; } } while (0)
+
+extern "C" const char *cs_last_error(void) { return g_err; }
+
+extern "C" int cs_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+static int use_device(int device)
+{
+	int n = cs_device_count();
+	if (n <= 0) return set_err(CS_E_NODEVICE, "no CUDA device visible: compseed_b200 has no CPU path");
+	if (device < 0 || device >= n) return set_err(CS_E_ARG, "device %d out of range (%d visible)", device, n);
+	cudaError_t e = cudaSetDevice(device);
+	if (e != cudaSuccess) return set_err(CS_E_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+	return CS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// index
+// ---------------------------------------------------------------------------------------------
+struct cs_index {
+	int device;
+	DevIndex d;
+	uint4 *d_buckets;
+	uint64_t *d_sa;
+	uint64_t bytes;
+	uint64_t bwt_size_ref;  // words of the reference layout
+	int sa_intv;
+	int n_sm;
+};
+
+static int log2_exact(uint64_t v) { int s = 0; while ((1ull << s) < v) ++s; return (1ull << s) == v ? s : -1; }
+
+// replaces the device SA by one sampled every new_intv rows
+static int resample_sa(cs_index *idx, int new_intv)
+{
+	uint64_t *d_new = nullptr;
+	int sh = log2_exact((uint64_t)new_intv);
+	if (sh < 0) return set_err(CS_E_ARG, "SA interval %d is not a power of two", new_intv);
+	uint64_t n_new = (idx->d.seq_len + new_intv) / new_intv;
+	CK(cudaMalloc(&d_new, n_new * 8));
+	k_resample_sa<<<idx->n_sm * 8, 256>>>(idx->d, d_new, n_new, (uint32_t)sh);
+	CK(cudaGetLastError());
+	CK(cudaDeviceSynchronize());
+	CK(cudaFree(idx->d_sa));
+	idx->bytes += n_new * 8; idx->bytes -= idx->d.n_sa * 8;
+	idx->d_sa = d_new; idx->d.sa = d_new; idx->d.n_sa = n_new;
+	idx->d.sa_mask = (uint32_t)new_intv - 1; idx->d.sa_shift = (uint32_t)sh; idx->sa_intv = new_intv;
+	return CS_OK;
+fail:
+	if (d_new) cudaFree(d_new);
+	return CS_E_CUDA;
+}
+
+extern "C" cs_index_t *cs_index_upload(const cs_bwt_view_t *v, int device, int dense_sa_intv)
+{
+	cs_index *idx = nullptr;
+	uint32_t *d_src = nullptr;
+	if (!v || !v->bwt || !v->sa) { set_err(CS_E_ARG, "null bwt view"); return nullptr; }
+	if (v->seq_len == 0 || v->seq_len >= (1ull << 37)) { set_err(CS_E_ARG, "seq_len %llu outside (0, 2^37)", (unsigned long long)v->seq_len); return nullptr; }
+	if (log2_exact((uint64_t)v->sa_intv) < 0) { set_err(CS_E_ARG, "sa_intv %d is not a power of two", v->sa_intv); return nullptr; }
+	if (use_device(device) != CS_OK) return nullptr;
+	idx = (cs_index*)calloc(1, sizeof(cs_index));
+	idx->device = device;
+	{
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, device));
+		idx->n_sm = prop.multiProcessorCount;
+	}
+	idx->bwt_size_ref = v->bwt_size;
+	idx->d.primary = v->primary; idx->d.seq_len = v->seq_len;
+	for (int i = 0; i < 5; ++i) idx->d.L2[i] = v->L2[i];
+	idx->d.n_buckets = (v->seq_len + 63) / 64 + 1; // one zero pad bucket: row `primary` may index one past the end (bwt.c:55-58)
+	CK(cudaMalloc(&idx->d_buckets, idx->d.n_buckets * 32));
+	CK(cudaMemset(idx->d_buckets, 0, idx->d.n_buckets * 32));
+	CK(cudaMalloc(&d_src, v->bwt_size * 4));
+	CK(cudaMemcpy(d_src, v->bwt, v->bwt_size * 4, cudaMemcpyHostToDevice));
+	k_relayout<<<idx->n_sm * 8, 256>>>(d_src, v->bwt_size, v->seq_len, idx->d_buckets, idx->d.n_buckets - 1);
+	CK(cudaGetLastError());
+	CK(cudaDeviceSynchronize());
+	CK(cudaFree(d_src)); d_src = nullptr;
+	idx->d.buckets = idx->d_buckets;
+	CK(cudaMalloc(&idx->d_sa, v->n_sa * 8));
+	CK(cudaMemcpy(idx->d_sa, v->sa, v->n_sa * 8, cudaMemcpyHostToDevice));
+	{
+		uint64_t m1 = (uint64_t)-1;
+		CK(cudaMemcpy(idx->d_sa, &m1, 8, cudaMemcpyHostToDevice)); // sa[0] = -1 (bwt.c:83,437)
+	}
+	idx->d.sa = idx->d_sa; idx->d.n_sa = v->n_sa;
+	idx->sa_intv = v->sa_intv;
+	idx->d.sa_mask = (uint32_t)v->sa_intv - 1; idx->d.sa_shift = (uint32_t)log2_exact((uint64_t)v->sa_intv);
+	idx->bytes = idx->d.n_buckets * 32 + v->n_sa * 8;
+	if (dense_sa_intv > 0 && dense_sa_intv < v->sa_intv)
+		if (resample_sa(idx, dense_sa_intv) != CS_OK) goto fail;
+	return idx;
+fail:
+	if (d_src) cudaFree(d_src);
+	if (idx) { if (idx->d_buckets) cudaFree(idx->d_buckets); if (idx->d_sa) cudaFree(idx->d_sa); free(idx); }
+	return nullptr;
+}
+
+extern "C" cs_index_t *cs_index_load(const char *prefix, int device, int dense_sa_intv)
+{ // file format: bwt.c:385-407 (dump), bwt.c:421-462 (restore)
+	char fn[4096];
+	cs_bwt_view_t v;
+	memset(&v, 0, sizeof v);
+	uint32_t *bwt = nullptr; uint64_t *sa = nullptr;
+	cs_index_t *idx = nullptr;
+	FILE *fp;
+	uint64_t hdr[7];
+	if (cs_device_count() <= 0) { set_err(CS_E_NODEVICE, "no CUDA device visible: compseed_b200 has no CPU path"); return nullptr; }
+	snprintf(fn, sizeof fn, "%s.bwt", prefix);
+	if ((fp = fopen(fn, "rb")) == nullptr) { set_err(CS_E_IO, "cannot open %s", fn); return nullptr; }
+	fseek(fp, 0, SEEK_END);
+	v.bwt_size = ((uint64_t)ftell(fp) - 40) >> 2;
+	fseek(fp, 0, SEEK_SET);
+	bwt = (uint32_t*)malloc(v.bwt_size * 4);
+	if (fread(&v.primary, 8, 1, fp) != 1 || fread(v.L2 + 1, 8, 4, fp) != 4 || fread(bwt, 4, v.bwt_size, fp) != v.bwt_size) {
+		fclose(fp); set_err(CS_E_IO, "short read on %s", fn); goto done;
+	}
+	fclose(fp);
+	v.seq_len = v.L2[4];
+	snprintf(fn, sizeof fn, "%s.sa", prefix);
+	if ((fp = fopen(fn, "rb")) == nullptr) { set_err(CS_E_IO, "cannot open %s", fn); goto done; }
+	if (fread(hdr, 8, 7, fp) != 7) { fclose(fp); set_err(CS_E_IO, "short read on %s", fn); goto done; }
+	if (hdr[0] != v.primary || hdr[6] != v.seq_len) { fclose(fp); set_err(CS_E_IO, "SA-BWT inconsistency in %s (bwt.c:429,433)", fn); goto done; }
+	v.sa_intv = (int32_t)hdr[5];
+	v.n_sa = (v.seq_len + v.sa_intv) / v.sa_intv;
+	sa = (uint64_t*)malloc(v.n_sa * 8);
+	sa[0] = (uint64_t)-1;
+	if (fread(sa + 1, 8, v.n_sa - 1, fp) != v.n_sa - 1) { fclose(fp); set_err(CS_E_IO, "short read on %s", fn); goto done; }
+	fclose(fp);
+	v.bwt = bwt; v.sa = sa;
+	idx = cs_index_upload(&v, device, dense_sa_intv);
+done:
+	free(bwt); free(sa);
+	return idx;
+}
+
+extern "C" int cs_index_info(const cs_index_t *idx, cs_bwt_view_t *v, uint64_t *device_bytes)
+{
+	if (!idx) return set_err(CS_E_ARG, "null index");
+	if (v) {
+		memset(v, 0, sizeof *v);
+		v->primary = idx->d.primary; v->seq_len = idx->d.seq_len;
+		for (int i = 0; i < 5; ++i) v->L2[i] = idx->d.L2[i];
+		v->bwt_size = idx->bwt_size_ref; v->sa_intv = idx->sa_intv; v->n_sa = idx->d.n_sa;
+	}
+	if (device_bytes) *device_bytes = idx->bytes;
+	return CS_OK;
+}
+
+extern "C" int cs_index_download(const cs_index_t *idx, cs_bwt_view_t *v, uint32_t *bwt, uint64_t *sa, int out_sa_intv)
+{
+	uint32_t *d_ref = nullptr; uint64_t *d_sa = nullptr;
+	if (!idx || !v) return set_err(CS_E_ARG, "null argument");
+	int sh = log2_exact((uint64_t)out_sa_intv);
+	if (sh < 0) return set_err(CS_E_ARG, "out_sa_intv %d is not a power of two", out_sa_intv);
+	if (use_device(idx->device) != CS_OK) return CS_E_CUDA;
+	cs_index_info(idx, v, nullptr);
+	v->sa_intv = out_sa_intv;
+	v->n_sa = (idx->d.seq_len + out_sa_intv) / out_sa_intv;
+	if (!bwt && !sa) return CS_OK;
+	if (bwt) {
+		CK(cudaMalloc(&d_ref, idx->bwt_size_ref * 4));
+		CK(cudaMemset(d_ref, 0, idx->bwt_size_ref * 4));
+		k_unlayout<<<idx->n_sm * 8, 256>>>(idx->d_buckets, idx->d.seq_len, d_ref, idx->bwt_size_ref);
+		CK(cudaGetLastError());
+		CK(cudaMemcpy(bwt, d_ref, idx->bwt_size_ref * 4, cudaMemcpyDeviceToHost));
+		CK(cudaFree(d_ref)); d_ref = nullptr;
+	}
+	if (sa) {
+		if (out_sa_intv == idx->sa_intv) CK(cudaMemcpy(sa, idx->d_sa, v->n_sa * 8, cudaMemcpyDeviceToHost));
+		else {
+			CK(cudaMalloc(&d_sa, v->n_sa * 8));
+			k_resample_sa<<<idx->n_sm * 8, 256>>>(idx->d, d_sa, v->n_sa, (uint32_t)sh);
+			CK(cudaGetLastError());
+			CK(cudaMemcpy(sa, d_sa, v->n_sa * 8, cudaMemcpyDeviceToHost));
+			CK(cudaFree(d_sa)); d_sa = nullptr;
+		}
+	}
+	return CS_OK;
+fail:
+	if (d_ref) cudaFree(d_ref);
+	if (d_sa) cudaFree(d_sa);
+	return CS_E_CUDA;
+}
+
+extern "C" void cs_index_free(cs_index_t *idx)
+{
+	if (!idx) return;
+	cudaSetDevice(idx->device);
+	cudaFree(idx->d_buckets); cudaFree(idx->d_sa);
+	free(idx);
+}
+
+// internal: wrap device arrays produced by the on-device builder (cs_index_build.cu)
+cs_index_t *cs_index_adopt(int device, uint4 *d_buckets, uint64_t n_buckets, uint64_t *d_sa, uint64_t n_sa, int sa_intv,
+                           uint64_t primary, const uint64_t L2[5], uint64_t seq_len)
+{
+	cs_index *idx = (cs_index*)calloc(1, sizeof(cs_index));
+	cudaDeviceProp prop;
+	cudaGetDeviceProperties(&prop, device);
+	idx->device = device; idx->n_sm = prop.multiProcessorCount;
+	idx->d_buckets = d_buckets; idx->d_sa = d_sa;
+	idx->d.buckets = d_buckets; idx->d.n_buckets = n_buckets;
+	idx->d.primary = primary; idx->d.seq_len = seq_len;
+	for (int i = 0; i < 5; ++i) idx->d.L2[i] = L2[i];
+	idx->d.sa = d_sa; idx->d.n_sa = n_sa; idx->sa_intv = sa_intv;
+	idx->d.sa_mask = (uint32_t)sa_intv - 1; idx->d.sa_shift = (uint32_t)log2_exact((uint64_t)sa_intv);
+	idx->bwt_size_ref = ((seq_len + 15) >> 4) + ((seq_len + 127) / 128 + 1) * 8;
+	idx->bytes = n_buckets * 32 + n_sa * 8;
+	return idx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// probes
+// ---------------------------------------------------------------------------------------------
+extern "C" int cs_occ4(const cs_index_t *idx, uint32_t n, const uint64_t *k, uint64_t *cnt)
+{
+	uint64_t *d_k = nullptr, *d_c = nullptr;
+	if (!idx || !k || !cnt) return set_err(CS_E_ARG, "null argument");
+	if (n == 0) return CS_OK;
+	if (use_device(idx->device) != CS_OK) return CS_E_CUDA;
+	CK(cudaMalloc(&d_k, (size_t)n * 8)); CK(cudaMalloc(&d_c, (size_t)n * 32));
+	CK(cudaMemcpy(d_k, k, (size_t)n * 8, cudaMemcpyHostToDevice));
+	k_probe_occ4<<<(n + 255) / 256, 256>>>(idx->d, n, d_k, d_c);
+	CK(cudaGetLastError());
+	CK(cudaMemcpy(cnt, d_c, (size_t)n * 32, cudaMemcpyDeviceToHost));
+	cudaFree(d_k); cudaFree(d_c);
+	return CS_OK;
+fail:
+	cudaFree(d_k); cudaFree(d_c);
+	return CS_E_CUDA;
+}
+
+extern "C" int cs_extend(const cs_index_t *idx, uint32_t n, const uint64_t *ik, const int32_t *is_back, uint64_t *ok)
+{
+	uint64_t *d_ik = nullptr, *d_ok = nullptr; int32_t *d_b = nullptr;
+	if (!idx || !ik || !is_back || !ok) return set_err(CS_E_ARG, "null argument");
+	if (n == 0) return CS_OK;
+	if (use_device(idx->device) != CS_OK) return CS_E_CUDA;
+	CK(cudaMalloc(&d_ik, (size_t)n * 24)); CK(cudaMalloc(&d_ok, (size_t)n * 96)); CK(cudaMalloc(&d_b, (size_t)n * 4));
+	CK(cudaMemcpy(d_ik, ik, (size_t)n * 24, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d_b, is_back, (size_t)n * 4, cudaMemcpyHostToDevice));
+	k_probe_extend<<<(n + 255) / 256, 256>>>(idx->d, n, d_ik, d_b, d_ok);
+	CK(cudaGetLastError());
+	CK(cudaMemcpy(ok, d_ok, (size_t)n * 96, cudaMemcpyDeviceToHost));
+	cudaFree(d_ik); cudaFree(d_ok); cudaFree(d_b);
+	return CS_OK;
+fail:
+	cudaFree(d_ik); cudaFree(d_ok); cudaFree(d_b);
+	return CS_E_CUDA;
+}
+
+extern "C" int cs_sa(const cs_index_t *idx, uint32_t n, const uint64_t *k, uint64_t *out)
+{
+	uint64_t *d_k = nullptr; unsigned long long *d_w = nullptr;
+	if (!idx || !k || !out) return set_err(CS_E_ARG, "null argument");
+	if (n == 0) return CS_OK;
+	if (use_device(idx->device) != CS_OK) return CS_E_CUDA;
+	CK(cudaMalloc(&d_k, (size_t)n * 8)); CK(cudaMalloc(&d_w, 24));
+	CK(cudaMemset(d_w, 0, 24));
+	CK(cudaMemcpy(d_w + 2, &n, 4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d_k, k, (size_t)n * 8, cudaMemcpyHostToDevice));
+	k_sa_resolve<<<idx->n_sm * 4, 256>>>(idx->d, reinterpret_cast<const uint32_t*>(d_w + 2), n, d_k, d_w, d_w + 1);
+	CK(cudaGetLastError());
+	CK(cudaMemcpy(out, d_k, (size_t)n * 8, cudaMemcpyDeviceToHost));
+	cudaFree(d_k); cudaFree(d_w);
+	return CS_OK;
+fail:
+	cudaFree(d_k); cudaFree(d_w);
+	return CS_E_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch contexts
+// ---------------------------------------------------------------------------------------------
+struct Ctrl { // zeroed before every run; copied back after it
+	uint32_t next_read, pad0;
+	unsigned long long pool_used;
+	unsigned long long counters[4];
+	unsigned long long sa_work, lf_steps;
+	int error, pad1;
+	uint32_t n_mems, n_seeds;
+};
+
+struct Slot {
+	cudaStream_t stream;
+	cudaEvent_t ev[5];   // slot start, seed start, seed end, collect end, sa end
+	cudaEvent_t ev_done;
+	// pinned host
+	uint8_t *h_bases; uint32_t *h_off;
+	uint32_t *h_mem_off, *h_seed_off; cs_mem_t *h_mems; int64_t *h_rbeg;
+	Ctrl *h_ctrl;
+	// device
+	uint8_t *d_bases; uint32_t *d_off;
+	Ctrl *d_ctrl;
+	cs_mem_t *d_thread_mems; uint4 *d_spill;
+	cs_mem_t *d_pool, *d_mems;
+	uint64_t *d_read_pool_off;
+	uint32_t *d_read_n_mems, *d_mem_off, *d_read_n_seeds, *d_seed_off;
+	uint64_t *d_rows;
+	void *d_scan_tmp; size_t scan_tmp_bytes;
+	// state
+	int state;           // 0 idle, 1 staged, 2 running, 3 done (results on device)
+	uint32_t n_reads;
+	cs_seed_opt_t opt;
+};
+
+struct cs_ctx {
+	const cs_index *idx;
+	uint32_t max_reads, max_read_len;
+	uint64_t max_bases, max_mems, max_seeds;
+	int n_slots;
+	int grid;             // CTAs of k_seed
+	uint32_t mem_cap, spill_cap;
+	Slot *slots;
+};
+
+static void slot_free(Slot *s)
+{
+	if (s->stream) cudaStreamDestroy(s->stream);
+	for (int i = 0; i < 5; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+	if (s->ev_done) cudaEventDestroy(s->ev_done);
+	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
+	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
+	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
+	cudaFree(s->d_pool); cudaFree(s->d_mems); cudaFree(s->d_read_pool_off); cudaFree(s->d_read_n_mems);
+	cudaFree(s->d_mem_off); cudaFree(s->d_read_n_seeds); cudaFree(s->d_seed_off); cudaFree(s->d_rows); cudaFree(s->d_scan_tmp);
+}
+
+extern "C" void cs_ctx_free(cs_ctx_t *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->idx->device);
+	for (int i = 0; i < ctx->n_slots; ++i) slot_free(&ctx->slots[i]);
+	free(ctx->slots); free(ctx);
+}
+
+extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, uint64_t max_bases, uint32_t max_read_len,
+                                   uint64_t max_mems, uint64_t max_seeds, int n_slots)
+{
+	cs_ctx *ctx = nullptr;
+	if (!idx) { set_err(CS_E_ARG, "null index"); return nullptr; }
+	if (max_reads == 0 || max_bases == 0 || max_read_len == 0 || max_read_len > 65535 || n_slots < 1 || n_slots > 16 ||
+	    max_bases >= (1ull << 32)) {
+		set_err(CS_E_ARG, "bad ctx geometry (reads %u, bases %llu, read_len %u (<= 65535, comp_seed.h:39), slots %d)",
+		        max_reads, (unsigned long long)max_bases, max_read_len, n_slots);
+		return nullptr;
+	}
+	if (use_device(idx->device) != CS_OK) return nullptr;
+	ctx = (cs_ctx*)calloc(1, sizeof(cs_ctx));
+	ctx->idx = idx; ctx->max_reads = max_reads; ctx->max_bases = max_bases; ctx->max_read_len = max_read_len;
+	ctx->max_mems = max_mems ? max_mems : (uint64_t)max_reads * 16;
+	ctx->max_seeds = max_seeds ? max_seeds : (uint64_t)max_reads * 32;
+	if (ctx->max_mems >= (1ull << 32) || ctx->max_seeds >= (1ull << 32)) { set_err(CS_E_ARG, "result capacities must be < 2^32 per slot"); free(ctx); return nullptr; }
+	ctx->n_slots = n_slots;
+	ctx->slots = (Slot*)calloc(n_slots, sizeof(Slot));
+	{
+		const size_t smem = (size_t)CS_LIST_SMEM * CS_SEED_BLOCK * sizeof(uint4);
+		int per_sm = 0;
+		CK(cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed, CS_SEED_BLOCK, smem));
+		if (per_sm < 1) { set_err(CS_E_CUDA, "k_seed does not fit on an SM"); goto fail; }
+		ctx->grid = idx->n_sm * per_sm;
+		uint32_t need = (max_reads + CS_SEED_BLOCK - 1) / CS_SEED_BLOCK;
+		if ((uint32_t)ctx->grid > need) ctx->grid = (int)need;
+	}
+	ctx->mem_cap = std::min<uint32_t>(2 * max_read_len + 16, 4096);
+	ctx->spill_cap = max_read_len > CS_LIST_SMEM ? max_read_len - CS_LIST_SMEM + 1 : 1;
+	for (int i = 0; i < n_slots; ++i) {
+		Slot *s = &ctx->slots[i];
+		const size_t nthreads = (size_t)ctx->grid * CS_SEED_BLOCK;
+		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+		for (int e = 0; e < 5; ++e) CK(cudaEventCreate(&s->ev[e]));
+		CK(cudaEventCreate(&s->ev_done));
+		CK(cudaMallocHost(&s->h_bases, max_bases));
+		CK(cudaMallocHost(&s->h_off, ((size_t)max_reads + 1) * 4));
+		CK(cudaMallocHost(&s->h_mem_off, ((size_t)max_reads + 1) * 4));
+		CK(cudaMallocHost(&s->h_seed_off, ((size_t)max_reads + 1) * 4));
+		CK(cudaMallocHost(&s->h_mems, ctx->max_mems * sizeof(cs_mem_t)));
+		CK(cudaMallocHost(&s->h_rbeg, ctx->max_seeds * 8));
+		CK(cudaMallocHost(&s->h_ctrl, sizeof(Ctrl)));
+		CK(cudaMalloc(&s->d_bases, max_bases));
+		CK(cudaMalloc(&s->d_off, ((size_t)max_reads + 1) * 4));
+		CK(cudaMalloc(&s->d_ctrl, sizeof(Ctrl)));
+		CK(cudaMalloc(&s->d_thread_mems, nthreads * ctx->mem_cap * sizeof(cs_mem_t)));
+		CK(cudaMalloc(&s->d_spill, nthreads * ctx->spill_cap * sizeof(uint4)));
+		CK(cudaMalloc(&s->d_pool, ctx->max_mems * sizeof(cs_mem_t)));
+		CK(cudaMalloc(&s->d_mems, ctx->max_mems * sizeof(cs_mem_t)));
+		CK(cudaMalloc(&s->d_read_pool_off, (size_t)max_reads * 8));
+		CK(cudaMalloc(&s->d_read_n_mems, ((size_t)max_reads + 1) * 4));
+		CK(cudaMalloc(&s->d_mem_off, ((size_t)max_reads + 1) * 4));
+		CK(cudaMalloc(&s->d_read_n_seeds, ((size_t)max_reads + 1) * 4));
+		CK(cudaMalloc(&s->d_seed_off, ((size_t)max_reads + 1) * 4));
+		CK(cudaMalloc(&s->d_rows, ctx->max_seeds * 8));
+		s->scan_tmp_bytes = 0;
+		CK(cub::DeviceScan::ExclusiveSum(nullptr, s->scan_tmp_bytes, s->d_read_n_mems, s->d_mem_off, (int)max_reads + 1, s->stream));
+		CK(cudaMalloc(&s->d_scan_tmp, s->scan_tmp_bytes + 256));
+	}
+	return ctx;
+fail:
+	cs_ctx_free(ctx);
+	return nullptr;
+}
+
+static int check_slot(cs_ctx *ctx, int slot)
+{
+	if (!ctx) return set_err(CS_E_ARG, "null ctx");
+	if (slot < 0 || slot >= ctx->n_slots) return set_err(CS_E_ARG, "slot %d out of range (%d slots)", slot, ctx->n_slots);
+	return CS_OK;
+}
+
+// enqueue everything that runs on the device for one batch whose inputs are already in d_bases/d_off
+static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt)
+{
+	const cs_index *idx = ctx->idx;
+	const uint32_t n = s->n_reads;
+	const size_t smem = (size_t)CS_LIST_SMEM * CS_SEED_BLOCK * sizeof(uint4);
+	int grid = std::min<int>(ctx->grid, (int)((n + CS_SEED_BLOCK - 1) / CS_SEED_BLOCK));
+	if (grid < 1) grid = 1;
+	SeedArgs a;
+	CollectArgs c;
+	s->opt = *opt;
+	CK(cudaMemsetAsync(s->d_ctrl, 0, sizeof(Ctrl), s->stream));
+	CK(cudaEventRecord(s->ev[1], s->stream));
+	a.bases = s->d_bases; a.off = s->d_off; a.n_reads = n; a.opt = *opt;
+	a.next_read = &s->d_ctrl->next_read;
+	a.thread_mems = s->d_thread_mems; a.mem_cap = ctx->mem_cap;
+	a.spill = s->d_spill; a.spill_cap = ctx->spill_cap;
+	a.pool = s->d_pool; a.pool_cap = ctx->max_mems; a.pool_used = &s->d_ctrl->pool_used;
+	a.read_pool_off = s->d_read_pool_off; a.read_n_mems = s->d_read_n_mems;
+	a.counters = s->d_ctrl->counters; a.error = &s->d_ctrl->error;
+	// the spill stride must match the launched grid
+	k_seed<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(s->ev[2], s->stream));
+	// collect: offsets, sort, SA rows
+	CK(cudaMemsetAsync(s->d_read_n_mems + n, 0, 4, s->stream));
+	CK(cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, s->scan_tmp_bytes, s->d_read_n_mems, s->d_mem_off, (int)n + 1, s->stream));
+	c.n_reads = n; c.opt = *opt; c.pool = s->d_pool; c.read_pool_off = s->d_read_pool_off; c.read_n_mems = s->d_read_n_mems;
+	c.mem_off = s->d_mem_off; c.mems = s->d_mems; c.read_n_seeds = s->d_read_n_seeds; c.seed_off = s->d_seed_off;
+	c.seed_rows = s->d_rows; c.seed_cap = ctx->max_seeds; c.error = &s->d_ctrl->error;
+	{
+		int cgrid = (int)std::min<uint64_t>(((uint64_t)n * 32 + 255) / 256, (uint64_t)idx->n_sm * 16);
+		k_collect_sort<<<cgrid, 256, 0, s->stream>>>(c);
+		CK(cudaGetLastError());
+		CK(cudaMemsetAsync(s->d_read_n_seeds + n, 0, 4, s->stream));
+		CK(cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, s->scan_tmp_bytes, s->d_read_n_seeds, s->d_seed_off, (int)n + 1, s->stream));
+		k_collect_rows<<<cgrid, 256, 0, s->stream>>>(c);
+		CK(cudaGetLastError());
+	}
+	CK(cudaMemcpyAsync(&s->d_ctrl->n_mems, s->d_mem_off + n, 4, cudaMemcpyDeviceToDevice, s->stream));
+	CK(cudaMemcpyAsync(&s->d_ctrl->n_seeds, s->d_seed_off + n, 4, cudaMemcpyDeviceToDevice, s->stream));
+	CK(cudaEventRecord(s->ev[3], s->stream));
+	// SA resolution: the kernel reads n_seeds from ctrl on the device, so nothing waits for the host
+	k_sa_resolve<<<idx->n_sm * 8, 256, 0, s->stream>>>(idx->d, &s->d_ctrl->n_seeds, ctx->max_seeds, s->d_rows,
+	                                                    &s->d_ctrl->sa_work, &s->d_ctrl->lf_steps);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(s->ev[4], s->stream));
+	CK(cudaMemcpyAsync(s->h_ctrl, s->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+	s->state = 2;
+	return CS_OK;
+fail:
+	return CS_E_CUDA;
+}
+
+// wait for the device side of a run and check its status
+static int finish_run(cs_ctx *ctx, Slot *s)
+{
+	CK(cudaStreamSynchronize(s->stream));
+	s->state = 3;
+	if (s->h_ctrl->error != 0 || s->h_ctrl->pool_used > ctx->max_mems || s->h_ctrl->n_seeds > ctx->max_seeds)
+		return set_err(CS_E_OVERFLOW, "result buffers too small for this batch: mems %llu of %llu, seeds %llu of %llu "
+		               "(or a read needed more than %u mems / %u list entries); re-create the ctx with larger max_mems/max_seeds",
+		               (unsigned long long)s->h_ctrl->pool_used, (unsigned long long)ctx->max_mems,
+		               (unsigned long long)s->h_ctrl->n_seeds, (unsigned long long)ctx->max_seeds, ctx->mem_cap,
+		               ctx->spill_cap + CS_LIST_SMEM);
+	return CS_OK;
+fail:
+	return CS_E_CUDA;
+}
+
+static void fill_result(cs_ctx *ctx, Slot *s, cs_result_t *out, bool host_ptrs)
+{
+	memset(out, 0, sizeof *out);
+	out->n_reads = s->n_reads;
+	out->n_mems = s->h_ctrl->n_mems; out->n_seeds = s->h_ctrl->n_seeds;
+	out->counters.ext_queries = s->h_ctrl->counters[0];
+	out->counters.ext_calls = s->h_ctrl->counters[1];
+	out->counters.sal_queries = s->h_ctrl->n_seeds;
+	out->counters.sal_calls = s->h_ctrl->lf_steps;
+	if (host_ptrs) { out->mem_off = s->h_mem_off; out->mems = s->h_mems; out->seed_off = s->h_seed_off; out->rbeg = s->h_rbeg; }
+	cudaEventElapsedTime(&out->kernel_ms[0], s->ev[1], s->ev[2]);
+	cudaEventElapsedTime(&out->kernel_ms[1], s->ev[2], s->ev[3]);
+	cudaEventElapsedTime(&out->kernel_ms[2], s->ev[3], s->ev[4]);
+	cudaEventElapsedTime(&out->kernel_ms[3], s->ev[0], s->ev_done);
+	(void)ctx;
+}
+
+static int check_batch(cs_ctx *ctx, uint32_t n_reads, const uint32_t *offsets)
+{
+	if (n_reads == 0 || n_reads > ctx->max_reads) return set_err(CS_E_ARG, "n_reads %u outside [1, %u]", n_reads, ctx->max_reads);
+	if (offsets[0] != 0) return set_err(CS_E_ARG, "offsets[0] must be 0");
+	if (offsets[n_reads] > ctx->max_bases) return set_err(CS_E_ARG, "batch has %u bases, ctx sized for %llu", offsets[n_reads], (unsigned long long)ctx->max_bases);
+	for (uint32_t r = 0; r < n_reads; ++r) {
+		if (offsets[r + 1] < offsets[r]) return set_err(CS_E_ARG, "offsets not monotone at read %u", r);
+		if (offsets[r + 1] - offsets[r] > ctx->max_read_len)
+			return set_err(CS_E_ARG, "read %u has length %u > max_read_len %u", r, offsets[r + 1] - offsets[r], ctx->max_read_len);
+	}
+	return CS_OK;
+}
+
+extern "C" int cs_seed_batch_stage(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint8_t *bases, const uint32_t *offsets)
+{
+	int rc;
+	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
+	if (!bases || !offsets) return set_err(CS_E_ARG, "null argument");
+	if ((rc = check_batch(ctx, n_reads, offsets)) != CS_OK) return rc;
+	Slot *s = &ctx->slots[slot];
+	if (s->state == 2) return set_err(CS_E_STATE, "slot %d is busy", slot);
+	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	memcpy(s->h_bases, bases, offsets[n_reads]);
+	memcpy(s->h_off, offsets, ((size_t)n_reads + 1) * 4);
+	s->n_reads = n_reads;
+	CK(cudaEventRecord(s->ev[0], s->stream));
+	CK(cudaMemcpyAsync(s->d_bases, s->h_bases, offsets[n_reads], cudaMemcpyHostToDevice, s->stream));
+	CK(cudaMemcpyAsync(s->d_off, s->h_off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s->stream));
+	s->state = 1;
+	return CS_OK;
+fail:
+	return CS_E_CUDA;
+}
+
+static int check_opt(const cs_seed_opt_t *opt)
+{
+	if (!opt) return set_err(CS_E_ARG, "null options");
+	if (opt->min_seed_len < 1 || opt->max_occ < 1 || opt->max_mem_intv < 0 || opt->split_width < 0)
+		return set_err(CS_E_ARG, "bad seeding options (k %d, split_len %d, s %d, y %d, c %d)", opt->min_seed_len, opt->split_len,
+		               opt->split_width, opt->max_mem_intv, opt->max_occ);
+	return CS_OK;
+}
+
+extern "C" int cs_seed_batch_run_staged(cs_ctx_t *ctx, int slot, const cs_seed_opt_t *opt)
+{
+	int rc;
+	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
+	if ((rc = check_opt(opt)) != CS_OK) return rc;
+	Slot *s = &ctx->slots[slot];
+	if (s->state == 0) return set_err(CS_E_STATE, "slot %d has no staged batch", slot);
+	if (s->state == 2) return set_err(CS_E_STATE, "slot %d is busy", slot);
+	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	if (s->state == 3) cudaEventRecord(s->ev[0], s->stream);
+	return enqueue_run(ctx, s, opt);
+}
+
+extern "C" int cs_seed_batch_submit(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint8_t *bases, const uint32_t *offsets,
+                                    const cs_seed_opt_t *opt)
+{
+	int rc;
+	if ((rc = check_opt(opt)) != CS_OK) return rc;
+	if ((rc = cs_seed_batch_stage(ctx, slot, n_reads, bases, offsets)) != CS_OK) return rc;
+	return enqueue_run(ctx, &ctx->slots[slot], opt);
+}
+
+extern "C" int cs_seed_batch_wait_device(cs_ctx_t *ctx, int slot, cs_result_t *out)
+{
+	int rc;
+	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
+	if (!out) return set_err(CS_E_ARG, "null result");
+	Slot *s = &ctx->slots[slot];
+	if (s->state != 2) return set_err(CS_E_STATE, "slot %d has no batch in flight", slot);
+	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	rc = finish_run(ctx, s);
+	cudaEventRecord(s->ev_done, s->stream);
+	cudaEventSynchronize(s->ev_done);
+	if (rc != CS_OK) { s->state = 1; return rc; }
+	fill_result(ctx, s, out, false);
+	return CS_OK;
+}
+
+static int fetch(cs_ctx *ctx, Slot *s)
+{
+	const uint32_t n = s->n_reads;
+	CK(cudaMemcpyAsync(s->h_mem_off, s->d_mem_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaMemcpyAsync(s->h_seed_off, s->d_seed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+	if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(s->h_mems, s->d_mems, (size_t)s->h_ctrl->n_mems * sizeof(cs_mem_t), cudaMemcpyDeviceToHost, s->stream));
+	if (s->h_ctrl->n_seeds) CK(cudaMemcpyAsync(s->h_rbeg, s->d_rows, (size_t)s->h_ctrl->n_seeds * 8, cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaEventRecord(s->ev_done, s->stream));
+	CK(cudaEventSynchronize(s->ev_done));
+	(void)ctx;
+	return CS_OK;
+fail:
+	return CS_E_CUDA;
+}
+
+extern "C" int cs_seed_batch_fetch(cs_ctx_t *ctx, int slot, cs_result_t *out)
+{
+	int rc;
+	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
+	if (!out) return set_err(CS_E_ARG, "null result");
+	Slot *s = &ctx->slots[slot];
+	if (s->state != 3) return set_err(CS_E_STATE, "slot %d has no finished batch", slot);
+	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	if ((rc = fetch(ctx, s)) != CS_OK) return rc;
+	fill_result(ctx, s, out, true);
+	return CS_OK;
+}
+
+extern "C" int cs_seed_batch_wait(cs_ctx_t *ctx, int slot, cs_result_t *out)
+{
+	int rc;
+	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
+	if (!out) return set_err(CS_E_ARG, "null result");
+	Slot *s = &ctx->slots[slot];
+	if (s->state != 2) return set_err(CS_E_STATE, "slot %d has no batch in flight", slot);
+	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	if ((rc = finish_run(ctx, s)) != CS_OK) { s->state = 1; return rc; }
+	if ((rc = fetch(ctx, s)) != CS_OK) return rc;
+	fill_result(ctx, s, out, true);
+	return CS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// measurement helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int cs_probe_random_gather(int device, uint64_t table_bytes, uint32_t granule, uint64_t n_loads, int iters,
+                                      double *gbytes_per_s, double *gloads_per_s)
+{
+	uint4 *d_t = nullptr; unsigned long long *d_sink = nullptr;
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	float best = 1e30f;
+	if (granule != 16 && granule != 32 && granule != 64 && granule != 128) return set_err(CS_E_ARG, "granule must be 16, 32, 64 or 128");
+	if (use_device(device) != CS_OK) return CS_E_CUDA;
+	{
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, device));
+		uint64_t n16 = table_bytes / 16;
+		CK(cudaMalloc(&d_t, n16 * 16)); CK(cudaMalloc(&d_sink, 8));
+		CK(cudaMemset(d_sink, 0, 8));
+		k_fill<<<prop.multiProcessorCount * 8, 256>>>(d_t, n16, 7u);
+		CK(cudaGetLastError());
+		CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+		for (int it = 0; it < iters + 1; ++it) {
+			CK(cudaEventRecord(e0));
+			k_gather_probe<<<prop.multiProcessorCount * 8, 256>>>(d_t, table_bytes / granule, granule / 16, n_loads, 0x1234567ull + it, d_sink);
+			CK(cudaGetLastError());
+			CK(cudaEventRecord(e1));
+			CK(cudaEventSynchronize(e1));
+			float ms;
+			CK(cudaEventElapsedTime(&ms, e0, e1));
+			if (it > 0 && ms < best) best = ms;
+		}
+	}
+	if (gloads_per_s) *gloads_per_s = (double)n_loads / (best * 1e-3) * 1e-9;
+	if (gbytes_per_s) *gbytes_per_s = (double)n_loads * granule / (best * 1e-3) * 1e-9;
+	cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_t); cudaFree(d_sink);
+	return CS_OK;
+fail:
+	if (e0) cudaEventDestroy(e0);
+	if (e1) cudaEventDestroy(e1);
+	cudaFree(d_t); cudaFree(d_sink);
+	return CS_E_CUDA;
+}
+
+extern "C" int cs_flush_l2(int device)
+{
+	static uint4 *buf[16] = {nullptr};
+	const uint64_t bytes = 512ull << 20;
+	if (use_device(device) != CS_OK) return CS_E_CUDA;
+	if (device >= 16) return set_err(CS_E_ARG, "device index too large");
+	if (!buf[device]) CK(cudaMalloc(&buf[device], bytes));
+	k_fill<<<1024, 256>>>(buf[device], bytes / 16, 3u);
+	CK(cudaGetLastError());
+	CK(cudaDeviceSynchronize());
+	return CS_OK;
+fail:
+	return CS_E_CUDA;
+}

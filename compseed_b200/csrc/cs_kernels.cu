@@ -1,0 +1,455 @@
+// Hand-written sm_100a kernels of the SMEM seeding path.  See DESIGN.md for the layout, the
+// per-kernel roofline and the mapping to the reference (FM_index/bwt.c, mapping/bwamem.c:218-272,
+// mapping/comp_seed.cpp:67-160,2255-2346).
+#include "cs_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Index re-layout: reference 64-byte buckets (4 x u64 checkpoint + 8 x u32, 16 bases per word,
+// base i at bits (15-i)*2; index_main.c:152-174) -> 32-byte device buckets (cs_device.cuh).
+// One thread per device bucket.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t msb_to_lsb16(uint32_t w)
+{ // reverse the order of the sixteen 2-bit fields
+	uint32_t v = __brev(w);
+	return ((v & 0x55555555u) << 1) | ((v >> 1) & 0x55555555u);
+}
+
+__global__ void k_relayout(const uint32_t *src, uint64_t src_words, uint64_t seq_len, uint4 *dst, uint64_t n_buckets)
+{
+	for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < n_buckets; b += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t B = b >> 1, base = B << 4;       // source bucket, its first word
+		uint32_t half = (uint32_t)b & 1;
+		uint64_t cnt[4] = {0, 0, 0, 0};
+		uint32_t w[8];
+		if (b << 6 < seq_len) {
+			const uint64_t *cp = reinterpret_cast<const uint64_t*>(src + base);
+			cnt[0] = cp[0]; cnt[1] = cp[1]; cnt[2] = cp[2]; cnt[3] = cp[3];
+		}
+		for (int j = 0; j < 8; ++j) {
+			uint64_t row = (B << 7) + 16 * j, idx = base + 8 + j;
+			w[j] = (row < seq_len && idx < src_words) ? src[idx] : 0u;
+		}
+		if (half) { // add the first 64 rows of the source bucket to the checkpoint
+			for (int j = 0; j < 4; ++j)
+				for (int i = 0; i < 16; ++i) {
+					uint64_t row = (B << 7) + 16 * j + i;
+					if (row < seq_len) ++cnt[(w[j] >> ((15 - i) << 1)) & 3];
+				}
+		}
+		const uint32_t *ws = w + 4 * half;
+		uint64_t w0 = (uint64_t)msb_to_lsb16(ws[0]) | ((uint64_t)msb_to_lsb16(ws[1]) << 32);
+		uint64_t w1 = (uint64_t)msb_to_lsb16(ws[2]) | ((uint64_t)msb_to_lsb16(ws[3]) << 32);
+		uint4 lo, hi;
+		lo.x = (uint32_t)w0; lo.y = (uint32_t)(w0 >> 32); lo.z = (uint32_t)w1; lo.w = (uint32_t)(w1 >> 32);
+		hi.x = (uint32_t)cnt[0]; hi.y = (uint32_t)cnt[1]; hi.z = (uint32_t)cnt[2];
+		hi.w = ((uint32_t)(cnt[0] >> 32) & 0xff) | (((uint32_t)(cnt[1] >> 32) & 0xff) << 8) | (((uint32_t)(cnt[2] >> 32) & 0xff) << 16);
+		dst[2 * b] = lo; dst[2 * b + 1] = hi;
+	}
+}
+
+// Inverse of k_relayout: rebuild the reference layout (for cs_index_download).  One thread per
+// reference bucket (128 rows); the trailing checkpoint-only record is written by the last thread.
+__global__ void k_unlayout(const uint4 *src, uint64_t seq_len, uint32_t *dst, uint64_t dst_words)
+{
+	uint64_t n_ref = (seq_len + 127) >> 7;
+	for (uint64_t B = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; B <= n_ref; B += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t row0 = B << 7;
+		// checkpoint at row0: from device bucket 2B if it exists, else from the last bucket's totals
+		uint64_t cnt[4];
+		uint64_t b = row0 >> 6;
+		uint64_t nb = (seq_len + 63) >> 6;
+		if (b < nb) {
+			uint4 h = src[2 * b + 1];
+			cnt[0] = (uint64_t)h.x | ((uint64_t)(h.w & 0xff) << 32);
+			cnt[1] = (uint64_t)h.y | ((uint64_t)((h.w >> 8) & 0xff) << 32);
+			cnt[2] = (uint64_t)h.z | ((uint64_t)((h.w >> 16) & 0xff) << 32);
+			cnt[3] = row0 - cnt[0] - cnt[1] - cnt[2];
+		} else { // row0 >= seq_len: totals = checkpoint of the last bucket + its bases
+			uint64_t lb = nb - 1;
+			uint4 l = src[2 * lb], h = src[2 * lb + 1];
+			cnt[0] = (uint64_t)h.x | ((uint64_t)(h.w & 0xff) << 32);
+			cnt[1] = (uint64_t)h.y | ((uint64_t)((h.w >> 8) & 0xff) << 32);
+			cnt[2] = (uint64_t)h.z | ((uint64_t)((h.w >> 16) & 0xff) << 32);
+			cnt[3] = (lb << 6) - cnt[0] - cnt[1] - cnt[2];
+			uint64_t w0 = (uint64_t)l.x | ((uint64_t)l.y << 32), w1 = (uint64_t)l.z | ((uint64_t)l.w << 32);
+			for (uint64_t r = lb << 6; r < seq_len; ++r) {
+				uint32_t i = (uint32_t)(r & 63);
+				++cnt[((i < 32 ? w0 : w1) >> (2 * (i & 31))) & 3];
+			}
+		}
+		// position of this record in the reference array: 16 words per full bucket
+		uint64_t base = B << 4;
+		if (B == n_ref) { // trailing record sits right after the last BWT word (index_main.c:171)
+			base = ((n_ref - (n_ref > 0)) << 4);
+			if (n_ref > 0) base += 8 + (((seq_len - ((n_ref - 1) << 7)) + 15) >> 4);
+		}
+		if (base + 8 <= dst_words) {
+			uint64_t *cp = reinterpret_cast<uint64_t*>(dst + base);
+			cp[0] = cnt[0]; cp[1] = cnt[1]; cp[2] = cnt[2]; cp[3] = cnt[3];
+		}
+		if (B < n_ref) {
+			for (int j = 0; j < 8; ++j) {
+				uint64_t row = row0 + 16 * j;
+				if (row >= seq_len) break;
+				uint64_t bb = row >> 6;
+				uint4 l = src[2 * bb];
+				uint32_t q = (uint32_t)(row & 63) >> 4;   // which 16-base quarter of the device bucket
+				uint32_t v = q == 0 ? l.x : q == 1 ? l.y : q == 2 ? l.z : l.w;
+				uint32_t r = ((v & 0x55555555u) << 1) | ((v >> 1) & 0x55555555u);
+				dst[base + 8 + j] = __brev(r);
+			}
+		}
+	}
+}
+
+// Re-sample the suffix array at a denser (or sparser) interval: out[r >> out_shift] = bwt_sa(r).
+__global__ void k_resample_sa(DevIndex I, uint64_t *out, uint64_t n_out, uint32_t out_shift)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_out; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t steps;
+		out[i] = i == 0 ? (uint64_t)-1 : dev_sa(I, i << out_shift, steps);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Unit-level probes (bwt_occ4 / bwt_extend twins)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_probe_occ4(DevIndex I, uint32_t n, const uint64_t *k, uint64_t *cnt)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint64_t c[4] = {0, 0, 0, 0};
+	if (k[i] != (uint64_t)-1) dev_occ4(I, k[i], c);
+	for (int j = 0; j < 4; ++j) cnt[4 * (size_t)i + j] = c[j];
+}
+
+__global__ void k_probe_extend(DevIndex I, uint32_t n, const uint64_t *ik, const int32_t *is_back, uint64_t *ok)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint64_t in[3] = { ik[3 * (size_t)i], ik[3 * (size_t)i + 1], ik[3 * (size_t)i + 2] };
+	uint64_t out4[12];
+	dev_extend4(I, in, is_back[i] != 0, out4);
+	// cross-check the single-child path used by the seeding kernel against the 4-child path
+	if (in[(is_back[i] != 0) ? 0 : 1] >= 1 && in[2] > 0) {
+		for (int c = 0; c < 4; ++c) {
+			uint64_t o0, o1, o2; uint32_t two;
+			dev_extend(I, in[0], in[1], in[2], c, is_back[i] != 0, o0, o1, o2, two);
+			if (o0 != out4[c * 3] || o1 != out4[c * 3 + 1] || o2 != out4[c * 3 + 2]) out4[c * 3 + 2] = ~0ull; // poison
+		}
+	}
+	for (int j = 0; j < 12; ++j) ok[12 * (size_t)i + j] = out4[j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// SA resolution: rows_inout[i] = bwt_sa(rows_inout[i]).  LF walks have a geometric length
+// distribution (mean 31, max 396+ at sa_intv 32), so lanes refill from a global
+// work counter as soon as their own walk ends instead of waiting for the slowest lane.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, uint64_t *rows_inout, unsigned long long *work,
+                             unsigned long long *lf_steps)
+{
+	unsigned long long steps_total = 0;
+	uint64_t n = *n_ptr;           // produced on the device by the collect pass: no host round trip
+	if (n > cap) return;           // overflow is reported by the collect pass
+	if (I.sa_mask == 0) { // dense suffix array: one 8-byte gather per seed
+		for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+			rows_inout[i] = __ldg(I.sa + rows_inout[i]);
+		return;
+	}
+	for (;;) {
+		unsigned long long i = atomicAdd(work, 1ull);
+		if (i >= n) break;
+		uint32_t steps;
+		rows_inout[i] = dev_sa(I, rows_inout[i], steps);
+		steps_total += steps;
+	}
+	if (steps_total) atomicAdd(lf_steps, steps_total);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The seeding kernel.
+//
+// One read per THREAD, persistent threads, reads handed out in input order by an atomic counter
+// (neighbouring reordered reads run at the same time on neighbouring threads, so the sectors they
+// share are hit in L1/L2).  Every thread runs the three-round algorithm as an explicit state
+// machine whose only expensive step -- one bwt_extend == one or two 32-byte sector gathers -- is
+// executed convergently by the whole warp once per trip of the outer loop; the cheap, divergent
+// bookkeeping (list pushes, mem emission, pivot selection) happens in between.  With ~100k
+// threads resident this keeps ~100-200k independent random sector reads in flight, which is what
+// a latency-bound dependent-gather workload needs (hard part 3).
+//
+// Interval lists (bwt_smem1a's prev/curr, FM_index/bwt.c:293-344) are a single in-place stack of
+// packed 16-byte entries: the first CS_LIST_SMEM per thread in shared memory (bank-conflict-free
+// [entry][thread] layout), the rest spilled to HBM.
+// ---------------------------------------------------------------------------------------------
+enum { ST_FETCH = 0, ST_R1_PIVOT, ST_FWD, ST_BWD_INIT, ST_BWD_SWEEP, ST_BWD_ENTRY, ST_CALL_DONE, ST_R2_NEXT,
+       ST_R3_PIVOT, ST_R3_FWD, ST_READ_DONE };
+
+__global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs a)
+{
+	extern __shared__ uint4 s_list[];
+	const int t = threadIdx.x;
+	const size_t nthreads = (size_t)gridDim.x * CS_SEED_BLOCK;
+	const size_t gtid = (size_t)blockIdx.x * CS_SEED_BLOCK + t;
+	cs_mem_t *my = a.thread_mems + gtid * a.mem_cap;
+	const cs_seed_opt_t opt = a.opt;
+
+	unsigned long long n_ext = 0, n_call = 0, n_two = 0;
+	int st = ST_FETCH;
+	uint32_t rd = 0; int len = 0;
+	const uint8_t *q = nullptr;
+	uint32_t nmem = 0, old_n = 0, r2k = 0;
+	int round = 1;
+	int x = 0, i = 0, bi = 0, ret = 0;
+	uint64_t c0 = 0, c1 = 0, c2 = 0; uint32_t cend = 0;   // current interval (forward ik / backward p)
+	int n = 0, lo = 0, j = 0, w = 0;
+	bool pushed = false; uint64_t last_sz = 0;
+	uint64_t min_intv = 1;
+	uint32_t call_nmem = 0; int last_start = 0;
+	int c = 0, is_back = 0;
+	bool err_list = false, err_mem = false;
+
+	auto list_put = [&](int idx, uint4 v) {
+		if (idx < CS_LIST_SMEM) s_list[idx * CS_SEED_BLOCK + t] = v;
+		else if ((uint32_t)(idx - CS_LIST_SMEM) < a.spill_cap) a.spill[(size_t)(idx - CS_LIST_SMEM) * nthreads + gtid] = v;
+		else err_list = true;
+	};
+	auto list_get = [&](int idx) -> uint4 {
+		if (idx < CS_LIST_SMEM) return s_list[idx * CS_SEED_BLOCK + t];
+		if ((uint32_t)(idx - CS_LIST_SMEM) < a.spill_cap) return a.spill[(size_t)(idx - CS_LIST_SMEM) * nthreads + gtid];
+		return make_uint4(0, 0, 0, 0);
+	};
+	auto emit = [&](uint64_t x0, uint64_t x1, uint64_t x2, uint32_t start, uint32_t end) {
+		if (nmem < a.mem_cap) {
+			uint4 *p = reinterpret_cast<uint4*>(my + nmem);
+			p[0] = make_uint4((uint32_t)x0, (uint32_t)(x0 >> 32), (uint32_t)x1, (uint32_t)(x1 >> 32));
+			p[1] = make_uint4((uint32_t)x2, (uint32_t)(x2 >> 32), end, start);
+		} else err_mem = true;
+		++nmem;
+	};
+	auto start_call = [&](int pivot, uint64_t mi) { // bwt_smem1a prologue, bwt.c:295-302
+		x = pivot; min_intv = mi < 1 ? 1 : mi;
+		int b = q[x];
+		c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
+		i = x + 1; n = 0; call_nmem = 0;
+		st = ST_FWD;
+	};
+
+	for (;;) {
+		bool need = false;
+		while (!need) {
+			switch (st) {
+			case ST_FETCH: {
+				rd = atomicAdd(a.next_read, 1u);
+				if (rd >= a.n_reads) {
+					if (n_ext) atomicAdd(a.counters + 0, n_ext);
+					if (n_call) atomicAdd(a.counters + 1, n_call);
+					if (n_two) atomicAdd(a.counters + 2, n_two);
+					return;
+				}
+				uint32_t o = a.off[rd];
+				q = a.bases + o; len = (int)(a.off[rd + 1] - o);
+				nmem = 0; round = 1; x = 0; err_list = err_mem = false;
+				st = ST_R1_PIVOT;
+			} break;
+			case ST_R1_PIVOT: // first pass of mem_collect_intv, bwamem.c:226-236
+				while (x < len && q[x] > 3) ++x;
+				if (x >= len) { old_n = nmem; r2k = 0; st = ST_R2_NEXT; }
+				else start_call(x, 1);
+				break;
+			case ST_FWD: // forward extension, bwt.c:304-321
+				if (i >= len || q[i] > 3) { list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i)); st = ST_BWD_INIT; }
+				else { c = 3 - q[i]; is_back = 0; need = true; }
+				break;
+			case ST_BWD_INIT: // bwt.c:322-326; list[n-1] is the longest match
+				ret = (int)(list_get(n - 1).w >> 16);
+				bi = x - 1; lo = 0;
+				st = ST_BWD_SWEEP;
+				break;
+			case ST_BWD_SWEEP: { // one value of i in bwt.c:326
+				c = bi < 0 ? -1 : (q[bi] < 4 ? q[bi] : -1);
+				if (c < 0) { // every interval ends here; only the longest can be a new SMEM (bwt.c:331-337)
+					if (call_nmem == 0 || bi + 1 < last_start) {
+						unpack_entry(list_get(n - 1), c0, c1, c2, cend);
+						++call_nmem; last_start = bi + 1;
+						if ((int)cend - (bi + 1) >= opt.min_seed_len) emit(c0, c1, c2, (uint32_t)(bi + 1), cend);
+					}
+					st = ST_CALL_DONE;
+				} else { j = n - 1; w = n; pushed = false; st = ST_BWD_ENTRY; }
+			} break;
+			case ST_BWD_ENTRY:
+				if (j < lo) {
+					if (!pushed) st = ST_CALL_DONE;
+					else { lo = w; --bi; st = ST_BWD_SWEEP; }
+				} else { unpack_entry(list_get(j), c0, c1, c2, cend); is_back = 1; need = true; }
+				break;
+			case ST_CALL_DONE:
+				if (round == 1) { x = ret; st = ST_R1_PIVOT; } else st = ST_R2_NEXT;
+				break;
+			case ST_R2_NEXT: { // second pass, bwamem.c:238-249
+				st = opt.max_mem_intv > 0 ? ST_R3_PIVOT : ST_READ_DONE;
+				x = 0;
+				uint32_t lim = old_n < a.mem_cap ? old_n : a.mem_cap;
+				while (r2k < lim) {
+					const uint4 *p = reinterpret_cast<const uint4*>(my + r2k);
+					uint4 v = p[1];
+					++r2k;
+					int s = (int)v.w, e = (int)v.z;
+					uint64_t sz = (uint64_t)v.x | ((uint64_t)v.y << 32);
+					if (e - s < opt.split_len || sz > (uint64_t)opt.split_width) continue;
+					round = 2;
+					start_call((s + e) >> 1, sz + 1);
+					break;
+				}
+			} break;
+			case ST_R3_PIVOT: // third pass, bwamem.c:253-268 + bwt_seed_strategy1 prologue bwt.c:363-365
+				while (x < len && q[x] > 3) ++x;
+				if (x >= len) st = ST_READ_DONE;
+				else {
+					int b = q[x];
+					c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
+					i = x + 1;
+					st = ST_R3_FWD;
+				}
+				break;
+			case ST_R3_FWD: // bwt.c:366-378
+				if (i >= len) st = ST_READ_DONE;
+				else if (q[i] > 3) { x = i + 1; st = ST_R3_PIVOT; }
+				else if (c2 == 0) { // children of an empty interval are empty: no memory access needed
+					++n_ext;
+					if (i - x >= opt.min_seed_len) { x = i + 1; st = ST_R3_PIVOT; } else ++i;
+				} else { c = 3 - q[i]; is_back = 0; need = true; }
+				break;
+			case ST_READ_DONE: {
+				uint32_t cnt = nmem;
+				if (err_mem || err_list) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
+				unsigned long long o = atomicAdd(a.pool_used, (unsigned long long)cnt);
+				if (o + cnt > a.pool_cap) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
+				a.read_pool_off[rd] = o; a.read_n_mems[rd] = cnt;
+				const uint4 *src = reinterpret_cast<const uint4*>(my);
+				uint4 *dst = reinterpret_cast<uint4*>(a.pool + o);
+				for (uint32_t m = 0; m < 2 * cnt; ++m) dst[m] = src[m];
+				st = ST_FETCH;
+			} break;
+			}
+		}
+
+		// ---- the one convergent, memory-bound step: bwt_extend of (c0,c1,c2) by base c ----
+		uint64_t o0, o1, o2; uint32_t two;
+		dev_extend(I, c0, c1, c2, c, is_back, o0, o1, o2, two);
+		++n_ext; ++n_call; n_two += two;
+
+		if (st == ST_FWD) { // bwt.c:311-315
+			if (o2 != c2) {
+				list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i));
+				if (o2 < min_intv) { st = ST_BWD_INIT; continue; }
+			}
+			c0 = o0; c1 = o1; c2 = o2; ++i;
+		} else if (st == ST_BWD_ENTRY) { // bwt.c:331-341
+			if (o2 < min_intv) {
+				if (!pushed && (call_nmem == 0 || bi + 1 < last_start)) {
+					++call_nmem; last_start = bi + 1;
+					if ((int)cend - (bi + 1) >= opt.min_seed_len) emit(c0, c1, c2, (uint32_t)(bi + 1), cend);
+				}
+			} else if (!pushed || o2 != last_sz) {
+				list_put(--w, pack_entry(o0, o1, o2, cend));
+				pushed = true; last_sz = o2;
+			}
+			--j;
+		} else { // ST_R3_FWD, bwt.c:370-375
+			if (o2 < (uint64_t)opt.max_mem_intv && i - x >= opt.min_seed_len) {
+				if (o2 > 0) emit(o0, o1, o2, (uint32_t)x, (uint32_t)(i + 1));
+				x = i + 1; st = ST_R3_PIVOT;
+			} else { c0 = o0; c1 = o1; c2 = o2; ++i; }
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Collect: put each read's mems in input order, sorted by info (ks_introsort, bwamem.c:271;
+// std::sort, comp_seed.cpp:2301), and expand them to SA rows (bwamem.c:386-399).
+// One warp per read; rank sort (ties are bit-identical records, so their order is immaterial).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t seeds_of(uint64_t x2, int32_t max_occ)
+{ // number of iterations of "for (k = count = 0; k < x2 && count < max_occ; k += step, ++count)"
+	return x2 < (uint64_t)max_occ ? (uint32_t)x2 : (uint32_t)max_occ;
+}
+
+__global__ void k_collect_sort(CollectArgs a)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.n_reads; r += nwarps) {
+		const uint32_t n = a.read_n_mems[r];
+		const cs_mem_t *src = a.pool + a.read_pool_off[r];
+		cs_mem_t *dst = a.mems + a.mem_off[r];
+		uint32_t n_seeds = 0;
+		for (uint32_t m = lane; m < n; m += 32) {
+			const uint4 *p = reinterpret_cast<const uint4*>(src + m);
+			uint4 v0 = p[0], v1 = p[1];
+			uint64_t info = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
+			uint32_t rank = 0;
+			for (uint32_t o = 0; o < n; ++o) {
+				uint64_t oi = src[o].info;
+				rank += (oi < info) || (oi == info && o < m);
+			}
+			uint4 *d = reinterpret_cast<uint4*>(dst + rank);
+			d[0] = v0; d[1] = v1;
+			n_seeds += seeds_of((uint64_t)v1.x | ((uint64_t)v1.y << 32), a.opt.max_occ);
+		}
+		for (int s = 16; s > 0; s >>= 1) n_seeds += __shfl_xor_sync(0xffffffffu, n_seeds, s);
+		if (lane == 0) a.read_n_seeds[r] = n_seeds;
+	}
+}
+
+__global__ void k_collect_rows(CollectArgs a)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.n_reads; r += nwarps) {
+		const uint32_t n = a.mem_off[r + 1] - a.mem_off[r];
+		const cs_mem_t *mem = a.mems + a.mem_off[r];
+		uint64_t o = a.seed_off[r];
+		if ((uint64_t)a.seed_off[r + 1] > a.seed_cap) { if (lane == 0) atomicExch(a.error, CS_E_OVERFLOW); continue; }
+		for (uint32_t m = 0; m < n; ++m) {
+			uint64_t x0 = mem[m].x[0], x2 = mem[m].x[2];
+			uint32_t cnt = seeds_of(x2, a.opt.max_occ);
+			uint64_t step = x2 > (uint64_t)a.opt.max_occ ? x2 / (uint64_t)a.opt.max_occ : 1;
+			for (uint32_t k = lane; k < cnt; k += 32) a.seed_rows[o + k] = x0 + (uint64_t)k * step;
+			o += cnt;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Measurement helpers
+// ---------------------------------------------------------------------------------------------
+// Independent uniformly random granule-sized loads over a table: the random-sector roofline.
+__global__ void k_gather_probe(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed,
+                               unsigned long long *sink)
+{
+	uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint64_t s = seed ^ (tid * 0x9E3779B97F4A7C15ull);
+	uint32_t acc = 0;
+	for (uint64_t i = tid; i < n_loads; i += stride) {
+		s ^= s << 13; s ^= s >> 7; s ^= s << 17;            // xorshift64
+		uint64_t g = (uint64_t)(((unsigned __int128)s * n_granules) >> 64);
+		const uint4 *p = table + g * granule16;
+		if (granule16 == 2) {
+			uint64_t a, b, c, d;
+			asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+			acc += (uint32_t)(a ^ b ^ c ^ d);
+		} else {
+			for (uint32_t j = 0; j < granule16; ++j) { uint4 v = __ldg(p + j); acc += v.x ^ v.y ^ v.z ^ v.w; }
+		}
+	}
+	if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
+__global__ void k_fill(uint4 *p, uint64_t n, uint32_t v)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		p[i] = make_uint4(v, v + 1, v + 2, (uint32_t)i);
+}

@@ -1,0 +1,56 @@
+// Kernels of the seeding path (sm_100a).  Host-side launch code is in cs_api.cu.
+#pragma once
+#include "cs_device.cuh"
+#include "../../include/compseed_b200.h"
+
+#define CS_SEED_BLOCK   256     // threads per CTA of the seeding kernel
+#define CS_LIST_SMEM    16      // interval-list entries per thread kept in shared memory
+
+struct SeedArgs {
+	const uint8_t *bases;       // nt4 codes, concatenated
+	const uint32_t *off;        // n_reads + 1
+	uint32_t n_reads;
+	cs_seed_opt_t opt;
+	// scratch
+	uint32_t *next_read;        // work counter
+	cs_mem_t *thread_mems;      // [n_threads][mem_cap] per-thread mem list of the read in flight
+	uint32_t mem_cap;
+	uint4 *spill;               // [spill_cap][n_threads] interval-list entries beyond CS_LIST_SMEM
+	uint32_t spill_cap;
+	// outputs
+	cs_mem_t *pool;             // unsorted mems, reads in completion order
+	uint64_t pool_cap;
+	unsigned long long *pool_used;
+	uint64_t *read_pool_off;    // [n_reads] where the read's mems start in pool
+	uint32_t *read_n_mems;      // [n_reads]
+	unsigned long long *counters; // [0] ext queries [1] ext calls (bucket path) [2] two-sector extends
+	int *error;                 // sticky CS_E_* code
+};
+
+struct CollectArgs {
+	uint32_t n_reads;
+	cs_seed_opt_t opt;
+	const cs_mem_t *pool;
+	const uint64_t *read_pool_off;
+	const uint32_t *read_n_mems;
+	const uint32_t *mem_off;    // exclusive scan of read_n_mems, n_reads + 1
+	cs_mem_t *mems;             // sorted output
+	uint32_t *read_n_seeds;     // [n_reads]
+	const uint32_t *seed_off;   // exclusive scan of read_n_seeds (for pass 2)
+	uint64_t *seed_rows;        // [n_seeds] SA rows in emission order (pass 2), resolved in place by k_sa_resolve
+	uint64_t seed_cap;
+	int *error;
+};
+
+__global__ void k_relayout(const uint32_t *src, uint64_t src_words, uint64_t seq_len, uint4 *dst, uint64_t n_buckets);
+__global__ void k_unlayout(const uint4 *src, uint64_t seq_len, uint32_t *dst, uint64_t dst_words);
+__global__ void k_resample_sa(DevIndex I, uint64_t *out, uint64_t n_out, uint32_t out_shift);
+__global__ void k_probe_occ4(DevIndex I, uint32_t n, const uint64_t *k, uint64_t *cnt);
+__global__ void k_probe_extend(DevIndex I, uint32_t n, const uint64_t *ik, const int32_t *is_back, uint64_t *ok);
+__global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, uint64_t *rows_inout, unsigned long long *work,
+                             unsigned long long *lf_steps);
+__global__ void k_seed(DevIndex I, SeedArgs a);
+__global__ void k_collect_sort(CollectArgs a);
+__global__ void k_collect_rows(CollectArgs a);
+__global__ void k_gather_probe(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed, unsigned long long *sink);
+__global__ void k_fill(uint4 *p, uint64_t n, uint32_t v);

@@ -1,0 +1,384 @@
+"""Host-side mirror of the reference's seeding interface, bound to the C-ABI in
+include/compseed_b200.h through ctypes.
+
+Names follow the reference: an FM-index (`bwt_t`, FM_index/bwt.h:48-60) with `occ4` / `extend` /
+`sa` queries (bwt_occ4 / bwt_extend / bwt_sa), seeding options that are the -k/-r/-s/-y/-c fields
+of `mem_opt_t` (mapping/comp_seed.h:41-73), and a batch call that returns, per read, the sorted mems
+(`aux.match[r]`, comp_seed.cpp:2261-2301 == `aux->mem`, bwamem.c:218-272) and the resolved seed
+positions in emission order (comp_seed.cpp:2306-2346 == bwamem.c:386-399).
+
+There is NO CPU fallback: if libcompseed_b200.so is missing or no CUDA device is visible, every
+call raises.  PyTorch is not used here at all; numpy arrays are the host buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import synth
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libcompseed_b200.so")
+
+CS_OK, CS_E_ARG, CS_E_CUDA, CS_E_OVERFLOW, CS_E_IO, CS_E_NODEVICE, CS_E_STATE = 0, -1, -2, -3, -4, -5, -6
+
+
+class CompSeedError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"compseed_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _BwtView(C.Structure):
+    _fields_ = [("primary", C.c_uint64), ("L2", C.c_uint64 * 5), ("seq_len", C.c_uint64), ("bwt_size", C.c_uint64),
+                ("bwt", C.c_void_p), ("sa_intv", C.c_int32), ("n_sa", C.c_uint64), ("sa", C.c_void_p)]
+
+
+class _SeedOpt(C.Structure):
+    _fields_ = [("min_seed_len", C.c_int32), ("split_len", C.c_int32), ("split_width", C.c_int32),
+                ("max_mem_intv", C.c_int32), ("max_occ", C.c_int32)]
+
+
+class _Counters(C.Structure):
+    _fields_ = [("ext_queries", C.c_uint64), ("ext_calls", C.c_uint64), ("sal_queries", C.c_uint64), ("sal_calls", C.c_uint64)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_mems", C.c_uint64), ("n_seeds", C.c_uint64),
+                ("mem_off", C.POINTER(C.c_uint32)), ("mems", C.POINTER(C.c_uint64)),
+                ("seed_off", C.POINTER(C.c_uint32)), ("rbeg", C.POINTER(C.c_int64)),
+                ("counters", _Counters), ("kernel_ms", C.c_float * 4)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library.  Fails loudly: there is no other implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m compseed_b200.build` "
+                           "(nvcc, sm_100a).  compseed_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.cs_last_error.restype = C.c_char_p
+    L.cs_device_count.restype = C.c_int
+    L.cs_index_upload.restype = C.c_void_p
+    L.cs_index_upload.argtypes = [C.POINTER(_BwtView), C.c_int, C.c_int]
+    L.cs_index_load.restype = C.c_void_p
+    L.cs_index_load.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    L.cs_index_build.restype = C.c_void_p
+    L.cs_index_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+    L.cs_index_download.argtypes = [C.c_void_p, C.POINTER(_BwtView), C.c_void_p, C.c_void_p, C.c_int]
+    L.cs_index_info.argtypes = [C.c_void_p, C.POINTER(_BwtView), C.POINTER(C.c_uint64)]
+    L.cs_index_free.argtypes = [C.c_void_p]
+    L.cs_occ4.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.cs_extend.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cs_sa.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.cs_ctx_create.restype = C.c_void_p
+    L.cs_ctx_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int]
+    L.cs_ctx_free.argtypes = [C.c_void_p]
+    L.cs_seed_batch_submit.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(_SeedOpt)]
+    L.cs_seed_batch_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Result)]
+    L.cs_seed_batch_stage.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.cs_seed_batch_run_staged.argtypes = [C.c_void_p, C.c_int, C.POINTER(_SeedOpt)]
+    L.cs_seed_batch_wait_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Result)]
+    L.cs_seed_batch_fetch.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Result)]
+    L.cs_probe_random_gather.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.cs_flush_l2.argtypes = [C.c_int]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != CS_OK:
+        raise CompSeedError(rc, load_library().cs_last_error().decode())
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count() -> int:
+    return load_library().cs_device_count()
+
+
+@dataclass
+class SeedOpt:
+    """-k / -r / -s / -y / -c of mem_opt_t with the defaults of mem_opt_init (comp_seed.cpp:26-61)."""
+    min_seed_len: int = 19
+    split_factor: float = 1.5
+    split_width: int = 10
+    max_mem_intv: int = 20
+    max_occ: int = 500
+    caller: str = "bwamem"   # whose rounding of split_len to reproduce: "bwamem" (bwamem.c:223) or "compseed" (comp_seed.cpp:2279)
+
+    @property
+    def split_len(self) -> int:
+        f = synth.split_len_bwamem if self.caller == "bwamem" else synth.split_len_compseed
+        return f(self.min_seed_len, self.split_factor)
+
+    def _c(self) -> _SeedOpt:
+        return _SeedOpt(self.min_seed_len, self.split_len, self.split_width, self.max_mem_intv, self.max_occ)
+
+
+@dataclass
+class SeedResult:
+    mem_off: np.ndarray      # u32 [n+1]
+    mems: np.ndarray         # u64 [n_mems, 4]: x0 (k), x1 (l), x2 (s), info = start << 32 | end
+    seed_off: np.ndarray     # u32 [n+1]
+    rbeg: np.ndarray         # i64 [n_seeds]
+    counters: dict = field(default_factory=dict)
+    kernel_ms: tuple = (0.0, 0.0, 0.0, 0.0)
+
+    @property
+    def n_reads(self) -> int:
+        return self.mem_off.shape[0] - 1
+
+
+class FMIndex:
+    """GPU-resident FM-index (device twin of bwt_t)."""
+
+    def __init__(self, handle, device: int):
+        if not handle:
+            raise CompSeedError(CS_E_CUDA, load_library().cs_last_error().decode())
+        self.h = C.c_void_p(handle)
+        self.device = device
+        v = _BwtView()
+        nbytes = C.c_uint64()
+        _check(load_library().cs_index_info(self.h, C.byref(v), C.byref(nbytes)))
+        self.primary, self.seq_len, self.bwt_size = int(v.primary), int(v.seq_len), int(v.bwt_size)
+        self.L2 = np.array(list(v.L2), dtype=np.uint64)
+        self.sa_intv, self.n_sa = int(v.sa_intv), int(v.n_sa)
+        self.device_bytes = int(nbytes.value)
+
+    @classmethod
+    def upload(cls, primary: int, L2, seq_len: int, bwt: np.ndarray, sa: np.ndarray, sa_intv: int,
+               device: int = 0, dense_sa_intv: int = 0) -> "FMIndex":
+        """From arrays in the reference's in-memory layout (what bwt_restore_bwt/sa produce)."""
+        bwt = np.ascontiguousarray(bwt, dtype=np.uint32)
+        sa = np.ascontiguousarray(sa, dtype=np.uint64)
+        v = _BwtView()
+        v.primary, v.seq_len, v.bwt_size = int(primary), int(seq_len), int(bwt.shape[0])
+        for i in range(5):
+            v.L2[i] = int(L2[i])
+        v.bwt, v.sa_intv, v.n_sa, v.sa = _ptr(bwt), int(sa_intv), int(sa.shape[0]), _ptr(sa)
+        return cls(load_library().cs_index_upload(C.byref(v), device, dense_sa_intv), device)
+
+    @classmethod
+    def load(cls, prefix: str, device: int = 0, dense_sa_intv: int = 0) -> "FMIndex":
+        """From P.bwt / P.sa written by bwaidx (bwt_restore_bwt / bwt_restore_sa, bwt.c:421-462)."""
+        return cls(load_library().cs_index_load(prefix.encode(), device, dense_sa_intv), device)
+
+    @classmethod
+    def build(cls, fwd: np.ndarray, device: int = 0, sa_intv: int = 32) -> "FMIndex":
+        """Construct the index of fwd + revcomp(fwd) on the GPU (what bwaidx computes on the CPU)."""
+        fwd = np.ascontiguousarray(fwd, dtype=np.uint8)
+        return cls(load_library().cs_index_build(_ptr(fwd), fwd.shape[0], device, sa_intv), device)
+
+    def download(self, sa_intv: int = 32):
+        """Back to the reference layout: dict(primary, L2, seq_len, bwt, sa, sa_intv)."""
+        L = load_library()
+        v = _BwtView()
+        _check(L.cs_index_download(self.h, C.byref(v), None, None, sa_intv))
+        bwt = np.zeros(int(v.bwt_size), dtype=np.uint32)
+        sa = np.zeros(int(v.n_sa), dtype=np.uint64)
+        _check(L.cs_index_download(self.h, C.byref(v), _ptr(bwt), _ptr(sa), sa_intv))
+        return dict(primary=self.primary, L2=self.L2.copy(), seq_len=self.seq_len, bwt=bwt, sa=sa, sa_intv=sa_intv)
+
+    def close(self) -> None:
+        if self.h:
+            load_library().cs_index_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- unit-level queries (bwt_occ4 / bwt_extend / bwt_sa) ----------------------------------
+    def occ4(self, k) -> np.ndarray:
+        k = np.ascontiguousarray(k, dtype=np.uint64)
+        out = np.empty((k.shape[0], 4), dtype=np.uint64)
+        _check(load_library().cs_occ4(self.h, k.shape[0], _ptr(k), _ptr(out)))
+        return out
+
+    def extend(self, ik, is_back) -> np.ndarray:
+        ik = np.ascontiguousarray(ik, dtype=np.uint64)
+        is_back = np.ascontiguousarray(is_back, dtype=np.int32)
+        out = np.empty((ik.shape[0], 4, 3), dtype=np.uint64)
+        _check(load_library().cs_extend(self.h, ik.shape[0], _ptr(ik), _ptr(is_back), _ptr(out)))
+        return out
+
+    def sa(self, k) -> np.ndarray:
+        k = np.ascontiguousarray(k, dtype=np.uint64)
+        out = np.empty(k.shape[0], dtype=np.uint64)
+        _check(load_library().cs_sa(self.h, k.shape[0], _ptr(k), _ptr(out)))
+        return out
+
+
+class SeedContext:
+    """Slots of pinned + device buffers with one CUDA stream each (the kt_for worker pool's
+    replacement, bwamem.c:1343 / comp_seed.cpp:2541-2548)."""
+
+    def __init__(self, index: FMIndex, max_reads: int, max_bases: int, max_read_len: int = 256,
+                 max_mems: int = 0, max_seeds: int = 0, n_slots: int = 2):
+        self.index = index
+        self.max_reads, self.max_bases, self.max_read_len = max_reads, max_bases, max_read_len
+        self.n_slots = n_slots
+        h = load_library().cs_ctx_create(index.h, max_reads, max_bases, max_read_len, max_mems, max_seeds, n_slots)
+        if not h:
+            raise CompSeedError(CS_E_CUDA, load_library().cs_last_error().decode())
+        self.h = C.c_void_p(h)
+
+    def close(self) -> None:
+        if self.h:
+            load_library().cs_ctx_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _prep(bases, off):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        return bases, off
+
+    def submit(self, slot: int, bases, off, opt: SeedOpt) -> None:
+        bases, off = self._prep(bases, off)
+        o = opt._c()
+        _check(load_library().cs_seed_batch_submit(self.h, slot, off.shape[0] - 1, _ptr(bases), _ptr(off), C.byref(o)))
+
+    def stage(self, slot: int, bases, off) -> None:
+        bases, off = self._prep(bases, off)
+        _check(load_library().cs_seed_batch_stage(self.h, slot, off.shape[0] - 1, _ptr(bases), _ptr(off)))
+
+    def run_staged(self, slot: int, opt: SeedOpt) -> None:
+        o = opt._c()
+        _check(load_library().cs_seed_batch_run_staged(self.h, slot, C.byref(o)))
+
+    def wait_device(self, slot: int) -> SeedResult:
+        r = _Result()
+        _check(load_library().cs_seed_batch_wait_device(self.h, slot, C.byref(r)))
+        return self._result(r, copy=False)
+
+    def fetch(self, slot: int, copy: bool = True) -> SeedResult:
+        r = _Result()
+        _check(load_library().cs_seed_batch_fetch(self.h, slot, C.byref(r)))
+        return self._result(r, copy=copy)
+
+    def wait(self, slot: int, copy: bool = True) -> SeedResult:
+        r = _Result()
+        _check(load_library().cs_seed_batch_wait(self.h, slot, C.byref(r)))
+        return self._result(r, copy=copy)
+
+    @staticmethod
+    def _result(r: _Result, copy: bool) -> SeedResult:
+        n, nm, ns = int(r.n_reads), int(r.n_mems), int(r.n_seeds)
+        cnt = dict(ext_queries=int(r.counters.ext_queries), ext_calls=int(r.counters.ext_calls),
+                   sal_queries=int(r.counters.sal_queries), sal_calls=int(r.counters.sal_calls))
+        ms = tuple(float(x) for x in r.kernel_ms)
+        if not r.mem_off:  # device-resident result
+            e = np.empty(0, dtype=np.uint32)
+            res = SeedResult(e, np.empty((0, 4), dtype=np.uint64), e, np.empty(0, dtype=np.int64), cnt, ms)
+            res.n_mems_device, res.n_seeds_device, res.n_reads_device = nm, ns, n
+            return res
+        mem_off = np.ctypeslib.as_array(r.mem_off, shape=(n + 1,))
+        seed_off = np.ctypeslib.as_array(r.seed_off, shape=(n + 1,))
+        mems = np.ctypeslib.as_array(r.mems, shape=(nm, 4)) if nm else np.empty((0, 4), dtype=np.uint64)
+        rbeg = np.ctypeslib.as_array(r.rbeg, shape=(ns,)) if ns else np.empty(0, dtype=np.int64)
+        if copy:
+            mem_off, seed_off, mems, rbeg = mem_off.copy(), seed_off.copy(), mems.copy(), rbeg.copy()
+        return SeedResult(mem_off, mems, seed_off, rbeg, cnt, ms)
+
+
+def seed_reads(index: FMIndex, bases, off, opt: SeedOpt | None = None, batch_reads: int = 1 << 19,
+               n_slots: int = 2, max_mems_per_read: int = 16, max_seeds_per_read: int = 32) -> SeedResult:
+    """Seed a whole read set: contiguous batches pipelined through the slots of one context
+    (batch i+1 is submitted before batch i is waited on), results concatenated in input order.
+    On CS_E_OVERFLOW the context is re-created with doubled result capacities and the set is redone."""
+    opt = opt or SeedOpt()
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint32)
+    n = off.shape[0] - 1
+    if n == 0:
+        z = np.zeros(1, dtype=np.uint32)
+        return SeedResult(z, np.empty((0, 4), dtype=np.uint64), z.copy(), np.empty(0, dtype=np.int64))
+    lens = np.diff(off.astype(np.int64))
+    max_len = max(1, int(lens.max()))
+    starts = list(range(0, n, batch_reads))
+    max_b = max(int(off[min(n, s + batch_reads)]) - int(off[s]) for s in starts)
+    while True:
+        ctx = SeedContext(index, min(batch_reads, n), max(1, max_b), max_len,
+                          min(batch_reads, n) * max_mems_per_read, min(batch_reads, n) * max_seeds_per_read, n_slots)
+        try:
+            parts: list[SeedResult] = []
+            inflight: list[int] = []
+
+            def _submit(bi: int) -> None:
+                s = starts[bi]
+                e = min(n, s + batch_reads)
+                o = (off[s:e + 1].astype(np.int64) - int(off[s])).astype(np.uint32)
+                ctx.submit(bi % n_slots, bases[int(off[s]):int(off[e])], o, opt)
+                inflight.append(bi)
+
+            nxt = 0
+            while nxt < len(starts) and len(inflight) < n_slots:
+                _submit(nxt)
+                nxt += 1
+            while inflight:
+                bi = inflight.pop(0)
+                parts.append(ctx.wait(bi % n_slots))
+                if nxt < len(starts):
+                    _submit(nxt)
+                    nxt += 1
+            break
+        except CompSeedError as e:
+            if e.code != CS_E_OVERFLOW or max_seeds_per_read > (1 << 16):
+                raise
+            max_mems_per_read *= 4
+            max_seeds_per_read *= 8
+        finally:
+            ctx.close()
+    return concat_results(parts)
+
+
+def concat_results(parts: list[SeedResult]) -> SeedResult:
+    if len(parts) == 1:
+        return parts[0]
+    mem_off = [np.zeros(1, dtype=np.uint32)]
+    seed_off = [np.zeros(1, dtype=np.uint32)]
+    mb = sb = 0
+    cnt: dict = {}
+    ms = [0.0, 0.0, 0.0, 0.0]
+    for p in parts:
+        mem_off.append((p.mem_off[1:].astype(np.int64) + mb).astype(np.uint32))
+        seed_off.append((p.seed_off[1:].astype(np.int64) + sb).astype(np.uint32))
+        mb += int(p.mem_off[-1])
+        sb += int(p.seed_off[-1])
+        for k, v in p.counters.items():
+            cnt[k] = cnt.get(k, 0) + v
+        ms = [a + b for a, b in zip(ms, p.kernel_ms)]
+    return SeedResult(np.concatenate(mem_off), np.concatenate([p.mems for p in parts]), np.concatenate(seed_off),
+                      np.concatenate([p.rbeg for p in parts]), cnt, tuple(ms))
+
+
+def probe_random_gather(device: int = 0, table_bytes: int = 4 << 30, granule: int = 32, n_loads: int = 1 << 28, iters: int = 3):
+    """(GB/s, Gloads/s) of independent uniformly random granule-sized loads: the random-sector roofline."""
+    gb, gl = C.c_double(), C.c_double()
+    _check(load_library().cs_probe_random_gather(device, table_bytes, granule, n_loads, iters, C.byref(gb), C.byref(gl)))
+    return gb.value, gl.value
+
+
+def flush_l2(device: int = 0) -> None:
+    _check(load_library().cs_flush_l2(device))

@@ -1,0 +1,161 @@
+/* compseed_b200 -- C-ABI of the B200-native SMEM seeding path.
+ *
+ * This is the drop-in boundary for the seeding hot path of i-xiaohu/CompSeed (a BWA-MEM 0.7.17 fork).
+ * The reference has no plugin/FFI interface (it is statically linked C/C++), so the seam is
+ * data-shaped: everything upstream of mem_chain() is replaced by the calls below.
+ * Plain pointers and sizes only; no torch / CUDA types cross this boundary.
+ * Reference paths are relative to the reference tree (i-xiaohu/CompSeed).
+ *
+ *   reference interface                                   replaced by
+ *   ---------------------------------------------------   ----------------------------------------
+ *   bwt_t after bwt_restore_bwt/bwt_restore_sa             cs_index_upload / cs_index_load
+ *     (FM_index/bwt.c:421-462, bwalib/bwa.c:288)
+ *   bwt_occ4 / bwt_2occ4   (FM_index/bwt.c:169,189)        cs_occ4            (unit-level probe)
+ *   bwt_extend             (FM_index/bwt.c:262)            cs_extend          (unit-level probe)
+ *   bwt_sa                 (FM_index/bwt.c:86)             cs_sa              (also used by the batch path)
+ *   mem_collect_intv       (mapping/bwamem.c:218-272)      cs_seed_batch_submit / cs_seed_batch_wait
+ *   seeding block of seed_and_extend                        "        (mems[] == aux.match[r], sorted by info)
+ *     (mapping/comp_seed.cpp:2255-2302)
+ *   seed expansion + bwt_sa                                 "        (rbeg[] == seed[r][*].rbeg, emission order)
+ *     (mapping/bwamem.c:386-399, comp_seed.cpp:2306-2346)
+ *   kt_for workers over reads / 512-read blocks            slots of a cs_ctx_t (pinned buffers, one CUDA
+ *     (mapping/bwamem.c:1343, comp_seed.cpp:2541-2548)       stream per slot; submit batch i+1 while waiting on i)
+ *
+ * Error convention: every int-returning call returns CS_OK (0) or a negative CS_E_* code and sets a
+ * thread-local message readable through cs_last_error().  The reference's convention is "fatal"
+ * (err_fatal / xassert, bwalib/utils.c:92-124); the host shim turns non-zero into err_fatal.
+ * There is no CPU fallback anywhere behind this ABI: without a CUDA device every call fails.
+ */
+#ifndef COMPSEED_B200_H
+#define COMPSEED_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_OK            0
+#define CS_E_ARG        -1   /* bad argument */
+#define CS_E_CUDA       -2   /* CUDA runtime error (message in cs_last_error) */
+#define CS_E_OVERFLOW   -3   /* a result buffer of the ctx is too small for this batch (see cs_last_error) */
+#define CS_E_IO         -4   /* index file could not be read */
+#define CS_E_NODEVICE   -5   /* no CUDA device: this library has no CPU path */
+#define CS_E_STATE      -6   /* slot used out of order (wait without submit, submit on a busy slot) */
+
+/* The fields of bwt_t that the seeding path reads (FM_index/bwt.h:48-60), in the reference's own
+ * in-memory layout: bwt[] = 64-byte buckets (4 x u64 checkpoint + 8 x u32 of 16 bases, MSB first),
+ * sa[0] == (uint64_t)-1.  The caller keeps ownership; cs_index_upload copies. */
+typedef struct {
+	uint64_t primary;
+	uint64_t L2[5];
+	uint64_t seq_len;
+	uint64_t bwt_size;      /* uint32 words in bwt[] */
+	const uint32_t *bwt;
+	int32_t  sa_intv;       /* power of two */
+	uint64_t n_sa;
+	const uint64_t *sa;
+} cs_bwt_view_t;
+
+/* == bwtintv_t (FM_index/bwt.h:62-64): x[0]=k, x[1]=l, x[2]=s, info = (start << 32) | end */
+typedef struct { uint64_t x[3]; uint64_t info; } cs_mem_t;
+
+/* The seeding scalars of mem_opt_t (mapping/comp_seed.h:41-73).  split_len is computed by the
+ * caller exactly as its own code does: (int)(min_seed_len*split_factor+.499) in float (bwamem.c:223)
+ * or (int)(1.0*min_seed_len*split_factor+.499) in double (comp_seed.cpp:2279). */
+typedef struct {
+	int32_t min_seed_len;   /* -k, default 19  */
+	int32_t split_len;      /* from -r, default 28 */
+	int32_t split_width;    /* -s, default 10  */
+	int32_t max_mem_intv;   /* -y, default 20; 0 disables round 3 */
+	int32_t max_occ;        /* -c, default 500 */
+} cs_seed_opt_t;
+
+/* Counters with the meaning of the reference's profile (comp_seed.h:158-160, main.cpp:203-214):
+ * queries = logical requests, calls = those that touched the FM-index / suffix array in HBM. */
+typedef struct {
+	uint64_t ext_queries;   /* bwt_extend requests issued by the seeding kernels */
+	uint64_t ext_calls;     /* of those, served from the 64-row Occ buckets (the rest: k-mer table / short-circuits) */
+	uint64_t sal_queries;   /* SA rows requested (== number of seeds) */
+	uint64_t sal_calls;     /* LF steps walked for them (0 with a dense SA) */
+} cs_counters_t;
+
+typedef struct {
+	uint32_t n_reads;
+	uint64_t n_mems, n_seeds;
+	/* Pinned host memory owned by the ctx, valid until the slot is resubmitted.  NULL for
+	 * cs_seed_batch_wait_device (results stay in HBM). */
+	const uint32_t *mem_off;   /* [n_reads+1] */
+	const cs_mem_t *mems;      /* [n_mems]  per read sorted ascending by info (duplicates kept) */
+	const uint32_t *seed_off;  /* [n_reads+1] */
+	const int64_t  *rbeg;      /* [n_seeds] SA[x0 + k*step] in the emission order of bwamem.c:386-399 */
+	cs_counters_t counters;
+	float kernel_ms[4];        /* CUDA-event durations on the slot's stream: seed, collect, SA-resolve, whole slot (incl. copies) */
+} cs_result_t;
+
+typedef struct cs_index cs_index_t;
+typedef struct cs_ctx cs_ctx_t;
+
+const char *cs_last_error(void);
+int cs_device_count(void);
+
+/* --- index ------------------------------------------------------------------------------------
+ * The device copy is re-laid-out once at upload: 32-byte buckets of 64 BWT rows (128-bit base words
+ * + 3 x 40-bit checkpoint), read with one 256-bit load.  dense_sa_intv: 0 keeps the sampling of the
+ * input; a power of two < sa_intv re-samples the suffix array on the device (bwt_sa(k) does not
+ * depend on the sampling, FM_index/bwt.c:86-96), 1 = full suffix array. */
+cs_index_t *cs_index_upload(const cs_bwt_view_t *bwt, int device, int dense_sa_intv);
+/* Reads P.bwt and P.sa exactly as bwt_restore_bwt / bwt_restore_sa do (FM_index/bwt.c:421-462). */
+cs_index_t *cs_index_load(const char *prefix, int device, int dense_sa_intv);
+/* Builds the FM-index of fwd+revcomp(fwd) on the device (fwd: l_pac nt4 codes 0..3 in host memory).
+ * Same BWT / Occ / SA as bwaidx (FM_index/index_main.c:257-325); the SA is kept at sa_intv rows. */
+cs_index_t *cs_index_build(const uint8_t *fwd, uint64_t l_pac, int device, int sa_intv);
+/* Copies the index back in the reference layout (for a host-side consumer such as the CPU baseline).
+ * Call once with bwt == NULL to get sizes in *view, then with caller-allocated arrays of
+ * view->bwt_size uint32 and view->n_sa uint64 (at the reference sampling out_sa_intv, e.g. 32). */
+int cs_index_download(const cs_index_t *idx, cs_bwt_view_t *view, uint32_t *bwt, uint64_t *sa, int out_sa_intv);
+int cs_index_info(const cs_index_t *idx, cs_bwt_view_t *view /* pointers set to NULL */, uint64_t *device_bytes);
+void cs_index_free(cs_index_t *idx);
+
+/* unit-level probes: n queries from host arrays, answered by the same device functions the batch
+ * kernels use.  cnt: n*4, ik: n*3 (x0,x1,x2), ok: n*4*3, is_back: n. */
+int cs_occ4(const cs_index_t *idx, uint32_t n, const uint64_t *k, uint64_t *cnt);
+int cs_extend(const cs_index_t *idx, uint32_t n, const uint64_t *ik, const int32_t *is_back, uint64_t *ok);
+int cs_sa(const cs_index_t *idx, uint32_t n, const uint64_t *k, uint64_t *out);
+
+/* --- batches ----------------------------------------------------------------------------------
+ * A ctx owns n_slots independent slots (stream + pinned host buffers + device buffers).  One
+ * submitting thread per ctx; the index handle may be shared read-only between ctxs.
+ * max_mems / max_seeds: result capacities per slot (0: 16 / 32 per read). */
+cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, uint64_t max_bases, uint32_t max_read_len,
+                        uint64_t max_mems, uint64_t max_seeds, int n_slots);
+void cs_ctx_free(cs_ctx_t *ctx);
+
+/* bases: nt4 codes (0..3, anything > 3 is ambiguous) of all reads concatenated, converted as
+ * comp_seed.cpp:2258-2260 does; offsets: n_reads+1.  Copies into the slot's pinned buffer, then
+ * enqueues H2D + kernels on the slot's stream and returns without waiting. */
+int cs_seed_batch_submit(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint8_t *bases, const uint32_t *offsets,
+                         const cs_seed_opt_t *opt);
+/* Waits for the slot, copies the results to its pinned host buffers and fills *out. */
+int cs_seed_batch_wait(cs_ctx_t *ctx, int slot, cs_result_t *out);
+
+/* Device-resident variant (inputs already in HBM, results left in HBM): stage once, run many. */
+int cs_seed_batch_stage(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint8_t *bases, const uint32_t *offsets);
+int cs_seed_batch_run_staged(cs_ctx_t *ctx, int slot, const cs_seed_opt_t *opt);
+int cs_seed_batch_wait_device(cs_ctx_t *ctx, int slot, cs_result_t *out);
+/* Copies the results of the last run on this slot to the pinned host buffers (after *_wait_device). */
+int cs_seed_batch_fetch(cs_ctx_t *ctx, int slot, cs_result_t *out);
+
+/* --- measurement helpers ----------------------------------------------------------------------
+ * Random-gather probe: the "HBM random sector" roofline denominator.
+ * n_loads independent uniformly random `granule`-byte aligned loads (32 or 64) over table_bytes. */
+int cs_probe_random_gather(int device, uint64_t table_bytes, uint32_t granule, uint64_t n_loads, int iters,
+                           double *gbytes_per_s, double *gloads_per_s);
+/* Writes a buffer larger than L2 (flush between timed iterations). */
+int cs_flush_l2(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,66 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds for sm_100a, loads, exports every
+symbol include/compseed_b200.h declares, and fails loudly (no CPU fallback) without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from compseed_b200 import build as B
+    return B.build()
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "compseed_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cs_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/compseed_b200.h but not exported"
+
+
+def test_library_contains_sm100a_code(lib_path):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_device():
+    import compseed_b200 as cs
+    if cs.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    with pytest.raises(cs.CompSeedError):
+        cs.FMIndex.upload(1, [0, 1, 2, 3, 4], 4, np.zeros(24, np.uint32), np.zeros(1, np.uint64), 32)
+    with pytest.raises(cs.CompSeedError):
+        cs.FMIndex.load("/nonexistent/prefix")
+    with pytest.raises(cs.CompSeedError):
+        cs.probe_random_gather(0, 1 << 20, 32, 1024, 1)
+
+
+def test_product_path_does_not_touch_the_oracle():
+    """The shipped package must never import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "compseed_b200")
+    bad = re.compile(r"(from\s+oracle|import\s+oracle|oracle_py|liboracle|libcsref|cs_oracle|oracle/)")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert not bad.search(txt), f"{f} references the oracle"
+
+
+def test_option_mirror_defaults():
+    import compseed_b200 as cs
+    o = cs.SeedOpt()   # mem_opt_init, comp_seed.cpp:26-61
+    assert (o.min_seed_len, o.split_width, o.max_mem_intv, o.max_occ, o.split_len) == (19, 10, 20, 500, 28)
+    assert cs.SeedOpt(split_factor=1.0).split_len == 19

@@ -1,0 +1,149 @@
+"""GPU parity tests (run on the B200 box): every call goes through the C-ABI
+(include/compseed_b200.h) and is compared bit-exactly with the golden vectors of the unmodified
+reference and with the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from compseed_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _opts(g, i):
+    o = g[f"opt{i}"]
+    return dict(min_seed_len=int(o[0]), split_len=int(o[1]), split_width=int(o[2]), max_mem_intv=int(o[3]), max_occ=int(o[4]))
+
+
+class _Opt:
+    """SeedOpt with an explicit split_len (the goldens store the integer)."""
+    def __init__(self, cs, d):
+        self.o = cs.SeedOpt(min_seed_len=d["min_seed_len"], split_width=d["split_width"], max_mem_intv=d["max_mem_intv"], max_occ=d["max_occ"])
+        self.split_len = d["split_len"]
+
+    def _c(self):
+        c = self.o._c()
+        c.split_len = self.split_len
+        return c
+
+
+def _upload(cs, g, dense=0):
+    return cs.FMIndex.upload(int(g["primary"]), g["L2"], int(g["seq_len"]), g["bwt"], g["sa"], int(g["sa_intv"]), dense_sa_intv=dense)
+
+
+def _assert_same(r, mem_off, mems, seed_off, rbeg):
+    assert np.array_equal(r.mem_off, mem_off)
+    assert np.array_equal(r.mems, mems)
+    assert np.array_equal(r.seed_off, seed_off)
+    assert np.array_equal(r.rbeg, rbeg)
+
+
+def test_golden_primitives(cuda_lib, golden):
+    idx = _upload(cuda_lib, golden)
+    assert np.array_equal(idx.occ4(golden["occ_k"]), golden["occ_cnt"])
+    assert np.array_equal(idx.extend(golden["ext_ik"], golden["ext_back"]), golden["ext_ok"])
+    assert np.array_equal(idx.sa(golden["sa_k"]), golden["sa_v"])
+
+
+@pytest.mark.parametrize("dense", [0, 4, 1])
+def test_golden_seeding(cuda_lib, golden, dense):
+    idx = _upload(cuda_lib, golden, dense)
+    assert idx.sa_intv == (dense or int(golden["sa_intv"]))
+    for i in range(golden["n_opts"]):
+        r = cuda_lib.seed_reads(idx, golden["bases"], golden["off"], _Opt(cuda_lib, _opts(golden, i)), batch_reads=128, n_slots=3)
+        _assert_same(r, golden[f"mem_off{i}"], golden[f"mems{i}"], golden[f"seed_off{i}"], golden[f"rbeg{i}"])
+        assert r.counters["sal_queries"] == golden[f"rbeg{i}"].shape[0]
+        if dense == 1:
+            assert r.counters["sal_calls"] == 0
+
+
+def test_index_download_roundtrip(cuda_lib, golden):
+    idx = _upload(cuda_lib, golden, dense=1)
+    d = idx.download(sa_intv=int(golden["sa_intv"]))
+    assert np.array_equal(d["bwt"], golden["bwt"])
+    assert np.array_equal(d["sa"], golden["sa"])
+
+
+@pytest.mark.parametrize("kind,n_reads", [("random", 20000), ("repeat", 4000), ("long", 300)])
+def test_oracle_parity_seeded(cuda_lib, oracle_lib, kind, n_reads):
+    if kind == "random":      # config 1 in miniature
+        ref = synth.random_reference(400_000, seed=101)
+        bases, off, _ = synth.simulate_reads(ref, n_reads, 150, 0.01, seed=102)
+    elif kind == "repeat":    # config 4 in miniature: x[2] > max_occ, 3rd-round reseeding, long SA walks
+        ref = synth.repeat_rich_reference(300_000, seed=103, n_segdup=100, segdup_len=2000, n_tandem=60)
+        bases, off, _ = synth.simulate_reads(ref, n_reads, [100, 150, 250], 0.02, seed=104, n_rate=0.003)
+    else:                     # reads longer than 255 and longer than the shared-memory interval list
+        ref = synth.repeat_rich_reference(200_000, seed=105, n_segdup=40, segdup_len=3000, n_tandem=40)
+        bases, off, _ = synth.simulate_reads(ref, n_reads, [400, 1000, 3000], 0.01, seed=106, n_rate=0.001)
+    oi = oracle_lib.OracleIndex.build(ref)
+    idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv)
+    for r_factor, y, c in [(1.5, 20, 500), (1.0, 20, 50), (2.5, 40, 500)]:
+        opt = cuda_lib.SeedOpt(split_factor=r_factor, max_mem_intv=y, max_occ=c)
+        want = oi.seed(bases, off, split_len=opt.split_len, max_mem_intv=y, max_occ=c, n_threads=8)
+        got = cuda_lib.seed_reads(idx, bases, off, opt, batch_reads=8192)
+        _assert_same(got, want.mem_off, want.mems, want.seed_off, want.rbeg)
+        # every logical extend is accounted for: queries == bwamem's bwt_extend call count (SURVEY 8d "E")
+        assert got.counters["ext_queries"] == want.counters["ext"]
+        assert got.counters["sal_calls"] == want.counters["lf"]
+
+
+def test_batching_and_slots_do_not_change_results(cuda_lib, oracle_lib):
+    """Determinism contract: output independent of batch size, slot count, read order."""
+    ref = synth.random_reference(100_000, seed=111)
+    bases, off, _ = synth.simulate_reads(ref, 3000, [100, 150], 0.01, seed=112, n_rate=0.001)
+    oi = oracle_lib.OracleIndex.build(ref)
+    idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv, dense_sa_intv=1)
+    a = cuda_lib.seed_reads(idx, bases, off, batch_reads=3000, n_slots=1)
+    b = cuda_lib.seed_reads(idx, bases, off, batch_reads=257, n_slots=4)
+    _assert_same(b, a.mem_off, a.mems, a.seed_off, a.rbeg)
+    sb, so, perm = synth.shuffle_reads(bases, off)
+    c = cuda_lib.seed_reads(idx, sb, so, batch_reads=1000)
+    for j in (0, 17, 2999):
+        r = int(perm[j])
+        assert np.array_equal(c.mems[c.mem_off[j]:c.mem_off[j + 1]], a.mems[a.mem_off[r]:a.mem_off[r + 1]])
+        assert np.array_equal(c.rbeg[c.seed_off[j]:c.seed_off[j + 1]], a.rbeg[a.seed_off[r]:a.seed_off[r + 1]])
+
+
+def test_staged_device_resident_run_and_fetch(cuda_lib, golden):
+    idx = _upload(cuda_lib, golden, dense=1)
+    n = golden["off"].shape[0] - 1
+    ctx = cuda_lib.SeedContext(idx, n, int(golden["off"][-1]), 256, n * 64, n * 600, 1)
+    ctx.stage(0, golden["bases"], golden["off"])
+    opt = _Opt(cuda_lib, _opts(golden, 0))
+    for _ in range(2):   # stage once, run twice: same answer
+        ctx.run_staged(0, opt)
+        d = ctx.wait_device(0)
+        assert d.n_mems_device == golden["mems0"].shape[0] and d.n_seeds_device == golden["rbeg0"].shape[0]
+        r = ctx.fetch(0)
+        _assert_same(r, golden["mem_off0"], golden["mems0"], golden["seed_off0"], golden["rbeg0"])
+        assert r.kernel_ms[0] > 0
+    ctx.close()
+
+
+def test_overflow_is_reported_not_truncated(cuda_lib, golden):
+    if golden["name"] != "repeat30k":
+        pytest.skip("needs the repeat-rich fixture")
+    idx = _upload(cuda_lib, golden)
+    n = golden["off"].shape[0] - 1
+    ctx = cuda_lib.SeedContext(idx, n, int(golden["off"][-1]), 256, n * 16, n * 4, 1)   # seeds cannot fit
+    ctx.submit(0, golden["bases"], golden["off"], _Opt(cuda_lib, _opts(golden, 0)))
+    with pytest.raises(cuda_lib.CompSeedError) as e:
+        ctx.wait(0)
+    assert e.value.code == -3
+    ctx.close()
+
+
+def test_argument_errors(cuda_lib, golden):
+    idx = _upload(cuda_lib, golden)
+    ctx = cuda_lib.SeedContext(idx, 16, 1024, 100, 0, 0, 1)
+    with pytest.raises(cuda_lib.CompSeedError):   # read longer than max_read_len
+        ctx.submit(0, np.zeros(200, np.uint8), np.array([0, 200], np.uint32), cuda_lib.SeedOpt())
+    with pytest.raises(cuda_lib.CompSeedError):   # wait without submit
+        ctx.wait(0)
+    with pytest.raises(cuda_lib.CompSeedError):   # bad slot
+        ctx.submit(3, np.zeros(10, np.uint8), np.array([0, 10], np.uint32), cuda_lib.SeedOpt())
+    ctx.close()
+
+
+def test_random_gather_probe_runs(cuda_lib):
+    gb, gl = cuda_lib.probe_random_gather(0, 256 << 20, 32, 1 << 22, 1)
+    assert gb > 0 and gl > 0
