@@ -25,6 +25,7 @@ static int set_err(int code, const char *fmt, ...)
 	set_err(CS_E_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); goto fail; } } while (0)
 
 extern "C" const char *cs_last_error(void) { return g_err; }
+void cs_internal_set_error(int code, const char *msg) { set_err(code, "%s", msg); }
 
 extern "C" int cs_device_count(void)
 {
@@ -405,10 +406,6 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		CK(cudaEventCreate(&s->ev_done));
 		CK(cudaMallocHost(&s->h_bases, max_bases));
 		CK(cudaMallocHost(&s->h_off, ((size_t)max_reads + 1) * 4));
-		CK(cudaMallocHost(&s->h_mem_off, ((size_t)max_reads + 1) * 4));
-		CK(cudaMallocHost(&s->h_seed_off, ((size_t)max_reads + 1) * 4));
-		CK(cudaMallocHost(&s->h_mems, ctx->max_mems * sizeof(cs_mem_t)));
-		CK(cudaMallocHost(&s->h_rbeg, ctx->max_seeds * 8));
 		CK(cudaMallocHost(&s->h_ctrl, sizeof(Ctrl)));
 		CK(cudaMalloc(&s->d_bases, max_bases));
 		CK(cudaMalloc(&s->d_off, ((size_t)max_reads + 1) * 4));
@@ -611,13 +608,18 @@ extern "C" int cs_seed_batch_wait_device(cs_ctx_t *ctx, int slot, cs_result_t *o
 static int fetch(cs_ctx *ctx, Slot *s)
 {
 	const uint32_t n = s->n_reads;
+	if (!s->h_mems) { // pinned result buffers are allocated on first use (device-resident runs never need them)
+		CK(cudaMallocHost(&s->h_mem_off, ((size_t)ctx->max_reads + 1) * 4));
+		CK(cudaMallocHost(&s->h_seed_off, ((size_t)ctx->max_reads + 1) * 4));
+		CK(cudaMallocHost(&s->h_mems, ctx->max_mems * sizeof(cs_mem_t)));
+		CK(cudaMallocHost(&s->h_rbeg, ctx->max_seeds * 8));
+	}
 	CK(cudaMemcpyAsync(s->h_mem_off, s->d_mem_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaMemcpyAsync(s->h_seed_off, s->d_seed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
 	if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(s->h_mems, s->d_mems, (size_t)s->h_ctrl->n_mems * sizeof(cs_mem_t), cudaMemcpyDeviceToHost, s->stream));
 	if (s->h_ctrl->n_seeds) CK(cudaMemcpyAsync(s->h_rbeg, s->d_rows, (size_t)s->h_ctrl->n_seeds * 8, cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaEventRecord(s->ev_done, s->stream));
 	CK(cudaEventSynchronize(s->ev_done));
-	(void)ctx;
 	return CS_OK;
 fail:
 	return CS_E_CUDA;

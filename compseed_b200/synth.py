@@ -127,3 +127,49 @@ def split_len_bwamem(min_seed_len: int, split_factor: float) -> int:
 def split_len_compseed(min_seed_len: int, split_factor: float) -> int:
     """comp_seed.cpp:2279: 1.0 * int * float in double."""
     return int(1.0 * min_seed_len * float(np.float32(split_factor)) + .499)
+
+
+# ---------------------------------------------------------------------------------------------
+# Large workloads (configs 2/3): generated on the GPU with torch (plumbing only) because numpy
+# would need minutes and tens of GB for 3.1 Gbp / 10 M reads.  Seeded and deterministic for a given
+# torch build.
+# ---------------------------------------------------------------------------------------------
+def random_reference_torch(l_pac: int, seed: int, device: str):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty(l_pac, dtype=torch.uint8, device=device)
+    step = 1 << 28
+    for s in range(0, l_pac, step):
+        e = min(l_pac, s + step)
+        out[s:e] = torch.randint(0, 4, (e - s,), dtype=torch.uint8, device=device, generator=g)
+    return out
+
+
+def simulate_reads_torch(ref, n_reads: int, read_len: int, sub_rate: float, seed: int, window: tuple[int, int] | None = None,
+                         chunk: int = 1 << 20):
+    """Fixed-length reads, uniform starts inside `window`, position-sorted, 50 % reverse-complemented,
+    `sub_rate` substitutions.  `ref` is a uint8 CUDA tensor.  Returns numpy (bases u8, offsets u32, pos i64)."""
+    import torch
+    dev = ref.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    l_pac = ref.shape[0]
+    lo, hi = (0, l_pac) if window is None else window
+    pos = torch.randint(lo, max(lo + 1, hi - read_len), (n_reads,), device=dev, generator=g, dtype=torch.int64)
+    pos, _ = torch.sort(pos)
+    bases = np.empty(n_reads * read_len, dtype=np.uint8)
+    ar = torch.arange(read_len, device=dev, dtype=torch.int64)
+    for s in range(0, n_reads, chunk):
+        e = min(n_reads, s + chunk)
+        p = pos[s:e]
+        rev = torch.rand(e - s, device=dev, generator=g) < 0.5
+        idx = torch.where(rev[:, None], p[:, None] + (read_len - 1) - ar[None, :], p[:, None] + ar[None, :])
+        b = ref[idx]
+        b = torch.where(rev[:, None], 3 - b, b)
+        mut = torch.rand((e - s, read_len), device=dev, generator=g) < sub_rate
+        add = torch.randint(1, 4, (e - s, read_len), device=dev, generator=g, dtype=torch.uint8)
+        b = torch.where(mut, (b + add) & 3, b).to(torch.uint8)
+        bases[s * read_len:e * read_len] = b.reshape(-1).cpu().numpy()
+    off = (np.arange(n_reads + 1, dtype=np.int64) * read_len).astype(np.uint32)
+    return bases, off, pos.cpu().numpy()

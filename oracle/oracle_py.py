@@ -98,8 +98,9 @@ def _ptr(a: np.ndarray):
 class OracleIndex:
     """FM-index in the reference's in-memory layout, owned by liboracle.so."""
 
-    def __init__(self, handle):
+    def __init__(self, handle, keep=None):
         self.h = handle
+        self._keep = keep   # arrays we only borrow (from_arrays): never freed by the C side
         i = handle.contents
         self.primary = int(i.primary)
         self.L2 = np.array(list(i.L2), dtype=np.uint64)
@@ -126,13 +127,29 @@ class OracleIndex:
             raise RuntimeError(f"cannot load index {prefix}")
         return cls(h)
 
+    @classmethod
+    def from_arrays(cls, primary, L2, seq_len, bwt, sa, sa_intv) -> "OracleIndex":
+        """Wrap arrays in the reference layout (e.g. an index downloaded from the GPU builder)."""
+        lib()
+        bwt = np.ascontiguousarray(bwt, dtype=np.uint32)
+        sa = np.ascontiguousarray(sa, dtype=np.uint64)
+        st = _Index()
+        st.primary, st.seq_len, st.bwt_size = int(primary), int(seq_len), int(bwt.shape[0])
+        for i in range(5):
+            st.L2[i] = int(L2[i])
+        st.bwt = bwt.ctypes.data_as(C.POINTER(C.c_uint32))
+        st.sa_intv, st.n_sa = int(sa_intv), int(sa.shape[0])
+        st.sa = sa.ctypes.data_as(C.POINTER(C.c_uint64))
+        return cls(C.pointer(st), keep=(st, bwt, sa))
+
     def dump(self, prefix: str) -> None:
         if lib().cso_index_dump(self.h, prefix.encode()) != 0:
             raise RuntimeError("cso_index_dump failed")
 
     def __del__(self):
         try:
-            lib().cso_index_free(self.h)
+            if self._keep is None:
+                lib().cso_index_free(self.h)
         except Exception:
             pass
 

@@ -147,3 +147,35 @@ def test_argument_errors(cuda_lib, golden):
 def test_random_gather_probe_runs(cuda_lib):
     gb, gl = cuda_lib.probe_random_gather(0, 256 << 20, 32, 1 << 22, 1)
     assert gb > 0 and gl > 0
+
+
+@pytest.mark.parametrize("kind", ["random", "repeat", "tiny", "homopolymer"])
+def test_gpu_index_build_matches_bwaidx_semantics(cuda_lib, oracle_lib, kind):
+    """cs_index_build (device suffix sort) == the oracle builder, which is pinned to bwaidx by the goldens."""
+    if kind == "random":
+        ref = synth.random_reference(300_000, seed=201)
+    elif kind == "repeat":   # long ties: tandem repeats and exact duplications force many refinement rounds
+        ref = synth.repeat_rich_reference(200_000, seed=202, n_segdup=60, segdup_len=2500, n_tandem=40, divergence=0.0)
+    elif kind == "tiny":
+        ref = synth.random_reference(37, seed=203)
+    else:                    # worst case for ties and for the '$'-is-smallest rule
+        ref = np.zeros(5000, dtype=np.uint8)
+        ref[2500:] = 3
+    oi = oracle_lib.OracleIndex.build(ref)
+    for intv in (32, 1):
+        idx = cuda_lib.FMIndex.build(ref, sa_intv=intv)
+        assert idx.primary == oi.primary and np.array_equal(idx.L2, oi.L2) and idx.seq_len == oi.seq_len
+        d = idx.download(sa_intv=32)
+        assert np.array_equal(d["bwt"], oi.bwt)
+        assert np.array_equal(d["sa"], oi.sa)
+        idx.close()
+
+
+def test_golden_reference_rebuilt_on_gpu(cuda_lib, golden):
+    """Index built on the GPU from the golden reference sequence == the index bwaidx wrote."""
+    idx = cuda_lib.FMIndex.build(golden["ref"], sa_intv=int(golden["sa_intv"]))
+    d = idx.download(sa_intv=int(golden["sa_intv"]))
+    assert idx.primary == int(golden["primary"])
+    assert np.array_equal(d["bwt"], golden["bwt"]) and np.array_equal(d["sa"], golden["sa"])
+    r = cuda_lib.seed_reads(idx, golden["bases"], golden["off"], _Opt(cuda_lib, _opts(golden, 0)))
+    _assert_same(r, golden["mem_off0"], golden["mems0"], golden["seed_off0"], golden["rbeg0"])
