@@ -83,9 +83,8 @@ __global__ void k_unlayout(const uint4 *src, uint64_t seq_len, uint32_t *dst, ui
 			base = ((n_ref - (n_ref > 0)) << 4);
 			if (n_ref > 0) base += 8 + (((seq_len - ((n_ref - 1) << 7)) + 15) >> 4);
 		}
-		if (base + 8 <= dst_words) {
-			uint64_t *cp = reinterpret_cast<uint64_t*>(dst + base);
-			cp[0] = cnt[0]; cp[1] = cnt[1]; cp[2] = cnt[2]; cp[3] = cnt[3];
+		if (base + 8 <= dst_words) { // the trailing record may be only 4-byte aligned: write 32-bit halves
+			for (int c = 0; c < 4; ++c) { dst[base + 2 * c] = (uint32_t)cnt[c]; dst[base + 2 * c + 1] = (uint32_t)(cnt[c] >> 32); }
 		}
 		if (B < n_ref) {
 			for (int j = 0; j < 8; ++j) {
