@@ -655,14 +655,24 @@ extern "C" int cs_seed_batch_wait(cs_ctx_t *ctx, int slot, cs_result_t *out)
 // ---------------------------------------------------------------------------------------------
 // measurement helpers
 // ---------------------------------------------------------------------------------------------
+extern "C" int cs_probe_random_gather_ex(int device, uint64_t table_bytes, uint32_t granule, uint64_t n_loads, int iters, int unroll,
+                                         int l2_fetch_granularity, double *gbytes_per_s, double *gloads_per_s);
+
 extern "C" int cs_probe_random_gather(int device, uint64_t table_bytes, uint32_t granule, uint64_t n_loads, int iters,
                                       double *gbytes_per_s, double *gloads_per_s)
+{
+	return cs_probe_random_gather_ex(device, table_bytes, granule, n_loads, iters, 1, 0, gbytes_per_s, gloads_per_s);
+}
+
+extern "C" int cs_probe_random_gather_ex(int device, uint64_t table_bytes, uint32_t granule, uint64_t n_loads, int iters, int unroll,
+                                         int l2_fetch_granularity, double *gbytes_per_s, double *gloads_per_s)
 {
 	uint4 *d_t = nullptr; unsigned long long *d_sink = nullptr;
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	float best = 1e30f;
-	if (granule != 16 && granule != 32 && granule != 64 && granule != 128) return set_err(CS_E_ARG, "granule must be 16, 32, 64 or 128");
+	if (granule != 16 && granule != 32 && granule != 64) return set_err(CS_E_ARG, "granule must be 16, 32 or 64");
 	if (use_device(device) != CS_OK) return CS_E_CUDA;
+	if (l2_fetch_granularity) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)l2_fetch_granularity);
 	{
 		cudaDeviceProp prop;
 		CK(cudaGetDeviceProperties(&prop, device));
@@ -674,7 +684,8 @@ extern "C" int cs_probe_random_gather(int device, uint64_t table_bytes, uint32_t
 		CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 		for (int it = 0; it < iters + 1; ++it) {
 			CK(cudaEventRecord(e0));
-			k_gather_probe<<<prop.multiProcessorCount * 8, 256>>>(d_t, table_bytes / granule, granule / 16, n_loads, 0x1234567ull + it, d_sink);
+			if (unroll >= 4) k_gather_probe4<<<prop.multiProcessorCount * 8, 256>>>(d_t, table_bytes / granule, granule / 16, n_loads, 0x1234567ull + it, d_sink);
+			else k_gather_probe<<<prop.multiProcessorCount * 8, 256>>>(d_t, table_bytes / granule, granule / 16, n_loads, 0x1234567ull + it, d_sink);
 			CK(cudaGetLastError());
 			CK(cudaEventRecord(e1));
 			CK(cudaEventSynchronize(e1));

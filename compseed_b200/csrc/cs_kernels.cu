@@ -183,7 +183,7 @@ __global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, ui
 // [entry][thread] layout), the rest spilled to HBM.
 // ---------------------------------------------------------------------------------------------
 enum { ST_FETCH = 0, ST_R1_PIVOT, ST_FWD, ST_BWD_INIT, ST_BWD_SWEEP, ST_BWD_ENTRY, ST_CALL_DONE, ST_R2_NEXT,
-       ST_R3_PIVOT, ST_R3_FWD, ST_READ_DONE };
+       ST_R3_PIVOT, ST_R3_FWD, ST_READ_DONE, ST_IDLE };
 
 __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs a)
 {
@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 	bool pushed = false; uint64_t last_sz = 0;
 	uint64_t min_intv = 1;
 	uint32_t call_nmem = 0; int last_start = 0;
-	int c = 0, is_back = 0;
+	int c = 0;
+	bool need = false;
 	bool err_list = false, err_mem = false;
 
 	auto list_put = [&](int idx, uint4 v) {
@@ -227,26 +228,31 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 		} else err_mem = true;
 		++nmem;
 	};
+	auto set_intv = [&](int b) { // bwt_set_intv, bwt.h:82
+		c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
+	};
 	auto start_call = [&](int pivot, uint64_t mi) { // bwt_smem1a prologue, bwt.c:295-302
 		x = pivot; min_intv = mi < 1 ? 1 : mi;
-		int b = q[x];
-		c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
+		set_intv(q[x]);
 		i = x + 1; n = 0; call_nmem = 0;
 		st = ST_FWD;
 	};
+	// a match [bi+1, cend) ends at this sweep: it is an SMEM only if no longer match survived the
+	// sweep and it is not contained in the previous one (bwt.c:332-336)
+	auto mem_candidate = [&]() {
+		if (call_nmem == 0 || bi + 1 < last_start) {
+			++call_nmem; last_start = bi + 1;
+			if ((int)cend - (bi + 1) >= opt.min_seed_len) emit(c0, c1, c2, (uint32_t)(bi + 1), cend);
+		}
+	};
 
 	for (;;) {
-		bool need = false;
-		while (!need) {
+		// ---- divergent bookkeeping: advance this lane's state machine until it needs an extend ----
+		while (!need && st != ST_IDLE) {
 			switch (st) {
 			case ST_FETCH: {
 				rd = atomicAdd(a.next_read, 1u);
-				if (rd >= a.n_reads) {
-					if (n_ext) atomicAdd(a.counters + 0, n_ext);
-					if (n_call) atomicAdd(a.counters + 1, n_call);
-					if (n_two) atomicAdd(a.counters + 2, n_two);
-					return;
-				}
+				if (rd >= a.n_reads) { st = ST_IDLE; break; }
 				uint32_t o = a.off[rd];
 				q = a.bases + o; len = (int)(a.off[rd + 1] - o);
 				nmem = 0; round = 1; x = 0; err_list = err_mem = false;
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 				break;
 			case ST_FWD: // forward extension, bwt.c:304-321
 				if (i >= len || q[i] > 3) { list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i)); st = ST_BWD_INIT; }
-				else { c = 3 - q[i]; is_back = 0; need = true; }
+				else { c = 3 - q[i]; need = true; }
 				break;
 			case ST_BWD_INIT: // bwt.c:322-326; list[n-1] is the longest match
 				ret = (int)(list_get(n - 1).w >> 16);
@@ -269,11 +275,8 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 			case ST_BWD_SWEEP: { // one value of i in bwt.c:326
 				c = bi < 0 ? -1 : (q[bi] < 4 ? q[bi] : -1);
 				if (c < 0) { // every interval ends here; only the longest can be a new SMEM (bwt.c:331-337)
-					if (call_nmem == 0 || bi + 1 < last_start) {
-						unpack_entry(list_get(n - 1), c0, c1, c2, cend);
-						++call_nmem; last_start = bi + 1;
-						if ((int)cend - (bi + 1) >= opt.min_seed_len) emit(c0, c1, c2, (uint32_t)(bi + 1), cend);
-					}
+					unpack_entry(list_get(n - 1), c0, c1, c2, cend);
+					mem_candidate();
 					st = ST_CALL_DONE;
 				} else { j = n - 1; w = n; pushed = false; st = ST_BWD_ENTRY; }
 			} break;
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 				if (j < lo) {
 					if (!pushed) st = ST_CALL_DONE;
 					else { lo = w; --bi; st = ST_BWD_SWEEP; }
-				} else { unpack_entry(list_get(j), c0, c1, c2, cend); is_back = 1; need = true; }
+				} else { unpack_entry(list_get(j), c0, c1, c2, cend); need = true; }
 				break;
 			case ST_CALL_DONE:
 				if (round == 1) { x = ret; st = ST_R1_PIVOT; } else st = ST_R2_NEXT;
@@ -305,12 +308,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 			case ST_R3_PIVOT: // third pass, bwamem.c:253-268 + bwt_seed_strategy1 prologue bwt.c:363-365
 				while (x < len && q[x] > 3) ++x;
 				if (x >= len) st = ST_READ_DONE;
-				else {
-					int b = q[x];
-					c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
-					i = x + 1;
-					st = ST_R3_FWD;
-				}
+				else { set_intv(q[x]); i = x + 1; st = ST_R3_FWD; }
 				break;
 			case ST_R3_FWD: // bwt.c:366-378
 				if (i >= len) st = ST_READ_DONE;
@@ -318,7 +316,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 				else if (c2 == 0) { // children of an empty interval are empty: no memory access needed
 					++n_ext;
 					if (i - x >= opt.min_seed_len) { x = i + 1; st = ST_R3_PIVOT; } else ++i;
-				} else { c = 3 - q[i]; is_back = 0; need = true; }
+				} else { c = 3 - q[i]; need = true; }
 				break;
 			case ST_READ_DONE: {
 				uint32_t cnt = nmem;
@@ -334,7 +332,16 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 			}
 		}
 
+		// ---- explicit reconvergence: all 32 lanes meet here every trip; nobody leaves early ----
+		if (__all_sync(0xffffffffu, st == ST_IDLE)) break;
+		if (!need) continue;
+
 		// ---- the one convergent, memory-bound step: bwt_extend of (c0,c1,c2) by base c ----
+		const int is_back = (st == ST_BWD_ENTRY);
+		// look-ahead base for the step after this one, fetched together with the Occ sectors
+		const int pf_idx = is_back ? bi - 1 : i + 1;
+		uint32_t nb = 4;
+		if (pf_idx >= 0 && pf_idx < len) nb = q[pf_idx];
 		uint64_t o0, o1, o2; uint32_t two;
 		dev_extend(I, c0, c1, c2, c, is_back, o0, o1, o2, two);
 		++n_ext; ++n_call; n_two += two;
@@ -342,27 +349,41 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 		if (st == ST_FWD) { // bwt.c:311-315
 			if (o2 != c2) {
 				list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i));
-				if (o2 < min_intv) { st = ST_BWD_INIT; continue; }
+				if (o2 < min_intv) { st = ST_BWD_INIT; need = false; }
 			}
-			c0 = o0; c1 = o1; c2 = o2; ++i;
+			if (need) {
+				c0 = o0; c1 = o1; c2 = o2; ++i;
+				if (i >= len || nb > 3) { list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i)); st = ST_BWD_INIT; need = false; }
+				else c = 3 - (int)nb;
+			}
 		} else if (st == ST_BWD_ENTRY) { // bwt.c:331-341
 			if (o2 < min_intv) {
-				if (!pushed && (call_nmem == 0 || bi + 1 < last_start)) {
-					++call_nmem; last_start = bi + 1;
-					if ((int)cend - (bi + 1) >= opt.min_seed_len) emit(c0, c1, c2, (uint32_t)(bi + 1), cend);
-				}
+				if (!pushed) mem_candidate();
 			} else if (!pushed || o2 != last_sz) {
 				list_put(--w, pack_entry(o0, o1, o2, cend));
 				pushed = true; last_sz = o2;
 			}
 			--j;
+			if (j >= lo) unpack_entry(list_get(j), c0, c1, c2, cend);       // next interval of this sweep
+			else if (pushed && bi >= 1 && nb < 4) {                         // next sweep, one base further left
+				lo = w; --bi; c = (int)nb;
+				j = n - 1; w = n; pushed = false;
+				unpack_entry(list_get(j), c0, c1, c2, cend);
+			} else need = false;                                            // ST_BWD_ENTRY finishes the sweep on the slow path
 		} else { // ST_R3_FWD, bwt.c:370-375
 			if (o2 < (uint64_t)opt.max_mem_intv && i - x >= opt.min_seed_len) {
 				if (o2 > 0) emit(o0, o1, o2, (uint32_t)x, (uint32_t)(i + 1));
-				x = i + 1; st = ST_R3_PIVOT;
-			} else { c0 = o0; c1 = o1; c2 = o2; ++i; }
+				x = i + 1; st = ST_R3_PIVOT; need = false;
+			} else {
+				c0 = o0; c1 = o1; c2 = o2; ++i;
+				if (i >= len || nb > 3 || c2 == 0) need = false;              // ST_R3_FWD decides on the slow path
+				else c = 3 - (int)nb;
+			}
 		}
 	}
+	if (n_ext) atomicAdd(a.counters + 0, n_ext);
+	if (n_call) atomicAdd(a.counters + 1, n_call);
+	if (n_two) atomicAdd(a.counters + 2, n_two);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -425,27 +446,47 @@ __global__ void k_collect_rows(CollectArgs a)
 // Measurement helpers
 // ---------------------------------------------------------------------------------------------
 // Independent uniformly random granule-sized loads over a table: the random-sector roofline.
-__global__ void k_gather_probe(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed,
-                               unsigned long long *sink)
+// `unroll` independent loads are issued back to back per thread before any of them is consumed.
+template <int UNROLL>
+__device__ __forceinline__ void gather_body(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads,
+                                            uint64_t seed, unsigned long long *sink)
 {
 	uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	uint64_t s = seed ^ (tid * 0x9E3779B97F4A7C15ull);
 	uint32_t acc = 0;
-	for (uint64_t i = tid; i < n_loads; i += stride) {
-		s ^= s << 13; s ^= s >> 7; s ^= s << 17;            // xorshift64
-		uint64_t g = (uint64_t)(((unsigned __int128)s * n_granules) >> 64);
-		const uint4 *p = table + g * granule16;
-		if (granule16 == 2) {
-			uint64_t a, b, c, d;
-			asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
-			acc += (uint32_t)(a ^ b ^ c ^ d);
-		} else {
-			for (uint32_t j = 0; j < granule16; ++j) { uint4 v = __ldg(p + j); acc += v.x ^ v.y ^ v.z ^ v.w; }
+	for (uint64_t i = tid; i < n_loads; i += stride * UNROLL) {
+		uint64_t a[UNROLL], b[UNROLL], c[UNROLL], d[UNROLL];
+#pragma unroll
+		for (int u = 0; u < UNROLL; ++u) {
+			s ^= s << 13; s ^= s >> 7; s ^= s << 17;            // xorshift64
+			uint64_t g = (uint64_t)(((unsigned __int128)s * n_granules) >> 64);
+			const uint4 *p = table + g * granule16;
+			if (granule16 >= 2) {
+				asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a[u]), "=l"(b[u]), "=l"(c[u]), "=l"(d[u]) : "l"(p));
+				if (granule16 >= 4) { // second sector of a 64-byte granule
+					uint64_t a2, b2, c2, d2;
+					asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a2), "=l"(b2), "=l"(c2), "=l"(d2) : "l"(p + 2));
+					a[u] ^= a2; b[u] ^= b2; c[u] ^= c2; d[u] ^= d2;
+				}
+			} else {
+				uint4 v = __ldg(p);
+				a[u] = v.x; b[u] = v.y; c[u] = v.z; d[u] = v.w;
+			}
 		}
+#pragma unroll
+		for (int u = 0; u < UNROLL; ++u) acc += (uint32_t)(a[u] ^ b[u] ^ c[u] ^ d[u]);
 	}
 	if (acc == 0x12345678u) atomicAdd(sink, 1ull);
 }
+
+__global__ void k_gather_probe(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed,
+                               unsigned long long *sink)
+{ gather_body<1>(table, n_granules, granule16, n_loads, seed, sink); }
+
+__global__ void k_gather_probe4(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed,
+                                unsigned long long *sink)
+{ gather_body<4>(table, n_granules, granule16, n_loads, seed, sink); }
 
 __global__ void k_fill(uint4 *p, uint64_t n, uint32_t v)
 {

@@ -53,4 +53,5 @@ __global__ void k_seed(DevIndex I, SeedArgs a);
 __global__ void k_collect_sort(CollectArgs a);
 __global__ void k_collect_rows(CollectArgs a);
 __global__ void k_gather_probe(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed, unsigned long long *sink);
+__global__ void k_gather_probe4(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed, unsigned long long *sink);
 __global__ void k_fill(uint4 *p, uint64_t n, uint32_t v);

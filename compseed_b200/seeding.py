@@ -90,6 +90,8 @@ def load_library():
     L.cs_seed_batch_fetch.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Result)]
     L.cs_probe_random_gather.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int,
                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.cs_probe_random_gather_ex.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.cs_flush_l2.argtypes = [C.c_int]
     _lib = L
     return L
@@ -373,10 +375,12 @@ def concat_results(parts: list[SeedResult]) -> SeedResult:
                       np.concatenate([p.rbeg for p in parts]), cnt, tuple(ms))
 
 
-def probe_random_gather(device: int = 0, table_bytes: int = 4 << 30, granule: int = 32, n_loads: int = 1 << 28, iters: int = 3):
+def probe_random_gather(device: int = 0, table_bytes: int = 4 << 30, granule: int = 32, n_loads: int = 1 << 28, iters: int = 3,
+                        unroll: int = 1, l2_fetch_granularity: int = 0):
     """(GB/s, Gloads/s) of independent uniformly random granule-sized loads: the random-sector roofline."""
     gb, gl = C.c_double(), C.c_double()
-    _check(load_library().cs_probe_random_gather(device, table_bytes, granule, n_loads, iters, C.byref(gb), C.byref(gl)))
+    _check(load_library().cs_probe_random_gather_ex(device, table_bytes, granule, n_loads, iters, unroll, l2_fetch_granularity,
+                                                    C.byref(gb), C.byref(gl)))
     return gb.value, gl.value
 
 

@@ -152,6 +152,10 @@ int cs_seed_batch_fetch(cs_ctx_t *ctx, int slot, cs_result_t *out);
  * n_loads independent uniformly random `granule`-byte aligned loads (32 or 64) over table_bytes. */
 int cs_probe_random_gather(int device, uint64_t table_bytes, uint32_t granule, uint64_t n_loads, int iters,
                            double *gbytes_per_s, double *gloads_per_s);
+/* Same with `unroll` (1 or 4) independent loads in flight per thread and an optional
+ * cudaLimitMaxL2FetchGranularity (0 = leave as is, else 32 / 64 / 128). */
+int cs_probe_random_gather_ex(int device, uint64_t table_bytes, uint32_t granule, uint64_t n_loads, int iters, int unroll,
+                              int l2_fetch_granularity, double *gbytes_per_s, double *gloads_per_s);
 /* Writes a buffer larger than L2 (flush between timed iterations). */
 int cs_flush_l2(int device);
 
