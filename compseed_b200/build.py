@@ -8,7 +8,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
-LIB = os.path.join(LIB_DIR, "libcompseed_b200.so")
+# experiment builds: CS_DEFS="-DCS_LIST_SMEM=12 -DCS_SEED_MINBLOCKS=4" CS_TAG=e12b4 python -m compseed_b200.build
+TAG = os.environ.get("CS_TAG", "")
+EXTRA_DEFS = os.environ.get("CS_DEFS", "").split()
+LIB = os.path.join(LIB_DIR, f"libcompseed_b200{('_' + TAG) if TAG else ''}.so")
 SOURCES = ["cs_kernels.cu", "cs_api.cu", "cs_index_build.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr", "-rdc=false"]
@@ -30,8 +33,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(LIB_DIR, src.replace(".cu", (("_" + TAG) if TAG else "") + ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_DEFS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

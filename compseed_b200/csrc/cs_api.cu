@@ -316,7 +316,7 @@ struct Ctrl { // zeroed before every run; copied back after it
 
 struct Slot {
 	cudaStream_t stream;
-	cudaEvent_t ev[5];   // slot start, seed start, seed end, collect end, sa end
+	cudaEvent_t ev[6];   // slot start, seed start, seed end, collect end, sa end, k_seed end (k_seed_r3 runs after it)
 	cudaEvent_t ev_done;
 	// pinned host
 	uint8_t *h_bases; uint32_t *h_off;
@@ -330,6 +330,8 @@ struct Slot {
 	uint64_t *d_read_pool_off;
 	uint32_t *d_read_n_mems, *d_mem_off, *d_read_n_seeds, *d_seed_off;
 	uint64_t *d_rows;
+	cs_mem_t *d_r3_mems; uint64_t r3_cap;   // third-pass seeds, read r at off[r]/(k+1) + r
+	uint32_t *d_r3_n_mems, *d_tot_n_mems;
 	void *d_scan_tmp; size_t scan_tmp_bytes;
 	// state
 	int state;           // 0 idle, 1 staged, 2 running, 3 done (results on device)
@@ -343,6 +345,7 @@ struct cs_ctx {
 	uint64_t max_bases, max_mems, max_seeds;
 	int n_slots;
 	int grid;             // CTAs of k_seed
+	int grid_r3;          // CTAs of k_seed_r3
 	uint32_t mem_cap, spill_cap;
 	Slot *slots;
 };
@@ -350,12 +353,13 @@ struct cs_ctx {
 static void slot_free(Slot *s)
 {
 	if (s->stream) cudaStreamDestroy(s->stream);
-	for (int i = 0; i < 5; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+	for (int i = 0; i < 6; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
 	if (s->ev_done) cudaEventDestroy(s->ev_done);
 	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
 	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
 	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
 	cudaFree(s->d_pool); cudaFree(s->d_mems); cudaFree(s->d_read_pool_off); cudaFree(s->d_read_n_mems);
+	cudaFree(s->d_r3_mems); cudaFree(s->d_r3_n_mems); cudaFree(s->d_tot_n_mems);
 	cudaFree(s->d_mem_off); cudaFree(s->d_read_n_seeds); cudaFree(s->d_seed_off); cudaFree(s->d_rows); cudaFree(s->d_scan_tmp);
 }
 
@@ -395,6 +399,10 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		ctx->grid = idx->n_sm * per_sm;
 		uint32_t need = (max_reads + CS_SEED_BLOCK - 1) / CS_SEED_BLOCK;
 		if ((uint32_t)ctx->grid > need) ctx->grid = (int)need;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed_r3, 256, 0));
+		if (per_sm < 1) per_sm = 1;
+		ctx->grid_r3 = idx->n_sm * per_sm;
+		if ((uint32_t)ctx->grid_r3 > need) ctx->grid_r3 = (int)need;
 	}
 	ctx->mem_cap = std::min<uint32_t>(2 * max_read_len + 16, 4096);
 	ctx->spill_cap = max_read_len > CS_LIST_SMEM ? max_read_len - CS_LIST_SMEM + 1 : 1;
@@ -402,7 +410,7 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		Slot *s = &ctx->slots[i];
 		const size_t nthreads = (size_t)ctx->grid * CS_SEED_BLOCK;
 		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-		for (int e = 0; e < 5; ++e) CK(cudaEventCreate(&s->ev[e]));
+		for (int e = 0; e < 6; ++e) CK(cudaEventCreate(&s->ev[e]));
 		CK(cudaEventCreate(&s->ev_done));
 		CK(cudaMallocHost(&s->h_bases, max_bases));
 		CK(cudaMallocHost(&s->h_off, ((size_t)max_reads + 1) * 4));
@@ -420,6 +428,10 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		CK(cudaMalloc(&s->d_read_n_seeds, ((size_t)max_reads + 1) * 4));
 		CK(cudaMalloc(&s->d_seed_off, ((size_t)max_reads + 1) * 4));
 		CK(cudaMalloc(&s->d_rows, ctx->max_seeds * 8));
+		s->r3_cap = max_bases / 16 + max_reads + 1;   // enough for min_seed_len >= 15; grown on demand in enqueue_run
+		CK(cudaMalloc(&s->d_r3_mems, s->r3_cap * sizeof(cs_mem_t)));
+		CK(cudaMalloc(&s->d_r3_n_mems, ((size_t)max_reads + 1) * 4));
+		CK(cudaMalloc(&s->d_tot_n_mems, ((size_t)max_reads + 1) * 4));
 		s->scan_tmp_bytes = 0;
 		CK(cub::DeviceScan::ExclusiveSum(nullptr, s->scan_tmp_bytes, s->d_read_n_mems, s->d_mem_off, (int)max_reads + 1, s->stream));
 		CK(cudaMalloc(&s->d_scan_tmp, s->scan_tmp_bytes + 256));
@@ -447,7 +459,17 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt)
 	if (grid < 1) grid = 1;
 	SeedArgs a;
 	CollectArgs c;
+	const bool pass3 = opt->max_mem_intv > 0;
 	s->opt = *opt;
+	if (pass3) { // third-pass seeds of read r live at off[r]/(k+1) + r: at most bases/(k+1) + n entries
+		uint64_t need3 = (uint64_t)s->h_off[n] / ((uint32_t)opt->min_seed_len + 1) + n + 1;
+		if (need3 > s->r3_cap) {
+			CK(cudaStreamSynchronize(s->stream));
+			CK(cudaFree(s->d_r3_mems)); s->d_r3_mems = nullptr; s->r3_cap = 0;
+			CK(cudaMalloc(&s->d_r3_mems, need3 * sizeof(cs_mem_t)));
+			s->r3_cap = need3;
+		}
+	}
 	CK(cudaMemsetAsync(s->d_ctrl, 0, sizeof(Ctrl), s->stream));
 	CK(cudaEventRecord(s->ev[1], s->stream));
 	a.bases = s->d_bases; a.off = s->d_off; a.n_reads = n; a.opt = *opt;
@@ -456,16 +478,26 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt)
 	a.spill = s->d_spill; a.spill_cap = ctx->spill_cap;
 	a.pool = s->d_pool; a.pool_cap = ctx->max_mems; a.pool_used = &s->d_ctrl->pool_used;
 	a.read_pool_off = s->d_read_pool_off; a.read_n_mems = s->d_read_n_mems;
+	a.r3_mems = s->d_r3_mems; a.r3_n_mems = s->d_r3_n_mems;
 	a.counters = s->d_ctrl->counters; a.error = &s->d_ctrl->error;
-	// the spill stride must match the launched grid
+	// passes 1-2 (the spill stride inside the kernel follows the launched grid), then pass 3
 	k_seed<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
 	CK(cudaGetLastError());
+	CK(cudaEventRecord(s->ev[5], s->stream));
+	if (pass3) {
+		int g3 = std::min<int>(ctx->grid_r3, (int)((n + 255) / 256));
+		k_seed_r3<<<g3 < 1 ? 1 : g3, 256, 0, s->stream>>>(idx->d, a);
+		CK(cudaGetLastError());
+	}
 	CK(cudaEventRecord(s->ev[2], s->stream));
 	// collect: offsets, sort, SA rows
-	CK(cudaMemsetAsync(s->d_read_n_mems + n, 0, 4, s->stream));
-	CK(cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, s->scan_tmp_bytes, s->d_read_n_mems, s->d_mem_off, (int)n + 1, s->stream));
+	k_mem_counts<<<std::min<int>(idx->n_sm * 8, (int)((n + 255) / 256)), 256, 0, s->stream>>>(s->d_read_n_mems, pass3 ? s->d_r3_n_mems : nullptr, n, s->d_tot_n_mems);
+	CK(cudaGetLastError());
+	CK(cudaMemsetAsync(s->d_tot_n_mems + n, 0, 4, s->stream));
+	CK(cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, s->scan_tmp_bytes, s->d_tot_n_mems, s->d_mem_off, (int)n + 1, s->stream));
 	c.n_reads = n; c.opt = *opt; c.pool = s->d_pool; c.read_pool_off = s->d_read_pool_off; c.read_n_mems = s->d_read_n_mems;
-	c.mem_off = s->d_mem_off; c.mems = s->d_mems; c.read_n_seeds = s->d_read_n_seeds; c.seed_off = s->d_seed_off;
+	c.off = s->d_off; c.r3_mems = s->d_r3_mems; c.r3_n_mems = pass3 ? s->d_r3_n_mems : nullptr;
+	c.mem_off = s->d_mem_off; c.mems = s->d_mems; c.mems_cap = ctx->max_mems; c.read_n_seeds = s->d_read_n_seeds; c.seed_off = s->d_seed_off;
 	c.seed_rows = s->d_rows; c.seed_cap = ctx->max_seeds; c.error = &s->d_ctrl->error;
 	{
 		int cgrid = (int)std::min<uint64_t>(((uint64_t)n * 32 + 255) / 256, (uint64_t)idx->n_sm * 16);
@@ -496,7 +528,7 @@ static int finish_run(cs_ctx *ctx, Slot *s)
 {
 	CK(cudaStreamSynchronize(s->stream));
 	s->state = 3;
-	if (s->h_ctrl->error != 0 || s->h_ctrl->pool_used > ctx->max_mems || s->h_ctrl->n_seeds > ctx->max_seeds)
+	if (s->h_ctrl->error != 0 || s->h_ctrl->pool_used > ctx->max_mems || s->h_ctrl->n_mems > ctx->max_mems || s->h_ctrl->n_seeds > ctx->max_seeds)
 		return set_err(CS_E_OVERFLOW, "result buffers too small for this batch: mems %llu of %llu, seeds %llu of %llu "
 		               "(or a read needed more than %u mems / %u list entries); re-create the ctx with larger max_mems/max_seeds",
 		               (unsigned long long)s->h_ctrl->pool_used, (unsigned long long)ctx->max_mems,
@@ -521,6 +553,8 @@ static void fill_result(cs_ctx *ctx, Slot *s, cs_result_t *out, bool host_ptrs)
 	cudaEventElapsedTime(&out->kernel_ms[1], s->ev[2], s->ev[3]);
 	cudaEventElapsedTime(&out->kernel_ms[2], s->ev[3], s->ev[4]);
 	cudaEventElapsedTime(&out->kernel_ms[3], s->ev[0], s->ev_done);
+	cudaEventElapsedTime(&out->kernel_ms[4], s->ev[1], s->ev[5]);
+	cudaEventElapsedTime(&out->kernel_ms[5], s->ev[5], s->ev[2]);
 	(void)ctx;
 }
 

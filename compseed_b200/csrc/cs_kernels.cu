@@ -183,9 +183,9 @@ __global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, ui
 // [entry][thread] layout), the rest spilled to HBM.
 // ---------------------------------------------------------------------------------------------
 enum { ST_FETCH = 0, ST_R1_PIVOT, ST_FWD, ST_BWD_INIT, ST_BWD_SWEEP, ST_BWD_ENTRY, ST_CALL_DONE, ST_R2_NEXT,
-       ST_R3_PIVOT, ST_R3_FWD, ST_READ_DONE, ST_IDLE };
+       ST_READ_DONE, ST_IDLE };
 
-__global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs a)
+__global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIndex I, SeedArgs a)
 {
 	extern __shared__ uint4 s_list[];
 	const int t = threadIdx.x;
@@ -289,9 +289,8 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 			case ST_CALL_DONE:
 				if (round == 1) { x = ret; st = ST_R1_PIVOT; } else st = ST_R2_NEXT;
 				break;
-			case ST_R2_NEXT: { // second pass, bwamem.c:238-249
-				st = opt.max_mem_intv > 0 ? ST_R3_PIVOT : ST_READ_DONE;
-				x = 0;
+			case ST_R2_NEXT: { // second pass, bwamem.c:238-249 (the third pass runs in k_seed_r3)
+				st = ST_READ_DONE;
 				uint32_t lim = old_n < a.mem_cap ? old_n : a.mem_cap;
 				while (r2k < lim) {
 					const uint4 *p = reinterpret_cast<const uint4*>(my + r2k);
@@ -305,19 +304,6 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 					break;
 				}
 			} break;
-			case ST_R3_PIVOT: // third pass, bwamem.c:253-268 + bwt_seed_strategy1 prologue bwt.c:363-365
-				while (x < len && q[x] > 3) ++x;
-				if (x >= len) st = ST_READ_DONE;
-				else { set_intv(q[x]); i = x + 1; st = ST_R3_FWD; }
-				break;
-			case ST_R3_FWD: // bwt.c:366-378
-				if (i >= len) st = ST_READ_DONE;
-				else if (q[i] > 3) { x = i + 1; st = ST_R3_PIVOT; }
-				else if (c2 == 0) { // children of an empty interval are empty: no memory access needed
-					++n_ext;
-					if (i - x >= opt.min_seed_len) { x = i + 1; st = ST_R3_PIVOT; } else ++i;
-				} else { c = 3 - q[i]; need = true; }
-				break;
 			case ST_READ_DONE: {
 				uint32_t cnt = nmem;
 				if (err_mem || err_list) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
@@ -346,7 +332,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 		dev_extend(I, c0, c1, c2, c, is_back, o0, o1, o2, two);
 		++n_ext; ++n_call; n_two += two;
 
-		if (st == ST_FWD) { // bwt.c:311-315
+		if (!is_back) { // ST_FWD, bwt.c:311-315
 			if (o2 != c2) {
 				list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i));
 				if (o2 < min_intv) { st = ST_BWD_INIT; need = false; }
@@ -356,7 +342,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 				if (i >= len || nb > 3) { list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i)); st = ST_BWD_INIT; need = false; }
 				else c = 3 - (int)nb;
 			}
-		} else if (st == ST_BWD_ENTRY) { // bwt.c:331-341
+		} else { // ST_BWD_ENTRY, bwt.c:331-341
 			if (o2 < min_intv) {
 				if (!pushed) mem_candidate();
 			} else if (!pushed || o2 != last_sz) {
@@ -370,20 +356,79 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, 3) k_seed(DevIndex I, SeedArgs 
 				j = n - 1; w = n; pushed = false;
 				unpack_entry(list_get(j), c0, c1, c2, cend);
 			} else need = false;                                            // ST_BWD_ENTRY finishes the sweep on the slow path
-		} else { // ST_R3_FWD, bwt.c:370-375
-			if (o2 < (uint64_t)opt.max_mem_intv && i - x >= opt.min_seed_len) {
-				if (o2 > 0) emit(o0, o1, o2, (uint32_t)x, (uint32_t)(i + 1));
-				x = i + 1; st = ST_R3_PIVOT; need = false;
-			} else {
-				c0 = o0; c1 = o1; c2 = o2; ++i;
-				if (i >= len || nb > 3 || c2 == 0) need = false;              // ST_R3_FWD decides on the slow path
-				else c = 3 - (int)nb;
-			}
 		}
 	}
 	if (n_ext) atomicAdd(a.counters + 0, n_ext);
 	if (n_call) atomicAdd(a.counters + 1, n_call);
 	if (n_two) atomicAdd(a.counters + 2, n_two);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Third pass ("LAST-like", bwamem.c:253-268 + bwt_seed_strategy1, bwt.c:358-379) as its own kernel:
+// forward-only chains with no interval lists, so it needs no shared memory and few registers and
+// runs at full occupancy.  It is independent of passes 1-2; the collect pass merges and sorts.
+// Read r may emit at most len/(min_seed_len+1) seeds; they go to r3_mems[off[r]/(k+1) + r ...].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4) k_seed_r3(DevIndex I, SeedArgs a)
+{
+	const cs_seed_opt_t opt = a.opt;
+	const uint32_t kp1 = (uint32_t)opt.min_seed_len + 1;
+	unsigned long long n_ext = 0, n_call = 0;
+	bool idle = false, need = false;
+	uint32_t rd = 0, nmem = 0; int len = 0, x = 0, i = 0, c = 0;
+	const uint8_t *q = nullptr;
+	cs_mem_t *out = nullptr;
+	uint64_t c0 = 0, c1 = 0, c2 = 0;
+	bool have_read = false;
+
+	for (;;) {
+		while (!need && !idle) {
+			if (!have_read) {
+				rd = atomicAdd(a.next_read + 1, 1u);
+				if (rd >= a.n_reads) { idle = true; break; }
+				uint32_t o = a.off[rd];
+				q = a.bases + o; len = (int)(a.off[rd + 1] - o);
+				out = a.r3_mems + ((uint64_t)(o / kp1) + rd);
+				nmem = 0; x = 0; i = 0; have_read = true;
+			}
+			if (i <= x) { // need a new pivot
+				while (x < len && q[x] > 3) ++x;
+				if (x >= len) { a.r3_n_mems[rd] = nmem; have_read = false; continue; }
+				int b = q[x];
+				c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
+				i = x + 1;
+			}
+			// bwt.c:366-378
+			if (i >= len) { a.r3_n_mems[rd] = nmem; have_read = false; }
+			else if (q[i] > 3) { x = i + 1; i = 0; }
+			else if (c2 == 0) { // children of an empty interval are empty: no memory access needed
+				++n_ext;
+				if (i - x >= opt.min_seed_len) { x = i + 1; i = 0; } else ++i;
+			} else { c = 3 - q[i]; need = true; }
+		}
+		if (__all_sync(0xffffffffu, idle)) break;
+		if (!need) continue;
+		uint32_t nb = 4;
+		if (i + 1 < len) nb = q[i + 1];
+		uint64_t o0, o1, o2; uint32_t two;
+		dev_extend(I, c0, c1, c2, c, 0, o0, o1, o2, two);
+		++n_ext; ++n_call;
+		if (o2 < (uint64_t)opt.max_mem_intv && i - x >= opt.min_seed_len) { // bwt.c:370-374
+			if (o2 > 0) {
+				uint4 *p = reinterpret_cast<uint4*>(out + nmem);
+				p[0] = make_uint4((uint32_t)o0, (uint32_t)(o0 >> 32), (uint32_t)o1, (uint32_t)(o1 >> 32));
+				p[1] = make_uint4((uint32_t)o2, (uint32_t)(o2 >> 32), (uint32_t)(i + 1), (uint32_t)x);
+				++nmem;
+			}
+			x = i + 1; i = 0; need = false;
+		} else {
+			c0 = o0; c1 = o1; c2 = o2; ++i;
+			if (i >= len || nb > 3 || c2 == 0) need = false;
+			else c = 3 - (int)nb;
+		}
+	}
+	if (n_ext) atomicAdd(a.counters + 0, n_ext);
+	if (n_call) atomicAdd(a.counters + 1, n_call);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -400,18 +445,26 @@ __global__ void k_collect_sort(CollectArgs a)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	const uint32_t kp1 = (uint32_t)a.opt.min_seed_len + 1;
 	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.n_reads; r += nwarps) {
-		const uint32_t n = a.read_n_mems[r];
-		const cs_mem_t *src = a.pool + a.read_pool_off[r];
+		const uint32_t n12 = a.read_n_mems[r];                 // passes 1-2 (k_seed)
+		const uint32_t n3 = a.r3_n_mems ? a.r3_n_mems[r] : 0;  // pass 3 (k_seed_r3)
+		const uint32_t n = n12 + n3;
+		const cs_mem_t *src12 = a.pool + a.read_pool_off[r];
+		const cs_mem_t *src3 = a.r3_mems + ((uint64_t)(a.off[r] / kp1) + r);
 		cs_mem_t *dst = a.mems + a.mem_off[r];
 		uint32_t n_seeds = 0;
+		if ((uint64_t)a.mem_off[r] + n > a.mems_cap) { // result buffer too small: report, never write past it
+			if (lane == 0) { atomicExch(a.error, CS_E_OVERFLOW); a.read_n_seeds[r] = 0; }
+			continue;
+		}
 		for (uint32_t m = lane; m < n; m += 32) {
-			const uint4 *p = reinterpret_cast<const uint4*>(src + m);
+			const uint4 *p = reinterpret_cast<const uint4*>(m < n12 ? src12 + m : src3 + (m - n12));
 			uint4 v0 = p[0], v1 = p[1];
 			uint64_t info = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
 			uint32_t rank = 0;
 			for (uint32_t o = 0; o < n; ++o) {
-				uint64_t oi = src[o].info;
+				uint64_t oi = o < n12 ? src12[o].info : src3[o - n12].info;
 				rank += (oi < info) || (oi == info && o < m);
 			}
 			uint4 *d = reinterpret_cast<uint4*>(dst + rank);
@@ -423,6 +476,13 @@ __global__ void k_collect_sort(CollectArgs a)
 	}
 }
 
+// total mems per read (passes 1-2 + pass 3), the input of the offsets scan
+__global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, uint32_t n_reads, uint32_t *out)
+{
+	for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x)
+		out[r] = n12[r] + (n3 ? n3[r] : 0);
+}
+
 __global__ void k_collect_rows(CollectArgs a)
 {
 	const uint32_t lane = threadIdx.x & 31;
@@ -431,7 +491,10 @@ __global__ void k_collect_rows(CollectArgs a)
 		const uint32_t n = a.mem_off[r + 1] - a.mem_off[r];
 		const cs_mem_t *mem = a.mems + a.mem_off[r];
 		uint64_t o = a.seed_off[r];
-		if ((uint64_t)a.seed_off[r + 1] > a.seed_cap) { if (lane == 0) atomicExch(a.error, CS_E_OVERFLOW); continue; }
+		if ((uint64_t)a.seed_off[r + 1] > a.seed_cap || (uint64_t)a.mem_off[r + 1] > a.mems_cap) {
+			if (lane == 0) atomicExch(a.error, CS_E_OVERFLOW);
+			continue;
+		}
 		for (uint32_t m = 0; m < n; ++m) {
 			uint64_t x0 = mem[m].x[0], x2 = mem[m].x[2];
 			uint32_t cnt = seeds_of(x2, a.opt.max_occ);

@@ -4,7 +4,12 @@
 #include "../../include/compseed_b200.h"
 
 #define CS_SEED_BLOCK   256     // threads per CTA of the seeding kernel
+#ifndef CS_LIST_SMEM
 #define CS_LIST_SMEM    16      // interval-list entries per thread kept in shared memory
+#endif
+#ifndef CS_SEED_MINBLOCKS
+#define CS_SEED_MINBLOCKS 3     // CTAs per SM the register allocation of k_seed is tuned for
+#endif
 
 struct SeedArgs {
 	const uint8_t *bases;       // nt4 codes, concatenated
@@ -12,7 +17,7 @@ struct SeedArgs {
 	uint32_t n_reads;
 	cs_seed_opt_t opt;
 	// scratch
-	uint32_t *next_read;        // work counter
+	uint32_t *next_read;        // work counters: [0] k_seed, [1] k_seed_r3
 	cs_mem_t *thread_mems;      // [n_threads][mem_cap] per-thread mem list of the read in flight
 	uint32_t mem_cap;
 	uint4 *spill;               // [spill_cap][n_threads] interval-list entries beyond CS_LIST_SMEM
@@ -23,6 +28,8 @@ struct SeedArgs {
 	unsigned long long *pool_used;
 	uint64_t *read_pool_off;    // [n_reads] where the read's mems start in pool
 	uint32_t *read_n_mems;      // [n_reads]
+	cs_mem_t *r3_mems;          // third-pass seeds of read r at [off[r]/(k+1) + r ...]
+	uint32_t *r3_n_mems;        // [n_reads]
 	unsigned long long *counters; // [0] ext queries [1] ext calls (bucket path) [2] two-sector extends
 	int *error;                 // sticky CS_E_* code
 };
@@ -33,8 +40,12 @@ struct CollectArgs {
 	const cs_mem_t *pool;
 	const uint64_t *read_pool_off;
 	const uint32_t *read_n_mems;
-	const uint32_t *mem_off;    // exclusive scan of read_n_mems, n_reads + 1
+	const uint32_t *off;        // read offsets (locates the third-pass seeds)
+	const cs_mem_t *r3_mems;
+	const uint32_t *r3_n_mems;  // NULL when the third pass is disabled (max_mem_intv == 0)
+	const uint32_t *mem_off;    // exclusive scan of the per-read totals, n_reads + 1
 	cs_mem_t *mems;             // sorted output
+	uint64_t mems_cap;
 	uint32_t *read_n_seeds;     // [n_reads]
 	const uint32_t *seed_off;   // exclusive scan of read_n_seeds (for pass 2)
 	uint64_t *seed_rows;        // [n_seeds] SA rows in emission order (pass 2), resolved in place by k_sa_resolve
@@ -50,6 +61,8 @@ __global__ void k_probe_extend(DevIndex I, uint32_t n, const uint64_t *ik, const
 __global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, uint64_t *rows_inout, unsigned long long *work,
                              unsigned long long *lf_steps);
 __global__ void k_seed(DevIndex I, SeedArgs a);
+__global__ void k_seed_r3(DevIndex I, SeedArgs a);
+__global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, uint32_t n_reads, uint32_t *out);
 __global__ void k_collect_sort(CollectArgs a);
 __global__ void k_collect_rows(CollectArgs a);
 __global__ void k_gather_probe(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed, unsigned long long *sink);

@@ -21,7 +21,9 @@ import numpy as np
 from . import synth
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libcompseed_b200.so")
+# COMPSEED_LIB_TAG selects an experiment build of the same sources (see build.py); default: the product library
+_TAG = os.environ.get("COMPSEED_LIB_TAG", "")
+LIB_PATH = os.path.join(_HERE, "_lib", f"libcompseed_b200{('_' + _TAG) if _TAG else ''}.so")
 
 CS_OK, CS_E_ARG, CS_E_CUDA, CS_E_OVERFLOW, CS_E_IO, CS_E_NODEVICE, CS_E_STATE = 0, -1, -2, -3, -4, -5, -6
 
@@ -50,7 +52,7 @@ class _Result(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_mems", C.c_uint64), ("n_seeds", C.c_uint64),
                 ("mem_off", C.POINTER(C.c_uint32)), ("mems", C.POINTER(C.c_uint64)),
                 ("seed_off", C.POINTER(C.c_uint32)), ("rbeg", C.POINTER(C.c_int64)),
-                ("counters", _Counters), ("kernel_ms", C.c_float * 4)]
+                ("counters", _Counters), ("kernel_ms", C.c_float * 6)]
 
 
 _lib = None
@@ -136,7 +138,7 @@ class SeedResult:
     seed_off: np.ndarray     # u32 [n+1]
     rbeg: np.ndarray         # i64 [n_seeds]
     counters: dict = field(default_factory=dict)
-    kernel_ms: tuple = (0.0, 0.0, 0.0, 0.0)
+    kernel_ms: tuple = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
 
     @property
     def n_reads(self) -> int:
@@ -362,7 +364,7 @@ def concat_results(parts: list[SeedResult]) -> SeedResult:
     seed_off = [np.zeros(1, dtype=np.uint32)]
     mb = sb = 0
     cnt: dict = {}
-    ms = [0.0, 0.0, 0.0, 0.0]
+    ms = [0.0] * 6
     for p in parts:
         mem_off.append((p.mem_off[1:].astype(np.int64) + mb).astype(np.uint32))
         seed_off.append((p.seed_off[1:].astype(np.int64) + sb).astype(np.uint32))

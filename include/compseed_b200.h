@@ -91,7 +91,8 @@ typedef struct {
 	const uint32_t *seed_off;  /* [n_reads+1] */
 	const int64_t  *rbeg;      /* [n_seeds] SA[x0 + k*step] in the emission order of bwamem.c:386-399 */
 	cs_counters_t counters;
-	float kernel_ms[4];        /* CUDA-event durations on the slot's stream: seed, collect, SA-resolve, whole slot (incl. copies) */
+	float kernel_ms[6];        /* CUDA-event durations on the slot's stream: [0] seeding (k_seed + k_seed_r3), [1] collect,
+	                              [2] SA-resolve, [3] whole slot incl. copies, [4] k_seed alone, [5] k_seed_r3 alone */
 } cs_result_t;
 
 typedef struct cs_index cs_index_t;

@@ -310,6 +310,22 @@ static inline void set_intv(const cso_index_t *idx, int c, cso_mem_t *ik) /* bwt
 	ik->x[0] = idx->L2[c] + 1; ik->x[2] = idx->L2[c + 1] - idx->L2[c]; ik->x[1] = idx->L2[3 - c] + 1; ik->info = 0;
 }
 
+/* optional profiling histogram (env CSO_HIST=1): extends by [round][direction][length of the extended string] */
+static int64_t g_hist[3][2][64];
+static int g_hist_on = -1;
+void cso_hist_get(int64_t *out) { memcpy(out, g_hist, sizeof g_hist); }
+void cso_hist_reset(void) { memset(g_hist, 0, sizeof g_hist); }
+
+static inline void counted_extend_len(work_t *w, const cso_mem_t *ik, uint64_t ok[4][3], int is_back, int new_len)
+{
+	if (g_hist_on < 0) g_hist_on = getenv("CSO_HIST") != 0;
+	if (g_hist_on) __atomic_fetch_add(&g_hist[w->round][is_back][new_len < 63 ? new_len : 63], 1, __ATOMIC_RELAXED);
+	++w->cnt[CSO_CNT_EXT];
+	++w->cnt[CSO_CNT_EXT_R1 + w->round];
+	w->cnt[CSO_CNT_EXT2] += ext_two_buckets(w->idx, ik->x, is_back);
+	cso_extend(w->idx, ik->x, ok, is_back);
+}
+
 static inline void counted_extend(work_t *w, const cso_mem_t *ik, uint64_t ok[4][3], int is_back)
 {
 	++w->cnt[CSO_CNT_EXT];
@@ -338,7 +354,7 @@ static int smem1(work_t *w, int len, const uint8_t *q, int x, uint64_t min_intv)
 	for (i = x + 1; i < len; ++i) { /* forward: record the interval every time its size changes */
 		if (q[i] < 4) {
 			c = 3 - q[i];
-			counted_extend(w, &ik, ok, 0);
+			counted_extend_len(w, &ik, ok, 0, i - x + 1);
 			if (ok[c][2] != ik.x[2]) {
 				memv_push(curr, &ik);
 				if (ok[c][2] < min_intv) break;
@@ -358,7 +374,7 @@ static int smem1(work_t *w, int len, const uint8_t *q, int x, uint64_t min_intv)
 		c = i < 0 ? -1 : q[i] < 4 ? q[i] : -1;
 		for (j = 0, curr->n = 0; j < prev->n; ++j) {
 			cso_mem_t *p = &prev->a[j];
-			if (c >= 0) counted_extend(w, p, ok, 1);
+			if (c >= 0) counted_extend_len(w, p, ok, 1, (int)(uint32_t)p->info - i);
 			if (c < 0 || ok[c][2] < min_intv) {
 				if (curr->n == 0) { /* no longer match survived this sweep */
 					if (mem->n == 0 || (uint64_t)(i + 1) < mem->a[mem->n - 1].info >> 32) {
