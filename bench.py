@@ -327,7 +327,7 @@ def main():
     achieved = seed_bytes_per_read * n_reads / (seed_ms_per_launch * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_seed_traffic.json"))).get("dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_seed_traffic.json")))["dram_bytes_per_read"] * n_reads
     except Exception:
         pass
     roofline = {"kernel": "k_seed", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
