@@ -1,0 +1,24 @@
+/* Reference-side binding of compseed_b200: the five calls a maintainer adds to mapping/bwamem.c
+ * (integration/build_bwamem_gpu.sh applies them to a scratch copy). */
+#ifndef CS_SHIM_H
+#define CS_SHIM_H
+#include <stdint.h>
+#include "FM_index/bwt.h"
+#include "mapping/bwamem.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* bwamem.c:1343, before kt_for(worker1): seed the whole -K batch on the GPU */
+void csgpu_seed_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const bseq1_t *seqs);
+/* bwamem.c:1299-1305, worker1: which read the calling thread is about to align */
+void csgpu_set_read(int i);
+/* bwamem.c:373, replaces mem_collect_intv(opt, bwt, len, seq, aux, tid): aux->mem = sorted mems of the read */
+void csgpu_fill_mems(bwtintv_v *mem);
+/* bwamem.c:398, replaces bwt_sa(bwt, p->x[0] + k): next resolved position in emission order */
+int64_t csgpu_next_rbeg(void);
+void csgpu_destroy(void);
+#ifdef __cplusplus
+}
+#endif
+#endif
