@@ -52,6 +52,7 @@ struct cs_index {
 	DevIndex d;
 	uint4 *d_buckets;
 	uint64_t *d_sa;
+	uint4 *d_kt;            // top-of-search table (depths 1..d.kt_depth)
 	uint64_t bytes;
 	uint64_t bwt_size_ref;  // words of the reference layout
 	int sa_intv;
@@ -59,6 +60,36 @@ struct cs_index {
 };
 
 static int log2_exact(uint64_t v) { int s = 0; while ((1ull << s) < v) ++s; return (1ull << s) == v ? s : -1; }
+
+// Top-of-search table (cs_device.cuh): depth chosen so that the deepest level still has ~64 rows per
+// entry (deeper levels cost HBM without saving sector reads: k and l already share a bucket there).
+// CS_KMER_TABLE_DEPTH overrides (0 disables).
+static int build_kmer_table(cs_index *idx)
+{
+	int depth = 0;
+	const char *env = getenv("CS_KMER_TABLE_DEPTH");
+	while (depth < 13 && (idx->d.seq_len >> (2 * (depth + 1))) >= 64) ++depth;
+	if (env) depth = atoi(env);
+	if (depth < 0) depth = 0;
+	if (depth > 15) depth = 15;
+	idx->d.kt = nullptr; idx->d.kt_depth = 0; idx->d_kt = nullptr;
+	if (depth == 0) return CS_OK;
+	uint64_t entries = ((1ull << (2 * (depth + 1))) - 4) / 3;
+	CK(cudaMalloc(&idx->d_kt, entries * sizeof(uint4)));
+	for (int d = 1; d <= depth; ++d) {
+		uint64_t n_parent = 1ull << (2 * (d - 1));
+		int grid = (int)std::min<uint64_t>((n_parent + 255) / 256, (uint64_t)idx->n_sm * 16);
+		k_kt_build<<<grid, 256>>>(idx->d, idx->d_kt, (uint32_t)d);
+		CK(cudaGetLastError());
+	}
+	CK(cudaDeviceSynchronize());
+	idx->d.kt = idx->d_kt; idx->d.kt_depth = (uint32_t)depth;
+	idx->bytes += entries * sizeof(uint4);
+	return CS_OK;
+fail:
+	if (idx->d_kt) { cudaFree(idx->d_kt); idx->d_kt = nullptr; }
+	return CS_E_CUDA;
+}
 
 // replaces the device SA by one sampled every new_intv rows
 static int resample_sa(cs_index *idx, int new_intv)
@@ -121,10 +152,11 @@ extern "C" cs_index_t *cs_index_upload(const cs_bwt_view_t *v, int device, int d
 	idx->bytes = idx->d.n_buckets * 32 + v->n_sa * 8;
 	if (dense_sa_intv > 0 && dense_sa_intv < v->sa_intv)
 		if (resample_sa(idx, dense_sa_intv) != CS_OK) goto fail;
+	if (build_kmer_table(idx) != CS_OK) goto fail;
 	return idx;
 fail:
 	if (d_src) cudaFree(d_src);
-	if (idx) { if (idx->d_buckets) cudaFree(idx->d_buckets); if (idx->d_sa) cudaFree(idx->d_sa); free(idx); }
+	if (idx) { if (idx->d_buckets) cudaFree(idx->d_buckets); if (idx->d_sa) cudaFree(idx->d_sa); if (idx->d_kt) cudaFree(idx->d_kt); free(idx); }
 	return nullptr;
 }
 
@@ -219,7 +251,7 @@ extern "C" void cs_index_free(cs_index_t *idx)
 {
 	if (!idx) return;
 	cudaSetDevice(idx->device);
-	cudaFree(idx->d_buckets); cudaFree(idx->d_sa);
+	cudaFree(idx->d_buckets); cudaFree(idx->d_sa); cudaFree(idx->d_kt);
 	free(idx);
 }
 
@@ -239,6 +271,7 @@ cs_index_t *cs_index_adopt(int device, uint4 *d_buckets, uint64_t n_buckets, uin
 	idx->d.sa_mask = (uint32_t)sa_intv - 1; idx->d.sa_shift = (uint32_t)log2_exact((uint64_t)sa_intv);
 	idx->bwt_size_ref = ((seq_len + 15) >> 4) + ((seq_len + 127) / 128 + 1) * 8;
 	idx->bytes = n_buckets * 32 + n_sa * 8;
+	if (build_kmer_table(idx) != CS_OK) { cudaFree(d_buckets); cudaFree(d_sa); free(idx); return nullptr; }
 	return idx;
 }
 
@@ -324,6 +357,7 @@ struct Slot {
 	Ctrl *h_ctrl;
 	// device
 	uint8_t *d_bases; uint32_t *d_off;
+	uint64_t *d_packed; uint32_t *d_nmask;   // 2-bit packed reads + ambiguity mask (k_pack_reads)
 	Ctrl *d_ctrl;
 	cs_mem_t *d_thread_mems; uint4 *d_spill;
 	cs_mem_t *d_pool, *d_mems;
@@ -357,7 +391,7 @@ static void slot_free(Slot *s)
 	if (s->ev_done) cudaEventDestroy(s->ev_done);
 	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
 	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
-	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
+	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
 	cudaFree(s->d_pool); cudaFree(s->d_mems); cudaFree(s->d_read_pool_off); cudaFree(s->d_read_n_mems);
 	cudaFree(s->d_r3_mems); cudaFree(s->d_r3_n_mems); cudaFree(s->d_tot_n_mems);
 	cudaFree(s->d_mem_off); cudaFree(s->d_read_n_seeds); cudaFree(s->d_seed_off); cudaFree(s->d_rows); cudaFree(s->d_scan_tmp);
@@ -417,6 +451,8 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		CK(cudaMallocHost(&s->h_ctrl, sizeof(Ctrl)));
 		CK(cudaMalloc(&s->d_bases, max_bases));
 		CK(cudaMalloc(&s->d_off, ((size_t)max_reads + 1) * 4));
+		CK(cudaMalloc(&s->d_packed, ((max_bases >> 5) + 2 * (size_t)max_reads + 4) * 8));
+		CK(cudaMalloc(&s->d_nmask, ((max_bases >> 5) + 2 * (size_t)max_reads + 4) * 4));
 		CK(cudaMalloc(&s->d_ctrl, sizeof(Ctrl)));
 		CK(cudaMalloc(&s->d_thread_mems, nthreads * ctx->mem_cap * sizeof(cs_mem_t)));
 		CK(cudaMalloc(&s->d_spill, nthreads * ctx->spill_cap * sizeof(uint4)));
@@ -472,7 +508,11 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt)
 	}
 	CK(cudaMemsetAsync(s->d_ctrl, 0, sizeof(Ctrl), s->stream));
 	CK(cudaEventRecord(s->ev[1], s->stream));
+	k_pack_reads<<<(int)std::min<uint64_t>(((uint64_t)n * 32 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, s->stream>>>(
+		s->d_bases, s->d_off, n, s->d_packed, s->d_nmask);
+	CK(cudaGetLastError());
 	a.bases = s->d_bases; a.off = s->d_off; a.n_reads = n; a.opt = *opt;
+	a.packed = s->d_packed; a.nmask = s->d_nmask;
 	a.next_read = &s->d_ctrl->next_read;
 	a.thread_mems = s->d_thread_mems; a.mem_cap = ctx->mem_cap;
 	a.spill = s->d_spill; a.spill_cap = ctx->spill_cap;

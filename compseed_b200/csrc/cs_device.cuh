@@ -22,6 +22,11 @@ struct DevIndex {
 	uint64_t n_sa;
 	uint32_t sa_mask;       // sa_intv - 1
 	uint32_t sa_shift;      // log2(sa_intv)
+	// Top-of-search table (the SST's role, SURVEY section 7 hard part 2): the bi-interval of EVERY
+	// string of 1..kt_depth bases, 16 bytes each, depth d at entry offset (4^d - 4)/3.  A pure memo of
+	// bwt_extend: entry(S + b) == bwt_extend(entry(S), forward, b).  Key: base j of the string at bits 2j.
+	const uint4 *kt;
+	uint32_t kt_depth;      // 0 = no table
 };
 
 struct Bucket { uint64_t w0, w1; uint32_t c0, c1, c2, hi; };
@@ -145,6 +150,34 @@ __device__ __forceinline__ uint64_t dev_sa(const DevIndex &I, uint64_t k, uint32
 	while (k & I.sa_mask) { ++sa; k = dev_lf(I, k); }
 	steps = (uint32_t)sa;
 	return sa + __ldg(I.sa + (k >> I.sa_shift));
+}
+
+// ---- top-of-search table and 2-bit packed reads ----
+__device__ __forceinline__ uint64_t kt_offset(uint32_t d) { return ((1ull << (2 * d)) - 4) / 3; }
+
+__device__ __forceinline__ void kt_lookup(const DevIndex &I, uint32_t d, uint64_t key, uint64_t &x0, uint64_t &x1, uint64_t &x2)
+{
+	uint4 v = __ldg(I.kt + kt_offset(d) + key);
+	x0 = (uint64_t)v.x | ((uint64_t)(v.w & 31) << 32);
+	x1 = (uint64_t)v.y | ((uint64_t)((v.w >> 5) & 31) << 32);
+	x2 = (uint64_t)v.z | ((uint64_t)((v.w >> 10) & 31) << 32);
+}
+
+// reads packed 2 bits per base, 32 bases per u64 (base j of a word at bits 2j), one zero pad word per read
+__device__ __forceinline__ uint64_t read_key(const uint64_t *pw, int a, int cnt)
+{ // the cnt (<= 16) bases starting at read position a
+	uint32_t w = (uint32_t)a >> 5, sh = ((uint32_t)a & 31) * 2;
+	uint64_t v = __ldg(pw + w) >> sh;
+	if (sh) v |= __ldg(pw + w + 1) << (64 - sh);
+	return v & ((1ull << (2 * cnt)) - 1);
+}
+// 1 bit per base: set where the base is ambiguous (> 3) or past the end of the read
+__device__ __forceinline__ bool read_has_n(const uint32_t *pn, int a, int cnt)
+{
+	uint32_t w = (uint32_t)a >> 5, sh = (uint32_t)a & 31;
+	uint32_t m = __ldg(pn + w) >> sh;
+	if (sh) m |= __ldg(pn + w + 1) << (32 - sh);
+	return (m & ((cnt >= 32 ? 0u : (1u << cnt)) - 1u)) != 0;
 }
 
 // packed interval-list entry (16 bytes): three 37-bit coordinates + 16-bit read position

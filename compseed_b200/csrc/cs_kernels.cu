@@ -141,6 +141,54 @@ __global__ void k_probe_extend(DevIndex I, uint32_t n, const uint64_t *ik, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// Top-of-search table: depth d from depth d-1, one thread per parent string (4 children each).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_kt_build(DevIndex I, uint4 *kt, uint32_t d)
+{
+	const uint64_t n_parent = 1ull << (2 * (d - 1));
+	for (uint64_t pk = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; pk < n_parent; pk += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t ok[12];
+		if (d == 1) { // bwt_set_intv, bwt.h:82; stored in the order dev_extend4 uses: child of base b at index 3-b
+			for (int b = 0; b < 4; ++b) { ok[(3 - b) * 3] = I.L2[b] + 1; ok[(3 - b) * 3 + 1] = I.L2[3 - b] + 1; ok[(3 - b) * 3 + 2] = I.L2[b + 1] - I.L2[b]; }
+		} else {
+			uint4 v = kt[kt_offset(d - 1) + pk];
+			uint64_t ik[3];
+			ik[0] = (uint64_t)v.x | ((uint64_t)(v.w & 31) << 32);
+			ik[1] = (uint64_t)v.y | ((uint64_t)((v.w >> 5) & 31) << 32);
+			ik[2] = (uint64_t)v.z | ((uint64_t)((v.w >> 10) & 31) << 32);
+			if (ik[2] == 0) { for (int j = 0; j < 12; ++j) ok[j] = 0; }
+			else dev_extend4(I, ik, 0, ok); // appending base b == prepending its complement on the reverse strand (bwt.c:309)
+		}
+		for (int b = 0; b < 4; ++b) {
+			const uint64_t *c = ok + (3 - b) * 3;
+			uint64_t x2 = c[2];
+			kt[kt_offset(d) + (pk | ((uint64_t)b << (2 * (d - 1))))] = x2 ? pack_entry(c[0], c[1], x2, 0) : make_uint4(0, 0, 0, 0);
+		}
+	}
+}
+
+// 2-bit packing of the reads of a batch + ambiguity mask; one warp per read, one lane per 32-base word
+__global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t n_reads, uint64_t *packed, uint32_t *nmask)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += nwarps) {
+		const uint32_t o = off[r], len = off[r + 1] - o;
+		const uint64_t w0 = (uint64_t)(o >> 5) + 2 * r;
+		const uint32_t nw = (len >> 5) + 2;
+		for (uint32_t w = lane; w < nw; w += 32) {
+			uint64_t v = 0; uint32_t m = 0;
+			for (uint32_t j = 0; j < 32; ++j) {
+				uint32_t p = (w << 5) + j;
+				uint32_t b = p < len ? bases[o + p] : 4u;
+				if (b > 3) m |= 1u << j; else v |= (uint64_t)b << (2 * j);
+			}
+			packed[w0 + w] = v; nmask[w0 + w] = m;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
 // SA resolution: rows_inout[i] = bwt_sa(rows_inout[i]).  LF walks have a geometric length
 // distribution (mean 31, max 396+ at sa_intv 32), so lanes refill from a global
 // work counter as soon as their own walk ends instead of waiting for the slowest lane.
@@ -198,6 +246,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 	int st = ST_FETCH;
 	uint32_t rd = 0; int len = 0;
 	const uint8_t *q = nullptr;
+	const uint64_t *pw = nullptr;                         // this read, 2-bit packed
 	uint32_t nmem = 0, old_n = 0, r2k = 0;
 	int round = 1;
 	int x = 0, i = 0, bi = 0, ret = 0;
@@ -255,6 +304,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 				if (rd >= a.n_reads) { st = ST_IDLE; break; }
 				uint32_t o = a.off[rd];
 				q = a.bases + o; len = (int)(a.off[rd + 1] - o);
+				pw = a.packed + ((uint64_t)(o >> 5) + 2ull * rd);
 				nmem = 0; round = 1; x = 0; err_list = err_mem = false;
 				st = ST_R1_PIVOT;
 			} break;
@@ -328,9 +378,16 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 		const int pf_idx = is_back ? bi - 1 : i + 1;
 		uint32_t nb = 4;
 		if (pf_idx >= 0 && pf_idx < len) nb = q[pf_idx];
-		uint64_t o0, o1, o2; uint32_t two;
-		dev_extend(I, c0, c1, c2, c, is_back, o0, o1, o2, two);
-		++n_ext; ++n_call; n_two += two;
+		uint64_t o0, o1, o2;
+		{
+			// the extended string is q[x..i] (forward) or q[bi..cend) (backward); short strings come from
+			// the top-of-search table (one 16-byte gather, no Occ sectors), the rest from the FM-index
+			const int s_beg = is_back ? bi : x;
+			const int new_len = is_back ? (int)cend - bi : i + 1 - x;
+			++n_ext;
+			if (new_len <= (int)I.kt_depth) kt_lookup(I, (uint32_t)new_len, read_key(pw, s_beg, new_len), o0, o1, o2);
+			else { uint32_t two; dev_extend(I, c0, c1, c2, c, is_back, o0, o1, o2, two); ++n_call; n_two += two; }
+		}
 
 		if (!is_back) { // ST_FWD, bwt.c:311-315
 			if (o2 != c2) {
@@ -377,9 +434,13 @@ __global__ void __launch_bounds__(256, 4) k_seed_r3(DevIndex I, SeedArgs a)
 	bool idle = false, need = false;
 	uint32_t rd = 0, nmem = 0; int len = 0, x = 0, i = 0, c = 0;
 	const uint8_t *q = nullptr;
+	const uint64_t *pw = nullptr; const uint32_t *pn = nullptr;
 	cs_mem_t *out = nullptr;
 	uint64_t c0 = 0, c1 = 0, c2 = 0;
 	bool have_read = false;
+	// a chain may start directly at depth `jump` from the top-of-search table: no seed can end before
+	// min_seed_len + 1 bases (bwt.c:370), so the skipped intervals are never looked at
+	const int jump = (int)I.kt_depth < opt.min_seed_len ? (int)I.kt_depth : opt.min_seed_len;
 
 	for (;;) {
 		while (!need && !idle) {
@@ -388,15 +449,21 @@ __global__ void __launch_bounds__(256, 4) k_seed_r3(DevIndex I, SeedArgs a)
 				if (rd >= a.n_reads) { idle = true; break; }
 				uint32_t o = a.off[rd];
 				q = a.bases + o; len = (int)(a.off[rd + 1] - o);
+				pw = a.packed + ((uint64_t)(o >> 5) + 2ull * rd); pn = a.nmask + ((uint64_t)(o >> 5) + 2ull * rd);
 				out = a.r3_mems + ((uint64_t)(o / kp1) + rd);
 				nmem = 0; x = 0; i = 0; have_read = true;
 			}
 			if (i <= x) { // need a new pivot
 				while (x < len && q[x] > 3) ++x;
 				if (x >= len) { a.r3_n_mems[rd] = nmem; have_read = false; continue; }
-				int b = q[x];
-				c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
-				i = x + 1;
+				if (jump >= 2 && !read_has_n(pn, x, jump)) { // q[x..x+jump) is inside the read and unambiguous
+					kt_lookup(I, (uint32_t)jump, read_key(pw, x, jump), c0, c1, c2);
+					i = x + jump; n_ext += (unsigned)(jump - 1);
+				} else {
+					int b = q[x];
+					c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
+					i = x + 1;
+				}
 			}
 			// bwt.c:366-378
 			if (i >= len) { a.r3_n_mems[rd] = nmem; have_read = false; }

@@ -16,6 +16,8 @@ struct SeedArgs {
 	const uint32_t *off;        // n_reads + 1
 	uint32_t n_reads;
 	cs_seed_opt_t opt;
+	const uint64_t *packed;     // 2-bit packed reads (k_pack_reads): read r starts at word (off[r] >> 5) + 2r
+	const uint32_t *nmask;      // ambiguity / end-of-read mask, same word indexing
 	// scratch
 	uint32_t *next_read;        // work counters: [0] k_seed, [1] k_seed_r3
 	cs_mem_t *thread_mems;      // [n_threads][mem_cap] per-thread mem list of the read in flight
@@ -60,6 +62,8 @@ __global__ void k_probe_occ4(DevIndex I, uint32_t n, const uint64_t *k, uint64_t
 __global__ void k_probe_extend(DevIndex I, uint32_t n, const uint64_t *ik, const int32_t *is_back, uint64_t *ok);
 __global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, uint64_t *rows_inout, unsigned long long *work,
                              unsigned long long *lf_steps);
+__global__ void k_kt_build(DevIndex I, uint4 *kt, uint32_t d);
+__global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t n_reads, uint64_t *packed, uint32_t *nmask);
 __global__ void k_seed(DevIndex I, SeedArgs a);
 __global__ void k_seed_r3(DevIndex I, SeedArgs a);
 __global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, uint32_t n_reads, uint32_t *out);
