@@ -53,6 +53,7 @@ struct cs_index {
 	uint4 *d_buckets;
 	uint64_t *d_sa;
 	uint4 *d_kt;            // top-of-search table (depths 1..d.kt_depth)
+	uint32_t *d_pt;         // occurrence filter (2-bit counts of all d.pt_k-mers)
 	uint64_t bytes;
 	uint64_t bwt_size_ref;  // words of the reference layout
 	int sa_intv;
@@ -60,6 +61,51 @@ struct cs_index {
 };
 
 static int log2_exact(uint64_t v) { int s = 0; while ((1ull << s) < v) ++s; return (1ull << s) == v ? s : -1; }
+
+// Occurrence filter (cs_device.cuh, ST_PRUNE in k_seed): 2-bit saturating counts of all K-mers of the
+// indexed text, K = ceil(log4(seq_len)) + 2 capped at 19 (17 GB at K = 18, 69 GB at K = 19): long enough
+// that a random K-mer is almost always absent, short enough to stay below the default min_seed_len.
+// W is the 2-bit text if the caller has it (the on-device builder); otherwise it is rebuilt from the
+// BWT and the SA.  CS_PRUNE_K overrides (0 disables).
+int cs_internal_build_filter(cs_index *idx, const uint64_t *W)
+{
+	unsigned long long *own = nullptr;
+	int K = 2;
+	const char *env = getenv("CS_PRUNE_K");
+	const uint64_t n = idx->d.seq_len;
+	while (K < 19 && (1ull << (2 * (K - 2))) < n) ++K;      // K - 2 >= log4(n)
+	if (K < 8) K = 8;
+	if (env) K = atoi(env);
+	idx->d.pt = nullptr; idx->d.pt_k = 0; idx->d_pt = nullptr;
+	if (K <= 0 || n < (uint64_t)K) return CS_OK;
+	if (K < 4) K = 4;
+	if (K > 19) K = 19;
+	{
+		const uint64_t words = (1ull << (2 * K)) / 16;
+		int grid = idx->n_sm * 8;
+		if (!W) {
+			const uint64_t n_words = (n + 31) / 32 + 2;
+			CK(cudaMalloc(&own, n_words * 8));
+			CK(cudaMemset(own, 0, n_words * 8));
+			k_text_from_index<<<grid, 256>>>(idx->d, own);
+			CK(cudaGetLastError());
+			W = reinterpret_cast<const uint64_t*>(own);
+		}
+		CK(cudaMalloc(&idx->d_pt, words * 4));
+		CK(cudaMemset(idx->d_pt, 0, words * 4));
+		k_pt_count<<<grid, 256>>>(W, n, (uint32_t)K, idx->d_pt);
+		CK(cudaGetLastError());
+		CK(cudaDeviceSynchronize());
+		idx->d.pt = idx->d_pt; idx->d.pt_k = (uint32_t)K;
+		idx->bytes += words * 4;
+	}
+	if (own) cudaFree(own);
+	return CS_OK;
+fail:
+	if (own) cudaFree(own);
+	if (idx->d_pt) { cudaFree(idx->d_pt); idx->d_pt = nullptr; }
+	return CS_E_CUDA;
+}
 
 // Top-of-search table (cs_device.cuh): depth chosen so that the deepest level still has ~64 rows per
 // entry (deeper levels cost HBM without saving sector reads: k and l already share a bucket there).
@@ -153,10 +199,11 @@ extern "C" cs_index_t *cs_index_upload(const cs_bwt_view_t *v, int device, int d
 	if (dense_sa_intv > 0 && dense_sa_intv < v->sa_intv)
 		if (resample_sa(idx, dense_sa_intv) != CS_OK) goto fail;
 	if (build_kmer_table(idx) != CS_OK) goto fail;
+	if (cs_internal_build_filter(idx, nullptr) != CS_OK) goto fail;
 	return idx;
 fail:
 	if (d_src) cudaFree(d_src);
-	if (idx) { if (idx->d_buckets) cudaFree(idx->d_buckets); if (idx->d_sa) cudaFree(idx->d_sa); if (idx->d_kt) cudaFree(idx->d_kt); free(idx); }
+	if (idx) { if (idx->d_buckets) cudaFree(idx->d_buckets); if (idx->d_sa) cudaFree(idx->d_sa); if (idx->d_kt) cudaFree(idx->d_kt); if (idx->d_pt) cudaFree(idx->d_pt); free(idx); }
 	return nullptr;
 }
 
@@ -251,13 +298,13 @@ extern "C" void cs_index_free(cs_index_t *idx)
 {
 	if (!idx) return;
 	cudaSetDevice(idx->device);
-	cudaFree(idx->d_buckets); cudaFree(idx->d_sa); cudaFree(idx->d_kt);
+	cudaFree(idx->d_buckets); cudaFree(idx->d_sa); cudaFree(idx->d_kt); cudaFree(idx->d_pt);
 	free(idx);
 }
 
 // internal: wrap device arrays produced by the on-device builder (cs_index_build.cu)
 cs_index_t *cs_index_adopt(int device, uint4 *d_buckets, uint64_t n_buckets, uint64_t *d_sa, uint64_t n_sa, int sa_intv,
-                           uint64_t primary, const uint64_t L2[5], uint64_t seq_len)
+                           uint64_t primary, const uint64_t L2[5], uint64_t seq_len, const uint64_t *W)
 {
 	cs_index *idx = (cs_index*)calloc(1, sizeof(cs_index));
 	cudaDeviceProp prop;
@@ -271,7 +318,10 @@ cs_index_t *cs_index_adopt(int device, uint4 *d_buckets, uint64_t n_buckets, uin
 	idx->d.sa_mask = (uint32_t)sa_intv - 1; idx->d.sa_shift = (uint32_t)log2_exact((uint64_t)sa_intv);
 	idx->bwt_size_ref = ((seq_len + 15) >> 4) + ((seq_len + 127) / 128 + 1) * 8;
 	idx->bytes = n_buckets * 32 + n_sa * 8;
-	if (build_kmer_table(idx) != CS_OK) { cudaFree(d_buckets); cudaFree(d_sa); free(idx); return nullptr; }
+	if (build_kmer_table(idx) != CS_OK || cs_internal_build_filter(idx, W) != CS_OK) {
+		cudaFree(idx->d_kt); cudaFree(d_buckets); cudaFree(d_sa); free(idx);
+		return nullptr;
+	}
 	return idx;
 }
 

@@ -27,6 +27,11 @@ struct DevIndex {
 	// bwt_extend: entry(S + b) == bwt_extend(entry(S), forward, b).  Key: base j of the string at bits 2j.
 	const uint4 *kt;
 	uint32_t kt_depth;      // 0 = no table
+	// Occurrence filter: a 2-bit saturating count (0,1,2,>=3) of every pt_k-mer of the indexed text
+	// (both strands), key as in read_key.  Lets the backward phase drop, with one gather, every forward
+	// match that cannot grow to min_seed_len bases (see ST_PRUNE in k_seed).  0 = no filter.
+	const uint32_t *pt;
+	uint32_t pt_k;
 };
 
 struct Bucket { uint64_t w0, w1; uint32_t c0, c1, c2, hi; };

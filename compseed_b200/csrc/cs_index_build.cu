@@ -21,7 +21,7 @@
 #include "cs_kernels.cuh"
 
 cs_index_t *cs_index_adopt(int device, uint4 *d_buckets, uint64_t n_buckets, uint64_t *d_sa, uint64_t n_sa, int sa_intv,
-                           uint64_t primary, const uint64_t L2[5], uint64_t seq_len);
+                           uint64_t primary, const uint64_t L2[5], uint64_t seq_len, const uint64_t *W);
 void cs_internal_set_error(int code, const char *msg);
 
 namespace {
@@ -483,7 +483,7 @@ extern "C" cs_index_t *cs_index_build(const uint8_t *fwd, uint64_t l_pac, int de
 		BCK(cudaGetLastError());
 	}
 	BCK(cudaDeviceSynchronize());
-	idx = cs_index_adopt(device, buckets, n_buckets, d_sa, n_sa, sa_intv, primary, L2, n);
+	idx = cs_index_adopt(device, buckets, n_buckets, d_sa, n_sa, sa_intv, primary, L2, n, W);
 	buckets = nullptr; d_sa = nullptr;
 fail:
 	cudaFree(d_fwd); cudaFree(W); cudaFree(safull); cudaFree(d_small); cudaFree(keys_in); cudaFree(keys_out); cudaFree(vals_out);

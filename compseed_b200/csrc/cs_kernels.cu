@@ -167,6 +167,57 @@ __global__ void k_kt_build(DevIndex I, uint4 *kt, uint32_t d)
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// Occurrence filter construction.
+// k_text_from_index: rebuild the indexed text T (2 bits/base, 32 bases per u64, base j of a word at
+// bits 62-2j) from the BWT and the sampled SA: one LF walk per sampled row, each writing the
+// characters between two samples (T[SA[r]-1] is the BWT character of row r).
+// k_pt_count: saturating 2-bit count of every K-mer of T.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_text_from_index(DevIndex I, unsigned long long *W)
+{
+	for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < I.n_sa; s += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t r = s << I.sa_shift;
+		uint64_t p = s == 0 ? I.seq_len : I.sa[s];
+		for (;;) {
+			if (r == I.primary || p == 0) break;              // the '$' row: nothing precedes text position 0
+			uint64_t x = r - (r > I.primary);
+			uint64_t b = x >> 6; uint32_t q = (uint32_t)x & 63;
+			Bucket B = load_bucket(I, b);
+			uint32_t c = (uint32_t)((q < 32 ? B.w0 : B.w1) >> (2 * (q & 31))) & 3;
+			--p;
+			if (c) atomicOr(W + (p >> 5), (unsigned long long)c << (62 - 2 * (p & 31)));
+			uint64_t cnt[4];
+			bucket_occ4(B, b, q, cnt);
+			r = l2_at(I, (int)c) + (c == 0 ? cnt[0] : c == 1 ? cnt[1] : c == 2 ? cnt[2] : cnt[3]);
+			if ((r & I.sa_mask) == 0) break;                  // the next sample's walk takes over
+		}
+	}
+}
+
+#define PT_CHUNK 256
+__global__ void k_pt_count(const uint64_t *W, uint64_t n, uint32_t K, uint32_t *pt)
+{
+	if (n < K) return;
+	const uint64_t n_pos = n - K + 1;
+	for (uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * PT_CHUNK; i0 < n_pos; i0 += (uint64_t)gridDim.x * blockDim.x * PT_CHUNK) {
+		uint64_t key = 0;
+		for (uint32_t j = 0; j + 1 < K; ++j) { uint64_t p = i0 + j; key |= ((W[p >> 5] >> (62 - 2 * (p & 31))) & 3) << (2 * (j + 1)); }
+		uint64_t i1 = i0 + PT_CHUNK < n_pos ? i0 + PT_CHUNK : n_pos;
+		for (uint64_t i = i0; i < i1; ++i) { // key of T[i..i+K): base j at bits 2j
+			uint64_t p = i + K - 1;
+			key = (key >> 2) | (((W[p >> 5] >> (62 - 2 * (p & 31))) & 3) << (2 * (K - 1)));
+			uint32_t *w = pt + (key >> 4); uint32_t sh = 2 * ((uint32_t)key & 15);
+			uint32_t old = *w;
+			while (((old >> sh) & 3) != 3) {
+				uint32_t seen = atomicCAS(w, old, old + (1u << sh));
+				if (seen == old) break;
+				old = seen;
+			}
+		}
+	}
+}
+
 // 2-bit packing of the reads of a batch + ambiguity mask; one warp per read, one lane per 32-base word
 __global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t n_reads, uint64_t *packed, uint32_t *nmask)
 {
@@ -230,7 +281,7 @@ __global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, ui
 // packed 16-byte entries: the first CS_LIST_SMEM per thread in shared memory (bank-conflict-free
 // [entry][thread] layout), the rest spilled to HBM.
 // ---------------------------------------------------------------------------------------------
-enum { ST_FETCH = 0, ST_R1_PIVOT, ST_FWD, ST_BWD_INIT, ST_BWD_SWEEP, ST_BWD_ENTRY, ST_CALL_DONE, ST_R2_NEXT,
+enum { ST_FETCH = 0, ST_R1_PIVOT, ST_FWD, ST_BWD_INIT, ST_PRUNE, ST_BWD_SWEEP, ST_BWD_ENTRY, ST_CALL_DONE, ST_R2_NEXT,
        ST_READ_DONE, ST_IDLE };
 
 __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIndex I, SeedArgs a)
@@ -242,11 +293,13 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 	cs_mem_t *my = a.thread_mems + gtid * a.mem_cap;
 	const cs_seed_opt_t opt = a.opt;
 
-	unsigned long long n_ext = 0, n_call = 0, n_two = 0;
+	unsigned long long n_ext = 0, n_call = 0, n_two = 0, n_probe = 0;
 	int st = ST_FETCH;
 	uint32_t rd = 0; int len = 0;
 	const uint8_t *q = nullptr;
 	const uint64_t *pw = nullptr;                         // this read, 2-bit packed
+	// occurrence filter usable only if a filtered match is certain to be shorter than min_seed_len
+	const int prune_k = (I.pt_k > 0 && opt.min_seed_len >= (int)I.pt_k) ? (int)I.pt_k : 0;
 	uint32_t nmem = 0, old_n = 0, r2k = 0;
 	int round = 1;
 	int x = 0, i = 0, bi = 0, ret = 0;
@@ -297,7 +350,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 
 	for (;;) {
 		// ---- divergent bookkeeping: advance this lane's state machine until it needs an extend ----
-		while (!need && st != ST_IDLE) {
+		while (!need && st != ST_IDLE && st != ST_PRUNE) {
 			switch (st) {
 			case ST_FETCH: {
 				rd = atomicAdd(a.next_read, 1u);
@@ -320,7 +373,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 			case ST_BWD_INIT: // bwt.c:322-326; list[n-1] is the longest match
 				ret = (int)(list_get(n - 1).w >> 16);
 				bi = x - 1; lo = 0;
-				st = ST_BWD_SWEEP;
+				st = prune_k ? ST_PRUNE : ST_BWD_SWEEP;   // ST_PRUNE is served by the whole warp below
 				break;
 			case ST_BWD_SWEEP: { // one value of i in bwt.c:326
 				c = bi < 0 ? -1 : (q[bi] < 4 ? q[bi] : -1);
@@ -370,6 +423,51 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 
 		// ---- explicit reconvergence: all 32 lanes meet here every trip; nobody leaves early ----
 		if (__all_sync(0xffffffffu, st == ST_IDLE)) break;
+
+		// ---- occurrence filter (result-neutral), served by the whole warp for one requesting lane at a
+		//      time.  A forward match [x, e) can only yield a mem of >= min_seed_len bases if q[e-K, e)
+		//      occurs >= min_intv times (K <= min_seed_len) and lies inside the read without an N; a match
+		//      that cannot is dropped before the sweeps: its own mem would be discarded by the length
+		//      filter (bwamem.c:231-233,247), and it can neither block nor unblock a longer match (it dies
+		//      no later than any longer one).  Lane l tests entry l: one 2-bit gather replaces the entry's
+		//      whole column of backward extensions. ----
+		for (unsigned req = __ballot_sync(0xffffffffu, st == ST_PRUNE); req; req &= req - 1) {
+			const int owner = __ffs(req) - 1, lane = t & 31;
+			const int on = __shfl_sync(0xffffffffu, n, owner), ox = __shfl_sync(0xffffffffu, x, owner);
+			const uint64_t *opw = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)pw, owner));
+			const uint64_t omin = __shfl_sync(0xffffffffu, (unsigned long long)min_intv, owner);
+			const uint32_t *opn = a.nmask + (opw - a.packed);
+			const int ot = t - lane + owner; const size_t ogtid = gtid - lane + owner;
+			int kept = 0;
+			for (int base = 0; base < on; base += 32) {
+				const int jj = base + lane;
+				bool keep = false;
+				uint4 ent = make_uint4(0, 0, 0, 0);
+				if (jj < on) {
+					ent = jj < CS_LIST_SMEM ? s_list[jj * CS_SEED_BLOCK + ot]
+					    : ((uint32_t)(jj - CS_LIST_SMEM) < a.spill_cap ? a.spill[(size_t)(jj - CS_LIST_SMEM) * nthreads + ogtid] : ent);
+					const int e = (int)(ent.w >> 16), ws = e - prune_k;
+					if (e - ox >= prune_k) keep = true;                    // already long enough
+					else if (ws >= 0 && !read_has_n(opn, ws, ox - ws)) {   // else it ends at the read start / an N first
+						const uint64_t key = read_key(opw, ws, prune_k);
+						const uint32_t cnt = (__ldg(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3;
+						keep = cnt == 3 || cnt >= omin;
+						++n_probe;
+					}
+				}
+				const unsigned km = __ballot_sync(0xffffffffu, keep);      // every lane holds its entry by now
+				if (keep) {
+					const int dst = kept + __popc(km & ((1u << lane) - 1));
+					if (dst != jj) {
+						if (dst < CS_LIST_SMEM) s_list[dst * CS_SEED_BLOCK + ot] = ent;
+						else a.spill[(size_t)(dst - CS_LIST_SMEM) * nthreads + ogtid] = ent;
+					}
+				}
+				kept += __popc(km);
+				__syncwarp();
+			}
+			if (lane == owner) { n = kept; st = kept ? ST_BWD_SWEEP : ST_CALL_DONE; }
+		}
 		if (!need) continue;
 
 		// ---- the one convergent, memory-bound step: bwt_extend of (c0,c1,c2) by base c ----
@@ -418,6 +516,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 	if (n_ext) atomicAdd(a.counters + 0, n_ext);
 	if (n_call) atomicAdd(a.counters + 1, n_call);
 	if (n_two) atomicAdd(a.counters + 2, n_two);
+	if (n_probe) atomicAdd(a.counters + 3, n_probe);
 }
 
 // ---------------------------------------------------------------------------------------------

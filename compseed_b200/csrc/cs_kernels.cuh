@@ -32,7 +32,7 @@ struct SeedArgs {
 	uint32_t *read_n_mems;      // [n_reads]
 	cs_mem_t *r3_mems;          // third-pass seeds of read r at [off[r]/(k+1) + r ...]
 	uint32_t *r3_n_mems;        // [n_reads]
-	unsigned long long *counters; // [0] ext queries [1] ext calls (bucket path) [2] two-sector extends
+	unsigned long long *counters; // [0] ext queries [1] ext calls (bucket path) [2] two-sector extends [3] occurrence-filter probes
 	int *error;                 // sticky CS_E_* code
 };
 
@@ -63,6 +63,8 @@ __global__ void k_probe_extend(DevIndex I, uint32_t n, const uint64_t *ik, const
 __global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, uint64_t *rows_inout, unsigned long long *work,
                              unsigned long long *lf_steps);
 __global__ void k_kt_build(DevIndex I, uint4 *kt, uint32_t d);
+__global__ void k_text_from_index(DevIndex I, unsigned long long *W);
+__global__ void k_pt_count(const uint64_t *W, uint64_t n, uint32_t K, uint32_t *pt);
 __global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t n_reads, uint64_t *packed, uint32_t *nmask);
 __global__ void k_seed(DevIndex I, SeedArgs a);
 __global__ void k_seed_r3(DevIndex I, SeedArgs a);
