@@ -670,11 +670,22 @@ extern "C" int cs_seed_batch_stage(cs_ctx_t *ctx, int slot, uint32_t n_reads, co
 	Slot *s = &ctx->slots[slot];
 	if (s->state == 2) return set_err(CS_E_STATE, "slot %d is busy", slot);
 	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
-	memcpy(s->h_bases, bases, offsets[n_reads]);
 	memcpy(s->h_off, offsets, ((size_t)n_reads + 1) * 4);
 	s->n_reads = n_reads;
 	CK(cudaEventRecord(s->ev[0], s->stream));
-	CK(cudaMemcpyAsync(s->d_bases, s->h_bases, offsets[n_reads], cudaMemcpyHostToDevice, s->stream));
+	{
+		// bases already in page-locked memory (cs_host_register / cudaHostAlloc by the caller): DMA straight
+		// from the caller's buffer, which must then stay untouched until the slot is waited on;
+		// otherwise stage through the slot's own pinned buffer
+		cudaPointerAttributes pa;
+		bool pinned = cudaPointerGetAttributes(&pa, bases) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+		if (pinned) CK(cudaMemcpyAsync(s->d_bases, bases, offsets[n_reads], cudaMemcpyHostToDevice, s->stream));
+		else {
+			memcpy(s->h_bases, bases, offsets[n_reads]);
+			CK(cudaMemcpyAsync(s->d_bases, s->h_bases, offsets[n_reads], cudaMemcpyHostToDevice, s->stream));
+		}
+	}
 	CK(cudaMemcpyAsync(s->d_off, s->h_off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s->stream));
 	s->state = 1;
 	return CS_OK;
@@ -827,6 +838,21 @@ fail:
 	if (e1) cudaEventDestroy(e1);
 	cudaFree(d_t); cudaFree(d_sink);
 	return CS_E_CUDA;
+}
+
+extern "C" int cs_host_register(void *ptr, size_t bytes)
+{
+	if (cs_device_count() <= 0) return set_err(CS_E_NODEVICE, "no CUDA device visible: compseed_b200 has no CPU path");
+	cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+	if (e != cudaSuccess) { cudaGetLastError(); return set_err(CS_E_CUDA, "cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e)); }
+	return CS_OK;
+}
+
+extern "C" int cs_host_unregister(void *ptr)
+{
+	cudaError_t e = cudaHostUnregister(ptr);
+	if (e != cudaSuccess) { cudaGetLastError(); return set_err(CS_E_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+	return CS_OK;
 }
 
 extern "C" int cs_flush_l2(int device)

@@ -95,6 +95,8 @@ def load_library():
     L.cs_probe_random_gather_ex.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.cs_flush_l2.argtypes = [C.c_int]
+    L.cs_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.cs_host_unregister.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -384,6 +386,15 @@ def probe_random_gather(device: int = 0, table_bytes: int = 4 << 30, granule: in
     _check(load_library().cs_probe_random_gather_ex(device, table_bytes, granule, n_loads, iters, unroll, l2_fetch_granularity,
                                                     C.byref(gb), C.byref(gl)))
     return gb.value, gl.value
+
+
+def host_register(a: np.ndarray) -> None:
+    """Page-lock a numpy array so that submit() DMAs straight out of it (no staging copy)."""
+    _check(load_library().cs_host_register(_ptr(a), a.nbytes))
+
+
+def host_unregister(a: np.ndarray) -> None:
+    _check(load_library().cs_host_unregister(_ptr(a)))
 
 
 def flush_l2(device: int = 0) -> None:

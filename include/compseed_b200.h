@@ -141,6 +141,12 @@ int cs_seed_batch_submit(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint8_
 /* Waits for the slot, copies the results to its pinned host buffers and fills *out. */
 int cs_seed_batch_wait(cs_ctx_t *ctx, int slot, cs_result_t *out);
 
+/* Page-locks a caller-owned buffer (e.g. the read buffer of the batch loop).  cs_seed_batch_submit
+ * then DMAs straight out of it instead of staging through the slot's pinned buffer; the caller must
+ * leave the bases of a submitted batch untouched until the slot is waited on. */
+int cs_host_register(void *ptr, size_t bytes);
+int cs_host_unregister(void *ptr);
+
 /* Device-resident variant (inputs already in HBM, results left in HBM): stage once, run many. */
 int cs_seed_batch_stage(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint8_t *bases, const uint32_t *offsets);
 int cs_seed_batch_run_staged(cs_ctx_t *ctx, int slot, const cs_seed_opt_t *opt);
