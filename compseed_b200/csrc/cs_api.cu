@@ -475,7 +475,7 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 	ctx->n_slots = n_slots;
 	ctx->slots = (Slot*)calloc(n_slots, sizeof(Slot));
 	{
-		const size_t smem = (size_t)CS_LIST_SMEM * CS_SEED_BLOCK * sizeof(uint4);
+		const size_t smem = CS_SEED_SMEM_BYTES;
 		int per_sm = 0;
 		CK(cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed, CS_SEED_BLOCK, smem));
@@ -540,7 +540,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt)
 {
 	const cs_index *idx = ctx->idx;
 	const uint32_t n = s->n_reads;
-	const size_t smem = (size_t)CS_LIST_SMEM * CS_SEED_BLOCK * sizeof(uint4);
+	const size_t smem = CS_SEED_SMEM_BYTES;
 	int grid = std::min<int>(ctx->grid, (int)((n + CS_SEED_BLOCK - 1) / CS_SEED_BLOCK));
 	if (grid < 1) grid = 1;
 	SeedArgs a;

@@ -4,11 +4,12 @@
 // buckets, FM_index/bwt.h:74-80, index_main.c:152-174):
 //
 //   bucket b (32 bytes, one L2/DRAM sector, 64 BWT rows [64b, 64b+64)):
-//     u64 w0, w1   bases LSB-first: row 64b+i is at bits 2*(i&31) of w[i>>5]
-//     u32 c0, c1, c2   low 32 bits of the number of A / C / G in rows [0, 64b)
-//     u32 hi           bits 0-7 / 8-15 / 16-23: bits 32-39 of c0 / c1 / c2
-//   The T checkpoint is implied: c3 = 64b - c0 - c1 - c2 (the '$' row is not stored, as in the
-//   reference).  One occ4 lookup == one 256-bit load (LDG.E.256), i.e. exactly one 32-byte sector.
+//     u32 w0..w3   bases LSB-first: row 64b+i is at bits 2*(i&15) of w[i>>4]
+//     u32 p1, p2, p3   low 32 bits of the PREFIX sums #A, #A+#C, #A+#C+#G over rows [0, 64b)
+//     u32 hi           bits 0-7 / 8-15 / 16-23: bits 32-39 of p1 / p2 / p3
+//   The last prefix sum is implied: p4 = 64b (the '$' row is not stored, as in the reference).
+//   Prefix sums let one extend pick "bases <= c" and "bases < c" with two selects instead of
+//   assembling four 64-bit counts.  One occ lookup == one 256-bit load (LDG.E.256) == one 32-byte sector.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -34,7 +35,7 @@ struct DevIndex {
 	uint32_t pt_k;
 };
 
-struct Bucket { uint64_t w0, w1; uint32_t c0, c1, c2, hi; };
+struct Bucket { uint32_t w0, w1, w2, w3; uint32_t p1, p2, p3, hi; };
 
 // L2[c] for a run-time c without indexing the kernel-parameter struct dynamically (which would
 // force a local-memory copy of it)
@@ -48,33 +49,119 @@ __device__ __forceinline__ uint64_t l2_at(const DevIndex &I, int c)
 __device__ __forceinline__ Bucket load_bucket(const DevIndex &I, uint64_t b)
 {
 	Bucket r;
-	uint64_t c01, c2h;
 	const uint4 *p = I.buckets + 2 * b;
-	asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
-	             : "=l"(r.w0), "=l"(r.w1), "=l"(c01), "=l"(c2h) : "l"(p));
-	r.c0 = (uint32_t)c01; r.c1 = (uint32_t)(c01 >> 32);
-	r.c2 = (uint32_t)c2h; r.hi = (uint32_t)(c2h >> 32);
+	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(r.w0), "=r"(r.w1), "=r"(r.w2), "=r"(r.w3), "=r"(r.p1), "=r"(r.p2), "=r"(r.p3), "=r"(r.hi) : "l"(p));
 	return r;
+}
+
+// Low-bit-plane masks of the first n bases of a bucket (n = 0..64), one 32-bit mask per 16-base word.
+// 1 KB, always L1-resident; fetched together with the bucket so the masks cost no dependent ALU work.
+__device__ const uint4 g_occ_mask[65] = {
+	{0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00000001u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00000005u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00000015u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00000055u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00000155u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00000555u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00001555u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00005555u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00015555u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00055555u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00155555u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x00555555u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x01555555u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x05555555u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x15555555u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00000000u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00000001u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00000005u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00000015u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00000055u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00000155u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00000555u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00001555u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00005555u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00015555u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00055555u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00155555u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x00555555u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x01555555u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x05555555u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x15555555u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00000000u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00000001u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00000005u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00000015u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00000055u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00000155u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00000555u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00001555u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00005555u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00015555u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00055555u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00155555u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x00555555u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x01555555u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x05555555u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x15555555u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00000000u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00000001u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00000005u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00000015u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00000055u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00000155u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00000555u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00001555u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00005555u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00015555u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00055555u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00155555u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x00555555u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x01555555u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x05555555u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x15555555u},
+	{0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u}
+};
+
+// Base counts among the first n bases of a bucket from three popcount pairs:
+//   T = #T, H = #G + #T (high bit set), E = #C + #T (low bit set)   =>   #A = n - H - E + T.
+// Words are merged pairwise (word 0 on the even bits, word 1 shifted onto the odd bits) to halve the popcounts.
+__device__ __forceinline__ void bucket_the(const Bucket &B, uint4 m, uint32_t &T, uint32_t &H, uint32_t &E)
+{
+	uint32_t m1s = m.y << 1, m3s = m.w << 1;
+	uint32_t E01 = (B.w0 & m.x) | ((B.w1 << 1) & m1s), H01 = ((B.w0 >> 1) & m.x) | (B.w1 & m1s);
+	uint32_t E23 = (B.w2 & m.z) | ((B.w3 << 1) & m3s), H23 = ((B.w2 >> 1) & m.z) | (B.w3 & m3s);
+	E = __popc(E01) + __popc(E23);
+	H = __popc(H01) + __popc(H23);
+	T = __popc(E01 & H01) + __popc(E23 & H23);
+}
+
+// checkpoint prefix sums: P0 = 0, P1 = #A, P2 = #A+#C, P3 = #A+#C+#G, P4 = 64b (rows before the bucket)
+__device__ __forceinline__ uint64_t bucket_p(const Bucket &B, int j) // j = 1..3
+{
+	uint32_t lo = j == 1 ? B.p1 : j == 2 ? B.p2 : B.p3;
+	return (uint64_t)lo | ((uint64_t)((B.hi >> (8 * (j - 1))) & 0xff) << 32);
+}
+
+// the base stored at position r (0..63) of a bucket
+__device__ __forceinline__ uint32_t bucket_base(const Bucket &B, uint32_t r)
+{
+	uint32_t w = (r & 32) ? ((r & 16) ? B.w3 : B.w2) : ((r & 16) ? B.w1 : B.w0);
+	return (w >> (2 * (r & 15))) & 3;
 }
 
 // cnt[c] = number of base c in rows [0 .. 64b + r] of the stored BWT (r in 0..63, inclusive)
 __device__ __forceinline__ void bucket_occ4(const Bucket &B, uint64_t b, uint32_t r, uint64_t cnt[4])
 {
-	const uint64_t M = 0x5555555555555555ull;
-	uint32_t n = r + 1;                                  // bases counted, 1..64
-	uint64_t m0 = n >= 32 ? M : (((1ull << (2 * n)) - 1) & M);
-	uint64_t m1 = n <= 32 ? 0ull : (n == 64 ? M : (((1ull << (2 * (n - 32))) - 1) & M));
-	uint64_t e0 = B.w0 & m0, h0 = (B.w0 >> 1) & m0;      // low / high bit planes
-	uint64_t e1 = B.w1 & m1, h1 = (B.w1 >> 1) & m1;
-	uint32_t nT = __popcll(e0 & h0) + __popcll(e1 & h1);
-	uint32_t nH = __popcll(h0) + __popcll(h1);           // G + T
-	uint32_t nE = __popcll(e0) + __popcll(e1);           // C + T
-	uint32_t nG = nH - nT, nC = nE - nT, nA = n - nH - nC;
-	uint64_t c0 = (uint64_t)B.c0 | ((uint64_t)(B.hi & 0xff) << 32);
-	uint64_t c1 = (uint64_t)B.c1 | ((uint64_t)((B.hi >> 8) & 0xff) << 32);
-	uint64_t c2 = (uint64_t)B.c2 | ((uint64_t)((B.hi >> 16) & 0xff) << 32);
-	uint64_t c3 = (b << 6) - c0 - c1 - c2;
-	cnt[0] = c0 + nA; cnt[1] = c1 + nC; cnt[2] = c2 + nG; cnt[3] = c3 + nT;
+	uint32_t n = r + 1, T, H, E;
+	bucket_the(B, __ldg(&g_occ_mask[n]), T, H, E);
+	uint64_t P1 = bucket_p(B, 1), P2 = bucket_p(B, 2), P3 = bucket_p(B, 3);
+	cnt[0] = P1 + (n - H - E + T);
+	cnt[1] = (P2 - P1) + (E - T);
+	cnt[2] = (P3 - P2) + (H - T);
+	cnt[3] = ((b << 6) - P3) + T;
 }
 
 // bwt_occ4 (FM_index/bwt.c:169-186) for k != -1
@@ -87,34 +174,58 @@ __device__ __forceinline__ void dev_occ4(const DevIndex &I, uint64_t k, uint64_t
 }
 
 // bwt_extend (FM_index/bwt.c:262-275), returning only child c.  in/out: (x0, x1, x2).
-// `two` receives 1 when k and l needed two different sectors (the E2 counter of SURVEY 8d, at
-// this layout's 64-row granularity).
+// Written around cumulative counts: with U(pos) = #bases <= c and W(pos) = #bases < c in rows [0..pos],
+//   occ(pos, c) = U - W,   ok[c].x[2] = occ(l,c) - occ(k,c),
+//   sum of ok[j].x[2] for j > c (what bwt.c:271-274 accumulates) = (l' - k') - (U(l) - U(k)),
+// so only two 64-bit values per position are assembled, selected by c from the prefix-sum checkpoint
+// and from (n, T, H, E) of the bucket.  `two` = k and l needed two different sectors.
 __device__ __forceinline__ void dev_extend(const DevIndex &I, uint64_t x0, uint64_t x1, uint64_t x2, int c, int is_back,
                                            uint64_t &o0, uint64_t &o1, uint64_t &o2, uint32_t &two)
 {
-	uint64_t a = is_back ? x0 : x1;      // x[!is_back]
-	uint64_t o = is_back ? x1 : x0;      // x[is_back]
-	uint64_t k = a - 1, l = k + x2;
-	uint64_t kk = k - (k >= I.primary), ll = l - (l >= I.primary);
-	uint64_t bk = kk >> 6, bl = ll >> 6;
+	const uint64_t a = is_back ? x0 : x1;      // x[!is_back]
+	const uint64_t o = is_back ? x1 : x0;      // x[is_back]
+	const uint64_t k = a - 1, l = k + x2;
+	const uint64_t kk = k - (k >= I.primary), ll = l - (l >= I.primary);
+	const uint64_t bk = kk >> 6, bl = ll >> 6;
+	const uint32_t nk = ((uint32_t)kk & 63) + 1, nl = ((uint32_t)ll & 63) + 1;
+	const bool same = (bl == bk);
+	const uint4 mk = __ldg(&g_occ_mask[nk]), ml = __ldg(&g_occ_mask[nl]);
 	Bucket Bk = load_bucket(I, bk), Bl;
-	if (bl != bk) Bl = load_bucket(I, bl); else Bl = Bk;
-	two = (bl != bk);
-	uint64_t tk[4], tl[4];
-	bucket_occ4(Bk, bk, (uint32_t)kk & 63, tk);
-	bucket_occ4(Bl, bl, (uint32_t)ll & 63, tl);
-	uint64_t s3 = tl[3] - tk[3], s2 = tl[2] - tk[2], s1 = tl[1] - tk[1], s0 = tl[0] - tk[0];
-	uint64_t base = o + ((a <= I.primary) && (a + x2 - 1 >= I.primary));
-	// ok[3].x[is_back] = base; ok[2] = ok[3] + s3; ok[1] = ok[2] + s2; ok[0] = ok[1] + s1
-	uint64_t na, no, ns;
-	if (c == 3)      { na = tk[3]; ns = s3; no = base; }
-	else if (c == 2) { na = tk[2]; ns = s2; no = base + s3; }
-	else if (c == 1) { na = tk[1]; ns = s1; no = base + s3 + s2; }
-	else             { na = tk[0]; ns = s0; no = base + s3 + s2 + s1; }
-	na += l2_at(I, c) + 1;
+	if (!same) Bl = load_bucket(I, bl); else Bl = Bk;
+	two = !same;
+	const bool c1 = c & 1, c2 = c & 2;
+	uint64_t Uk, Wk, Ul, Wl;
+	{
+		uint32_t T, H, E;
+		bucket_the(Bk, mk, T, H, E);
+		const uint32_t v1 = nk - H - E + T, v2 = nk - H, v3 = nk - T;           // #A, #A+#C, #A+#C+#G among the first nk
+		const uint32_t ui = c2 ? (c1 ? nk : v3) : (c1 ? v2 : v1), wi = c2 ? (c1 ? v3 : v2) : (c1 ? v1 : 0u);
+		const uint32_t ulo = c2 ? (c1 ? (uint32_t)(bk << 6) : Bk.p3) : (c1 ? Bk.p2 : Bk.p1);
+		const uint32_t wlo = c2 ? (c1 ? Bk.p3 : Bk.p2) : (c1 ? Bk.p1 : 0u);
+		const uint32_t uhi = (c1 && c2) ? (uint32_t)(bk >> 26) : ((Bk.hi >> (8 * c)) & 0xff);
+		const uint32_t whi = c ? ((Bk.hi >> (8 * (c - 1))) & 0xff) : 0u;
+		Uk = (((uint64_t)uhi << 32) | ulo) + ui;
+		Wk = (((uint64_t)whi << 32) | wlo) + wi;
+	}
+	{
+		uint32_t T, H, E;
+		bucket_the(Bl, ml, T, H, E);
+		const uint32_t v1 = nl - H - E + T, v2 = nl - H, v3 = nl - T;
+		const uint32_t ui = c2 ? (c1 ? nl : v3) : (c1 ? v2 : v1), wi = c2 ? (c1 ? v3 : v2) : (c1 ? v1 : 0u);
+		const uint32_t ulo = c2 ? (c1 ? (uint32_t)(bl << 6) : Bl.p3) : (c1 ? Bl.p2 : Bl.p1);
+		const uint32_t wlo = c2 ? (c1 ? Bl.p3 : Bl.p2) : (c1 ? Bl.p1 : 0u);
+		const uint32_t uhi = (c1 && c2) ? (uint32_t)(bl >> 26) : ((Bl.hi >> (8 * c)) & 0xff);
+		const uint32_t whi = c ? ((Bl.hi >> (8 * (c - 1))) & 0xff) : 0u;
+		Ul = (((uint64_t)uhi << 32) | ulo) + ui;
+		Wl = (((uint64_t)whi << 32) | wlo) + wi;
+	}
+	const uint64_t tk = Uk - Wk, tl = Ul - Wl;
+	const uint64_t gsum = (ll - kk) - (Ul - Uk);
+	const uint64_t base = o + ((a <= I.primary) && (a + x2 - 1 >= I.primary));
+	const uint64_t na = l2_at(I, c) + 1 + tk, no = base + gsum;
 	o0 = is_back ? na : no;
 	o1 = is_back ? no : na;
-	o2 = ns;
+	o2 = tl - tk;
 }
 
 // all four children (for the cs_extend probe): ok[c*3 + j]
@@ -140,8 +251,7 @@ __device__ __forceinline__ uint64_t dev_lf(const DevIndex &I, uint64_t k)
 	uint64_t b = x >> 6;
 	uint32_t r = (uint32_t)x & 63;
 	Bucket B = load_bucket(I, b);
-	uint64_t w = r < 32 ? B.w0 : B.w1;
-	uint32_t c = (uint32_t)(w >> (2 * (r & 31))) & 3;
+	uint32_t c = bucket_base(B, r);
 	// occ(k, c) counts rows [0..k] inclusive; k - (k >= primary) == x for k != primary
 	uint64_t cnt[4];
 	bucket_occ4(B, b, r, cnt);

@@ -223,7 +223,7 @@ __global__ void k_bwt_buckets(const uint64_t *W, const uint64_t *safull, uint64_
 __global__ void k_bucket_counts(const uint64_t *exA, const uint64_t *exC, const uint64_t *exG, uint4 *buckets, uint64_t n_buckets)
 {
 	for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < n_buckets; b += (uint64_t)gridDim.x * blockDim.x) {
-		uint64_t a = exA[b], c = exC[b], g = exG[b];
+		uint64_t a = exA[b], c = a + exC[b], g = c + exG[b];   // prefix sums #A, #A+#C, #A+#C+#G (cs_device.cuh)
 		buckets[2 * b + 1] = make_uint4((uint32_t)a, (uint32_t)c, (uint32_t)g,
 		                                ((uint32_t)(a >> 32) & 0xff) | (((uint32_t)(c >> 32) & 0xff) << 8) | (((uint32_t)(g >> 32) & 0xff) << 16));
 	}

@@ -41,8 +41,9 @@ __global__ void k_relayout(const uint32_t *src, uint64_t src_words, uint64_t seq
 		uint64_t w1 = (uint64_t)msb_to_lsb16(ws[2]) | ((uint64_t)msb_to_lsb16(ws[3]) << 32);
 		uint4 lo, hi;
 		lo.x = (uint32_t)w0; lo.y = (uint32_t)(w0 >> 32); lo.z = (uint32_t)w1; lo.w = (uint32_t)(w1 >> 32);
-		hi.x = (uint32_t)cnt[0]; hi.y = (uint32_t)cnt[1]; hi.z = (uint32_t)cnt[2];
-		hi.w = ((uint32_t)(cnt[0] >> 32) & 0xff) | (((uint32_t)(cnt[1] >> 32) & 0xff) << 8) | (((uint32_t)(cnt[2] >> 32) & 0xff) << 16);
+		const uint64_t p1 = cnt[0], p2 = p1 + cnt[1], p3 = p2 + cnt[2];   // prefix-sum checkpoint (cs_device.cuh)
+		hi.x = (uint32_t)p1; hi.y = (uint32_t)p2; hi.z = (uint32_t)p3;
+		hi.w = ((uint32_t)(p1 >> 32) & 0xff) | (((uint32_t)(p2 >> 32) & 0xff) << 8) | (((uint32_t)(p3 >> 32) & 0xff) << 16);
 		dst[2 * b] = lo; dst[2 * b + 1] = hi;
 	}
 }
@@ -60,17 +61,17 @@ __global__ void k_unlayout(const uint4 *src, uint64_t seq_len, uint32_t *dst, ui
 		uint64_t nb = (seq_len + 63) >> 6;
 		if (b < nb) {
 			uint4 h = src[2 * b + 1];
-			cnt[0] = (uint64_t)h.x | ((uint64_t)(h.w & 0xff) << 32);
-			cnt[1] = (uint64_t)h.y | ((uint64_t)((h.w >> 8) & 0xff) << 32);
-			cnt[2] = (uint64_t)h.z | ((uint64_t)((h.w >> 16) & 0xff) << 32);
-			cnt[3] = row0 - cnt[0] - cnt[1] - cnt[2];
+			uint64_t p1 = (uint64_t)h.x | ((uint64_t)(h.w & 0xff) << 32);
+			uint64_t p2 = (uint64_t)h.y | ((uint64_t)((h.w >> 8) & 0xff) << 32);
+			uint64_t p3 = (uint64_t)h.z | ((uint64_t)((h.w >> 16) & 0xff) << 32);
+			cnt[0] = p1; cnt[1] = p2 - p1; cnt[2] = p3 - p2; cnt[3] = row0 - p3;
 		} else { // row0 >= seq_len: totals = checkpoint of the last bucket + its bases
 			uint64_t lb = nb - 1;
 			uint4 l = src[2 * lb], h = src[2 * lb + 1];
-			cnt[0] = (uint64_t)h.x | ((uint64_t)(h.w & 0xff) << 32);
-			cnt[1] = (uint64_t)h.y | ((uint64_t)((h.w >> 8) & 0xff) << 32);
-			cnt[2] = (uint64_t)h.z | ((uint64_t)((h.w >> 16) & 0xff) << 32);
-			cnt[3] = (lb << 6) - cnt[0] - cnt[1] - cnt[2];
+			uint64_t p1 = (uint64_t)h.x | ((uint64_t)(h.w & 0xff) << 32);
+			uint64_t p2 = (uint64_t)h.y | ((uint64_t)((h.w >> 8) & 0xff) << 32);
+			uint64_t p3 = (uint64_t)h.z | ((uint64_t)((h.w >> 16) & 0xff) << 32);
+			cnt[0] = p1; cnt[1] = p2 - p1; cnt[2] = p3 - p2; cnt[3] = (lb << 6) - p3;
 			uint64_t w0 = (uint64_t)l.x | ((uint64_t)l.y << 32), w1 = (uint64_t)l.z | ((uint64_t)l.w << 32);
 			for (uint64_t r = lb << 6; r < seq_len; ++r) {
 				uint32_t i = (uint32_t)(r & 63);
@@ -184,7 +185,7 @@ __global__ void k_text_from_index(DevIndex I, unsigned long long *W)
 			uint64_t x = r - (r > I.primary);
 			uint64_t b = x >> 6; uint32_t q = (uint32_t)x & 63;
 			Bucket B = load_bucket(I, b);
-			uint32_t c = (uint32_t)((q < 32 ? B.w0 : B.w1) >> (2 * (q & 31))) & 3;
+			uint32_t c = bucket_base(B, q);
 			--p;
 			if (c) atomicOr(W + (p >> 5), (unsigned long long)c << (62 - 2 * (p & 31)));
 			uint64_t cnt[4];
@@ -286,7 +287,9 @@ enum { ST_FETCH = 0, ST_R1_PIVOT, ST_FWD, ST_BWD_INIT, ST_PRUNE, ST_BWD_SWEEP, S
 
 __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIndex I, SeedArgs a)
 {
-	extern __shared__ uint4 s_list[];
+	extern __shared__ uint4 s_list[];                     // [CS_LIST_SMEM][CS_SEED_BLOCK] interval lists
+	uint64_t *s_rd = reinterpret_cast<uint64_t*>(s_list + CS_LIST_SMEM * CS_SEED_BLOCK);   // [CS_READ_SMEM][CS_SEED_BLOCK] packed read
+	uint32_t *s_nm = reinterpret_cast<uint32_t*>(s_rd + CS_READ_SMEM * CS_SEED_BLOCK);     // [CS_READ_SMEM][CS_SEED_BLOCK] N mask
 	const int t = threadIdx.x;
 	const size_t nthreads = (size_t)gridDim.x * CS_SEED_BLOCK;
 	const size_t gtid = (size_t)blockIdx.x * CS_SEED_BLOCK + t;
@@ -296,8 +299,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 	unsigned long long n_ext = 0, n_call = 0, n_two = 0, n_probe = 0;
 	int st = ST_FETCH;
 	uint32_t rd = 0; int len = 0;
-	const uint8_t *q = nullptr;
-	const uint64_t *pw = nullptr;                         // this read, 2-bit packed
+	const uint64_t *pw = nullptr;                         // this read, 2-bit packed (first CS_READ_SMEM words also in s_rd)
 	// occurrence filter usable only if a filtered match is certain to be shorter than min_seed_len
 	const int prune_k = (I.pt_k > 0 && opt.min_seed_len >= (int)I.pt_k) ? (int)I.pt_k : 0;
 	uint32_t nmem = 0, old_n = 0, r2k = 0;
@@ -330,12 +332,35 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 		} else err_mem = true;
 		++nmem;
 	};
+	// the read in flight: 2 bits per base + N mask, words 0..CS_READ_SMEM-1 from shared memory
+	auto rd_word = [&](int tt, const uint64_t *gp, uint32_t wi) -> uint64_t {
+		return wi < CS_READ_SMEM ? s_rd[wi * CS_SEED_BLOCK + tt] : __ldg(gp + wi);
+	};
+	auto nm_word = [&](int tt, const uint64_t *gp, uint32_t wi) -> uint32_t {
+		return wi < CS_READ_SMEM ? s_nm[wi * CS_SEED_BLOCK + tt] : __ldg(a.nmask + (gp - a.packed) + wi);
+	};
+	auto base_at = [&](int pos) -> int { // nt4 code of q[pos]: 0..3, or 4 for an ambiguous base
+		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
+		return ((nm_word(t, pw, wi) >> sh) & 1) ? 4 : (int)((rd_word(t, pw, wi) >> (2 * sh)) & 3);
+	};
+	auto key_of = [&](int tt, const uint64_t *gp, int pos, int cnt) -> uint64_t { // the cnt (<= 32) bases from pos, base j at bits 2j
+		uint32_t wi = (uint32_t)pos >> 5, sh = ((uint32_t)pos & 31) * 2;
+		uint64_t v = rd_word(tt, gp, wi) >> sh;
+		if (sh) v |= rd_word(tt, gp, wi + 1) << (64 - sh);
+		return cnt >= 32 ? v : (v & ((1ull << (2 * cnt)) - 1));
+	};
+	auto has_n = [&](int tt, const uint64_t *gp, int pos, int cnt) -> bool { // any ambiguous / out-of-read base in [pos, pos+cnt), cnt < 32
+		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
+		uint32_t m = nm_word(tt, gp, wi) >> sh;
+		if (sh) m |= nm_word(tt, gp, wi + 1) << (32 - sh);
+		return (m & ((1u << cnt) - 1u)) != 0;
+	};
 	auto set_intv = [&](int b) { // bwt_set_intv, bwt.h:82
 		c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
 	};
 	auto start_call = [&](int pivot, uint64_t mi) { // bwt_smem1a prologue, bwt.c:295-302
 		x = pivot; min_intv = mi < 1 ? 1 : mi;
-		set_intv(q[x]);
+		set_intv(base_at(x));
 		i = x + 1; n = 0; call_nmem = 0;
 		st = ST_FWD;
 	};
@@ -356,19 +381,30 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 				rd = atomicAdd(a.next_read, 1u);
 				if (rd >= a.n_reads) { st = ST_IDLE; break; }
 				uint32_t o = a.off[rd];
-				q = a.bases + o; len = (int)(a.off[rd + 1] - o);
+				len = (int)(a.off[rd + 1] - o);
 				pw = a.packed + ((uint64_t)(o >> 5) + 2ull * rd);
+				{
+					const uint32_t *gn = a.nmask + (pw - a.packed);
+					const uint32_t nw = ((uint32_t)len >> 5) + 2;
+					for (uint32_t wi = 0; wi < CS_READ_SMEM; ++wi) {
+						s_rd[wi * CS_SEED_BLOCK + t] = wi < nw ? __ldg(pw + wi) : 0ull;
+						s_nm[wi * CS_SEED_BLOCK + t] = wi < nw ? __ldg(gn + wi) : 0xffffffffu;
+					}
+				}
 				nmem = 0; round = 1; x = 0; err_list = err_mem = false;
 				st = ST_R1_PIVOT;
 			} break;
 			case ST_R1_PIVOT: // first pass of mem_collect_intv, bwamem.c:226-236
-				while (x < len && q[x] > 3) ++x;
+				while (x < len && base_at(x) > 3) ++x;
 				if (x >= len) { old_n = nmem; r2k = 0; st = ST_R2_NEXT; }
 				else start_call(x, 1);
 				break;
 			case ST_FWD: // forward extension, bwt.c:304-321
-				if (i >= len || q[i] > 3) { list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i)); st = ST_BWD_INIT; }
-				else { c = 3 - q[i]; need = true; }
+				{
+					int b = i < len ? base_at(i) : 4;
+					if (b > 3) { list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i)); st = ST_BWD_INIT; }
+					else { c = 3 - b; need = true; }
+				}
 				break;
 			case ST_BWD_INIT: // bwt.c:322-326; list[n-1] is the longest match
 				ret = (int)(list_get(n - 1).w >> 16);
@@ -376,7 +412,8 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 				st = prune_k ? ST_PRUNE : ST_BWD_SWEEP;   // ST_PRUNE is served by the whole warp below
 				break;
 			case ST_BWD_SWEEP: { // one value of i in bwt.c:326
-				c = bi < 0 ? -1 : (q[bi] < 4 ? q[bi] : -1);
+				c = bi < 0 ? -1 : base_at(bi);
+				if (c > 3) c = -1;
 				if (c < 0) { // every interval ends here; only the longest can be a new SMEM (bwt.c:331-337)
 					unpack_entry(list_get(n - 1), c0, c1, c2, cend);
 					mem_candidate();
@@ -423,6 +460,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 
 		// ---- explicit reconvergence: all 32 lanes meet here every trip; nobody leaves early ----
 		if (__all_sync(0xffffffffu, st == ST_IDLE)) break;
+		__syncwarp();   // vote intrinsics are not memory barriers: make every lane's list / read words visible to the warp
 
 		// ---- occurrence filter (result-neutral), served by the whole warp for one requesting lane at a
 		//      time.  A forward match [x, e) can only yield a mem of >= min_seed_len bases if q[e-K, e)
@@ -436,7 +474,6 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 			const int on = __shfl_sync(0xffffffffu, n, owner), ox = __shfl_sync(0xffffffffu, x, owner);
 			const uint64_t *opw = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)pw, owner));
 			const uint64_t omin = __shfl_sync(0xffffffffu, (unsigned long long)min_intv, owner);
-			const uint32_t *opn = a.nmask + (opw - a.packed);
 			const int ot = t - lane + owner; const size_t ogtid = gtid - lane + owner;
 			int kept = 0;
 			for (int base = 0; base < on; base += 32) {
@@ -448,8 +485,8 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 					    : ((uint32_t)(jj - CS_LIST_SMEM) < a.spill_cap ? a.spill[(size_t)(jj - CS_LIST_SMEM) * nthreads + ogtid] : ent);
 					const int e = (int)(ent.w >> 16), ws = e - prune_k;
 					if (e - ox >= prune_k) keep = true;                    // already long enough
-					else if (ws >= 0 && !read_has_n(opn, ws, ox - ws)) {   // else it ends at the read start / an N first
-						const uint64_t key = read_key(opw, ws, prune_k);
+					else if (ws >= 0 && !has_n(ot, opw, ws, ox - ws)) {     // else it ends at the read start / an N first
+						const uint64_t key = key_of(ot, opw, ws, prune_k);
 						const uint32_t cnt = (__ldg(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3;
 						keep = cnt == 3 || cnt >= omin;
 						++n_probe;
@@ -475,7 +512,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 		// look-ahead base for the step after this one, fetched together with the Occ sectors
 		const int pf_idx = is_back ? bi - 1 : i + 1;
 		uint32_t nb = 4;
-		if (pf_idx >= 0 && pf_idx < len) nb = q[pf_idx];
+		if (pf_idx >= 0 && pf_idx < len) nb = (uint32_t)base_at(pf_idx);
 		uint64_t o0, o1, o2;
 		{
 			// the extended string is q[x..i] (forward) or q[bi..cend) (backward); short strings come from
@@ -483,7 +520,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 			const int s_beg = is_back ? bi : x;
 			const int new_len = is_back ? (int)cend - bi : i + 1 - x;
 			++n_ext;
-			if (new_len <= (int)I.kt_depth) kt_lookup(I, (uint32_t)new_len, read_key(pw, s_beg, new_len), o0, o1, o2);
+			if (new_len <= (int)I.kt_depth) kt_lookup(I, (uint32_t)new_len, key_of(t, pw, s_beg, new_len), o0, o1, o2);
 			else { uint32_t two; dev_extend(I, c0, c1, c2, c, is_back, o0, o1, o2, two); ++n_call; n_two += two; }
 		}
 

@@ -5,8 +5,13 @@
 
 #define CS_SEED_BLOCK   256     // threads per CTA of the seeding kernel
 #ifndef CS_LIST_SMEM
-#define CS_LIST_SMEM    16      // interval-list entries per thread kept in shared memory
+#define CS_LIST_SMEM    12      // interval-list entries per thread kept in shared memory
 #endif
+#ifndef CS_READ_SMEM
+#define CS_READ_SMEM    5       // 32-base words of the read in flight kept in shared memory (160 bases)
+#endif
+// dynamic shared memory of k_seed: interval lists [entry][thread] + packed reads [word][thread] + N masks
+#define CS_SEED_SMEM_BYTES ((size_t)CS_SEED_BLOCK * (CS_LIST_SMEM * 16 + CS_READ_SMEM * 12))
 #ifndef CS_SEED_MINBLOCKS
 #define CS_SEED_MINBLOCKS 3     // CTAs per SM the register allocation of k_seed is tuned for
 #endif
