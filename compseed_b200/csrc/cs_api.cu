@@ -478,6 +478,7 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		const size_t smem = CS_SEED_SMEM_BYTES;
 		int per_sm = 0;
 		CK(cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(k_seed_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed, CS_SEED_BLOCK, smem));
 		if (per_sm < 1) { set_err(CS_E_CUDA, "k_seed does not fit on an SM"); goto fail; }
 		ctx->grid = idx->n_sm * per_sm;
@@ -571,7 +572,8 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt)
 	a.r3_mems = s->d_r3_mems; a.r3_n_mems = s->d_r3_n_mems;
 	a.counters = s->d_ctrl->counters; a.error = &s->d_ctrl->error;
 	// passes 1-2 (the spill stride inside the kernel follows the launched grid), then pass 3
-	k_seed<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
+	if (ctx->max_read_len + 32 <= 32 * CS_READ_SMEM) k_seed<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
+	else k_seed_long<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(s->ev[5], s->stream));
 	if (pass3) {

@@ -267,41 +267,51 @@ __global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, ui
 }
 
 // ---------------------------------------------------------------------------------------------
-// The seeding kernel.
+// The seeding kernel (passes 1 and 2 of mem_collect_intv).
 //
 // One read per THREAD, persistent threads, reads handed out in input order by an atomic counter
 // (neighbouring reordered reads run at the same time on neighbouring threads, so the sectors they
-// share are hit in L1/L2).  Every thread runs the three-round algorithm as an explicit state
-// machine whose only expensive step -- one bwt_extend == one or two 32-byte sector gathers -- is
-// executed convergently by the whole warp once per trip of the outer loop; the cheap, divergent
-// bookkeeping (list pushes, mem emission, pivot selection) happens in between.  With ~100k
-// threads resident this keeps ~100-200k independent random sector reads in flight, which is what
-// a latency-bound dependent-gather workload needs (hard part 3).
+// share are hit in L1/L2).  Every thread runs bwt_smem1a as an explicit state machine whose only
+// expensive step -- one bwt_extend == one or two 32-byte sector gathers -- is executed convergently
+// by the whole warp once per trip of the outer loop (__all_sync re-converges the 32 lanes every
+// trip; idle lanes never leave early); the cheap, divergent bookkeeping (list pushes, mem emission,
+// pivot selection) happens in between.  With ~114k threads resident this keeps ~150k independent
+// random sector reads in flight, which is what a latency-bound dependent-gather workload needs
+// (hard part 3).
 //
-// Interval lists (bwt_smem1a's prev/curr, FM_index/bwt.c:293-344) are a single in-place stack of
-// packed 16-byte entries: the first CS_LIST_SMEM per thread in shared memory (bank-conflict-free
-// [entry][thread] layout), the rest spilled to HBM.
+// Shared memory per thread: the interval list of bwt_smem1a (prev/curr, FM_index/bwt.c:293-344) as
+// ONE in-place stack of packed 16-byte entries ([entry][thread], bank-conflict free; entries beyond
+// CS_LIST_SMEM spill to HBM), and the read in flight, 2 bits per base + N mask (RW 32-base words;
+// RW == 0: read from global memory, for reads longer than 32*RW bases).
+//
+// Occurrence filter (result-neutral): at the start of every bwt_smem1a
+// call the warp tests, for one requesting lane at a time, the K-mers q[e-K, e) for e = x+1 .. x+K-1
+// (one 2-bit gather per lane).  A forward match [x, e) shorter than K whose K-mer window occurs
+// fewer than min_intv times, or runs into the read start / an N, cannot grow to min_seed_len >= K
+// bases: its own mem would be dropped by the length filter (bwamem.c:231-233,247) and it can neither
+// block nor unblock a longer match (it dies no later than any longer one), so it is never pushed.
 // ---------------------------------------------------------------------------------------------
-enum { ST_FETCH = 0, ST_R1_PIVOT, ST_FWD, ST_BWD_INIT, ST_PRUNE, ST_BWD_SWEEP, ST_BWD_ENTRY, ST_CALL_DONE, ST_R2_NEXT,
+enum { ST_FETCH = 0, ST_R1_PIVOT, ST_FILTER, ST_FWD, ST_BWD_INIT, ST_BWD_SWEEP, ST_BWD_ENTRY, ST_CALL_DONE, ST_R2_NEXT,
        ST_READ_DONE, ST_IDLE };
 
-__global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIndex I, SeedArgs a)
+template <int RW>
+__device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 {
 	extern __shared__ uint4 s_list[];                     // [CS_LIST_SMEM][CS_SEED_BLOCK] interval lists
-	uint64_t *s_rd = reinterpret_cast<uint64_t*>(s_list + CS_LIST_SMEM * CS_SEED_BLOCK);   // [CS_READ_SMEM][CS_SEED_BLOCK] packed read
-	uint32_t *s_nm = reinterpret_cast<uint32_t*>(s_rd + CS_READ_SMEM * CS_SEED_BLOCK);     // [CS_READ_SMEM][CS_SEED_BLOCK] N mask
+	uint64_t *s_rd = reinterpret_cast<uint64_t*>(s_list + CS_LIST_SMEM * CS_SEED_BLOCK);       // [RW][CS_SEED_BLOCK] packed read
+	uint32_t *s_nm = reinterpret_cast<uint32_t*>(s_rd + (RW ? RW : 1) * CS_SEED_BLOCK);        // [RW][CS_SEED_BLOCK] N mask
 	const int t = threadIdx.x;
 	const size_t nthreads = (size_t)gridDim.x * CS_SEED_BLOCK;
 	const size_t gtid = (size_t)blockIdx.x * CS_SEED_BLOCK + t;
-	cs_mem_t *my = a.thread_mems + gtid * a.mem_cap;
+	cs_mem_t *const my = a.thread_mems + gtid * a.mem_cap;
 	const cs_seed_opt_t opt = a.opt;
+	// the filter is usable only if a filtered match is certain to be shorter than min_seed_len
+	const int prune_k = (I.pt_k > 0 && opt.min_seed_len >= (int)I.pt_k) ? (int)I.pt_k : 0;
 
 	unsigned long long n_ext = 0, n_call = 0, n_two = 0, n_probe = 0;
 	int st = ST_FETCH;
 	uint32_t rd = 0; int len = 0;
-	const uint64_t *pw = nullptr;                         // this read, 2-bit packed (first CS_READ_SMEM words also in s_rd)
-	// occurrence filter usable only if a filtered match is certain to be shorter than min_seed_len
-	const int prune_k = (I.pt_k > 0 && opt.min_seed_len >= (int)I.pt_k) ? (int)I.pt_k : 0;
+	const uint64_t *pw = nullptr;                         // this read, 2-bit packed, in global memory
 	uint32_t nmem = 0, old_n = 0, r2k = 0;
 	int round = 1;
 	int x = 0, i = 0, bi = 0, ret = 0;
@@ -310,6 +320,7 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 	bool pushed = false; uint64_t last_sz = 0;
 	uint64_t min_intv = 1;
 	uint32_t call_nmem = 0; int last_start = 0;
+	uint32_t kmask = 0xffffffffu;                         // bit d-1: a forward match of d < K bases may be pushed
 	int c = 0;
 	bool need = false;
 	bool err_list = false, err_mem = false;
@@ -332,37 +343,43 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 		} else err_mem = true;
 		++nmem;
 	};
-	// the read in flight: 2 bits per base + N mask, words 0..CS_READ_SMEM-1 from shared memory
+	// the read in flight: 2 bits per base + N mask
 	auto rd_word = [&](int tt, const uint64_t *gp, uint32_t wi) -> uint64_t {
-		return wi < CS_READ_SMEM ? s_rd[wi * CS_SEED_BLOCK + tt] : __ldg(gp + wi);
+		if (RW) return s_rd[wi * CS_SEED_BLOCK + tt];
+		return __ldg(gp + wi);
 	};
 	auto nm_word = [&](int tt, const uint64_t *gp, uint32_t wi) -> uint32_t {
-		return wi < CS_READ_SMEM ? s_nm[wi * CS_SEED_BLOCK + tt] : __ldg(a.nmask + (gp - a.packed) + wi);
+		if (RW) return s_nm[wi * CS_SEED_BLOCK + tt];
+		return __ldg(a.nmask + (gp - a.packed) + wi);
 	};
 	auto base_at = [&](int pos) -> int { // nt4 code of q[pos]: 0..3, or 4 for an ambiguous base
 		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
 		return ((nm_word(t, pw, wi) >> sh) & 1) ? 4 : (int)((rd_word(t, pw, wi) >> (2 * sh)) & 3);
 	};
-	auto key_of = [&](int tt, const uint64_t *gp, int pos, int cnt) -> uint64_t { // the cnt (<= 32) bases from pos, base j at bits 2j
+	auto key_of = [&](int tt, const uint64_t *gp, int pos, int cnt) -> uint64_t { // cnt (< 32) bases from pos, base j at bits 2j
 		uint32_t wi = (uint32_t)pos >> 5, sh = ((uint32_t)pos & 31) * 2;
 		uint64_t v = rd_word(tt, gp, wi) >> sh;
 		if (sh) v |= rd_word(tt, gp, wi + 1) << (64 - sh);
-		return cnt >= 32 ? v : (v & ((1ull << (2 * cnt)) - 1));
+		return v & ((1ull << (2 * cnt)) - 1);
 	};
-	auto has_n = [&](int tt, const uint64_t *gp, int pos, int cnt) -> bool { // any ambiguous / out-of-read base in [pos, pos+cnt), cnt < 32
+	auto has_n = [&](int tt, const uint64_t *gp, int pos, int cnt) -> bool { // any N / out-of-read base in [pos, pos+cnt), cnt < 32
 		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
 		uint32_t m = nm_word(tt, gp, wi) >> sh;
 		if (sh) m |= nm_word(tt, gp, wi + 1) << (32 - sh);
 		return (m & ((1u << cnt) - 1u)) != 0;
 	};
-	auto set_intv = [&](int b) { // bwt_set_intv, bwt.h:82
-		c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
-	};
 	auto start_call = [&](int pivot, uint64_t mi) { // bwt_smem1a prologue, bwt.c:295-302
 		x = pivot; min_intv = mi < 1 ? 1 : mi;
-		set_intv(base_at(x));
-		i = x + 1; n = 0; call_nmem = 0;
-		st = ST_FWD;
+		int b = base_at(x);
+		c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b); // bwt_set_intv, bwt.h:82
+		i = x + 1; n = 0; call_nmem = 0; ret = x + 1;
+		st = prune_k ? ST_FILTER : ST_FWD;
+	};
+	// kv_push(curr, ik) of the forward pass (bwt.c:312,317,321) -- unless the filter proved the match useless
+	auto fwd_push = [&](int end) {
+		ret = end;                                       // bwt.c:323: the longest forward match ends here
+		int d = end - x;
+		if (d >= prune_k || ((kmask >> (d - 1)) & 1)) list_put(n++, pack_entry(c0, c1, c2, (uint32_t)end));
 	};
 	// a match [bi+1, cend) ends at this sweep: it is an SMEM only if no longer match survived the
 	// sweep and it is not contained in the previous one (bwt.c:332-336)
@@ -374,8 +391,8 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 	};
 
 	for (;;) {
-		// ---- divergent bookkeeping: advance this lane's state machine until it needs an extend ----
-		while (!need && st != ST_IDLE && st != ST_PRUNE) {
+		// ---- divergent bookkeeping: advance this lane's state machine until it needs the warp ----
+		while (!need && st != ST_IDLE && st != ST_FILTER) {
 			switch (st) {
 			case ST_FETCH: {
 				rd = atomicAdd(a.next_read, 1u);
@@ -383,10 +400,11 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 				uint32_t o = a.off[rd];
 				len = (int)(a.off[rd + 1] - o);
 				pw = a.packed + ((uint64_t)(o >> 5) + 2ull * rd);
-				{
+				if (RW) {
 					const uint32_t *gn = a.nmask + (pw - a.packed);
 					const uint32_t nw = ((uint32_t)len >> 5) + 2;
-					for (uint32_t wi = 0; wi < CS_READ_SMEM; ++wi) {
+#pragma unroll
+					for (uint32_t wi = 0; wi < (RW ? RW : 1); ++wi) {
 						s_rd[wi * CS_SEED_BLOCK + t] = wi < nw ? __ldg(pw + wi) : 0ull;
 						s_nm[wi * CS_SEED_BLOCK + t] = wi < nw ? __ldg(gn + wi) : 0xffffffffu;
 					}
@@ -399,17 +417,14 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 				if (x >= len) { old_n = nmem; r2k = 0; st = ST_R2_NEXT; }
 				else start_call(x, 1);
 				break;
-			case ST_FWD: // forward extension, bwt.c:304-321
-				{
-					int b = i < len ? base_at(i) : 4;
-					if (b > 3) { list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i)); st = ST_BWD_INIT; }
-					else { c = 3 - b; need = true; }
-				}
-				break;
-			case ST_BWD_INIT: // bwt.c:322-326; list[n-1] is the longest match
-				ret = (int)(list_get(n - 1).w >> 16);
-				bi = x - 1; lo = 0;
-				st = prune_k ? ST_PRUNE : ST_BWD_SWEEP;   // ST_PRUNE is served by the whole warp below
+			case ST_FWD: { // forward extension, bwt.c:304-321
+				int b = i < len ? base_at(i) : 4;
+				if (b > 3) { fwd_push(i); st = ST_BWD_INIT; }
+				else { c = 3 - b; need = true; }
+			} break;
+			case ST_BWD_INIT: // bwt.c:322-326; list[n-1] is the longest match that was kept
+				if (n == 0) st = ST_CALL_DONE;
+				else { bi = x - 1; lo = 0; st = ST_BWD_SWEEP; }
 				break;
 			case ST_BWD_SWEEP: { // one value of i in bwt.c:326
 				c = bi < 0 ? -1 : base_at(bi);
@@ -460,56 +475,32 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 
 		// ---- explicit reconvergence: all 32 lanes meet here every trip; nobody leaves early ----
 		if (__all_sync(0xffffffffu, st == ST_IDLE)) break;
-		__syncwarp();   // vote intrinsics are not memory barriers: make every lane's list / read words visible to the warp
+		__syncwarp();   // vote intrinsics are not memory barriers: make every lane's read words visible to the warp
 
-		// ---- occurrence filter (result-neutral), served by the whole warp for one requesting lane at a
-		//      time.  A forward match [x, e) can only yield a mem of >= min_seed_len bases if q[e-K, e)
-		//      occurs >= min_intv times (K <= min_seed_len) and lies inside the read without an N; a match
-		//      that cannot is dropped before the sweeps: its own mem would be discarded by the length
-		//      filter (bwamem.c:231-233,247), and it can neither block nor unblock a longer match (it dies
-		//      no later than any longer one).  Lane l tests entry l: one 2-bit gather replaces the entry's
-		//      whole column of backward extensions. ----
-		for (unsigned req = __ballot_sync(0xffffffffu, st == ST_PRUNE); req; req &= req - 1) {
+		// ---- occurrence filter, served by the whole warp for one requesting lane at a time: lane l
+		//      tests the window that ends l+1 bases after the pivot ----
+		for (unsigned req = __ballot_sync(0xffffffffu, st == ST_FILTER); req; req &= req - 1) {
 			const int owner = __ffs(req) - 1, lane = t & 31;
-			const int on = __shfl_sync(0xffffffffu, n, owner), ox = __shfl_sync(0xffffffffu, x, owner);
+			const int ox = __shfl_sync(0xffffffffu, x, owner);
 			const uint64_t *opw = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)pw, owner));
-			const uint64_t omin = __shfl_sync(0xffffffffu, (unsigned long long)min_intv, owner);
-			const int ot = t - lane + owner; const size_t ogtid = gtid - lane + owner;
-			int kept = 0;
-			for (int base = 0; base < on; base += 32) {
-				const int jj = base + lane;
-				bool keep = false;
-				uint4 ent = make_uint4(0, 0, 0, 0);
-				if (jj < on) {
-					ent = jj < CS_LIST_SMEM ? s_list[jj * CS_SEED_BLOCK + ot]
-					    : ((uint32_t)(jj - CS_LIST_SMEM) < a.spill_cap ? a.spill[(size_t)(jj - CS_LIST_SMEM) * nthreads + ogtid] : ent);
-					const int e = (int)(ent.w >> 16), ws = e - prune_k;
-					if (e - ox >= prune_k) keep = true;                    // already long enough
-					else if (ws >= 0 && !has_n(ot, opw, ws, ox - ws)) {     // else it ends at the read start / an N first
-						const uint64_t key = key_of(ot, opw, ws, prune_k);
-						const uint32_t cnt = (__ldg(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3;
-						keep = cnt == 3 || cnt >= omin;
-						++n_probe;
-					}
-				}
-				const unsigned km = __ballot_sync(0xffffffffu, keep);      // every lane holds its entry by now
-				if (keep) {
-					const int dst = kept + __popc(km & ((1u << lane) - 1));
-					if (dst != jj) {
-						if (dst < CS_LIST_SMEM) s_list[dst * CS_SEED_BLOCK + ot] = ent;
-						else a.spill[(size_t)(dst - CS_LIST_SMEM) * nthreads + ogtid] = ent;
-					}
-				}
-				kept += __popc(km);
-				__syncwarp();
+			const uint32_t omin = (uint32_t)__shfl_sync(0xffffffffu, (unsigned)(min_intv > 3 ? 4 : min_intv), owner);
+			const int ot = t - lane + owner;
+			const int ws = ox + 1 + lane - prune_k;           // window [ws, ws + K) ends lane+1 bases after the pivot
+			bool keep = false;
+			if (lane + 1 < prune_k && ws >= 0 && !has_n(ot, opw, ws, ox - ws)) { // else it ends at the read start / an N first
+				const uint64_t key = key_of(ot, opw, ws, prune_k);
+				const uint32_t cnt = (__ldg(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3;
+				keep = cnt == 3 || cnt >= omin;              // 3 == "3 or more"
+				++n_probe;
 			}
-			if (lane == owner) { n = kept; st = kept ? ST_BWD_SWEEP : ST_CALL_DONE; }
+			const unsigned km = __ballot_sync(0xffffffffu, keep);
+			if (lane == owner) { kmask = km; st = ST_FWD; }
 		}
 		if (!need) continue;
 
 		// ---- the one convergent, memory-bound step: bwt_extend of (c0,c1,c2) by base c ----
 		const int is_back = (st == ST_BWD_ENTRY);
-		// look-ahead base for the step after this one, fetched together with the Occ sectors
+		// look-ahead base for the step after this one
 		const int pf_idx = is_back ? bi - 1 : i + 1;
 		uint32_t nb = 4;
 		if (pf_idx >= 0 && pf_idx < len) nb = (uint32_t)base_at(pf_idx);
@@ -526,12 +517,12 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 
 		if (!is_back) { // ST_FWD, bwt.c:311-315
 			if (o2 != c2) {
-				list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i));
+				fwd_push(i);
 				if (o2 < min_intv) { st = ST_BWD_INIT; need = false; }
 			}
 			if (need) {
 				c0 = o0; c1 = o1; c2 = o2; ++i;
-				if (i >= len || nb > 3) { list_put(n++, pack_entry(c0, c1, c2, (uint32_t)i)); st = ST_BWD_INIT; need = false; }
+				if (i >= len || nb > 3) { fwd_push(i); st = ST_BWD_INIT; need = false; }
 				else c = 3 - (int)nb;
 			}
 		} else { // ST_BWD_ENTRY, bwt.c:331-341
@@ -555,6 +546,10 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 	if (n_two) atomicAdd(a.counters + 2, n_two);
 	if (n_probe) atomicAdd(a.counters + 3, n_probe);
 }
+
+__global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIndex I, SeedArgs a) { seed_body<CS_READ_SMEM>(I, a); }
+// reads longer than 32 * CS_READ_SMEM bases: the packed read stays in global memory
+__global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed_long(DevIndex I, SeedArgs a) { seed_body<0>(I, a); }
 
 // ---------------------------------------------------------------------------------------------
 // Third pass ("LAST-like", bwamem.c:253-268 + bwt_seed_strategy1, bwt.c:358-379) as its own kernel:

@@ -5,10 +5,10 @@
 
 #define CS_SEED_BLOCK   256     // threads per CTA of the seeding kernel
 #ifndef CS_LIST_SMEM
-#define CS_LIST_SMEM    12      // interval-list entries per thread kept in shared memory
+#define CS_LIST_SMEM    8       // interval-list entries per thread kept in shared memory
 #endif
 #ifndef CS_READ_SMEM
-#define CS_READ_SMEM    5       // 32-base words of the read in flight kept in shared memory (160 bases)
+#define CS_READ_SMEM    9       // 32-base words of the read in flight kept in shared memory (reads <= 256 bases + pad word)
 #endif
 // dynamic shared memory of k_seed: interval lists [entry][thread] + packed reads [word][thread] + N masks
 #define CS_SEED_SMEM_BYTES ((size_t)CS_SEED_BLOCK * (CS_LIST_SMEM * 16 + CS_READ_SMEM * 12))
@@ -72,6 +72,7 @@ __global__ void k_text_from_index(DevIndex I, unsigned long long *W);
 __global__ void k_pt_count(const uint64_t *W, uint64_t n, uint32_t K, uint32_t *pt);
 __global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t n_reads, uint64_t *packed, uint32_t *nmask);
 __global__ void k_seed(DevIndex I, SeedArgs a);
+__global__ void k_seed_long(DevIndex I, SeedArgs a);
 __global__ void k_seed_r3(DevIndex I, SeedArgs a);
 __global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, uint32_t n_reads, uint32_t *out);
 __global__ void k_collect_sort(CollectArgs a);
