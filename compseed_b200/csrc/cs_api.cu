@@ -54,6 +54,7 @@ struct cs_index {
 	uint64_t *d_sa;
 	uint4 *d_kt;            // top-of-search table (depths 1..d.kt_depth)
 	uint32_t *d_pt;         // occurrence filter (2-bit counts of all d.pt_k-mers)
+	uint64_t *d_text, *d_isa; // unique-match fast path: 2-bit text and sampled inverse SA
 	uint64_t bytes;
 	uint64_t bwt_size_ref;  // words of the reference layout
 	int sa_intv;
@@ -61,6 +62,36 @@ struct cs_index {
 };
 
 static int log2_exact(uint64_t v) { int s = 0; while ((1ull << s) < v) ++s; return (1ull << s) == v ? s : -1; }
+
+// Unique-match fast path (cs_device.cuh): 2-bit text in read bit order + sampled inverse SA.  Only with a
+// dense SA.  CS_ISA_INTV sets the ISA sampling (power of two, default 4; 0 disables the fast path).
+static int cs_internal_build_text(cs_index *idx, const uint64_t *W)
+{
+	const char *env = getenv("CS_ISA_INTV");
+	int intv = env ? atoi(env) : 4, shift = 0;
+	const uint64_t n = idx->d.seq_len;
+	idx->d.text = nullptr; idx->d.isa = nullptr; idx->d.isa_shift = 0; idx->d_text = nullptr; idx->d_isa = nullptr;
+	if (intv <= 0 || idx->d.sa_mask != 0 || !W) return CS_OK;
+	while ((1 << shift) < intv) ++shift;
+	{
+		const uint64_t n_words = (n + 31) / 32 + 2, n_isa = (n >> shift) + 2;
+		int grid = idx->n_sm * 8;
+		CK(cudaMalloc(&idx->d_text, n_words * 8));
+		k_text_lsb<<<grid, 256>>>(W, n_words, idx->d_text);
+		CK(cudaGetLastError());
+		CK(cudaMalloc(&idx->d_isa, n_isa * 8));
+		CK(cudaMemset(idx->d_isa, 0, n_isa * 8));
+		k_isa_sample<<<grid, 256>>>(idx->d, idx->d_isa, (uint32_t)shift);
+		CK(cudaGetLastError());
+		CK(cudaDeviceSynchronize());
+		idx->d.text = idx->d_text; idx->d.isa = idx->d_isa; idx->d.isa_shift = (uint32_t)shift;
+		idx->bytes += n_words * 8 + n_isa * 8;
+	}
+	return CS_OK;
+fail:
+	cudaFree(idx->d_text); cudaFree(idx->d_isa); idx->d_text = idx->d_isa = nullptr;
+	return CS_E_CUDA;
+}
 
 // Occurrence filter (cs_device.cuh, ST_PRUNE in k_seed): 2-bit saturating counts of all K-mers of the
 // indexed text, K = ceil(log4(seq_len)) + 2 capped at 19 (17 GB at K = 18, 69 GB at K = 19): long enough
@@ -73,24 +104,25 @@ int cs_internal_build_filter(cs_index *idx, const uint64_t *W)
 	int K = 2;
 	const char *env = getenv("CS_PRUNE_K");
 	const uint64_t n = idx->d.seq_len;
+	const int grid = idx->n_sm * 8;
 	while (K < 19 && (1ull << (2 * (K - 2))) < n) ++K;      // K - 2 >= log4(n)
 	if (K < 8) K = 8;
 	if (env) K = atoi(env);
-	idx->d.pt = nullptr; idx->d.pt_k = 0; idx->d_pt = nullptr;
-	if (K <= 0 || n < (uint64_t)K) return CS_OK;
-	if (K < 4) K = 4;
+	if (K > 0 && K < 4) K = 4;
 	if (K > 19) K = 19;
-	{
+	if (K < 0 || n < (uint64_t)K) K = 0;
+	idx->d.pt = nullptr; idx->d.pt_k = 0; idx->d_pt = nullptr;
+	idx->d.text = nullptr; idx->d.isa = nullptr; idx->d.isa_shift = 0; idx->d_text = nullptr; idx->d_isa = nullptr;
+	if (!W) { // rebuild the 2-bit text from the BWT and the SA
+		const uint64_t n_words = (n + 31) / 32 + 2;
+		CK(cudaMalloc(&own, n_words * 8));
+		CK(cudaMemset(own, 0, n_words * 8));
+		k_text_from_index<<<grid, 256>>>(idx->d, own);
+		CK(cudaGetLastError());
+		W = reinterpret_cast<const uint64_t*>(own);
+	}
+	if (K > 0) {
 		const uint64_t words = (1ull << (2 * K)) / 16;
-		int grid = idx->n_sm * 8;
-		if (!W) {
-			const uint64_t n_words = (n + 31) / 32 + 2;
-			CK(cudaMalloc(&own, n_words * 8));
-			CK(cudaMemset(own, 0, n_words * 8));
-			k_text_from_index<<<grid, 256>>>(idx->d, own);
-			CK(cudaGetLastError());
-			W = reinterpret_cast<const uint64_t*>(own);
-		}
 		CK(cudaMalloc(&idx->d_pt, words * 4));
 		CK(cudaMemset(idx->d_pt, 0, words * 4));
 		k_pt_count<<<grid, 256>>>(W, n, (uint32_t)K, idx->d_pt);
@@ -99,6 +131,7 @@ int cs_internal_build_filter(cs_index *idx, const uint64_t *W)
 		idx->d.pt = idx->d_pt; idx->d.pt_k = (uint32_t)K;
 		idx->bytes += words * 4;
 	}
+	if (cs_internal_build_text(idx, W) != CS_OK) goto fail;
 	if (own) cudaFree(own);
 	return CS_OK;
 fail:
@@ -298,7 +331,7 @@ extern "C" void cs_index_free(cs_index_t *idx)
 {
 	if (!idx) return;
 	cudaSetDevice(idx->device);
-	cudaFree(idx->d_buckets); cudaFree(idx->d_sa); cudaFree(idx->d_kt); cudaFree(idx->d_pt);
+	cudaFree(idx->d_buckets); cudaFree(idx->d_sa); cudaFree(idx->d_kt); cudaFree(idx->d_pt); cudaFree(idx->d_text); cudaFree(idx->d_isa);
 	free(idx);
 }
 

@@ -33,6 +33,13 @@ struct DevIndex {
 	// match that cannot grow to min_seed_len bases (see ST_PRUNE in k_seed).  0 = no filter.
 	const uint32_t *pt;
 	uint32_t pt_k;
+	// Unique-match fast path (k_seed, ST_TXT_*): the indexed text T = fwd + revcomp(fwd), 2 bits per
+	// base, 32 bases per u64 with base j of a word at bits 2j (like the packed reads), and the inverse
+	// suffix array sampled every 2^isa_shift text positions (isa[p >> isa_shift] = row of suffix p).
+	// Needs the dense SA (sa_mask == 0).  text == NULL: fast path off.
+	const uint64_t *text;
+	const uint64_t *isa;
+	uint32_t isa_shift;
 };
 
 struct Bucket { uint32_t w0, w1, w2, w3; uint32_t p1, p2, p3, hi; };
@@ -293,6 +300,15 @@ __device__ __forceinline__ bool read_has_n(const uint32_t *pn, int a, int cnt)
 	uint32_t m = __ldg(pn + w) >> sh;
 	if (sh) m |= __ldg(pn + w + 1) << (32 - sh);
 	return (m & ((cnt >= 32 ? 0u : (1u << cnt)) - 1u)) != 0;
+}
+
+// 32 consecutive bases of a 2-bit packed sequence (base j of a word at bits 2j) starting at position pos
+__device__ __forceinline__ uint64_t packed_window(const uint64_t *p, uint64_t pos)
+{
+	uint64_t w = pos >> 5; uint32_t sh = ((uint32_t)pos & 31) * 2;
+	uint64_t v = __ldg(p + w) >> sh;
+	if (sh) v |= __ldg(p + w + 1) << (64 - sh);
+	return v;
 }
 
 // packed interval-list entry (16 bytes): three 37-bit coordinates + 16-bit read position

@@ -196,6 +196,25 @@ __global__ void k_text_from_index(DevIndex I, unsigned long long *W)
 	}
 }
 
+// text in the bit order of the packed reads (base j of a word at bits 2j) from the builder's order (bits 62-2j)
+__global__ void k_text_lsb(const uint64_t *W, uint64_t n_words, uint64_t *out)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t v = __brevll(W[i]);                     // reverses bits: base order fixed, bit order inside a base swapped
+		out[i] = ((v & 0x5555555555555555ull) << 1) | ((v >> 1) & 0x5555555555555555ull);
+	}
+}
+
+// inverse suffix array sampled every 2^shift text positions, from the dense SA (sa[r] = text position of row r)
+__global__ void k_isa_sample(DevIndex I, uint64_t *isa, uint32_t shift)
+{
+	const uint64_t mask = (1ull << shift) - 1;
+	for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < I.n_sa; r += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t p = r == 0 ? I.seq_len : I.sa[r];
+		if ((p & mask) == 0) isa[p >> shift] = r;
+	}
+}
+
 #define PT_CHUNK 256
 __global__ void k_pt_count(const uint64_t *W, uint64_t n, uint32_t K, uint32_t *pt)
 {
@@ -292,7 +311,7 @@ __global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, ui
 // block nor unblock a longer match (it dies no later than any longer one), so it is never pushed.
 // ---------------------------------------------------------------------------------------------
 enum { ST_FETCH = 0, ST_R1_PIVOT, ST_FILTER, ST_FWD, ST_BWD_INIT, ST_BWD_SWEEP, ST_BWD_ENTRY, ST_CALL_DONE, ST_R2_NEXT,
-       ST_READ_DONE, ST_IDLE };
+       ST_READ_DONE, ST_TXT_SA, ST_TXT_CMP, ST_TXT_ISA, ST_TXT_LF, ST_IDLE };
 
 template <int RW>
 __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
@@ -321,6 +340,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 	uint64_t min_intv = 1;
 	uint32_t call_nmem = 0; int last_start = 0;
 	uint32_t kmask = 0xffffffffu;                         // bit d-1: a forward match of d < K bases may be pushed
+	uint64_t tpos = 0;                                    // ST_TXT_*: text position aligned with read position i
 	int c = 0;
 	bool need = false;
 	bool err_list = false, err_mem = false;
@@ -361,6 +381,18 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 		uint64_t v = rd_word(tt, gp, wi) >> sh;
 		if (sh) v |= rd_word(tt, gp, wi + 1) << (64 - sh);
 		return v & ((1ull << (2 * cnt)) - 1);
+	};
+	auto nmask_window = [&](int pos) -> uint32_t { // bit j: q[pos + j] is ambiguous or past the end of the read
+		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
+		uint32_t m = nm_word(t, pw, wi) >> sh;
+		if (sh) m |= nm_word(t, pw, wi + 1) << (32 - sh);
+		return m;
+	};
+	auto read_window = [&](int pos) -> uint64_t { // the 32 bases from pos, base j at bits 2j
+		uint32_t wi = (uint32_t)pos >> 5, sh = ((uint32_t)pos & 31) * 2;
+		uint64_t v = rd_word(t, pw, wi) >> sh;
+		if (sh) v |= rd_word(t, pw, wi + 1) << (64 - sh);
+		return v;
 	};
 	auto has_n = [&](int tt, const uint64_t *gp, int pos, int cnt) -> bool { // any N / out-of-read base in [pos, pos+cnt), cnt < 32
 		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
@@ -498,6 +530,46 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 		}
 		if (!need) continue;
 
+		// ---- unique-match fast path (result-neutral).  Once the forward interval holds ONE occurrence
+		//      (x[2] == 1, min_intv == 1) every further bwt_extend only asks "does the next read base equal
+		//      the next text base": x[0] stays the row of that occurrence, nothing is pushed while the size
+		//      stays 1 (bwt.c:311), and the extension ends at the first mismatch / N / end.  So: one SA
+		//      gather for the text position, 32 bases per step compared against the 2-bit text, then x[1] =
+		//      row of the reverse-complement occurrence from the sampled inverse SA plus < 2^isa_shift LF steps. ----
+		if (st >= ST_TXT_SA && st <= ST_TXT_LF) {
+			bool fin = false;
+			if (st == ST_TXT_SA) {
+				tpos = __ldg(I.sa + c0) + (uint64_t)(i - x);
+				j = 0; st = ST_TXT_CMP;
+			} else if (st == ST_TXT_CMP) {
+				const uint64_t diff = read_window(i) ^ packed_window(I.text, tpos);
+				const uint32_t nmw = nmask_window(i);
+				uint32_t m = diff ? (uint32_t)(__ffsll((long long)diff) - 1) >> 1 : 32u;
+				const uint32_t nn = nmw ? (uint32_t)__ffs((int)nmw) - 1u : 32u;
+				const uint64_t left = I.seq_len - tpos;
+				if (nn < m) m = nn;
+				if (left < m) m = (uint32_t)left;
+				i += (int)m; tpos += m; j += (int)m;
+				if (m < 32) { if (j > 0) st = ST_TXT_ISA; else fin = true; }
+			} else if (st == ST_TXT_ISA) {
+				const uint64_t sp = I.seq_len - tpos;                   // where revcomp(match) starts in the text
+				const uint64_t smask = (1ull << I.isa_shift) - 1;
+				uint64_t jj = (sp + smask) & ~smask;
+				if (jj > I.seq_len) jj = I.seq_len;
+				c1 = jj == I.seq_len ? 0ull : __ldg(I.isa + (jj >> I.isa_shift));   // row of suffix jj ('$' suffix: row 0)
+				w = (int)(jj - sp);
+				if (w == 0) fin = true; else st = ST_TXT_LF;
+			} else {
+				c1 = dev_lf(I, c1);                                      // row of the preceding suffix
+				if (--w == 0) fin = true;
+			}
+			if (fin) { // the forward pass ends here: at an N, the read end, the text end, or a mismatch (child size 0 != 1)
+				n_ext += (unsigned)j + 1;
+				fwd_push(i); st = ST_BWD_INIT; need = false;
+			}
+			continue;
+		}
+
 		// ---- the one convergent, memory-bound step: bwt_extend of (c0,c1,c2) by base c ----
 		const int is_back = (st == ST_BWD_ENTRY);
 		// look-ahead base for the step after this one
@@ -523,6 +595,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 			if (need) {
 				c0 = o0; c1 = o1; c2 = o2; ++i;
 				if (i >= len || nb > 3) { fwd_push(i); st = ST_BWD_INIT; need = false; }
+				else if (I.text != nullptr && c2 == 1 && min_intv == 1) st = ST_TXT_SA;   // unique from here on
 				else c = 3 - (int)nb;
 			}
 		} else { // ST_BWD_ENTRY, bwt.c:331-341
