@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--sa-intv", type=int, default=1, help="device SA sampling (1 = dense; 32 = the reference's on-disk sampling)")
-    ap.add_argument("--e2e-batch", type=int, default=1 << 19, help="reads per pipelined batch on the host-buffer path")
+    ap.add_argument("--e2e-batch", type=int, default=1 << 21, help="reads per pipelined batch on the host-buffer path")
     ap.add_argument("--cpu-sample", type=int, default=300_000, help="reads of the same workload timed on the host cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -350,12 +350,14 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": {"workload": workload_name(args, world), "sa_intv_device": args.sa_intv, "index_bytes_per_gpu": idx.device_bytes,
+                       "result_neutral_structures": "dense SA, top-of-search k-mer table (depth <= 13), 2-bit occurrence filter (K <= 19), "
+                                                    "2-bit text + sampled inverse SA for unique matches (DESIGN.md section 5)",
                        "l2_policy": "inputs larger than L2 (index %.1f GB, reads %.1f GB per step)" % (idx.device_bytes / 1e9, bases.nbytes / 1e9),
                        "parallelism": f"index replicated x{world}, reads sharded in contiguous blocks, host gather, no collective"},
             "occ_lookups_per_s": occ_per_read * value, "occ_lookups_per_read": occ_per_read,
             "mems_per_read": n_mems / n_reads, "seeds_per_read": n_seeds / n_reads,
             "wall_ms_per_step": wall_ms_max / args.steps,
-            "e2e": e2e, "gpu_launches": 6 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "gpu_launches": 7 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "counters": counters, "setup_s": setup_s}
     print(json.dumps(line))
     if use_dist:
