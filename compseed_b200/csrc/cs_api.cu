@@ -422,9 +422,10 @@ fail:
 // batch contexts
 // ---------------------------------------------------------------------------------------------
 struct Ctrl { // zeroed before every run; copied back after it
-	uint32_t next_read, pad0;
+	uint32_t next_read[3];   // work counters: [0] k_seed, [1] k_seed_r3, [2] k_seed_fast
+	uint32_t n_defer;        // reads k_seed_fast handed to k_seed
 	unsigned long long pool_used;
-	unsigned long long counters[4];
+	unsigned long long counters[4 + 32];   // [4..19] k_seed, [20..35] k_seed_fast: event counters of a -DCS_STATS diagnostics build, else 0
 	unsigned long long sa_work, lf_steps;
 	int error, pad1;
 	uint32_t n_mems, n_seeds;
@@ -432,7 +433,7 @@ struct Ctrl { // zeroed before every run; copied back after it
 
 struct Slot {
 	cudaStream_t stream;
-	cudaEvent_t ev[6];   // slot start, seed start, seed end, collect end, sa end, k_seed end (k_seed_r3 runs after it)
+	cudaEvent_t ev[7];   // slot start, seed start, seed end, collect end, sa end, k_seed end (k_seed_r3 runs after it), k_seed_fast end
 	cudaEvent_t ev_done;
 	// pinned host
 	uint8_t *h_bases; uint32_t *h_off;
@@ -441,6 +442,10 @@ struct Slot {
 	// device
 	uint8_t *d_bases; uint32_t *d_off;
 	uint64_t *d_packed; uint32_t *d_nmask;   // 2-bit packed reads + ambiguity mask (k_pack_reads)
+	uint4 *d_defer_q;                         // calls the fast kernel hands to the literal kernel (SeedArgs::defer_q)
+	uint32_t *d_read_last_q, *d_x_n; uint64_t *d_x_off;
+	cs_mem_t *d_stage;                        // collect: a read's sources gathered before the sort
+	bool used_fast;
 	Ctrl *d_ctrl;
 	cs_mem_t *d_thread_mems; uint4 *d_spill;
 	cs_mem_t *d_pool, *d_mems;
@@ -462,19 +467,20 @@ struct cs_ctx {
 	uint64_t max_bases, max_mems, max_seeds;
 	int n_slots;
 	int grid;             // CTAs of k_seed
+	int grid_fast;        // CTAs of k_seed_fast (0: the index or the read length does not allow the fast kernel)
 	int grid_r3;          // CTAs of k_seed_r3
-	uint32_t mem_cap, spill_cap;
+	uint32_t mem_cap, spill_cap, defer_cap;
 	Slot *slots;
 };
 
 static void slot_free(Slot *s)
 {
 	if (s->stream) cudaStreamDestroy(s->stream);
-	for (int i = 0; i < 6; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+	for (int i = 0; i < 7; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
 	if (s->ev_done) cudaEventDestroy(s->ev_done);
 	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
 	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
-	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
+	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
 	cudaFree(s->d_pool); cudaFree(s->d_mems); cudaFree(s->d_read_pool_off); cudaFree(s->d_read_n_mems);
 	cudaFree(s->d_r3_mems); cudaFree(s->d_r3_n_mems); cudaFree(s->d_tot_n_mems);
 	cudaFree(s->d_mem_off); cudaFree(s->d_read_n_seeds); cudaFree(s->d_seed_off); cudaFree(s->d_rows); cudaFree(s->d_scan_tmp);
@@ -517,6 +523,19 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		ctx->grid = idx->n_sm * per_sm;
 		uint32_t need = (max_reads + CS_SEED_BLOCK - 1) / CS_SEED_BLOCK;
 		if ((uint32_t)ctx->grid > need) ctx->grid = (int)need;
+		// the fast kernel needs the 2-bit text + inverse SA, the occurrence filter, the top-of-search table, and
+		// reads that fit its shared-memory words; otherwise k_seed takes every read
+		ctx->grid_fast = 0;
+		{
+			const char *env = getenv("CS_FAST");
+			const DevIndex &d = idx->d;
+			if (!(env && atoi(env) == 0) && d.text && d.isa && d.pt && d.pt_k >= 4 && d.pt_k <= 19 && d.kt && d.kt_depth >= 2 &&
+			    d.kt_depth < d.pt_k && max_read_len + 32 <= 32 * CS_READ_SMEM) {
+				CK(cudaFuncSetAttribute(k_seed_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_FAST_SMEM_BYTES));
+				CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed_fast, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES));
+				if (per_sm >= 1) ctx->grid_fast = std::min<int>(idx->n_sm * per_sm, (int)((max_reads + CS_FAST_BLOCK - 1) / CS_FAST_BLOCK));
+			}
+		}
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed_r3, 256, 0));
 		if (per_sm < 1) per_sm = 1;
 		ctx->grid_r3 = idx->n_sm * per_sm;
@@ -524,11 +543,12 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 	}
 	ctx->mem_cap = std::min<uint32_t>(2 * max_read_len + 16, 4096);
 	ctx->spill_cap = max_read_len > CS_LIST_SMEM ? max_read_len - CS_LIST_SMEM + 1 : 1;
+	ctx->defer_cap = 2 * max_reads + 4096;   // a batch that defers more calls than this is rerun without the fast kernel
 	for (int i = 0; i < n_slots; ++i) {
 		Slot *s = &ctx->slots[i];
-		const size_t nthreads = (size_t)ctx->grid * CS_SEED_BLOCK;
+		const size_t nthreads = std::max((size_t)ctx->grid * CS_SEED_BLOCK, (size_t)ctx->grid_fast * CS_FAST_BLOCK);
 		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-		for (int e = 0; e < 6; ++e) CK(cudaEventCreate(&s->ev[e]));
+		for (int e = 0; e < 7; ++e) CK(cudaEventCreate(&s->ev[e]));
 		CK(cudaEventCreate(&s->ev_done));
 		CK(cudaMallocHost(&s->h_bases, max_bases));
 		CK(cudaMallocHost(&s->h_off, ((size_t)max_reads + 1) * 4));
@@ -538,6 +558,11 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		CK(cudaMalloc(&s->d_packed, ((max_bases >> 5) + 2 * (size_t)max_reads + 4) * 8));
 		CK(cudaMalloc(&s->d_nmask, ((max_bases >> 5) + 2 * (size_t)max_reads + 4) * 4));
 		CK(cudaMalloc(&s->d_ctrl, sizeof(Ctrl)));
+		CK(cudaMalloc(&s->d_defer_q, (size_t)ctx->defer_cap * sizeof(uint4)));
+		CK(cudaMalloc(&s->d_x_off, (size_t)ctx->defer_cap * 8));
+		CK(cudaMalloc(&s->d_x_n, (size_t)ctx->defer_cap * 4));
+		CK(cudaMalloc(&s->d_read_last_q, ((size_t)max_reads + 1) * 4));
+		CK(cudaMalloc(&s->d_stage, ctx->max_mems * sizeof(cs_mem_t)));
 		CK(cudaMalloc(&s->d_thread_mems, nthreads * ctx->mem_cap * sizeof(cs_mem_t)));
 		CK(cudaMalloc(&s->d_spill, nthreads * ctx->spill_cap * sizeof(uint4)));
 		CK(cudaMalloc(&s->d_pool, ctx->max_mems * sizeof(cs_mem_t)));
@@ -570,7 +595,7 @@ static int check_slot(cs_ctx *ctx, int slot)
 }
 
 // enqueue everything that runs on the device for one batch whose inputs are already in d_bases/d_off
-static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt)
+static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allow_fast = true)
 {
 	const cs_index *idx = ctx->idx;
 	const uint32_t n = s->n_reads;
@@ -597,14 +622,27 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt)
 	CK(cudaGetLastError());
 	a.bases = s->d_bases; a.off = s->d_off; a.n_reads = n; a.opt = *opt;
 	a.packed = s->d_packed; a.nmask = s->d_nmask;
-	a.next_read = &s->d_ctrl->next_read;
+	a.next_read = s->d_ctrl->next_read;
+	a.defer_q = nullptr; a.defer_cap = ctx->defer_cap; a.n_defer = &s->d_ctrl->n_defer;
+	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n;
+	s->used_fast = false;
 	a.thread_mems = s->d_thread_mems; a.mem_cap = ctx->mem_cap;
 	a.spill = s->d_spill; a.spill_cap = ctx->spill_cap;
 	a.pool = s->d_pool; a.pool_cap = ctx->max_mems; a.pool_used = &s->d_ctrl->pool_used;
 	a.read_pool_off = s->d_read_pool_off; a.read_n_mems = s->d_read_n_mems;
 	a.r3_mems = s->d_r3_mems; a.r3_n_mems = s->d_r3_n_mems;
 	a.counters = s->d_ctrl->counters; a.error = &s->d_ctrl->error;
-	// passes 1-2 (the spill stride inside the kernel follows the launched grid), then pass 3
+	// passes 1-2: the call-synchronous fast kernel first; the reads it cannot prove simple (or all reads, when it
+	// is not available, or when min_seed_len is below the filter's K) go through the literal kernel
+	if (allow_fast && ctx->grid_fast > 0 && opt->min_seed_len >= (int)idx->d.pt_k) {
+		int gf = std::min<int>(ctx->grid_fast, (int)((n + CS_FAST_BLOCK - 1) / CS_FAST_BLOCK));
+		a.defer_q = s->d_defer_q;
+		s->used_fast = true;
+		k_seed_fast<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, s->stream>>>(idx->d, a);
+		CK(cudaGetLastError());
+	}
+	CK(cudaEventRecord(s->ev[6], s->stream));
+	// (the spill stride inside k_seed follows the launched grid), then pass 3
 	if (ctx->max_read_len + 32 <= 32 * CS_READ_SMEM) k_seed<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
 	else k_seed_long<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
 	CK(cudaGetLastError());
@@ -616,12 +654,14 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt)
 	}
 	CK(cudaEventRecord(s->ev[2], s->stream));
 	// collect: offsets, sort, SA rows
-	k_mem_counts<<<std::min<int>(idx->n_sm * 8, (int)((n + 255) / 256)), 256, 0, s->stream>>>(s->d_read_n_mems, pass3 ? s->d_r3_n_mems : nullptr, n, s->d_tot_n_mems);
+	k_mem_counts<<<std::min<int>(idx->n_sm * 8, (int)((n + 255) / 256)), 256, 0, s->stream>>>(s->d_read_n_mems, pass3 ? s->d_r3_n_mems : nullptr,
+		s->used_fast ? s->d_read_last_q : nullptr, s->d_defer_q, s->d_x_n, n, s->d_tot_n_mems);
 	CK(cudaGetLastError());
 	CK(cudaMemsetAsync(s->d_tot_n_mems + n, 0, 4, s->stream));
 	CK(cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, s->scan_tmp_bytes, s->d_tot_n_mems, s->d_mem_off, (int)n + 1, s->stream));
 	c.n_reads = n; c.opt = *opt; c.pool = s->d_pool; c.read_pool_off = s->d_read_pool_off; c.read_n_mems = s->d_read_n_mems;
 	c.off = s->d_off; c.r3_mems = s->d_r3_mems; c.r3_n_mems = pass3 ? s->d_r3_n_mems : nullptr;
+	c.read_last_q = s->used_fast ? s->d_read_last_q : nullptr; c.defer_q = s->d_defer_q; c.x_off = s->d_x_off; c.x_n = s->d_x_n; c.stage = s->d_stage;
 	c.mem_off = s->d_mem_off; c.mems = s->d_mems; c.mems_cap = ctx->max_mems; c.read_n_seeds = s->d_read_n_seeds; c.seed_off = s->d_seed_off;
 	c.seed_rows = s->d_rows; c.seed_cap = ctx->max_seeds; c.error = &s->d_ctrl->error;
 	{
@@ -652,6 +692,11 @@ fail:
 static int finish_run(cs_ctx *ctx, Slot *s)
 {
 	CK(cudaStreamSynchronize(s->stream));
+	if (s->used_fast && s->h_ctrl->n_defer > ctx->defer_cap) { // more hard calls than the queue holds (repeat-rich batch): literal kernel alone
+		cs_seed_opt_t o = s->opt;
+		if (enqueue_run(ctx, s, &o, false) != CS_OK) return CS_E_CUDA;
+		CK(cudaStreamSynchronize(s->stream));
+	}
 	s->state = 3;
 	if (s->h_ctrl->error != 0 || s->h_ctrl->pool_used > ctx->max_mems || s->h_ctrl->n_mems > ctx->max_mems || s->h_ctrl->n_seeds > ctx->max_seeds)
 		return set_err(CS_E_OVERFLOW, "result buffers too small for this batch: mems %llu of %llu, seeds %llu of %llu "
@@ -680,6 +725,9 @@ static void fill_result(cs_ctx *ctx, Slot *s, cs_result_t *out, bool host_ptrs)
 	cudaEventElapsedTime(&out->kernel_ms[3], s->ev[0], s->ev_done);
 	cudaEventElapsedTime(&out->kernel_ms[4], s->ev[1], s->ev[5]);
 	cudaEventElapsedTime(&out->kernel_ms[5], s->ev[5], s->ev[2]);
+	cudaEventElapsedTime(&out->kernel_ms[6], s->ev[1], s->ev[6]);
+	out->kernel_ms[7] = 0.f;
+	out->n_deferred = s->h_ctrl->n_defer;
 	(void)ctx;
 }
 
@@ -873,6 +921,17 @@ fail:
 	if (e1) cudaEventDestroy(e1);
 	cudaFree(d_t); cudaFree(d_sink);
 	return CS_E_CUDA;
+}
+
+extern "C" int cs_debug_stats(cs_ctx_t *ctx, int slot, uint64_t out[40])
+{
+	if (check_slot(ctx, slot) != CS_OK) return CS_E_ARG;
+	if (!out) return set_err(CS_E_ARG, "null argument");
+	for (int k = 0; k < 20; ++k) out[k] = ctx->slots[slot].h_ctrl->counters[k];
+	out[20] = ctx->slots[slot].h_ctrl->n_defer;
+	out[21] = ctx->grid_fast; out[22] = ctx->grid; out[23] = 0;
+	for (int k = 0; k < 16; ++k) out[24 + k] = ctx->slots[slot].h_ctrl->counters[20 + k];
+	return CS_OK;
 }
 
 extern "C" int cs_host_register(void *ptr, size_t bytes)

@@ -311,7 +311,18 @@ __global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, ui
 // block nor unblock a longer match (it dies no later than any longer one), so it is never pushed.
 // ---------------------------------------------------------------------------------------------
 enum { ST_FETCH = 0, ST_R1_PIVOT, ST_FILTER, ST_FWD, ST_BWD_INIT, ST_BWD_SWEEP, ST_BWD_ENTRY, ST_CALL_DONE, ST_R2_NEXT,
-       ST_READ_DONE, ST_TXT_SA, ST_TXT_CMP, ST_TXT_ISA, ST_TXT_LF, ST_IDLE };
+       ST_READ_DONE, ST_TXT_SA, ST_TXT_CMP, ST_BTX_SA, ST_BTX_CMP, ST_ROW_ISA, ST_ROW_LF, ST_IDLE };
+#ifndef CS_BK_QUORUM
+#define CS_BK_QUORUM 1     // lanes that must be waiting before the warp runs the divergent bookkeeping section (1 = every trip)
+#endif
+#ifdef CS_STATS   // diagnostics build: event counters (scripts/spec_stats.py)
+#define STAT(k) (++sst[k])
+#else
+#define STAT(k) ((void)0)
+#endif
+#ifndef CS_SPEC
+#define CS_SPEC 1          // 0: never take the speculative unique-match path (literal sweeps only)
+#endif
 
 template <int RW>
 __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
@@ -326,10 +337,16 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 	const cs_seed_opt_t opt = a.opt;
 	// the filter is usable only if a filtered match is certain to be shorter than min_seed_len
 	const int prune_k = (I.pt_k > 0 && opt.min_seed_len >= (int)I.pt_k) ? (int)I.pt_k : 0;
+	const bool utext = I.text != nullptr;                 // unique-match fast paths available (2-bit text + sampled inverse SA)
+	// (in call mode k_seed_fast has already tried the speculative route on every call it hands over)
+	const bool can_spec = CS_SPEC && utext && prune_k > 0 && (int)I.kt_depth >= 2 && (int)I.kt_depth < prune_k && a.defer_q == nullptr;
 
-	unsigned long long n_ext = 0, n_call = 0, n_two = 0, n_probe = 0;
+	uint32_t n_ext = 0, n_call = 0, n_two = 0, n_probe = 0, ext_mark = 0;
+#ifdef CS_STATS
+	uint32_t sst[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 	int st = ST_FETCH;
-	uint32_t rd = 0; int len = 0;
+	uint32_t rd = 0, cur_q = 0; int len = 0;
 	const uint64_t *pw = nullptr;                         // this read, 2-bit packed, in global memory
 	uint32_t nmem = 0, old_n = 0, r2k = 0;
 	int round = 1;
@@ -340,9 +357,10 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 	uint64_t min_intv = 1;
 	uint32_t call_nmem = 0; int last_start = 0;
 	uint32_t kmask = 0xffffffffu;                         // bit d-1: a forward match of d < K bases may be pushed
-	uint64_t tpos = 0;                                    // ST_TXT_*: text position aligned with read position i
+	uint64_t tpos = 0;                                    // text position: of q[i] (ST_TXT_*), of q[bi+1] (ST_BTX_*, ST_ROW_* after them)
 	int c = 0;
-	bool need = false;
+	bool need = false, jumped = false, spec = false;
+	int rowm = 0;                                         // ST_ROW_*: 1 = x[0] wanted, 2 = x[1] wanted, 4 = forward pass (push), else emit
 	bool err_list = false, err_mem = false;
 
 	auto list_put = [&](int idx, uint4 v) {
@@ -400,11 +418,17 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 		if (sh) m |= nm_word(tt, gp, wi + 1) << (32 - sh);
 		return (m & ((1u << cnt) - 1u)) != 0;
 	};
+	auto set_intv = [&]() { // bwt_set_intv, bwt.h:82, for q[x]
+		int b = base_at(x);
+		c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
+		i = x + 1; n = 0; jumped = false;
+	};
 	auto start_call = [&](int pivot, uint64_t mi) { // bwt_smem1a prologue, bwt.c:295-302
 		x = pivot; min_intv = mi < 1 ? 1 : mi;
-		int b = base_at(x);
-		c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b); // bwt_set_intv, bwt.h:82
-		i = x + 1; n = 0; call_nmem = 0; ret = x + 1;
+		set_intv();
+		call_nmem = 0; ret = x + 1; ext_mark = n_ext;
+		spec = can_spec && min_intv == 1;
+		STAT(4); if (spec) STAT(5);
 		st = prune_k ? ST_FILTER : ST_FWD;
 	};
 	// kv_push(curr, ik) of the forward pass (bwt.c:312,317,321) -- unless the filter proved the match useless
@@ -421,14 +445,58 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 			if ((int)cend - (bi + 1) >= opt.min_seed_len) emit(c0, c1, c2, (uint32_t)(bi + 1), cend);
 		}
 	};
+	// Speculative mode (see "unique-match paths" below): the forward pass pushed nothing.  If the literal
+	// pass would not have pushed anything either, the call is over; otherwise redo it literally.
+	// Forward jump (result-neutral): no match shorter than J = (first depth the filter lets through) can be pushed,
+	// so the table entry of q[x, x+J) is fetched directly instead of one depth per trip.  In speculative mode
+	// nothing is pushed before the match is unique, so J is the table depth.  If that string occurs fewer
+	// than min_intv times the call restarts one base at a time (see `jumped`).
+	auto try_jump = [&]() {
+		int J = (spec || kmask == 0) ? 32 : __ffs((int)kmask);
+		if (J > (int)I.kt_depth) J = (int)I.kt_depth;
+		if (J >= 2 && J < prune_k && !has_n(t, pw, x, J)) { i = x + J - 1; jumped = true; }
+	};
+	auto spec_abort = [&]() { spec = false; n_ext = ext_mark; set_intv(); try_jump(); st = ST_FWD; need = false; };
+	auto spec_stop = [&](int end) { // the forward match [x, end) ended before it became unique, or is shorter than K
+		int d = end - x;
+		if (d < prune_k && (kmask & ((1u << d) - 1u)) == 0) { ret = end; st = ST_CALL_DONE; need = false; STAT(7); }   // nothing pushable: bwt.c:322 with curr->n == 0
+		else { spec_abort(); STAT(8); }
+	};
+	// end of the forward pass at read position `end` (N, read end): bwt.c:317,321
+	auto fwd_end = [&](int end) {
+		if (spec) spec_stop(end);
+		else { fwd_push(end); st = ST_BWD_INIT; need = false; }
+	};
+	// row of the suffix starting at text position p: nearest sample to the right, then `steps` LF steps back
+	auto isa_near = [&](uint64_t p, uint64_t &row, int &steps) {
+		const uint64_t smask = (1ull << I.isa_shift) - 1;
+		uint64_t jj = (p + smask) & ~smask;
+		if (jj > I.seq_len) jj = I.seq_len;
+		row = jj == I.seq_len ? 0ull : __ldg(I.isa + (jj >> I.isa_shift));   // the '$' suffix is row 0
+		steps = (int)(jj - p);
+	};
 
 	for (;;) {
-		// ---- divergent bookkeeping: advance this lane's state machine until it needs the warp ----
-		while (!need && st != ST_IDLE && st != ST_FILTER) {
+		// ---- divergent bookkeeping: advance this lane's state machine until it needs the warp.  With
+		//      CS_BK_QUORUM > 1 the warp enters this section only when that many lanes wait for it (or
+		//      nobody has convergent work), so its instructions are issued for several lanes at once ----
+		bool bk = !need && st != ST_IDLE && st != ST_FILTER;
+		if (CS_BK_QUORUM > 1) {
+			const unsigned waiting = __ballot_sync(0xffffffffu, bk);
+			const unsigned busy = __ballot_sync(0xffffffffu, need || st == ST_FILTER);
+			if (busy && __popc(waiting) < CS_BK_QUORUM) bk = false;
+		}
+		if (bk) STAT(12);
+		while (bk && !need && st != ST_IDLE && st != ST_FILTER) {
 			switch (st) {
 			case ST_FETCH: {
 				rd = atomicAdd(a.next_read, 1u);
-				if (rd >= a.n_reads) { st = ST_IDLE; break; }
+				uint4 item = make_uint4(0, 0, 0, 0);
+				if (a.defer_q) { // call mode: only the calls k_seed_fast handed over
+					const uint32_t nq = *a.n_defer;
+					if (rd >= (nq < a.defer_cap ? nq : a.defer_cap)) { st = ST_IDLE; break; }
+					cur_q = rd; item = a.defer_q[rd]; rd = item.x;
+				} else if (rd >= a.n_reads) { st = ST_IDLE; break; }
 				uint32_t o = a.off[rd];
 				len = (int)(a.off[rd + 1] - o);
 				pw = a.packed + ((uint64_t)(o >> 5) + 2ull * rd);
@@ -443,6 +511,10 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				}
 				nmem = 0; round = 1; x = 0; err_list = err_mem = false;
 				st = ST_R1_PIVOT;
+				if (a.defer_q) { // one call: a first-pass pivot (then the second pass of what it finds) or a second-pass pivot
+					round = (int)(item.y >> 16); old_n = 0; r2k = 0;
+					start_call((int)(item.y & 0xffff), (uint64_t)item.z);
+				}
 			} break;
 			case ST_R1_PIVOT: // first pass of mem_collect_intv, bwamem.c:226-236
 				while (x < len && base_at(x) > 3) ++x;
@@ -451,7 +523,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				break;
 			case ST_FWD: { // forward extension, bwt.c:304-321
 				int b = i < len ? base_at(i) : 4;
-				if (b > 3) { fwd_push(i); st = ST_BWD_INIT; }
+				if (b > 3) fwd_end(i);
 				else { c = 3 - b; need = true; }
 			} break;
 			case ST_BWD_INIT: // bwt.c:322-326; list[n-1] is the longest match that was kept
@@ -465,7 +537,14 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 					unpack_entry(list_get(n - 1), c0, c1, c2, cend);
 					mem_candidate();
 					st = ST_CALL_DONE;
-				} else { j = n - 1; w = n; pushed = false; st = ST_BWD_ENTRY; }
+				} else {
+					j = n - 1; w = n; pushed = false; st = ST_BWD_ENTRY;
+					if (utext && n - lo == 1 && min_intv == 1) { // one interval left: load it here, maybe take the text path
+						unpack_entry(list_get(j), c0, c1, c2, cend);
+						if (c2 == 1) st = ST_BTX_SA;
+						need = true;
+					}
+				}
 			} break;
 			case ST_BWD_ENTRY:
 				if (j < lo) {
@@ -474,7 +553,9 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				} else { unpack_entry(list_get(j), c0, c1, c2, cend); need = true; }
 				break;
 			case ST_CALL_DONE:
-				if (round == 1) { x = ret; st = ST_R1_PIVOT; } else st = ST_R2_NEXT;
+				if (round != 1) st = ST_R2_NEXT;
+				else if (a.defer_q) { old_n = nmem; r2k = 0; st = ST_R2_NEXT; }   // call mode: k_seed_fast goes on with the first pass
+				else { x = ret; st = ST_R1_PIVOT; }
 				break;
 			case ST_R2_NEXT: { // second pass, bwamem.c:238-249 (the third pass runs in k_seed_r3)
 				st = ST_READ_DONE;
@@ -496,7 +577,8 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				if (err_mem || err_list) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
 				unsigned long long o = atomicAdd(a.pool_used, (unsigned long long)cnt);
 				if (o + cnt > a.pool_cap) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
-				a.read_pool_off[rd] = o; a.read_n_mems[rd] = cnt;
+				if (a.defer_q) { a.x_off[cur_q] = o; a.x_n[cur_q] = cnt; }
+				else { a.read_pool_off[rd] = o; a.read_n_mems[rd] = cnt; }
 				const uint4 *src = reinterpret_cast<const uint4*>(my);
 				uint4 *dst = reinterpret_cast<uint4*>(a.pool + o);
 				for (uint32_t m = 0; m < 2 * cnt; ++m) dst[m] = src[m];
@@ -508,6 +590,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 		// ---- explicit reconvergence: all 32 lanes meet here every trip; nobody leaves early ----
 		if (__all_sync(0xffffffffu, st == ST_IDLE)) break;
 		__syncwarp();   // vote intrinsics are not memory barriers: make every lane's read words visible to the warp
+		if ((t & 31) == 0) STAT(0);
 
 		// ---- occurrence filter, served by the whole warp for one requesting lane at a time: lane l
 		//      tests the window that ends l+1 bases after the pivot ----
@@ -526,18 +609,34 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				++n_probe;
 			}
 			const unsigned km = __ballot_sync(0xffffffffu, keep);
-			if (lane == owner) { kmask = km; st = ST_FWD; }
+			if (lane == owner) {
+				STAT(13);
+				kmask = km; st = ST_FWD;
+				try_jump();
+			}
 		}
 		if (!need) continue;
 
-		// ---- unique-match fast path (result-neutral).  Once the forward interval holds ONE occurrence
-		//      (x[2] == 1, min_intv == 1) every further bwt_extend only asks "does the next read base equal
-		//      the next text base": x[0] stays the row of that occurrence, nothing is pushed while the size
-		//      stays 1 (bwt.c:311), and the extension ends at the first mismatch / N / end.  So: one SA
-		//      gather for the text position, 32 bases per step compared against the 2-bit text, then x[1] =
-		//      row of the reverse-complement occurrence from the sampled inverse SA plus < 2^isa_shift LF steps. ----
-		if (st >= ST_TXT_SA && st <= ST_TXT_LF) {
+		// ---- unique-match paths (result-neutral).  Once an interval holds ONE occurrence (x[2] == 1, min_intv ==
+		//      1) every further bwt_extend only asks "does the next read base equal the next text base", so the
+		//      extension is done 32 bases per step against the 2-bit text at the occurrence (one SA gather), and the
+		//      coordinate that moves (x[1] forward, x[0] backward) is rebuilt at the end from the sampled inverse SA
+		//      plus < 2^isa_shift LF steps.
+		//      Forward (ST_TXT_*): x[0] stays the row of the occurrence, nothing is pushed while the size stays 1
+		//      (bwt.c:311), the pass ends at the first mismatch / N / end.
+		//      Backward (ST_BTX_*), one interval left in the sweep (bwt.c:329-341 with prev->n == 1): x[1], x[2] stay,
+		//      the sweep that fails (read start, N, mismatch, text start) makes the SMEM.
+		//      Speculative call (`spec`): the forward pass pushes nothing until the match is unique, and the backward
+		//      pass follows only that longest match L = [x, cend) to the position f where it fails.  Every shorter
+		//      match the literal pass would have pushed contains L's occurrence, so it survives every sweep L
+		//      survives and cannot become an SMEM before f (curr->n > 0, bwt.c:332); at f it is rejected as
+		//      contained (bwt.c:333) unless it survives f.  All of them start with q[f, f+K) once extended to f
+		//      (their length is >= dlow, the first depth the filter lets through, and x + dlow - f >= K is checked),
+		//      so if that K-mer does not occur in the text (one filter probe) none survives: the call's only
+		//      SMEM is [f+1, cend).  Otherwise the call is redone literally (spec_abort). ----
+		if (st >= ST_TXT_SA && st <= ST_ROW_LF) {
 			bool fin = false;
+			STAT(3); if (st == ST_TXT_CMP) STAT(15); if (st == ST_ROW_LF) STAT(11);
 			if (st == ST_TXT_SA) {
 				tpos = __ldg(I.sa + c0) + (uint64_t)(i - x);
 				j = 0; st = ST_TXT_CMP;
@@ -550,22 +649,79 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				if (nn < m) m = nn;
 				if (left < m) m = (uint32_t)left;
 				i += (int)m; tpos += m; j += (int)m;
-				if (m < 32) { if (j > 0) st = ST_TXT_ISA; else fin = true; }
-			} else if (st == ST_TXT_ISA) {
-				const uint64_t sp = I.seq_len - tpos;                   // where revcomp(match) starts in the text
-				const uint64_t smask = (1ull << I.isa_shift) - 1;
-				uint64_t jj = (sp + smask) & ~smask;
-				if (jj > I.seq_len) jj = I.seq_len;
-				c1 = jj == I.seq_len ? 0ull : __ldg(I.isa + (jj >> I.isa_shift));   // row of suffix jj ('$' suffix: row 0)
-				w = (int)(jj - sp);
-				if (w == 0) fin = true; else st = ST_TXT_LF;
-			} else {
-				c1 = dev_lf(I, c1);                                      // row of the preceding suffix
-				if (--w == 0) fin = true;
+				if (m < 32) { // the forward pass ends here: at an N, the read end, the text end, or a mismatch (child size 0 != 1)
+					n_ext += (unsigned)j + ((i < len && base_at(i) <= 3) ? 1u : 0u);   // bwt.c:306-320: no bwt_extend at an N / the read end
+					if (!spec) {
+						if (j > 0) { rowm = 2 | 4; st = ST_ROW_ISA; }
+						else { fwd_push(i); st = ST_BWD_INIT; need = false; }
+					} else if (i - x < prune_k && !((kmask >> (i - x - 1)) & 1)) spec_stop(i);   // L itself would not be pushed
+					else { // L = [x, i): follow it backward from x - 1
+						rowm = j > 0 ? 2 : 0;
+						cend = (uint32_t)i; ret = i; bi = x - 1; tpos -= (uint64_t)(i - x); j = 0; st = ST_BTX_CMP;
+					}
+				}
+			} else if (st == ST_BTX_SA) {
+				tpos = __ldg(I.sa + c0);
+				j = 0; rowm = 0; st = ST_BTX_CMP;
+			} else if (st == ST_BTX_CMP) {
+				uint32_t cnt = 32, m = 0;
+				if ((uint32_t)(bi + 1) < cnt) cnt = (uint32_t)(bi + 1);
+				if (tpos < cnt) cnt = (uint32_t)tpos;
+				if (cnt) { // the cnt bases q[bi-cnt+1 .. bi] against the cnt text bases before tpos, compared from the top
+					const int sr = bi + 1 - (int)cnt;
+					const uint64_t diff = (read_window(sr) ^ packed_window(I.text, tpos - cnt)) << (2 * (32 - cnt));
+					const uint32_t nmw = nmask_window(sr) << (32 - cnt);
+					m = diff ? (uint32_t)__clzll((long long)diff) >> 1 : 32u;
+					const uint32_t nn = nmw ? (uint32_t)__clz((int)nmw) : 32u;
+					if (nn < m) m = nn;
+					if (cnt < m) m = cnt;
+				}
+				bi -= (int)m; tpos -= m; j += (int)m;
+				if (m < 32) { // bi is the first position that does not extend the match
+					const bool ext_fails = bi >= 0 && base_at(bi) <= 3;   // bwt.c:330: no bwt_extend at the read start / an N
+					n_ext += (unsigned)j + (ext_fails ? 1u : 0u);
+					bool ok = true;
+					if (spec && ext_fails) { // could a shorter match survive position bi?
+						const int dlow = kmask ? __ffs((int)kmask) : prune_k;
+						ok = false; STAT(10);
+						if (x + dlow - bi >= prune_k && !has_n(t, pw, bi, prune_k)) {
+							const uint64_t key = key_of(t, pw, bi, prune_k);
+							ok = ((__ldg(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) == 0;
+							++n_probe;
+#ifdef CS_STATS
+							--sst[10]; if (!ok) STAT(9);
+#endif
+						}
+					}
+					if (!ok) spec_abort();
+					else {
+						if (spec) STAT(6);
+						st = ST_CALL_DONE; need = false;
+						if (call_nmem == 0 || bi + 1 < last_start) { // bwt.c:332-336
+							++call_nmem; last_start = bi + 1;
+							if ((int)cend - (bi + 1) >= opt.min_seed_len) {
+								if (j > 0) rowm |= 1;
+								if (rowm) { st = ST_ROW_ISA; need = true; }
+								else emit(c0, c1, c2, (uint32_t)(bi + 1), cend);
+							}
+						}
+					}
+				}
+			} else if (st == ST_ROW_ISA) {
+				int w0 = 0, w1 = 0;
+				if (rowm & 1) isa_near(tpos, c0, w0);                                       // row of the suffix at the match start
+				if (rowm & 2) isa_near(I.seq_len - tpos - ((rowm & 4) ? 0ull : (uint64_t)((int)cend - bi - 1)), c1, w1);   // ... of its reverse complement
+				w = w0 | (w1 << 8);
+				if (w == 0) fin = true; else st = ST_ROW_LF;
+			} else { // ST_ROW_LF: one LF step (row of the preceding suffix) on each coordinate still walking
+				if (w & 0xff) { c0 = dev_lf(I, c0); w -= 1; }
+				if (w >> 8) { c1 = dev_lf(I, c1); w -= 256; }
+				if (w == 0) fin = true;
 			}
-			if (fin) { // the forward pass ends here: at an N, the read end, the text end, or a mismatch (child size 0 != 1)
-				n_ext += (unsigned)j + 1;
-				fwd_push(i); st = ST_BWD_INIT; need = false;
+			if (fin) {
+				if (rowm & 4) { fwd_push(i); st = ST_BWD_INIT; }
+				else { emit(c0, c1, c2, (uint32_t)(bi + 1), cend); st = ST_CALL_DONE; }
+				need = false;
 			}
 			continue;
 		}
@@ -583,19 +739,24 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 			const int s_beg = is_back ? bi : x;
 			const int new_len = is_back ? (int)cend - bi : i + 1 - x;
 			++n_ext;
-			if (new_len <= (int)I.kt_depth) kt_lookup(I, (uint32_t)new_len, key_of(t, pw, s_beg, new_len), o0, o1, o2);
-			else { uint32_t two; dev_extend(I, c0, c1, c2, c, is_back, o0, o1, o2, two); ++n_call; n_two += two; }
+			if (new_len <= (int)I.kt_depth) { kt_lookup(I, (uint32_t)new_len, key_of(t, pw, s_beg, new_len), o0, o1, o2); STAT(1); }
+			else { uint32_t two; dev_extend(I, c0, c1, c2, c, is_back, o0, o1, o2, two); ++n_call; n_two += two; STAT(2); }
 		}
 
 		if (!is_back) { // ST_FWD, bwt.c:311-315
+			if (jumped) { // this was the table entry of q[x, i]: J = i + 1 - x bases fetched at once
+				jumped = false;
+				if (o2 < min_intv) { i = x + 1; --n_ext; need = false; STAT(14); continue; }   // too rare: redo this call one base at a time
+				n_ext += (unsigned)(i - x - 1); c2 = o2;
+			}
 			if (o2 != c2) {
-				fwd_push(i);
-				if (o2 < min_intv) { st = ST_BWD_INIT; need = false; }
+				if (!spec) fwd_push(i);
+				if (o2 < min_intv) { if (spec) spec_stop(i); else st = ST_BWD_INIT; need = false; }
 			}
 			if (need) {
 				c0 = o0; c1 = o1; c2 = o2; ++i;
-				if (i >= len || nb > 3) { fwd_push(i); st = ST_BWD_INIT; need = false; }
-				else if (I.text != nullptr && c2 == 1 && min_intv == 1) st = ST_TXT_SA;   // unique from here on
+				if (i >= len || nb > 3) fwd_end(i);
+				else if (utext && c2 == 1 && min_intv == 1) st = ST_TXT_SA;   // unique from here on
 				else c = 3 - (int)nb;
 			}
 		} else { // ST_BWD_ENTRY, bwt.c:331-341
@@ -611,18 +772,314 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				lo = w; --bi; c = (int)nb;
 				j = n - 1; w = n; pushed = false;
 				unpack_entry(list_get(j), c0, c1, c2, cend);
+				if (utext && n - lo == 1 && c2 == 1 && min_intv == 1) st = ST_BTX_SA;   // one occurrence left: compare against the text
 			} else need = false;                                            // ST_BWD_ENTRY finishes the sweep on the slow path
 		}
 	}
-	if (n_ext) atomicAdd(a.counters + 0, n_ext);
-	if (n_call) atomicAdd(a.counters + 1, n_call);
-	if (n_two) atomicAdd(a.counters + 2, n_two);
-	if (n_probe) atomicAdd(a.counters + 3, n_probe);
+	if (n_ext) atomicAdd(a.counters + 0, (unsigned long long)n_ext);
+	if (n_call) atomicAdd(a.counters + 1, (unsigned long long)n_call);
+	if (n_two) atomicAdd(a.counters + 2, (unsigned long long)n_two);
+	if (n_probe) atomicAdd(a.counters + 3, (unsigned long long)n_probe);
+#ifdef CS_STATS
+	for (int k = 0; k < 16; ++k) if (sst[k]) atomicAdd(a.counters + 4 + k, (unsigned long long)sst[k]);
+#endif
 }
 
 __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIndex I, SeedArgs a) { seed_body<CS_READ_SMEM>(I, a); }
 // reads longer than 32 * CS_READ_SMEM bases: the packed read stays in global memory
 __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed_long(DevIndex I, SeedArgs a) { seed_body<0>(I, a); }
+
+// ---------------------------------------------------------------------------------------------
+// Fast seeding kernel (passes 1 and 2 for reads whose every bwt_smem1a call is "simple").
+//
+// k_seed above is a trip-synchronous state machine: every warp trip pays for every divergent path
+// some lane is on, which makes it issue-bound (profiles/r01_ncu_k_seed_final_*).  This kernel is
+// CALL-synchronous instead: every lane runs one whole bwt_smem1a call per iteration of the outer
+// loop, and all lanes walk through the same phases (filter probes -> table jump -> FM extends until
+// the match is unique -> text comparison forward and backward -> one K-mer probe -> rows from the
+// sampled inverse SA).  It never builds an interval list.  It relies on the argument spelled out at
+// "unique-match paths" in seed_body: the call's only SMEM is the backward extension of the longest
+// forward match L when L is one occurrence and the K-mer at the position where L fails does not
+// occur in the text; and a call whose forward pass could not push anything returns nothing.  Any
+// CALL that does not fit (a shorter match could survive, pass 2 needs a list, scratch overflow) is
+// queued as (read, pivot, min_intv, pass) for k_seed, which executes it literally -- and, for a
+// first-pass call, the second-pass calls of the SMEMs it finds (bwamem.c:238-249 depend only on
+// their own SMEM).  The first pass goes on here: the next pivot is the end of the longest forward
+// match (bwt.c:323), which this kernel knows exactly.  The collect pass merges a read's chain of
+// deferred results with the ones written here.  Results are bit-identical by construction; only the
+// share of deferred calls depends on the data (about 0.6 per read on the i.i.d. 3.1 Gbp
+// configuration -- a random 19-mer has a second occurrence there with probability 2 % --, most
+// calls on repeat-rich references).
+// ---------------------------------------------------------------------------------------------
+template <int RW>
+__device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs &a)
+{
+	extern __shared__ uint4 s_dyn[];
+	uint64_t *s_rd = reinterpret_cast<uint64_t*>(s_dyn);                                   // [RW][CS_FAST_BLOCK] packed read
+	uint32_t *s_nm = reinterpret_cast<uint32_t*>(s_rd + RW * CS_FAST_BLOCK);              // [RW][CS_FAST_BLOCK] N mask
+	const int t = threadIdx.x;
+	const size_t gtid = (size_t)blockIdx.x * CS_FAST_BLOCK + t;
+	cs_mem_t *const my = a.thread_mems + gtid * a.mem_cap;
+	const cs_seed_opt_t opt = a.opt;
+	const int K = (int)I.pt_k, kd = (int)I.kt_depth;       // host guarantees 2 <= kd < K <= min_seed_len, K <= 19
+
+	uint32_t n_ext = 0, n_call = 0, n_two = 0, n_probe = 0;
+	uint32_t r_ext = 0, r_call = 0;                        // of the call in flight: counted only if it is not deferred
+#ifdef CS_STATS
+	uint32_t sst[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+	bool have = false, exhausted = false;
+	uint32_t last_q = 0xffffffffu;                        // most recent deferred call of the read in flight (chain head)
+	uint32_t rd = 0; int len = 0;
+	int round = 1, x = 0;
+	uint32_t nmem = 0, old_n = 0, r2k = 0;
+
+	auto rd_word = [&](uint32_t wi) -> uint64_t { return s_rd[wi * CS_FAST_BLOCK + t]; };
+	auto nm_word = [&](uint32_t wi) -> uint32_t { return s_nm[wi * CS_FAST_BLOCK + t]; };
+	auto base_at = [&](int pos) -> int {
+		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
+		return ((nm_word(wi) >> sh) & 1) ? 4 : (int)((rd_word(wi) >> (2 * sh)) & 3);
+	};
+	auto read_window = [&](int pos) -> uint64_t { // the 32 bases from pos, base j at bits 2j
+		uint32_t wi = (uint32_t)pos >> 5, sh = ((uint32_t)pos & 31) * 2;
+		uint64_t v = rd_word(wi) >> sh;
+		if (sh) v |= rd_word(wi + 1) << (64 - sh);
+		return v;
+	};
+	auto nmask_window = [&](int pos) -> uint32_t { // bit j: q[pos + j] is ambiguous or past the end of the read
+		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
+		uint32_t m = nm_word(wi) >> sh;
+		if (sh) m |= nm_word(wi + 1) << (32 - sh);
+		return m;
+	};
+	auto key_of = [&](int pos, int cnt) -> uint64_t { return read_window(pos) & ((1ull << (2 * cnt)) - 1); };   // cnt < 32
+	auto has_n = [&](int pos, int cnt) -> bool { return (nmask_window(pos) & ((1u << cnt) - 1u)) != 0; };       // cnt < 32
+	auto pt_count = [&](uint64_t key) -> uint32_t { return (__ldg(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3; };
+	auto isa_near = [&](uint64_t p, uint64_t &row, int &steps) {
+		const uint64_t smask = (1ull << I.isa_shift) - 1;
+		uint64_t jj = (p + smask) & ~smask;
+		if (jj > I.seq_len) jj = I.seq_len;
+		row = jj == I.seq_len ? 0ull : __ldg(I.isa + (jj >> I.isa_shift));
+		steps = (int)(jj - p);
+	};
+	// hand the call (pivot, min_intv) of the read in flight to the literal kernel
+	auto defer_call = [&](int pivot, uint64_t mi) {
+		const uint32_t q = atomicAdd(a.n_defer, 1u);
+		// (past the capacity nothing is stored: the host sees n_defer > defer_cap and reruns the batch through k_seed alone)
+		if (q < a.defer_cap) { a.defer_q[q] = make_uint4(rd, (uint32_t)pivot | ((uint32_t)round << 16), (uint32_t)mi, last_q); last_q = q; }
+	};
+
+	for (;;) {
+		// ---- pick this lane's next call: (cx, cmin) ----
+		bool active = false; int cx = 0; uint64_t cmin = 1;
+		while (!exhausted) {
+			if (!have) {
+				rd = atomicAdd(a.next_read + 2, 1u);
+				if (rd >= a.n_reads) { exhausted = true; break; }
+				const uint32_t o = a.off[rd];
+				len = (int)(a.off[rd + 1] - o);
+				const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * rd;
+				const uint32_t nw = ((uint32_t)len >> 5) + 2;
+#pragma unroll
+				for (uint32_t wi = 0; wi < RW; ++wi) {
+					s_rd[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.packed + w0 + wi) : 0ull;
+					s_nm[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.nmask + w0 + wi) : 0xffffffffu;
+				}
+				nmem = 0; round = 1; x = 0; have = true; last_q = 0xffffffffu;
+			}
+			{
+				if (round == 1) { // first pass of mem_collect_intv, bwamem.c:226-236
+					while (x < len && base_at(x) > 3) ++x;
+					if (x < len) { cx = x; cmin = 1; active = true; break; }
+					old_n = nmem; r2k = 0; round = 2;
+				}
+				while (r2k < old_n) { // second pass, bwamem.c:238-249
+					const uint4 v = reinterpret_cast<const uint4*>(my + r2k)[1];
+					++r2k;
+					const int s = (int)v.w, e = (int)v.z;
+					const uint64_t sz = (uint64_t)v.x | ((uint64_t)v.y << 32);
+					if (e - s < opt.split_len || sz > (uint64_t)opt.split_width) continue;
+					cx = (s + e) >> 1; cmin = sz + 1; active = true;
+					break;
+				}
+				if (active) break;
+			}
+			// the read is finished
+			{
+				uint32_t cnt = nmem;
+				unsigned long long o = atomicAdd(a.pool_used, (unsigned long long)cnt);
+				if (o + cnt > a.pool_cap) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
+				a.read_pool_off[rd] = o; a.read_n_mems[rd] = cnt;
+				const uint4 *src = reinterpret_cast<const uint4*>(my);
+				uint4 *dst = reinterpret_cast<uint4*>(a.pool + o);
+				for (uint32_t m = 0; m < 2 * cnt; ++m) dst[m] = src[m];
+				a.read_last_q[rd] = last_q;
+			}
+			have = false;
+		}
+		if (__all_sync(0xffffffffu, !active)) break;
+		if ((t & 31) == 0) STAT(0);
+		if (!active) continue;     // exhausted lanes wait at the vote above
+		STAT(1); if (cmin != 1) STAT(2);
+		r_ext = r_call = 0;
+
+		// ---- occurrence filter (as in seed_body): bit e-1 of kmask <=> the K-mer ending e bases after the pivot
+		//      occurs >= min(cmin, 3) times, i.e. a forward match of e bases may be pushed.  All probes of a
+		//      call are independent loads. ----
+		uint32_t kmask = 0;
+		{
+			const uint32_t omin = cmin > 3 ? 4u : (uint32_t)cmin;
+			const int s0 = cx >= 31 ? cx - 31 : 0, cl = cx - s0;     // N-free run immediately left of the pivot, capped at 31
+			int nl = 0;
+			if (cl > 0) {
+				const uint32_t m = (nmask_window(s0) & ((1u << cl) - 1u)) << (32 - cl);
+				nl = m ? __clz((int)m) : cl;
+			}
+			const int e0 = K - nl < 1 ? 1 : K - nl;                     // first window that starts inside that run
+			uint32_t cnt[18];
+#pragma unroll
+			for (int u = 0; u < 18; ++u) {
+				const int e = u + 1;
+				cnt[u] = 0;
+				if (e >= e0 && e < K) { cnt[u] = pt_count(key_of(cx + e - K, K)); ++n_probe; }
+			}
+#pragma unroll
+			for (int u = 0; u < 18; ++u) if (cnt[u] == 3 || (cnt[u] != 0 && cnt[u] >= omin)) kmask |= 1u << u;
+		}
+
+		// ---- forward pass (bwt.c:304-321) without pushes: until the match is one occurrence, dies, or hits an N / the end ----
+		uint64_t c0, c1, c2;
+		{
+			const int b = base_at(cx);
+			c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);   // bwt_set_intv, bwt.h:82
+		}
+		int i = cx + 1;
+		bool unique = false;
+		if (!has_n(cx, kd)) { // q[cx, cx+kd) is inside the read and unambiguous: its table entry directly
+			uint64_t o0, o1, o2;
+			kt_lookup(I, (uint32_t)kd, key_of(cx, kd), o0, o1, o2);
+			if (o2 >= cmin) { c0 = o0; c1 = o1; c2 = o2; i = cx + kd; r_ext += (uint32_t)(kd - 1); }
+		}
+		for (;;) {
+			if (c2 == 1 && cmin == 1) { unique = true; break; }
+			const int b = i < len ? base_at(i) : 4;
+			if (b > 3) break;
+			const int new_len = i + 1 - cx;
+			uint64_t o0, o1, o2;
+			++r_ext;
+			if (new_len <= kd) kt_lookup(I, (uint32_t)new_len, key_of(cx, new_len), o0, o1, o2);
+			else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - b, 0, o0, o1, o2, two); ++r_call; n_two += two; }
+			if (o2 < cmin) break;                                   // bwt.c:313: this extension fails, the match ends at i
+			c0 = o0; c1 = o1; c2 = o2; ++i;
+		}
+		// unique from here on: compare against the text at the occurrence, 32 bases per step
+		uint64_t tp0 = 0; int jf = 0;
+		if (unique) {
+			tp0 = __ldg(I.sa + c0);                                 // text position of q[cx]
+			uint64_t tpos = tp0 + (uint64_t)(i - cx);
+			for (;;) {
+				const uint64_t diff = read_window(i) ^ packed_window(I.text, tpos);
+				const uint32_t nmw = nmask_window(i);
+				uint32_t m = diff ? (uint32_t)(__ffsll((long long)diff) - 1) >> 1 : 32u;
+				const uint32_t nn = nmw ? (uint32_t)__ffs((int)nmw) - 1u : 32u;
+				const uint64_t left = I.seq_len - tpos;
+				if (nn < m) m = nn;
+				if (left < m) m = (uint32_t)left;
+				i += (int)m; tpos += m; jf += (int)m;
+				if (m < 32) break;
+			}
+			r_ext += (uint32_t)jf + ((i < len && base_at(i) <= 3) ? 1u : 0u);
+		}
+		const int end = i, d = end - cx;                            // the longest forward match is L = [cx, end)
+		if (round == 1) x = end;                                    // next pivot (bwt.c:323, bwamem.c:228)
+
+		// ---- what would the literal pass have pushed? ----
+		const bool pushable = d >= K || (kmask & ((1u << d) - 1u)) != 0;
+		if (!pushable) { STAT(3); n_ext += r_ext; n_call += r_call; continue; }   // nothing: the call returns no SMEM
+		if (cmin != 1 || !(d >= K || ((kmask >> (d - 1)) & 1))) { // pass 2 with a list, or L itself not pushed
+			if (cmin != 1) STAT(4); else STAT(5);
+			defer_call(cx, cmin); continue;
+		}
+		if (!unique) STAT(6);
+
+		// ---- backward: follow L alone to the position where it fails.  While L still has several occurrences
+		//      (a short L: the next mismatch came before the match was unique) the sweep is a literal
+		//      bwt_extend of L's interval; once one occurrence is left it is a comparison against the text. ----
+		int bi = cx - 1, jb = 0;
+		bool failed = false, bad = false;                           // failed: the sweep at bi already failed inside the FM loop
+		for (int steps = 0; c2 > 1; ++steps) {
+			const int b = bi >= 0 ? base_at(bi) : 4;
+			if (b > 3 || steps >= 64) { failed = true; bad = steps >= 64; if (bad) STAT(7); break; }   // read start / N (a long repeat goes to the literal kernel)
+			const int new_len = end - bi;
+			uint64_t o0, o1, o2;
+			++r_ext;
+			if (new_len <= kd) kt_lookup(I, (uint32_t)new_len, key_of(bi, new_len), o0, o1, o2);
+			else { uint32_t two; dev_extend(I, c0, c1, c2, b, 1, o0, o1, o2, two); ++r_call; n_two += two; }
+			if (o2 < 1) { failed = true; break; }                   // bwt.c:331: L ends here
+			c0 = o0; c1 = o1; c2 = o2; --bi;
+		}
+		if (bad) { defer_call(cx, cmin); continue; }
+		uint64_t tb = tp0;                                          // text position of q[bi+1]
+		if (!failed) {
+			if (!unique) tb = __ldg(I.sa + c0);
+			for (;;) {
+				uint32_t cnt = 32, m = 0;
+				if ((uint32_t)(bi + 1) < cnt) cnt = (uint32_t)(bi + 1);
+				if (tb < cnt) cnt = (uint32_t)tb;
+				if (cnt) {
+					const int sr = bi + 1 - (int)cnt;
+					const uint64_t diff = (read_window(sr) ^ packed_window(I.text, tb - cnt)) << (2 * (32 - cnt));
+					const uint32_t nmw = nmask_window(sr) << (32 - cnt);
+					m = diff ? (uint32_t)__clzll((long long)diff) >> 1 : 32u;
+					const uint32_t nn = nmw ? (uint32_t)__clz((int)nmw) : 32u;
+					if (nn < m) m = nn;
+					if (cnt < m) m = cnt;
+				}
+				bi -= (int)m; tb -= m; jb += (int)m;
+				if (m < 32) break;
+			}
+		}
+		const bool ext_fails = bi >= 0 && base_at(bi) <= 3;         // bwt.c:330: no bwt_extend at the read start / an N
+		if (!failed) r_ext += (uint32_t)jb + (ext_fails ? 1u : 0u);
+		if (ext_fails) { // could a shorter match survive position bi?  They all start with q[bi, bi+K) there.
+			const int dlow = kmask ? __ffs((int)kmask) : K;
+			bool ok = false;
+			if (cx + dlow - bi >= K && !has_n(bi, K)) { ok = pt_count(key_of(bi, K)) == 0; ++n_probe; if (!ok) STAT(8); }
+			else STAT(9);
+			if (!ok) { defer_call(cx, cmin); continue; }
+		}
+		STAT(10);
+		if (end - (bi + 1) >= opt.min_seed_len && nmem >= a.mem_cap) { defer_call(cx, cmin); continue; }   // scratch full: the literal kernel stores it
+		n_ext += r_ext; n_call += r_call;
+		if (end - (bi + 1) < opt.min_seed_len) continue;            // bwamem.c:231-233,247
+		STAT(11);
+		// ---- the coordinates that moved by text comparison: x[0] backward, x[1] forward ----
+		{
+			int w0 = 0, w1 = 0;
+			if (jb > 0) isa_near(tb, c0, w0);
+			if (jf > 0) isa_near(I.seq_len - tb - (uint64_t)(end - bi - 1), c1, w1);
+			while (w0 | w1) {
+				if (w0) { c0 = dev_lf(I, c0); --w0; }
+				if (w1) { c1 = dev_lf(I, c1); --w1; }
+			}
+		}
+		{
+			uint4 *p = reinterpret_cast<uint4*>(my + nmem);
+			p[0] = make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)c1, (uint32_t)(c1 >> 32));
+			p[1] = make_uint4((uint32_t)c2, (uint32_t)(c2 >> 32), (uint32_t)end, (uint32_t)(bi + 1));
+			++nmem;
+		}
+	}
+	if (n_ext) atomicAdd(a.counters + 0, (unsigned long long)n_ext);
+	if (n_call) atomicAdd(a.counters + 1, (unsigned long long)n_call);
+	if (n_two) atomicAdd(a.counters + 2, (unsigned long long)n_two);
+	if (n_probe) atomicAdd(a.counters + 3, (unsigned long long)n_probe);
+#ifdef CS_STATS
+	for (int k = 0; k < 16; ++k) if (sst[k]) atomicAdd(a.counters + 20 + k, (unsigned long long)sst[k]);
+#endif
+}
+
+__global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_fast(DevIndex I, SeedArgs a) { seed_fast_body<CS_READ_SMEM>(I, a); }
 
 // ---------------------------------------------------------------------------------------------
 // Third pass ("LAST-like", bwamem.c:253-268 + bwt_seed_strategy1, bwt.c:358-379) as its own kernel:
@@ -718,9 +1175,9 @@ __global__ void k_collect_sort(CollectArgs a)
 	const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
 	const uint32_t kp1 = (uint32_t)a.opt.min_seed_len + 1;
 	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.n_reads; r += nwarps) {
-		const uint32_t n12 = a.read_n_mems[r];                 // passes 1-2 (k_seed)
+		const uint32_t n12 = a.read_n_mems[r];                 // passes 1-2 (k_seed_fast, or k_seed alone)
 		const uint32_t n3 = a.r3_n_mems ? a.r3_n_mems[r] : 0;  // pass 3 (k_seed_r3)
-		const uint32_t n = n12 + n3;
+		const uint32_t n = a.mem_off[r + 1] - a.mem_off[r];    // + the deferred calls of this read (k_seed in call mode)
 		const cs_mem_t *src12 = a.pool + a.read_pool_off[r];
 		const cs_mem_t *src3 = a.r3_mems + ((uint64_t)(a.off[r] / kp1) + r);
 		cs_mem_t *dst = a.mems + a.mem_off[r];
@@ -729,13 +1186,30 @@ __global__ void k_collect_sort(CollectArgs a)
 			if (lane == 0) { atomicExch(a.error, CS_E_OVERFLOW); a.read_n_seeds[r] = 0; }
 			continue;
 		}
+		const cs_mem_t *all = src12;                           // the read's mems, unsorted, in one place
+		if (n != n12) { // several sources: gather them into the staging copy of the output region first
+			cs_mem_t *stg = a.stage + a.mem_off[r];
+			uint32_t o = 0;
+			for (uint32_t m = lane; m < n12; m += 32) { const uint4 *p = reinterpret_cast<const uint4*>(src12 + m); uint4 *d = reinterpret_cast<uint4*>(stg + m); d[0] = p[0]; d[1] = p[1]; }
+			o = n12;
+			if (a.read_last_q)
+				for (uint32_t q = a.read_last_q[r]; q != 0xffffffffu; q = a.defer_q[q].w) {
+					const cs_mem_t *sx = a.pool + a.x_off[q];
+					const uint32_t nx = a.x_n[q];
+					for (uint32_t m = lane; m < nx; m += 32) { const uint4 *p = reinterpret_cast<const uint4*>(sx + m); uint4 *d = reinterpret_cast<uint4*>(stg + o + m); d[0] = p[0]; d[1] = p[1]; }
+					o += nx;
+				}
+			for (uint32_t m = lane; m < n3; m += 32) { const uint4 *p = reinterpret_cast<const uint4*>(src3 + m); uint4 *d = reinterpret_cast<uint4*>(stg + o + m); d[0] = p[0]; d[1] = p[1]; }
+			__syncwarp();
+			all = stg;
+		}
 		for (uint32_t m = lane; m < n; m += 32) {
-			const uint4 *p = reinterpret_cast<const uint4*>(m < n12 ? src12 + m : src3 + (m - n12));
+			const uint4 *p = reinterpret_cast<const uint4*>(all + m);
 			uint4 v0 = p[0], v1 = p[1];
 			uint64_t info = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
 			uint32_t rank = 0;
 			for (uint32_t o = 0; o < n; ++o) {
-				uint64_t oi = o < n12 ? src12[o].info : src3[o - n12].info;
+				uint64_t oi = all[o].info;
 				rank += (oi < info) || (oi == info && o < m);
 			}
 			uint4 *d = reinterpret_cast<uint4*>(dst + rank);
@@ -748,10 +1222,15 @@ __global__ void k_collect_sort(CollectArgs a)
 }
 
 // total mems per read (passes 1-2 + pass 3), the input of the offsets scan
-__global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, uint32_t n_reads, uint32_t *out)
+__global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, const uint32_t *read_last_q, const uint4 *defer_q, const uint32_t *x_n,
+                             uint32_t n_reads, uint32_t *out)
 {
-	for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x)
-		out[r] = n12[r] + (n3 ? n3[r] : 0);
+	for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) {
+		uint32_t n = n12[r] + (n3 ? n3[r] : 0);
+		if (read_last_q)
+			for (uint32_t q = read_last_q[r]; q != 0xffffffffu; q = defer_q[q].w) n += x_n[q];
+		out[r] = n;
+	}
 }
 
 __global__ void k_collect_rows(CollectArgs a)

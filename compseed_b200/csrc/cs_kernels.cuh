@@ -16,6 +16,12 @@
 #define CS_SEED_MINBLOCKS 3     // CTAs per SM the register allocation of k_seed is tuned for
 #endif
 
+#define CS_FAST_BLOCK   256     // threads per CTA of k_seed_fast
+#ifndef CS_FAST_MINBLOCKS
+#define CS_FAST_MINBLOCKS 4
+#endif
+#define CS_FAST_SMEM_BYTES ((size_t)CS_FAST_BLOCK * (CS_READ_SMEM * 12))
+
 struct SeedArgs {
 	const uint8_t *bases;       // nt4 codes, concatenated
 	const uint32_t *off;        // n_reads + 1
@@ -24,7 +30,15 @@ struct SeedArgs {
 	const uint64_t *packed;     // 2-bit packed reads (k_pack_reads): read r starts at word (off[r] >> 5) + 2r
 	const uint32_t *nmask;      // ambiguity / end-of-read mask, same word indexing
 	// scratch
-	uint32_t *next_read;        // work counters: [0] k_seed, [1] k_seed_r3
+	uint32_t *next_read;        // work counters: [0] k_seed, [1] k_seed_r3, [2] k_seed_fast
+	// calls k_seed_fast hands to k_seed: {read, pivot | pass << 16, min_intv, previous deferred call of the same
+	// read or ~0}.  NULL: k_seed runs in read mode and takes every read.
+	uint4 *defer_q;
+	uint32_t defer_cap;
+	uint32_t *n_defer;
+	uint32_t *read_last_q;      // [n_reads] last deferred call of each read (chain head), ~0 if none
+	uint64_t *x_off;            // [defer_cap] where the mems of a deferred call start in pool
+	uint32_t *x_n;              // [defer_cap]
 	cs_mem_t *thread_mems;      // [n_threads][mem_cap] per-thread mem list of the read in flight
 	uint32_t mem_cap;
 	uint4 *spill;               // [spill_cap][n_threads] interval-list entries beyond CS_LIST_SMEM
@@ -50,6 +64,11 @@ struct CollectArgs {
 	const uint32_t *off;        // read offsets (locates the third-pass seeds)
 	const cs_mem_t *r3_mems;
 	const uint32_t *r3_n_mems;  // NULL when the third pass is disabled (max_mem_intv == 0)
+	const uint32_t *read_last_q; // deferred calls of each read (NULL: none): chain through defer_q[].w, results at x_off / x_n
+	const uint4 *defer_q;
+	const uint64_t *x_off;
+	const uint32_t *x_n;
+	cs_mem_t *stage;            // scratch with the layout of `mems`: a read's sources gathered before the sort
 	const uint32_t *mem_off;    // exclusive scan of the per-read totals, n_reads + 1
 	cs_mem_t *mems;             // sorted output
 	uint64_t mems_cap;
@@ -75,8 +94,10 @@ __global__ void k_pt_count(const uint64_t *W, uint64_t n, uint32_t K, uint32_t *
 __global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t n_reads, uint64_t *packed, uint32_t *nmask);
 __global__ void k_seed(DevIndex I, SeedArgs a);
 __global__ void k_seed_long(DevIndex I, SeedArgs a);
+__global__ void k_seed_fast(DevIndex I, SeedArgs a);
 __global__ void k_seed_r3(DevIndex I, SeedArgs a);
-__global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, uint32_t n_reads, uint32_t *out);
+__global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, const uint32_t *read_last_q, const uint4 *defer_q, const uint32_t *x_n,
+                             uint32_t n_reads, uint32_t *out);
 __global__ void k_collect_sort(CollectArgs a);
 __global__ void k_collect_rows(CollectArgs a);
 __global__ void k_gather_probe(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed, unsigned long long *sink);

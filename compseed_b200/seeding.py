@@ -52,7 +52,7 @@ class _Result(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_mems", C.c_uint64), ("n_seeds", C.c_uint64),
                 ("mem_off", C.POINTER(C.c_uint32)), ("mems", C.POINTER(C.c_uint64)),
                 ("seed_off", C.POINTER(C.c_uint32)), ("rbeg", C.POINTER(C.c_int64)),
-                ("counters", _Counters), ("kernel_ms", C.c_float * 6)]
+                ("counters", _Counters), ("kernel_ms", C.c_float * 8), ("n_deferred", C.c_uint64)]
 
 
 _lib = None
@@ -95,6 +95,7 @@ def load_library():
     L.cs_probe_random_gather_ex.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.cs_flush_l2.argtypes = [C.c_int]
+    L.cs_debug_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.cs_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.cs_host_unregister.argtypes = [C.c_void_p]
     _lib = L
@@ -140,7 +141,7 @@ class SeedResult:
     seed_off: np.ndarray     # u32 [n+1]
     rbeg: np.ndarray         # i64 [n_seeds]
     counters: dict = field(default_factory=dict)
-    kernel_ms: tuple = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+    kernel_ms: tuple = (0.0,) * 8
 
     @property
     def n_reads(self) -> int:
@@ -278,6 +279,12 @@ class SeedContext:
         _check(load_library().cs_seed_batch_wait_device(self.h, slot, C.byref(r)))
         return self._result(r, copy=False)
 
+    def debug_stats(self, slot: int) -> np.ndarray:
+        """Raw device counters of the last finished run on `slot` (cs_debug_stats)."""
+        out = np.zeros(40, dtype=np.uint64)
+        _check(load_library().cs_debug_stats(self.h, slot, _ptr(out)))
+        return out
+
     def fetch(self, slot: int, copy: bool = True) -> SeedResult:
         r = _Result()
         _check(load_library().cs_seed_batch_fetch(self.h, slot, C.byref(r)))
@@ -292,7 +299,8 @@ class SeedContext:
     def _result(r: _Result, copy: bool) -> SeedResult:
         n, nm, ns = int(r.n_reads), int(r.n_mems), int(r.n_seeds)
         cnt = dict(ext_queries=int(r.counters.ext_queries), ext_calls=int(r.counters.ext_calls),
-                   sal_queries=int(r.counters.sal_queries), sal_calls=int(r.counters.sal_calls))
+                   sal_queries=int(r.counters.sal_queries), sal_calls=int(r.counters.sal_calls),
+                   deferred_reads=int(r.n_deferred))
         ms = tuple(float(x) for x in r.kernel_ms)
         if not r.mem_off:  # device-resident result
             e = np.empty(0, dtype=np.uint32)
@@ -366,7 +374,7 @@ def concat_results(parts: list[SeedResult]) -> SeedResult:
     seed_off = [np.zeros(1, dtype=np.uint32)]
     mb = sb = 0
     cnt: dict = {}
-    ms = [0.0] * 6
+    ms = [0.0] * 8
     for p in parts:
         mem_off.append((p.mem_off[1:].astype(np.int64) + mb).astype(np.uint32))
         seed_off.append((p.seed_off[1:].astype(np.int64) + sb).astype(np.uint32))

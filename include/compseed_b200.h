@@ -91,8 +91,10 @@ typedef struct {
 	const uint32_t *seed_off;  /* [n_reads+1] */
 	const int64_t  *rbeg;      /* [n_seeds] SA[x0 + k*step] in the emission order of bwamem.c:386-399 */
 	cs_counters_t counters;
-	float kernel_ms[6];        /* CUDA-event durations on the slot's stream: [0] seeding (k_seed + k_seed_r3), [1] collect,
-	                              [2] SA-resolve, [3] whole slot incl. copies, [4] k_seed alone, [5] k_seed_r3 alone */
+	float kernel_ms[8];        /* CUDA-event durations on the slot's stream: [0] seeding (k_pack_reads + k_seed_fast + k_seed +
+	                              k_seed_r3), [1] collect, [2] SA-resolve, [3] whole slot incl. copies, [4] passes 1-2 (k_pack_reads +
+	                              k_seed_fast + k_seed), [5] k_seed_r3 alone, [6] k_pack_reads + k_seed_fast, [7] reserved */
+	uint64_t n_deferred;       /* reads the fast kernel handed to the literal kernel */
 } cs_result_t;
 
 typedef struct cs_index cs_index_t;
@@ -163,6 +165,11 @@ int cs_probe_random_gather(int device, uint64_t table_bytes, uint32_t granule, u
  * cudaLimitMaxL2FetchGranularity (0 = leave as is, else 32 / 64 / 128). */
 int cs_probe_random_gather_ex(int device, uint64_t table_bytes, uint32_t granule, uint64_t n_loads, int iters, int unroll,
                               int l2_fetch_granularity, double *gbytes_per_s, double *gloads_per_s);
+/* Raw device counters of the last finished run on a slot: [0] ext queries, [1] ext calls, [2] extends whose
+ * k and l needed two sectors, [3] occurrence-filter probes, [4..19] event counters of a -DCS_STATS build (else 0), [20] reads the fast
+ * kernel deferred to the literal kernel, [21] CTAs of k_seed_fast (0 = not available), [22] CTAs of k_seed,
+ * [24..39] event counters of k_seed_fast in a -DCS_STATS build. */
+int cs_debug_stats(cs_ctx_t *ctx, int slot, uint64_t out[40]);
 /* Writes a buffer larger than L2 (flush between timed iterations). */
 int cs_flush_l2(int device);
 

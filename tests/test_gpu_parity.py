@@ -63,8 +63,9 @@ def test_index_download_roundtrip(cuda_lib, golden):
     assert np.array_equal(d["sa"], golden["sa"])
 
 
+@pytest.mark.parametrize("dense", [0, 1])
 @pytest.mark.parametrize("kind,n_reads", [("random", 20000), ("repeat", 4000), ("long", 300)])
-def test_oracle_parity_seeded(cuda_lib, oracle_lib, kind, n_reads):
+def test_oracle_parity_seeded(cuda_lib, oracle_lib, kind, n_reads, dense):
     if kind == "random":      # config 1 in miniature
         ref = synth.random_reference(400_000, seed=101)
         bases, off, _ = synth.simulate_reads(ref, n_reads, 150, 0.01, seed=102)
@@ -75,7 +76,8 @@ def test_oracle_parity_seeded(cuda_lib, oracle_lib, kind, n_reads):
         ref = synth.repeat_rich_reference(200_000, seed=105, n_segdup=40, segdup_len=3000, n_tandem=40)
         bases, off, _ = synth.simulate_reads(ref, n_reads, [400, 1000, 3000], 0.01, seed=106, n_rate=0.001)
     oi = oracle_lib.OracleIndex.build(ref)
-    idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv)
+    # dense = 1 also switches on the unique-match text paths (forward and backward) of k_seed
+    idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv, dense_sa_intv=dense)
     for r_factor, y, c in [(1.5, 20, 500), (1.0, 20, 50), (2.5, 40, 500)]:
         opt = cuda_lib.SeedOpt(split_factor=r_factor, max_mem_intv=y, max_occ=c)
         want = oi.seed(bases, off, split_len=opt.split_len, max_mem_intv=y, max_occ=c, n_threads=8)
@@ -83,7 +85,7 @@ def test_oracle_parity_seeded(cuda_lib, oracle_lib, kind, n_reads):
         _assert_same(got, want.mem_off, want.mems, want.seed_off, want.rbeg)
         # the occurrence filter only ever removes work: queries <= bwamem's bwt_extend call count (SURVEY 8d "E")
         assert got.counters["ext_queries"] <= want.counters["ext"]
-        assert got.counters["sal_calls"] == want.counters["lf"]
+        assert got.counters["sal_calls"] == (0 if dense else want.counters["lf"])
 
 
 def test_batching_and_slots_do_not_change_results(cuda_lib, oracle_lib):
@@ -190,12 +192,18 @@ def test_result_neutral_caches_can_be_switched_off(cuda_lib, oracle_lib, monkeyp
     want = oi.seed(bases, off, n_threads=8)
     results = {}
     for name, env in {"plain": {"CS_KMER_TABLE_DEPTH": "0", "CS_PRUNE_K": "0"}, "table": {"CS_PRUNE_K": "0"},
-                      "filter": {"CS_KMER_TABLE_DEPTH": "0"}, "both": {}, "deep": {"CS_KMER_TABLE_DEPTH": "11", "CS_PRUNE_K": "16"}}.items():
-        for k in ("CS_KMER_TABLE_DEPTH", "CS_PRUNE_K"):
+                      "filter": {"CS_KMER_TABLE_DEPTH": "0"}, "both": {}, "deep": {"CS_KMER_TABLE_DEPTH": "11", "CS_PRUNE_K": "16"},
+                      # dense SA => unique-match text paths on; they must account for exactly the extends they replace
+                      "text": {"CS_PRUNE_K": "0", "DENSE": "1"}, "text_isa1": {"CS_PRUNE_K": "0", "DENSE": "1", "CS_ISA_INTV": "1"},
+                      "text_isa32": {"CS_KMER_TABLE_DEPTH": "0", "CS_PRUNE_K": "0", "DENSE": "1", "CS_ISA_INTV": "32"},
+                      "all_dense": {"DENSE": "1"}, "all_dense_nofast": {"DENSE": "1", "CS_FAST": "0"}, "all_dense_k12": {"DENSE": "1", "CS_PRUNE_K": "12", "CS_KMER_TABLE_DEPTH": "9"}}.items():
+        for k in ("CS_KMER_TABLE_DEPTH", "CS_PRUNE_K", "CS_ISA_INTV", "CS_FAST"):
             monkeypatch.delenv(k, raising=False)
+        env = dict(env)
+        dense = int(env.pop("DENSE", "0"))
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv)
+        idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv, dense_sa_intv=dense)
         got = cuda_lib.seed_reads(idx, bases, off, batch_reads=2048)
         _assert_same(got, want.mem_off, want.mems, want.seed_off, want.rbeg)
         results[name] = got.counters
@@ -204,3 +212,7 @@ def test_result_neutral_caches_can_be_switched_off(cuda_lib, oracle_lib, monkeyp
     assert results["table"]["ext_queries"] == want.counters["ext"] and results["table"]["ext_calls"] < results["plain"]["ext_calls"]
     assert results["filter"]["ext_queries"] < want.counters["ext"]
     assert results["both"]["ext_calls"] < results["table"]["ext_calls"]
+    for name in ("text", "text_isa1", "text_isa32"):
+        assert results[name]["ext_queries"] == want.counters["ext"], name
+        assert results[name]["ext_calls"] < results["plain"]["ext_calls"], name
+    assert results["all_dense"]["ext_queries"] <= results["all_dense_nofast"]["ext_queries"] <= results["both"]["ext_queries"]
