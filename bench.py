@@ -339,7 +339,7 @@ def main():
                 "algorithmic_bytes_per_read": seed_bytes_per_read, "whole_path_bytes_per_read": path_bytes_per_read,
                 "extends_per_read": E, "two_bucket_ratio": e2_ratio,
                 "device_extends_per_read": counters["ext_queries"] / n_reads, "device_fm_extends_per_read": counters["ext_calls"] / n_reads,
-                "fast_ms_per_launch": fast_ms / args.steps, "deferred_read_share": counters.get("deferred_reads", 0) / n_reads,
+                "fast_ms_per_launch": fast_ms / args.steps, "deferred_calls_per_read": counters.get("deferred_calls", 0) / n_reads,
                 "kernel_share_of_step": {"k_seed_fast": fast_ms / dev_ms, "k_seed": (seed_ms - fast_ms) / dev_ms, "k_seed_r3": r3_ms / dev_ms, "collect": coll_ms / dev_ms, "k_sa_resolve": sa_ms / dev_ms}}
     occ_per_read = 2.0 * E + S
     if args.probe:

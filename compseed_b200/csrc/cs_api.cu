@@ -544,6 +544,7 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 	ctx->mem_cap = std::min<uint32_t>(2 * max_read_len + 16, 4096);
 	ctx->spill_cap = max_read_len > CS_LIST_SMEM ? max_read_len - CS_LIST_SMEM + 1 : 1;
 	ctx->defer_cap = 2 * max_reads + 4096;   // a batch that defers more calls than this is rerun without the fast kernel
+	if (const char *env = getenv("CS_DEFER_CAP")) ctx->defer_cap = (uint32_t)std::max(1, atoi(env));   // (tests force the rerun)
 	for (int i = 0; i < n_slots; ++i) {
 		Slot *s = &ctx->slots[i];
 		const size_t nthreads = std::max((size_t)ctx->grid * CS_SEED_BLOCK, (size_t)ctx->grid_fast * CS_FAST_BLOCK);

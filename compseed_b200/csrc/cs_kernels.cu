@@ -923,29 +923,34 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		STAT(1); if (cmin != 1) STAT(2);
 		r_ext = r_call = 0;
 
-		// ---- occurrence filter (as in seed_body): bit e-1 of kmask <=> the K-mer ending e bases after the pivot
-		//      occurs >= min(cmin, 3) times, i.e. a forward match of e bases may be pushed.  All probes of a
-		//      call are independent loads. ----
-		uint32_t kmask = 0;
+		// ---- occurrence filter (as in seed_body): bit e-1 <=> the K-mer ending e bases after the pivot occurs
+		//      >= min(cmin, 3) times, i.e. a forward match of e bases may be pushed.  Evaluated lazily: only the
+		//      windows a decision below depends on are probed (these probes are the largest share of this
+		//      kernel's DRAM traffic).  All probes of one request are independent loads. ----
+		int e0;                                                     // first window that starts inside the N-free run left of the pivot
 		{
-			const uint32_t omin = cmin > 3 ? 4u : (uint32_t)cmin;
-			const int s0 = cx >= 31 ? cx - 31 : 0, cl = cx - s0;     // N-free run immediately left of the pivot, capped at 31
+			const int s0 = cx >= 31 ? cx - 31 : 0, cl = cx - s0;     // that run, capped at 31 bases
 			int nl = 0;
 			if (cl > 0) {
 				const uint32_t m = (nmask_window(s0) & ((1u << cl) - 1u)) << (32 - cl);
 				nl = m ? __clz((int)m) : cl;
 			}
-			const int e0 = K - nl < 1 ? 1 : K - nl;                     // first window that starts inside that run
-			uint32_t cnt[18];
+			e0 = K - nl < 1 ? 1 : K - nl;
+		}
+		auto probe_bits = [&](int elo, int ehi) -> uint32_t {       // filter bits of the windows elo..ehi
+			const uint32_t omin = cmin > 3 ? 4u : (uint32_t)cmin;
+			uint32_t cnt[18], mask = 0;
+			if (elo < e0) elo = e0;
 #pragma unroll
 			for (int u = 0; u < 18; ++u) {
 				const int e = u + 1;
 				cnt[u] = 0;
-				if (e >= e0 && e < K) { cnt[u] = pt_count(key_of(cx + e - K, K)); ++n_probe; }
+				if (e >= elo && e <= ehi && e < K) { cnt[u] = pt_count(key_of(cx + e - K, K)); ++n_probe; }
 			}
 #pragma unroll
-			for (int u = 0; u < 18; ++u) if (cnt[u] == 3 || (cnt[u] != 0 && cnt[u] >= omin)) kmask |= 1u << u;
-		}
+			for (int u = 0; u < 18; ++u) if (cnt[u] == 3 || (cnt[u] != 0 && cnt[u] >= omin)) mask |= 1u << u;
+			return mask;
+		};
 
 		// ---- forward pass (bwt.c:304-321) without pushes: until the match is one occurrence, dies, or hits an N / the end ----
 		uint64_t c0, c1, c2;
@@ -993,9 +998,12 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		const int end = i, d = end - cx;                            // the longest forward match is L = [cx, end)
 		if (round == 1) x = end;                                    // next pivot (bwt.c:323, bwamem.c:228)
 
-		// ---- what would the literal pass have pushed? ----
-		const bool pushable = d >= K || (kmask & ((1u << d) - 1u)) != 0;
-		if (!pushable) { STAT(3); n_ext += r_ext; n_call += r_call; continue; }   // nothing: the call returns no SMEM
+		// ---- what would the literal pass have pushed?  Matches of >= K bases always; shorter ones by the filter. ----
+		uint32_t kmask = 0;
+		if (d < K) {
+			kmask = probe_bits(1, d);
+			if (kmask == 0) { STAT(3); n_ext += r_ext; n_call += r_call; continue; }   // nothing: the call returns no SMEM
+		}
 		if (cmin != 1 || !(d >= K || ((kmask >> (d - 1)) & 1))) { // pass 2 with a list, or L itself not pushed
 			if (cmin != 1) STAT(4); else STAT(5);
 			defer_call(cx, cmin); continue;
@@ -1041,8 +1049,14 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		}
 		const bool ext_fails = bi >= 0 && base_at(bi) <= 3;         // bwt.c:330: no bwt_extend at the read start / an N
 		if (!failed) r_ext += (uint32_t)jb + (ext_fails ? 1u : 0u);
-		if (ext_fails) { // could a shorter match survive position bi?  They all start with q[bi, bi+K) there.
-			const int dlow = kmask ? __ffs((int)kmask) : K;
+		if (ext_fails) { // could a shorter match survive position bi?  They all start with q[bi, bi+K) there ...
+			int dlow;                                               // ... if none of them is shorter than K - (cx - bi) bases
+			if (d < K) dlow = __ffs((int)kmask);
+			else {
+				const int need_d = K - (cx - bi);
+				const uint32_t m = need_d > 1 ? probe_bits(1, need_d - 1) : 0u;
+				dlow = m ? __ffs((int)m) : (need_d > 1 ? need_d : 1);
+			}
 			bool ok = false;
 			if (cx + dlow - bi >= K && !has_n(bi, K)) { ok = pt_count(key_of(bi, K)) == 0; ++n_probe; if (!ok) STAT(8); }
 			else STAT(9);

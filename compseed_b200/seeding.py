@@ -300,7 +300,7 @@ class SeedContext:
         n, nm, ns = int(r.n_reads), int(r.n_mems), int(r.n_seeds)
         cnt = dict(ext_queries=int(r.counters.ext_queries), ext_calls=int(r.counters.ext_calls),
                    sal_queries=int(r.counters.sal_queries), sal_calls=int(r.counters.sal_calls),
-                   deferred_reads=int(r.n_deferred))
+                   deferred_calls=int(r.n_deferred))
         ms = tuple(float(x) for x in r.kernel_ms)
         if not r.mem_off:  # device-resident result
             e = np.empty(0, dtype=np.uint32)

@@ -94,7 +94,7 @@ typedef struct {
 	float kernel_ms[8];        /* CUDA-event durations on the slot's stream: [0] seeding (k_pack_reads + k_seed_fast + k_seed +
 	                              k_seed_r3), [1] collect, [2] SA-resolve, [3] whole slot incl. copies, [4] passes 1-2 (k_pack_reads +
 	                              k_seed_fast + k_seed), [5] k_seed_r3 alone, [6] k_pack_reads + k_seed_fast, [7] reserved */
-	uint64_t n_deferred;       /* reads the fast kernel handed to the literal kernel */
+	uint64_t n_deferred;       /* bwt_smem1a calls the fast kernel handed to the literal kernel */
 } cs_result_t;
 
 typedef struct cs_index cs_index_t;

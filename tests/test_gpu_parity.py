@@ -196,8 +196,8 @@ def test_result_neutral_caches_can_be_switched_off(cuda_lib, oracle_lib, monkeyp
                       # dense SA => unique-match text paths on; they must account for exactly the extends they replace
                       "text": {"CS_PRUNE_K": "0", "DENSE": "1"}, "text_isa1": {"CS_PRUNE_K": "0", "DENSE": "1", "CS_ISA_INTV": "1"},
                       "text_isa32": {"CS_KMER_TABLE_DEPTH": "0", "CS_PRUNE_K": "0", "DENSE": "1", "CS_ISA_INTV": "32"},
-                      "all_dense": {"DENSE": "1"}, "all_dense_nofast": {"DENSE": "1", "CS_FAST": "0"}, "all_dense_k12": {"DENSE": "1", "CS_PRUNE_K": "12", "CS_KMER_TABLE_DEPTH": "9"}}.items():
-        for k in ("CS_KMER_TABLE_DEPTH", "CS_PRUNE_K", "CS_ISA_INTV", "CS_FAST"):
+                      "all_dense": {"DENSE": "1"}, "all_dense_tiny_queue": {"DENSE": "1", "CS_DEFER_CAP": "7"}, "all_dense_nofast": {"DENSE": "1", "CS_FAST": "0"}, "all_dense_k12": {"DENSE": "1", "CS_PRUNE_K": "12", "CS_KMER_TABLE_DEPTH": "9"}}.items():
+        for k in ("CS_KMER_TABLE_DEPTH", "CS_PRUNE_K", "CS_ISA_INTV", "CS_FAST", "CS_DEFER_CAP"):
             monkeypatch.delenv(k, raising=False)
         env = dict(env)
         dense = int(env.pop("DENSE", "0"))
@@ -216,3 +216,7 @@ def test_result_neutral_caches_can_be_switched_off(cuda_lib, oracle_lib, monkeyp
         assert results[name]["ext_queries"] == want.counters["ext"], name
         assert results[name]["ext_calls"] < results["plain"]["ext_calls"], name
     assert results["all_dense"]["ext_queries"] <= results["all_dense_nofast"]["ext_queries"] <= results["both"]["ext_queries"]
+    assert results["all_dense"]["deferred_calls"] > 7                 # the fast kernel ran and handed calls over
+    assert results["all_dense_nofast"]["deferred_calls"] == 0
+    # a queue too small for the batch: rerun through the literal kernel alone, same answer (checked above)
+    assert results["all_dense_tiny_queue"]["ext_queries"] == results["all_dense_nofast"]["ext_queries"]
