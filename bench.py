@@ -207,11 +207,11 @@ def main():
     barrier()
     sampler.start()
     t0 = time.perf_counter()
-    dev_ms, seed_ms, coll_ms, sa_ms, r3_ms, fast_ms = 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
+    dev_ms, seed_ms, coll_ms, sa_ms, r3_ms, fast_ms, walk_ms = 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
     for _ in range(args.steps):
         ctx.run_staged(0, opt)
         last = ctx.wait_device(0)
-        seed_ms += last.kernel_ms[4]; r3_ms += last.kernel_ms[5]; fast_ms += last.kernel_ms[6]
+        seed_ms += last.kernel_ms[4]; r3_ms += last.kernel_ms[5]; fast_ms += last.kernel_ms[6]; walk_ms += last.kernel_ms[7]
         coll_ms += last.kernel_ms[1]
         sa_ms += last.kernel_ms[2]
         dev_ms += last.kernel_ms[0] + last.kernel_ms[1] + last.kernel_ms[2]   # CUDA events on the launching stream
@@ -334,13 +334,13 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "k_seed_traffic.json")))["dram_bytes_per_read"] * n_reads
     except Exception:
         pass
-    roofline = {"kernel": "k_seed_fast + k_seed + k_seed_r3 (the three passes of mem_collect_intv)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"kernel": "k_seed_fast + k_seed_walk + k_seed + k_seed_r3 (the three passes of mem_collect_intv)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "ms_per_launch": seed_ms_per_launch,
                 "algorithmic_bytes_per_read": seed_bytes_per_read, "whole_path_bytes_per_read": path_bytes_per_read,
                 "extends_per_read": E, "two_bucket_ratio": e2_ratio,
                 "device_extends_per_read": counters["ext_queries"] / n_reads, "device_fm_extends_per_read": counters["ext_calls"] / n_reads,
                 "fast_ms_per_launch": fast_ms / args.steps, "deferred_calls_per_read": counters.get("deferred_calls", 0) / n_reads,
-                "kernel_share_of_step": {"k_seed_fast": fast_ms / dev_ms, "k_seed": (seed_ms - fast_ms) / dev_ms, "k_seed_r3": r3_ms / dev_ms, "collect": coll_ms / dev_ms, "k_sa_resolve": sa_ms / dev_ms}}
+                "kernel_share_of_step": {"k_seed_fast": fast_ms / dev_ms, "k_seed_walk": walk_ms / dev_ms, "k_seed": (seed_ms - fast_ms - walk_ms) / dev_ms, "k_seed_r3": r3_ms / dev_ms, "collect": coll_ms / dev_ms, "k_sa_resolve": sa_ms / dev_ms}}
     occ_per_read = 2.0 * E + S
     if args.probe:
         gb, gl = cs.probe_random_gather(local_rank, 4 << 30, 32, 1 << 28, 2)
@@ -358,7 +358,7 @@ def main():
             "occ_lookups_per_s": occ_per_read * value, "occ_lookups_per_read": occ_per_read,
             "mems_per_read": n_mems / n_reads, "seeds_per_read": n_seeds / n_reads,
             "wall_ms_per_step": wall_ms_max / args.steps,
-            "e2e": e2e, "gpu_launches": 8 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "gpu_launches": 9 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "counters": counters, "setup_s": setup_s}
     print(json.dumps(line))
     if use_dist:

@@ -422,8 +422,9 @@ fail:
 // batch contexts
 // ---------------------------------------------------------------------------------------------
 struct Ctrl { // zeroed before every run; copied back after it
-	uint32_t next_read[3];   // work counters: [0] k_seed, [1] k_seed_r3, [2] k_seed_fast
-	uint32_t n_defer;        // reads k_seed_fast handed to k_seed
+	uint32_t next_read[4];   // work counters: [0] k_seed, [1] k_seed_r3, [2] k_seed_fast, [3] k_seed_walk
+	uint32_t n_defer;        // calls handed on by k_seed_fast (and k_seed_walk)
+	uint32_t pad0;
 	unsigned long long pool_used;
 	unsigned long long counters[4 + 32];   // [4..19] k_seed, [20..35] k_seed_fast: event counters of a -DCS_STATS diagnostics build, else 0
 	unsigned long long sa_work, lf_steps;
@@ -433,7 +434,7 @@ struct Ctrl { // zeroed before every run; copied back after it
 
 struct Slot {
 	cudaStream_t stream;
-	cudaEvent_t ev[7];   // slot start, seed start, seed end, collect end, sa end, k_seed end (k_seed_r3 runs after it), k_seed_fast end
+	cudaEvent_t ev[8];   // slot start, seed start, seed end, collect end, sa end, k_seed end (k_seed_r3 runs after it), k_seed_fast end
 	cudaEvent_t ev_done;
 	// pinned host
 	uint8_t *h_bases; uint32_t *h_off;
@@ -443,7 +444,7 @@ struct Slot {
 	uint8_t *d_bases; uint32_t *d_off;
 	uint64_t *d_packed; uint32_t *d_nmask;   // 2-bit packed reads + ambiguity mask (k_pack_reads)
 	uint4 *d_defer_q;                         // calls the fast kernel hands to the literal kernel (SeedArgs::defer_q)
-	uint32_t *d_read_last_q, *d_x_n; uint64_t *d_x_off;
+	uint32_t *d_read_last_q, *d_x_n, *d_defer_bits; uint64_t *d_x_off;
 	cs_mem_t *d_stage;                        // collect: a read's sources gathered before the sort
 	bool used_fast;
 	Ctrl *d_ctrl;
@@ -476,11 +477,11 @@ struct cs_ctx {
 static void slot_free(Slot *s)
 {
 	if (s->stream) cudaStreamDestroy(s->stream);
-	for (int i = 0; i < 7; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+	for (int i = 0; i < 8; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
 	if (s->ev_done) cudaEventDestroy(s->ev_done);
 	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
 	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
-	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
+	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_defer_bits); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
 	cudaFree(s->d_pool); cudaFree(s->d_mems); cudaFree(s->d_read_pool_off); cudaFree(s->d_read_n_mems);
 	cudaFree(s->d_r3_mems); cudaFree(s->d_r3_n_mems); cudaFree(s->d_tot_n_mems);
 	cudaFree(s->d_mem_off); cudaFree(s->d_read_n_seeds); cudaFree(s->d_seed_off); cudaFree(s->d_rows); cudaFree(s->d_scan_tmp);
@@ -532,6 +533,8 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 			if (!(env && atoi(env) == 0) && d.text && d.isa && d.pt && d.pt_k >= 4 && d.pt_k <= 19 && d.kt && d.kt_depth >= 2 &&
 			    d.kt_depth < d.pt_k && max_read_len + 32 <= 32 * CS_READ_SMEM) {
 				CK(cudaFuncSetAttribute(k_seed_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_FAST_SMEM_BYTES));
+				CK(cudaFuncSetAttribute(k_seed_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_FAST_SMEM_BYTES));
+				CK(cudaFuncSetAttribute(k_seed_r3_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_FAST_SMEM_BYTES));
 				CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed_fast, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES));
 				if (per_sm >= 1) ctx->grid_fast = std::min<int>(idx->n_sm * per_sm, (int)((max_reads + CS_FAST_BLOCK - 1) / CS_FAST_BLOCK));
 			}
@@ -549,7 +552,7 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		Slot *s = &ctx->slots[i];
 		const size_t nthreads = std::max((size_t)ctx->grid * CS_SEED_BLOCK, (size_t)ctx->grid_fast * CS_FAST_BLOCK);
 		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-		for (int e = 0; e < 7; ++e) CK(cudaEventCreate(&s->ev[e]));
+		for (int e = 0; e < 8; ++e) CK(cudaEventCreate(&s->ev[e]));
 		CK(cudaEventCreate(&s->ev_done));
 		CK(cudaMallocHost(&s->h_bases, max_bases));
 		CK(cudaMallocHost(&s->h_off, ((size_t)max_reads + 1) * 4));
@@ -562,6 +565,7 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		CK(cudaMalloc(&s->d_defer_q, (size_t)ctx->defer_cap * sizeof(uint4)));
 		CK(cudaMalloc(&s->d_x_off, (size_t)ctx->defer_cap * 8));
 		CK(cudaMalloc(&s->d_x_n, (size_t)ctx->defer_cap * 4));
+		CK(cudaMalloc(&s->d_defer_bits, (size_t)ctx->defer_cap * 4));
 		CK(cudaMalloc(&s->d_read_last_q, ((size_t)max_reads + 1) * 4));
 		CK(cudaMalloc(&s->d_stage, ctx->max_mems * sizeof(cs_mem_t)));
 		CK(cudaMalloc(&s->d_thread_mems, nthreads * ctx->mem_cap * sizeof(cs_mem_t)));
@@ -625,7 +629,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	a.packed = s->d_packed; a.nmask = s->d_nmask;
 	a.next_read = s->d_ctrl->next_read;
 	a.defer_q = nullptr; a.defer_cap = ctx->defer_cap; a.n_defer = &s->d_ctrl->n_defer;
-	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n;
+	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n; a.defer_bits = s->d_defer_bits;
 	s->used_fast = false;
 	a.thread_mems = s->d_thread_mems; a.mem_cap = ctx->mem_cap;
 	a.spill = s->d_spill; a.spill_cap = ctx->spill_cap;
@@ -641,16 +645,28 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 		s->used_fast = true;
 		k_seed_fast<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, s->stream>>>(idx->d, a);
 		CK(cudaGetLastError());
+		CK(cudaEventRecord(s->ev[6], s->stream));
+		k_seed_walk<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, s->stream>>>(idx->d, a);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(s->ev[7], s->stream));
+	} else {
+		CK(cudaEventRecord(s->ev[6], s->stream));
+		CK(cudaEventRecord(s->ev[7], s->stream));
 	}
-	CK(cudaEventRecord(s->ev[6], s->stream));
 	// (the spill stride inside k_seed follows the launched grid), then pass 3
 	if (ctx->max_read_len + 32 <= 32 * CS_READ_SMEM) k_seed<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
 	else k_seed_long<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(s->ev[5], s->stream));
 	if (pass3) {
-		int g3 = std::min<int>(ctx->grid_r3, (int)((n + 255) / 256));
-		k_seed_r3<<<g3 < 1 ? 1 : g3, 256, 0, s->stream>>>(idx->d, a);
+		const char *env = getenv("CS_R3_FAST");
+		if (s->used_fast && !(env && atoi(env) == 0)) { // text-assisted: reads the first-pass SMEMs k_seed_fast left in the pool
+			int gf = std::min<int>(ctx->grid_fast, (int)((n + CS_FAST_BLOCK - 1) / CS_FAST_BLOCK));
+			k_seed_r3_fast<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, s->stream>>>(idx->d, a);
+		} else {
+			int g3 = std::min<int>(ctx->grid_r3, (int)((n + 255) / 256));
+			k_seed_r3<<<g3 < 1 ? 1 : g3, 256, 0, s->stream>>>(idx->d, a);
+		}
 		CK(cudaGetLastError());
 	}
 	CK(cudaEventRecord(s->ev[2], s->stream));
@@ -727,7 +743,7 @@ static void fill_result(cs_ctx *ctx, Slot *s, cs_result_t *out, bool host_ptrs)
 	cudaEventElapsedTime(&out->kernel_ms[4], s->ev[1], s->ev[5]);
 	cudaEventElapsedTime(&out->kernel_ms[5], s->ev[5], s->ev[2]);
 	cudaEventElapsedTime(&out->kernel_ms[6], s->ev[1], s->ev[6]);
-	out->kernel_ms[7] = 0.f;
+	cudaEventElapsedTime(&out->kernel_ms[7], s->ev[6], s->ev[7]);
 	out->n_deferred = s->h_ctrl->n_defer;
 	(void)ctx;
 }

@@ -496,6 +496,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 					const uint32_t nq = *a.n_defer;
 					if (rd >= (nq < a.defer_cap ? nq : a.defer_cap)) { st = ST_IDLE; break; }
 					cur_q = rd; item = a.defer_q[rd]; rd = item.x;
+					if (item.y >> 31) break;                            // done by k_seed_walk: fetch again
 				} else if (rd >= a.n_reads) { st = ST_IDLE; break; }
 				uint32_t o = a.off[rd];
 				len = (int)(a.off[rd + 1] - o);
@@ -512,7 +513,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				nmem = 0; round = 1; x = 0; err_list = err_mem = false;
 				st = ST_R1_PIVOT;
 				if (a.defer_q) { // one call: a first-pass pivot (then the second pass of what it finds) or a second-pass pivot
-					round = (int)(item.y >> 16); old_n = 0; r2k = 0;
+					round = (int)((item.y >> 16) & 3); old_n = 0; r2k = 0;
 					start_call((int)(item.y & 0xffff), (uint64_t)item.z);
 				}
 			} break;
@@ -868,6 +869,14 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		// (past the capacity nothing is stored: the host sees n_defer > defer_cap and reruns the batch through k_seed alone)
 		if (q < a.defer_cap) { a.defer_q[q] = make_uint4(rd, (uint32_t)pivot | ((uint32_t)round << 16), (uint32_t)mi, last_q); last_q = q; }
 	};
+	// ... or, when its list can only hold the few short matches `bits` (depth of the longest forward match: d), to k_seed_walk
+	auto defer_walk = [&](int pivot, uint64_t mi, int d, uint32_t bits) {
+		const uint32_t q = atomicAdd(a.n_defer, 1u);
+		if (q < a.defer_cap) {
+			a.defer_q[q] = make_uint4(rd, (uint32_t)pivot | ((uint32_t)round << 16) | ((uint32_t)d << 18) | 0x80000000u, (uint32_t)mi, last_q);
+			a.defer_bits[q] = bits; last_q = q;
+		}
+	};
 
 	for (;;) {
 		// ---- pick this lane's next call: (cx, cmin) ----
@@ -1006,7 +1015,9 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		}
 		if (cmin != 1 || !(d >= K || ((kmask >> (d - 1)) & 1))) { // pass 2 with a list, or L itself not pushed
 			if (cmin != 1) STAT(4); else STAT(5);
-			defer_call(cx, cmin); continue;
+			if (d < K && __popc(kmask) <= CS_WALK_MAX && cmin < 0x80000000ull) defer_walk(cx, cmin, d, kmask);
+			else defer_call(cx, cmin);
+			continue;
 		}
 		if (!unique) STAT(6);
 
@@ -1096,6 +1107,152 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_fast(DevIndex I, SeedArgs a) { seed_fast_body<CS_READ_SMEM>(I, a); }
 
 // ---------------------------------------------------------------------------------------------
+// Walk kernel: the deferred calls whose interval list is SHORT forward matches only.
+//
+// k_seed_fast hands over, with their filter bits, the calls whose longest forward match L has fewer
+// than K bases and is either not pushable itself (first pass) or belongs to the second pass: the list
+// of the literal pass then holds at most CS_WALK_MAX matches E_e = q[cx, cx+e), one per filter bit.
+// In bwt_smem1a's backward phase a list entry's fate does not depend on the others except through
+// the start of the last SMEM found: a longer entry is a right-extension of a shorter one, so it dies
+// no later; hence when E_e fails to extend no longer entry is alive (curr->n == 0, bwt.c:332), and
+// duplicates dropped by the size test (bwt.c:338) would fail at the same base as the entry that
+// shadows them and be rejected as contained (bwt.c:333).  So each entry is walked backward alone,
+// longest first, with plain bwt_extend steps (table or FM-index), and the containment test is applied
+// in that order.  An entry is in the list only if the forward pass pushed it: the size changed at
+// the next base (bwt.c:311-312) or it is the forward pass's last interval (bwt.c:317,321).
+// One task per lane; all lanes run the same phases.  A walk that does not end within CS_WALK_STEPS
+// bases goes back to the literal kernel.
+// ---------------------------------------------------------------------------------------------
+#define CS_WALK_STEPS 96
+__global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(DevIndex I, SeedArgs a)
+{
+	constexpr int RW = CS_READ_SMEM;
+	extern __shared__ uint4 s_dyn[];
+	uint64_t *s_rd = reinterpret_cast<uint64_t*>(s_dyn);
+	uint32_t *s_nm = reinterpret_cast<uint32_t*>(s_rd + RW * CS_FAST_BLOCK);
+	const int t = threadIdx.x;
+	const size_t gtid = (size_t)blockIdx.x * CS_FAST_BLOCK + t;
+	cs_mem_t *const my = a.thread_mems + gtid * a.mem_cap;
+	const cs_seed_opt_t opt = a.opt;
+	const int kd = (int)I.kt_depth;
+	uint32_t n_ext = 0, n_call = 0, n_two = 0;
+	bool exhausted = false;
+
+	auto rd_word = [&](uint32_t wi) -> uint64_t { return s_rd[wi * CS_FAST_BLOCK + t]; };
+	auto nm_word = [&](uint32_t wi) -> uint32_t { return s_nm[wi * CS_FAST_BLOCK + t]; };
+	auto base_at = [&](int pos) -> int {
+		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
+		return ((nm_word(wi) >> sh) & 1) ? 4 : (int)((rd_word(wi) >> (2 * sh)) & 3);
+	};
+	auto key_of = [&](int pos, int cnt) -> uint64_t { // cnt < 32 bases from pos, base j at bits 2j
+		uint32_t wi = (uint32_t)pos >> 5, sh = ((uint32_t)pos & 31) * 2;
+		uint64_t v = rd_word(wi) >> sh;
+		if (sh) v |= rd_word(wi + 1) << (64 - sh);
+		return v & ((1ull << (2 * cnt)) - 1);
+	};
+
+	for (;;) {
+		// ---- next walk task of the queue (tasks of the literal kernel are skipped) ----
+		uint32_t q = 0; uint4 item = make_uint4(0, 0, 0, 0);
+		bool active = false;
+		while (!exhausted) {
+			q = atomicAdd(a.next_read + 3, 1u);
+			const uint32_t nq = *reinterpret_cast<volatile uint32_t*>(a.n_defer);
+			if (q >= (nq < a.defer_cap ? nq : a.defer_cap)) { exhausted = true; break; }
+			item = a.defer_q[q];
+			if (item.y >> 31) { active = true; break; }
+		}
+		if (__all_sync(0xffffffffu, !active)) break;
+		if (!active) continue;
+		const uint32_t rd = item.x;
+		const int cx = (int)(item.y & 0xffff), round = (int)((item.y >> 16) & 3), d = (int)((item.y >> 18) & 31);
+		const uint64_t cmin = item.z;
+		uint32_t bits = a.defer_bits[q];
+		{
+			const uint32_t o = a.off[rd];
+			const int len = (int)(a.off[rd + 1] - o);
+			const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * rd;
+			const uint32_t nw = ((uint32_t)len >> 5) + 2;
+#pragma unroll
+			for (uint32_t wi = 0; wi < RW; ++wi) {
+				s_rd[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.packed + w0 + wi) : 0ull;
+				s_nm[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.nmask + w0 + wi) : 0xffffffffu;
+			}
+		}
+		uint32_t nm = 0, t_ext = 0, t_call = 0;
+		bool first = true, punt = false;
+		int last_start = 0;
+		while (bits && !punt) { // entries, longest first
+			const int e = 32 - __clz((int)bits);
+			bits &= ~(1u << (e - 1));
+			// the interval of q[cx, cx+e) ...
+			uint64_t c0, c1, c2;
+			kt_lookup(I, (uint32_t)(e < kd ? e : kd), key_of(cx, e < kd ? e : kd), c0, c1, c2);
+			for (int k = kd; k < e; ++k) { // ... deeper than the table: forward bwt_extend steps
+				uint64_t o0, o1, o2; uint32_t two;
+				dev_extend(I, c0, c1, c2, 3 - base_at(cx + k), 0, o0, o1, o2, two);
+				c0 = o0; c1 = o1; c2 = o2; ++t_call; n_two += two;
+			}
+			if (e < d) { // pushed only if the next forward step changed the size (bwt.c:311-312)
+				uint64_t o0, o1, o2;
+				if (e + 1 <= kd) kt_lookup(I, (uint32_t)(e + 1), key_of(cx, e + 1), o0, o1, o2);
+				else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - base_at(cx + e), 0, o0, o1, o2, two); ++t_call; n_two += two; }
+				if (o2 == c2) continue;
+			}
+			// backward sweeps of this entry alone (bwt.c:326-345)
+			int bi = cx - 1;
+			for (int steps = 0; ; ++steps) {
+				const int b = bi >= 0 ? base_at(bi) : 4;
+				if (b > 3) break;                                   // read start / N: no bwt_extend (bwt.c:330)
+				if (steps >= CS_WALK_STEPS) { punt = true; break; }
+				const int new_len = cx + e - bi;
+				uint64_t o0, o1, o2;
+				++t_ext;
+				if (new_len <= kd) kt_lookup(I, (uint32_t)new_len, key_of(bi, new_len), o0, o1, o2);
+				else { uint32_t two; dev_extend(I, c0, c1, c2, b, 1, o0, o1, o2, two); ++t_call; n_two += two; }
+				if (o2 < cmin) break;                               // bwt.c:331
+				c0 = o0; c1 = o1; c2 = o2; --bi;
+			}
+			if (punt) break;
+			if (first || bi + 1 < last_start) { // bwt.c:332-336
+				first = false; last_start = bi + 1;
+				if (cx + e - (bi + 1) >= opt.min_seed_len) { // bwamem.c:231-233,247
+					if (nm >= a.mem_cap) { punt = true; break; }
+					uint4 *p = reinterpret_cast<uint4*>(my + nm);
+					p[0] = make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)c1, (uint32_t)(c1 >> 32));
+					p[1] = make_uint4((uint32_t)c2, (uint32_t)(c2 >> 32), (uint32_t)(cx + e), (uint32_t)(bi + 1));
+					++nm;
+				}
+			}
+		}
+		if (punt) { a.defer_q[q].y = item.y & 0x7fffffffu; continue; }   // the literal kernel takes it (it runs after this one)
+		n_ext += t_ext; n_call += t_call;
+		// second-pass calls of what a first-pass call found (bwamem.c:238-249): ordinary calls for the literal kernel
+		if (round == 1)
+			for (uint32_t m = 0; m < nm; ++m) {
+				const uint4 v = reinterpret_cast<const uint4*>(my + m)[1];
+				const int s = (int)v.w, e = (int)v.z;
+				const uint64_t sz = (uint64_t)v.x | ((uint64_t)v.y << 32);
+				if (e - s < opt.split_len || sz > (uint64_t)opt.split_width) continue;
+				const uint32_t q2 = atomicAdd(a.n_defer, 1u);
+				if (q2 < a.defer_cap) a.defer_q[q2] = make_uint4(rd, (uint32_t)((s + e) >> 1) | (2u << 16), (uint32_t)(sz + 1), atomicExch(a.read_last_q + rd, q2));
+			}
+		{
+			uint32_t cnt = nm;
+			unsigned long long o = atomicAdd(a.pool_used, (unsigned long long)cnt);
+			if (o + cnt > a.pool_cap) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
+			a.x_off[q] = o; a.x_n[q] = cnt;
+			const uint4 *src = reinterpret_cast<const uint4*>(my);
+			uint4 *dst = reinterpret_cast<uint4*>(a.pool + o);
+			for (uint32_t m = 0; m < 2 * cnt; ++m) dst[m] = src[m];
+		}
+	}
+	if (n_ext) atomicAdd(a.counters + 0, (unsigned long long)n_ext);
+	if (n_call) atomicAdd(a.counters + 1, (unsigned long long)n_call);
+	if (n_two) atomicAdd(a.counters + 2, (unsigned long long)n_two);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Third pass ("LAST-like", bwamem.c:253-268 + bwt_seed_strategy1, bwt.c:358-379) as its own kernel:
 // forward-only chains with no interval lists, so it needs no shared memory and few registers and
 // runs at full occupancy.  It is independent of passes 1-2; the collect pass merges and sorts.
@@ -1171,6 +1328,176 @@ __global__ void __launch_bounds__(256, 4) k_seed_r3(DevIndex I, SeedArgs a)
 	}
 	if (n_ext) atomicAdd(a.counters + 0, n_ext);
 	if (n_call) atomicAdd(a.counters + 1, n_call);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Third pass, text-assisted (used together with k_seed_fast; k_seed_r3 above is the general kernel).
+//
+// bwt_seed_strategy1 (bwt.c:358-379) walks forward from x until the interval has fewer than
+// max_mem_intv rows AND at least min_seed_len + 1 bases; on a mostly unique reference that is the
+// (min_seed_len+1)-mer W = q[x, x+k+1) itself.  If W lies inside a first-pass SMEM with ONE
+// occurrence (k_seed_fast left it in the read's pool entry, and its text position is SA[x[0]]), W
+// occurs at a known text position P; and if the K-mer filter says that W's first K bases occur
+// exactly once in the text, W occurs exactly once too: its bi-interval is (row of suffix P, row of
+// the suffix where revcomp(W) starts, 1), two lookups in the sampled inverse SA plus a few LF steps
+// instead of one table jump and k+1-13 bwt_extend calls with two Occ sectors each.  A chain that
+// cannot reach k+1 bases (N, read end) or whose first K bases do not occur at all ends without a
+// seed, with the same next x as the reference.  Every other chain (repeats,
+// K > k, chains outside such an SMEM whose K-mer exists) is walked literally, as in k_seed_r3.
+// One read per lane, one chain per iteration, all lanes in the same phase.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fast(DevIndex I, SeedArgs a)
+{
+	constexpr int RW = CS_READ_SMEM;
+	extern __shared__ uint4 s_dyn[];
+	uint64_t *s_rd = reinterpret_cast<uint64_t*>(s_dyn);
+	uint32_t *s_nm = reinterpret_cast<uint32_t*>(s_rd + RW * CS_FAST_BLOCK);
+	const int t = threadIdx.x;
+	const cs_seed_opt_t opt = a.opt;
+	const int K = (int)I.pt_k, kd = (int)I.kt_depth, W = opt.min_seed_len + 1;   // host guarantees K <= min_seed_len
+	const uint32_t kp1 = (uint32_t)W;
+	const int jump = kd < opt.min_seed_len ? kd : opt.min_seed_len;
+	uint32_t n_ext = 0, n_call = 0, n_probe = 0;
+	bool have = false, exhausted = false;
+	uint32_t rd = 0, nmem = 0, n12 = 0; int len = 0, x = 0;
+	const cs_mem_t *pool12 = nullptr; cs_mem_t *out = nullptr;
+	int ms = 0, me = 0; uint64_t mtb = 0;                     // the unique first-pass SMEM [ms, me) last used, at text position mtb
+
+	auto rd_word = [&](uint32_t wi) -> uint64_t { return s_rd[wi * CS_FAST_BLOCK + t]; };
+	auto nm_word = [&](uint32_t wi) -> uint32_t { return s_nm[wi * CS_FAST_BLOCK + t]; };
+	auto base_at = [&](int pos) -> int {
+		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
+		return ((nm_word(wi) >> sh) & 1) ? 4 : (int)((rd_word(wi) >> (2 * sh)) & 3);
+	};
+	auto key_of = [&](int pos, int cnt) -> uint64_t {
+		uint32_t wi = (uint32_t)pos >> 5, sh = ((uint32_t)pos & 31) * 2;
+		uint64_t v = rd_word(wi) >> sh;
+		if (sh) v |= rd_word(wi + 1) << (64 - sh);
+		return v & ((1ull << (2 * cnt)) - 1);
+	};
+	auto nmask_window = [&](int pos) -> uint32_t {
+		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
+		uint32_t m = nm_word(wi) >> sh;
+		if (sh) m |= nm_word(wi + 1) << (32 - sh);
+		return m;
+	};
+	auto isa_near = [&](uint64_t p, uint64_t &row, int &steps) {
+		const uint64_t smask = (1ull << I.isa_shift) - 1;
+		uint64_t jj = (p + smask) & ~smask;
+		if (jj > I.seq_len) jj = I.seq_len;
+		row = jj == I.seq_len ? 0ull : __ldg(I.isa + (jj >> I.isa_shift));
+		steps = (int)(jj - p);
+	};
+	auto put = [&](uint64_t x0, uint64_t x1, uint64_t x2, int start, int end) {
+		uint4 *p = reinterpret_cast<uint4*>(out + nmem);
+		p[0] = make_uint4((uint32_t)x0, (uint32_t)(x0 >> 32), (uint32_t)x1, (uint32_t)(x1 >> 32));
+		p[1] = make_uint4((uint32_t)x2, (uint32_t)(x2 >> 32), (uint32_t)end, (uint32_t)start);
+		++nmem;
+	};
+
+	for (;;) {
+		// ---- this lane's next chain start x (bwamem.c:253-268) ----
+		bool active = false;
+		while (!exhausted) {
+			if (!have) {
+				rd = atomicAdd(a.next_read + 1, 1u);
+				if (rd >= a.n_reads) { exhausted = true; break; }
+				const uint32_t o = a.off[rd];
+				len = (int)(a.off[rd + 1] - o);
+				const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * rd;
+				const uint32_t nw = ((uint32_t)len >> 5) + 2;
+#pragma unroll
+				for (uint32_t wi = 0; wi < RW; ++wi) {
+					s_rd[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.packed + w0 + wi) : 0ull;
+					s_nm[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.nmask + w0 + wi) : 0xffffffffu;
+				}
+				out = a.r3_mems + ((uint64_t)(o / kp1) + rd);
+				pool12 = a.pool + a.read_pool_off[rd]; n12 = a.read_n_mems[rd];
+				nmem = 0; x = 0; ms = me = 0; have = true;
+			}
+			while (x < len && base_at(x) > 3) ++x;
+			if (x < len) { active = true; break; }
+			a.r3_n_mems[rd] = nmem; have = false;
+		}
+		if (__all_sync(0xffffffffu, !active)) break;
+		if (!active) continue;
+
+		// ---- the chain that starts at x ----
+		bool walk = false;                                          // needs the literal walk
+		if (W >= 32 || opt.max_mem_intv < 2) walk = true;           // the shortcuts below assume a 1-row interval ends the chain
+		else if (x + W > len || (nmask_window(x) & ((1u << W) - 1u))) {
+			// an N or the read end comes before W bases: no seed; the next chain starts after the N (bwt.c:376), or nowhere
+			int i = x + 1;
+			while (i < len && base_at(i) <= 3) ++i;
+			n_ext += (uint32_t)(i - x - 1);
+			x = i < len ? i + 1 : len;
+		} else {
+			const uint32_t c19 = (__ldg(I.pt + (key_of(x, K) >> 4)) >> (2 * ((uint32_t)key_of(x, K) & 15))) & 3;
+			++n_probe;
+			if (c19 == 0) { n_ext += (uint32_t)(W - 1); x += W; }   // W does not occur: an x[2] == 0 record, discarded (bwamem.c:260)
+			else if (c19 != 1) walk = true;
+			else {
+				if (!(ms <= x && x + W <= me)) { // find a unique first-pass SMEM around W
+					ms = me = 0;
+					for (uint32_t m = 0; m < n12; ++m) {
+						const uint4 v = reinterpret_cast<const uint4*>(pool12 + m)[1];   // x[2] lo, hi, end, start
+						if (v.x == 1 && v.y == 0 && (int)v.w <= x && x + W <= (int)v.z) {
+							ms = (int)v.w; me = (int)v.z;
+							mtb = __ldg(I.sa + pool12[m].x[0]);
+							break;
+						}
+					}
+				}
+				if (me == 0) walk = true;
+				else {
+					const uint64_t P = mtb + (uint64_t)(x - ms);
+					uint64_t r0, r1; int w0, w1;
+					isa_near(P, r0, w0);
+					isa_near(I.seq_len - P - (uint64_t)W, r1, w1);
+					while (w0 | w1) {
+						if (w0) { r0 = dev_lf(I, r0); --w0; }
+						if (w1) { r1 = dev_lf(I, r1); --w1; }
+					}
+					put(r0, r1, 1, x, x + W);
+					n_ext += (uint32_t)(W - 1);
+					x += W;
+				}
+			}
+		}
+		if (!walk) continue;
+		// ---- literal walk of this chain (bwt.c:366-378), as in k_seed_r3 ----
+		{
+			uint64_t c0, c1, c2; int i;
+			if (jump >= 2 && x + jump <= len && !(nmask_window(x) & ((1u << jump) - 1u))) {
+				kt_lookup(I, (uint32_t)jump, key_of(x, jump), c0, c1, c2);
+				i = x + jump; n_ext += (uint32_t)(jump - 1);
+			} else {
+				const int b = base_at(x);
+				c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
+				i = x + 1;
+			}
+			for (;;) {
+				if (i >= len) { x = len; break; }
+				const int b = base_at(i);
+				if (b > 3) { x = i + 1; break; }
+				++n_ext;
+				if (c2 == 0) { // children of an empty interval are empty
+					if (i - x >= opt.min_seed_len) { x = i + 1; break; }
+					++i; continue;
+				}
+				uint64_t o0, o1, o2; uint32_t two;
+				dev_extend(I, c0, c1, c2, 3 - b, 0, o0, o1, o2, two); ++n_call;
+				if (o2 < (uint64_t)opt.max_mem_intv && i - x >= opt.min_seed_len) {
+					if (o2 > 0) put(o0, o1, o2, x, i + 1);
+					x = i + 1; break;
+				}
+				c0 = o0; c1 = o1; c2 = o2; ++i;
+			}
+		}
+	}
+	if (n_ext) atomicAdd(a.counters + 0, (unsigned long long)n_ext);
+	if (n_call) atomicAdd(a.counters + 1, (unsigned long long)n_call);
+	if (n_probe) atomicAdd(a.counters + 3, (unsigned long long)n_probe);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -20,6 +20,9 @@
 #ifndef CS_FAST_MINBLOCKS
 #define CS_FAST_MINBLOCKS 4
 #endif
+#ifndef CS_WALK_MAX
+#define CS_WALK_MAX 3           // short forward matches a call may have to be walked by k_seed_walk (else k_seed)
+#endif
 #define CS_FAST_SMEM_BYTES ((size_t)CS_FAST_BLOCK * (CS_READ_SMEM * 12))
 
 struct SeedArgs {
@@ -30,10 +33,12 @@ struct SeedArgs {
 	const uint64_t *packed;     // 2-bit packed reads (k_pack_reads): read r starts at word (off[r] >> 5) + 2r
 	const uint32_t *nmask;      // ambiguity / end-of-read mask, same word indexing
 	// scratch
-	uint32_t *next_read;        // work counters: [0] k_seed, [1] k_seed_r3, [2] k_seed_fast
-	// calls k_seed_fast hands to k_seed: {read, pivot | pass << 16, min_intv, previous deferred call of the same
-	// read or ~0}.  NULL: k_seed runs in read mode and takes every read.
+	uint32_t *next_read;        // work counters: [0] k_seed, [1] k_seed_r3, [2] k_seed_fast, [3] k_seed_walk
+	// calls k_seed_fast hands on: {read, pivot | pass << 16 | d << 18 | walk << 31, min_intv, previous deferred call of
+	// the same read or ~0}; walk = 1: for k_seed_walk, with the filter bits of its short matches in defer_bits[] and
+	// the length d of its longest forward match; walk = 0: for k_seed.  NULL: k_seed runs in read mode and takes every read.
 	uint4 *defer_q;
+	uint32_t *defer_bits;
 	uint32_t defer_cap;
 	uint32_t *n_defer;
 	uint32_t *read_last_q;      // [n_reads] last deferred call of each read (chain head), ~0 if none
@@ -95,6 +100,8 @@ __global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t
 __global__ void k_seed(DevIndex I, SeedArgs a);
 __global__ void k_seed_long(DevIndex I, SeedArgs a);
 __global__ void k_seed_fast(DevIndex I, SeedArgs a);
+__global__ void k_seed_walk(DevIndex I, SeedArgs a);
+__global__ void k_seed_r3_fast(DevIndex I, SeedArgs a);
 __global__ void k_seed_r3(DevIndex I, SeedArgs a);
 __global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, const uint32_t *read_last_q, const uint4 *defer_q, const uint32_t *x_n,
                              uint32_t n_reads, uint32_t *out);

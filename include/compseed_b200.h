@@ -91,9 +91,9 @@ typedef struct {
 	const uint32_t *seed_off;  /* [n_reads+1] */
 	const int64_t  *rbeg;      /* [n_seeds] SA[x0 + k*step] in the emission order of bwamem.c:386-399 */
 	cs_counters_t counters;
-	float kernel_ms[8];        /* CUDA-event durations on the slot's stream: [0] seeding (k_pack_reads + k_seed_fast + k_seed +
+	float kernel_ms[8];        /* CUDA-event durations on the slot's stream: [0] seeding (k_pack_reads + k_seed_fast + k_seed_walk + k_seed +
 	                              k_seed_r3), [1] collect, [2] SA-resolve, [3] whole slot incl. copies, [4] passes 1-2 (k_pack_reads +
-	                              k_seed_fast + k_seed), [5] k_seed_r3 alone, [6] k_pack_reads + k_seed_fast, [7] reserved */
+	                              k_seed_fast + k_seed_walk + k_seed), [5] k_seed_r3 alone, [6] k_pack_reads + k_seed_fast, [7] k_seed_walk */
 	uint64_t n_deferred;       /* bwt_smem1a calls the fast kernel handed to the literal kernel */
 } cs_result_t;
 

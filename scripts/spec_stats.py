@@ -22,7 +22,7 @@ for _ in range(2):
     ctx.run_staged(0, cs.SeedOpt())
     r = ctx.wait_device(0)
 st = ctx.debug_stats(0)
-print(f"reads {n_reads}  passes 1-2 {r.kernel_ms[4]:.2f} ms (pack + fast {r.kernel_ms[6]:.2f} ms)  r3 {r.kernel_ms[5]:.2f} ms")
+print(f"reads {n_reads}  passes 1-2 {r.kernel_ms[4]:.2f} ms (pack + fast {r.kernel_ms[6]:.2f} ms, walk {r.kernel_ms[7]:.2f} ms)  r3 {r.kernel_ms[5]:.2f} ms  collect {r.kernel_ms[1]:.2f} ms")
 print(f"  per read: ext queries {st[0]/n_reads:.1f}  FM extends (k_seed + r3) {st[1]/n_reads:.1f}  filter probes {st[3]/n_reads:.1f}")
 for k, name in enumerate(NAMES):
     print(f"  {name:36s} {int(st[4 + k]):14d}  {st[4 + k] / n_reads:9.3f} / read")

@@ -196,8 +196,8 @@ def test_result_neutral_caches_can_be_switched_off(cuda_lib, oracle_lib, monkeyp
                       # dense SA => unique-match text paths on; they must account for exactly the extends they replace
                       "text": {"CS_PRUNE_K": "0", "DENSE": "1"}, "text_isa1": {"CS_PRUNE_K": "0", "DENSE": "1", "CS_ISA_INTV": "1"},
                       "text_isa32": {"CS_KMER_TABLE_DEPTH": "0", "CS_PRUNE_K": "0", "DENSE": "1", "CS_ISA_INTV": "32"},
-                      "all_dense": {"DENSE": "1"}, "all_dense_tiny_queue": {"DENSE": "1", "CS_DEFER_CAP": "7"}, "all_dense_nofast": {"DENSE": "1", "CS_FAST": "0"}, "all_dense_k12": {"DENSE": "1", "CS_PRUNE_K": "12", "CS_KMER_TABLE_DEPTH": "9"}}.items():
-        for k in ("CS_KMER_TABLE_DEPTH", "CS_PRUNE_K", "CS_ISA_INTV", "CS_FAST", "CS_DEFER_CAP"):
+                      "all_dense": {"DENSE": "1"}, "all_dense_tiny_queue": {"DENSE": "1", "CS_DEFER_CAP": "7"}, "all_dense_nofast": {"DENSE": "1", "CS_FAST": "0"}, "all_dense_r3slow": {"DENSE": "1", "CS_R3_FAST": "0"}, "all_dense_k12": {"DENSE": "1", "CS_PRUNE_K": "12", "CS_KMER_TABLE_DEPTH": "9"}}.items():
+        for k in ("CS_KMER_TABLE_DEPTH", "CS_PRUNE_K", "CS_ISA_INTV", "CS_FAST", "CS_DEFER_CAP", "CS_R3_FAST"):
             monkeypatch.delenv(k, raising=False)
         env = dict(env)
         dense = int(env.pop("DENSE", "0"))
