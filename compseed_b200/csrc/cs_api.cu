@@ -557,7 +557,7 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		CK(cudaMallocHost(&s->h_bases, max_bases));
 		CK(cudaMallocHost(&s->h_off, ((size_t)max_reads + 1) * 4));
 		CK(cudaMallocHost(&s->h_ctrl, sizeof(Ctrl)));
-		CK(cudaMalloc(&s->d_bases, max_bases));
+		CK(cudaMalloc(&s->d_bases, max_bases + 256));   // k_pack_reads reads whole aligned words past a read's last base
 		CK(cudaMalloc(&s->d_off, ((size_t)max_reads + 1) * 4));
 		CK(cudaMalloc(&s->d_packed, ((max_bases >> 5) + 2 * (size_t)max_reads + 4) * 8));
 		CK(cudaMalloc(&s->d_nmask, ((max_bases >> 5) + 2 * (size_t)max_reads + 4) * 4));
@@ -622,7 +622,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	}
 	CK(cudaMemsetAsync(s->d_ctrl, 0, sizeof(Ctrl), s->stream));
 	CK(cudaEventRecord(s->ev[1], s->stream));
-	k_pack_reads<<<(int)std::min<uint64_t>(((uint64_t)n * 32 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, s->stream>>>(
+	k_pack_reads<<<(int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, s->stream>>>(
 		s->d_bases, s->d_off, n, s->d_packed, s->d_nmask);
 	CK(cudaGetLastError());
 	a.bases = s->d_bases; a.off = s->d_off; a.n_reads = n; a.opt = *opt;
@@ -682,7 +682,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	c.mem_off = s->d_mem_off; c.mems = s->d_mems; c.mems_cap = ctx->max_mems; c.read_n_seeds = s->d_read_n_seeds; c.seed_off = s->d_seed_off;
 	c.seed_rows = s->d_rows; c.seed_cap = ctx->max_seeds; c.error = &s->d_ctrl->error;
 	{
-		int cgrid = (int)std::min<uint64_t>(((uint64_t)n * 32 + 255) / 256, (uint64_t)idx->n_sm * 16);
+		int cgrid = (int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16);
 		k_collect_sort<<<cgrid, 256, 0, s->stream>>>(c);
 		CK(cudaGetLastError());
 		CK(cudaMemsetAsync(s->d_read_n_seeds + n, 0, 4, s->stream));

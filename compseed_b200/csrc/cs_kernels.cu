@@ -238,21 +238,41 @@ __global__ void k_pt_count(const uint64_t *W, uint64_t n, uint32_t K, uint32_t *
 	}
 }
 
-// 2-bit packing of the reads of a batch + ambiguity mask; one warp per read, one lane per 32-base word
+// 2-bit packing of the reads of a batch + ambiguity mask.  Eight lanes per read (four reads per warp), one lane
+// per 32-base word; a word is built from nine aligned 32-bit loads (the read may start at any byte), four
+// bases per SIMD step.  The byte buffer is padded so that the aligned loads past a read's end stay inside it.
 __global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t n_reads, uint64_t *packed, uint32_t *nmask)
 {
-	const uint32_t lane = threadIdx.x & 31;
-	const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += nwarps) {
+	const uint32_t sub = threadIdx.x & 7;
+	const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
+	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n_reads; r += ngroups) {
 		const uint32_t o = off[r], len = off[r + 1] - o;
 		const uint64_t w0 = (uint64_t)(o >> 5) + 2 * r;
 		const uint32_t nw = (len >> 5) + 2;
-		for (uint32_t w = lane; w < nw; w += 32) {
-			uint64_t v = 0; uint32_t m = 0;
-			for (uint32_t j = 0; j < 32; ++j) {
-				uint32_t p = (w << 5) + j;
-				uint32_t b = p < len ? bases[o + p] : 4u;
-				if (b > 3) m |= 1u << j; else v |= (uint64_t)b << (2 * j);
+		for (uint32_t w = sub; w < nw; w += 8) {
+			uint64_t v = 0; uint32_t m = 0xffffffffu;
+			const uint32_t p0 = w << 5;
+			if (p0 < len) {
+				const uint64_t addr = (uint64_t)o + p0;
+				const uint32_t *ap = reinterpret_cast<const uint32_t*>(bases + (addr & ~3ull));
+				const uint32_t sh = ((uint32_t)addr & 3) * 8;
+				uint32_t u = __ldg(ap);
+				m = 0;
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					const uint32_t un = __ldg(ap + k + 1);
+					const uint32_t x = __funnelshift_r(u, un, sh);              // bases p0+4k .. p0+4k+3, one per byte
+					u = un;
+					const uint32_t amb = __vcmpgtu4(x, 0x03030303u);            // 0xff where the code is > 3
+					uint32_t c = x & 0x03030303u & ~amb;
+					c |= c >> 6; c = (c | (c >> 12)) & 0xffu;                    // four 2-bit codes, base j at bits 2j
+					uint32_t a1 = amb & 0x01010101u;
+					a1 = (a1 | (a1 >> 7) | (a1 >> 14) | (a1 >> 21)) & 0xfu;
+					v |= (uint64_t)c << (8 * k);
+					m |= a1 << (4 * k);
+				}
+				const uint32_t valid = len - p0;                                // bases of this word inside the read
+				if (valid < 32) { v &= (1ull << (2 * valid)) - 1; m |= ~((1u << valid) - 1u); }
 			}
 			packed[w0 + w] = v; nmask[w0 + w] = m;
 		}
@@ -1511,40 +1531,41 @@ __device__ __forceinline__ uint32_t seeds_of(uint64_t x2, int32_t max_occ)
 }
 
 __global__ void k_collect_sort(CollectArgs a)
-{
-	const uint32_t lane = threadIdx.x & 31;
-	const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+{ // eight lanes per read (four reads per warp): a read has ~9 mems on ordinary data
+	const uint32_t lane = threadIdx.x & 31, sub = lane & 7;
+	const unsigned gmask = 0xffu << (lane & 24);
+	const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
 	const uint32_t kp1 = (uint32_t)a.opt.min_seed_len + 1;
-	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.n_reads; r += nwarps) {
+	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < a.n_reads; r += ngroups) {
 		const uint32_t n12 = a.read_n_mems[r];                 // passes 1-2 (k_seed_fast, or k_seed alone)
 		const uint32_t n3 = a.r3_n_mems ? a.r3_n_mems[r] : 0;  // pass 3 (k_seed_r3)
-		const uint32_t n = a.mem_off[r + 1] - a.mem_off[r];    // + the deferred calls of this read (k_seed in call mode)
+		const uint32_t n = a.mem_off[r + 1] - a.mem_off[r];    // + the deferred calls of this read (k_seed_walk, k_seed in call mode)
 		const cs_mem_t *src12 = a.pool + a.read_pool_off[r];
 		const cs_mem_t *src3 = a.r3_mems + ((uint64_t)(a.off[r] / kp1) + r);
 		cs_mem_t *dst = a.mems + a.mem_off[r];
 		uint32_t n_seeds = 0;
 		if ((uint64_t)a.mem_off[r] + n > a.mems_cap) { // result buffer too small: report, never write past it
-			if (lane == 0) { atomicExch(a.error, CS_E_OVERFLOW); a.read_n_seeds[r] = 0; }
+			if (sub == 0) { atomicExch(a.error, CS_E_OVERFLOW); a.read_n_seeds[r] = 0; }
 			continue;
 		}
 		const cs_mem_t *all = src12;                           // the read's mems, unsorted, in one place
 		if (n != n12) { // several sources: gather them into the staging copy of the output region first
 			cs_mem_t *stg = a.stage + a.mem_off[r];
 			uint32_t o = 0;
-			for (uint32_t m = lane; m < n12; m += 32) { const uint4 *p = reinterpret_cast<const uint4*>(src12 + m); uint4 *d = reinterpret_cast<uint4*>(stg + m); d[0] = p[0]; d[1] = p[1]; }
+			for (uint32_t m = sub; m < n12; m += 8) { const uint4 *p = reinterpret_cast<const uint4*>(src12 + m); uint4 *d = reinterpret_cast<uint4*>(stg + m); d[0] = p[0]; d[1] = p[1]; }
 			o = n12;
 			if (a.read_last_q)
 				for (uint32_t q = a.read_last_q[r]; q != 0xffffffffu; q = a.defer_q[q].w) {
 					const cs_mem_t *sx = a.pool + a.x_off[q];
 					const uint32_t nx = a.x_n[q];
-					for (uint32_t m = lane; m < nx; m += 32) { const uint4 *p = reinterpret_cast<const uint4*>(sx + m); uint4 *d = reinterpret_cast<uint4*>(stg + o + m); d[0] = p[0]; d[1] = p[1]; }
+					for (uint32_t m = sub; m < nx; m += 8) { const uint4 *p = reinterpret_cast<const uint4*>(sx + m); uint4 *d = reinterpret_cast<uint4*>(stg + o + m); d[0] = p[0]; d[1] = p[1]; }
 					o += nx;
 				}
-			for (uint32_t m = lane; m < n3; m += 32) { const uint4 *p = reinterpret_cast<const uint4*>(src3 + m); uint4 *d = reinterpret_cast<uint4*>(stg + o + m); d[0] = p[0]; d[1] = p[1]; }
-			__syncwarp();
+			for (uint32_t m = sub; m < n3; m += 8) { const uint4 *p = reinterpret_cast<const uint4*>(src3 + m); uint4 *d = reinterpret_cast<uint4*>(stg + o + m); d[0] = p[0]; d[1] = p[1]; }
+			__syncwarp(gmask);
 			all = stg;
 		}
-		for (uint32_t m = lane; m < n; m += 32) {
+		for (uint32_t m = sub; m < n; m += 8) {
 			const uint4 *p = reinterpret_cast<const uint4*>(all + m);
 			uint4 v0 = p[0], v1 = p[1];
 			uint64_t info = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
@@ -1557,8 +1578,8 @@ __global__ void k_collect_sort(CollectArgs a)
 			d[0] = v0; d[1] = v1;
 			n_seeds += seeds_of((uint64_t)v1.x | ((uint64_t)v1.y << 32), a.opt.max_occ);
 		}
-		for (int s = 16; s > 0; s >>= 1) n_seeds += __shfl_xor_sync(0xffffffffu, n_seeds, s);
-		if (lane == 0) a.read_n_seeds[r] = n_seeds;
+		for (int sft = 4; sft > 0; sft >>= 1) n_seeds += __shfl_xor_sync(gmask, n_seeds, sft);
+		if (sub == 0) a.read_n_seeds[r] = n_seeds;
 	}
 }
 
@@ -1575,22 +1596,22 @@ __global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, const uint
 }
 
 __global__ void k_collect_rows(CollectArgs a)
-{
-	const uint32_t lane = threadIdx.x & 31;
-	const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.n_reads; r += nwarps) {
+{ // eight lanes per read
+	const uint32_t sub = threadIdx.x & 7;
+	const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
+	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < a.n_reads; r += ngroups) {
 		const uint32_t n = a.mem_off[r + 1] - a.mem_off[r];
 		const cs_mem_t *mem = a.mems + a.mem_off[r];
 		uint64_t o = a.seed_off[r];
 		if ((uint64_t)a.seed_off[r + 1] > a.seed_cap || (uint64_t)a.mem_off[r + 1] > a.mems_cap) {
-			if (lane == 0) atomicExch(a.error, CS_E_OVERFLOW);
+			if (sub == 0) atomicExch(a.error, CS_E_OVERFLOW);
 			continue;
 		}
 		for (uint32_t m = 0; m < n; ++m) {
 			uint64_t x0 = mem[m].x[0], x2 = mem[m].x[2];
 			uint32_t cnt = seeds_of(x2, a.opt.max_occ);
 			uint64_t step = x2 > (uint64_t)a.opt.max_occ ? x2 / (uint64_t)a.opt.max_occ : 1;
-			for (uint32_t k = lane; k < cnt; k += 32) a.seed_rows[o + k] = x0 + (uint64_t)k * step;
+			for (uint32_t k = sub; k < cnt; k += 8) a.seed_rows[o + k] = x0 + (uint64_t)k * step;
 			o += cnt;
 		}
 	}
