@@ -42,6 +42,24 @@ struct DevIndex {
 	uint32_t isa_shift;
 };
 
+
+// Random single-word gathers from the big tables (filter, SA, inverse SA, text, top-of-search table).  ncu
+// shows L2 filling about four sectors per such request by default (lts__t_sectors_srcunit_tex_op_read ~ 3.7 x
+// lts__t_requests); nothing else of the 128-byte line is ever used, so the prefetch size is capped at 64 bytes,
+// the smallest PTX offers.  -DCS_L2_DEFAULT restores plain __ldg.
+#ifdef CS_L2_DEFAULT
+__device__ __forceinline__ uint32_t gather_u32(const uint32_t *p) { return __ldg(p); }
+__device__ __forceinline__ uint64_t gather_u64(const uint64_t *p) { return __ldg(p); }
+__device__ __forceinline__ uint4 gather_u128(const uint4 *p) { return __ldg(p); }
+#else
+__device__ __forceinline__ uint32_t gather_u32(const uint32_t *p)
+{ uint32_t v; asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint64_t gather_u64(const uint64_t *p)
+{ uint64_t v; asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint4 gather_u128(const uint4 *p)
+{ uint4 v; asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
+#endif
+
 struct Bucket { uint32_t w0, w1, w2, w3; uint32_t p1, p2, p3, hi; };
 
 // L2[c] for a run-time c without indexing the kernel-parameter struct dynamically (which would
@@ -271,7 +289,7 @@ __device__ __forceinline__ uint64_t dev_sa(const DevIndex &I, uint64_t k, uint32
 	uint64_t sa = 0;
 	while (k & I.sa_mask) { ++sa; k = dev_lf(I, k); }
 	steps = (uint32_t)sa;
-	return sa + __ldg(I.sa + (k >> I.sa_shift));
+	return sa + gather_u64(I.sa + (k >> I.sa_shift));
 }
 
 // ---- top-of-search table and 2-bit packed reads ----
@@ -279,7 +297,7 @@ __device__ __forceinline__ uint64_t kt_offset(uint32_t d) { return ((1ull << (2 
 
 __device__ __forceinline__ void kt_lookup(const DevIndex &I, uint32_t d, uint64_t key, uint64_t &x0, uint64_t &x1, uint64_t &x2)
 {
-	uint4 v = __ldg(I.kt + kt_offset(d) + key);
+	uint4 v = gather_u128(I.kt + kt_offset(d) + key);
 	x0 = (uint64_t)v.x | ((uint64_t)(v.w & 31) << 32);
 	x1 = (uint64_t)v.y | ((uint64_t)((v.w >> 5) & 31) << 32);
 	x2 = (uint64_t)v.z | ((uint64_t)((v.w >> 10) & 31) << 32);
@@ -306,8 +324,8 @@ __device__ __forceinline__ bool read_has_n(const uint32_t *pn, int a, int cnt)
 __device__ __forceinline__ uint64_t packed_window(const uint64_t *p, uint64_t pos)
 {
 	uint64_t w = pos >> 5; uint32_t sh = ((uint32_t)pos & 31) * 2;
-	uint64_t v = __ldg(p + w) >> sh;
-	if (sh) v |= __ldg(p + w + 1) << (64 - sh);
+	uint64_t v = gather_u64(p + w) >> sh;
+	if (sh) v |= gather_u64(p + w + 1) << (64 - sh);
 	return v;
 }
 

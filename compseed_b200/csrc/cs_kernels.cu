@@ -292,7 +292,7 @@ __global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, ui
 	if (n > cap) return;           // overflow is reported by the collect pass
 	if (I.sa_mask == 0) { // dense suffix array: one 8-byte gather per seed
 		for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-			rows_inout[i] = __ldg(I.sa + rows_inout[i]);
+			rows_inout[i] = gather_u64(I.sa + rows_inout[i]);
 		return;
 	}
 	for (;;) {
@@ -492,7 +492,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 		const uint64_t smask = (1ull << I.isa_shift) - 1;
 		uint64_t jj = (p + smask) & ~smask;
 		if (jj > I.seq_len) jj = I.seq_len;
-		row = jj == I.seq_len ? 0ull : __ldg(I.isa + (jj >> I.isa_shift));   // the '$' suffix is row 0
+		row = jj == I.seq_len ? 0ull : gather_u64(I.isa + (jj >> I.isa_shift));   // the '$' suffix is row 0
 		steps = (int)(jj - p);
 	};
 
@@ -625,7 +625,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 			bool keep = false;
 			if (lane + 1 < prune_k && ws >= 0 && !has_n(ot, opw, ws, ox - ws)) { // else it ends at the read start / an N first
 				const uint64_t key = key_of(ot, opw, ws, prune_k);
-				const uint32_t cnt = (__ldg(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3;
+				const uint32_t cnt = (gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3;
 				keep = cnt == 3 || cnt >= omin;              // 3 == "3 or more"
 				++n_probe;
 			}
@@ -659,7 +659,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 			bool fin = false;
 			STAT(3); if (st == ST_TXT_CMP) STAT(15); if (st == ST_ROW_LF) STAT(11);
 			if (st == ST_TXT_SA) {
-				tpos = __ldg(I.sa + c0) + (uint64_t)(i - x);
+				tpos = gather_u64(I.sa + c0) + (uint64_t)(i - x);
 				j = 0; st = ST_TXT_CMP;
 			} else if (st == ST_TXT_CMP) {
 				const uint64_t diff = read_window(i) ^ packed_window(I.text, tpos);
@@ -682,7 +682,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 					}
 				}
 			} else if (st == ST_BTX_SA) {
-				tpos = __ldg(I.sa + c0);
+				tpos = gather_u64(I.sa + c0);
 				j = 0; rowm = 0; st = ST_BTX_CMP;
 			} else if (st == ST_BTX_CMP) {
 				uint32_t cnt = 32, m = 0;
@@ -707,7 +707,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 						ok = false; STAT(10);
 						if (x + dlow - bi >= prune_k && !has_n(t, pw, bi, prune_k)) {
 							const uint64_t key = key_of(t, pw, bi, prune_k);
-							ok = ((__ldg(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) == 0;
+							ok = ((gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) == 0;
 							++n_probe;
 #ifdef CS_STATS
 							--sst[10]; if (!ok) STAT(9);
@@ -810,6 +810,34 @@ __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed(DevIn
 // reads longer than 32 * CS_READ_SMEM bases: the packed read stays in global memory
 __global__ void __launch_bounds__(CS_SEED_BLOCK, CS_SEED_MINBLOCKS) k_seed_long(DevIndex I, SeedArgs a) { seed_body<0>(I, a); }
 
+// Warp-aggregated work distribution: the lanes of `want` get consecutive values of *ctr with ONE atomic per
+// warp (the counters of a batch share a sector; one atomic per lane serialises in a single L2 slice).
+// Must be called by all 32 lanes.
+__device__ __forceinline__ uint32_t warp_take(uint32_t *ctr, bool want)
+{
+	const unsigned m = __ballot_sync(0xffffffffu, want);
+	if (!m) return 0;
+	const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+	uint32_t base = 0;
+	if (lane == leader) base = atomicAdd(ctr, (uint32_t)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+// ... and `cnt` consecutive slots each (cnt = 0 for lanes that want none): exclusive warp scan + one atomic
+__device__ __forceinline__ unsigned long long warp_alloc(unsigned long long *ctr, uint32_t cnt)
+{
+	const int lane = threadIdx.x & 31;
+	uint32_t incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+	const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+	unsigned long long base = 0;
+	if (total == 0) return 0;
+	if (lane == 31) base = atomicAdd(ctr, (unsigned long long)total);
+	base = __shfl_sync(0xffffffffu, base, 31);
+	return base + (incl - cnt);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fast seeding kernel (passes 1 and 2 for reads whose every bwt_smem1a call is "simple").
 //
@@ -875,76 +903,95 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 	};
 	auto key_of = [&](int pos, int cnt) -> uint64_t { return read_window(pos) & ((1ull << (2 * cnt)) - 1); };   // cnt < 32
 	auto has_n = [&](int pos, int cnt) -> bool { return (nmask_window(pos) & ((1u << cnt) - 1u)) != 0; };       // cnt < 32
-	auto pt_count = [&](uint64_t key) -> uint32_t { return (__ldg(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3; };
+	auto pt_count = [&](uint64_t key) -> uint32_t { return (gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3; };
 	auto isa_near = [&](uint64_t p, uint64_t &row, int &steps) {
 		const uint64_t smask = (1ull << I.isa_shift) - 1;
 		uint64_t jj = (p + smask) & ~smask;
 		if (jj > I.seq_len) jj = I.seq_len;
-		row = jj == I.seq_len ? 0ull : __ldg(I.isa + (jj >> I.isa_shift));
+		row = jj == I.seq_len ? 0ull : gather_u64(I.isa + (jj >> I.isa_shift));
 		steps = (int)(jj - p);
 	};
-	// hand the call (pivot, min_intv) of the read in flight to the literal kernel
+	// hand the call (pivot, min_intv) of the read in flight to the literal kernel; the queue slot is taken at the top
+	// of the next iteration, for the whole warp at once
+	uint32_t pend_y = 0, pend_z = 0, pend_bits = 0;           // pend_y != 0: a call waits to be queued
 	auto defer_call = [&](int pivot, uint64_t mi) {
-		const uint32_t q = atomicAdd(a.n_defer, 1u);
-		// (past the capacity nothing is stored: the host sees n_defer > defer_cap and reruns the batch through k_seed alone)
-		if (q < a.defer_cap) { a.defer_q[q] = make_uint4(rd, (uint32_t)pivot | ((uint32_t)round << 16), (uint32_t)mi, last_q); last_q = q; }
+		pend_y = (uint32_t)pivot | ((uint32_t)round << 16); pend_z = (uint32_t)mi;
 	};
 	// ... or, when its list can only hold the few short matches `bits` (depth of the longest forward match: d), to k_seed_walk
 	auto defer_walk = [&](int pivot, uint64_t mi, int d, uint32_t bits) {
-		const uint32_t q = atomicAdd(a.n_defer, 1u);
-		if (q < a.defer_cap) {
-			a.defer_q[q] = make_uint4(rd, (uint32_t)pivot | ((uint32_t)round << 16) | ((uint32_t)d << 18) | 0x80000000u, (uint32_t)mi, last_q);
-			a.defer_bits[q] = bits; last_q = q;
-		}
+		pend_y = (uint32_t)pivot | ((uint32_t)round << 16) | ((uint32_t)d << 18) | 0x80000000u; pend_z = (uint32_t)mi; pend_bits = bits;
 	};
 
 	for (;;) {
-		// ---- pick this lane's next call: (cx, cmin) ----
-		bool active = false; int cx = 0; uint64_t cmin = 1;
-		while (!exhausted) {
-			if (!have) {
-				rd = atomicAdd(a.next_read + 2, 1u);
-				if (rd >= a.n_reads) { exhausted = true; break; }
-				const uint32_t o = a.off[rd];
-				len = (int)(a.off[rd + 1] - o);
-				const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * rd;
-				const uint32_t nw = ((uint32_t)len >> 5) + 2;
-#pragma unroll
-				for (uint32_t wi = 0; wi < RW; ++wi) {
-					s_rd[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.packed + w0 + wi) : 0ull;
-					s_nm[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.nmask + w0 + wi) : 0xffffffffu;
+		// ---- queue the calls deferred in the previous iteration (one atomic per warp) ----
+		{
+			const uint32_t q = warp_take(a.n_defer, pend_y != 0);
+			if (pend_y != 0) {
+				// (past the capacity nothing is stored: the host sees n_defer > defer_cap and reruns the batch through k_seed alone)
+				if (q < a.defer_cap) {
+					a.defer_q[q] = make_uint4(rd, pend_y, pend_z, last_q);
+					if (pend_y >> 31) a.defer_bits[q] = pend_bits;
+					last_q = q;
 				}
-				nmem = 0; round = 1; x = 0; have = true; last_q = 0xffffffffu;
+				pend_y = 0;
 			}
-			{
+		}
+		// ---- pick this lane's next call: (cx, cmin).  Reads are handed out, and finished reads get their place in
+		//      the pool, for the whole warp at once. ----
+		bool active = false; int cx = 0; uint64_t cmin = 1;
+		for (;;) {
+			const bool want = !exhausted && !have;
+			const uint32_t take = warp_take(a.next_read + 2, want);
+			if (want) {
+				rd = take;
+				if (rd >= a.n_reads) exhausted = true;
+				else {
+					const uint32_t o = a.off[rd];
+					len = (int)(a.off[rd + 1] - o);
+					const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * rd;
+					const uint32_t nw = ((uint32_t)len >> 5) + 2;
+#pragma unroll
+					for (uint32_t wi = 0; wi < RW; ++wi) {
+						s_rd[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.packed + w0 + wi) : 0ull;
+						s_nm[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.nmask + w0 + wi) : 0xffffffffu;
+					}
+					nmem = 0; round = 1; x = 0; have = true; last_q = 0xffffffffu;
+				}
+			}
+			bool finished = false;
+			if (have && !active) {
 				if (round == 1) { // first pass of mem_collect_intv, bwamem.c:226-236
 					while (x < len && base_at(x) > 3) ++x;
-					if (x < len) { cx = x; cmin = 1; active = true; break; }
-					old_n = nmem; r2k = 0; round = 2;
+					if (x < len) { cx = x; cmin = 1; active = true; }
+					else { old_n = nmem; r2k = 0; round = 2; }
 				}
-				while (r2k < old_n) { // second pass, bwamem.c:238-249
-					const uint4 v = reinterpret_cast<const uint4*>(my + r2k)[1];
-					++r2k;
-					const int s = (int)v.w, e = (int)v.z;
-					const uint64_t sz = (uint64_t)v.x | ((uint64_t)v.y << 32);
-					if (e - s < opt.split_len || sz > (uint64_t)opt.split_width) continue;
-					cx = (s + e) >> 1; cmin = sz + 1; active = true;
-					break;
+				if (!active) {
+					while (r2k < old_n) { // second pass, bwamem.c:238-249
+						const uint4 v = reinterpret_cast<const uint4*>(my + r2k)[1];
+						++r2k;
+						const int s = (int)v.w, e = (int)v.z;
+						const uint64_t sz = (uint64_t)v.x | ((uint64_t)v.y << 32);
+						if (e - s < opt.split_len || sz > (uint64_t)opt.split_width) continue;
+						cx = (s + e) >> 1; cmin = sz + 1; active = true;
+						break;
+					}
+					finished = !active;
 				}
-				if (active) break;
 			}
-			// the read is finished
-			{
-				uint32_t cnt = nmem;
-				unsigned long long o = atomicAdd(a.pool_used, (unsigned long long)cnt);
-				if (o + cnt > a.pool_cap) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
-				a.read_pool_off[rd] = o; a.read_n_mems[rd] = cnt;
-				const uint4 *src = reinterpret_cast<const uint4*>(my);
-				uint4 *dst = reinterpret_cast<uint4*>(a.pool + o);
-				for (uint32_t m = 0; m < 2 * cnt; ++m) dst[m] = src[m];
-				a.read_last_q[rd] = last_q;
+			{ // the finished reads
+				uint32_t cnt = finished ? nmem : 0;
+				const unsigned long long o = warp_alloc(a.pool_used, cnt);
+				if (finished) {
+					if (o + cnt > a.pool_cap) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
+					a.read_pool_off[rd] = o; a.read_n_mems[rd] = cnt;
+					const uint4 *src = reinterpret_cast<const uint4*>(my);
+					uint4 *dst = reinterpret_cast<uint4*>(a.pool + o);
+					for (uint32_t m = 0; m < 2 * cnt; ++m) dst[m] = src[m];
+					a.read_last_q[rd] = last_q;
+					have = false;
+				}
 			}
-			have = false;
+			if (!__any_sync(0xffffffffu, finished && !exhausted)) break;   // nobody is waiting for another read
 		}
 		if (__all_sync(0xffffffffu, !active)) break;
 		if ((t & 31) == 0) STAT(0);
@@ -1009,7 +1056,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		// unique from here on: compare against the text at the occurrence, 32 bases per step
 		uint64_t tp0 = 0; int jf = 0;
 		if (unique) {
-			tp0 = __ldg(I.sa + c0);                                 // text position of q[cx]
+			tp0 = gather_u64(I.sa + c0);                                 // text position of q[cx]
 			uint64_t tpos = tp0 + (uint64_t)(i - cx);
 			for (;;) {
 				const uint64_t diff = read_window(i) ^ packed_window(I.text, tpos);
@@ -1060,7 +1107,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		if (bad) { defer_call(cx, cmin); continue; }
 		uint64_t tb = tp0;                                          // text position of q[bi+1]
 		if (!failed) {
-			if (!unique) tb = __ldg(I.sa + c0);
+			if (!unique) tb = gather_u64(I.sa + c0);
 			for (;;) {
 				uint32_t cnt = 32, m = 0;
 				if ((uint32_t)(bi + 1) < cnt) cnt = (uint32_t)(bi + 1);
@@ -1175,20 +1222,23 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 		// ---- next walk task of the queue (tasks of the literal kernel are skipped) ----
 		uint32_t q = 0; uint4 item = make_uint4(0, 0, 0, 0);
 		bool active = false;
-		while (!exhausted) {
-			q = atomicAdd(a.next_read + 3, 1u);
-			const uint32_t nq = *reinterpret_cast<volatile uint32_t*>(a.n_defer);
-			if (q >= (nq < a.defer_cap ? nq : a.defer_cap)) { exhausted = true; break; }
-			item = a.defer_q[q];
-			if (item.y >> 31) { active = true; break; }
+		for (;;) { // queue slots for the whole warp at once; lanes that drew a task of the literal kernel draw again
+			const bool want = !exhausted && !active;
+			const uint32_t take = warp_take(a.next_read + 3, want);
+			if (want) {
+				const uint32_t nq = *reinterpret_cast<volatile uint32_t*>(a.n_defer);
+				q = take;
+				if (q >= (nq < a.defer_cap ? nq : a.defer_cap)) exhausted = true;
+				else { item = a.defer_q[q]; active = (item.y >> 31) != 0; }
+			}
+			if (!__any_sync(0xffffffffu, !exhausted && !active)) break;
 		}
 		if (__all_sync(0xffffffffu, !active)) break;
-		if (!active) continue;
 		const uint32_t rd = item.x;
 		const int cx = (int)(item.y & 0xffff), round = (int)((item.y >> 16) & 3), d = (int)((item.y >> 18) & 31);
 		const uint64_t cmin = item.z;
-		uint32_t bits = a.defer_bits[q];
-		{
+		uint32_t bits = active ? a.defer_bits[q] : 0u;
+		if (active) {
 			const uint32_t o = a.off[rd];
 			const int len = (int)(a.off[rd + 1] - o);
 			const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * rd;
@@ -1245,10 +1295,11 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 				}
 			}
 		}
-		if (punt) { a.defer_q[q].y = item.y & 0x7fffffffu; continue; }   // the literal kernel takes it (it runs after this one)
-		n_ext += t_ext; n_call += t_call;
+		if (punt) a.defer_q[q].y = item.y & 0x7fffffffu;            // the literal kernel takes it (it runs after this one)
+		const bool fin = active && !punt;
+		if (fin) { n_ext += t_ext; n_call += t_call; }
 		// second-pass calls of what a first-pass call found (bwamem.c:238-249): ordinary calls for the literal kernel
-		if (round == 1)
+		if (fin && round == 1)
 			for (uint32_t m = 0; m < nm; ++m) {
 				const uint4 v = reinterpret_cast<const uint4*>(my + m)[1];
 				const int s = (int)v.w, e = (int)v.z;
@@ -1258,13 +1309,15 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 				if (q2 < a.defer_cap) a.defer_q[q2] = make_uint4(rd, (uint32_t)((s + e) >> 1) | (2u << 16), (uint32_t)(sz + 1), atomicExch(a.read_last_q + rd, q2));
 			}
 		{
-			uint32_t cnt = nm;
-			unsigned long long o = atomicAdd(a.pool_used, (unsigned long long)cnt);
-			if (o + cnt > a.pool_cap) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
-			a.x_off[q] = o; a.x_n[q] = cnt;
-			const uint4 *src = reinterpret_cast<const uint4*>(my);
-			uint4 *dst = reinterpret_cast<uint4*>(a.pool + o);
-			for (uint32_t m = 0; m < 2 * cnt; ++m) dst[m] = src[m];
+			uint32_t cnt = fin ? nm : 0;
+			const unsigned long long o = warp_alloc(a.pool_used, cnt);
+			if (fin) {
+				if (o + cnt > a.pool_cap) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
+				a.x_off[q] = o; a.x_n[q] = cnt;
+				const uint4 *src = reinterpret_cast<const uint4*>(my);
+				uint4 *dst = reinterpret_cast<uint4*>(a.pool + o);
+				for (uint32_t m = 0; m < 2 * cnt; ++m) dst[m] = src[m];
+			}
 		}
 	}
 	if (n_ext) atomicAdd(a.counters + 0, (unsigned long long)n_ext);
@@ -1405,7 +1458,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 		const uint64_t smask = (1ull << I.isa_shift) - 1;
 		uint64_t jj = (p + smask) & ~smask;
 		if (jj > I.seq_len) jj = I.seq_len;
-		row = jj == I.seq_len ? 0ull : __ldg(I.isa + (jj >> I.isa_shift));
+		row = jj == I.seq_len ? 0ull : gather_u64(I.isa + (jj >> I.isa_shift));
 		steps = (int)(jj - p);
 	};
 	auto put = [&](uint64_t x0, uint64_t x1, uint64_t x2, int start, int end) {
@@ -1418,26 +1471,34 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 	for (;;) {
 		// ---- this lane's next chain start x (bwamem.c:253-268) ----
 		bool active = false;
-		while (!exhausted) {
-			if (!have) {
-				rd = atomicAdd(a.next_read + 1, 1u);
-				if (rd >= a.n_reads) { exhausted = true; break; }
-				const uint32_t o = a.off[rd];
-				len = (int)(a.off[rd + 1] - o);
-				const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * rd;
-				const uint32_t nw = ((uint32_t)len >> 5) + 2;
+		for (;;) { // reads are handed out for the whole warp at once
+			const bool want = !exhausted && !have;
+			const uint32_t take = warp_take(a.next_read + 1, want);
+			if (want) {
+				rd = take;
+				if (rd >= a.n_reads) exhausted = true;
+				else {
+					const uint32_t o = a.off[rd];
+					len = (int)(a.off[rd + 1] - o);
+					const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * rd;
+					const uint32_t nw = ((uint32_t)len >> 5) + 2;
 #pragma unroll
-				for (uint32_t wi = 0; wi < RW; ++wi) {
-					s_rd[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.packed + w0 + wi) : 0ull;
-					s_nm[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.nmask + w0 + wi) : 0xffffffffu;
+					for (uint32_t wi = 0; wi < RW; ++wi) {
+						s_rd[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.packed + w0 + wi) : 0ull;
+						s_nm[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.nmask + w0 + wi) : 0xffffffffu;
+					}
+					out = a.r3_mems + ((uint64_t)(o / kp1) + rd);
+					pool12 = a.pool + a.read_pool_off[rd]; n12 = a.read_n_mems[rd];
+					nmem = 0; x = 0; ms = me = 0; have = true;
 				}
-				out = a.r3_mems + ((uint64_t)(o / kp1) + rd);
-				pool12 = a.pool + a.read_pool_off[rd]; n12 = a.read_n_mems[rd];
-				nmem = 0; x = 0; ms = me = 0; have = true;
 			}
-			while (x < len && base_at(x) > 3) ++x;
-			if (x < len) { active = true; break; }
-			a.r3_n_mems[rd] = nmem; have = false;
+			bool finished = false;
+			if (have && !active) {
+				while (x < len && base_at(x) > 3) ++x;
+				if (x < len) active = true;
+				else { a.r3_n_mems[rd] = nmem; have = false; finished = true; }
+			}
+			if (!__any_sync(0xffffffffu, finished && !exhausted)) break;
 		}
 		if (__all_sync(0xffffffffu, !active)) break;
 		if (!active) continue;
@@ -1452,7 +1513,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 			n_ext += (uint32_t)(i - x - 1);
 			x = i < len ? i + 1 : len;
 		} else {
-			const uint32_t c19 = (__ldg(I.pt + (key_of(x, K) >> 4)) >> (2 * ((uint32_t)key_of(x, K) & 15))) & 3;
+			const uint32_t c19 = (gather_u32(I.pt + (key_of(x, K) >> 4)) >> (2 * ((uint32_t)key_of(x, K) & 15))) & 3;
 			++n_probe;
 			if (c19 == 0) { n_ext += (uint32_t)(W - 1); x += W; }   // W does not occur: an x[2] == 0 record, discarded (bwamem.c:260)
 			else if (c19 != 1) walk = true;
@@ -1463,7 +1524,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 						const uint4 v = reinterpret_cast<const uint4*>(pool12 + m)[1];   // x[2] lo, hi, end, start
 						if (v.x == 1 && v.y == 0 && (int)v.w <= x && x + W <= (int)v.z) {
 							ms = (int)v.w; me = (int)v.z;
-							mtb = __ldg(I.sa + pool12[m].x[0]);
+							mtb = gather_u64(I.sa + pool12[m].x[0]);
 							break;
 						}
 					}
