@@ -424,7 +424,7 @@ fail:
 struct Ctrl { // zeroed before every run; copied back after it
 	uint32_t next_read[4];   // work counters: [0] k_seed, [1] k_seed_r3, [2] k_seed_fast, [3] k_seed_walk
 	uint32_t n_defer;        // calls handed on by k_seed_fast (and k_seed_walk)
-	uint32_t pad0;
+	uint32_t n_lit;          // of those, for k_seed
 	unsigned long long pool_used;
 	unsigned long long counters[4 + 32];   // [4..19] k_seed, [20..35] k_seed_fast: event counters of a -DCS_STATS diagnostics build, else 0
 	unsigned long long sa_work, lf_steps;
@@ -444,7 +444,7 @@ struct Slot {
 	uint8_t *d_bases; uint32_t *d_off;
 	uint64_t *d_packed; uint32_t *d_nmask;   // 2-bit packed reads + ambiguity mask (k_pack_reads)
 	uint4 *d_defer_q;                         // calls the fast kernel hands to the literal kernel (SeedArgs::defer_q)
-	uint32_t *d_read_last_q, *d_x_n, *d_defer_bits; uint64_t *d_x_off;
+	uint32_t *d_read_last_q, *d_x_n, *d_defer_bits, *d_lit_q; uint64_t *d_x_off;
 	cs_mem_t *d_stage;                        // collect: a read's sources gathered before the sort
 	bool used_fast;
 	Ctrl *d_ctrl;
@@ -481,7 +481,7 @@ static void slot_free(Slot *s)
 	if (s->ev_done) cudaEventDestroy(s->ev_done);
 	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
 	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
-	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_defer_bits); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
+	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_defer_bits); cudaFree(s->d_lit_q); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
 	cudaFree(s->d_pool); cudaFree(s->d_mems); cudaFree(s->d_read_pool_off); cudaFree(s->d_read_n_mems);
 	cudaFree(s->d_r3_mems); cudaFree(s->d_r3_n_mems); cudaFree(s->d_tot_n_mems);
 	cudaFree(s->d_mem_off); cudaFree(s->d_read_n_seeds); cudaFree(s->d_seed_off); cudaFree(s->d_rows); cudaFree(s->d_scan_tmp);
@@ -566,6 +566,7 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		CK(cudaMalloc(&s->d_x_off, (size_t)ctx->defer_cap * 8));
 		CK(cudaMalloc(&s->d_x_n, (size_t)ctx->defer_cap * 4));
 		CK(cudaMalloc(&s->d_defer_bits, (size_t)ctx->defer_cap * 4));
+		CK(cudaMalloc(&s->d_lit_q, (size_t)ctx->defer_cap * 4));
 		CK(cudaMalloc(&s->d_read_last_q, ((size_t)max_reads + 1) * 4));
 		CK(cudaMalloc(&s->d_stage, ctx->max_mems * sizeof(cs_mem_t)));
 		CK(cudaMalloc(&s->d_thread_mems, nthreads * ctx->mem_cap * sizeof(cs_mem_t)));
@@ -629,7 +630,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	a.packed = s->d_packed; a.nmask = s->d_nmask;
 	a.next_read = s->d_ctrl->next_read;
 	a.defer_q = nullptr; a.defer_cap = ctx->defer_cap; a.n_defer = &s->d_ctrl->n_defer;
-	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n; a.defer_bits = s->d_defer_bits;
+	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n; a.defer_bits = s->d_defer_bits; a.lit_q = s->d_lit_q; a.n_lit = &s->d_ctrl->n_lit;
 	s->used_fast = false;
 	a.thread_mems = s->d_thread_mems; a.mem_cap = ctx->mem_cap;
 	a.spill = s->d_spill; a.spill_cap = ctx->spill_cap;
@@ -654,6 +655,11 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 		CK(cudaEventRecord(s->ev[7], s->stream));
 	}
 	// (the spill stride inside k_seed follows the launched grid), then pass 3
+	if (s->used_fast) { // call mode: few, long tasks -- fewer resident warps make each trip of the state machine faster
+		const char *env = getenv("CS_LIT_CTAS_PER_SM");
+		const int per_sm = env ? atoi(env) : 0;
+		if (per_sm > 0) grid = std::min<int>(grid, idx->n_sm * per_sm);
+	}
 	if (ctx->max_read_len + 32 <= 32 * CS_READ_SMEM) k_seed<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
 	else k_seed_long<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
 	CK(cudaGetLastError());

@@ -513,10 +513,8 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				rd = atomicAdd(a.next_read, 1u);
 				uint4 item = make_uint4(0, 0, 0, 0);
 				if (a.defer_q) { // call mode: only the calls k_seed_fast handed over
-					const uint32_t nq = *a.n_defer;
-					if (rd >= (nq < a.defer_cap ? nq : a.defer_cap)) { st = ST_IDLE; break; }
-					cur_q = rd; item = a.defer_q[rd]; rd = item.x;
-					if (item.y >> 31) break;                            // done by k_seed_walk: fetch again
+					if (rd >= *a.n_lit) { st = ST_IDLE; break; }
+					cur_q = a.lit_q[rd]; item = a.defer_q[cur_q]; rd = item.x;
 				} else if (rd >= a.n_reads) { st = ST_IDLE; break; }
 				uint32_t o = a.off[rd];
 				len = (int)(a.off[rd + 1] - o);
@@ -933,8 +931,12 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 					if (pend_y >> 31) a.defer_bits[q] = pend_bits;
 					last_q = q;
 				}
-				pend_y = 0;
 			}
+			// the calls for the literal kernel are also listed on their own, so that it does not scan the walk tasks
+			const bool lit = pend_y != 0 && !(pend_y >> 31) && q < a.defer_cap;
+			const uint32_t li = warp_take(a.n_lit, lit);
+			if (lit) a.lit_q[li] = q;
+			pend_y = 0;
 		}
 		// ---- pick this lane's next call: (cx, cmin).  Reads are handed out, and finished reads get their place in
 		//      the pool, for the whole warp at once. ----
@@ -1127,21 +1129,19 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		}
 		const bool ext_fails = bi >= 0 && base_at(bi) <= 3;         // bwt.c:330: no bwt_extend at the read start / an N
 		if (!failed) r_ext += (uint32_t)jb + (ext_fails ? 1u : 0u);
-		if (ext_fails) { // could a shorter match survive position bi?  They all start with q[bi, bi+K) there ...
-			int dlow;                                               // ... if none of them is shorter than K - (cx - bi) bases
-			if (d < K) dlow = __ffs((int)kmask);
-			else {
-				const int need_d = K - (cx - bi);
-				const uint32_t m = need_d > 1 ? probe_bits(1, need_d - 1) : 0u;
-				dlow = m ? __ffs((int)m) : (need_d > 1 ? need_d : 1);
-			}
+		uint32_t shallow = 0;                                       // pushed matches too short to contain q[bi, bi+K): walked one by one
+		if (ext_fails) { // could a shorter match survive position bi?  Those of >= K - (cx - bi) bases all start with q[bi, bi+K) there
+			const int need_d = K - (cx - bi);
+			if (need_d > 1) shallow = (d < K ? kmask : probe_bits(1, need_d - 1)) & ((1u << (need_d - 1)) - 1u);
 			bool ok = false;
-			if (cx + dlow - bi >= K && !has_n(bi, K)) { ok = pt_count(key_of(bi, K)) == 0; ++n_probe; if (!ok) STAT(8); }
+			if (__popc(shallow) <= CS_WALK_MAX && !has_n(bi, K)) { ok = pt_count(key_of(bi, K)) == 0; ++n_probe; if (!ok) STAT(8); }
 			else STAT(9);
 			if (!ok) { defer_call(cx, cmin); continue; }
 		}
 		STAT(10);
 		if (end - (bi + 1) >= opt.min_seed_len && nmem >= a.mem_cap) { defer_call(cx, cmin); continue; }   // scratch full: the literal kernel stores it
+		// the shallow ones come after L in the sweep order: k_seed_walk starts its containment test from L's start
+		if (shallow) defer_walk(cx, cmin, d < 31 ? d : 31, shallow | ((uint32_t)(bi + 2) << 18));
 		n_ext += r_ext; n_call += r_call;
 		if (end - (bi + 1) < opt.min_seed_len) continue;            // bwamem.c:231-233,247
 		STAT(11);
@@ -1238,6 +1238,8 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 		const int cx = (int)(item.y & 0xffff), round = (int)((item.y >> 16) & 3), d = (int)((item.y >> 18) & 31);
 		const uint64_t cmin = item.z;
 		uint32_t bits = active ? a.defer_bits[q] : 0u;
+		const int ls0 = (int)(bits >> 18);                          // 1 + start of the SMEM k_seed_fast already found for this call (0: none)
+		bits &= 0x3ffffu;
 		if (active) {
 			const uint32_t o = a.off[rd];
 			const int len = (int)(a.off[rd + 1] - o);
@@ -1250,8 +1252,8 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 			}
 		}
 		uint32_t nm = 0, t_ext = 0, t_call = 0;
-		bool first = true, punt = false;
-		int last_start = 0;
+		bool first = ls0 == 0, punt = false;
+		int last_start = ls0 - 1;
 		while (bits && !punt) { // entries, longest first
 			const int e = 32 - __clz((int)bits);
 			bits &= ~(1u << (e - 1));
@@ -1274,7 +1276,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 			for (int steps = 0; ; ++steps) {
 				const int b = bi >= 0 ? base_at(bi) : 4;
 				if (b > 3) break;                                   // read start / N: no bwt_extend (bwt.c:330)
-				if (steps >= CS_WALK_STEPS) { punt = true; break; }
+				if (steps >= CS_WALK_STEPS && ls0 == 0) { punt = true; break; }   // (a task that follows an SMEM of k_seed_fast is finished here)
 				const int new_len = cx + e - bi;
 				uint64_t o0, o1, o2;
 				++t_ext;
@@ -1295,7 +1297,10 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 				}
 			}
 		}
-		if (punt) a.defer_q[q].y = item.y & 0x7fffffffu;            // the literal kernel takes it (it runs after this one)
+		if (punt) { // the literal kernel takes it (it runs after this one)
+			a.defer_q[q].y = item.y & 0x7fffffffu;
+			a.lit_q[atomicAdd(a.n_lit, 1u)] = q;
+		}
 		const bool fin = active && !punt;
 		if (fin) { n_ext += t_ext; n_call += t_call; }
 		// second-pass calls of what a first-pass call found (bwamem.c:238-249): ordinary calls for the literal kernel
@@ -1306,7 +1311,10 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 				const uint64_t sz = (uint64_t)v.x | ((uint64_t)v.y << 32);
 				if (e - s < opt.split_len || sz > (uint64_t)opt.split_width) continue;
 				const uint32_t q2 = atomicAdd(a.n_defer, 1u);
-				if (q2 < a.defer_cap) a.defer_q[q2] = make_uint4(rd, (uint32_t)((s + e) >> 1) | (2u << 16), (uint32_t)(sz + 1), atomicExch(a.read_last_q + rd, q2));
+				if (q2 < a.defer_cap) {
+					a.defer_q[q2] = make_uint4(rd, (uint32_t)((s + e) >> 1) | (2u << 16), (uint32_t)(sz + 1), atomicExch(a.read_last_q + rd, q2));
+					a.lit_q[atomicAdd(a.n_lit, 1u)] = q2;
+				}
 			}
 		{
 			uint32_t cnt = fin ? nm : 0;

@@ -39,6 +39,7 @@ struct SeedArgs {
 	// the length d of its longest forward match; walk = 0: for k_seed.  NULL: k_seed runs in read mode and takes every read.
 	uint4 *defer_q;
 	uint32_t *defer_bits;
+	uint32_t *lit_q, *n_lit;    // the walk = 0 entries of defer_q (indices), listed for k_seed
 	uint32_t defer_cap;
 	uint32_t *n_defer;
 	uint32_t *read_last_q;      // [n_reads] last deferred call of each read (chain head), ~0 if none
