@@ -1056,9 +1056,12 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			c0 = o0; c1 = o1; c2 = o2; ++i;
 		}
 		// unique from here on: compare against the text at the occurrence, 32 bases per step
-		uint64_t tp0 = 0; int jf = 0;
+		uint64_t tp0 = 0, bw0 = 0; int jf = 0; uint32_t cnt0 = 0;
 		if (unique) {
 			tp0 = gather_u64(I.sa + c0);                                 // text position of q[cx]
+			// the text before the occurrence is wanted by the backward pass below: fetch its first window together with the forward one
+			cnt0 = 32; if ((uint32_t)cx < cnt0) cnt0 = (uint32_t)cx; if (tp0 < cnt0) cnt0 = (uint32_t)tp0;
+			if (cnt0) bw0 = packed_window(I.text, tp0 - cnt0);
 			uint64_t tpos = tp0 + (uint64_t)(i - cx);
 			for (;;) {
 				const uint64_t diff = read_window(i) ^ packed_window(I.text, tpos);
@@ -1088,47 +1091,35 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			else defer_call(cx, cmin);
 			continue;
 		}
-		if (!unique) STAT(6);
-
-		// ---- backward: follow L alone to the position where it fails.  While L still has several occurrences
-		//      (a short L: the next mismatch came before the match was unique) the sweep is a literal
-		//      bwt_extend of L's interval; once one occurrence is left it is a comparison against the text. ----
-		int bi = cx - 1, jb = 0;
-		bool failed = false, bad = false;                           // failed: the sweep at bi already failed inside the FM loop
-		for (int steps = 0; c2 > 1; ++steps) {
-			const int b = bi >= 0 ? base_at(bi) : 4;
-			if (b > 3 || steps >= 64) { failed = true; bad = steps >= 64; if (bad) STAT(7); break; }   // read start / N (a long repeat goes to the literal kernel)
-			const int new_len = end - bi;
-			uint64_t o0, o1, o2;
-			++r_ext;
-			if (new_len <= kd) kt_lookup(I, (uint32_t)new_len, key_of(bi, new_len), o0, o1, o2);
-			else { uint32_t two; dev_extend(I, c0, c1, c2, b, 1, o0, o1, o2, two); ++r_call; n_two += two; }
-			if (o2 < 1) { failed = true; break; }                   // bwt.c:331: L ends here
-			c0 = o0; c1 = o1; c2 = o2; --bi;
+		if (!unique) { // a short L that still has several occurrences (the next mismatch came before the match was unique): its
+			STAT(6);    // backward sweeps are bwt_extend steps like those of any other short match -- k_seed_walk does them
+			if (d < K) { defer_walk(cx, cmin, d, kmask); pend_y |= 1u << 23; }   // bit 23: L first, then the K-mer probe decides about the rest
+			else defer_call(cx, cmin);
+			continue;
 		}
-		if (bad) { defer_call(cx, cmin); continue; }
+
+		// ---- backward: follow L alone (one occurrence, text position tp0) to the position where it fails ----
+		int bi = cx - 1, jb = 0;
 		uint64_t tb = tp0;                                          // text position of q[bi+1]
-		if (!failed) {
-			if (!unique) tb = gather_u64(I.sa + c0);
-			for (;;) {
-				uint32_t cnt = 32, m = 0;
-				if ((uint32_t)(bi + 1) < cnt) cnt = (uint32_t)(bi + 1);
-				if (tb < cnt) cnt = (uint32_t)tb;
-				if (cnt) {
-					const int sr = bi + 1 - (int)cnt;
-					const uint64_t diff = (read_window(sr) ^ packed_window(I.text, tb - cnt)) << (2 * (32 - cnt));
-					const uint32_t nmw = nmask_window(sr) << (32 - cnt);
-					m = diff ? (uint32_t)__clzll((long long)diff) >> 1 : 32u;
-					const uint32_t nn = nmw ? (uint32_t)__clz((int)nmw) : 32u;
-					if (nn < m) m = nn;
-					if (cnt < m) m = cnt;
-				}
-				bi -= (int)m; tb -= m; jb += (int)m;
-				if (m < 32) break;
+		for (bool first_w = true; ; first_w = false) {
+			uint32_t cnt = 32, m = 0;
+			if ((uint32_t)(bi + 1) < cnt) cnt = (uint32_t)(bi + 1);
+			if (tb < cnt) cnt = (uint32_t)tb;
+			if (cnt) {
+				const int sr = bi + 1 - (int)cnt;
+				const uint64_t tw = first_w ? bw0 : packed_window(I.text, tb - cnt);   // (first window: cnt == cnt0)
+				const uint64_t diff = (read_window(sr) ^ tw) << (2 * (32 - cnt));
+				const uint32_t nmw = nmask_window(sr) << (32 - cnt);
+				m = diff ? (uint32_t)__clzll((long long)diff) >> 1 : 32u;
+				const uint32_t nn = nmw ? (uint32_t)__clz((int)nmw) : 32u;
+				if (nn < m) m = nn;
+				if (cnt < m) m = cnt;
 			}
+			bi -= (int)m; tb -= m; jb += (int)m;
+			if (m < 32) break;
 		}
 		const bool ext_fails = bi >= 0 && base_at(bi) <= 3;         // bwt.c:330: no bwt_extend at the read start / an N
-		if (!failed) r_ext += (uint32_t)jb + (ext_fails ? 1u : 0u);
+		r_ext += (uint32_t)jb + (ext_fails ? 1u : 0u);
 		uint32_t shallow = 0;                                       // pushed matches too short to contain q[bi, bi+K): walked one by one
 		if (ext_fails) { // could a shorter match survive position bi?  Those of >= K - (cx - bi) bases all start with q[bi, bi+K) there
 			const int need_d = K - (cx - bi);
@@ -1236,6 +1227,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 		if (__all_sync(0xffffffffu, !active)) break;
 		const uint32_t rd = item.x;
 		const int cx = (int)(item.y & 0xffff), round = (int)((item.y >> 16) & 3), d = (int)((item.y >> 18) & 31);
+		bool lprobe = ((item.y >> 23) & 1) != 0;                    // the longest entry is L itself; see below
 		const uint64_t cmin = item.z;
 		uint32_t bits = active ? a.defer_bits[q] : 0u;
 		const int ls0 = (int)(bits >> 18);                          // 1 + start of the SMEM k_seed_fast already found for this call (0: none)
@@ -1294,6 +1286,23 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 					p[0] = make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)c1, (uint32_t)(c1 >> 32));
 					p[1] = make_uint4((uint32_t)c2, (uint32_t)(c2 >> 32), (uint32_t)(cx + e), (uint32_t)(bi + 1));
 					++nm;
+				}
+			}
+			if (lprobe) { // that was L (k_seed_fast's argument): the other entries of >= K - (cx - bi) bases all start with q[bi, bi+K)
+				lprobe = false;                                     // once extended to bi; if that K-mer does not occur they all end there, contained in L
+				if (bi < 0 || base_at(bi) > 3) bits = 0;            // read start / N: every interval ends here (bwt.c:331)
+				else {
+					const int K = (int)I.pt_k, need_d = K - (cx - bi);
+					const uint32_t shallow = need_d > 1 ? bits & ((1u << (need_d - 1)) - 1u) : 0u;
+					if (bits != shallow) { // some entry is long enough to need the probe
+						const uint32_t wi = (uint32_t)bi >> 5, sh = (uint32_t)bi & 31;
+						uint32_t nmw = nm_word(wi) >> sh;
+						if (sh) nmw |= nm_word(wi + 1) << (32 - sh);
+						const uint64_t key = key_of(bi, K);
+						if ((nmw & ((1u << K) - 1u)) || ((gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) != 0) punt = true;
+					}
+					if (__popc(shallow) > CS_WALK_MAX) punt = true;
+					bits = shallow;
 				}
 			}
 		}
