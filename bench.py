@@ -52,10 +52,17 @@ class ClockSampler:
 
     def __init__(self, gpu: int):
         self.gpu, self.rows, self.p = gpu, [], None
+        self.t0 = self.t1 = None   # the timed region (host clock); only samples that arrived inside it are used
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "40"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -63,19 +70,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self) -> dict:
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.p.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.05)]
+        rows = inside if inside else [r for _, r in self.rows[-3:]]   # a region shorter than the polling period: the nearest samples
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "samples_inside_timed_region": len(inside), "polling_ms": 40}
 
 
 def make_workload(args, rank: int, world: int, device: str):
@@ -200,12 +209,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi needs a moment to come up: start it before the warm-up
     for _ in range(args.warmup):
         ctx.run_staged(0, opt)
         last = ctx.wait_device(0)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     dev_ms, seed_ms, coll_ms, sa_ms, r3_ms, fast_ms, walk_ms = 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
     for _ in range(args.steps):
@@ -217,6 +227,7 @@ def main():
         dev_ms += last.kernel_ms[0] + last.kernel_ms[1] + last.kernel_ms[2]   # CUDA events on the launching stream
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler.mark_end()
     clocks = sampler.stop()
     counters = last.counters
     n_mems, n_seeds = last.n_mems_device, last.n_seeds_device

@@ -1182,6 +1182,9 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_fast(
 // bases goes back to the literal kernel.
 // ---------------------------------------------------------------------------------------------
 #define CS_WALK_STEPS 96
+#ifndef CS_R3_QUORUM
+#define CS_R3_QUORUM 8
+#endif
 __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(DevIndex I, SeedArgs a)
 {
 	constexpr int RW = CS_READ_SMEM;
@@ -1449,6 +1452,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 	const int jump = kd < opt.min_seed_len ? kd : opt.min_seed_len;
 	uint32_t n_ext = 0, n_call = 0, n_probe = 0;
 	bool have = false, exhausted = false;
+	bool parked = false;                                      // this lane's chain needs the literal walk and waits for company
 	uint32_t rd = 0, nmem = 0, n12 = 0; int len = 0, x = 0;
 	const cs_mem_t *pool12 = nullptr; cs_mem_t *out = nullptr;
 	int ms = 0, me = 0; uint64_t mtb = 0;                     // the unique first-pass SMEM [ms, me) last used, at text position mtb
@@ -1489,7 +1493,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 		// ---- this lane's next chain start x (bwamem.c:253-268) ----
 		bool active = false;
 		for (;;) { // reads are handed out for the whole warp at once
-			const bool want = !exhausted && !have;
+			const bool want = !exhausted && !have && !parked;
 			const uint32_t take = warp_take(a.next_read + 1, want);
 			if (want) {
 				rd = take;
@@ -1510,19 +1514,19 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 				}
 			}
 			bool finished = false;
-			if (have && !active) {
+			if (have && !active && !parked) {
 				while (x < len && base_at(x) > 3) ++x;
 				if (x < len) active = true;
 				else { a.r3_n_mems[rd] = nmem; have = false; finished = true; }
 			}
 			if (!__any_sync(0xffffffffu, finished && !exhausted)) break;
 		}
-		if (__all_sync(0xffffffffu, !active)) break;
-		if (!active) continue;
+		if (__all_sync(0xffffffffu, !active && !parked)) break;
 
 		// ---- the chain that starts at x ----
 		bool walk = false;                                          // needs the literal walk
-		if (W >= 32 || opt.max_mem_intv < 2) walk = true;           // the shortcuts below assume a 1-row interval ends the chain
+		if (!active) ;
+		else if (W >= 32 || opt.max_mem_intv < 2) walk = true;      // the shortcuts below assume a 1-row interval ends the chain
 		else if (x + W > len || (nmask_window(x) & ((1u << W) - 1u))) {
 			// an N or the read end comes before W bases: no seed; the next chain starts after the N (bwt.c:376), or nowhere
 			int i = x + 1;
@@ -1562,9 +1566,17 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 				}
 			}
 		}
-		if (!walk) continue;
-		// ---- literal walk of this chain (bwt.c:366-378), as in k_seed_r3 ----
+		// ---- literal walk of a chain (bwt.c:366-378), as in k_seed_r3.  It costs ten times a text-assisted chain and few
+		//      chains need it, so the lanes that do wait ("parked") until CS_R3_QUORUM of them can walk together, or until
+		//      nobody else has anything to do. ----
+		if (walk) parked = true;
 		{
+			const unsigned pm = __ballot_sync(0xffffffffu, parked);
+			const unsigned busy = __ballot_sync(0xffffffffu, active && !parked);
+			if (!(__popc(pm) >= CS_R3_QUORUM || (pm && !busy))) continue;
+		}
+		if (parked) {
+			parked = false;
 			uint64_t c0, c1, c2; int i;
 			if (jump >= 2 && x + jump <= len && !(nmask_window(x) & ((1u << jump) - 1u))) {
 				kt_lookup(I, (uint32_t)jump, key_of(x, jump), c0, c1, c2);
