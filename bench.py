@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--sa-intv", type=int, default=1, help="device SA sampling (1 = dense; 32 = the reference's on-disk sampling)")
     ap.add_argument("--e2e-batch", type=int, default=1 << 20, help="reads per pipelined batch on the host-buffer path")
+    ap.add_argument("--e2e-slots", type=int, default=3, help="pipelined batches in flight on the host-buffer path")
     ap.add_argument("--cpu-sample", type=int, default=300_000, help="reads of the same workload timed on the host cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -257,7 +258,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         bs = min(args.e2e_batch, n_reads)
-        n_slots = 3
+        n_slots = args.e2e_slots
         cs.host_register(bases)   # the reads sit in page-locked host memory, as the bench contract asks
         ectx = cs.SeedContext(idx, bs, bs * args.read_len, args.read_len, bs * 14, bs * 20, n_slots)
         starts_b = list(range(0, n_reads, bs))

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <vector>
 #include <algorithm>
+#include <time.h>
 #include <cub/device/device_scan.cuh>
 #include "cs_kernels.cuh"
 
@@ -436,6 +437,8 @@ struct Slot {
 	cudaStream_t stream;
 	cudaEvent_t ev[8];   // slot start, seed start, seed end, collect end, sa end, k_seed end (k_seed_r3 runs after it), k_seed_fast end
 	cudaEvent_t ev_done;
+	cudaEvent_t ev_kdone;  // kernels and the control block copy of the batch in flight are complete
+	bool want_fetch;       // submitted through cs_seed_batch_submit: the host wants the results (see prefetch_ready)
 	// pinned host
 	uint8_t *h_bases; uint32_t *h_off;
 	uint32_t *h_mem_off, *h_seed_off; cs_mem_t *h_mems; int64_t *h_rbeg;
@@ -479,6 +482,7 @@ static void slot_free(Slot *s)
 	if (s->stream) cudaStreamDestroy(s->stream);
 	for (int i = 0; i < 8; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
 	if (s->ev_done) cudaEventDestroy(s->ev_done);
+	if (s->ev_kdone) cudaEventDestroy(s->ev_kdone);
 	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
 	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
 	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_defer_bits); cudaFree(s->d_lit_q); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
@@ -554,6 +558,7 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 		for (int e = 0; e < 8; ++e) CK(cudaEventCreate(&s->ev[e]));
 		CK(cudaEventCreate(&s->ev_done));
+		CK(cudaEventCreateWithFlags(&s->ev_kdone, cudaEventDisableTiming));
 		CK(cudaMallocHost(&s->h_bases, max_bases));
 		CK(cudaMallocHost(&s->h_off, ((size_t)max_reads + 1) * 4));
 		CK(cudaMallocHost(&s->h_ctrl, sizeof(Ctrl)));
@@ -705,6 +710,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(s->ev[4], s->stream));
 	CK(cudaMemcpyAsync(s->h_ctrl, s->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaEventRecord(s->ev_kdone, s->stream));
 	s->state = 2;
 	return CS_OK;
 fail:
@@ -774,7 +780,7 @@ extern "C" int cs_seed_batch_stage(cs_ctx_t *ctx, int slot, uint32_t n_reads, co
 	if (!bases || !offsets) return set_err(CS_E_ARG, "null argument");
 	if ((rc = check_batch(ctx, n_reads, offsets)) != CS_OK) return rc;
 	Slot *s = &ctx->slots[slot];
-	if (s->state == 2) return set_err(CS_E_STATE, "slot %d is busy", slot);
+	if (s->state == 2 || s->state == 4) return set_err(CS_E_STATE, "slot %d is busy", slot);
 	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
 	memcpy(s->h_off, offsets, ((size_t)n_reads + 1) * 4);
 	s->n_reads = n_reads;
@@ -799,6 +805,8 @@ fail:
 	return CS_E_CUDA;
 }
 
+static void prefetch_ready(cs_ctx *ctx, const Slot *except);
+
 static int check_opt(const cs_seed_opt_t *opt)
 {
 	if (!opt) return set_err(CS_E_ARG, "null options");
@@ -815,9 +823,10 @@ extern "C" int cs_seed_batch_run_staged(cs_ctx_t *ctx, int slot, const cs_seed_o
 	if ((rc = check_opt(opt)) != CS_OK) return rc;
 	Slot *s = &ctx->slots[slot];
 	if (s->state == 0) return set_err(CS_E_STATE, "slot %d has no staged batch", slot);
-	if (s->state == 2) return set_err(CS_E_STATE, "slot %d is busy", slot);
+	if (s->state == 2 || s->state == 4) return set_err(CS_E_STATE, "slot %d is busy", slot);
 	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
 	if (s->state == 3) cudaEventRecord(s->ev[0], s->stream);
+	s->want_fetch = false;
 	return enqueue_run(ctx, s, opt);
 }
 
@@ -827,7 +836,10 @@ extern "C" int cs_seed_batch_submit(cs_ctx_t *ctx, int slot, uint32_t n_reads, c
 	int rc;
 	if ((rc = check_opt(opt)) != CS_OK) return rc;
 	if ((rc = cs_seed_batch_stage(ctx, slot, n_reads, bases, offsets)) != CS_OK) return rc;
-	return enqueue_run(ctx, &ctx->slots[slot], opt);
+	ctx->slots[slot].want_fetch = true;
+	rc = enqueue_run(ctx, &ctx->slots[slot], opt);
+	prefetch_ready(ctx, nullptr);
+	return rc;
 }
 
 extern "C" int cs_seed_batch_wait_device(cs_ctx_t *ctx, int slot, cs_result_t *out)
@@ -860,10 +872,45 @@ static int fetch(cs_ctx *ctx, Slot *s)
 	if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(s->h_mems, s->d_mems, (size_t)s->h_ctrl->n_mems * sizeof(cs_mem_t), cudaMemcpyDeviceToHost, s->stream));
 	if (s->h_ctrl->n_seeds) CK(cudaMemcpyAsync(s->h_rbeg, s->d_rows, (size_t)s->h_ctrl->n_seeds * 8, cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaEventRecord(s->ev_done, s->stream));
-	CK(cudaEventSynchronize(s->ev_done));
 	return CS_OK;
 fail:
 	return CS_E_CUDA;
+}
+
+static bool results_fit(const cs_ctx *ctx, const Slot *s)
+{
+	return !(s->h_ctrl->error != 0 || s->h_ctrl->pool_used > ctx->max_mems || s->h_ctrl->n_mems > ctx->max_mems || s->h_ctrl->n_seeds > ctx->max_seeds);
+}
+
+// Non-blocking: the result copies of every other slot whose kernels have finished are enqueued now, so that the
+// device-to-host engine goes from one batch to the next without waiting for the host to ask (the results are the
+// larger transfer: 355 bytes per read on ordinary data).  Anything unusual is left to the blocking path.
+static void prefetch_ready(cs_ctx *ctx, const Slot *except)
+{
+	// Off unless CS_PREFETCH=1: on the cfg2 bench it made the host-buffer path slower (79 vs 94 M reads/s, same box):
+	// two result copies then share the link, the slot being waited on returns later, and the next batch is submitted later.
+	static const bool on = getenv("CS_PREFETCH") && atoi(getenv("CS_PREFETCH")) == 1;
+	if (!on) return;
+	for (int i = 0; i < ctx->n_slots; ++i) {
+		Slot *s = &ctx->slots[i];
+		if (s == except || s->state != 2 || !s->want_fetch) continue;
+		if (cudaEventQuery(s->ev_kdone) != cudaSuccess) { cudaGetLastError(); continue; }
+		if ((s->used_fast && s->h_ctrl->n_defer > ctx->defer_cap) || !results_fit(ctx, s)) continue;
+		if (fetch(ctx, s) == CS_OK) s->state = 4;   // 4: results on their way to the host
+	}
+}
+
+// wait for the result copies of a slot; meanwhile keep the copy engine fed with the other slots' results
+static int fetch_wait(cs_ctx *ctx, Slot *s)
+{
+	for (;;) {
+		cudaError_t e = cudaEventQuery(s->ev_done);
+		if (e == cudaSuccess) return CS_OK;
+		if (e != cudaErrorNotReady) return set_err(CS_E_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+		cudaGetLastError();
+		prefetch_ready(ctx, s);
+		{ struct timespec ts = {0, 100000}; nanosleep(&ts, nullptr); }   // 0.1 ms: a busy poll slows the driver down
+	}
 }
 
 extern "C" int cs_seed_batch_fetch(cs_ctx_t *ctx, int slot, cs_result_t *out)
@@ -875,6 +922,7 @@ extern "C" int cs_seed_batch_fetch(cs_ctx_t *ctx, int slot, cs_result_t *out)
 	if (s->state != 3) return set_err(CS_E_STATE, "slot %d has no finished batch", slot);
 	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
 	if ((rc = fetch(ctx, s)) != CS_OK) return rc;
+	if ((rc = fetch_wait(ctx, s)) != CS_OK) return rc;
 	fill_result(ctx, s, out, true);
 	return CS_OK;
 }
@@ -885,10 +933,14 @@ extern "C" int cs_seed_batch_wait(cs_ctx_t *ctx, int slot, cs_result_t *out)
 	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
 	if (!out) return set_err(CS_E_ARG, "null result");
 	Slot *s = &ctx->slots[slot];
-	if (s->state != 2) return set_err(CS_E_STATE, "slot %d has no batch in flight", slot);
+	if (s->state != 2 && s->state != 4) return set_err(CS_E_STATE, "slot %d has no batch in flight", slot);
 	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
-	if ((rc = finish_run(ctx, s)) != CS_OK) { s->state = 1; return rc; }
-	if ((rc = fetch(ctx, s)) != CS_OK) return rc;
+	if (s->state == 2) {
+		if ((rc = finish_run(ctx, s)) != CS_OK) { s->state = 1; return rc; }
+		if ((rc = fetch(ctx, s)) != CS_OK) return rc;
+	}
+	if ((rc = fetch_wait(ctx, s)) != CS_OK) return rc;
+	s->state = 3;
 	fill_result(ctx, s, out, true);
 	return CS_OK;
 }
