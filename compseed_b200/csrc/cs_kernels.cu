@@ -1036,7 +1036,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			const int b = base_at(cx);
 			c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);   // bwt_set_intv, bwt.h:82
 		}
-		int i = cx + 1;
+		int i = cx + 1, udepth = 0;                                 // udepth: bases after which one occurrence was left
 		bool unique = false;
 		if (!has_n(cx, kd)) { // q[cx, cx+kd) is inside the read and unambiguous: its table entry directly
 			uint64_t o0, o1, o2;
@@ -1044,7 +1044,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			if (o2 >= cmin) { c0 = o0; c1 = o1; c2 = o2; i = cx + kd; r_ext += (uint32_t)(kd - 1); }
 		}
 		for (;;) {
-			if (c2 == 1 && cmin == 1) { unique = true; break; }
+			if (c2 == 1 && cmin == 1) { unique = true; udepth = i - cx; break; }
 			const int b = i < len ? base_at(i) : 4;
 			if (b > 3) break;
 			const int new_len = i + 1 - cx;
@@ -1120,19 +1120,25 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		}
 		const bool ext_fails = bi >= 0 && base_at(bi) <= 3;         // bwt.c:330: no bwt_extend at the read start / an N
 		r_ext += (uint32_t)jb + (ext_fails ? 1u : 0u);
-		uint32_t shallow = 0;                                       // pushed matches too short to contain q[bi, bi+K): walked one by one
-		if (ext_fails) { // could a shorter match survive position bi?  Those of >= K - (cx - bi) bases all start with q[bi, bi+K) there
+		uint32_t rest = 0;                                          // pushed matches that may survive position bi: k_seed_walk walks them one by one
+		if (ext_fails) { // Those of >= K - (cx - bi) bases all start with q[bi, bi+K) there: if it does not occur they end there, contained in L
 			const int need_d = K - (cx - bi);
-			if (need_d > 1) shallow = (d < K ? kmask : probe_bits(1, need_d - 1)) & ((1u << (need_d - 1)) - 1u);
-			bool ok = false;
-			if (__popc(shallow) <= CS_WALK_MAX && !has_n(bi, K)) { ok = pt_count(key_of(bi, K)) == 0; ++n_probe; if (!ok) STAT(8); }
-			else STAT(9);
-			if (!ok) { defer_call(cx, cmin); continue; }
+			if (need_d > 1) rest = (d < K ? kmask : probe_bits(1, need_d - 1)) & ((1u << (need_d - 1)) - 1u);
+			bool absent = false;
+			if (!has_n(bi, K)) { absent = pt_count(key_of(bi, K)) == 0; ++n_probe; }
+			if (!absent) { // every pushed match has to be looked at.  Beyond K bases only size changes before the match was unique are pushed:
+				STAT(8);    // none if it was unique by then (otherwise the literal kernel takes the call)
+				if (udepth > K) { defer_call(cx, cmin); continue; }
+				rest = d < K ? kmask & ~(1u << (d - 1)) : probe_bits(1, K - 1);
+				if (udepth >= 1 && udepth < 32) rest &= (1u << (udepth - 1)) - 1u;   // from udepth on the size stays 1: not pushed (bwt.c:311)
+			}
 		}
 		STAT(10);
 		if (end - (bi + 1) >= opt.min_seed_len && nmem >= a.mem_cap) { defer_call(cx, cmin); continue; }   // scratch full: the literal kernel stores it
-		// the shallow ones come after L in the sweep order: k_seed_walk starts its containment test from L's start
-		if (shallow) defer_walk(cx, cmin, d < 31 ? d : 31, shallow | ((uint32_t)(bi + 2) << 18));
+		// (each entry is a walk of its own in one lane of k_seed_walk: calls with many of them would hold their warp up)
+		if (__popc(rest) > CS_WALK_MAX) { defer_call(cx, cmin); continue; }
+		// they come after L in the sweep order: k_seed_walk starts its containment test from L's start
+		if (rest) defer_walk(cx, cmin, d < 31 ? d : 31, rest | ((uint32_t)(bi + 2) << 18));
 		n_ext += r_ext; n_call += r_call;
 		if (end - (bi + 1) < opt.min_seed_len) continue;            // bwamem.c:231-233,247
 		STAT(11);
@@ -1169,7 +1175,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_fast(
 //
 // k_seed_fast hands over, with their filter bits, the calls whose longest forward match L has fewer
 // than K bases and is either not pushable itself (first pass) or belongs to the second pass: the list
-// of the literal pass then holds at most CS_WALK_MAX matches E_e = q[cx, cx+e), one per filter bit.
+// of the literal pass then holds at most K - 1 matches E_e = q[cx, cx+e), one per filter bit.
 // In bwt_smem1a's backward phase a list entry's fate does not depend on the others except through
 // the start of the last SMEM found: a longer entry is a right-extension of a shorter one, so it dies
 // no later; hence when E_e fails to extend no longer entry is alive (curr->n == 0, bwt.c:332), and
@@ -1297,15 +1303,15 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 				else {
 					const int K = (int)I.pt_k, need_d = K - (cx - bi);
 					const uint32_t shallow = need_d > 1 ? bits & ((1u << (need_d - 1)) - 1u) : 0u;
-					if (bits != shallow) { // some entry is long enough to need the probe
+					if (bits != shallow) { // some entry is long enough for the probe to decide
 						const uint32_t wi = (uint32_t)bi >> 5, sh = (uint32_t)bi & 31;
 						uint32_t nmw = nm_word(wi) >> sh;
 						if (sh) nmw |= nm_word(wi + 1) << (32 - sh);
 						const uint64_t key = key_of(bi, K);
-						if ((nmw & ((1u << K) - 1u)) || ((gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) != 0) punt = true;
+						const bool absent = !(nmw & ((1u << K) - 1u)) && ((gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) == 0;
+						if (absent) bits = shallow;                     // else every entry is walked
 					}
-					if (__popc(shallow) > CS_WALK_MAX) punt = true;
-					bits = shallow;
+					if (__popc(bits) > CS_WALK_MAX) punt = true;        // too many for one lane: the literal kernel takes the call
 				}
 			}
 		}

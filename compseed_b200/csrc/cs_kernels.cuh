@@ -21,7 +21,7 @@
 #define CS_FAST_MINBLOCKS 4
 #endif
 #ifndef CS_WALK_MAX
-#define CS_WALK_MAX 3           // short forward matches a call may have to be walked by k_seed_walk (else k_seed)
+#define CS_WALK_MAX 6           // short forward matches a call may have to be walked by k_seed_walk (else k_seed)
 #endif
 #define CS_FAST_SMEM_BYTES ((size_t)CS_FAST_BLOCK * (CS_READ_SMEM * 12))
 
