@@ -1255,42 +1255,55 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 		uint32_t nm = 0, t_ext = 0, t_call = 0;
 		bool first = ls0 == 0, punt = false;
 		int last_start = ls0 - 1;
-		while (bits && !punt) { // entries, longest first
-			const int e = 32 - __clz((int)bits);
-			bits &= ~(1u << (e - 1));
-			// the interval of q[cx, cx+e) ...
-			uint64_t c0, c1, c2;
-			kt_lookup(I, (uint32_t)(e < kd ? e : kd), key_of(cx, e < kd ? e : kd), c0, c1, c2);
-			for (int k = kd; k < e; ++k) { // ... deeper than the table: forward bwt_extend steps
-				uint64_t o0, o1, o2; uint32_t two;
-				dev_extend(I, c0, c1, c2, 3 - base_at(cx + k), 0, o0, o1, o2, two);
-				c0 = o0; c1 = o1; c2 = o2; ++t_call; n_two += two;
+		// The loops below are made warp-uniform with votes: left to themselves the lanes drift apart (their entries take
+		// the table or the FM-index at different steps) and the hardware ends up running them one after the other.
+		while (__any_sync(0xffffffffu, bits && !punt)) { // entries, longest first
+			const bool on = bits && !punt;
+			int e = 0;
+			uint64_t c0 = 0, c1 = 0, c2 = 0;
+			bool go = false;
+			if (on) {
+				e = 32 - __clz((int)bits);
+				bits &= ~(1u << (e - 1));
+				// the interval of q[cx, cx+e) ...
+				kt_lookup(I, (uint32_t)(e < kd ? e : kd), key_of(cx, e < kd ? e : kd), c0, c1, c2);
+				for (int k = kd; k < e; ++k) { // ... deeper than the table: forward bwt_extend steps
+					uint64_t o0, o1, o2; uint32_t two;
+					dev_extend(I, c0, c1, c2, 3 - base_at(cx + k), 0, o0, o1, o2, two);
+					c0 = o0; c1 = o1; c2 = o2; ++t_call; n_two += two;
+				}
+				go = true;
+				if (e < d) { // pushed only if the next forward step changed the size (bwt.c:311-312)
+					uint64_t o0, o1, o2;
+					if (e + 1 <= kd) kt_lookup(I, (uint32_t)(e + 1), key_of(cx, e + 1), o0, o1, o2);
+					else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - base_at(cx + e), 0, o0, o1, o2, two); ++t_call; n_two += two; }
+					if (o2 == c2) go = false;
+				}
 			}
-			if (e < d) { // pushed only if the next forward step changed the size (bwt.c:311-312)
-				uint64_t o0, o1, o2;
-				if (e + 1 <= kd) kt_lookup(I, (uint32_t)(e + 1), key_of(cx, e + 1), o0, o1, o2);
-				else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - base_at(cx + e), 0, o0, o1, o2, two); ++t_call; n_two += two; }
-				if (o2 == c2) continue;
-			}
+			const bool walked = go;
 			// backward sweeps of this entry alone (bwt.c:326-345)
 			int bi = cx - 1;
-			for (int steps = 0; ; ++steps) {
-				const int b = bi >= 0 ? base_at(bi) : 4;
-				if (b > 3) break;                                   // read start / N: no bwt_extend (bwt.c:330)
-				if (steps >= CS_WALK_STEPS && ls0 == 0) { punt = true; break; }   // (a task that follows an SMEM of k_seed_fast is finished here)
-				const int new_len = cx + e - bi;
-				uint64_t o0, o1, o2;
-				++t_ext;
-				if (new_len <= kd) kt_lookup(I, (uint32_t)new_len, key_of(bi, new_len), o0, o1, o2);
-				else { uint32_t two; dev_extend(I, c0, c1, c2, b, 1, o0, o1, o2, two); ++t_call; n_two += two; }
-				if (o2 < cmin) break;                               // bwt.c:331
-				c0 = o0; c1 = o1; c2 = o2; --bi;
+			for (int steps = 0; __any_sync(0xffffffffu, go); ++steps) {
+				if (go) {
+					const int b = bi >= 0 ? base_at(bi) : 4;
+					if (b > 3) go = false;                              // read start / N: no bwt_extend (bwt.c:330)
+					else if (steps >= CS_WALK_STEPS && ls0 == 0) { punt = true; go = false; }   // (a task that follows an SMEM of k_seed_fast is finished here)
+					else {
+						const int new_len = cx + e - bi;
+						uint64_t o0, o1, o2;
+						++t_ext;
+						if (new_len <= kd) kt_lookup(I, (uint32_t)new_len, key_of(bi, new_len), o0, o1, o2);
+						else { uint32_t two; dev_extend(I, c0, c1, c2, b, 1, o0, o1, o2, two); ++t_call; n_two += two; }
+						if (o2 < cmin) go = false;                      // bwt.c:331
+						else { c0 = o0; c1 = o1; c2 = o2; --bi; }
+					}
+				}
 			}
-			if (punt) break;
+			if (!walked || punt) continue;
 			if (first || bi + 1 < last_start) { // bwt.c:332-336
 				first = false; last_start = bi + 1;
 				if (cx + e - (bi + 1) >= opt.min_seed_len) { // bwamem.c:231-233,247
-					if (nm >= a.mem_cap) { punt = true; break; }
+					if (nm >= a.mem_cap) { punt = true; continue; }
 					uint4 *p = reinterpret_cast<uint4*>(my + nm);
 					p[0] = make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)c1, (uint32_t)(c1 >> 32));
 					p[1] = make_uint4((uint32_t)c2, (uint32_t)(c2 >> 32), (uint32_t)(cx + e), (uint32_t)(bi + 1));
