@@ -1543,7 +1543,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 		if (__all_sync(0xffffffffu, !active && !parked)) break;
 
 		// ---- the chain that starts at x ----
-		bool walk = false;                                          // needs the literal walk
+		bool walk = false, from_text = false;                       // needs the literal walk / is resolved through the text
 		if (!active) ;
 		else if (W >= 32 || opt.max_mem_intv < 2) walk = true;      // the shortcuts below assume a 1-row interval ends the chain
 		else if (x + W > len || (nmask_window(x) & ((1u << W) - 1u))) {
@@ -1570,19 +1570,26 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 					}
 				}
 				if (me == 0) walk = true;
-				else {
-					const uint64_t P = mtb + (uint64_t)(x - ms);
-					uint64_t r0, r1; int w0, w1;
-					isa_near(P, r0, w0);
-					isa_near(I.seq_len - P - (uint64_t)W, r1, w1);
-					while (w0 | w1) {
-						if (w0) { r0 = dev_lf(I, r0); --w0; }
-						if (w1) { r1 = dev_lf(I, r1); --w1; }
-					}
-					put(r0, r1, 1, x, x + W);
-					n_ext += (uint32_t)(W - 1);
-					x += W;
-				}
+				else from_text = true;
+			}
+		}
+		// the seed of a chain inside a unique SMEM: rows of W's suffix and of its reverse complement's (all lanes take the
+		// LF steps together: the loop is controlled by a vote so that the warp does not drift apart)
+		{
+			uint64_t r0 = 0, r1 = 0; int w0 = 0, w1 = 0;
+			if (from_text) {
+				const uint64_t P = mtb + (uint64_t)(x - ms);
+				isa_near(P, r0, w0);
+				isa_near(I.seq_len - P - (uint64_t)W, r1, w1);
+			}
+			while (__any_sync(0xffffffffu, (w0 | w1) != 0)) {
+				if (w0) { r0 = dev_lf(I, r0); --w0; }
+				if (w1) { r1 = dev_lf(I, r1); --w1; }
+			}
+			if (from_text) {
+				put(r0, r1, 1, x, x + W);
+				n_ext += (uint32_t)(W - 1);
+				x += W;
 			}
 		}
 		// ---- literal walk of a chain (bwt.c:366-378), as in k_seed_r3.  It costs ten times a text-assisted chain and few
