@@ -94,7 +94,7 @@ fail:
 	return CS_E_CUDA;
 }
 
-// Occurrence filter (cs_device.cuh, ST_PRUNE in k_seed): 2-bit saturating counts of all K-mers of the
+// Occurrence filter (cs_device.cuh, "Occurrence filter" at k_seed): 2-bit saturating counts of all K-mers of the
 // indexed text, K = ceil(log4(seq_len)) + 2 capped at 19 (17 GB at K = 18, 69 GB at K = 19): long enough
 // that a random K-mer is almost always absent, short enough to stay below the default min_seed_len.
 // W is the 2-bit text if the caller has it (the on-device builder); otherwise it is rebuilt from the

@@ -30,7 +30,7 @@ struct DevIndex {
 	uint32_t kt_depth;      // 0 = no table
 	// Occurrence filter: a 2-bit saturating count (0,1,2,>=3) of every pt_k-mer of the indexed text
 	// (both strands), key as in read_key.  Lets the backward phase drop, with one gather, every forward
-	// match that cannot grow to min_seed_len bases (see ST_PRUNE in k_seed).  0 = no filter.
+	// match that cannot grow to min_seed_len bases (see "Occurrence filter" at k_seed).  0 = no filter.
 	const uint32_t *pt;
 	uint32_t pt_k;
 	// Unique-match fast path (k_seed, ST_TXT_*): the indexed text T = fwd + revcomp(fwd), 2 bits per

@@ -306,7 +306,10 @@ __global__ void k_sa_resolve(DevIndex I, const uint32_t *n_ptr, uint64_t cap, ui
 }
 
 // ---------------------------------------------------------------------------------------------
-// The seeding kernel (passes 1 and 2 of mem_collect_intv).
+// The LITERAL seeding kernel (passes 1 and 2 of mem_collect_intv): bwt_smem1a exactly as written, interval lists
+// and all.  Two modes: read mode (a.defer_q == NULL: every read of the batch; used when k_seed_fast is not
+// applicable -- sampled SA, long reads, min_seed_len below the filter's K) and call mode (the bwt_smem1a calls
+// k_seed_fast / k_seed_walk could not prove simple, one per lane, plus the second-pass calls of what they find).
 //
 // One read per THREAD, persistent threads, reads handed out in input order by an atomic counter
 // (neighbouring reordered reads run at the same time on neighbouring threads, so the sectors they
