@@ -426,6 +426,8 @@ struct Ctrl { // zeroed before every run; copied back after it
 	uint32_t next_read[4];   // work counters: [0] k_seed, [1] k_seed_r3, [2] k_seed_fast, [3] k_seed_walk
 	uint32_t n_defer;        // calls handed on by k_seed_fast (and k_seed_walk)
 	uint32_t n_lit;          // of those, for k_seed
+	uint32_t n_defer_fast;   // n_defer when k_seed_fast ended
+	uint32_t pad0;
 	unsigned long long pool_used;
 	unsigned long long counters[4 + 32];   // [4..19] k_seed, [20..35] k_seed_fast: event counters of a -DCS_STATS diagnostics build, else 0
 	unsigned long long sa_work, lf_steps;
@@ -635,7 +637,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	a.packed = s->d_packed; a.nmask = s->d_nmask;
 	a.next_read = s->d_ctrl->next_read;
 	a.defer_q = nullptr; a.defer_cap = ctx->defer_cap; a.n_defer = &s->d_ctrl->n_defer;
-	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n; a.defer_bits = s->d_defer_bits; a.lit_q = s->d_lit_q; a.n_lit = &s->d_ctrl->n_lit;
+	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n; a.defer_bits = s->d_defer_bits; a.lit_q = s->d_lit_q; a.n_lit = &s->d_ctrl->n_lit; a.n_defer_fast = &s->d_ctrl->n_defer_fast;
 	s->used_fast = false;
 	a.thread_mems = s->d_thread_mems; a.mem_cap = ctx->mem_cap;
 	a.spill = s->d_spill; a.spill_cap = ctx->spill_cap;
@@ -652,6 +654,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 		k_seed_fast<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, s->stream>>>(idx->d, a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(s->ev[6], s->stream));
+		CK(cudaMemcpyAsync(&s->d_ctrl->n_defer_fast, &s->d_ctrl->n_defer, 4, cudaMemcpyDeviceToDevice, s->stream));
 		k_seed_walk<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, s->stream>>>(idx->d, a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(s->ev[7], s->stream));

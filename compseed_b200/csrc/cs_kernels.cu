@@ -1229,8 +1229,8 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 			const bool want = !exhausted && !active;
 			const uint32_t take = warp_take(a.next_read + 3, want);
 			if (want) {
-				const uint32_t nq = *reinterpret_cast<volatile uint32_t*>(a.n_defer);
-				q = take;
+				const uint32_t nq = *a.n_defer_fast;             // the queue as k_seed_fast left it: entries appended by this kernel (second-pass
+				q = take;                                        // calls for k_seed) may still be in flight, over stale entries of an earlier batch
 				if (q >= (nq < a.defer_cap ? nq : a.defer_cap)) exhausted = true;
 				else { item = a.defer_q[q]; active = (item.y >> 31) != 0; }
 			}

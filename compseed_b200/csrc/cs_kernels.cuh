@@ -42,6 +42,7 @@ struct SeedArgs {
 	uint32_t *lit_q, *n_lit;    // the walk = 0 entries of defer_q (indices), listed for k_seed
 	uint32_t defer_cap;
 	uint32_t *n_defer;
+	const uint32_t *n_defer_fast; // n_defer as it stood when k_seed_fast ended (copied on the stream): what k_seed_walk scans
 	uint32_t *read_last_q;      // [n_reads] last deferred call of each read (chain head), ~0 if none
 	uint64_t *x_off;            // [defer_cap] where the mems of a deferred call start in pool
 	uint32_t *x_n;              // [defer_cap]

@@ -105,6 +105,25 @@ def test_batching_and_slots_do_not_change_results(cuda_lib, oracle_lib):
         assert np.array_equal(c.rbeg[c.seed_off[j]:c.seed_off[j + 1]], a.rbeg[a.seed_off[r]:a.seed_off[r + 1]])
 
 
+def test_slot_reuse_across_different_batches(cuda_lib, oracle_lib):
+    """A slot that has held another batch (stale deferred-call queue, scratch, chains) gives the same answer as a
+    fresh context.  (Regression: k_seed_walk once scanned queue entries that a concurrent lane had reserved but not
+    yet written, and could pick up a stale task of the previous batch.)"""
+    ref = synth.random_reference(300_000, seed=601)
+    sets = [synth.simulate_reads(ref, 6000, [100, 150, 250], 0.02, seed=602 + i, n_rate=0.002)[:2] for i in range(3)]
+    oi = oracle_lib.OracleIndex.build(ref)
+    idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv, dense_sa_intv=1)
+    want = [oi.seed(b, o, n_threads=8) for b, o in sets]
+    n_max = max(o.shape[0] - 1 for _, o in sets)
+    ctx = cuda_lib.SeedContext(idx, n_max, max(int(o[-1]) for _, o in sets), 256, n_max * 64, n_max * 600, 1)
+    for rep in range(4):
+        for (b, o), w in zip(sets, want):
+            ctx.submit(0, b, o, cuda_lib.SeedOpt())
+            r = ctx.wait(0)
+            _assert_same(r, w.mem_off, w.mems, w.seed_off, w.rbeg)
+    ctx.close()
+
+
 def test_staged_device_resident_run_and_fetch(cuda_lib, golden):
     idx = _upload(cuda_lib, golden, dense=1)
     n = golden["off"].shape[0] - 1
