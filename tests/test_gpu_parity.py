@@ -124,6 +124,24 @@ def test_slot_reuse_across_different_batches(cuda_lib, oracle_lib):
     ctx.close()
 
 
+def test_fast_route_equals_literal_route_midsize(cuda_lib, monkeypatch):
+    """100 Mbp reference (too large for the CPU oracle in test time): the fast route (k_seed_fast, k_seed_walk,
+    k_seed in call mode, k_seed_r3_fast) against the literal route (k_seed in read mode, k_seed_r3), which the
+    tests above pin to the oracle; every mem and seed position.  scripts/selfcheck_cfg2.py does the same at 3.1 Gbp."""
+    ref = synth.random_reference(100_000_000, seed=701)
+    bases, off, _ = synth.simulate_reads(ref, 400_000, [100, 150, 250], 0.01, seed=702, n_rate=0.0005)
+    idx = cuda_lib.FMIndex.build(ref, sa_intv=1)
+    out = {}
+    for fast in ("1", "0"):
+        monkeypatch.setenv("CS_FAST", fast)
+        out[fast] = cuda_lib.seed_reads(idx, bases, off, batch_reads=150_001, n_slots=2)
+    monkeypatch.delenv("CS_FAST")
+    a, b = out["1"], out["0"]
+    assert a.counters["deferred_calls"] > 0 and b.counters["deferred_calls"] == 0
+    _assert_same(a, b.mem_off, b.mems, b.seed_off, b.rbeg)
+    idx.close()
+
+
 def test_staged_device_resident_run_and_fetch(cuda_lib, golden):
     idx = _upload(cuda_lib, golden, dense=1)
     n = golden["off"].shape[0] - 1
