@@ -83,6 +83,45 @@ def simulate_reads(ref: np.ndarray, n_reads: int, read_len=150, sub_rate: float 
     return bases, off.astype(np.uint32), pos
 
 
+def boundary_reads(ref: np.ndarray, seed: int = 5):
+    """Crafted reads for the places where index arithmetic changes character (SURVEY.md section 8c and the
+    32-base word logic of the device kernels): matches at the first and last text position of both strands,
+    matches that bridge the forward / reverse-complement boundary, read lengths around multiples of 32 and
+    around 255/256, a substitution or an N at each word edge, an N next to a substitution."""
+    rng = np.random.default_rng(seed)
+    l_pac = ref.shape[0]
+    text = np.concatenate([ref, (3 - ref)[::-1]])          # what the FM-index indexes: fwd + revcomp(fwd)
+    reads = []
+
+    def add(seg, subs=(), ns=()):
+        r = np.array(seg, dtype=np.uint8, copy=True)
+        for p in subs:
+            if 0 <= p < r.shape[0]:
+                r[p] = (r[p] + 1 + int(rng.integers(0, 3))) & 3
+        for p in ns:
+            if 0 <= p < r.shape[0]:
+                r[p] = 4
+        reads.append(r)
+
+    edges = (0, 1, 30, 31, 32, 33, 62, 63, 64, 65, 95, 96, 127, 128, 148, 149)
+    for start in (0, 1, l_pac - 150, l_pac - 151, l_pac - 75, l_pac, l_pac + 1, 2 * l_pac - 150, 2 * l_pac - 151):
+        seg = text[start:start + 150]                      # text start/end of either strand, or across the strand boundary
+        add(seg)
+        for e in edges:
+            add(seg, subs=(e,))
+        add(seg, subs=(40, 41)); add(seg, subs=(20, 100)); add(seg, ns=(31,)); add(seg, ns=(32,), subs=(33,)); add(seg, subs=(63,), ns=(64,))
+        add(seg, ns=(0,)); add(seg, ns=(149,)); add(seg, subs=(0, 149))
+    mid = l_pac // 3
+    for L in (19, 20, 21, 27, 28, 29, 31, 32, 33, 38, 39, 40, 63, 64, 65, 95, 96, 97, 127, 128, 129, 159, 160, 161, 191, 192, 193, 223, 224, 225, 250, 254, 255, 256):
+        add(text[mid:mid + L])
+        add(text[mid + 1000:mid + 1000 + L], subs=(L // 2,))
+        add(text[mid + 2000:mid + 2000 + L], subs=(L // 3, 2 * L // 3))
+        add(text[2 * l_pac - mid - L:2 * l_pac - mid], ns=(L // 2,))
+    off = np.zeros(len(reads) + 1, np.uint32)
+    off[1:] = np.cumsum([r.shape[0] for r in reads])
+    return np.concatenate(reads).astype(np.uint8), off
+
+
 def shuffle_reads(bases: np.ndarray, off: np.ndarray, seed: int = 3):
     """Random permutation of a read set (the 'shuffled' arm of config 5)."""
     rng = np.random.default_rng(seed)

@@ -88,6 +88,23 @@ def test_live_against_reference(oracle_lib, kind):
         assert a.counters["sa"] == c.counters["sal_queries"]
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libcsref.so")),
+                    reason="oracle/_ref not built (needs /root/reference)")
+def test_boundary_reads_against_reference(oracle_lib):
+    """Text start / end of both strands, strand-bridging matches, lengths around 32-multiples and 255/256."""
+    ref = synth.random_reference(60_000, seed=51)
+    bases, off = synth.boundary_reads(ref)
+    oi = oracle_lib.OracleIndex.build(ref)
+    ri = oracle_lib.RefIndex.from_arrays(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv)
+    for kw in (dict(), dict(min_seed_len=19, split_factor=1.0, max_mem_intv=40, max_occ=50)):
+        a = oi.seed(bases, off, min_seed_len=kw.get("min_seed_len", 19), split_len=synth.split_len_bwamem(19, kw.get("split_factor", 1.5)),
+                    max_mem_intv=kw.get("max_mem_intv", 20), max_occ=kw.get("max_occ", 500), n_threads=4)
+        b = ri.seed(bases, off, "bwamem", n_threads=4, **kw)
+        c = ri.seed(bases, off, "compseed", n_threads=2, **kw)
+        assert a.same_as(b) and a.same_as(c)
+    assert a.mems.shape[0] > off.shape[0] - 1        # the set does produce seeds (most reads match end to end)
+
+
 def test_split_len_rounding():
     assert synth.split_len_bwamem(19, 1.5) == 28 and synth.split_len_compseed(19, 1.5) == 28
     assert synth.split_len_bwamem(19, 1.0) == 19 and synth.split_len_bwamem(19, 2.5) == 47
