@@ -105,6 +105,22 @@ def test_batching_and_slots_do_not_change_results(cuda_lib, oracle_lib):
         assert np.array_equal(c.rbeg[c.seed_off[j]:c.seed_off[j + 1]], a.rbeg[a.seed_off[r]:a.seed_off[r + 1]])
 
 
+@pytest.mark.parametrize("dense", [0, 1])
+def test_boundary_reads(cuda_lib, oracle_lib, dense):
+    """synth.boundary_reads: text start / end of both strands, strand-bridging matches, word-edge substitutions and Ns,
+    lengths around multiples of 32 and 255/256 (the oracle is checked against the reference on the same set in
+    tests/test_oracle.py)."""
+    ref = synth.random_reference(60_000, seed=51)
+    bases, off = synth.boundary_reads(ref)
+    oi = oracle_lib.OracleIndex.build(ref)
+    idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv, dense_sa_intv=dense)
+    for opt in (cuda_lib.SeedOpt(), cuda_lib.SeedOpt(split_factor=1.0, max_mem_intv=40, max_occ=50)):
+        want = oi.seed(bases, off, split_len=opt.split_len, max_mem_intv=opt.max_mem_intv, max_occ=opt.max_occ, n_threads=4)
+        got = cuda_lib.seed_reads(idx, bases, off, opt, batch_reads=500)
+        _assert_same(got, want.mem_off, want.mems, want.seed_off, want.rbeg)
+    idx.close()
+
+
 def test_slot_reuse_across_different_batches(cuda_lib, oracle_lib):
     """A slot that has held another batch (stale deferred-call queue, scratch, chains) gives the same answer as a
     fresh context.  (Regression: k_seed_walk once scanned queue entries that a concurrent lane had reserved but not
