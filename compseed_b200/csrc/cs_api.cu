@@ -452,6 +452,8 @@ struct Slot {
 	uint32_t *d_read_last_q, *d_x_n, *d_defer_bits, *d_lit_q; uint64_t *d_x_off;
 	cs_mem_t *d_stage;                        // collect: a read's sources gathered before the sort
 	bool used_fast;
+	bool packed_input;                        // the batch came through cs_seed_batch_submit_packed: d_packed / d_nmask are the input
+	uint64_t *h_packed; uint32_t *h_nmask;    // pinned staging for it (allocated on first use)
 	Ctrl *d_ctrl;
 	cs_mem_t *d_thread_mems; uint4 *d_spill;
 	cs_mem_t *d_pool, *d_mems;
@@ -485,6 +487,7 @@ static void slot_free(Slot *s)
 	for (int i = 0; i < 8; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
 	if (s->ev_done) cudaEventDestroy(s->ev_done);
 	if (s->ev_kdone) cudaEventDestroy(s->ev_kdone);
+	cudaFreeHost(s->h_packed); cudaFreeHost(s->h_nmask);
 	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
 	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
 	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_defer_bits); cudaFree(s->d_lit_q); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
@@ -630,9 +633,11 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	}
 	CK(cudaMemsetAsync(s->d_ctrl, 0, sizeof(Ctrl), s->stream));
 	CK(cudaEventRecord(s->ev[1], s->stream));
-	k_pack_reads<<<(int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, s->stream>>>(
-		s->d_bases, s->d_off, n, s->d_packed, s->d_nmask);
-	CK(cudaGetLastError());
+	if (!s->packed_input) {
+		k_pack_reads<<<(int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, s->stream>>>(
+			s->d_bases, s->d_off, n, s->d_packed, s->d_nmask);
+		CK(cudaGetLastError());
+	}
 	a.bases = s->d_bases; a.off = s->d_off; a.n_reads = n; a.opt = *opt;
 	a.packed = s->d_packed; a.nmask = s->d_nmask;
 	a.next_read = s->d_ctrl->next_read;
@@ -679,6 +684,11 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 			k_seed_r3_fast<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, s->stream>>>(idx->d, a);
 		} else {
 			int g3 = std::min<int>(ctx->grid_r3, (int)((n + 255) / 256));
+			if (s->packed_input) { // the general third-pass kernel reads the byte form
+				k_unpack_reads<<<(int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, s->stream>>>(
+					s->d_packed, s->d_nmask, s->d_off, n, s->d_bases);
+				CK(cudaGetLastError());
+			}
 			k_seed_r3<<<g3 < 1 ? 1 : g3, 256, 0, s->stream>>>(idx->d, a);
 		}
 		CK(cudaGetLastError());
@@ -776,6 +786,9 @@ static int check_batch(cs_ctx *ctx, uint32_t n_reads, const uint32_t *offsets)
 	return CS_OK;
 }
 
+static void prefetch_ready(cs_ctx *ctx, const Slot *except);
+static int check_opt(const cs_seed_opt_t *opt);
+
 extern "C" int cs_seed_batch_stage(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint8_t *bases, const uint32_t *offsets)
 {
 	int rc;
@@ -802,13 +815,58 @@ extern "C" int cs_seed_batch_stage(cs_ctx_t *ctx, int slot, uint32_t n_reads, co
 		}
 	}
 	CK(cudaMemcpyAsync(s->d_off, s->h_off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s->stream));
+	s->packed_input = false;
 	s->state = 1;
 	return CS_OK;
 fail:
 	return CS_E_CUDA;
 }
 
-static void prefetch_ready(cs_ctx *ctx, const Slot *except);
+extern "C" uint64_t cs_packed_words(uint32_t n_reads, const uint32_t *offsets)
+{
+	return offsets ? (uint64_t)(offsets[n_reads] >> 5) + 2ull * n_reads : 0;
+}
+
+extern "C" int cs_seed_batch_submit_packed(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint64_t *packed, const uint32_t *nmask,
+                                           const uint32_t *offsets, const cs_seed_opt_t *opt)
+{
+	int rc;
+	if ((rc = check_opt(opt)) != CS_OK) return rc;
+	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
+	if (!packed || !nmask || !offsets) return set_err(CS_E_ARG, "null argument");
+	if ((rc = check_batch(ctx, n_reads, offsets)) != CS_OK) return rc;
+	Slot *s = &ctx->slots[slot];
+	if (s->state == 2 || s->state == 4) return set_err(CS_E_STATE, "slot %d is busy", slot);
+	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	{
+		const uint64_t nw = cs_packed_words(n_reads, offsets);
+		const size_t cap = ((size_t)(ctx->max_bases >> 5) + 2 * (size_t)ctx->max_reads + 4);
+		memcpy(s->h_off, offsets, ((size_t)n_reads + 1) * 4);
+		s->n_reads = n_reads;
+		CK(cudaEventRecord(s->ev[0], s->stream));
+		cudaPointerAttributes pa;
+		bool pinned = cudaPointerGetAttributes(&pa, packed) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+		              cudaPointerGetAttributes(&pa, nmask) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+		const uint64_t *src_p = packed; const uint32_t *src_m = nmask;
+		if (!pinned) { // stage through the slot's own page-locked buffers
+			if (!s->h_packed) { CK(cudaMallocHost(&s->h_packed, cap * 8)); CK(cudaMallocHost(&s->h_nmask, cap * 4)); }
+			memcpy(s->h_packed, packed, nw * 8); memcpy(s->h_nmask, nmask, nw * 4);
+			src_p = s->h_packed; src_m = s->h_nmask;
+		}
+		CK(cudaMemcpyAsync(s->d_packed, src_p, nw * 8, cudaMemcpyHostToDevice, s->stream));
+		CK(cudaMemcpyAsync(s->d_nmask, src_m, nw * 4, cudaMemcpyHostToDevice, s->stream));
+		CK(cudaMemcpyAsync(s->d_off, s->h_off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s->stream));
+	}
+	s->packed_input = true;
+	s->state = 1;
+	s->want_fetch = true;
+	rc = enqueue_run(ctx, s, opt);
+	prefetch_ready(ctx, nullptr);
+	return rc;
+fail:
+	return CS_E_CUDA;
+}
 
 static int check_opt(const cs_seed_opt_t *opt)
 {

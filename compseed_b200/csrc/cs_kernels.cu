@@ -279,6 +279,23 @@ __global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t
 	}
 }
 
+// Inverse of k_pack_reads, for batches submitted in packed form (cs_seed_batch_submit_packed) when a kernel that
+// reads the byte form is going to run (k_seed_r3).  One thread per base.
+__global__ void k_unpack_reads(const uint64_t *packed, const uint32_t *nmask, const uint32_t *off, uint32_t n_reads, uint8_t *bases)
+{
+	const uint32_t sub = threadIdx.x & 7;
+	const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
+	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n_reads; r += ngroups) {
+		const uint32_t o = off[r], len = off[r + 1] - o;
+		const uint64_t w0 = (uint64_t)(o >> 5) + 2 * r;
+		for (uint32_t p = sub; p < len; p += 8) {
+			const uint64_t v = packed[w0 + (p >> 5)];
+			const uint32_t m = nmask[w0 + (p >> 5)];
+			bases[o + p] = ((m >> (p & 31)) & 1) ? 4 : (uint8_t)((v >> (2 * (p & 31))) & 3);
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // SA resolution: rows_inout[i] = bwt_sa(rows_inout[i]).  LF walks have a geometric length
 // distribution (mean 31, max 396+ at sa_intv 32), so lanes refill from a global

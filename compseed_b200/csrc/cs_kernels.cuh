@@ -99,6 +99,7 @@ __global__ void k_text_lsb(const uint64_t *W, uint64_t n_words, uint64_t *out);
 __global__ void k_isa_sample(DevIndex I, uint64_t *isa, uint32_t shift);
 __global__ void k_pt_count(const uint64_t *W, uint64_t n, uint32_t K, uint32_t *pt);
 __global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t n_reads, uint64_t *packed, uint32_t *nmask);
+__global__ void k_unpack_reads(const uint64_t *packed, const uint32_t *nmask, const uint32_t *off, uint32_t n_reads, uint8_t *bases);
 __global__ void k_seed(DevIndex I, SeedArgs a);
 __global__ void k_seed_long(DevIndex I, SeedArgs a);
 __global__ void k_seed_fast(DevIndex I, SeedArgs a);

@@ -86,6 +86,9 @@ def load_library():
     L.cs_ctx_free.argtypes = [C.c_void_p]
     L.cs_seed_batch_submit.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(_SeedOpt)]
     L.cs_seed_batch_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Result)]
+    L.cs_seed_batch_submit_packed.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SeedOpt)]
+    L.cs_packed_words.argtypes = [C.c_uint32, C.c_void_p]
+    L.cs_packed_words.restype = C.c_uint64
     L.cs_seed_batch_stage.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
     L.cs_seed_batch_run_staged.argtypes = [C.c_void_p, C.c_int, C.POINTER(_SeedOpt)]
     L.cs_seed_batch_wait_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Result)]
@@ -266,6 +269,14 @@ class SeedContext:
         o = opt._c()
         _check(load_library().cs_seed_batch_submit(self.h, slot, off.shape[0] - 1, _ptr(bases), _ptr(off), C.byref(o)))
 
+    def submit_packed(self, slot: int, packed, nmask, off, opt: SeedOpt) -> None:
+        """Reads already 2-bit packed by the caller (pack_reads): cs_seed_batch_submit_packed."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint64)
+        nmask = np.ascontiguousarray(nmask, dtype=np.uint32)
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        o = opt._c()
+        _check(load_library().cs_seed_batch_submit_packed(self.h, slot, off.shape[0] - 1, _ptr(packed), _ptr(nmask), _ptr(off), C.byref(o)))
+
     def stage(self, slot: int, bases, off) -> None:
         bases, off = self._prep(bases, off)
         _check(load_library().cs_seed_batch_stage(self.h, slot, off.shape[0] - 1, _ptr(bases), _ptr(off)))
@@ -314,6 +325,42 @@ class SeedContext:
         if copy:
             mem_off, seed_off, mems, rbeg = mem_off.copy(), seed_off.copy(), mems.copy(), rbeg.copy()
         return SeedResult(mem_off, mems, seed_off, rbeg, cnt, ms)
+
+
+def packed_words(off: np.ndarray) -> int:
+    """Length of the packed / nmask arrays of a batch: (off[n] >> 5) + 2 n (== cs_packed_words)."""
+    return (int(off[-1]) >> 5) + 2 * (off.shape[0] - 1)
+
+
+def pack_reads(bases: np.ndarray, off: np.ndarray):
+    """Host-side packing into the layout cs_seed_batch_submit_packed takes (include/compseed_b200.h): read r owns
+    the words [(off[r] >> 5) + 2r, ... + (len_r >> 5) + 2); base j of a word at bits 2j of packed and bit j of nmask
+    (set for codes > 3 and past the end of the read).  Pure numpy; no device involved."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint32).astype(np.int64)
+    n = off.shape[0] - 1
+    nw_tot = (int(off[-1]) >> 5) + 2 * n
+    packed = np.zeros(nw_tot, dtype=np.uint64)
+    nmask = np.full(nw_tot, 0xffffffff, dtype=np.uint32)
+    if n == 0 or off[-1] == 0:
+        return packed, nmask
+    lens = np.diff(off)
+    w0 = (off[:-1] >> 5) + 2 * np.arange(n, dtype=np.int64)         # first word of each read
+    nw = (lens >> 5) + 2
+    # words between a read's last word and the next read's first one stay "all N"; so do the pad words of a read
+    read_of_base = np.repeat(np.arange(n, dtype=np.int64), lens)
+    pos = np.arange(int(off[-1]), dtype=np.int64) - off[:-1][read_of_base]
+    word = w0[read_of_base] + (pos >> 5)
+    sh = (pos & 31).astype(np.uint64)
+    amb = bases > 3
+    code = np.where(amb, 0, bases).astype(np.uint64) << (np.uint64(2) * sh)
+    np.bitwise_or.at(packed, word, code)
+    clear = (~amb).astype(np.uint32) << sh.astype(np.uint32)
+    keep = np.zeros(nw_tot, dtype=np.uint32)
+    np.bitwise_or.at(keep, word, clear)
+    nmask &= ~keep
+    assert int((w0 + nw).max()) <= nw_tot
+    return packed, nmask
 
 
 def seed_reads(index: FMIndex, bases, off, opt: SeedOpt | None = None, batch_reads: int = 1 << 19,

@@ -140,6 +140,14 @@ void cs_ctx_free(cs_ctx_t *ctx);
  * enqueues H2D + kernels on the slot's stream and returns without waiting. */
 int cs_seed_batch_submit(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint8_t *bases, const uint32_t *offsets,
                          const cs_seed_opt_t *opt);
+/* The same with the reads already packed by the caller (57 instead of 150 bytes per 150-bp read
+ * cross the host-to-device link).  Layout: read r owns the words [(offsets[r] >> 5) + 2r, … + (len_r >> 5) + 2);
+ * word w of a read holds its bases 32w .. 32w+31, base j at bits 2j of packed[] (0..3) and at bit j of nmask[]
+ * (1 = ambiguous, i.e. a code > 3, or past the end of the read; the packed bits of such a base are 0).
+ * cs_packed_words gives the length of both arrays.  bwa.c:78-111 / main.cpp:36-58 is where a host would pack. */
+uint64_t cs_packed_words(uint32_t n_reads, const uint32_t *offsets);
+int cs_seed_batch_submit_packed(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint64_t *packed, const uint32_t *nmask,
+                                const uint32_t *offsets, const cs_seed_opt_t *opt);
 /* Waits for the slot, copies the results to its pinned host buffers and fills *out. */
 int cs_seed_batch_wait(cs_ctx_t *ctx, int slot, cs_result_t *out);
 

@@ -64,3 +64,29 @@ def test_option_mirror_defaults():
     o = cs.SeedOpt()   # mem_opt_init, comp_seed.cpp:26-61
     assert (o.min_seed_len, o.split_width, o.max_mem_intv, o.max_occ, o.split_len) == (19, 10, 20, 500, 28)
     assert cs.SeedOpt(split_factor=1.0).split_len == 19
+
+
+def test_pack_reads_layout():
+    """Host-side packer of cs_seed_batch_submit_packed: layout of include/compseed_b200.h (no device needed)."""
+    import numpy as np
+    import compseed_b200 as cs
+    from compseed_b200 import synth
+    ref = synth.random_reference(5000, seed=3)
+    bases, off, _ = synth.simulate_reads(ref, 40, [1, 31, 32, 33, 64, 100, 150, 250], 0.02, seed=4, n_rate=0.05)
+    packed, nmask = cs.pack_reads(bases, off)
+    assert packed.shape[0] == nmask.shape[0] == cs.packed_words(off)
+    for r in range(off.shape[0] - 1):
+        o, ln = int(off[r]), int(off[r + 1] - off[r])
+        w0 = (o >> 5) + 2 * r
+        for p in range(ln + 40):                       # 40 positions past the end: flagged, packed bits 0
+            w, j = w0 + (p >> 5), p & 31
+            if w >= w0 + (ln >> 5) + 2:
+                break
+            code = (int(packed[w]) >> (2 * j)) & 3
+            flag = (int(nmask[w]) >> j) & 1
+            if p < ln and bases[o + p] <= 3:
+                assert flag == 0 and code == bases[o + p]
+            else:
+                assert flag == 1 and code == 0
+    e, m = cs.pack_reads(np.zeros(0, np.uint8), np.zeros(1, np.uint32))
+    assert e.shape[0] == 0 and m.shape[0] == 0

@@ -121,6 +121,25 @@ def test_boundary_reads(cuda_lib, oracle_lib, dense):
     idx.close()
 
 
+@pytest.mark.parametrize("dense", [0, 1])
+def test_packed_submission_equals_byte_submission(cuda_lib, golden, dense):
+    """cs_seed_batch_submit_packed (reads 2-bit packed by the host) == cs_seed_batch_submit == golden."""
+    idx = _upload(cuda_lib, golden, dense)
+    bases, off = golden["bases"], golden["off"]
+    n = off.shape[0] - 1
+    packed, nmask = cuda_lib.pack_reads(bases, off)
+    ctx = cuda_lib.SeedContext(idx, n, int(off[-1]), 256, n * 64, n * 600, 2)
+    opt = _Opt(cuda_lib, _opts(golden, 0))
+    ctx.submit_packed(0, packed, nmask, off, opt)
+    ctx.submit(1, bases, off, opt)
+    a, b = ctx.wait(0), ctx.wait(1)
+    _assert_same(a, b.mem_off, b.mems, b.seed_off, b.rbeg)
+    _assert_same(a, golden["mem_off0"], golden["mems0"], golden["seed_off0"], golden["rbeg0"])
+    ctx.submit_packed(1, packed, nmask, off, opt)       # the other slot, after it held a byte batch
+    _assert_same(ctx.wait(1), golden["mem_off0"], golden["mems0"], golden["seed_off0"], golden["rbeg0"])
+    ctx.close()
+
+
 def test_slot_reuse_across_different_batches(cuda_lib, oracle_lib):
     """A slot that has held another batch (stale deferred-call queue, scratch, chains) gives the same answer as a
     fresh context.  (Regression: k_seed_walk once scanned queue entries that a concurrent lane had reserved but not
