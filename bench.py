@@ -347,7 +347,8 @@ def main():
     except Exception:
         pass
     roofline = {"kernel": "k_seed_fast + k_seed_walk + k_seed + k_seed_r3 (the three passes of mem_collect_intv)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": seed_ms_per_launch,
+                "traffic": traffic, "traffic_of": "k_seed_fast alone (the dominant kernel; ncu dram__bytes_read + write per read x reads of a launch, profiles/k_seed_traffic.json)",
+                "peak_source": peak_src, "ms_per_launch": seed_ms_per_launch,
                 "algorithmic_bytes_per_read": seed_bytes_per_read, "whole_path_bytes_per_read": path_bytes_per_read,
                 "extends_per_read": E, "two_bucket_ratio": e2_ratio,
                 "device_extends_per_read": counters["ext_queries"] / n_reads, "device_fm_extends_per_read": counters["ext_calls"] / n_reads,
