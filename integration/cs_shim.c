@@ -96,7 +96,23 @@ void csgpu_seed_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const bseq1
 				int s = next * CHUNK_READS, e = s + CHUNK_READS < n ? s + CHUNK_READS : n, r;
 				uint32_t *lo = (uint32_t*)malloc(((size_t)(e - s) + 1) * 4);
 				for (r = s; r <= e; ++r) lo[r - s] = off[r] - off[s];
-				if (cs_seed_batch_submit(g_ctx, next % N_SLOTS, (uint32_t)(e - s), bases + off[s], lo, &so) != CS_OK) fatal("cs_seed_batch_submit");
+				if (!getenv("CSGPU_PACKED")) {
+					if (cs_seed_batch_submit(g_ctx, next % N_SLOTS, (uint32_t)(e - s), bases + off[s], lo, &so) != CS_OK) fatal("cs_seed_batch_submit");
+				} else { /* CSGPU_PACKED=1: send the chunk 2-bit packed (57 instead of 150 bytes per 150-bp read cross the link) */
+					const uint64_t nw = cs_packed_words((uint32_t)(e - s), lo);
+					uint64_t *pk = (uint64_t*)calloc(nw ? nw : 1, 8);
+					uint32_t *nm = (uint32_t*)malloc((nw ? nw : 1) * 4);
+					memset(nm, 0xff, (nw ? nw : 1) * 4);               /* everything a read does not cover counts as N */
+					for (r = 0; r < e - s; ++r) {
+						const uint8_t *q = bases + off[s + r];
+						const uint64_t w0 = (uint64_t)(lo[r] >> 5) + 2ull * (uint64_t)r;
+						uint32_t p, len = lo[r + 1] - lo[r];
+						for (p = 0; p < len; ++p)
+							if (q[p] <= 3) { pk[w0 + (p >> 5)] |= (uint64_t)q[p] << (2 * (p & 31)); nm[w0 + (p >> 5)] &= ~(1u << (p & 31)); }
+					}
+					if (cs_seed_batch_submit_packed(g_ctx, next % N_SLOTS, (uint32_t)(e - s), pk, nm, lo, &so) != CS_OK) fatal("cs_seed_batch_submit_packed");
+					free(pk); free(nm);                                   /* (the library staged them in its own pinned buffers) */
+				}
 				free(lo);
 				++next;
 			}

@@ -20,9 +20,10 @@ def _have():
     return all(os.path.exists(p) for p in [GPUBIN] + [os.path.join(REFBIN, b) for b in ("bwaidx", "bwamem", "CompSeed")])
 
 
-def _run(binary, args, out):
+def _run(binary, args, out, env=None):
     with open(out, "wb") as f:
-        subprocess.run([binary] + args, stdout=f, stderr=subprocess.DEVNULL, check=True, timeout=900)
+        subprocess.run([binary] + args, stdout=f, stderr=subprocess.DEVNULL, check=True, timeout=900,
+                       env=dict(os.environ, **env) if env else None)
     return hashlib.md5(open(out, "rb").read()).hexdigest()
 
 
@@ -51,6 +52,9 @@ def test_sam_is_byte_identical(cuda_lib, tmp_path, kind):
     # a different -K only moves batch boundaries: same SAM for single-end input
     got2 = _run(GPUBIN, ["-t", "2", "-K", "50000", idx, reads], os.path.join(d, "gpu2.sam"))
     assert got2 == want
+    # the shim sending the reads 2-bit packed (cs_seed_batch_submit_packed)
+    got3 = _run(GPUBIN, ["-t", "4", "-K", "200000", idx, reads], os.path.join(d, "gpu3.sam"), env={"CSGPU_PACKED": "1"})
+    assert got3 == want
     # non-default seeding options travel through the shim
     a = _run(os.path.join(REFBIN, "bwamem"), ["-t", "4", "-k", "15", "-r", "1.0", "-y", "40", "-c", "50", idx, reads], os.path.join(d, "a.sam"))
     b = _run(GPUBIN, ["-t", "4", "-k", "15", "-r", "1.0", "-y", "40", "-c", "50", idx, reads], os.path.join(d, "b.sam"))
