@@ -20,6 +20,7 @@ import subprocess
 import sys
 import threading
 import time
+from types import SimpleNamespace
 
 import numpy as np
 
@@ -42,7 +43,12 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=300_000, help="reads of the same workload timed on the host cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--probe", action="store_true", help="also measure the random 32-byte sector gather peak")
+    ap.add_argument("--no-probe", action="store_true", help="skip the in-run random 32-byte sector gather peak (the roofline denominator)")
+    ap.add_argument("--verify-stride", type=int, default=1, help="cs_index_verify on the index the run uses: every n-th row (1 = all rows, 0 = skip)")
+    ap.add_argument("--e2e-input", default="packed", choices=["packed", "bytes"],
+                    help="what crosses the host-to-device link on the host-buffer path: 2-bit packed reads (cs_seed_batch_submit_packed) or nt4 bytes")
+    ap.add_argument("--l2-persist-mb", type=int, default=0, help="cs_ctx_config_t.l2_persist_mb for the contexts of this run")
+    ap.add_argument("--no-overlap", action="store_true", help="cs_ctx_config_t.overlap_streams = 0")
     return ap.parse_args()
 
 
@@ -109,7 +115,8 @@ def workload_name(args, world: int) -> str:
 
 def cpu_seed_sample(host_idx, bases, off, n_sample: int, threads: int):
     """Times the reference's own CPU seeding (oracle/_ref, CompSeed SST path and the bwamem path)
-    or, when oracle/_ref is absent, our C port, on the first n_sample reads of the workload."""
+    or, when oracle/_ref is absent, our C port, on the first n_sample reads of the workload.
+    Returns (info, {name: result}, n): the results are what the GPU output is compared with (parity)."""
     from oracle import oracle_py as O
     n = min(n_sample, off.shape[0] - 1)
     b, o = bases[:int(off[n])], off[:n + 1]
@@ -120,12 +127,23 @@ def cpu_seed_sample(host_idx, bases, off, n_sample: int, threads: int):
         bw = ri.seed(b, o, "bwamem", n_threads=threads)
         out.update(kind="reference", value=n / cs.seconds, unit="reads/s", bwamem_reads_per_s=n / bw.seconds,
                    compseed_counters=cs.counters, seconds=cs.seconds)
-        res = cs
+        res = {"CompSeed collect_mem_with_sst/tem_forward_sst + SAL (comp_seed.cpp:67,141,2255-2346)": cs,
+               "bwamem bwt_smem1/bwt_seed_strategy1/bwt_sa (bwt.c:289-379,86-96)": bw}
     else:
         oi = O.OracleIndex.from_arrays(host_idx["primary"], host_idx["L2"], host_idx["seq_len"], host_idx["bwt"], host_idx["sa"], host_idx["sa_intv"])
-        res = oi.seed(b, o, n_threads=threads)
-        out.update(kind="port", value=n / res.seconds, unit="reads/s", seconds=res.seconds)
+        r = oi.seed(b, o, n_threads=threads)
+        out.update(kind="port", value=n / r.seconds, unit="reads/s", seconds=r.seconds)
+        res = {"oracle port (oracle/cs_oracle.c)": r}
     return out, res, n
+
+
+def same_prefix(got, want, n: int) -> bool:
+    """The first n reads of `got` (mem_off, mems, seed_off, rbeg of a longer run) == `want` (exactly n reads), bit for bit."""
+    nm, ns = int(want.mem_off[-1]), int(want.seed_off[-1])
+    if got.mem_off.shape[0] < n + 1 or int(got.mem_off[n]) != nm or int(got.seed_off[n]) != ns:
+        return False
+    return bool(np.array_equal(got.mem_off[:n + 1], want.mem_off) and np.array_equal(got.seed_off[:n + 1], want.seed_off)
+                and np.array_equal(got.mems[:nm], want.mems) and np.array_equal(got.rbeg[:ns], want.rbeg))
 
 
 def work_counters(host_idx, bases, off, n_sample: int, threads: int):
@@ -166,12 +184,12 @@ def main():
     ref, bases, off = make_workload(args, rank if args.impl == "ours" else 0, world if args.impl == "ours" else 1, device)
     n_reads = off.shape[0] - 1
     idx = cs.FMIndex.build(ref, device=local_rank, sa_intv=args.sa_intv)
-    del ref
     opt = cs.SeedOpt()
     setup_s = time.time() - t_setup
 
     # ---------------------------------------------------------------------------------------
     if args.impl == "reference":
+        del ref
         host_idx = idx.download(sa_intv=32)
         idx.close()
         n_s = min(args.cpu_sample, n_reads)
@@ -199,9 +217,29 @@ def main():
         return 0
 
     # ---------------------------------------------------------------------------------------
-    # our arm.  (1) device-resident: all reads of the step staged in HBM once
+    # our arm.  (0) the index this run rests on, checked against the definitions of its parts (the 3.1 Gbp index is
+    # built on the GPU; bwaidx would need hours), and the random-sector peak of its own arrays: the roofline denominator
+    index_verify = None
+    if args.verify_stride > 0 and args.sa_intv == 1:
+        t_v = time.time()
+        index_verify = idx.verify(ref, stride=args.verify_stride)
+        index_verify["seconds"] = time.time() - t_v
+        index_verify["stride"] = args.verify_stride
+    del ref
+    probe = None
+    if not args.no_probe:
+        p1 = idx.probe_gather(1 << 28, 2, 1)
+        p4 = idx.probe_gather(1 << 28, 2, 4)
+        best = max(p1, p4, key=lambda x: x[1])
+        probe = {"gloads_per_s": best[1], "gb_per_s": best[0], "one_load_in_flight_per_thread_gloads_per_s": p1[1],
+                 "four_loads_in_flight_per_thread_gloads_per_s": p4[1],
+                 "what": "independent uniformly random 32-byte sector loads over this index's own arrays (%.1f GB), 1184 CTAs x 256 threads, "
+                         "measured in this run before the timed region (cs_probe_index_gather)" % (idx.device_bytes / 1e9)}
+    ccfg = cs.CtxConfig(l2_persist_mb=args.l2_persist_mb, overlap_streams=0 if args.no_overlap else -1)
+
+    # (1) device-resident: all reads of the step staged in HBM once
     max_mems, max_seeds = n_reads * 14, n_reads * 20
-    ctx = cs.SeedContext(idx, n_reads, int(off[-1]), args.read_len, max_mems, max_seeds, 1)
+    ctx = cs.SeedContext(idx, n_reads, int(off[-1]), args.read_len, max_mems, max_seeds, 1, ccfg)
     ctx.stage(0, bases, off)
 
     def barrier():
@@ -216,24 +254,28 @@ def main():
         ctx.run_staged(0, opt)
         last = ctx.wait_device(0)
     barrier()
+    launches0 = ctx.launches
     sampler.mark_begin()
     t0 = time.perf_counter()
-    dev_ms, seed_ms, coll_ms, sa_ms, r3_ms, fast_ms, walk_ms = 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
+    ms = {k: 0.0 for k in ("dev", "seed_span", "pack", "fast", "walk", "lit", "r3", "r3_tail", "collect", "sa")}
+    req = np.zeros(6, dtype=np.float64)
     for _ in range(args.steps):
         ctx.run_staged(0, opt)
         last = ctx.wait_device(0)
-        seed_ms += last.kernel_ms[4]; r3_ms += last.kernel_ms[5]; fast_ms += last.kernel_ms[6]; walk_ms += last.kernel_ms[7]
-        coll_ms += last.kernel_ms[1]
-        sa_ms += last.kernel_ms[2]
-        dev_ms += last.kernel_ms[0] + last.kernel_ms[1] + last.kernel_ms[2]   # CUDA events on the launching stream
+        km, k2 = last.kernel_ms, last.kernel_ms2
+        ms["seed_span"] += km[0]; ms["collect"] += km[1]; ms["sa"] += km[2]
+        ms["pack"] += k2[2]; ms["fast"] += km[6] - k2[2]; ms["walk"] += km[7]; ms["lit"] += k2[0]; ms["r3"] += k2[1]; ms["r3_tail"] += km[5]
+        ms["dev"] += km[0] + km[1] + km[2]   # CUDA events on the launching stream: pack .. SA resolution
+        req += np.array(last.gather_requests, dtype=np.float64)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     sampler.mark_end()
     clocks = sampler.stop()
+    dev_launches = ctx.launches - launches0
     counters = last.counters
     n_mems, n_seeds = last.n_mems_device, last.n_seeds_device
-    # parity spot check at full size: size-independent properties
-    got = ctx.fetch(0)
+    # size-independent properties on the whole step ...
+    got = ctx.fetch(0, copy=False)
     starts = (got.mems[:, 3] >> np.uint64(32)).astype(np.int64)
     ends = (got.mems[:, 3] & np.uint64(0xffffffff)).astype(np.int64)
     assert got.mem_off[-1] == n_mems and got.seed_off[-1] == n_seeds
@@ -243,8 +285,16 @@ def main():
     same_read = np.ones(info.shape[0], dtype=bool)
     same_read[got.mem_off[1:-1][got.mem_off[1:-1] < info.shape[0]]] = False
     assert np.all((info[1:] >= info[:-1]) | ~same_read[1:]), "mems not sorted by info inside a read"
+    del starts, ends, info, same_read
+    # ... and the first cpu_sample reads kept for the bit-exact comparison with the reference below
+    n_par = min(args.cpu_sample, n_reads)
+    nm_p, ns_p = int(got.mem_off[n_par]), int(got.seed_off[n_par])
+    dev_head = SimpleNamespace(mem_off=got.mem_off[:n_par + 1].copy(), mems=got.mems[:nm_p].copy(),
+                               seed_off=got.seed_off[:n_par + 1].copy(), rbeg=got.rbeg[:ns_p].copy())
+    del got
     ctx.close()
 
+    dev_ms = ms["dev"]
     if use_dist:
         t = torch.tensor([dev_ms, wall_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -255,15 +305,24 @@ def main():
     value = total_reads / (dev_ms_max * 1e-3)
 
     # (2) end to end through the C-ABI with HOST buffers: pipelined batches, H2D + D2H inside the timed region
-    e2e = None
-    if not args.no_e2e:
+    def run_e2e(packed_in: bool, keep_head: bool):
         bs = min(args.e2e_batch, n_reads)
         n_slots = args.e2e_slots
-        cs.host_register(bases)   # the reads sit in page-locked host memory, as the bench contract asks
-        ectx = cs.SeedContext(idx, bs, bs * args.read_len, args.read_len, bs * 14, bs * 20, n_slots)
         starts_b = list(range(0, n_reads, bs))
+        host_batches = []
+        if packed_in:   # the host holds the reads 2-bit packed, per batch, in page-locked memory (what a packing reader would leave)
+            for s0 in starts_b:
+                e0 = min(n_reads, s0 + bs)
+                o = (off[s0:e0 + 1].astype(np.int64) - int(off[s0])).astype(np.uint32)
+                pk, nm = cs.pack_reads_host(bases[int(off[s0]):int(off[e0])], o, threads)
+                cs.host_register(pk); cs.host_register(nm)
+                host_batches.append((pk, nm, o))
+        else:
+            cs.host_register(bases)   # the reads sit in page-locked host memory, as the bench contract asks
+        ectx = cs.SeedContext(idx, bs, bs * args.read_len, args.read_len, bs * 14, bs * 20, n_slots, ccfg)
+        keep = {}
 
-        def one_pass():
+        def one_pass(keep_first: bool = False):
             h2d = d2h = 0
             inflight = []
             nxt = 0
@@ -271,6 +330,10 @@ def main():
             def submit(bi):
                 s = starts_b[bi]
                 e = min(n_reads, s + bs)
+                if packed_in:
+                    pk, nm, o = host_batches[bi]
+                    ectx.submit_packed(bi % n_slots, pk, nm, o, opt)
+                    return pk.nbytes + nm.nbytes + o.nbytes
                 o = off[s:e + 1] - off[s]
                 ectx.submit(bi % n_slots, bases[int(off[s]):int(off[e])], o, opt)
                 return int(off[e]) - int(off[s]) + 4 * (e - s + 1)
@@ -283,6 +346,8 @@ def main():
             while inflight:
                 bi = inflight.pop(0)
                 r = ectx.wait(bi % n_slots, copy=False)
+                if keep_first and bi == 0:
+                    keep["first"] = SimpleNamespace(mem_off=r.mem_off.copy(), mems=r.mems.copy(), seed_off=r.seed_off.copy(), rbeg=r.rbeg.copy())
                 tot_m += int(r.mem_off[-1])
                 tot_s += int(r.seed_off[-1])
                 d2h += 4 * r.mem_off.shape[0] * 2 + 32 * int(r.mem_off[-1]) + 8 * int(r.seed_off[-1])
@@ -295,87 +360,117 @@ def main():
         for _ in range(max(1, args.warmup - 1)):
             one_pass()
         barrier()
+        l0 = ectx.launches
         t0 = time.perf_counter()
         for _ in range(args.steps):
             h2d, d2h, tot_m, tot_s = one_pass()
         barrier()
         e_ms = (time.perf_counter() - t0) * 1e3
+        n_launch = ectx.launches - l0
         assert tot_m == n_mems and tot_s == n_seeds, "host-buffer path disagrees with the device-resident path"
+        if keep_head:
+            one_pass(keep_first=True)     # untimed: the first batch's results, for the comparison with the reference
         if use_dist:
             t = torch.tensor([e_ms], device=device, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t[0])
-        e2e = {"value": total_reads / (e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-               "batch_reads": bs, "slots": n_slots, "timing": "host wall clock between device syncs; reads in page-locked host memory, results read back into the slots' pinned buffers"}
+        out = {"value": total_reads / (e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+               "batch_reads": bs, "slots": n_slots,
+               "input": "2-bit packed reads + N mask, packed by the host outside the timed region (cs_pack_reads_host, cs_seed_batch_submit_packed)" if packed_in else "nt4 bytes (cs_seed_batch_submit)",
+               "timing": "host wall clock between device syncs; inputs in page-locked host memory, results read back into the slots' pinned buffers"}
         ectx.close()
-        cs.host_unregister(bases)
+        if packed_in:
+            for pk, nm, _ in host_batches:
+                cs.host_unregister(pk); cs.host_unregister(nm)
+        else:
+            cs.host_unregister(bases)
+        return out, keep.get("first"), n_launch
+
+    e2e, e2e_head, e2e_launches = None, None, 0
+    if not args.no_e2e:
+        e2e, e2e_head, e2e_launches = run_e2e(args.e2e_input == "packed", True)
+        if args.e2e_input == "packed":   # the same with nt4 bytes crossing the link, for comparison (not the headline)
+            alt, _, _ = run_e2e(False, False)
+            e2e["nt4_bytes_input_variant"] = {k: alt[k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "input")}
 
     if rank != 0:
         if use_dist:
             dist.destroy_process_group()
         return 0
 
-    # (3) roofline of the dominant kernel (k_seed) + same-run CPU baseline (rank 0, N=1 only for the CPU leg)
+    # (3) same-run CPU baseline (rank 0, N=1 only) -- and PARITY: the reference's own mems and seed positions for the
+    # first cpu_sample reads of this very workload and index, against what the GPU returned above
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-    cpu_baseline, per_read = None, None
+    stream_peak, stream_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    cpu_baseline, per_read, parity = None, None, None
     if not args.no_cpu and world == 1:
         host_idx = idx.download(sa_intv=32)
-        cpu_baseline, _, _ = cpu_seed_sample(host_idx, bases, off, args.cpu_sample, threads)
+        cpu_baseline, ref_res, n_cmp = cpu_seed_sample(host_idx, bases, off, n_par, threads)
         per_read, _, n_cnt = work_counters(host_idx, bases, off, min(args.cpu_sample, 100_000), threads)
         del host_idx
-    # E = the reference's bwt_extend call count per read (logical work).  The device counters
-    # are lower: the occurrence filter and the top-of-search table remove work without changing results.
-    if per_read is not None:
-        E = per_read["ext"]
-        e2_ratio = per_read["ext2"] / per_read["ext"]
-        S, A, M = per_read["lf"], per_read["sa"], per_read["mem"]
-    else:
-        E, e2_ratio, S, A, M = 847.6, 0.6, 31.0 * n_seeds / n_reads, n_seeds / n_reads, n_mems / n_reads
-    # bytes of the seeding kernel = 64*(E+E2) + input bases + 32*M;  SA walk = 64*S + 16*A
-    seed_bytes_per_read = 64.0 * E * (1.0 + e2_ratio) + args.read_len + 32.0 * M
-    path_bytes_per_read = seed_bytes_per_read + 64.0 * S + 16.0 * A
-    seed_ms_per_launch = (seed_ms + r3_ms) / args.steps      # k_seed + k_seed_r3 == mem_collect_intv
-    achieved = seed_bytes_per_read * n_reads / (seed_ms_per_launch * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_seed_traffic.json")))["dram_bytes_per_read"] * n_reads
-    except Exception:
-        pass
-    # The same kernel seen from the memory system instead of from the reference's logical work: DRAM bytes ncu counted
-    # for k_seed_fast (per read, from the committed capture) over its live duration, and its L2 read requests per
-    # second next to the random-gather peak of this part (cs_probe_random_gather: 36-46 G loads/s).
-    measured = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "k_seed_traffic.json")))
-        fast_s = fast_ms / args.steps * 1e-3
-        measured = {"kernel": "k_seed_fast (with k_pack_reads)", "dram_gb_per_s": tj["dram_bytes_per_read"] * n_reads / fast_s / 1e9,
-                    "dram_frac_of_peak": tj["dram_bytes_per_read"] * n_reads / fast_s / 1e9 / peak,
-                    "l2_read_requests_per_s": tj.get("l2_read_requests_per_read", 98.7) * n_reads / fast_s,
-                    "random_gather_peak_loads_per_s": 37.9e9,
-                    "what": "achieved/frac above count the reference's logical bytes (SURVEY 8d), which the result-neutral structures mostly "
-                            "remove, hence frac > 1; these are the bytes and requests the dominant kernel really moves"}
-    except Exception:
-        pass
-    roofline = {"kernel": "k_seed_fast + k_seed_walk + k_seed + k_seed_r3 (the three passes of mem_collect_intv)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "measured_traffic_view": measured,
-                "traffic": traffic, "traffic_of": "k_seed_fast alone (the dominant kernel; ncu dram__bytes_read + write per read x reads of a launch, profiles/k_seed_traffic.json)",
-                "peak_source": peak_src, "ms_per_launch": seed_ms_per_launch,
-                "algorithmic_bytes_per_read": seed_bytes_per_read, "whole_path_bytes_per_read": path_bytes_per_read,
-                "extends_per_read": E, "two_bucket_ratio": e2_ratio,
-                "device_extends_per_read": counters["ext_queries"] / n_reads, "device_fm_extends_per_read": counters["ext_calls"] / n_reads,
-                "fast_ms_per_launch": fast_ms / args.steps, "deferred_calls_per_read": counters.get("deferred_calls", 0) / n_reads,
-                "kernel_share_of_step": {"k_seed_fast": fast_ms / dev_ms, "k_seed_walk": walk_ms / dev_ms, "k_seed": (seed_ms - fast_ms - walk_ms) / dev_ms, "k_seed_r3": r3_ms / dev_ms, "collect": coll_ms / dev_ms, "k_sa_resolve": sa_ms / dev_ms}}
-    occ_per_read = 2.0 * E + S
-    if args.probe:
-        gb, gl = cs.probe_random_gather(local_rank, 4 << 30, 32, 1 << 28, 2)
-        roofline["random_sector_peak"] = {"gloads_per_s": gl, "gb_per_s": gb, "what": "independent random 32-B loads over 4 GiB"}
-        roofline["sector_reads_per_s"] = E * (1.0 + e2_ratio) * n_reads / (seed_ms_per_launch * 1e-3) / 1e9
+        first = next(iter(ref_res.values()))
+        parity = {"reads": n_cmp, "mems": int(first.mem_off[-1]), "seeds": int(first.seed_off[-1]), "against": list(ref_res.keys()),
+                  "what": "mem_off, mems (x0, x1, x2, info), seed_off, rbeg of the first reads of the step, bit for bit",
+                  "device_resident_equal": all(same_prefix(dev_head, w, n_cmp) for w in ref_res.values())}
+        if e2e_head is not None:
+            n_e = min(n_cmp, e2e_head.mem_off.shape[0] - 1)
+            if n_e == n_cmp:
+                parity["e2e_equal"] = all(same_prefix(e2e_head, w, n_cmp) for w in ref_res.values())
+            else:   # the first host-buffer batch is shorter than the sample: compare it with the head of the device-resident result
+                parity["e2e_equal"] = same_prefix(dev_head, e2e_head, n_e) and parity["device_resident_equal"]
+        parity["equal"] = bool(parity["device_resident_equal"] and parity.get("e2e_equal", True))
+        parity["rows_at_or_above_2^32_in_sample"] = int((first.mems[:, 0] >= np.uint64(1 << 32)).sum())
 
+    # (4) roofline of the dominant kernel, k_seed_fast, from what it EXECUTES: memory requests counted in the kernel
+    # (one per lane and load that leaves the SM: Occ sectors, filter words, table entries, SA / inverse-SA / text words),
+    # 32 bytes (one sector) each, over its CUDA-event duration; the peak is the random-sector rate of the same arrays
+    # measured in this run.  The reference's logical work is reported next to it, not as a fraction of peak.
+    steps = args.steps
+    fast_s = ms["fast"] / steps * 1e-3
+    req_fast = req[0] / steps
+    achieved = req_fast * 32 / fast_s / 1e9
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_k_seed_fast_traffic.json")))
+        traffic = tj["dram_bytes_per_read"] * n_reads
+        traffic_src = "ncu --set full capture of k_seed_fast committed under profiles/ (%s): dram__bytes_read + write per read x reads of a launch; stale if the kernel changed since" % tj.get("capture", "?")
+    except Exception:
+        pass
+    peak = probe["gb_per_s"] if probe else None
+    roofline = {"kernel": "k_seed_fast", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if peak else None,
+                "peak_source": "random 32-byte sector gather over the index's own arrays, measured in this run" if probe else "not measured (--no-probe)",
+                "achieved_is": "executed memory requests of the kernel (in-kernel counter) x 32 B / CUDA-event duration",
+                "requests_per_read": req_fast / n_reads, "requests_per_s": req_fast / fast_s, "ms_per_launch": ms["fast"] / steps,
+                "random_sector_peak": probe,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "streaming_view": {"peak_gb_per_s": stream_peak, "peak_source": stream_src,
+                                   "dram_gb_per_s": (traffic / fast_s / 1e9) if traffic else None,
+                                   "frac": (traffic / fast_s / 1e9 / stream_peak) if traffic else None},
+                "all_kernels": {k: {"ms_per_step": ms[n] / steps, "requests_per_read": req[i] / steps / n_reads if i is not None else None,
+                                    "grequests_per_s": (req[i] / ms[n] / 1e6) if (i is not None and ms[n] > 0) else None}
+                                for k, n, i in (("k_pack_reads", "pack", None), ("k_seed_fast", "fast", 0), ("k_seed_walk", "walk", 1), ("k_seed", "lit", 2),
+                                                ("third pass (own stream, overlaps k_seed_walk / k_seed)", "r3", 3), ("collect", "collect", None), ("k_sa_resolve", "sa", 4))},
+                "kernel_share_of_step": {"k_pack_reads": ms["pack"] / dev_ms, "k_seed_fast": ms["fast"] / dev_ms, "k_seed_walk": ms["walk"] / dev_ms, "k_seed": ms["lit"] / dev_ms,
+                                         "third_pass_not_hidden": ms["r3_tail"] / dev_ms, "collect": ms["collect"] / dev_ms, "k_sa_resolve": ms["sa"] / dev_ms},
+                "deferred_calls_per_read": counters.get("deferred_calls", 0) / n_reads}
+    # the reference's logical work on the same reads (E extends, E2 of them over two buckets, S LF steps, A SA lookups, M mems)
+    ref_work = None
+    if per_read is not None:
+        E, e2_ratio, S, A, M = per_read["ext"], per_read["ext2"] / per_read["ext"], per_read["lf"], per_read["sa"], per_read["mem"]
+        seed_bytes = 64.0 * E * (1.0 + e2_ratio) + args.read_len + 32.0 * M
+        path_bytes = seed_bytes + 64.0 * S + 16.0 * A
+        occ_logical = 2.0 * E + S
+        ref_work = {"what": "SURVEY 8d: bytes the REFERENCE's algorithm would move for these reads (64-byte buckets, sa_intv 32); the result-neutral "
+                            "structures remove most of it, so this is a speed-up in work-equivalents, not a fraction of any peak",
+                    "extends_per_read": E, "two_bucket_ratio": e2_ratio, "lf_steps_per_read": S, "seeding_bytes_per_read": seed_bytes,
+                    "whole_path_bytes_per_read": path_bytes, "work_equivalent_gb_per_s": path_bytes * value / 1e9,
+                    "occ_lookups_per_read_logical": occ_logical, "occ_lookups_per_s_logical": occ_logical * value}
+    occ_exec_per_read = (2.0 * counters["ext_calls"] + counters["sal_calls"]) / n_reads
     line = {"metric": "smem_seeding_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
@@ -383,16 +478,25 @@ def main():
                        "result_neutral_structures": "dense SA, top-of-search k-mer table (depth <= 13), 2-bit occurrence filter (K <= 19), "
                                                     "2-bit text + sampled inverse SA for unique matches (DESIGN.md section 5)",
                        "l2_policy": "inputs larger than L2 (index %.1f GB, reads %.1f GB per step)" % (idx.device_bytes / 1e9, bases.nbytes / 1e9),
+                       "l2_persist_mb": args.l2_persist_mb, "overlap_streams": not args.no_overlap,
                        "parallelism": f"index replicated x{world}, reads sharded in contiguous blocks, host gather, no collective"},
-            "occ_lookups_per_s": occ_per_read * value, "occ_lookups_per_read": occ_per_read,
+            "parity": parity, "index_verify": index_verify,
+            "occ_lookups_per_s_executed": occ_exec_per_read * value, "occ_lookups_per_read_executed": occ_exec_per_read,
+            "occ_lookups_per_s_logical": ref_work["occ_lookups_per_s_logical"] if ref_work else None,
             "mems_per_read": n_mems / n_reads, "seeds_per_read": n_seeds / n_reads,
             "wall_ms_per_step": wall_ms_max / args.steps,
-            "e2e": e2e, "gpu_launches": 9 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "gpu_launches": int(dev_launches + e2e_launches),
+            "gpu_launches_what": "kernel launches counted at the launch sites of the library (cs_ctx_launches): %d in the device-resident timed region "
+                                 "(%d steps), %d in the host-buffer timed region" % (dev_launches, args.steps, e2e_launches),
+            "clocks": clocks, "roofline": roofline, "reference_work_equivalent": ref_work, "cpu_baseline": cpu_baseline,
             "counters": counters, "setup_s": setup_s}
     print(json.dumps(line))
     if use_dist:
         dist.destroy_process_group()
-    return 0
+    bad = (parity is not None and not parity["equal"]) or (index_verify is not None and not index_verify["ok"])
+    if bad:
+        sys.stderr.write("PARITY / INDEX CHECK FAILED: %s %s\n" % (parity, index_verify))
+    return 3 if bad else 0
 
 
 if __name__ == "__main__":

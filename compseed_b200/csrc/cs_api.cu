@@ -6,14 +6,17 @@
 #include <cstring>
 #include <cstdarg>
 #include <vector>
+#include <thread>
 #include <algorithm>
 #include <time.h>
 #include <cub/device/device_scan.cuh>
 #include "cs_kernels.cuh"
 
+#include "cs_internal.h"
+
 static thread_local char g_err[512] = "";
 
-static int set_err(int code, const char *fmt, ...)
+int cs_set_err(int code, const char *fmt, ...)
 {
 	va_list ap;
 	va_start(ap, fmt);
@@ -21,9 +24,7 @@ static int set_err(int code, const char *fmt, ...)
 	va_end(ap);
 	return code;
 }
-
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
-	set_err(CS_E_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); goto fail; } } while (0)
+#define set_err cs_set_err
 
 extern "C" const char *cs_last_error(void) { return g_err; }
 void cs_internal_set_error(int code, const char *msg) { set_err(code, "%s", msg); }
@@ -35,7 +36,7 @@ extern "C" int cs_device_count(void)
 	return n;
 }
 
-static int use_device(int device)
+int cs_use_device(int device)
 {
 	int n = cs_device_count();
 	if (n <= 0) return set_err(CS_E_NODEVICE, "no CUDA device visible: compseed_b200 has no CPU path");
@@ -44,32 +45,29 @@ static int use_device(int device)
 	if (e != cudaSuccess) return set_err(CS_E_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
 	return CS_OK;
 }
+#define use_device cs_use_device
 
-// ---------------------------------------------------------------------------------------------
-// index
-// ---------------------------------------------------------------------------------------------
-struct cs_index {
-	int device;
-	DevIndex d;
-	uint4 *d_buckets;
-	uint64_t *d_sa;
-	uint4 *d_kt;            // top-of-search table (depths 1..d.kt_depth)
-	uint32_t *d_pt;         // occurrence filter (2-bit counts of all d.pt_k-mers)
-	uint64_t *d_text, *d_isa; // unique-match fast path: 2-bit text and sampled inverse SA
-	uint64_t bytes;
-	uint64_t bwt_size_ref;  // words of the reference layout
-	int sa_intv;
-	int n_sm;
-};
+extern "C" void cs_index_config_default(cs_index_config_t *cfg)
+{
+	if (!cfg) return;
+	cfg->kmer_table_depth = -1; cfg->prune_k = -1; cfg->isa_intv = -1; cfg->reserved = 0;
+}
 
+extern "C" void cs_ctx_config_default(cs_ctx_config_t *cfg)
+{
+	if (!cfg) return;
+	cfg->use_fast = -1; cfg->use_r3_fast = -1; cfg->defer_cap = -1; cfg->lit_ctas_per_sm = -1;
+	cfg->prefetch_results = 0; cfg->l2_persist_mb = 0; cfg->overlap_streams = -1; cfg->reserved = 0;
+}
+
+static uint64_t kt_offset_host(uint32_t d) { return ((1ull << (2 * d)) - 4) / 3; }   // entries of depths 1 .. d-1 (kt_offset, cs_device.cuh)
 static int log2_exact(uint64_t v) { int s = 0; while ((1ull << s) < v) ++s; return (1ull << s) == v ? s : -1; }
 
 // Unique-match fast path (cs_device.cuh): 2-bit text in read bit order + sampled inverse SA.  Only with a
-// dense SA.  CS_ISA_INTV sets the ISA sampling (power of two, default 4; 0 disables the fast path).
+// dense SA.  cfg.isa_intv sets the ISA sampling (power of two, default 4; 0 disables the fast path).
 static int cs_internal_build_text(cs_index *idx, const uint64_t *W)
 {
-	const char *env = getenv("CS_ISA_INTV");
-	int intv = env ? atoi(env) : 4, shift = 0;
+	int intv = idx->cfg.isa_intv < 0 ? 4 : idx->cfg.isa_intv, shift = 0;
 	const uint64_t n = idx->d.seq_len;
 	idx->d.text = nullptr; idx->d.isa = nullptr; idx->d.isa_shift = 0; idx->d_text = nullptr; idx->d_isa = nullptr;
 	if (intv <= 0 || idx->d.sa_mask != 0 || !W) return CS_OK;
@@ -98,17 +96,16 @@ fail:
 // indexed text, K = ceil(log4(seq_len)) + 2 capped at 19 (17 GB at K = 18, 69 GB at K = 19): long enough
 // that a random K-mer is almost always absent, short enough to stay below the default min_seed_len.
 // W is the 2-bit text if the caller has it (the on-device builder); otherwise it is rebuilt from the
-// BWT and the SA.  CS_PRUNE_K overrides (0 disables).
+// BWT and the SA.  cfg.prune_k overrides (0 disables).
 int cs_internal_build_filter(cs_index *idx, const uint64_t *W)
 {
 	unsigned long long *own = nullptr;
 	int K = 2;
-	const char *env = getenv("CS_PRUNE_K");
 	const uint64_t n = idx->d.seq_len;
 	const int grid = idx->n_sm * 8;
 	while (K < 19 && (1ull << (2 * (K - 2))) < n) ++K;      // K - 2 >= log4(n)
 	if (K < 8) K = 8;
-	if (env) K = atoi(env);
+	if (idx->cfg.prune_k >= 0) K = idx->cfg.prune_k;
 	if (K > 0 && K < 4) K = 4;
 	if (K > 19) K = 19;
 	if (K < 0 || n < (uint64_t)K) K = 0;
@@ -143,13 +140,12 @@ fail:
 
 // Top-of-search table (cs_device.cuh): depth chosen so that the deepest level still has ~64 rows per
 // entry (deeper levels cost HBM without saving sector reads: k and l already share a bucket there).
-// CS_KMER_TABLE_DEPTH overrides (0 disables).
+// cfg.kmer_table_depth overrides (0 disables).
 static int build_kmer_table(cs_index *idx)
 {
 	int depth = 0;
-	const char *env = getenv("CS_KMER_TABLE_DEPTH");
 	while (depth < 13 && (idx->d.seq_len >> (2 * (depth + 1))) >= 64) ++depth;
-	if (env) depth = atoi(env);
+	if (idx->cfg.kmer_table_depth >= 0) depth = idx->cfg.kmer_table_depth;
 	if (depth < 0) depth = 0;
 	if (depth > 15) depth = 15;
 	idx->d.kt = nullptr; idx->d.kt_depth = 0; idx->d_kt = nullptr;
@@ -193,6 +189,9 @@ fail:
 }
 
 extern "C" cs_index_t *cs_index_upload(const cs_bwt_view_t *v, int device, int dense_sa_intv)
+{ return cs_index_upload_ex(v, device, dense_sa_intv, nullptr); }
+
+extern "C" cs_index_t *cs_index_upload_ex(const cs_bwt_view_t *v, int device, int dense_sa_intv, const cs_index_config_t *cfg)
 {
 	cs_index *idx = nullptr;
 	uint32_t *d_src = nullptr;
@@ -200,8 +199,12 @@ extern "C" cs_index_t *cs_index_upload(const cs_bwt_view_t *v, int device, int d
 	if (v->seq_len == 0 || v->seq_len >= (1ull << 37)) { set_err(CS_E_ARG, "seq_len %llu outside (0, 2^37)", (unsigned long long)v->seq_len); return nullptr; }
 	if (log2_exact((uint64_t)v->sa_intv) < 0) { set_err(CS_E_ARG, "sa_intv %d is not a power of two", v->sa_intv); return nullptr; }
 	if (use_device(device) != CS_OK) return nullptr;
+	if (v->n_sa != (v->seq_len + (uint64_t)v->sa_intv) / (uint64_t)v->sa_intv) { set_err(CS_E_ARG, "n_sa %llu does not match seq_len / sa_intv (bwt.c:435)", (unsigned long long)v->n_sa); return nullptr; }
+	if (v->bwt_size < ((v->seq_len + 15) >> 4)) { set_err(CS_E_ARG, "bwt_size %llu too small for seq_len %llu", (unsigned long long)v->bwt_size, (unsigned long long)v->seq_len); return nullptr; }
 	idx = (cs_index*)calloc(1, sizeof(cs_index));
+	if (!idx) { set_err(CS_E_ARG, "out of host memory"); return nullptr; }
 	idx->device = device;
+	if (cfg) idx->cfg = *cfg; else cs_index_config_default(&idx->cfg);
 	{
 		cudaDeviceProp prop;
 		CK(cudaGetDeviceProperties(&prop, device));
@@ -242,41 +245,98 @@ fail:
 }
 
 extern "C" cs_index_t *cs_index_load(const char *prefix, int device, int dense_sa_intv)
-{ // file format: bwt.c:385-407 (dump), bwt.c:421-462 (restore)
+{ return cs_index_load_ex(prefix, device, dense_sa_intv, nullptr); }
+
+static int64_t file_size(FILE *fp)
+{
+	if (fseek(fp, 0, SEEK_END) != 0) return -1;
+	const int64_t n = (int64_t)ftell(fp);
+	if (fseek(fp, 0, SEEK_SET) != 0) return -1;
+	return n;
+}
+
+extern "C" cs_index_t *cs_index_load_ex(const char *prefix, int device, int dense_sa_intv, const cs_index_config_t *cfg)
+{ // file format: bwt.c:385-407 (dump), bwt.c:421-462 (restore).  Corrupt or truncated files give CS_E_IO, never a crash.
 	char fn[4096];
 	cs_bwt_view_t v;
 	memset(&v, 0, sizeof v);
 	uint32_t *bwt = nullptr; uint64_t *sa = nullptr;
 	cs_index_t *idx = nullptr;
-	FILE *fp;
+	FILE *fp = nullptr;
 	uint64_t hdr[7];
+	int64_t fsz;
+	if (!prefix) { set_err(CS_E_ARG, "null prefix"); return nullptr; }
 	if (cs_device_count() <= 0) { set_err(CS_E_NODEVICE, "no CUDA device visible: compseed_b200 has no CPU path"); return nullptr; }
 	snprintf(fn, sizeof fn, "%s.bwt", prefix);
 	if ((fp = fopen(fn, "rb")) == nullptr) { set_err(CS_E_IO, "cannot open %s", fn); return nullptr; }
-	fseek(fp, 0, SEEK_END);
-	v.bwt_size = ((uint64_t)ftell(fp) - 40) >> 2;
-	fseek(fp, 0, SEEK_SET);
+	fsz = file_size(fp);
+	if (fsz < 40 + 4 || ((fsz - 40) & 3)) { set_err(CS_E_IO, "%s: %lld bytes is not a .bwt file (40-byte header + 32-bit words)", fn, (long long)fsz); goto done; }
+	v.bwt_size = (uint64_t)(fsz - 40) >> 2;
 	bwt = (uint32_t*)malloc(v.bwt_size * 4);
+	if (!bwt) { set_err(CS_E_IO, "out of host memory reading %s", fn); goto done; }
 	if (fread(&v.primary, 8, 1, fp) != 1 || fread(v.L2 + 1, 8, 4, fp) != 4 || fread(bwt, 4, v.bwt_size, fp) != v.bwt_size) {
-		fclose(fp); set_err(CS_E_IO, "short read on %s", fn); goto done;
+		set_err(CS_E_IO, "short read on %s", fn); goto done;
 	}
-	fclose(fp);
+	fclose(fp); fp = nullptr;
 	v.seq_len = v.L2[4];
+	if (v.seq_len == 0 || v.primary > v.seq_len || v.L2[1] > v.L2[2] || v.L2[2] > v.L2[3] || v.L2[3] > v.L2[4] ||
+	    v.bwt_size != ((v.seq_len + 15) >> 4) + ((v.seq_len + 127) / 128 + 1) * 8) {
+		set_err(CS_E_IO, "%s: header and size disagree (seq_len %llu, %llu words)", fn, (unsigned long long)v.seq_len, (unsigned long long)v.bwt_size); goto done;
+	}
 	snprintf(fn, sizeof fn, "%s.sa", prefix);
 	if ((fp = fopen(fn, "rb")) == nullptr) { set_err(CS_E_IO, "cannot open %s", fn); goto done; }
-	if (fread(hdr, 8, 7, fp) != 7) { fclose(fp); set_err(CS_E_IO, "short read on %s", fn); goto done; }
-	if (hdr[0] != v.primary || hdr[6] != v.seq_len) { fclose(fp); set_err(CS_E_IO, "SA-BWT inconsistency in %s (bwt.c:429,433)", fn); goto done; }
+	fsz = file_size(fp);
+	if (fsz < 56 || fread(hdr, 8, 7, fp) != 7) { set_err(CS_E_IO, "short read on %s", fn); goto done; }
+	if (hdr[0] != v.primary || hdr[6] != v.seq_len) { set_err(CS_E_IO, "SA-BWT inconsistency in %s (bwt.c:429,433)", fn); goto done; }
+	if (hdr[5] == 0 || hdr[5] > (1u << 20) || log2_exact(hdr[5]) < 0) { set_err(CS_E_IO, "%s: sa_intv %llu is not a power of two", fn, (unsigned long long)hdr[5]); goto done; }
 	v.sa_intv = (int32_t)hdr[5];
 	v.n_sa = (v.seq_len + v.sa_intv) / v.sa_intv;
+	if ((uint64_t)(fsz - 56) != (v.n_sa - 1) * 8) { set_err(CS_E_IO, "%s: %lld bytes, expected %llu (bwt.c:435)", fn, (long long)fsz, (unsigned long long)(56 + (v.n_sa - 1) * 8)); goto done; }
 	sa = (uint64_t*)malloc(v.n_sa * 8);
+	if (!sa) { set_err(CS_E_IO, "out of host memory reading %s", fn); goto done; }
 	sa[0] = (uint64_t)-1;
-	if (fread(sa + 1, 8, v.n_sa - 1, fp) != v.n_sa - 1) { fclose(fp); set_err(CS_E_IO, "short read on %s", fn); goto done; }
-	fclose(fp);
+	if (fread(sa + 1, 8, v.n_sa - 1, fp) != v.n_sa - 1) { set_err(CS_E_IO, "short read on %s", fn); goto done; }
+	fclose(fp); fp = nullptr;
 	v.bwt = bwt; v.sa = sa;
-	idx = cs_index_upload(&v, device, dense_sa_intv);
+	idx = cs_index_upload_ex(&v, device, dense_sa_intv, cfg);
 done:
+	if (fp) fclose(fp);
 	free(bwt); free(sa);
 	return idx;
+}
+
+extern "C" int cs_index_write(const cs_index_t *idx, const char *prefix, int sa_intv)
+{ // bwt_dump_bwt / bwt_dump_sa, FM_index/bwt.c:385-407
+	char fn[4096];
+	cs_bwt_view_t v;
+	uint32_t *bwt = nullptr; uint64_t *sa = nullptr;
+	FILE *fp = nullptr;
+	int rc;
+	if (!idx || !prefix) return set_err(CS_E_ARG, "null argument");
+	if ((rc = cs_index_download(idx, &v, nullptr, nullptr, sa_intv)) != CS_OK) return rc;
+	bwt = (uint32_t*)malloc(v.bwt_size * 4); sa = (uint64_t*)malloc(v.n_sa * 8);
+	if (!bwt || !sa) { free(bwt); free(sa); return set_err(CS_E_IO, "out of host memory"); }
+	if ((rc = cs_index_download(idx, &v, bwt, sa, sa_intv)) != CS_OK) { free(bwt); free(sa); return rc; }
+	rc = CS_E_IO;
+	snprintf(fn, sizeof fn, "%s.bwt", prefix);
+	if ((fp = fopen(fn, "wb")) == nullptr) { set_err(CS_E_IO, "cannot create %s", fn); goto done; }
+	if (fwrite(&v.primary, 8, 1, fp) != 1 || fwrite(v.L2 + 1, 8, 4, fp) != 4 || fwrite(bwt, 4, v.bwt_size, fp) != v.bwt_size) { set_err(CS_E_IO, "short write on %s", fn); goto done; }
+	if (fclose(fp) != 0) { fp = nullptr; set_err(CS_E_IO, "close failed on %s", fn); goto done; }
+	fp = nullptr;
+	snprintf(fn, sizeof fn, "%s.sa", prefix);
+	if ((fp = fopen(fn, "wb")) == nullptr) { set_err(CS_E_IO, "cannot create %s", fn); goto done; }
+	{
+		const uint64_t intv = (uint64_t)sa_intv;
+		if (fwrite(&v.primary, 8, 1, fp) != 1 || fwrite(v.L2 + 1, 8, 4, fp) != 4 || fwrite(&intv, 8, 1, fp) != 1 || fwrite(&v.seq_len, 8, 1, fp) != 1 ||
+		    fwrite(sa + 1, 8, v.n_sa - 1, fp) != v.n_sa - 1) { set_err(CS_E_IO, "short write on %s", fn); goto done; }
+	}
+	if (fclose(fp) != 0) { fp = nullptr; set_err(CS_E_IO, "close failed on %s", fn); goto done; }
+	fp = nullptr;
+	rc = CS_OK;
+done:
+	if (fp) fclose(fp);
+	free(bwt); free(sa);
+	return rc;
 }
 
 extern "C" int cs_index_info(const cs_index_t *idx, cs_bwt_view_t *v, uint64_t *device_bytes)
@@ -298,7 +358,7 @@ extern "C" int cs_index_download(const cs_index_t *idx, cs_bwt_view_t *v, uint32
 	if (!idx || !v) return set_err(CS_E_ARG, "null argument");
 	int sh = log2_exact((uint64_t)out_sa_intv);
 	if (sh < 0) return set_err(CS_E_ARG, "out_sa_intv %d is not a power of two", out_sa_intv);
-	if (use_device(idx->device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(idx->device); if (rc_ != CS_OK) return rc_; }
 	cs_index_info(idx, v, nullptr);
 	v->sa_intv = out_sa_intv;
 	v->n_sa = (idx->d.seq_len + out_sa_intv) / out_sa_intv;
@@ -338,10 +398,11 @@ extern "C" void cs_index_free(cs_index_t *idx)
 
 // internal: wrap device arrays produced by the on-device builder (cs_index_build.cu)
 cs_index_t *cs_index_adopt(int device, uint4 *d_buckets, uint64_t n_buckets, uint64_t *d_sa, uint64_t n_sa, int sa_intv,
-                           uint64_t primary, const uint64_t L2[5], uint64_t seq_len, const uint64_t *W)
+                           uint64_t primary, const uint64_t L2[5], uint64_t seq_len, const uint64_t *W, const cs_index_config_t *cfg)
 {
 	cs_index *idx = (cs_index*)calloc(1, sizeof(cs_index));
 	cudaDeviceProp prop;
+	if (cfg) idx->cfg = *cfg; else cs_index_config_default(&idx->cfg);
 	cudaGetDeviceProperties(&prop, device);
 	idx->device = device; idx->n_sm = prop.multiProcessorCount;
 	idx->d_buckets = d_buckets; idx->d_sa = d_sa;
@@ -367,7 +428,7 @@ extern "C" int cs_occ4(const cs_index_t *idx, uint32_t n, const uint64_t *k, uin
 	uint64_t *d_k = nullptr, *d_c = nullptr;
 	if (!idx || !k || !cnt) return set_err(CS_E_ARG, "null argument");
 	if (n == 0) return CS_OK;
-	if (use_device(idx->device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(idx->device); if (rc_ != CS_OK) return rc_; }
 	CK(cudaMalloc(&d_k, (size_t)n * 8)); CK(cudaMalloc(&d_c, (size_t)n * 32));
 	CK(cudaMemcpy(d_k, k, (size_t)n * 8, cudaMemcpyHostToDevice));
 	k_probe_occ4<<<(n + 255) / 256, 256>>>(idx->d, n, d_k, d_c);
@@ -385,7 +446,7 @@ extern "C" int cs_extend(const cs_index_t *idx, uint32_t n, const uint64_t *ik, 
 	uint64_t *d_ik = nullptr, *d_ok = nullptr; int32_t *d_b = nullptr;
 	if (!idx || !ik || !is_back || !ok) return set_err(CS_E_ARG, "null argument");
 	if (n == 0) return CS_OK;
-	if (use_device(idx->device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(idx->device); if (rc_ != CS_OK) return rc_; }
 	CK(cudaMalloc(&d_ik, (size_t)n * 24)); CK(cudaMalloc(&d_ok, (size_t)n * 96)); CK(cudaMalloc(&d_b, (size_t)n * 4));
 	CK(cudaMemcpy(d_ik, ik, (size_t)n * 24, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(d_b, is_back, (size_t)n * 4, cudaMemcpyHostToDevice));
@@ -404,7 +465,7 @@ extern "C" int cs_sa(const cs_index_t *idx, uint32_t n, const uint64_t *k, uint6
 	uint64_t *d_k = nullptr; unsigned long long *d_w = nullptr;
 	if (!idx || !k || !out) return set_err(CS_E_ARG, "null argument");
 	if (n == 0) return CS_OK;
-	if (use_device(idx->device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(idx->device); if (rc_ != CS_OK) return rc_; }
 	CK(cudaMalloc(&d_k, (size_t)n * 8)); CK(cudaMalloc(&d_w, 24));
 	CK(cudaMemset(d_w, 0, 24));
 	CK(cudaMemcpy(d_w + 2, &n, 4, cudaMemcpyHostToDevice));
@@ -431,13 +492,18 @@ struct Ctrl { // zeroed before every run; copied back after it
 	unsigned long long pool_used;
 	unsigned long long counters[4 + 32];   // [4..19] k_seed, [20..35] k_seed_fast: event counters of a -DCS_STATS diagnostics build, else 0
 	unsigned long long sa_work, lf_steps;
+	unsigned long long req[6];             // executed memory requests per kernel (SeedArgs::req)
+	unsigned long long tot12, tot3, tot_seeds;   // 64-bit batch totals: mems of passes 1-2, of pass 3, seeds
 	int error, pad1;
 	uint32_t n_mems, n_seeds;
 };
 
 struct Slot {
 	cudaStream_t stream;
-	cudaEvent_t ev[8];   // slot start, seed start, seed end, collect end, sa end, k_seed end (k_seed_r3 runs after it), k_seed_fast end
+	cudaStream_t stream2;  // the third-pass kernel runs here, next to k_seed_walk / k_seed (it depends on k_seed_fast only)
+	cudaEvent_t ev[8];   // slot start, seed start, seed end, collect end, sa end, k_seed end, k_seed_fast end, k_seed_walk end
+	cudaEvent_t ev_pack;   // k_pack_reads done
+	cudaEvent_t ev_fork, ev_join, ev_r3[2];   // fork / join of stream2; start and end of the third-pass kernel on it
 	cudaEvent_t ev_done;
 	cudaEvent_t ev_kdone;  // kernels and the control block copy of the batch in flight are complete
 	bool want_fetch;       // submitted through cs_seed_batch_submit: the host wants the results (see prefetch_ready)
@@ -478,13 +544,21 @@ struct cs_ctx {
 	int grid_fast;        // CTAs of k_seed_fast (0: the index or the read length does not allow the fast kernel)
 	int grid_r3;          // CTAs of k_seed_r3
 	uint32_t mem_cap, spill_cap, defer_cap;
+	cs_ctx_config_t cfg;
+	uint64_t n_launch;    // kernels launched so far (counted at the launch sites)
+	uint64_t need_mems[16], need_seeds[16];   // per slot: what the last overflowing batch would have needed
 	Slot *slots;
 };
 
 static void slot_free(Slot *s)
 {
 	if (s->stream) cudaStreamDestroy(s->stream);
+	if (s->stream2) cudaStreamDestroy(s->stream2);
 	for (int i = 0; i < 8; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+	if (s->ev_pack) cudaEventDestroy(s->ev_pack);
+	if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+	if (s->ev_join) cudaEventDestroy(s->ev_join);
+	for (int i = 0; i < 2; ++i) if (s->ev_r3[i]) cudaEventDestroy(s->ev_r3[i]);
 	if (s->ev_done) cudaEventDestroy(s->ev_done);
 	if (s->ev_kdone) cudaEventDestroy(s->ev_kdone);
 	cudaFreeHost(s->h_packed); cudaFreeHost(s->h_nmask);
@@ -506,6 +580,20 @@ extern "C" void cs_ctx_free(cs_ctx_t *ctx)
 
 extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, uint64_t max_bases, uint32_t max_read_len,
                                    uint64_t max_mems, uint64_t max_seeds, int n_slots)
+{ return cs_ctx_create_ex(idx, max_reads, max_bases, max_read_len, max_mems, max_seeds, n_slots, nullptr); }
+
+extern "C" uint64_t cs_ctx_launches(const cs_ctx_t *ctx) { return ctx ? ctx->n_launch : 0; }
+
+extern "C" int cs_ctx_need(const cs_ctx_t *ctx, int slot, uint64_t *need_mems, uint64_t *need_seeds)
+{
+	if (!ctx || slot < 0 || slot >= ctx->n_slots) return set_err(CS_E_ARG, "bad ctx / slot");
+	if (need_mems) *need_mems = ctx->need_mems[slot];
+	if (need_seeds) *need_seeds = ctx->need_seeds[slot];
+	return CS_OK;
+}
+
+extern "C" cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads, uint64_t max_bases, uint32_t max_read_len,
+                                      uint64_t max_mems, uint64_t max_seeds, int n_slots, const cs_ctx_config_t *cfg)
 {
 	cs_ctx *ctx = nullptr;
 	if (!idx) { set_err(CS_E_ARG, "null index"); return nullptr; }
@@ -517,6 +605,8 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 	}
 	if (use_device(idx->device) != CS_OK) return nullptr;
 	ctx = (cs_ctx*)calloc(1, sizeof(cs_ctx));
+	if (!ctx) { set_err(CS_E_ARG, "out of host memory"); return nullptr; }
+	if (cfg) ctx->cfg = *cfg; else cs_ctx_config_default(&ctx->cfg);
 	ctx->idx = idx; ctx->max_reads = max_reads; ctx->max_bases = max_bases; ctx->max_read_len = max_read_len;
 	ctx->max_mems = max_mems ? max_mems : (uint64_t)max_reads * 16;
 	ctx->max_seeds = max_seeds ? max_seeds : (uint64_t)max_reads * 32;
@@ -537,9 +627,8 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 		// reads that fit its shared-memory words; otherwise k_seed takes every read
 		ctx->grid_fast = 0;
 		{
-			const char *env = getenv("CS_FAST");
 			const DevIndex &d = idx->d;
-			if (!(env && atoi(env) == 0) && d.text && d.isa && d.pt && d.pt_k >= 4 && d.pt_k <= 19 && d.kt && d.kt_depth >= 2 &&
+			if (ctx->cfg.use_fast != 0 && d.text && d.isa && d.pt && d.pt_k >= 4 && d.pt_k <= 19 && d.kt && d.kt_depth >= 2 &&
 			    d.kt_depth < d.pt_k && max_read_len + 32 <= 32 * CS_READ_SMEM) {
 				CK(cudaFuncSetAttribute(k_seed_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_FAST_SMEM_BYTES));
 				CK(cudaFuncSetAttribute(k_seed_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_FAST_SMEM_BYTES));
@@ -556,12 +645,38 @@ extern "C" cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, ui
 	ctx->mem_cap = std::min<uint32_t>(2 * max_read_len + 16, 4096);
 	ctx->spill_cap = max_read_len > CS_LIST_SMEM ? max_read_len - CS_LIST_SMEM + 1 : 1;
 	ctx->defer_cap = 2 * max_reads + 4096;   // a batch that defers more calls than this is rerun without the fast kernel
-	if (const char *env = getenv("CS_DEFER_CAP")) ctx->defer_cap = (uint32_t)std::max(1, atoi(env));   // (tests force the rerun)
+	if (ctx->cfg.defer_cap > 0) ctx->defer_cap = (uint32_t)ctx->cfg.defer_cap;   // (tests force the rerun)
 	for (int i = 0; i < n_slots; ++i) {
 		Slot *s = &ctx->slots[i];
 		const size_t nthreads = std::max((size_t)ctx->grid * CS_SEED_BLOCK, (size_t)ctx->grid_fast * CS_FAST_BLOCK);
 		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
 		for (int e = 0; e < 8; ++e) CK(cudaEventCreate(&s->ev[e]));
+		CK(cudaEventCreate(&s->ev_pack));
+		CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+		for (int e = 0; e < 2; ++e) CK(cudaEventCreate(&s->ev_r3[e]));
+		if (ctx->cfg.l2_persist_mb > 0 && idx->d.kt) { // persisting L2 window over the top of the K-mer table (the "hot top-of-search" of north_star)
+			cudaDeviceProp prop;
+			CK(cudaGetDeviceProperties(&prop, idx->device));
+			size_t want = (size_t)ctx->cfg.l2_persist_mb << 20;
+			if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+			if (want > (size_t)prop.accessPolicyMaxWindowSize) want = (size_t)prop.accessPolicyMaxWindowSize;
+			const size_t kt_bytes = (size_t)(kt_offset_host(idx->d.kt_depth + 1)) * sizeof(uint4);
+			if (want > kt_bytes) want = kt_bytes;
+			if (want > 0) {
+				CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+				cudaStreamAttrValue av;
+				memset(&av, 0, sizeof av);
+				av.accessPolicyWindow.base_ptr = (void*)idx->d.kt;
+				av.accessPolicyWindow.num_bytes = want;
+				av.accessPolicyWindow.hitRatio = 1.0f;
+				av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+				av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+				CK(cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+				CK(cudaStreamSetAttribute(s->stream2, cudaStreamAttributeAccessPolicyWindow, &av));
+			}
+		}
 		CK(cudaEventCreate(&s->ev_done));
 		CK(cudaEventCreateWithFlags(&s->ev_kdone, cudaEventDisableTiming));
 		CK(cudaMallocHost(&s->h_bases, max_bases));
@@ -621,6 +736,38 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	SeedArgs a;
 	CollectArgs c;
 	const bool pass3 = opt->max_mem_intv > 0;
+	const bool overlap = ctx->cfg.overlap_streams != 0;
+	// The third pass depends on k_seed_fast alone (text-assisted: it reads the first-pass SMEMs k_seed_fast left in the
+	// pool) or on nothing (k_seed_r3): it runs on the slot's second stream, next to k_seed_walk / k_seed, whose few long
+	// tasks leave most of the GPU idle.
+	auto launch_r3 = [&](cudaStream_t st, bool text_assisted) -> cudaError_t {
+		if (text_assisted) {
+			int gf = std::min<int>(ctx->grid_fast, (int)((n + CS_FAST_BLOCK - 1) / CS_FAST_BLOCK));
+			k_seed_r3_fast<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, st>>>(idx->d, a);
+		} else {
+			int g3 = std::min<int>(ctx->grid_r3, (int)((n + 255) / 256));
+			if (s->packed_input) { // the general third-pass kernel reads the byte form
+				k_unpack_reads<<<(int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, st>>>(
+					s->d_packed, s->d_nmask, s->d_off, n, s->d_bases);
+				++ctx->n_launch;
+			}
+			k_seed_r3<<<g3 < 1 ? 1 : g3, 256, 0, st>>>(idx->d, a);
+		}
+		++ctx->n_launch;
+		return cudaGetLastError();
+	};
+	bool r3_done = !pass3;
+	auto fork_r3 = [&](bool text_assisted) -> cudaError_t { // after the kernel the third pass depends on has been enqueued on s->stream
+		cudaError_t e;
+		if ((e = cudaEventRecord(s->ev_fork, s->stream)) != cudaSuccess) return e;
+		if ((e = cudaStreamWaitEvent(s->stream2, s->ev_fork, 0)) != cudaSuccess) return e;
+		if ((e = cudaEventRecord(s->ev_r3[0], s->stream2)) != cudaSuccess) return e;
+		if ((e = launch_r3(s->stream2, text_assisted)) != cudaSuccess) return e;
+		if ((e = cudaEventRecord(s->ev_r3[1], s->stream2)) != cudaSuccess) return e;
+		if ((e = cudaEventRecord(s->ev_join, s->stream2)) != cudaSuccess) return e;
+		r3_done = true;
+		return cudaSuccess;
+	};
 	s->opt = *opt;
 	if (pass3) { // third-pass seeds of read r live at off[r]/(k+1) + r: at most bases/(k+1) + n entries
 		uint64_t need3 = (uint64_t)s->h_off[n] / ((uint32_t)opt->min_seed_len + 1) + n + 1;
@@ -636,8 +783,9 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	if (!s->packed_input) {
 		k_pack_reads<<<(int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, s->stream>>>(
 			s->d_bases, s->d_off, n, s->d_packed, s->d_nmask);
-		CK(cudaGetLastError());
+		CK(cudaGetLastError()); ++ctx->n_launch;
 	}
+	CK(cudaEventRecord(s->ev_pack, s->stream));
 	a.bases = s->d_bases; a.off = s->d_off; a.n_reads = n; a.opt = *opt;
 	a.packed = s->d_packed; a.nmask = s->d_nmask;
 	a.next_read = s->d_ctrl->next_read;
@@ -649,7 +797,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	a.pool = s->d_pool; a.pool_cap = ctx->max_mems; a.pool_used = &s->d_ctrl->pool_used;
 	a.read_pool_off = s->d_read_pool_off; a.read_n_mems = s->d_read_n_mems;
 	a.r3_mems = s->d_r3_mems; a.r3_n_mems = s->d_r3_n_mems;
-	a.counters = s->d_ctrl->counters; a.error = &s->d_ctrl->error;
+	a.counters = s->d_ctrl->counters; a.req = s->d_ctrl->req; a.error = &s->d_ctrl->error;
 	// passes 1-2: the call-synchronous fast kernel first; the reads it cannot prove simple (or all reads, when it
 	// is not available, or when min_seed_len is below the filter's K) go through the literal kernel
 	if (allow_fast && ctx->grid_fast > 0 && opt->min_seed_len >= (int)idx->d.pt_k) {
@@ -657,62 +805,53 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 		a.defer_q = s->d_defer_q;
 		s->used_fast = true;
 		k_seed_fast<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, s->stream>>>(idx->d, a);
-		CK(cudaGetLastError());
+		CK(cudaGetLastError()); ++ctx->n_launch;
 		CK(cudaEventRecord(s->ev[6], s->stream));
 		CK(cudaMemcpyAsync(&s->d_ctrl->n_defer_fast, &s->d_ctrl->n_defer, 4, cudaMemcpyDeviceToDevice, s->stream));
+		if (pass3 && overlap) CK(fork_r3(ctx->cfg.use_r3_fast != 0));
 		k_seed_walk<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, s->stream>>>(idx->d, a);
-		CK(cudaGetLastError());
+		CK(cudaGetLastError()); ++ctx->n_launch;
 		CK(cudaEventRecord(s->ev[7], s->stream));
 	} else {
 		CK(cudaEventRecord(s->ev[6], s->stream));
 		CK(cudaEventRecord(s->ev[7], s->stream));
+		if (pass3 && overlap) CK(fork_r3(false));
 	}
-	// (the spill stride inside k_seed follows the launched grid), then pass 3
-	if (s->used_fast) { // call mode: few, long tasks -- fewer resident warps make each trip of the state machine faster
-		const char *env = getenv("CS_LIT_CTAS_PER_SM");
-		const int per_sm = env ? atoi(env) : 0;
-		if (per_sm > 0) grid = std::min<int>(grid, idx->n_sm * per_sm);
-	}
+	// (the spill stride inside k_seed follows the launched grid)
+	if (s->used_fast && ctx->cfg.lit_ctas_per_sm > 0) // call mode: few, long tasks -- fewer resident warps make each trip of the state machine faster
+		grid = std::min<int>(grid, idx->n_sm * ctx->cfg.lit_ctas_per_sm);
 	if (ctx->max_read_len + 32 <= 32 * CS_READ_SMEM) k_seed<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
 	else k_seed_long<<<grid, CS_SEED_BLOCK, smem, s->stream>>>(idx->d, a);
-	CK(cudaGetLastError());
+	CK(cudaGetLastError()); ++ctx->n_launch;
 	CK(cudaEventRecord(s->ev[5], s->stream));
-	if (pass3) {
-		const char *env = getenv("CS_R3_FAST");
-		if (s->used_fast && !(env && atoi(env) == 0)) { // text-assisted: reads the first-pass SMEMs k_seed_fast left in the pool
-			int gf = std::min<int>(ctx->grid_fast, (int)((n + CS_FAST_BLOCK - 1) / CS_FAST_BLOCK));
-			k_seed_r3_fast<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, s->stream>>>(idx->d, a);
-		} else {
-			int g3 = std::min<int>(ctx->grid_r3, (int)((n + 255) / 256));
-			if (s->packed_input) { // the general third-pass kernel reads the byte form
-				k_unpack_reads<<<(int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, s->stream>>>(
-					s->d_packed, s->d_nmask, s->d_off, n, s->d_bases);
-				CK(cudaGetLastError());
-			}
-			k_seed_r3<<<g3 < 1 ? 1 : g3, 256, 0, s->stream>>>(idx->d, a);
-		}
-		CK(cudaGetLastError());
-	}
+	if (!r3_done) { // same stream, after the passes-1-2 kernels
+		CK(cudaEventRecord(s->ev_r3[0], s->stream));
+		CK(launch_r3(s->stream, s->used_fast && ctx->cfg.use_r3_fast != 0));
+		CK(cudaEventRecord(s->ev_r3[1], s->stream));
+	} else if (pass3) CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+	else { CK(cudaEventRecord(s->ev_r3[0], s->stream)); CK(cudaEventRecord(s->ev_r3[1], s->stream)); }
 	CK(cudaEventRecord(s->ev[2], s->stream));
 	// collect: offsets, sort, SA rows
 	k_mem_counts<<<std::min<int>(idx->n_sm * 8, (int)((n + 255) / 256)), 256, 0, s->stream>>>(s->d_read_n_mems, pass3 ? s->d_r3_n_mems : nullptr,
-		s->used_fast ? s->d_read_last_q : nullptr, s->d_defer_q, s->d_x_n, n, s->d_tot_n_mems);
-	CK(cudaGetLastError());
+		s->used_fast ? s->d_read_last_q : nullptr, s->d_defer_q, s->d_x_n, n, s->d_tot_n_mems, &s->d_ctrl->tot12, &s->d_ctrl->tot3);
+	CK(cudaGetLastError()); ++ctx->n_launch;
 	CK(cudaMemsetAsync(s->d_tot_n_mems + n, 0, 4, s->stream));
 	CK(cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, s->scan_tmp_bytes, s->d_tot_n_mems, s->d_mem_off, (int)n + 1, s->stream));
+	ctx->n_launch += 2;   // cub: init + scan kernel
 	c.n_reads = n; c.opt = *opt; c.pool = s->d_pool; c.read_pool_off = s->d_read_pool_off; c.read_n_mems = s->d_read_n_mems;
 	c.off = s->d_off; c.r3_mems = s->d_r3_mems; c.r3_n_mems = pass3 ? s->d_r3_n_mems : nullptr;
 	c.read_last_q = s->used_fast ? s->d_read_last_q : nullptr; c.defer_q = s->d_defer_q; c.x_off = s->d_x_off; c.x_n = s->d_x_n; c.stage = s->d_stage;
 	c.mem_off = s->d_mem_off; c.mems = s->d_mems; c.mems_cap = ctx->max_mems; c.read_n_seeds = s->d_read_n_seeds; c.seed_off = s->d_seed_off;
-	c.seed_rows = s->d_rows; c.seed_cap = ctx->max_seeds; c.error = &s->d_ctrl->error;
+	c.seed_rows = s->d_rows; c.seed_cap = ctx->max_seeds; c.tot_seeds = &s->d_ctrl->tot_seeds; c.error = &s->d_ctrl->error;
 	{
 		int cgrid = (int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16);
 		k_collect_sort<<<cgrid, 256, 0, s->stream>>>(c);
-		CK(cudaGetLastError());
+		CK(cudaGetLastError()); ++ctx->n_launch;
 		CK(cudaMemsetAsync(s->d_read_n_seeds + n, 0, 4, s->stream));
 		CK(cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, s->scan_tmp_bytes, s->d_read_n_seeds, s->d_seed_off, (int)n + 1, s->stream));
+		ctx->n_launch += 2;
 		k_collect_rows<<<cgrid, 256, 0, s->stream>>>(c);
-		CK(cudaGetLastError());
+		CK(cudaGetLastError()); ++ctx->n_launch;
 	}
 	CK(cudaMemcpyAsync(&s->d_ctrl->n_mems, s->d_mem_off + n, 4, cudaMemcpyDeviceToDevice, s->stream));
 	CK(cudaMemcpyAsync(&s->d_ctrl->n_seeds, s->d_seed_off + n, 4, cudaMemcpyDeviceToDevice, s->stream));
@@ -720,7 +859,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	// SA resolution: the kernel reads n_seeds from ctrl on the device, so nothing waits for the host
 	k_sa_resolve<<<idx->n_sm * 8, 256, 0, s->stream>>>(idx->d, &s->d_ctrl->n_seeds, ctx->max_seeds, s->d_rows,
 	                                                    &s->d_ctrl->sa_work, &s->d_ctrl->lf_steps);
-	CK(cudaGetLastError());
+	CK(cudaGetLastError()); ++ctx->n_launch;
 	CK(cudaEventRecord(s->ev[4], s->stream));
 	CK(cudaMemcpyAsync(s->h_ctrl, s->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaEventRecord(s->ev_kdone, s->stream));
@@ -728,6 +867,30 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	return CS_OK;
 fail:
 	return CS_E_CUDA;
+}
+
+// status of a finished run: CS_OK, or which kind of overflow (and, for the global kind, what the batch would need)
+static int run_status(cs_ctx *ctx, Slot *s)
+{
+	const Ctrl *h = s->h_ctrl;
+	const int slot = (int)(s - ctx->slots);
+	const uint64_t tot_mems = h->tot12 + h->tot3;
+	if (h->error == CS_E_READ_OVERFLOW)
+		return set_err(CS_E_READ_OVERFLOW, "a read of this batch needs more than %u mems or %u interval-list entries: the per-read scratch follows "
+		               "max_read_len (%u); larger max_mems / max_seeds do not help", ctx->mem_cap, ctx->spill_cap + CS_LIST_SMEM, ctx->max_read_len);
+	if (h->error != 0 || h->pool_used > ctx->max_mems || tot_mems > ctx->max_mems || h->tot_seeds > ctx->max_seeds) {
+		// passes 1-2 went through the pool (pool_used counts what was asked for, also past the capacity; tot12 misses the
+		// reads that did not fit); the seeds of reads whose mems did not fit in the pool are unknown: scale what is known
+		uint64_t nm = std::max<uint64_t>(h->pool_used, h->tot12) + h->tot3, ns = h->tot_seeds;
+		if (h->pool_used > ctx->max_mems) ns = std::max<uint64_t>(ns, (uint64_t)((double)ctx->max_seeds * ((double)nm / (double)ctx->max_mems) * 1.25));
+		ctx->need_mems[slot] = std::max<uint64_t>(nm + nm / 16 + 64, ctx->max_mems);
+		ctx->need_seeds[slot] = std::max<uint64_t>(ns + ns / 16 + 64, ctx->max_seeds);
+		return set_err(CS_E_OVERFLOW, "result buffers too small for this batch: mems %llu of %llu, seeds %llu of %llu; "
+		               "re-create the ctx with the capacities cs_ctx_need reports (%llu, %llu)",
+		               (unsigned long long)nm, (unsigned long long)ctx->max_mems, (unsigned long long)ns, (unsigned long long)ctx->max_seeds,
+		               (unsigned long long)ctx->need_mems[slot], (unsigned long long)ctx->need_seeds[slot]);
+	}
+	return CS_OK;
 }
 
 // wait for the device side of a run and check its status
@@ -740,13 +903,7 @@ static int finish_run(cs_ctx *ctx, Slot *s)
 		CK(cudaStreamSynchronize(s->stream));
 	}
 	s->state = 3;
-	if (s->h_ctrl->error != 0 || s->h_ctrl->pool_used > ctx->max_mems || s->h_ctrl->n_mems > ctx->max_mems || s->h_ctrl->n_seeds > ctx->max_seeds)
-		return set_err(CS_E_OVERFLOW, "result buffers too small for this batch: mems %llu of %llu, seeds %llu of %llu "
-		               "(or a read needed more than %u mems / %u list entries); re-create the ctx with larger max_mems/max_seeds",
-		               (unsigned long long)s->h_ctrl->pool_used, (unsigned long long)ctx->max_mems,
-		               (unsigned long long)s->h_ctrl->n_seeds, (unsigned long long)ctx->max_seeds, ctx->mem_cap,
-		               ctx->spill_cap + CS_LIST_SMEM);
-	return CS_OK;
+	return run_status(ctx, s);
 fail:
 	return CS_E_CUDA;
 }
@@ -769,7 +926,13 @@ static void fill_result(cs_ctx *ctx, Slot *s, cs_result_t *out, bool host_ptrs)
 	cudaEventElapsedTime(&out->kernel_ms[5], s->ev[5], s->ev[2]);
 	cudaEventElapsedTime(&out->kernel_ms[6], s->ev[1], s->ev[6]);
 	cudaEventElapsedTime(&out->kernel_ms[7], s->ev[6], s->ev[7]);
+	cudaEventElapsedTime(&out->kernel_ms2[0], s->ev[7], s->ev[5]);
+	cudaEventElapsedTime(&out->kernel_ms2[1], s->ev_r3[0], s->ev_r3[1]);
+	cudaEventElapsedTime(&out->kernel_ms2[2], s->ev[1], s->ev_pack);
 	out->n_deferred = s->h_ctrl->n_defer;
+	for (int k = 0; k < 4; ++k) out->gather_requests[k] = s->h_ctrl->req[k];
+	// k_sa_resolve: one 8-byte gather per seed with the dense SA, else one Occ sector per LF step plus the sample
+	out->gather_requests[4] = s->h_ctrl->n_seeds + s->h_ctrl->lf_steps;
 	(void)ctx;
 }
 
@@ -797,7 +960,7 @@ extern "C" int cs_seed_batch_stage(cs_ctx_t *ctx, int slot, uint32_t n_reads, co
 	if ((rc = check_batch(ctx, n_reads, offsets)) != CS_OK) return rc;
 	Slot *s = &ctx->slots[slot];
 	if (s->state == 2 || s->state == 4) return set_err(CS_E_STATE, "slot %d is busy", slot);
-	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
 	memcpy(s->h_off, offsets, ((size_t)n_reads + 1) * 4);
 	s->n_reads = n_reads;
 	CK(cudaEventRecord(s->ev[0], s->stream));
@@ -827,6 +990,41 @@ extern "C" uint64_t cs_packed_words(uint32_t n_reads, const uint32_t *offsets)
 	return offsets ? (uint64_t)(offsets[n_reads] >> 5) + 2ull * n_reads : 0;
 }
 
+extern "C" int cs_pack_reads_host(uint32_t n_reads, const uint8_t *bases, const uint32_t *offsets, uint64_t *packed, uint32_t *nmask, int n_threads)
+{ // the layout of cs_seed_batch_submit_packed; every word a read owns is written, the words between reads are left "all N"
+	if (!bases || !offsets || !packed || !nmask) return set_err(CS_E_ARG, "null argument");
+	if (n_threads < 1) n_threads = 1;
+	if (n_threads > 64) n_threads = 64;
+	const uint64_t nw_tot = cs_packed_words(n_reads, offsets);
+	auto work = [=](uint32_t r0, uint32_t r1) {
+		for (uint32_t r = r0; r < r1; ++r) {
+			const uint32_t o = offsets[r], len = offsets[r + 1] - o;
+			const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * r, nw = (uint64_t)(len >> 5) + 2;
+			const uint8_t *q = bases + o;
+			for (uint64_t w = 0; w < nw; ++w) {
+				uint64_t v = 0; uint32_t m = 0xffffffffu;
+				const uint32_t p0 = (uint32_t)w << 5, cnt = p0 < len ? (len - p0 < 32 ? len - p0 : 32) : 0;
+				for (uint32_t j = 0; j < cnt; ++j) {
+					const uint32_t c = q[p0 + j];
+					if (c <= 3) { v |= (uint64_t)c << (2 * j); m &= ~(1u << j); }
+				}
+				packed[w0 + w] = v; nmask[w0 + w] = m;
+			}
+			// words up to the next read's first word (there are none for equal-length reads that are multiples of 32 apart)
+			const uint64_t next0 = r + 1 < n_reads ? (uint64_t)(offsets[r + 1] >> 5) + 2ull * (r + 1) : nw_tot;
+			for (uint64_t w = w0 + nw; w < next0; ++w) { packed[w] = 0; nmask[w] = 0xffffffffu; }
+		}
+	};
+	if (n_threads == 1 || n_reads < 4096) { work(0, n_reads); return CS_OK; }
+	std::vector<std::thread> th;
+	for (int t = 0; t < n_threads; ++t) {
+		const uint32_t r0 = (uint32_t)((uint64_t)n_reads * t / n_threads), r1 = (uint32_t)((uint64_t)n_reads * (t + 1) / n_threads);
+		th.emplace_back(work, r0, r1);
+	}
+	for (auto &t : th) t.join();
+	return CS_OK;
+}
+
 extern "C" int cs_seed_batch_submit_packed(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint64_t *packed, const uint32_t *nmask,
                                            const uint32_t *offsets, const cs_seed_opt_t *opt)
 {
@@ -837,7 +1035,7 @@ extern "C" int cs_seed_batch_submit_packed(cs_ctx_t *ctx, int slot, uint32_t n_r
 	if ((rc = check_batch(ctx, n_reads, offsets)) != CS_OK) return rc;
 	Slot *s = &ctx->slots[slot];
 	if (s->state == 2 || s->state == 4) return set_err(CS_E_STATE, "slot %d is busy", slot);
-	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
 	{
 		const uint64_t nw = cs_packed_words(n_reads, offsets);
 		const size_t cap = ((size_t)(ctx->max_bases >> 5) + 2 * (size_t)ctx->max_reads + 4);
@@ -885,7 +1083,7 @@ extern "C" int cs_seed_batch_run_staged(cs_ctx_t *ctx, int slot, const cs_seed_o
 	Slot *s = &ctx->slots[slot];
 	if (s->state == 0) return set_err(CS_E_STATE, "slot %d has no staged batch", slot);
 	if (s->state == 2 || s->state == 4) return set_err(CS_E_STATE, "slot %d is busy", slot);
-	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
 	if (s->state == 3) cudaEventRecord(s->ev[0], s->stream);
 	s->want_fetch = false;
 	return enqueue_run(ctx, s, opt);
@@ -910,7 +1108,7 @@ extern "C" int cs_seed_batch_wait_device(cs_ctx_t *ctx, int slot, cs_result_t *o
 	if (!out) return set_err(CS_E_ARG, "null result");
 	Slot *s = &ctx->slots[slot];
 	if (s->state != 2) return set_err(CS_E_STATE, "slot %d has no batch in flight", slot);
-	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
 	rc = finish_run(ctx, s);
 	cudaEventRecord(s->ev_done, s->stream);
 	cudaEventSynchronize(s->ev_done);
@@ -940,7 +1138,8 @@ fail:
 
 static bool results_fit(const cs_ctx *ctx, const Slot *s)
 {
-	return !(s->h_ctrl->error != 0 || s->h_ctrl->pool_used > ctx->max_mems || s->h_ctrl->n_mems > ctx->max_mems || s->h_ctrl->n_seeds > ctx->max_seeds);
+	const Ctrl *h = s->h_ctrl;
+	return !(h->error != 0 || h->pool_used > ctx->max_mems || h->tot12 + h->tot3 > ctx->max_mems || h->tot_seeds > ctx->max_seeds);
 }
 
 // Non-blocking: the result copies of every other slot whose kernels have finished are enqueued now, so that the
@@ -948,10 +1147,9 @@ static bool results_fit(const cs_ctx *ctx, const Slot *s)
 // larger transfer: 355 bytes per read on ordinary data).  Anything unusual is left to the blocking path.
 static void prefetch_ready(cs_ctx *ctx, const Slot *except)
 {
-	// Off unless CS_PREFETCH=1: on the cfg2 bench it made the host-buffer path slower (79 vs 94 M reads/s, same box):
+	// Off unless cfg.prefetch_results: on the cfg2 bench it made the host-buffer path slower (79 vs 94 M reads/s, same box):
 	// two result copies then share the link, the slot being waited on returns later, and the next batch is submitted later.
-	static const bool on = getenv("CS_PREFETCH") && atoi(getenv("CS_PREFETCH")) == 1;
-	if (!on) return;
+	if (!ctx->cfg.prefetch_results) return;
 	for (int i = 0; i < ctx->n_slots; ++i) {
 		Slot *s = &ctx->slots[i];
 		if (s == except || s->state != 2 || !s->want_fetch) continue;
@@ -981,7 +1179,7 @@ extern "C" int cs_seed_batch_fetch(cs_ctx_t *ctx, int slot, cs_result_t *out)
 	if (!out) return set_err(CS_E_ARG, "null result");
 	Slot *s = &ctx->slots[slot];
 	if (s->state != 3) return set_err(CS_E_STATE, "slot %d has no finished batch", slot);
-	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
 	if ((rc = fetch(ctx, s)) != CS_OK) return rc;
 	if ((rc = fetch_wait(ctx, s)) != CS_OK) return rc;
 	fill_result(ctx, s, out, true);
@@ -995,7 +1193,7 @@ extern "C" int cs_seed_batch_wait(cs_ctx_t *ctx, int slot, cs_result_t *out)
 	if (!out) return set_err(CS_E_ARG, "null result");
 	Slot *s = &ctx->slots[slot];
 	if (s->state != 2 && s->state != 4) return set_err(CS_E_STATE, "slot %d has no batch in flight", slot);
-	if (use_device(ctx->idx->device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
 	if (s->state == 2) {
 		if ((rc = finish_run(ctx, s)) != CS_OK) { s->state = 1; return rc; }
 		if ((rc = fetch(ctx, s)) != CS_OK) return rc;
@@ -1025,7 +1223,7 @@ extern "C" int cs_probe_random_gather_ex(int device, uint64_t table_bytes, uint3
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	float best = 1e30f;
 	if (granule != 16 && granule != 32 && granule != 64) return set_err(CS_E_ARG, "granule must be 16, 32 or 64");
-	if (use_device(device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(device); if (rc_ != CS_OK) return rc_; }
 	if (l2_fetch_granularity) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)l2_fetch_granularity);
 	{
 		cudaDeviceProp prop;
@@ -1089,7 +1287,7 @@ extern "C" int cs_flush_l2(int device)
 {
 	static uint4 *buf[16] = {nullptr};
 	const uint64_t bytes = 512ull << 20;
-	if (use_device(device) != CS_OK) return CS_E_CUDA;
+	{ const int rc_ = use_device(device); if (rc_ != CS_OK) return rc_; }
 	if (device >= 16) return set_err(CS_E_ARG, "device index too large");
 	if (!buf[device]) CK(cudaMalloc(&buf[device], bytes));
 	k_fill<<<1024, 256>>>(buf[device], bytes / 16, 3u);

@@ -21,7 +21,7 @@
 #include "cs_kernels.cuh"
 
 cs_index_t *cs_index_adopt(int device, uint4 *d_buckets, uint64_t n_buckets, uint64_t *d_sa, uint64_t n_sa, int sa_intv,
-                           uint64_t primary, const uint64_t L2[5], uint64_t seq_len, const uint64_t *W);
+                           uint64_t primary, const uint64_t L2[5], uint64_t seq_len, const uint64_t *W, const cs_index_config_t *cfg);
 void cs_internal_set_error(int code, const char *msg);
 
 namespace {
@@ -258,6 +258,9 @@ cudaError_t sort_pairs(void *&tmp, size_t &tmp_bytes, const K *kin, K *kout, con
 } // namespace
 
 extern "C" cs_index_t *cs_index_build(const uint8_t *fwd, uint64_t l_pac, int device, int sa_intv)
+{ return cs_index_build_ex(fwd, l_pac, device, sa_intv, nullptr); }
+
+extern "C" cs_index_t *cs_index_build_ex(const uint8_t *fwd, uint64_t l_pac, int device, int sa_intv, const cs_index_config_t *cfg)
 {
 	const uint64_t n = 2 * l_pac;
 	int n_dev = 0, n_sm = 0, sa_shift = 0;
@@ -483,7 +486,7 @@ extern "C" cs_index_t *cs_index_build(const uint8_t *fwd, uint64_t l_pac, int de
 		BCK(cudaGetLastError());
 	}
 	BCK(cudaDeviceSynchronize());
-	idx = cs_index_adopt(device, buckets, n_buckets, d_sa, n_sa, sa_intv, primary, L2, n, W);
+	idx = cs_index_adopt(device, buckets, n_buckets, d_sa, n_sa, sa_intv, primary, L2, n, W, cfg);
 	buckets = nullptr; d_sa = nullptr;
 fail:
 	cudaFree(d_fwd); cudaFree(W); cudaFree(safull); cudaFree(d_small); cudaFree(keys_in); cudaFree(keys_out); cudaFree(vals_out);

@@ -1,0 +1,25 @@
+// Private to the library: the index handle and the error helpers shared by cs_api.cu, cs_verify.cu and cs_multi.cu.
+#pragma once
+#include <cstdarg>
+#include "cs_kernels.cuh"
+
+struct cs_index {
+	int device;
+	DevIndex d;
+	uint4 *d_buckets;
+	uint64_t *d_sa;
+	uint4 *d_kt;            // top-of-search table (depths 1..d.kt_depth)
+	uint32_t *d_pt;         // occurrence filter (2-bit counts of all d.pt_k-mers)
+	uint64_t *d_text, *d_isa; // unique-match fast path: 2-bit text and sampled inverse SA
+	uint64_t bytes;
+	uint64_t bwt_size_ref;  // words of the reference layout
+	int sa_intv;
+	int n_sm;
+	cs_index_config_t cfg;
+};
+
+int cs_set_err(int code, const char *fmt, ...);
+int cs_use_device(int device);
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	cs_set_err(CS_E_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); goto fail; } } while (0)

@@ -382,6 +382,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 	const bool can_spec = CS_SPEC && utext && prune_k > 0 && (int)I.kt_depth >= 2 && (int)I.kt_depth < prune_k && a.defer_q == nullptr;
 
 	uint32_t n_ext = 0, n_call = 0, n_two = 0, n_probe = 0, ext_mark = 0;
+	uint32_t n_req = 0;                                   // executed gathers besides Occ sectors and filter words (table, SA, inverse SA, text)
 #ifdef CS_STATS
 	uint32_t sst[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -513,7 +514,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 		uint64_t jj = (p + smask) & ~smask;
 		if (jj > I.seq_len) jj = I.seq_len;
 		row = jj == I.seq_len ? 0ull : gather_u64(I.isa + (jj >> I.isa_shift));   // the '$' suffix is row 0
-		steps = (int)(jj - p);
+		steps = (int)(jj - p); ++n_req;
 	};
 
 	for (;;) {
@@ -613,9 +614,9 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 			} break;
 			case ST_READ_DONE: {
 				uint32_t cnt = nmem;
-				if (err_mem || err_list) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
+				if (err_mem || err_list) { cnt = 0; atomicMin(a.error, CS_E_READ_OVERFLOW); }
 				unsigned long long o = atomicAdd(a.pool_used, (unsigned long long)cnt);
-				if (o + cnt > a.pool_cap) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
+				if (o + cnt > a.pool_cap) { cnt = 0; atomicMin(a.error, CS_E_OVERFLOW); }
 				if (a.defer_q) { a.x_off[cur_q] = o; a.x_n[cur_q] = cnt; }
 				else { a.read_pool_off[rd] = o; a.read_n_mems[rd] = cnt; }
 				const uint4 *src = reinterpret_cast<const uint4*>(my);
@@ -677,9 +678,10 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 			bool fin = false;
 			STAT(3); if (st == ST_TXT_CMP) STAT(15); if (st == ST_ROW_LF) STAT(11);
 			if (st == ST_TXT_SA) {
-				tpos = gather_u64(I.sa + c0) + (uint64_t)(i - x);
+				tpos = gather_u64(I.sa + c0) + (uint64_t)(i - x); ++n_req;
 				j = 0; st = ST_TXT_CMP;
 			} else if (st == ST_TXT_CMP) {
+				n_req += 1u + ((tpos & 31) != 0);
 				const uint64_t diff = read_window(i) ^ packed_window(I.text, tpos);
 				const uint32_t nmw = nmask_window(i);
 				uint32_t m = diff ? (uint32_t)(__ffsll((long long)diff) - 1) >> 1 : 32u;
@@ -700,7 +702,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 					}
 				}
 			} else if (st == ST_BTX_SA) {
-				tpos = gather_u64(I.sa + c0);
+				tpos = gather_u64(I.sa + c0); ++n_req;
 				j = 0; rowm = 0; st = ST_BTX_CMP;
 			} else if (st == ST_BTX_CMP) {
 				uint32_t cnt = 32, m = 0;
@@ -708,6 +710,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				if (tpos < cnt) cnt = (uint32_t)tpos;
 				if (cnt) { // the cnt bases q[bi-cnt+1 .. bi] against the cnt text bases before tpos, compared from the top
 					const int sr = bi + 1 - (int)cnt;
+					n_req += 1u + (((tpos - cnt) & 31) != 0);
 					const uint64_t diff = (read_window(sr) ^ packed_window(I.text, tpos - cnt)) << (2 * (32 - cnt));
 					const uint32_t nmw = nmask_window(sr) << (32 - cnt);
 					m = diff ? (uint32_t)__clzll((long long)diff) >> 1 : 32u;
@@ -753,8 +756,8 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				w = w0 | (w1 << 8);
 				if (w == 0) fin = true; else st = ST_ROW_LF;
 			} else { // ST_ROW_LF: one LF step (row of the preceding suffix) on each coordinate still walking
-				if (w & 0xff) { c0 = dev_lf(I, c0); w -= 1; }
-				if (w >> 8) { c1 = dev_lf(I, c1); w -= 256; }
+				if (w & 0xff) { c0 = dev_lf(I, c0); w -= 1; ++n_req; }
+				if (w >> 8) { c1 = dev_lf(I, c1); w -= 256; ++n_req; }
 				if (w == 0) fin = true;
 			}
 			if (fin) {
@@ -778,7 +781,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 			const int s_beg = is_back ? bi : x;
 			const int new_len = is_back ? (int)cend - bi : i + 1 - x;
 			++n_ext;
-			if (new_len <= (int)I.kt_depth) { kt_lookup(I, (uint32_t)new_len, key_of(t, pw, s_beg, new_len), o0, o1, o2); STAT(1); }
+			if (new_len <= (int)I.kt_depth) { kt_lookup(I, (uint32_t)new_len, key_of(t, pw, s_beg, new_len), o0, o1, o2); ++n_req; STAT(1); }
 			else { uint32_t two; dev_extend(I, c0, c1, c2, c, is_back, o0, o1, o2, two); ++n_call; n_two += two; STAT(2); }
 		}
 
@@ -819,6 +822,8 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 	if (n_call) atomicAdd(a.counters + 1, (unsigned long long)n_call);
 	if (n_two) atomicAdd(a.counters + 2, (unsigned long long)n_two);
 	if (n_probe) atomicAdd(a.counters + 3, (unsigned long long)n_probe);
+	n_req += n_call + n_two + n_probe;
+	if (n_req) atomicAdd(a.req + 2, (unsigned long long)n_req);
 #ifdef CS_STATS
 	for (int k = 0; k < 16; ++k) if (sst[k]) atomicAdd(a.counters + 4 + k, (unsigned long long)sst[k]);
 #endif
@@ -892,6 +897,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 
 	uint32_t n_ext = 0, n_call = 0, n_two = 0, n_probe = 0;
 	uint32_t r_ext = 0, r_call = 0;                        // of the call in flight: counted only if it is not deferred
+	uint32_t n_req = 0;                                    // EXECUTED gathers other than filter words (Occ sectors, table, SA, inverse SA, text), deferred calls included
 #ifdef CS_STATS
 	uint32_t sst[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -927,7 +933,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		uint64_t jj = (p + smask) & ~smask;
 		if (jj > I.seq_len) jj = I.seq_len;
 		row = jj == I.seq_len ? 0ull : gather_u64(I.isa + (jj >> I.isa_shift));
-		steps = (int)(jj - p);
+		steps = (int)(jj - p); ++n_req;
 	};
 	// hand the call (pivot, min_intv) of the read in flight to the literal kernel; the queue slot is taken at the top
 	// of the next iteration, for the whole warp at once
@@ -1004,7 +1010,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 				uint32_t cnt = finished ? nmem : 0;
 				const unsigned long long o = warp_alloc(a.pool_used, cnt);
 				if (finished) {
-					if (o + cnt > a.pool_cap) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
+					if (o + cnt > a.pool_cap) { cnt = 0; atomicMin(a.error, CS_E_OVERFLOW); }
 					a.read_pool_off[rd] = o; a.read_n_mems[rd] = cnt;
 					const uint4 *src = reinterpret_cast<const uint4*>(my);
 					uint4 *dst = reinterpret_cast<uint4*>(a.pool + o);
@@ -1060,7 +1066,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		bool unique = false;
 		if (!has_n(cx, kd)) { // q[cx, cx+kd) is inside the read and unambiguous: its table entry directly
 			uint64_t o0, o1, o2;
-			kt_lookup(I, (uint32_t)kd, key_of(cx, kd), o0, o1, o2);
+			kt_lookup(I, (uint32_t)kd, key_of(cx, kd), o0, o1, o2); ++n_req;
 			if (o2 >= cmin) { c0 = o0; c1 = o1; c2 = o2; i = cx + kd; r_ext += (uint32_t)(kd - 1); }
 		}
 		for (;;) {
@@ -1070,22 +1076,23 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			const int new_len = i + 1 - cx;
 			uint64_t o0, o1, o2;
 			++r_ext;
-			if (new_len <= kd) kt_lookup(I, (uint32_t)new_len, key_of(cx, new_len), o0, o1, o2);
-			else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - b, 0, o0, o1, o2, two); ++r_call; n_two += two; }
+			if (new_len <= kd) { kt_lookup(I, (uint32_t)new_len, key_of(cx, new_len), o0, o1, o2); ++n_req; }
+			else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - b, 0, o0, o1, o2, two); ++r_call; n_two += two; n_req += 1u + two; }
 			if (o2 < cmin) break;                                   // bwt.c:313: this extension fails, the match ends at i
 			c0 = o0; c1 = o1; c2 = o2; ++i;
 		}
 		// unique from here on: compare against the text at the occurrence, 32 bases per step
 		uint64_t tp0 = 0, bw0 = 0; int jf = 0; uint32_t cnt0 = 0;
 		if (unique) {
-			tp0 = gather_u64(I.sa + c0);                                 // text position of q[cx]
+			tp0 = gather_u64(I.sa + c0); ++n_req;                        // text position of q[cx]
 			// the text before the occurrence is wanted by the backward pass below: fetch its first window together with the forward one
 			cnt0 = 32; if ((uint32_t)cx < cnt0) cnt0 = (uint32_t)cx; if (tp0 < cnt0) cnt0 = (uint32_t)tp0;
-			if (cnt0) bw0 = packed_window(I.text, tp0 - cnt0);
+			if (cnt0) { bw0 = packed_window(I.text, tp0 - cnt0); n_req += 1u + (((tp0 - cnt0) & 31) != 0); }
 			uint64_t tpos = tp0 + (uint64_t)(i - cx);
 			for (;;) {
 				const uint64_t diff = read_window(i) ^ packed_window(I.text, tpos);
 				const uint32_t nmw = nmask_window(i);
+				n_req += 1u + ((tpos & 31) != 0);
 				uint32_t m = diff ? (uint32_t)(__ffsll((long long)diff) - 1) >> 1 : 32u;
 				const uint32_t nn = nmw ? (uint32_t)__ffs((int)nmw) - 1u : 32u;
 				const uint64_t left = I.seq_len - tpos;
@@ -1128,6 +1135,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			if (cnt) {
 				const int sr = bi + 1 - (int)cnt;
 				const uint64_t tw = first_w ? bw0 : packed_window(I.text, tb - cnt);   // (first window: cnt == cnt0)
+				if (!first_w) n_req += 1u + (((tb - cnt) & 31) != 0);
 				const uint64_t diff = (read_window(sr) ^ tw) << (2 * (32 - cnt));
 				const uint32_t nmw = nmask_window(sr) << (32 - cnt);
 				m = diff ? (uint32_t)__clzll((long long)diff) >> 1 : 32u;
@@ -1168,8 +1176,8 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			if (jb > 0) isa_near(tb, c0, w0);
 			if (jf > 0) isa_near(I.seq_len - tb - (uint64_t)(end - bi - 1), c1, w1);
 			while (w0 | w1) {
-				if (w0) { c0 = dev_lf(I, c0); --w0; }
-				if (w1) { c1 = dev_lf(I, c1); --w1; }
+				if (w0) { c0 = dev_lf(I, c0); --w0; ++n_req; }
+				if (w1) { c1 = dev_lf(I, c1); --w1; ++n_req; }
 			}
 		}
 		{
@@ -1183,6 +1191,8 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 	if (n_call) atomicAdd(a.counters + 1, (unsigned long long)n_call);
 	if (n_two) atomicAdd(a.counters + 2, (unsigned long long)n_two);
 	if (n_probe) atomicAdd(a.counters + 3, (unsigned long long)n_probe);
+	n_req += n_probe;
+	if (n_req) atomicAdd(a.req + 0, (unsigned long long)n_req);
 #ifdef CS_STATS
 	for (int k = 0; k < 16; ++k) if (sst[k]) atomicAdd(a.counters + 20 + k, (unsigned long long)sst[k]);
 #endif
@@ -1222,7 +1232,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 	cs_mem_t *const my = a.thread_mems + gtid * a.mem_cap;
 	const cs_seed_opt_t opt = a.opt;
 	const int kd = (int)I.kt_depth;
-	uint32_t n_ext = 0, n_call = 0, n_two = 0;
+	uint32_t n_ext = 0, n_call = 0, n_two = 0, n_req = 0;   // n_req: executed gathers (Occ sectors, table entries, filter words)
 	bool exhausted = false;
 
 	auto rd_word = [&](uint32_t wi) -> uint64_t { return s_rd[wi * CS_FAST_BLOCK + t]; };
@@ -1286,17 +1296,17 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 				e = 32 - __clz((int)bits);
 				bits &= ~(1u << (e - 1));
 				// the interval of q[cx, cx+e) ...
-				kt_lookup(I, (uint32_t)(e < kd ? e : kd), key_of(cx, e < kd ? e : kd), c0, c1, c2);
+				kt_lookup(I, (uint32_t)(e < kd ? e : kd), key_of(cx, e < kd ? e : kd), c0, c1, c2); ++n_req;
 				for (int k = kd; k < e; ++k) { // ... deeper than the table: forward bwt_extend steps
 					uint64_t o0, o1, o2; uint32_t two;
 					dev_extend(I, c0, c1, c2, 3 - base_at(cx + k), 0, o0, o1, o2, two);
-					c0 = o0; c1 = o1; c2 = o2; ++t_call; n_two += two;
+					c0 = o0; c1 = o1; c2 = o2; ++t_call; n_two += two; n_req += 1u + two;
 				}
 				go = true;
 				if (e < d) { // pushed only if the next forward step changed the size (bwt.c:311-312)
 					uint64_t o0, o1, o2;
-					if (e + 1 <= kd) kt_lookup(I, (uint32_t)(e + 1), key_of(cx, e + 1), o0, o1, o2);
-					else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - base_at(cx + e), 0, o0, o1, o2, two); ++t_call; n_two += two; }
+					if (e + 1 <= kd) { kt_lookup(I, (uint32_t)(e + 1), key_of(cx, e + 1), o0, o1, o2); ++n_req; }
+					else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - base_at(cx + e), 0, o0, o1, o2, two); ++t_call; n_two += two; n_req += 1u + two; }
 					if (o2 == c2) go = false;
 				}
 			}
@@ -1312,8 +1322,8 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 						const int new_len = cx + e - bi;
 						uint64_t o0, o1, o2;
 						++t_ext;
-						if (new_len <= kd) kt_lookup(I, (uint32_t)new_len, key_of(bi, new_len), o0, o1, o2);
-						else { uint32_t two; dev_extend(I, c0, c1, c2, b, 1, o0, o1, o2, two); ++t_call; n_two += two; }
+						if (new_len <= kd) { kt_lookup(I, (uint32_t)new_len, key_of(bi, new_len), o0, o1, o2); ++n_req; }
+						else { uint32_t two; dev_extend(I, c0, c1, c2, b, 1, o0, o1, o2, two); ++t_call; n_two += two; n_req += 1u + two; }
 						if (o2 < cmin) go = false;                      // bwt.c:331
 						else { c0 = o0; c1 = o1; c2 = o2; --bi; }
 					}
@@ -1342,6 +1352,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 						if (sh) nmw |= nm_word(wi + 1) << (32 - sh);
 						const uint64_t key = key_of(bi, K);
 						const bool absent = !(nmw & ((1u << K) - 1u)) && ((gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) == 0;
+						++n_req;
 						if (absent) bits = shallow;                     // else every entry is walked
 					}
 					if (__popc(bits) > CS_WALK_MAX) punt = true;        // too many for one lane: the literal kernel takes the call
@@ -1371,7 +1382,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 			uint32_t cnt = fin ? nm : 0;
 			const unsigned long long o = warp_alloc(a.pool_used, cnt);
 			if (fin) {
-				if (o + cnt > a.pool_cap) { cnt = 0; atomicExch(a.error, CS_E_OVERFLOW); }
+				if (o + cnt > a.pool_cap) { cnt = 0; atomicMin(a.error, CS_E_OVERFLOW); }
 				a.x_off[q] = o; a.x_n[q] = cnt;
 				const uint4 *src = reinterpret_cast<const uint4*>(my);
 				uint4 *dst = reinterpret_cast<uint4*>(a.pool + o);
@@ -1382,6 +1393,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 	if (n_ext) atomicAdd(a.counters + 0, (unsigned long long)n_ext);
 	if (n_call) atomicAdd(a.counters + 1, (unsigned long long)n_call);
 	if (n_two) atomicAdd(a.counters + 2, (unsigned long long)n_two);
+	if (n_req) atomicAdd(a.req + 1, (unsigned long long)n_req);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1394,7 +1406,7 @@ __global__ void __launch_bounds__(256, 4) k_seed_r3(DevIndex I, SeedArgs a)
 {
 	const cs_seed_opt_t opt = a.opt;
 	const uint32_t kp1 = (uint32_t)opt.min_seed_len + 1;
-	unsigned long long n_ext = 0, n_call = 0;
+	unsigned long long n_ext = 0, n_call = 0, n_req = 0;
 	bool idle = false, need = false;
 	uint32_t rd = 0, nmem = 0; int len = 0, x = 0, i = 0, c = 0;
 	const uint8_t *q = nullptr;
@@ -1422,7 +1434,7 @@ __global__ void __launch_bounds__(256, 4) k_seed_r3(DevIndex I, SeedArgs a)
 				if (x >= len) { a.r3_n_mems[rd] = nmem; have_read = false; continue; }
 				if (jump >= 2 && !read_has_n(pn, x, jump)) { // q[x..x+jump) is inside the read and unambiguous
 					kt_lookup(I, (uint32_t)jump, read_key(pw, x, jump), c0, c1, c2);
-					i = x + jump; n_ext += (unsigned)(jump - 1);
+					i = x + jump; n_ext += (unsigned)(jump - 1); ++n_req;
 				} else {
 					int b = q[x];
 					c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
@@ -1443,7 +1455,7 @@ __global__ void __launch_bounds__(256, 4) k_seed_r3(DevIndex I, SeedArgs a)
 		if (i + 1 < len) nb = q[i + 1];
 		uint64_t o0, o1, o2; uint32_t two;
 		dev_extend(I, c0, c1, c2, c, 0, o0, o1, o2, two);
-		++n_ext; ++n_call;
+		++n_ext; ++n_call; n_req += 1u + two;
 		if (o2 < (uint64_t)opt.max_mem_intv && i - x >= opt.min_seed_len) { // bwt.c:370-374
 			if (o2 > 0) {
 				uint4 *p = reinterpret_cast<uint4*>(out + nmem);
@@ -1460,6 +1472,7 @@ __global__ void __launch_bounds__(256, 4) k_seed_r3(DevIndex I, SeedArgs a)
 	}
 	if (n_ext) atomicAdd(a.counters + 0, n_ext);
 	if (n_call) atomicAdd(a.counters + 1, n_call);
+	if (n_req) atomicAdd(a.req + 3, n_req);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1489,7 +1502,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 	const int K = (int)I.pt_k, kd = (int)I.kt_depth, W = opt.min_seed_len + 1;   // host guarantees K <= min_seed_len
 	const uint32_t kp1 = (uint32_t)W;
 	const int jump = kd < opt.min_seed_len ? kd : opt.min_seed_len;
-	uint32_t n_ext = 0, n_call = 0, n_probe = 0;
+	uint32_t n_ext = 0, n_call = 0, n_probe = 0, n_req = 0;
 	bool have = false, exhausted = false;
 	bool parked = false;                                      // this lane's chain needs the literal walk and waits for company
 	uint32_t rd = 0, nmem = 0, n12 = 0; int len = 0, x = 0;
@@ -1519,7 +1532,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 		uint64_t jj = (p + smask) & ~smask;
 		if (jj > I.seq_len) jj = I.seq_len;
 		row = jj == I.seq_len ? 0ull : gather_u64(I.isa + (jj >> I.isa_shift));
-		steps = (int)(jj - p);
+		steps = (int)(jj - p); ++n_req;
 	};
 	auto put = [&](uint64_t x0, uint64_t x1, uint64_t x2, int start, int end) {
 		uint4 *p = reinterpret_cast<uint4*>(out + nmem);
@@ -1584,7 +1597,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 						const uint4 v = reinterpret_cast<const uint4*>(pool12 + m)[1];   // x[2] lo, hi, end, start
 						if (v.x == 1 && v.y == 0 && (int)v.w <= x && x + W <= (int)v.z) {
 							ms = (int)v.w; me = (int)v.z;
-							mtb = gather_u64(I.sa + pool12[m].x[0]);
+							mtb = gather_u64(I.sa + pool12[m].x[0]); ++n_req;
 							break;
 						}
 					}
@@ -1603,8 +1616,8 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 				isa_near(I.seq_len - P - (uint64_t)W, r1, w1);
 			}
 			while (__any_sync(0xffffffffu, (w0 | w1) != 0)) {
-				if (w0) { r0 = dev_lf(I, r0); --w0; }
-				if (w1) { r1 = dev_lf(I, r1); --w1; }
+				if (w0) { r0 = dev_lf(I, r0); --w0; ++n_req; }
+				if (w1) { r1 = dev_lf(I, r1); --w1; ++n_req; }
 			}
 			if (from_text) {
 				put(r0, r1, 1, x, x + W);
@@ -1626,7 +1639,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 			uint64_t c0, c1, c2; int i;
 			if (jump >= 2 && x + jump <= len && !(nmask_window(x) & ((1u << jump) - 1u))) {
 				kt_lookup(I, (uint32_t)jump, key_of(x, jump), c0, c1, c2);
-				i = x + jump; n_ext += (uint32_t)(jump - 1);
+				i = x + jump; n_ext += (uint32_t)(jump - 1); ++n_req;
 			} else {
 				const int b = base_at(x);
 				c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);
@@ -1642,7 +1655,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 					++i; continue;
 				}
 				uint64_t o0, o1, o2; uint32_t two;
-				dev_extend(I, c0, c1, c2, 3 - b, 0, o0, o1, o2, two); ++n_call;
+				dev_extend(I, c0, c1, c2, 3 - b, 0, o0, o1, o2, two); ++n_call; n_req += 1u + two;
 				if (o2 < (uint64_t)opt.max_mem_intv && i - x >= opt.min_seed_len) {
 					if (o2 > 0) put(o0, o1, o2, x, i + 1);
 					x = i + 1; break;
@@ -1654,6 +1667,8 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 	if (n_ext) atomicAdd(a.counters + 0, (unsigned long long)n_ext);
 	if (n_call) atomicAdd(a.counters + 1, (unsigned long long)n_call);
 	if (n_probe) atomicAdd(a.counters + 3, (unsigned long long)n_probe);
+	n_req += n_probe;
+	if (n_req) atomicAdd(a.req + 3, (unsigned long long)n_req);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1672,6 +1687,7 @@ __global__ void k_collect_sort(CollectArgs a)
 	const unsigned gmask = 0xffu << (lane & 24);
 	const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
 	const uint32_t kp1 = (uint32_t)a.opt.min_seed_len + 1;
+	unsigned long long seeds_total = 0;
 	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < a.n_reads; r += ngroups) {
 		const uint32_t n12 = a.read_n_mems[r];                 // passes 1-2 (k_seed_fast, or k_seed alone)
 		const uint32_t n3 = a.r3_n_mems ? a.r3_n_mems[r] : 0;  // pass 3 (k_seed_r3)
@@ -1680,8 +1696,15 @@ __global__ void k_collect_sort(CollectArgs a)
 		const cs_mem_t *src3 = a.r3_mems + ((uint64_t)(a.off[r] / kp1) + r);
 		cs_mem_t *dst = a.mems + a.mem_off[r];
 		uint32_t n_seeds = 0;
-		if ((uint64_t)a.mem_off[r] + n > a.mems_cap) { // result buffer too small: report, never write past it
-			if (sub == 0) { atomicExch(a.error, CS_E_OVERFLOW); a.read_n_seeds[r] = 0; }
+		if ((uint64_t)a.mem_off[r] + n > a.mems_cap) { // result buffer too small: report, never write past it -- but still count the
+			auto count = [&](const cs_mem_t *src, uint32_t cnt) { // seeds, so that cs_ctx_need can tell the caller both capacities at once
+				for (uint32_t m = sub; m < cnt; m += 8) seeds_total += seeds_of(src[m].x[2], a.opt.max_occ);
+			};
+			count(src12, n12);
+			if (a.read_last_q)
+				for (uint32_t q = a.read_last_q[r]; q != 0xffffffffu; q = a.defer_q[q].w) count(a.pool + a.x_off[q], a.x_n[q]);
+			count(src3, n3);
+			if (sub == 0) { atomicMin(a.error, CS_E_OVERFLOW); a.read_n_seeds[r] = 0; }
 			continue;
 		}
 		const cs_mem_t *all = src12;                           // the read's mems, unsorted, in one place
@@ -1715,20 +1738,29 @@ __global__ void k_collect_sort(CollectArgs a)
 			n_seeds += seeds_of((uint64_t)v1.x | ((uint64_t)v1.y << 32), a.opt.max_occ);
 		}
 		for (int sft = 4; sft > 0; sft >>= 1) n_seeds += __shfl_xor_sync(gmask, n_seeds, sft);
-		if (sub == 0) a.read_n_seeds[r] = n_seeds;
+		if (sub == 0) { a.read_n_seeds[r] = n_seeds; seeds_total += n_seeds; }
 	}
+	for (int sft = 16; sft > 0; sft >>= 1) seeds_total += __shfl_xor_sync(0xffffffffu, seeds_total, sft);
+	if (lane == 0 && seeds_total) atomicAdd(a.tot_seeds, seeds_total);
 }
 
-// total mems per read (passes 1-2 + pass 3), the input of the offsets scan
+// total mems per read (passes 1-2 + pass 3), the input of the offsets scan; the batch totals are also summed in 64 bits
+// (tot12: passes 1-2 incl. deferred calls, tot3: pass 3) so that a total past 2^32 -- where the u32 scan would wrap --
+// is reported as an overflow instead of passing the capacity checks
 __global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, const uint32_t *read_last_q, const uint4 *defer_q, const uint32_t *x_n,
-                             uint32_t n_reads, uint32_t *out)
+                             uint32_t n_reads, uint32_t *out, unsigned long long *tot12, unsigned long long *tot3)
 {
+	unsigned long long s12 = 0, s3 = 0;
 	for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) {
-		uint32_t n = n12[r] + (n3 ? n3[r] : 0);
+		uint32_t n = n12[r];
 		if (read_last_q)
 			for (uint32_t q = read_last_q[r]; q != 0xffffffffu; q = defer_q[q].w) n += x_n[q];
-		out[r] = n;
+		const uint32_t m3 = n3 ? n3[r] : 0;
+		s12 += n; s3 += m3;
+		out[r] = n + m3;
 	}
+	for (int sft = 16; sft > 0; sft >>= 1) { s12 += __shfl_xor_sync(0xffffffffu, s12, sft); s3 += __shfl_xor_sync(0xffffffffu, s3, sft); }
+	if ((threadIdx.x & 31) == 0) { if (s12) atomicAdd(tot12, s12); if (s3) atomicAdd(tot3, s3); }
 }
 
 __global__ void k_collect_rows(CollectArgs a)
@@ -1740,7 +1772,7 @@ __global__ void k_collect_rows(CollectArgs a)
 		const cs_mem_t *mem = a.mems + a.mem_off[r];
 		uint64_t o = a.seed_off[r];
 		if ((uint64_t)a.seed_off[r + 1] > a.seed_cap || (uint64_t)a.mem_off[r + 1] > a.mems_cap) {
-			if (sub == 0) atomicExch(a.error, CS_E_OVERFLOW);
+			if (sub == 0) atomicMin(a.error, CS_E_OVERFLOW);
 			continue;
 		}
 		for (uint32_t m = 0; m < n; ++m) {

@@ -59,7 +59,8 @@ struct SeedArgs {
 	cs_mem_t *r3_mems;          // third-pass seeds of read r at [off[r]/(k+1) + r ...]
 	uint32_t *r3_n_mems;        // [n_reads]
 	unsigned long long *counters; // [0] ext queries [1] ext calls (bucket path) [2] two-sector extends [3] occurrence-filter probes
-	int *error;                 // sticky CS_E_* code
+	unsigned long long *req;    // executed memory requests: [0] k_seed_fast [1] k_seed_walk [2] k_seed [3] third-pass kernel
+	int *error;                 // sticky CS_E_* code (atomicMin: the per-read code CS_E_READ_OVERFLOW wins over CS_E_OVERFLOW)
 };
 
 struct CollectArgs {
@@ -83,6 +84,7 @@ struct CollectArgs {
 	const uint32_t *seed_off;   // exclusive scan of read_n_seeds (for pass 2)
 	uint64_t *seed_rows;        // [n_seeds] SA rows in emission order (pass 2), resolved in place by k_sa_resolve
 	uint64_t seed_cap;
+	unsigned long long *tot_seeds;  // 64-bit total of read_n_seeds (the u32 offsets scan could wrap silently)
 	int *error;
 };
 
@@ -107,7 +109,7 @@ __global__ void k_seed_walk(DevIndex I, SeedArgs a);
 __global__ void k_seed_r3_fast(DevIndex I, SeedArgs a);
 __global__ void k_seed_r3(DevIndex I, SeedArgs a);
 __global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, const uint32_t *read_last_q, const uint4 *defer_q, const uint32_t *x_n,
-                             uint32_t n_reads, uint32_t *out);
+                             uint32_t n_reads, uint32_t *out, unsigned long long *tot12, unsigned long long *tot3);
 __global__ void k_collect_sort(CollectArgs a);
 __global__ void k_collect_rows(CollectArgs a);
 __global__ void k_gather_probe(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed, unsigned long long *sink);

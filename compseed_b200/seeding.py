@@ -25,7 +25,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _TAG = os.environ.get("COMPSEED_LIB_TAG", "")
 LIB_PATH = os.path.join(_HERE, "_lib", f"libcompseed_b200{('_' + _TAG) if _TAG else ''}.so")
 
-CS_OK, CS_E_ARG, CS_E_CUDA, CS_E_OVERFLOW, CS_E_IO, CS_E_NODEVICE, CS_E_STATE = 0, -1, -2, -3, -4, -5, -6
+CS_OK, CS_E_ARG, CS_E_CUDA, CS_E_OVERFLOW, CS_E_IO, CS_E_NODEVICE, CS_E_STATE, CS_E_READ_OVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7
 
 
 class CompSeedError(RuntimeError):
@@ -52,7 +52,44 @@ class _Result(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_mems", C.c_uint64), ("n_seeds", C.c_uint64),
                 ("mem_off", C.POINTER(C.c_uint32)), ("mems", C.POINTER(C.c_uint64)),
                 ("seed_off", C.POINTER(C.c_uint32)), ("rbeg", C.POINTER(C.c_int64)),
-                ("counters", _Counters), ("kernel_ms", C.c_float * 8), ("n_deferred", C.c_uint64)]
+                ("counters", _Counters), ("kernel_ms", C.c_float * 8), ("n_deferred", C.c_uint64),
+                ("gather_requests", C.c_uint64 * 6), ("kernel_ms2", C.c_float * 4)]
+
+
+class _IndexConfig(C.Structure):
+    _fields_ = [("kmer_table_depth", C.c_int32), ("prune_k", C.c_int32), ("isa_intv", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _CtxConfig(C.Structure):
+    _fields_ = [("use_fast", C.c_int32), ("use_r3_fast", C.c_int32), ("defer_cap", C.c_int32), ("lit_ctas_per_sm", C.c_int32),
+                ("prefetch_results", C.c_int32), ("l2_persist_mb", C.c_int32), ("overlap_streams", C.c_int32), ("reserved", C.c_int32)]
+
+
+@dataclass
+class IndexConfig:
+    """cs_index_config_t: the result-neutral structures built next to the index (-1 = default for the index size)."""
+    kmer_table_depth: int = -1
+    prune_k: int = -1
+    isa_intv: int = -1
+
+    def _c(self) -> _IndexConfig:
+        return _IndexConfig(self.kmer_table_depth, self.prune_k, self.isa_intv, 0)
+
+
+@dataclass
+class CtxConfig:
+    """cs_ctx_config_t: execution switches of a context (none of them changes a result)."""
+    use_fast: int = -1
+    use_r3_fast: int = -1
+    defer_cap: int = -1
+    lit_ctas_per_sm: int = -1
+    prefetch_results: int = 0
+    l2_persist_mb: int = 0
+    overlap_streams: int = -1
+
+    def _c(self) -> _CtxConfig:
+        return _CtxConfig(self.use_fast, self.use_r3_fast, self.defer_cap, self.lit_ctas_per_sm, self.prefetch_results,
+                          self.l2_persist_mb, self.overlap_streams, 0)
 
 
 _lib = None
@@ -75,6 +112,20 @@ def load_library():
     L.cs_index_load.argtypes = [C.c_char_p, C.c_int, C.c_int]
     L.cs_index_build.restype = C.c_void_p
     L.cs_index_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+    L.cs_index_upload_ex.restype = C.c_void_p
+    L.cs_index_upload_ex.argtypes = [C.POINTER(_BwtView), C.c_int, C.c_int, C.POINTER(_IndexConfig)]
+    L.cs_index_load_ex.restype = C.c_void_p
+    L.cs_index_load_ex.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(_IndexConfig)]
+    L.cs_index_build_ex.restype = C.c_void_p
+    L.cs_index_build_ex.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(_IndexConfig)]
+    L.cs_index_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.cs_index_verify.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+    L.cs_probe_index_gather.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.cs_ctx_create_ex.restype = C.c_void_p
+    L.cs_ctx_create_ex.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(_CtxConfig)]
+    L.cs_ctx_need.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.cs_ctx_launches.restype = C.c_uint64
+    L.cs_ctx_launches.argtypes = [C.c_void_p]
     L.cs_index_download.argtypes = [C.c_void_p, C.POINTER(_BwtView), C.c_void_p, C.c_void_p, C.c_int]
     L.cs_index_info.argtypes = [C.c_void_p, C.POINTER(_BwtView), C.POINTER(C.c_uint64)]
     L.cs_index_free.argtypes = [C.c_void_p]
@@ -87,6 +138,7 @@ def load_library():
     L.cs_seed_batch_submit.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(_SeedOpt)]
     L.cs_seed_batch_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Result)]
     L.cs_seed_batch_submit_packed.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SeedOpt)]
+    L.cs_pack_reads_host.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.cs_packed_words.argtypes = [C.c_uint32, C.c_void_p]
     L.cs_packed_words.restype = C.c_uint64
     L.cs_seed_batch_stage.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -145,6 +197,8 @@ class SeedResult:
     rbeg: np.ndarray         # i64 [n_seeds]
     counters: dict = field(default_factory=dict)
     kernel_ms: tuple = (0.0,) * 8
+    gather_requests: tuple = (0,) * 6   # executed memory requests per kernel (cs_result_t.gather_requests)
+    kernel_ms2: tuple = (0.0,) * 4
 
     @property
     def n_reads(self) -> int:
@@ -169,7 +223,7 @@ class FMIndex:
 
     @classmethod
     def upload(cls, primary: int, L2, seq_len: int, bwt: np.ndarray, sa: np.ndarray, sa_intv: int,
-               device: int = 0, dense_sa_intv: int = 0) -> "FMIndex":
+               device: int = 0, dense_sa_intv: int = 0, config: "IndexConfig | None" = None) -> "FMIndex":
         """From arrays in the reference's in-memory layout (what bwt_restore_bwt/sa produce)."""
         bwt = np.ascontiguousarray(bwt, dtype=np.uint32)
         sa = np.ascontiguousarray(sa, dtype=np.uint64)
@@ -178,18 +232,44 @@ class FMIndex:
         for i in range(5):
             v.L2[i] = int(L2[i])
         v.bwt, v.sa_intv, v.n_sa, v.sa = _ptr(bwt), int(sa_intv), int(sa.shape[0]), _ptr(sa)
-        return cls(load_library().cs_index_upload(C.byref(v), device, dense_sa_intv), device)
+        cfg = (config or IndexConfig())._c()
+        return cls(load_library().cs_index_upload_ex(C.byref(v), device, dense_sa_intv, C.byref(cfg)), device)
 
     @classmethod
-    def load(cls, prefix: str, device: int = 0, dense_sa_intv: int = 0) -> "FMIndex":
+    def load(cls, prefix: str, device: int = 0, dense_sa_intv: int = 0, config: "IndexConfig | None" = None) -> "FMIndex":
         """From P.bwt / P.sa written by bwaidx (bwt_restore_bwt / bwt_restore_sa, bwt.c:421-462)."""
-        return cls(load_library().cs_index_load(prefix.encode(), device, dense_sa_intv), device)
+        cfg = (config or IndexConfig())._c()
+        return cls(load_library().cs_index_load_ex(prefix.encode(), device, dense_sa_intv, C.byref(cfg)), device)
 
     @classmethod
-    def build(cls, fwd: np.ndarray, device: int = 0, sa_intv: int = 32) -> "FMIndex":
+    def build(cls, fwd: np.ndarray, device: int = 0, sa_intv: int = 32, config: "IndexConfig | None" = None) -> "FMIndex":
         """Construct the index of fwd + revcomp(fwd) on the GPU (what bwaidx computes on the CPU)."""
         fwd = np.ascontiguousarray(fwd, dtype=np.uint8)
-        return cls(load_library().cs_index_build(_ptr(fwd), fwd.shape[0], device, sa_intv), device)
+        cfg = (config or IndexConfig())._c()
+        return cls(load_library().cs_index_build_ex(_ptr(fwd), fwd.shape[0], device, sa_intv, C.byref(cfg)), device)
+
+    def write(self, prefix: str, sa_intv: int = 32) -> None:
+        """P.bwt / P.sa in the reference's on-disk format (bwt_dump_bwt / bwt_dump_sa, bwt.c:385-407)."""
+        _check(load_library().cs_index_write(self.h, prefix.encode(), sa_intv))
+
+    VERIFY_FIELDS = ("order_rows", "order_bad", "bwt_rows", "bwt_bad", "perm_bad", "occ_bad", "isa_samples", "isa_bad",
+                     "filter_samples", "filter_bad", "table_samples", "table_bad", "text_bases", "text_bad")
+
+    def verify(self, fwd: np.ndarray | None = None, stride: int = 1) -> dict:
+        """cs_index_verify: the index checked against the definitions of its parts (needs the dense SA)."""
+        out = np.zeros(16, dtype=np.uint64)
+        if fwd is not None:
+            fwd = np.ascontiguousarray(fwd, dtype=np.uint8)
+        _check(load_library().cs_index_verify(self.h, _ptr(fwd) if fwd is not None else None, 0 if fwd is None else fwd.shape[0], stride, _ptr(out)))
+        d = {k: int(v) for k, v in zip(self.VERIFY_FIELDS, out)}
+        d["ok"] = all(d[k] == 0 for k in d if k.endswith("_bad")) and d["order_rows"] > 0
+        return d
+
+    def probe_gather(self, n_loads: int = 1 << 28, iters: int = 2, unroll: int = 4):
+        """(GB/s, Gloads/s) of random 32-byte sector loads over this index's own arrays (cs_probe_index_gather)."""
+        gb, gl = C.c_double(), C.c_double()
+        _check(load_library().cs_probe_index_gather(self.h, n_loads, iters, unroll, C.byref(gb), C.byref(gl)))
+        return gb.value, gl.value
 
     def download(self, sa_intv: int = 32):
         """Back to the reference layout: dict(primary, L2, seq_len, bwt, sa, sa_intv)."""
@@ -238,11 +318,12 @@ class SeedContext:
     replacement, bwamem.c:1343 / comp_seed.cpp:2541-2548)."""
 
     def __init__(self, index: FMIndex, max_reads: int, max_bases: int, max_read_len: int = 256,
-                 max_mems: int = 0, max_seeds: int = 0, n_slots: int = 2):
+                 max_mems: int = 0, max_seeds: int = 0, n_slots: int = 2, config: "CtxConfig | None" = None):
         self.index = index
         self.max_reads, self.max_bases, self.max_read_len = max_reads, max_bases, max_read_len
         self.n_slots = n_slots
-        h = load_library().cs_ctx_create(index.h, max_reads, max_bases, max_read_len, max_mems, max_seeds, n_slots)
+        cfg = (config or CtxConfig())._c()
+        h = load_library().cs_ctx_create_ex(index.h, max_reads, max_bases, max_read_len, max_mems, max_seeds, n_slots, C.byref(cfg))
         if not h:
             raise CompSeedError(CS_E_CUDA, load_library().cs_last_error().decode())
         self.h = C.c_void_p(h)
@@ -251,6 +332,17 @@ class SeedContext:
         if self.h:
             load_library().cs_ctx_free(self.h)
             self.h = None
+
+    def need(self, slot: int):
+        """After CS_E_OVERFLOW on `slot`: (max_mems, max_seeds) that batch needs (cs_ctx_need)."""
+        m, sd = C.c_uint64(), C.c_uint64()
+        _check(load_library().cs_ctx_need(self.h, slot, C.byref(m), C.byref(sd)))
+        return int(m.value), int(sd.value)
+
+    @property
+    def launches(self) -> int:
+        """Kernels launched on behalf of this context so far (cs_ctx_launches)."""
+        return int(load_library().cs_ctx_launches(self.h))
 
     def __del__(self):
         try:
@@ -313,9 +405,11 @@ class SeedContext:
                    sal_queries=int(r.counters.sal_queries), sal_calls=int(r.counters.sal_calls),
                    deferred_calls=int(r.n_deferred))
         ms = tuple(float(x) for x in r.kernel_ms)
+        gr = tuple(int(x) for x in r.gather_requests)
+        ms2 = tuple(float(x) for x in r.kernel_ms2)
         if not r.mem_off:  # device-resident result
             e = np.empty(0, dtype=np.uint32)
-            res = SeedResult(e, np.empty((0, 4), dtype=np.uint64), e, np.empty(0, dtype=np.int64), cnt, ms)
+            res = SeedResult(e, np.empty((0, 4), dtype=np.uint64), e, np.empty(0, dtype=np.int64), cnt, ms, gr, ms2)
             res.n_mems_device, res.n_seeds_device, res.n_reads_device = nm, ns, n
             return res
         mem_off = np.ctypeslib.as_array(r.mem_off, shape=(n + 1,))
@@ -324,7 +418,7 @@ class SeedContext:
         rbeg = np.ctypeslib.as_array(r.rbeg, shape=(ns,)) if ns else np.empty(0, dtype=np.int64)
         if copy:
             mem_off, seed_off, mems, rbeg = mem_off.copy(), seed_off.copy(), mems.copy(), rbeg.copy()
-        return SeedResult(mem_off, mems, seed_off, rbeg, cnt, ms)
+        return SeedResult(mem_off, mems, seed_off, rbeg, cnt, ms, gr, ms2)
 
 
 def packed_words(off: np.ndarray) -> int:
@@ -363,11 +457,24 @@ def pack_reads(bases: np.ndarray, off: np.ndarray):
     return packed, nmask
 
 
+def pack_reads_host(bases: np.ndarray, off: np.ndarray, n_threads: int = 1):
+    """cs_pack_reads_host: the same layout as pack_reads, packed by the library's host-side C++ (no device involved)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint32)
+    nw = packed_words(off)
+    packed = np.empty(nw, dtype=np.uint64)
+    nmask = np.empty(nw, dtype=np.uint32)
+    _check(load_library().cs_pack_reads_host(off.shape[0] - 1, _ptr(bases), _ptr(off), _ptr(packed), _ptr(nmask), n_threads))
+    return packed, nmask
+
+
 def seed_reads(index: FMIndex, bases, off, opt: SeedOpt | None = None, batch_reads: int = 1 << 19,
-               n_slots: int = 2, max_mems_per_read: int = 16, max_seeds_per_read: int = 32) -> SeedResult:
+               n_slots: int = 2, max_mems_per_read: int = 16, max_seeds_per_read: int = 32,
+               config: "CtxConfig | None" = None) -> SeedResult:
     """Seed a whole read set: contiguous batches pipelined through the slots of one context
     (batch i+1 is submitted before batch i is waited on), results concatenated in input order.
-    On CS_E_OVERFLOW the context is re-created with doubled result capacities and the set is redone."""
+    On CS_E_OVERFLOW the context is re-created with the capacities cs_ctx_need reports and the set is redone;
+    CS_E_READ_OVERFLOW (one read beyond the per-read scratch) is raised: larger buffers cannot fix it."""
     opt = opt or SeedOpt()
     bases = np.ascontiguousarray(bases, dtype=np.uint8)
     off = np.ascontiguousarray(off, dtype=np.uint32)
@@ -379,9 +486,9 @@ def seed_reads(index: FMIndex, bases, off, opt: SeedOpt | None = None, batch_rea
     max_len = max(1, int(lens.max()))
     starts = list(range(0, n, batch_reads))
     max_b = max(int(off[min(n, s + batch_reads)]) - int(off[s]) for s in starts)
+    cap_m, cap_s = min(batch_reads, n) * max_mems_per_read, min(batch_reads, n) * max_seeds_per_read
     while True:
-        ctx = SeedContext(index, min(batch_reads, n), max(1, max_b), max_len,
-                          min(batch_reads, n) * max_mems_per_read, min(batch_reads, n) * max_seeds_per_read, n_slots)
+        ctx = SeedContext(index, min(batch_reads, n), max(1, max_b), max_len, cap_m, cap_s, n_slots, config)
         try:
             parts: list[SeedResult] = []
             inflight: list[int] = []
@@ -398,17 +505,20 @@ def seed_reads(index: FMIndex, bases, off, opt: SeedOpt | None = None, batch_rea
                 _submit(nxt)
                 nxt += 1
             while inflight:
-                bi = inflight.pop(0)
+                bi = inflight[0]
                 parts.append(ctx.wait(bi % n_slots))
+                inflight.pop(0)
                 if nxt < len(starts):
                     _submit(nxt)
                     nxt += 1
             break
         except CompSeedError as e:
-            if e.code != CS_E_OVERFLOW or max_seeds_per_read > (1 << 16):
+            if e.code != CS_E_OVERFLOW or not inflight:
                 raise
-            max_mems_per_read *= 4
-            max_seeds_per_read *= 8
+            need_m, need_s = ctx.need(inflight[0] % n_slots)
+            if (need_m <= cap_m and need_s <= cap_s) or need_m >= (1 << 32) or need_s >= (1 << 32):
+                raise
+            cap_m, cap_s = max(cap_m, need_m), max(cap_s, need_s)
         finally:
             ctx.close()
     return concat_results(parts)

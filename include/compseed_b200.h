@@ -43,6 +43,9 @@ extern "C" {
 #define CS_E_IO         -4   /* index file could not be read */
 #define CS_E_NODEVICE   -5   /* no CUDA device: this library has no CPU path */
 #define CS_E_STATE      -6   /* slot used out of order (wait without submit, submit on a busy slot) */
+#define CS_E_READ_OVERFLOW -7 /* ONE read needs more mems / interval-list entries than the per-read scratch of the ctx holds
+                                (max_read_len fixes it: 2*max_read_len+16 mems, max_read_len list entries); larger max_mems /
+                                max_seeds do not help -- unlike CS_E_OVERFLOW, where cs_ctx_need says how much would */
 
 /* The fields of bwt_t that the seeding path reads (FM_index/bwt.h:48-60), in the reference's own
  * in-memory layout: bwt[] = 64-byte buckets (4 x u64 checkpoint + 8 x u32 of 16 bases, MSB first),
@@ -95,10 +98,42 @@ typedef struct {
 	                              k_seed_r3), [1] collect, [2] SA-resolve, [3] whole slot incl. copies, [4] passes 1-2 (k_pack_reads +
 	                              k_seed_fast + k_seed_walk + k_seed), [5] k_seed_r3 alone, [6] k_pack_reads + k_seed_fast, [7] k_seed_walk */
 	uint64_t n_deferred;       /* bwt_smem1a calls the fast kernel handed to the literal kernel */
+	/* EXECUTED memory requests (one per lane and load instruction that leaves the SM towards L2: Occ sectors, filter words,
+	 * table entries, SA / inverse-SA words, text words), counted in the kernels: [0] k_seed_fast, [1] k_seed_walk,
+	 * [2] k_seed, [3] the third-pass kernel, [4] k_sa_resolve, [5] unused.  The roofline of bench.py is built on these. */
+	uint64_t gather_requests[6];
+	float kernel_ms2[4];       /* [0] k_seed (literal) alone, [1] third-pass kernel alone (it overlaps k_seed_walk / k_seed on the slot's
+	                              second stream: kernel_ms[5] is then only what is left of it after k_seed), [2] k_pack_reads, [3] unused */
 } cs_result_t;
 
 typedef struct cs_index cs_index_t;
 typedef struct cs_ctx cs_ctx_t;
+
+/* Result-neutral structures built next to the index.  Every field: -1 = the default for this
+ * index size.  None of them changes a result; they are here so that a host (and the tests) can switch each one off. */
+typedef struct {
+	int32_t kmer_table_depth;  /* top-of-search table of every string of <= this many bases (default: up to 13); 0 = none */
+	int32_t prune_k;           /* K of the K-mer occurrence filter (default ceil(log4 seq_len)+2, at most 19); 0 = none */
+	int32_t isa_intv;          /* sampling of the inverse SA used by the unique-match paths (power of two, default 4); 0 = no
+	                              2-bit text / inverse SA (the fast kernels are then not used) */
+	int32_t reserved;
+} cs_index_config_t;
+void cs_index_config_default(cs_index_config_t *cfg);
+
+/* Execution switches of a ctx.  -1 / 0 as documented per field; none of them changes a result. */
+typedef struct {
+	int32_t use_fast;          /* 1 (default -1 = 1): k_seed_fast / k_seed_walk where the index allows; 0: the literal kernel alone */
+	int32_t use_r3_fast;       /* 1 (default): text-assisted third pass; 0: k_seed_r3 */
+	int32_t defer_cap;         /* capacity of the deferred-call queue (default -1: 2*max_reads + 4096); a batch that overflows it
+	                              is rerun through the literal kernel alone */
+	int32_t lit_ctas_per_sm;   /* cap on resident CTAs of the literal kernel in call mode (default -1: no cap) */
+	int32_t prefetch_results;  /* 1: result copies of finished slots are enqueued while the host waits on another (default 0) */
+	int32_t l2_persist_mb;     /* > 0: an L2 access-policy window (persisting) of this many MB over the top of the K-mer table on
+	                              every slot stream (default 0: none; profiles/ has the measurement) */
+	int32_t overlap_streams;   /* 1 (default): kernels of one batch that do not depend on each other run on forked streams */
+	int32_t reserved;
+} cs_ctx_config_t;
+void cs_ctx_config_default(cs_ctx_config_t *cfg);
 
 const char *cs_last_error(void);
 int cs_device_count(void);
@@ -109,11 +144,29 @@ int cs_device_count(void);
  * input; a power of two < sa_intv re-samples the suffix array on the device (bwt_sa(k) does not
  * depend on the sampling, FM_index/bwt.c:86-96), 1 = full suffix array. */
 cs_index_t *cs_index_upload(const cs_bwt_view_t *bwt, int device, int dense_sa_intv);
+cs_index_t *cs_index_upload_ex(const cs_bwt_view_t *bwt, int device, int dense_sa_intv, const cs_index_config_t *cfg /* NULL = defaults */);
 /* Reads P.bwt and P.sa exactly as bwt_restore_bwt / bwt_restore_sa do (FM_index/bwt.c:421-462). */
 cs_index_t *cs_index_load(const char *prefix, int device, int dense_sa_intv);
+cs_index_t *cs_index_load_ex(const char *prefix, int device, int dense_sa_intv, const cs_index_config_t *cfg);
+/* Writes P.bwt and P.sa exactly as bwt_dump_bwt / bwt_dump_sa do (FM_index/bwt.c:385-407), at sampling sa_intv (the
+ * reference writes 32): an index built by cs_index_build can be loaded by the reference's bwt_restore_bwt/sa. */
+int cs_index_write(const cs_index_t *idx, const char *prefix, int sa_intv);
 /* Builds the FM-index of fwd+revcomp(fwd) on the device (fwd: l_pac nt4 codes 0..3 in host memory).
  * Same BWT / Occ / SA as bwaidx (FM_index/index_main.c:257-325); the SA is kept at sa_intv rows. */
 cs_index_t *cs_index_build(const uint8_t *fwd, uint64_t l_pac, int device, int sa_intv);
+cs_index_t *cs_index_build_ex(const uint8_t *fwd, uint64_t l_pac, int device, int sa_intv, const cs_index_config_t *cfg);
+/* Self-check of a device index (any origin), by the definitions rather than by comparison with another builder:
+ *   out[0] rows checked for "suffix SA[r-1] < suffix SA[r]" through the 2-bit text, out[1] violations
+ *   out[2] rows checked for "BWT[r] == T[SA[r]-1]",                               out[3] violations
+ *   out[4] text positions hit twice or never by SA (permutation test, full),      out[5] Occ checkpoints that are not
+ *          the running base counts of the BWT / L2 / primary inconsistencies
+ *   out[6] inverse-SA samples checked for SA[ISA[p]] == p,                          out[7] violations
+ *   out[8] K-mers checked: filter count == min(3, occurrences by backward search), out[9] violations
+ *   out[10] top-of-search entries checked against bwt_extend from scratch,        out[11] violations
+ *   out[12] text bases compared with fwd / revcomp(fwd) (when fwd != NULL),        out[13] mismatches
+ * Needs the dense SA and the 2-bit text.  stride: every stride-th row / sample (1 = all).  Returns CS_OK when it ran;
+ * the caller looks at the violation counts. */
+int cs_index_verify(const cs_index_t *idx, const uint8_t *fwd, uint64_t l_pac, uint32_t stride, uint64_t out[16]);
 /* Copies the index back in the reference layout (for a host-side consumer such as the CPU baseline).
  * Call once with bwt == NULL to get sizes in *view, then with caller-allocated arrays of
  * view->bwt_size uint32 and view->n_sa uint64 (at the reference sampling out_sa_intv, e.g. 32). */
@@ -133,7 +186,13 @@ int cs_sa(const cs_index_t *idx, uint32_t n, const uint64_t *k, uint64_t *out);
  * max_mems / max_seeds: result capacities per slot (0: 16 / 32 per read). */
 cs_ctx_t *cs_ctx_create(const cs_index_t *idx, uint32_t max_reads, uint64_t max_bases, uint32_t max_read_len,
                         uint64_t max_mems, uint64_t max_seeds, int n_slots);
+cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads, uint64_t max_bases, uint32_t max_read_len,
+                           uint64_t max_mems, uint64_t max_seeds, int n_slots, const cs_ctx_config_t *cfg /* NULL = defaults */);
 void cs_ctx_free(cs_ctx_t *ctx);
+/* After CS_E_OVERFLOW on a slot: the capacities this batch needs (pass them to a new ctx and redo the batch once). */
+int cs_ctx_need(const cs_ctx_t *ctx, int slot, uint64_t *need_mems, uint64_t *need_seeds);
+/* Kernels launched on behalf of this ctx so far (ours and the two cub scans per batch), counted at the launch sites. */
+uint64_t cs_ctx_launches(const cs_ctx_t *ctx);
 
 /* bases: nt4 codes (0..3, anything > 3 is ambiguous) of all reads concatenated, converted as
  * comp_seed.cpp:2258-2260 does; offsets: n_reads+1.  Copies into the slot's pinned buffer, then
@@ -146,6 +205,9 @@ int cs_seed_batch_submit(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint8_
  * (1 = ambiguous, i.e. a code > 3, or past the end of the read; the packed bits of such a base are 0).
  * cs_packed_words gives the length of both arrays.  bwa.c:78-111 / main.cpp:36-58 is where a host would pack. */
 uint64_t cs_packed_words(uint32_t n_reads, const uint32_t *offsets);
+/* Host-side packer into that layout (plain C++ on n_threads host threads; no device involved): what a reader does once per
+ * read where it converts ASCII to nt4 today.  packed / nmask: cs_packed_words(n_reads, offsets) entries each. */
+int cs_pack_reads_host(uint32_t n_reads, const uint8_t *bases, const uint32_t *offsets, uint64_t *packed, uint32_t *nmask, int n_threads);
 int cs_seed_batch_submit_packed(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint64_t *packed, const uint32_t *nmask,
                                 const uint32_t *offsets, const cs_seed_opt_t *opt);
 /* Waits for the slot, copies the results to its pinned host buffers and fills *out. */
@@ -173,6 +235,10 @@ int cs_probe_random_gather(int device, uint64_t table_bytes, uint32_t granule, u
  * cudaLimitMaxL2FetchGranularity (0 = leave as is, else 32 / 64 / 128). */
 int cs_probe_random_gather_ex(int device, uint64_t table_bytes, uint32_t granule, uint64_t n_loads, int iters, int unroll,
                               int l2_fetch_granularity, double *gbytes_per_s, double *gloads_per_s);
+/* The same probe over the index's OWN arrays (Occ buckets, suffix array, occurrence filter, text, inverse SA, table:
+ * each load picks an array with probability proportional to its size): the random-sector peak of exactly the memory
+ * the seeding kernels gather from, TLB reach included.  granule 32. */
+int cs_probe_index_gather(const cs_index_t *idx, uint64_t n_loads, int iters, int unroll, double *gbytes_per_s, double *gloads_per_s);
 /* Raw device counters of the last finished run on a slot: [0] ext queries, [1] ext calls, [2] extends whose
  * k and l needed two sectors, [3] occurrence-filter probes, [4..19] event counters of a -DCS_STATS build (else 0), [20] reads the fast
  * kernel deferred to the literal kernel, [21] CTAs of k_seed_fast (0 = not available), [22] CTAs of k_seed,

@@ -46,11 +46,13 @@ static void ensure_ctx(uint32_t reads, uint64_t bases, uint32_t max_len, uint64_
 void csgpu_seed_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const bseq1_t *seqs)
 {
 	cs_seed_opt_t so;
-	uint64_t total = 0, m_used = 0, s_used = 0;
+	uint64_t total = 0, m_used = 0, s_used = 0, need_m = 0, need_s = 0;
+	static int packed_input = -1;   /* CSGPU_PACKED, read once */
 	uint32_t max_len = 1, *off;
 	uint8_t *bases;
 	int i, c, n_chunks, next, done;
 	if (n <= 0) return;
+	if (packed_input < 0) packed_input = getenv("CSGPU_PACKED") != 0;
 	if (!g_idx) { /* the index the host already loaded (bwa_idx_load, bwa.c:288) -> HBM, once */
 		cs_bwt_view_t v;
 		const char *dense = getenv("CSGPU_SA_INTV");
@@ -89,27 +91,22 @@ void csgpu_seed_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const bseq1
 			int s = c * CHUNK_READS, e = s + CHUNK_READS < n ? s + CHUNK_READS : n;
 			if (off[e] - off[s] > cb) cb = off[e] - off[s];
 		}
-		ensure_ctx(per, cb ? cb : 1, max_len, g_ctx_mems ? g_ctx_mems : (uint64_t)per * 16, g_ctx_seeds ? g_ctx_seeds : (uint64_t)per * 32);
+		/* capacities follow the chunk size (16 mems / 32 seeds per read) until a batch has said what it needs */
+		ensure_ctx(per, cb ? cb : 1, max_len, g_ctx_mems > (uint64_t)per * 16 ? g_ctx_mems : (uint64_t)per * 16,
+		           g_ctx_seeds > (uint64_t)per * 32 ? g_ctx_seeds : (uint64_t)per * 32);
 		m_used = s_used = 0;
 		for (next = 0, done = 0; done < n_chunks && !overflow; ) {
 			while (next < n_chunks && next - done < N_SLOTS) { /* keep every slot busy */
 				int s = next * CHUNK_READS, e = s + CHUNK_READS < n ? s + CHUNK_READS : n, r;
 				uint32_t *lo = (uint32_t*)malloc(((size_t)(e - s) + 1) * 4);
 				for (r = s; r <= e; ++r) lo[r - s] = off[r] - off[s];
-				if (!getenv("CSGPU_PACKED")) {
+				if (!packed_input) {
 					if (cs_seed_batch_submit(g_ctx, next % N_SLOTS, (uint32_t)(e - s), bases + off[s], lo, &so) != CS_OK) fatal("cs_seed_batch_submit");
 				} else { /* CSGPU_PACKED=1: send the chunk 2-bit packed (57 instead of 150 bytes per 150-bp read cross the link) */
 					const uint64_t nw = cs_packed_words((uint32_t)(e - s), lo);
-					uint64_t *pk = (uint64_t*)calloc(nw ? nw : 1, 8);
+					uint64_t *pk = (uint64_t*)malloc((nw ? nw : 1) * 8);
 					uint32_t *nm = (uint32_t*)malloc((nw ? nw : 1) * 4);
-					memset(nm, 0xff, (nw ? nw : 1) * 4);               /* everything a read does not cover counts as N */
-					for (r = 0; r < e - s; ++r) {
-						const uint8_t *q = bases + off[s + r];
-						const uint64_t w0 = (uint64_t)(lo[r] >> 5) + 2ull * (uint64_t)r;
-						uint32_t p, len = lo[r + 1] - lo[r];
-						for (p = 0; p < len; ++p)
-							if (q[p] <= 3) { pk[w0 + (p >> 5)] |= (uint64_t)q[p] << (2 * (p & 31)); nm[w0 + (p >> 5)] &= ~(1u << (p & 31)); }
-					}
+					if (cs_pack_reads_host((uint32_t)(e - s), bases + off[s], lo, pk, nm, opt->n_threads) != CS_OK) fatal("cs_pack_reads_host");
 					if (cs_seed_batch_submit_packed(g_ctx, next % N_SLOTS, (uint32_t)(e - s), pk, nm, lo, &so) != CS_OK) fatal("cs_seed_batch_submit_packed");
 					free(pk); free(nm);                                   /* (the library staged them in its own pinned buffers) */
 				}
@@ -119,7 +116,7 @@ void csgpu_seed_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const bseq1
 			{
 				cs_result_t res;
 				int s = done * CHUNK_READS, r, rc = cs_seed_batch_wait(g_ctx, done % N_SLOTS, &res);
-				if (rc == CS_E_OVERFLOW) { overflow = 1; break; }
+				if (rc == CS_E_OVERFLOW) { overflow = 1; cs_ctx_need(g_ctx, done % N_SLOTS, &need_m, &need_s); break; }   /* (CS_E_READ_OVERFLOW is fatal: no buffer size fixes it) */
 				if (rc != CS_OK) fatal("cs_seed_batch_wait");
 				if (m_used + res.n_mems > g_mems_cap) { g_mems_cap = (m_used + res.n_mems) * 2; g_mems = (cs_mem_t*)realloc(g_mems, g_mems_cap * sizeof(cs_mem_t)); }
 				if (s_used + res.n_seeds > g_rbeg_cap) { g_rbeg_cap = (s_used + res.n_seeds) * 2; g_rbeg = (int64_t*)realloc(g_rbeg, g_rbeg_cap * 8); }
@@ -136,9 +133,9 @@ void csgpu_seed_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const bseq1
 		if (!overflow) break;
 		/* drain the slots still in flight, then grow and redo the batch */
 		for (c = done + 1; c < next; ++c) { cs_result_t res; cs_seed_batch_wait(g_ctx, c % N_SLOTS, &res); }
-		g_ctx_mems = (g_ctx_mems ? g_ctx_mems : (uint64_t)per * 16) * 4;
-		g_ctx_seeds = (g_ctx_seeds ? g_ctx_seeds : (uint64_t)per * 32) * 8;
-		if (g_ctx_seeds >= (1ull << 32)) { fprintf(stderr, "[csgpu] batch needs more than 2^32 seeds per chunk\n"); exit(EXIT_FAILURE); }
+		if (need_m >= (1ull << 32) || need_s >= (1ull << 32)) { fprintf(stderr, "[csgpu] a chunk needs more than 2^32 mems or seeds\n"); exit(EXIT_FAILURE); }
+		if (need_m > g_ctx_mems) g_ctx_mems = need_m;      /* what the library said this chunk needs: one retry is enough */
+		if (need_s > g_ctx_seeds) g_ctx_seeds = need_s;
 		cs_ctx_free(g_ctx); g_ctx = 0;
 	}
 	free(bases); free(off);

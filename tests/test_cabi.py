@@ -90,3 +90,36 @@ def test_pack_reads_layout():
                 assert flag == 1 and code == 0
     e, m = cs.pack_reads(np.zeros(0, np.uint8), np.zeros(1, np.uint32))
     assert e.shape[0] == 0 and m.shape[0] == 0
+    # the library's own host-side packer (cs_pack_reads_host, plain C++ threads, no device) writes the same words
+    for t in (1, 3):
+        p2, m2 = cs.pack_reads_host(bases, off, t)
+        assert np.array_equal(p2, packed) and np.array_equal(m2, nmask)
+    big_b, big_o, _ = synth.simulate_reads(ref, 9000, [100, 150, 151], 0.02, seed=5, n_rate=0.01)
+    pa, ma = cs.pack_reads(big_b, big_o)
+    pb, mb = cs.pack_reads_host(big_b, big_o, 4)       # the threaded path
+    assert np.array_equal(pa, pb) and np.array_equal(ma, mb)
+
+
+def test_config_defaults_and_error_codes():
+    """cs_index_config_default / cs_ctx_config_default mirror the dataclasses; the error codes of the header are the ones
+    the Python side names."""
+    import ctypes as C
+    import compseed_b200 as cs
+    from compseed_b200 import seeding as S
+    L = cs.load_library()
+    ic, cc = S._IndexConfig(), S._CtxConfig()
+    L.cs_index_config_default(C.byref(ic)); L.cs_ctx_config_default(C.byref(cc))
+    assert (ic.kmer_table_depth, ic.prune_k, ic.isa_intv) == (-1, -1, -1)
+    d = cs.CtxConfig()
+    assert (cc.use_fast, cc.use_r3_fast, cc.defer_cap, cc.lit_ctas_per_sm, cc.prefetch_results, cc.l2_persist_mb, cc.overlap_streams) == \
+           (d.use_fast, d.use_r3_fast, d.defer_cap, d.lit_ctas_per_sm, d.prefetch_results, d.l2_persist_mb, d.overlap_streams)
+    hdr = open(os.path.join(ROOT, "include", "compseed_b200.h")).read()
+    codes = dict(re.findall(r"#define (CS_E_[A-Z_]+)\s+(-\d+)", hdr))
+    assert int(codes["CS_E_OVERFLOW"]) == S.CS_E_OVERFLOW and int(codes["CS_E_READ_OVERFLOW"]) == S.CS_E_READ_OVERFLOW
+    assert int(codes["CS_E_IO"]) == S.CS_E_IO and int(codes["CS_E_NODEVICE"]) == S.CS_E_NODEVICE
+
+
+def test_library_reads_no_environment_switches():
+    """Behaviour is configured through cs_index_config_t / cs_ctx_config_t, never through getenv inside the library."""
+    for f in os.listdir(os.path.join(ROOT, "compseed_b200", "csrc")):
+        assert "getenv" not in open(os.path.join(ROOT, "compseed_b200", "csrc", f)).read(), f

@@ -159,21 +159,24 @@ def test_slot_reuse_across_different_batches(cuda_lib, oracle_lib):
     ctx.close()
 
 
-def test_fast_route_equals_literal_route_midsize(cuda_lib, monkeypatch):
+def test_fast_route_equals_literal_route_midsize(cuda_lib):
     """100 Mbp reference (too large for the CPU oracle in test time): the fast route (k_seed_fast, k_seed_walk,
     k_seed in call mode, k_seed_r3_fast) against the literal route (k_seed in read mode, k_seed_r3), which the
-    tests above pin to the oracle; every mem and seed position.  scripts/selfcheck_cfg2.py does the same at 3.1 Gbp."""
+    tests above pin to the oracle; every mem and seed position.  The index itself is checked by cs_index_verify."""
     ref = synth.random_reference(100_000_000, seed=701)
     bases, off, _ = synth.simulate_reads(ref, 400_000, [100, 150, 250], 0.01, seed=702, n_rate=0.0005)
     idx = cuda_lib.FMIndex.build(ref, sa_intv=1)
+    v = idx.verify(ref, stride=1)
+    assert v["ok"] and v["order_rows"] == idx.seq_len and v["text_bases"] == idx.seq_len, v
     out = {}
-    for fast in ("1", "0"):
-        monkeypatch.setenv("CS_FAST", fast)
-        out[fast] = cuda_lib.seed_reads(idx, bases, off, batch_reads=150_001, n_slots=2)
-    monkeypatch.delenv("CS_FAST")
-    a, b = out["1"], out["0"]
+    for fast in (1, 0):
+        out[fast] = cuda_lib.seed_reads(idx, bases, off, batch_reads=150_001, n_slots=2, config=cuda_lib.CtxConfig(use_fast=fast))
+    a, b = out[1], out[0]
     assert a.counters["deferred_calls"] > 0 and b.counters["deferred_calls"] == 0
     _assert_same(a, b.mem_off, b.mems, b.seed_off, b.rbeg)
+    # the third pass on its own stream next to the walk / literal kernels, or after them on the same stream: same answer
+    c = cuda_lib.seed_reads(idx, bases, off, batch_reads=150_001, n_slots=2, config=cuda_lib.CtxConfig(overlap_streams=0))
+    _assert_same(c, a.mem_off, a.mems, a.seed_off, a.rbeg)
     idx.close()
 
 
@@ -255,28 +258,29 @@ def test_golden_reference_rebuilt_on_gpu(cuda_lib, golden):
     _assert_same(r, golden["mem_off0"], golden["mems0"], golden["seed_off0"], golden["rbeg0"])
 
 
-def test_result_neutral_caches_can_be_switched_off(cuda_lib, oracle_lib, monkeypatch):
+def test_result_neutral_caches_can_be_switched_off(cuda_lib, oracle_lib):
     """Top-of-search table and occurrence filter are pure caches/filters: with both disabled the kernel
-    issues exactly bwamem's bwt_extend calls (E of SURVEY 8d) and still returns the same mems."""
+    issues exactly bwamem's bwt_extend calls (E of SURVEY 8d) and still returns the same mems.  Every switch of
+    cs_index_config_t / cs_ctx_config_t is exercised."""
     ref = synth.random_reference(250_000, seed=501)
     bases, off, _ = synth.simulate_reads(ref, 4000, [100, 150], 0.015, seed=502, n_rate=0.002)
     oi = oracle_lib.OracleIndex.build(ref)
     want = oi.seed(bases, off, n_threads=8)
+    IC, CC = cuda_lib.IndexConfig, cuda_lib.CtxConfig
     results = {}
-    for name, env in {"plain": {"CS_KMER_TABLE_DEPTH": "0", "CS_PRUNE_K": "0"}, "table": {"CS_PRUNE_K": "0"},
-                      "filter": {"CS_KMER_TABLE_DEPTH": "0"}, "both": {}, "deep": {"CS_KMER_TABLE_DEPTH": "11", "CS_PRUNE_K": "16"},
-                      # dense SA => unique-match text paths on; they must account for exactly the extends they replace
-                      "text": {"CS_PRUNE_K": "0", "DENSE": "1"}, "text_isa1": {"CS_PRUNE_K": "0", "DENSE": "1", "CS_ISA_INTV": "1"},
-                      "text_isa32": {"CS_KMER_TABLE_DEPTH": "0", "CS_PRUNE_K": "0", "DENSE": "1", "CS_ISA_INTV": "32"},
-                      "all_dense": {"DENSE": "1"}, "all_dense_tiny_queue": {"DENSE": "1", "CS_DEFER_CAP": "7"}, "all_dense_nofast": {"DENSE": "1", "CS_FAST": "0"}, "all_dense_r3slow": {"DENSE": "1", "CS_R3_FAST": "0"}, "all_dense_k12": {"DENSE": "1", "CS_PRUNE_K": "12", "CS_KMER_TABLE_DEPTH": "9"}}.items():
-        for k in ("CS_KMER_TABLE_DEPTH", "CS_PRUNE_K", "CS_ISA_INTV", "CS_FAST", "CS_DEFER_CAP", "CS_R3_FAST"):
-            monkeypatch.delenv(k, raising=False)
-        env = dict(env)
-        dense = int(env.pop("DENSE", "0"))
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv, dense_sa_intv=dense)
-        got = cuda_lib.seed_reads(idx, bases, off, batch_reads=2048)
+    for name, (dense, icfg, ccfg) in {
+            "plain": (0, IC(kmer_table_depth=0, prune_k=0), CC()), "table": (0, IC(prune_k=0), CC()),
+            "filter": (0, IC(kmer_table_depth=0), CC()), "both": (0, IC(), CC()), "deep": (0, IC(kmer_table_depth=11, prune_k=16), CC()),
+            # dense SA => unique-match text paths on; they must account for exactly the extends they replace
+            "text": (1, IC(prune_k=0), CC()), "text_isa1": (1, IC(prune_k=0, isa_intv=1), CC()),
+            "text_isa32": (1, IC(kmer_table_depth=0, prune_k=0, isa_intv=32), CC()),
+            "all_dense": (1, IC(), CC()), "all_dense_tiny_queue": (1, IC(), CC(defer_cap=7)), "all_dense_nofast": (1, IC(), CC(use_fast=0)),
+            "all_dense_r3slow": (1, IC(), CC(use_r3_fast=0)), "all_dense_k12": (1, IC(prune_k=12, kmer_table_depth=9), CC()),
+            "all_dense_serial": (1, IC(), CC(overlap_streams=0)), "all_dense_r3slow_serial": (1, IC(), CC(use_r3_fast=0, overlap_streams=0)),
+            "all_dense_l2window": (1, IC(), CC(l2_persist_mb=16)), "all_dense_litcap": (1, IC(), CC(lit_ctas_per_sm=1)),
+            "all_dense_prefetch": (1, IC(), CC(prefetch_results=1))}.items():
+        idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv, dense_sa_intv=dense, config=icfg)
+        got = cuda_lib.seed_reads(idx, bases, off, batch_reads=2048, config=ccfg)
         _assert_same(got, want.mem_off, want.mems, want.seed_off, want.rbeg)
         results[name] = got.counters
         idx.close()
@@ -292,3 +296,4 @@ def test_result_neutral_caches_can_be_switched_off(cuda_lib, oracle_lib, monkeyp
     assert results["all_dense_nofast"]["deferred_calls"] == 0
     # a queue too small for the batch: rerun through the literal kernel alone, same answer (checked above)
     assert results["all_dense_tiny_queue"]["ext_queries"] == results["all_dense_nofast"]["ext_queries"]
+    assert results["all_dense_serial"] == results["all_dense"]

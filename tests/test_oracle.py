@@ -119,3 +119,23 @@ def test_synth_reads_are_reproducible():
     sb, so, perm = synth.shuffle_reads(a[0], a[1])
     r = int(perm[3])
     assert np.array_equal(sb[so[3]:so[4]], a[0][a[1][r]:a[1][r + 1]])
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libcsref.so")),
+                    reason="oracle/_ref not built (needs /root/reference)")
+def test_cfg1_full_size_oracle_against_reference(oracle_lib, tmp_path):
+    """BASELINE.json configs[0] at its stated size (5 Mbp, 200 k position-sorted 150-bp reads, defaults): the oracle's
+    index == bwaidx's files, and its mems / seeds == both seeding paths of the unmodified reference."""
+    ref = synth.random_reference(5_000_000, seed=20261018)
+    bases, off, _ = synth.simulate_reads(ref, 200_000, 150, 0.01, seed=1)
+    d = str(tmp_path)
+    synth.write_fasta(os.path.join(d, "ref.fa"), ref)
+    oracle_lib.bwaidx(os.path.join(d, "ref.fa"), os.path.join(d, "ref"))
+    ri = oracle_lib.RefIndex.load(os.path.join(d, "ref"))
+    oi = oracle_lib.OracleIndex.build(ref)
+    assert oi.primary == ri.primary and np.array_equal(oi.bwt, ri.bwt) and np.array_equal(oi.sa, ri.sa)
+    a = oi.seed(bases, off, n_threads=8)
+    b = ri.seed(bases, off, "bwamem", n_threads=8)
+    c = ri.seed(bases, off, "compseed", n_threads=8)
+    assert a.same_as(b) and a.same_as(c)
+    assert a.mems.shape[0] > 1_000_000
