@@ -49,6 +49,8 @@ def parse_args():
                     help="what crosses the host-to-device link on the host-buffer path: 2-bit packed reads (cs_seed_batch_submit_packed) or nt4 bytes")
     ap.add_argument("--l2-persist-mb", type=int, default=0, help="cs_ctx_config_t.l2_persist_mb for the contexts of this run")
     ap.add_argument("--no-overlap", action="store_true", help="cs_ctx_config_t.overlap_streams = 0")
+    ap.add_argument("--isa-intv", type=int, default=-1, help="cs_index_config_t.isa_intv (sampling of the inverse SA; -1 = default 4)")
+    ap.add_argument("--lit-ctas", type=int, default=-1, help="cs_ctx_config_t.lit_ctas_per_sm")
     return ap.parse_args()
 
 
@@ -183,7 +185,7 @@ def main():
     t_setup = time.time()
     ref, bases, off = make_workload(args, rank if args.impl == "ours" else 0, world if args.impl == "ours" else 1, device)
     n_reads = off.shape[0] - 1
-    idx = cs.FMIndex.build(ref, device=local_rank, sa_intv=args.sa_intv)
+    idx = cs.FMIndex.build(ref, device=local_rank, sa_intv=args.sa_intv, config=cs.IndexConfig(isa_intv=args.isa_intv))
     opt = cs.SeedOpt()
     setup_s = time.time() - t_setup
 
@@ -230,12 +232,17 @@ def main():
     if not args.no_probe:
         p1 = idx.probe_gather(1 << 28, 2, 1)
         p4 = idx.probe_gather(1 << 28, 2, 4)
-        best = max(p1, p4, key=lambda x: x[1])
-        probe = {"gloads_per_s": best[1], "gb_per_s": best[0], "one_load_in_flight_per_thread_gloads_per_s": p1[1],
-                 "four_loads_in_flight_per_thread_gloads_per_s": p4[1],
-                 "what": "independent uniformly random 32-byte sector loads over this index's own arrays (%.1f GB), 1184 CTAs x 256 threads, "
-                         "measured in this run before the timed region (cs_probe_index_gather)" % (idx.device_bytes / 1e9)}
-    ccfg = cs.CtxConfig(l2_persist_mb=args.l2_persist_mb, overlap_streams=0 if args.no_overlap else -1)
+        t1 = cs.probe_random_gather(local_rank, 16 << 30, 32, 1 << 28, 2, 1)
+        t4 = cs.probe_random_gather(local_rank, 16 << 30, 32, 1 << 28, 2, 4)
+        best = max(p1, p4, t1, t4, key=lambda x: x[1])
+        probe = {"gloads_per_s": best[1], "gb_per_s": best[0],
+                 "over_the_index_arrays": {"one_load_in_flight_per_thread_gloads_per_s": p1[1], "four_loads_in_flight_per_thread_gloads_per_s": p4[1],
+                                           "bytes": idx.device_bytes},
+                 "over_one_16_GiB_table": {"one_load_in_flight_per_thread_gloads_per_s": t1[1], "four_loads_in_flight_per_thread_gloads_per_s": t4[1]},
+                 "what": "independent uniformly random 32-byte sector loads, 1184 CTAs x 256 threads, measured in this run before the timed region: over this "
+                         "index's own arrays (cs_probe_index_gather, each load picks an array in proportion to its size) and over one 16 GiB table "
+                         "(cs_probe_random_gather); the roofline peak is the best of the four"}
+    ccfg = cs.CtxConfig(l2_persist_mb=args.l2_persist_mb, overlap_streams=0 if args.no_overlap else -1, lit_ctas_per_sm=args.lit_ctas)
 
     # (1) device-resident: all reads of the step staged in HBM once
     max_mems, max_seeds = n_reads * 14, n_reads * 20
@@ -304,87 +311,68 @@ def main():
     total_reads = n_reads * world * args.steps
     value = total_reads / (dev_ms_max * 1e-3)
 
-    # (2) end to end through the C-ABI with HOST buffers: pipelined batches, H2D + D2H inside the timed region
+    # (2) end to end through the C-ABI with HOST buffers, H2D + D2H inside the timed region: the multi-device pipeline of the
+    # library (cs_multi_*: one host thread per GPU submits batches through the slots of a ctx, results arrive by DMA in the
+    # compact wire format in page-locked arrays).  Consecutive steps alternate between the two read sets the pipeline keeps
+    # in flight, as a host does with batch i+1 and batch i.
     def run_e2e(packed_in: bool, keep_head: bool):
         bs = min(args.e2e_batch, n_reads)
-        n_slots = args.e2e_slots
-        starts_b = list(range(0, n_reads, bs))
-        host_batches = []
-        if packed_in:   # the host holds the reads 2-bit packed, per batch, in page-locked memory (what a packing reader would leave)
-            for s0 in starts_b:
-                e0 = min(n_reads, s0 + bs)
-                o = (off[s0:e0 + 1].astype(np.int64) - int(off[s0])).astype(np.uint32)
-                pk, nm = cs.pack_reads_host(bases[int(off[s0]):int(off[e0])], o, threads)
-                cs.host_register(pk); cs.host_register(nm)
-                host_batches.append((pk, nm, o))
+        off64 = off.astype(np.uint64)
+        if packed_in:   # the host holds the reads 2-bit packed in page-locked memory (what a packing reader would leave)
+            pk, nm = cs.pack_reads_host64(bases, off64, threads)
+            cs.host_register(pk); cs.host_register(nm)
         else:
             cs.host_register(bases)   # the reads sit in page-locked host memory, as the bench contract asks
-        ectx = cs.SeedContext(idx, bs, bs * args.read_len, args.read_len, bs * 14, bs * 20, n_slots, ccfg)
-        keep = {}
+        ms_ = cs.MultiSeeder([idx], batch_reads=bs, max_read_len=args.read_len, n_slots=args.e2e_slots, mems_per_read=14, seeds_per_read=20, config=ccfg)
 
-        def one_pass(keep_first: bool = False):
-            h2d = d2h = 0
-            inflight = []
-            nxt = 0
+        def submit(set_id):
+            if packed_in:
+                ms_.submit_packed(set_id, pk, nm, off64, opt)
+            else:
+                ms_.submit(set_id, bases, off64, opt)
 
-            def submit(bi):
-                s = starts_b[bi]
-                e = min(n_reads, s + bs)
-                if packed_in:
-                    pk, nm, o = host_batches[bi]
-                    ectx.submit_packed(bi % n_slots, pk, nm, o, opt)
-                    return pk.nbytes + nm.nbytes + o.nbytes
-                o = off[s:e + 1] - off[s]
-                ectx.submit(bi % n_slots, bases[int(off[s]):int(off[e])], o, opt)
-                return int(off[e]) - int(off[s]) + 4 * (e - s + 1)
-
-            while nxt < len(starts_b) and len(inflight) < n_slots:
-                h2d += submit(nxt)
-                inflight.append(nxt)
-                nxt += 1
-            tot_m = tot_s = 0
-            while inflight:
-                bi = inflight.pop(0)
-                r = ectx.wait(bi % n_slots, copy=False)
-                if keep_first and bi == 0:
-                    keep["first"] = SimpleNamespace(mem_off=r.mem_off.copy(), mems=r.mems.copy(), seed_off=r.seed_off.copy(), rbeg=r.rbeg.copy())
-                tot_m += int(r.mem_off[-1])
-                tot_s += int(r.seed_off[-1])
-                d2h += 4 * r.mem_off.shape[0] * 2 + 32 * int(r.mem_off[-1]) + 8 * int(r.seed_off[-1])
-                if nxt < len(starts_b):
-                    h2d += submit(nxt)
-                    inflight.append(nxt)
-                    nxt += 1
-            return h2d, d2h, tot_m, tot_s
-
+        n_b = (n_reads + bs - 1) // bs
+        h2d = (pk.nbytes + nm.nbytes if packed_in else bases.nbytes) + 4 * (n_reads + n_b)
         for _ in range(max(1, args.warmup - 1)):
-            one_pass()
+            submit(0); submit(1)
+            ms_.wait(0, gather=False); ms_.wait(1, gather=False)
         barrier()
-        l0 = ectx.launches
+        l0 = ms_.launches
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            h2d, d2h, tot_m, tot_s = one_pass()
+        submit(0)
+        for i in range(1, args.steps):
+            submit(i & 1)
+            info = ms_.wait((i - 1) & 1, gather=False)
+        info = ms_.wait((args.steps - 1) & 1, gather=False)
         barrier()
         e_ms = (time.perf_counter() - t0) * 1e3
-        n_launch = ectx.launches - l0
-        assert tot_m == n_mems and tot_s == n_seeds, "host-buffer path disagrees with the device-resident path"
-        if keep_head:
-            one_pass(keep_first=True)     # untimed: the first batch's results, for the comparison with the reference
+        n_launch = ms_.launches - l0
+        assert info["n_mems"] == n_mems and info["n_seeds"] == n_seeds, "host-buffer path disagrees with the device-resident path"
+        head = None
+        if keep_head:     # untimed: one more pass, expanded to flat arrays, for the comparison with the reference
+            submit(0)
+            g = ms_.wait(0, gather=True, n_threads=threads)
+            nm_h, ns_h = int(g.mem_off[n_par]), int(g.seed_off[n_par])
+            head = SimpleNamespace(mem_off=g.mem_off[:n_par + 1].astype(np.uint32), mems=g.mems[:nm_h].copy(),
+                                   seed_off=g.seed_off[:n_par + 1].astype(np.uint32), rbeg=g.rbeg[:ns_h].copy())
+            del g
         if use_dist:
             t = torch.tensor([e_ms], device=device, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t[0])
-        out = {"value": total_reads / (e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-               "batch_reads": bs, "slots": n_slots,
-               "input": "2-bit packed reads + N mask, packed by the host outside the timed region (cs_pack_reads_host, cs_seed_batch_submit_packed)" if packed_in else "nt4 bytes (cs_seed_batch_submit)",
-               "timing": "host wall clock between device syncs; inputs in page-locked host memory, results read back into the slots' pinned buffers"}
-        ectx.close()
+        out = {"value": total_reads / (e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": info["wire_bytes"] * world,
+               "batch_reads": bs, "slots": args.e2e_slots,
+               "api": "cs_multi_submit%s / cs_multi_wait: the library's own pipeline (one host thread per GPU, no Python in the loop), two read sets in flight" % ("_packed" if packed_in else ""),
+               "input": "2-bit packed reads + N mask in page-locked host memory, packed by the host outside the timed region (cs_pack_reads_host64)" if packed_in else "nt4 bytes in page-locked host memory",
+               "output": "compact wire format (20 B per mem, 5 B per seed position, 8 B of offsets per read) by DMA into page-locked host arrays; "
+                         "a consumer expands a read where it uses it (cs_cmem_unpack / cs_multi_read)",
+               "timing": "host wall clock between device syncs"}
+        ms_.close()
         if packed_in:
-            for pk, nm, _ in host_batches:
-                cs.host_unregister(pk); cs.host_unregister(nm)
+            cs.host_unregister(pk); cs.host_unregister(nm)
         else:
             cs.host_unregister(bases)
-        return out, keep.get("first"), n_launch
+        return out, head, n_launch
 
     e2e, e2e_head, e2e_launches = None, None, 0
     if not args.no_e2e:
@@ -417,11 +405,7 @@ def main():
                   "what": "mem_off, mems (x0, x1, x2, info), seed_off, rbeg of the first reads of the step, bit for bit",
                   "device_resident_equal": all(same_prefix(dev_head, w, n_cmp) for w in ref_res.values())}
         if e2e_head is not None:
-            n_e = min(n_cmp, e2e_head.mem_off.shape[0] - 1)
-            if n_e == n_cmp:
-                parity["e2e_equal"] = all(same_prefix(e2e_head, w, n_cmp) for w in ref_res.values())
-            else:   # the first host-buffer batch is shorter than the sample: compare it with the head of the device-resident result
-                parity["e2e_equal"] = same_prefix(dev_head, e2e_head, n_e) and parity["device_resident_equal"]
+            parity["e2e_equal"] = all(same_prefix(e2e_head, w, n_cmp) for w in ref_res.values())
         parity["equal"] = bool(parity["device_resident_equal"] and parity.get("e2e_equal", True))
         parity["rows_at_or_above_2^32_in_sample"] = int((first.mems[:, 0] >= np.uint64(1 << 32)).sum())
 
@@ -443,7 +427,7 @@ def main():
     peak = probe["gb_per_s"] if probe else None
     roofline = {"kernel": "k_seed_fast", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if peak else None,
-                "peak_source": "random 32-byte sector gather over the index's own arrays, measured in this run" if probe else "not measured (--no-probe)",
+                "peak_source": "best random 32-byte sector gather rate measured in this run (see random_sector_peak)" if probe else "not measured (--no-probe)",
                 "achieved_is": "executed memory requests of the kernel (in-kernel counter) x 32 B / CUDA-event duration",
                 "requests_per_read": req_fast / n_reads, "requests_per_s": req_fast / fast_s, "ms_per_launch": ms["fast"] / steps,
                 "random_sector_peak": probe,
@@ -478,7 +462,8 @@ def main():
                        "result_neutral_structures": "dense SA, top-of-search k-mer table (depth <= 13), 2-bit occurrence filter (K <= 19), "
                                                     "2-bit text + sampled inverse SA for unique matches (DESIGN.md section 5)",
                        "l2_policy": "inputs larger than L2 (index %.1f GB, reads %.1f GB per step)" % (idx.device_bytes / 1e9, bases.nbytes / 1e9),
-                       "l2_persist_mb": args.l2_persist_mb, "overlap_streams": not args.no_overlap,
+                       "l2_persist_mb": args.l2_persist_mb, "overlap_streams": not args.no_overlap, "isa_intv": args.isa_intv, "lit_ctas_per_sm": args.lit_ctas,
+                       "library_tag": os.environ.get("COMPSEED_LIB_TAG", ""),
                        "parallelism": f"index replicated x{world}, reads sharded in contiguous blocks, host gather, no collective"},
             "parity": parity, "index_verify": index_verify,
             "occ_lookups_per_s_executed": occ_exec_per_read * value, "occ_lookups_per_read_executed": occ_exec_per_read,

@@ -15,10 +15,14 @@
 #include "cs_internal.h"
 
 static thread_local char g_err[512] = "";
+static thread_local int g_err_code = 0;
+
+extern "C" int cs_last_error_code(void) { return g_err_code; }
 
 int cs_set_err(int code, const char *fmt, ...)
 {
 	va_list ap;
+	g_err_code = code;
 	va_start(ap, fmt);
 	vsnprintf(g_err, sizeof g_err, fmt, ap);
 	va_end(ap);
@@ -57,7 +61,7 @@ extern "C" void cs_ctx_config_default(cs_ctx_config_t *cfg)
 {
 	if (!cfg) return;
 	cfg->use_fast = -1; cfg->use_r3_fast = -1; cfg->defer_cap = -1; cfg->lit_ctas_per_sm = -1;
-	cfg->prefetch_results = 0; cfg->l2_persist_mb = 0; cfg->overlap_streams = -1; cfg->reserved = 0;
+	cfg->prefetch_results = 0; cfg->l2_persist_mb = 0; cfg->overlap_streams = -1; cfg->compact_results = 0;
 }
 
 static uint64_t kt_offset_host(uint32_t d) { return ((1ull << (2 * d)) - 4) / 3; }   // entries of depths 1 .. d-1 (kt_offset, cs_device.cuh)
@@ -510,6 +514,9 @@ struct Slot {
 	// pinned host
 	uint8_t *h_bases; uint32_t *h_off;
 	uint32_t *h_mem_off, *h_seed_off; cs_mem_t *h_mems; int64_t *h_rbeg;
+	cs_cmem_t *h_cmems; uint32_t *h_rlo; uint8_t *h_rhi;   // compact wire format (pinned, allocated on first use)
+	cs_cmem_t *d_cmems; uint32_t *d_rlo; uint8_t *d_rhi;   // ... on the device (cfg.compact_results)
+	bool fetched_compact;
 	Ctrl *h_ctrl;
 	// device
 	uint8_t *d_bases; uint32_t *d_off;
@@ -519,6 +526,7 @@ struct Slot {
 	cs_mem_t *d_stage;                        // collect: a read's sources gathered before the sort
 	bool used_fast;
 	bool packed_input;                        // the batch came through cs_seed_batch_submit_packed: d_packed / d_nmask are the input
+	uint32_t off_bias;                        // ... as a slice of a larger packed set (SeedArgs::off_bias); 0 otherwise
 	uint64_t *h_packed; uint32_t *h_nmask;    // pinned staging for it (allocated on first use)
 	Ctrl *d_ctrl;
 	cs_mem_t *d_thread_mems; uint4 *d_spill;
@@ -562,6 +570,8 @@ static void slot_free(Slot *s)
 	if (s->ev_done) cudaEventDestroy(s->ev_done);
 	if (s->ev_kdone) cudaEventDestroy(s->ev_kdone);
 	cudaFreeHost(s->h_packed); cudaFreeHost(s->h_nmask);
+	cudaFreeHost(s->h_cmems); cudaFreeHost(s->h_rlo); cudaFreeHost(s->h_rhi);
+	cudaFree(s->d_cmems); cudaFree(s->d_rlo); cudaFree(s->d_rhi);
 	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
 	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
 	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_defer_bits); cudaFree(s->d_lit_q); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
@@ -684,8 +694,8 @@ extern "C" cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads,
 		CK(cudaMallocHost(&s->h_ctrl, sizeof(Ctrl)));
 		CK(cudaMalloc(&s->d_bases, max_bases + 256));   // k_pack_reads reads whole aligned words past a read's last base
 		CK(cudaMalloc(&s->d_off, ((size_t)max_reads + 1) * 4));
-		CK(cudaMalloc(&s->d_packed, ((max_bases >> 5) + 2 * (size_t)max_reads + 4) * 8));
-		CK(cudaMalloc(&s->d_nmask, ((max_bases >> 5) + 2 * (size_t)max_reads + 4) * 4));
+		CK(cudaMalloc(&s->d_packed, ((max_bases >> 5) + 2 * (size_t)max_reads + 8) * 8));
+		CK(cudaMalloc(&s->d_nmask, ((max_bases >> 5) + 2 * (size_t)max_reads + 8) * 4));
 		CK(cudaMalloc(&s->d_ctrl, sizeof(Ctrl)));
 		CK(cudaMalloc(&s->d_defer_q, (size_t)ctx->defer_cap * sizeof(uint4)));
 		CK(cudaMalloc(&s->d_x_off, (size_t)ctx->defer_cap * 8));
@@ -704,6 +714,11 @@ extern "C" cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads,
 		CK(cudaMalloc(&s->d_read_n_seeds, ((size_t)max_reads + 1) * 4));
 		CK(cudaMalloc(&s->d_seed_off, ((size_t)max_reads + 1) * 4));
 		CK(cudaMalloc(&s->d_rows, ctx->max_seeds * 8));
+		if (ctx->cfg.compact_results > 0) {
+			CK(cudaMalloc(&s->d_cmems, ctx->max_mems * sizeof(cs_cmem_t)));
+			CK(cudaMalloc(&s->d_rlo, ctx->max_seeds * 4));
+			CK(cudaMalloc(&s->d_rhi, ctx->max_seeds));
+		}
 		s->r3_cap = max_bases / 16 + max_reads + 1;   // enough for min_seed_len >= 15; grown on demand in enqueue_run
 		CK(cudaMalloc(&s->d_r3_mems, s->r3_cap * sizeof(cs_mem_t)));
 		CK(cudaMalloc(&s->d_r3_n_mems, ((size_t)max_reads + 1) * 4));
@@ -748,7 +763,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 			int g3 = std::min<int>(ctx->grid_r3, (int)((n + 255) / 256));
 			if (s->packed_input) { // the general third-pass kernel reads the byte form
 				k_unpack_reads<<<(int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, st>>>(
-					s->d_packed, s->d_nmask, s->d_off, n, s->d_bases);
+					s->d_packed, s->d_nmask, s->d_off, n, s->d_bases, s->off_bias);
 				++ctx->n_launch;
 			}
 			k_seed_r3<<<g3 < 1 ? 1 : g3, 256, 0, st>>>(idx->d, a);
@@ -787,7 +802,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	}
 	CK(cudaEventRecord(s->ev_pack, s->stream));
 	a.bases = s->d_bases; a.off = s->d_off; a.n_reads = n; a.opt = *opt;
-	a.packed = s->d_packed; a.nmask = s->d_nmask;
+	a.packed = s->d_packed; a.nmask = s->d_nmask; a.off_bias = s->packed_input ? s->off_bias : 0u;
 	a.next_read = s->d_ctrl->next_read;
 	a.defer_q = nullptr; a.defer_cap = ctx->defer_cap; a.n_defer = &s->d_ctrl->n_defer;
 	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n; a.defer_bits = s->d_defer_bits; a.lit_q = s->d_lit_q; a.n_lit = &s->d_ctrl->n_lit; a.n_defer_fast = &s->d_ctrl->n_defer_fast;
@@ -861,6 +876,11 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	                                                    &s->d_ctrl->sa_work, &s->d_ctrl->lf_steps);
 	CK(cudaGetLastError()); ++ctx->n_launch;
 	CK(cudaEventRecord(s->ev[4], s->stream));
+	if (s->d_cmems) {
+		k_compact_results<<<idx->n_sm * 8, 256, 0, s->stream>>>(&s->d_ctrl->n_mems, ctx->max_mems, s->d_mems, s->d_cmems,
+		                                                         &s->d_ctrl->n_seeds, ctx->max_seeds, s->d_rows, s->d_rlo, s->d_rhi);
+		CK(cudaGetLastError()); ++ctx->n_launch;
+	}
 	CK(cudaMemcpyAsync(s->h_ctrl, s->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaEventRecord(s->ev_kdone, s->stream));
 	s->state = 2;
@@ -961,7 +981,7 @@ extern "C" int cs_seed_batch_stage(cs_ctx_t *ctx, int slot, uint32_t n_reads, co
 	Slot *s = &ctx->slots[slot];
 	if (s->state == 2 || s->state == 4) return set_err(CS_E_STATE, "slot %d is busy", slot);
 	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
-	memcpy(s->h_off, offsets, ((size_t)n_reads + 1) * 4);
+	if (offsets != s->h_off) memcpy(s->h_off, offsets, ((size_t)n_reads + 1) * 4);
 	s->n_reads = n_reads;
 	CK(cudaEventRecord(s->ev[0], s->stream));
 	{
@@ -1025,23 +1045,15 @@ extern "C" int cs_pack_reads_host(uint32_t n_reads, const uint8_t *bases, const 
 	return CS_OK;
 }
 
-extern "C" int cs_seed_batch_submit_packed(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint64_t *packed, const uint32_t *nmask,
-                                           const uint32_t *offsets, const cs_seed_opt_t *opt)
+// a batch whose packed words are the slice [packed, packed + nw) of a larger packed set: read r of the batch starts at word
+// ((off_bias + h_off[r]) >> 5) + 2r of the slice (off_bias = 0 for a batch packed on its own).  s->h_off / s->n_reads are set.
+static int submit_packed_words(cs_ctx *ctx, Slot *s, const uint64_t *packed, const uint32_t *nmask, uint64_t nw, uint32_t off_bias, const cs_seed_opt_t *opt)
 {
-	int rc;
-	if ((rc = check_opt(opt)) != CS_OK) return rc;
-	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
-	if (!packed || !nmask || !offsets) return set_err(CS_E_ARG, "null argument");
-	if ((rc = check_batch(ctx, n_reads, offsets)) != CS_OK) return rc;
-	Slot *s = &ctx->slots[slot];
-	if (s->state == 2 || s->state == 4) return set_err(CS_E_STATE, "slot %d is busy", slot);
-	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
+	const size_t cap = ((size_t)(ctx->max_bases >> 5) + 2 * (size_t)ctx->max_reads + 8);
+	const uint32_t n_reads = s->n_reads;
+	if (nw > cap) return set_err(CS_E_ARG, "packed batch has %llu words, ctx sized for %zu", (unsigned long long)nw, cap);
+	CK(cudaEventRecord(s->ev[0], s->stream));
 	{
-		const uint64_t nw = cs_packed_words(n_reads, offsets);
-		const size_t cap = ((size_t)(ctx->max_bases >> 5) + 2 * (size_t)ctx->max_reads + 4);
-		memcpy(s->h_off, offsets, ((size_t)n_reads + 1) * 4);
-		s->n_reads = n_reads;
-		CK(cudaEventRecord(s->ev[0], s->stream));
 		cudaPointerAttributes pa;
 		bool pinned = cudaPointerGetAttributes(&pa, packed) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
 		              cudaPointerGetAttributes(&pa, nmask) == cudaSuccess && pa.type == cudaMemoryTypeHost;
@@ -1056,15 +1068,116 @@ extern "C" int cs_seed_batch_submit_packed(cs_ctx_t *ctx, int slot, uint32_t n_r
 		CK(cudaMemcpyAsync(s->d_nmask, src_m, nw * 4, cudaMemcpyHostToDevice, s->stream));
 		CK(cudaMemcpyAsync(s->d_off, s->h_off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, s->stream));
 	}
-	s->packed_input = true;
+	s->packed_input = true; s->off_bias = off_bias;
 	s->state = 1;
 	s->want_fetch = true;
-	rc = enqueue_run(ctx, s, opt);
-	prefetch_ready(ctx, nullptr);
-	return rc;
+	{
+		const int rc = enqueue_run(ctx, s, opt);
+		prefetch_ready(ctx, nullptr);
+		return rc;
+	}
 fail:
 	return CS_E_CUDA;
 }
+
+extern "C" int cs_seed_batch_submit_packed(cs_ctx_t *ctx, int slot, uint32_t n_reads, const uint64_t *packed, const uint32_t *nmask,
+                                           const uint32_t *offsets, const cs_seed_opt_t *opt)
+{
+	int rc;
+	if ((rc = check_opt(opt)) != CS_OK) return rc;
+	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
+	if (!packed || !nmask || !offsets) return set_err(CS_E_ARG, "null argument");
+	if ((rc = check_batch(ctx, n_reads, offsets)) != CS_OK) return rc;
+	Slot *s = &ctx->slots[slot];
+	if (s->state == 2 || s->state == 4) return set_err(CS_E_STATE, "slot %d is busy", slot);
+	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
+	memcpy(s->h_off, offsets, ((size_t)n_reads + 1) * 4);
+	s->n_reads = n_reads;
+	return submit_packed_words(ctx, s, packed, nmask, cs_packed_words(n_reads, offsets), 0, opt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// internals used by the multi-device pipeline (cs_multi.cu): a batch is reads [r0, r0 + n) of a set described by 64-bit
+// offsets; results are copied in the compact wire format straight to where the caller wants them (page-locked memory)
+// ---------------------------------------------------------------------------------------------
+int cs_i_submit(cs_ctx *ctx, int slot, uint32_t n, const uint64_t *off64, const uint8_t *bases, const uint64_t *packed, const uint32_t *nmask,
+                uint64_t r0, const cs_seed_opt_t *opt)
+{
+	int rc;
+	if ((rc = check_opt(opt)) != CS_OK) return rc;
+	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
+	if (n == 0 || n > ctx->max_reads) return set_err(CS_E_ARG, "n_reads %u outside [1, %u]", n, ctx->max_reads);
+	Slot *s = &ctx->slots[slot];
+	if (s->state == 2 || s->state == 4) return set_err(CS_E_STATE, "slot %d is busy", slot);
+	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
+	const uint64_t o0 = off64[r0];
+	if (off64[r0 + n] - o0 > ctx->max_bases) return set_err(CS_E_ARG, "batch has %llu bases, ctx sized for %llu", (unsigned long long)(off64[r0 + n] - o0), (unsigned long long)ctx->max_bases);
+	for (uint32_t r = 0; r <= n; ++r) s->h_off[r] = (uint32_t)(off64[r0 + r] - o0);
+	for (uint32_t r = 0; r < n; ++r)
+		if (s->h_off[r + 1] < s->h_off[r] || s->h_off[r + 1] - s->h_off[r] > ctx->max_read_len)
+			return set_err(CS_E_ARG, "read %llu has length %u > max_read_len %u (or offsets not monotone)", (unsigned long long)(r0 + r), s->h_off[r + 1] - s->h_off[r], ctx->max_read_len);
+	s->n_reads = n;
+	if (packed) { // slice of the set-global packed arrays (cs_pack_reads_host64): words [(o0 >> 5) + 2 r0, (o1 >> 5) + 2 (r0 + n))
+		const uint64_t w_lo = (o0 >> 5) + 2 * r0, w_hi = (off64[r0 + n] >> 5) + 2 * (r0 + n);
+		return submit_packed_words(ctx, s, packed + w_lo, nmask + w_lo, w_hi - w_lo, (uint32_t)(o0 & 31), opt);
+	}
+	if ((rc = cs_seed_batch_stage(ctx, slot, n, bases + o0, s->h_off)) != CS_OK) return rc;
+	s->want_fetch = true;
+	rc = enqueue_run(ctx, s, opt);
+	return rc;
+}
+
+// kernels of the slot done: status and result sizes
+int cs_i_finish(cs_ctx *ctx, int slot, uint64_t *n_mems, uint64_t *n_seeds)
+{
+	Slot *s = &ctx->slots[slot];
+	if (s->state != 2) return set_err(CS_E_STATE, "slot %d has no batch in flight", slot);
+	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
+	const int rc = finish_run(ctx, s);
+	if (rc != CS_OK) { s->state = 1; return rc; }
+	*n_mems = s->h_ctrl->n_mems; *n_seeds = s->h_ctrl->n_seeds;
+	return CS_OK;
+}
+
+// enqueue the result copies of a finished slot (compact wire format) to caller-owned page-locked memory
+int cs_i_fetch_compact_into(cs_ctx *ctx, int slot, uint32_t *mem_off, uint32_t *seed_off, cs_cmem_t *cm, uint32_t *lo, uint8_t *hi)
+{
+	Slot *s = &ctx->slots[slot];
+	const uint32_t n = s->n_reads;
+	if (s->state != 3 || !s->d_cmems) return set_err(CS_E_STATE, "slot %d has no finished batch with compact results", slot);
+	CK(cudaMemcpyAsync(mem_off, s->d_mem_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaMemcpyAsync(seed_off, s->d_seed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+	if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(cm, s->d_cmems, (size_t)s->h_ctrl->n_mems * sizeof(cs_cmem_t), cudaMemcpyDeviceToHost, s->stream));
+	if (s->h_ctrl->n_seeds) {
+		CK(cudaMemcpyAsync(lo, s->d_rlo, (size_t)s->h_ctrl->n_seeds * 4, cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaMemcpyAsync(hi, s->d_rhi, (size_t)s->h_ctrl->n_seeds, cudaMemcpyDeviceToHost, s->stream));
+	}
+	CK(cudaEventRecord(s->ev_done, s->stream));
+	s->state = 4;
+	return CS_OK;
+fail:
+	return CS_E_CUDA;
+}
+
+int cs_i_fetch_wait(cs_ctx *ctx, int slot, cs_counters_t *cnt, float *slot_ms)
+{
+	Slot *s = &ctx->slots[slot];
+	if (s->state != 4) return set_err(CS_E_STATE, "slot %d has no copy in flight", slot);
+	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
+	CK(cudaEventSynchronize(s->ev_done));
+	s->state = 3;
+	if (cnt) {
+		cnt->ext_queries += s->h_ctrl->counters[0]; cnt->ext_calls += s->h_ctrl->counters[1];
+		cnt->sal_queries += s->h_ctrl->n_seeds; cnt->sal_calls += s->h_ctrl->lf_steps;
+	}
+	if (slot_ms) cudaEventElapsedTime(slot_ms, s->ev[0], s->ev_done);
+	return CS_OK;
+fail:
+	return CS_E_CUDA;
+}
+
+void cs_i_ctx_caps(const cs_ctx *ctx, uint64_t *max_mems, uint64_t *max_seeds) { *max_mems = ctx->max_mems; *max_seeds = ctx->max_seeds; }
+const cs_index *cs_i_ctx_index(const cs_ctx *ctx) { return ctx->idx; }
 
 static int check_opt(const cs_seed_opt_t *opt)
 {
@@ -1117,19 +1230,35 @@ extern "C" int cs_seed_batch_wait_device(cs_ctx_t *ctx, int slot, cs_result_t *o
 	return CS_OK;
 }
 
-static int fetch(cs_ctx *ctx, Slot *s)
+static int fetch(cs_ctx *ctx, Slot *s, bool compact = false)
 {
 	const uint32_t n = s->n_reads;
-	if (!s->h_mems) { // pinned result buffers are allocated on first use (device-resident runs never need them)
+	if (!s->h_mem_off) { // pinned result buffers are allocated on first use (device-resident runs never need them)
 		CK(cudaMallocHost(&s->h_mem_off, ((size_t)ctx->max_reads + 1) * 4));
 		CK(cudaMallocHost(&s->h_seed_off, ((size_t)ctx->max_reads + 1) * 4));
+	}
+	if (!compact && !s->h_mems) {
 		CK(cudaMallocHost(&s->h_mems, ctx->max_mems * sizeof(cs_mem_t)));
 		CK(cudaMallocHost(&s->h_rbeg, ctx->max_seeds * 8));
 	}
+	if (compact && !s->h_cmems) {
+		CK(cudaMallocHost(&s->h_cmems, ctx->max_mems * sizeof(cs_cmem_t)));
+		CK(cudaMallocHost(&s->h_rlo, ctx->max_seeds * 4));
+		CK(cudaMallocHost(&s->h_rhi, ctx->max_seeds));
+	}
 	CK(cudaMemcpyAsync(s->h_mem_off, s->d_mem_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaMemcpyAsync(s->h_seed_off, s->d_seed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
-	if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(s->h_mems, s->d_mems, (size_t)s->h_ctrl->n_mems * sizeof(cs_mem_t), cudaMemcpyDeviceToHost, s->stream));
-	if (s->h_ctrl->n_seeds) CK(cudaMemcpyAsync(s->h_rbeg, s->d_rows, (size_t)s->h_ctrl->n_seeds * 8, cudaMemcpyDeviceToHost, s->stream));
+	if (!compact) {
+		if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(s->h_mems, s->d_mems, (size_t)s->h_ctrl->n_mems * sizeof(cs_mem_t), cudaMemcpyDeviceToHost, s->stream));
+		if (s->h_ctrl->n_seeds) CK(cudaMemcpyAsync(s->h_rbeg, s->d_rows, (size_t)s->h_ctrl->n_seeds * 8, cudaMemcpyDeviceToHost, s->stream));
+	} else {
+		if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(s->h_cmems, s->d_cmems, (size_t)s->h_ctrl->n_mems * sizeof(cs_cmem_t), cudaMemcpyDeviceToHost, s->stream));
+		if (s->h_ctrl->n_seeds) {
+			CK(cudaMemcpyAsync(s->h_rlo, s->d_rlo, (size_t)s->h_ctrl->n_seeds * 4, cudaMemcpyDeviceToHost, s->stream));
+			CK(cudaMemcpyAsync(s->h_rhi, s->d_rhi, (size_t)s->h_ctrl->n_seeds, cudaMemcpyDeviceToHost, s->stream));
+		}
+	}
+	s->fetched_compact = compact;
 	CK(cudaEventRecord(s->ev_done, s->stream));
 	return CS_OK;
 fail:
@@ -1204,6 +1333,45 @@ extern "C" int cs_seed_batch_wait(cs_ctx_t *ctx, int slot, cs_result_t *out)
 	return CS_OK;
 }
 
+extern "C" int cs_seed_batch_wait_compact(cs_ctx_t *ctx, int slot, cs_compact_result_t *out)
+{
+	int rc;
+	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
+	if (!out) return set_err(CS_E_ARG, "null result");
+	Slot *s = &ctx->slots[slot];
+	if (!s->d_cmems) return set_err(CS_E_STATE, "the ctx was created without compact_results");
+	if (s->state != 2 && s->state != 3) return set_err(CS_E_STATE, "slot %d has no batch in flight or finished", slot);
+	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
+	if (s->state == 2 && (rc = finish_run(ctx, s)) != CS_OK) { s->state = 1; return rc; }
+	if ((rc = fetch(ctx, s, true)) != CS_OK) return rc;
+	if ((rc = fetch_wait(ctx, s)) != CS_OK) return rc;
+	s->state = 3;
+	memset(out, 0, sizeof *out);
+	out->n_reads = s->n_reads; out->n_mems = s->h_ctrl->n_mems; out->n_seeds = s->h_ctrl->n_seeds;
+	out->mem_off = s->h_mem_off; out->cmems = s->h_cmems; out->seed_off = s->h_seed_off; out->rbeg_lo = s->h_rlo; out->rbeg_hi = s->h_rhi;
+	out->counters.ext_queries = s->h_ctrl->counters[0]; out->counters.ext_calls = s->h_ctrl->counters[1];
+	out->counters.sal_queries = s->h_ctrl->n_seeds; out->counters.sal_calls = s->h_ctrl->lf_steps;
+	return CS_OK;
+}
+
+extern "C" int cs_compact_expand(const cs_compact_result_t *res, cs_mem_t *mems, int64_t *rbeg, int n_threads)
+{ // host-side C++, no device involved
+	if (!res || (res->n_mems && !mems) || (res->n_seeds && !rbeg)) return set_err(CS_E_ARG, "null argument");
+	if (n_threads < 1) n_threads = 1;
+	if (n_threads > 64) n_threads = 64;
+	auto work = [=](int t) {
+		const uint64_t m0 = res->n_mems * t / n_threads, m1 = res->n_mems * (t + 1) / n_threads;
+		for (uint64_t i = m0; i < m1; ++i) cs_cmem_unpack(res->cmems + i, mems + i);
+		const uint64_t s0 = res->n_seeds * t / n_threads, s1 = res->n_seeds * (t + 1) / n_threads;
+		for (uint64_t i = s0; i < s1; ++i) rbeg[i] = cs_crbeg(res->rbeg_lo, res->rbeg_hi, i);
+	};
+	if (n_threads == 1) { work(0); return CS_OK; }
+	std::vector<std::thread> th;
+	for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+	for (auto &t : th) t.join();
+	return CS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // measurement helpers
 // ---------------------------------------------------------------------------------------------
@@ -1263,7 +1431,7 @@ extern "C" int cs_debug_stats(cs_ctx_t *ctx, int slot, uint64_t out[40])
 	if (!out) return set_err(CS_E_ARG, "null argument");
 	for (int k = 0; k < 20; ++k) out[k] = ctx->slots[slot].h_ctrl->counters[k];
 	out[20] = ctx->slots[slot].h_ctrl->n_defer;
-	out[21] = ctx->grid_fast; out[22] = ctx->grid; out[23] = 0;
+	out[21] = ctx->grid_fast; out[22] = ctx->grid; out[23] = ctx->slots[slot].h_ctrl->n_lit;
 	for (int k = 0; k < 16; ++k) out[24 + k] = ctx->slots[slot].h_ctrl->counters[20 + k];
 	return CS_OK;
 }

@@ -23,3 +23,13 @@ int cs_use_device(int device);
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
 	cs_set_err(CS_E_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); goto fail; } } while (0)
+
+// cs_api.cu internals used by the multi-device pipeline (cs_multi.cu)
+struct cs_ctx;
+int cs_i_submit(cs_ctx *ctx, int slot, uint32_t n, const uint64_t *off64, const uint8_t *bases, const uint64_t *packed, const uint32_t *nmask,
+                uint64_t r0, const cs_seed_opt_t *opt);
+int cs_i_finish(cs_ctx *ctx, int slot, uint64_t *n_mems, uint64_t *n_seeds);
+int cs_i_fetch_compact_into(cs_ctx *ctx, int slot, uint32_t *mem_off, uint32_t *seed_off, cs_cmem_t *cm, uint32_t *lo, uint8_t *hi);
+int cs_i_fetch_wait(cs_ctx *ctx, int slot, cs_counters_t *cnt, float *slot_ms);
+void cs_i_ctx_caps(const cs_ctx *ctx, uint64_t *max_mems, uint64_t *max_seeds);
+const cs_index *cs_i_ctx_index(const cs_ctx *ctx);

@@ -281,13 +281,13 @@ __global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t
 
 // Inverse of k_pack_reads, for batches submitted in packed form (cs_seed_batch_submit_packed) when a kernel that
 // reads the byte form is going to run (k_seed_r3).  One thread per base.
-__global__ void k_unpack_reads(const uint64_t *packed, const uint32_t *nmask, const uint32_t *off, uint32_t n_reads, uint8_t *bases)
+__global__ void k_unpack_reads(const uint64_t *packed, const uint32_t *nmask, const uint32_t *off, uint32_t n_reads, uint8_t *bases, uint32_t off_bias)
 {
 	const uint32_t sub = threadIdx.x & 7;
 	const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
 	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n_reads; r += ngroups) {
 		const uint32_t o = off[r], len = off[r + 1] - o;
-		const uint64_t w0 = (uint64_t)(o >> 5) + 2 * r;
+		const uint64_t w0 = (uint64_t)((o + off_bias) >> 5) + 2 * r;
 		for (uint32_t p = sub; p < len; p += 8) {
 			const uint64_t v = packed[w0 + (p >> 5)];
 			const uint32_t m = nmask[w0 + (p >> 5)];
@@ -539,7 +539,7 @@ __device__ __forceinline__ void seed_body(const DevIndex &I, const SeedArgs &a)
 				} else if (rd >= a.n_reads) { st = ST_IDLE; break; }
 				uint32_t o = a.off[rd];
 				len = (int)(a.off[rd + 1] - o);
-				pw = a.packed + ((uint64_t)(o >> 5) + 2ull * rd);
+				pw = a.packed + ((uint64_t)((o + a.off_bias) >> 5) + 2ull * rd);
 				if (RW) {
 					const uint32_t *gn = a.nmask + (pw - a.packed);
 					const uint32_t nw = ((uint32_t)len >> 5) + 2;
@@ -976,7 +976,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 				else {
 					const uint32_t o = a.off[rd];
 					len = (int)(a.off[rd + 1] - o);
-					const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * rd;
+					const uint64_t w0 = (uint64_t)((o + a.off_bias) >> 5) + 2ull * rd;
 					const uint32_t nw = ((uint32_t)len >> 5) + 2;
 #pragma unroll
 					for (uint32_t wi = 0; wi < RW; ++wi) {
@@ -1089,17 +1089,34 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			cnt0 = 32; if ((uint32_t)cx < cnt0) cnt0 = (uint32_t)cx; if (tp0 < cnt0) cnt0 = (uint32_t)tp0;
 			if (cnt0) { bw0 = packed_window(I.text, tp0 - cnt0); n_req += 1u + (((tp0 - cnt0) & 31) != 0); }
 			uint64_t tpos = tp0 + (uint64_t)(i - cx);
-			for (;;) {
-				const uint64_t diff = read_window(i) ^ packed_window(I.text, tpos);
-				const uint32_t nmw = nmask_window(i);
-				n_req += 1u + ((tpos & 31) != 0);
-				uint32_t m = diff ? (uint32_t)(__ffsll((long long)diff) - 1) >> 1 : 32u;
-				const uint32_t nn = nmw ? (uint32_t)__ffs((int)nmw) - 1u : 32u;
+			// Up to CS_FWD_WIN windows of 32 bases are fetched at once (all their loads in flight together) instead of one
+			// per trip of a loop whose trip count differs from lane to lane: at 1 % substitutions a unique match runs on for
+			// ~100 bases, so most of the words are needed, and the warp no longer waits four times for its longest lane.
+			for (bool go = true; go; ) {
 				const uint64_t left = I.seq_len - tpos;
-				if (nn < m) m = nn;
-				if (left < m) m = (uint32_t)left;
-				i += (int)m; tpos += m; jf += (int)m;
-				if (m < 32) break;
+				uint64_t room = (uint64_t)(len - i); if (left < room) room = left;            // bases that can still match
+				const uint32_t nwin = room >= 32u * CS_FWD_WIN ? (uint32_t)CS_FWD_WIN : (uint32_t)((room + 31) >> 5);
+				const uint64_t w = tpos >> 5; const uint32_t sh = ((uint32_t)tpos & 31) * 2;
+				uint64_t tw[CS_FWD_WIN + 1];
+#pragma unroll
+				for (int k = 0; k <= CS_FWD_WIN; ++k) tw[k] = ((uint32_t)k < nwin || ((uint32_t)k == nwin && sh && nwin)) ? gather_u64(I.text + w + k) : 0ull;
+				n_req += nwin + ((sh && nwin) ? 1u : 0u);
+				if (nwin == 0) break;                                                         // read end / text end: nothing left to compare
+#pragma unroll
+				for (int k = 0; k < CS_FWD_WIN; ++k) {
+					if (!go) break;
+					if ((uint32_t)k >= nwin) { go = false; break; }
+					const uint64_t win = sh ? (tw[k] >> sh) | (tw[k + 1] << (64 - sh)) : tw[k];
+					const uint64_t diff = read_window(i) ^ win;
+					const uint32_t nmw = nmask_window(i);
+					uint32_t m = diff ? (uint32_t)(__ffsll((long long)diff) - 1) >> 1 : 32u;
+					const uint32_t nn = nmw ? (uint32_t)__ffs((int)nmw) - 1u : 32u;
+					const uint64_t lft = I.seq_len - tpos;
+					if (nn < m) m = nn;
+					if (lft < m) m = (uint32_t)lft;
+					i += (int)m; tpos += m; jf += (int)m;
+					if (m < 32) go = false;
+				}
 			}
 			r_ext += (uint32_t)jf + ((i < len && base_at(i) <= 3) ? 1u : 0u);
 		}
@@ -1274,7 +1291,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 		if (active) {
 			const uint32_t o = a.off[rd];
 			const int len = (int)(a.off[rd + 1] - o);
-			const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * rd;
+			const uint64_t w0 = (uint64_t)((o + a.off_bias) >> 5) + 2ull * rd;
 			const uint32_t nw = ((uint32_t)len >> 5) + 2;
 #pragma unroll
 			for (uint32_t wi = 0; wi < RW; ++wi) {
@@ -1425,7 +1442,7 @@ __global__ void __launch_bounds__(256, 4) k_seed_r3(DevIndex I, SeedArgs a)
 				if (rd >= a.n_reads) { idle = true; break; }
 				uint32_t o = a.off[rd];
 				q = a.bases + o; len = (int)(a.off[rd + 1] - o);
-				pw = a.packed + ((uint64_t)(o >> 5) + 2ull * rd); pn = a.nmask + ((uint64_t)(o >> 5) + 2ull * rd);
+				pw = a.packed + ((uint64_t)((o + a.off_bias) >> 5) + 2ull * rd); pn = a.nmask + ((uint64_t)((o + a.off_bias) >> 5) + 2ull * rd);
 				out = a.r3_mems + ((uint64_t)(o / kp1) + rd);
 				nmem = 0; x = 0; i = 0; have_read = true;
 			}
@@ -1553,7 +1570,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 				else {
 					const uint32_t o = a.off[rd];
 					len = (int)(a.off[rd + 1] - o);
-					const uint64_t w0 = (uint64_t)(o >> 5) + 2ull * rd;
+					const uint64_t w0 = (uint64_t)((o + a.off_bias) >> 5) + 2ull * rd;
 					const uint32_t nw = ((uint32_t)len >> 5) + 2;
 #pragma unroll
 					for (uint32_t wi = 0; wi < RW; ++wi) {
@@ -1783,6 +1800,28 @@ __global__ void k_collect_rows(CollectArgs a)
 			o += cnt;
 		}
 	}
+}
+
+// Compact wire format (include/compseed_b200.h, cs_cmem_t): 20 bytes per mem, 5 per seed position.  Runs after
+// k_sa_resolve; counts are read on the device.
+__global__ void k_compact_results(const uint32_t *n_mems_ptr, uint64_t mems_cap, const cs_mem_t *mems, cs_cmem_t *cmems,
+                                  const uint32_t *n_seeds_ptr, uint64_t seeds_cap, const uint64_t *rbeg, uint32_t *lo, uint8_t *hi)
+{
+	const uint64_t nm = *n_mems_ptr, ns = *n_seeds_ptr;
+	const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+	if (nm <= mems_cap)
+		for (uint64_t i = tid; i < nm; i += nth) {
+			const uint4 *p = reinterpret_cast<const uint4*>(mems + i);
+			const uint4 a = p[0], b = p[1];              // x0 lo hi, x1 lo hi | x2 lo hi, end, start
+			uint32_t *d = reinterpret_cast<uint32_t*>(cmems + i);
+			d[0] = a.x; d[1] = a.z; d[2] = b.x; d[3] = (b.w << 16) | (b.z & 0xffffu);
+			d[4] = (a.y & 31u) | ((a.w & 31u) << 5) | ((b.y & 31u) << 10);
+		}
+	if (ns <= seeds_cap)
+		for (uint64_t i = tid; i < ns; i += nth) {
+			const uint64_t v = rbeg[i];
+			lo[i] = (uint32_t)v; hi[i] = (uint8_t)(v >> 32);
+		}
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -23,6 +23,9 @@
 #ifndef CS_WALK_MAX
 #define CS_WALK_MAX 6           // short forward matches a call may have to be walked by k_seed_walk (else k_seed)
 #endif
+#ifndef CS_FWD_WIN
+#define CS_FWD_WIN 4            // 32-base text windows k_seed_fast fetches at once when it follows a unique match forward
+#endif
 #define CS_FAST_SMEM_BYTES ((size_t)CS_FAST_BLOCK * (CS_READ_SMEM * 12))
 
 struct SeedArgs {
@@ -30,7 +33,8 @@ struct SeedArgs {
 	const uint32_t *off;        // n_reads + 1
 	uint32_t n_reads;
 	cs_seed_opt_t opt;
-	const uint64_t *packed;     // 2-bit packed reads (k_pack_reads): read r starts at word (off[r] >> 5) + 2r
+	const uint64_t *packed;     // 2-bit packed reads (k_pack_reads): read r starts at word ((off_bias + off[r]) >> 5) + 2r
+	uint32_t off_bias;          // 0..31: the batch is a slice of a larger packed set that starts off_bias bases into its first word
 	const uint32_t *nmask;      // ambiguity / end-of-read mask, same word indexing
 	// scratch
 	uint32_t *next_read;        // work counters: [0] k_seed, [1] k_seed_r3, [2] k_seed_fast, [3] k_seed_walk
@@ -101,7 +105,7 @@ __global__ void k_text_lsb(const uint64_t *W, uint64_t n_words, uint64_t *out);
 __global__ void k_isa_sample(DevIndex I, uint64_t *isa, uint32_t shift);
 __global__ void k_pt_count(const uint64_t *W, uint64_t n, uint32_t K, uint32_t *pt);
 __global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t n_reads, uint64_t *packed, uint32_t *nmask);
-__global__ void k_unpack_reads(const uint64_t *packed, const uint32_t *nmask, const uint32_t *off, uint32_t n_reads, uint8_t *bases);
+__global__ void k_unpack_reads(const uint64_t *packed, const uint32_t *nmask, const uint32_t *off, uint32_t n_reads, uint8_t *bases, uint32_t off_bias);
 __global__ void k_seed(DevIndex I, SeedArgs a);
 __global__ void k_seed_long(DevIndex I, SeedArgs a);
 __global__ void k_seed_fast(DevIndex I, SeedArgs a);
@@ -112,6 +116,8 @@ __global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, const uint
                              uint32_t n_reads, uint32_t *out, unsigned long long *tot12, unsigned long long *tot3);
 __global__ void k_collect_sort(CollectArgs a);
 __global__ void k_collect_rows(CollectArgs a);
+__global__ void k_compact_results(const uint32_t *n_mems_ptr, uint64_t mems_cap, const cs_mem_t *mems, cs_cmem_t *cmems,
+                                  const uint32_t *n_seeds_ptr, uint64_t seeds_cap, const uint64_t *rbeg, uint32_t *lo, uint8_t *hi);
 __global__ void k_gather_probe(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed, unsigned long long *sink);
 __global__ void k_gather_probe4(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed, unsigned long long *sink);
 __global__ void k_fill(uint4 *p, uint64_t n, uint32_t v);

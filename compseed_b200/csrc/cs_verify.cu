@@ -213,7 +213,7 @@ __global__ void k_verify_text(DevIndex I, const uint8_t *chunk, uint64_t p0, uin
 }
 
 // random 32-byte sectors over several arrays at once: load i picks array a with probability size_a / total
-struct ProbeArrays { const uint4 *base[6]; uint64_t cum[7]; int n; };   // cum: cumulative sizes in 32-byte sectors
+struct ProbeArrays { const uint4 *base[6]; uint64_t cum[7]; uint64_t total; int n; };   // cum: cumulative sizes in 32-byte sectors
 
 template <int UNROLL>
 __global__ void k_index_gather(ProbeArrays A, uint64_t n_loads, uint64_t seed, unsigned long long *sink)
@@ -221,7 +221,7 @@ __global__ void k_index_gather(ProbeArrays A, uint64_t n_loads, uint64_t seed, u
 	const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
 	uint64_t s = seed ^ (tid * 0x9E3779B97F4A7C15ull);
 	uint32_t acc = 0;
-	const uint64_t total = A.cum[A.n];
+	const uint64_t total = A.total;           // (no run-time index into the parameter struct: that would move it to local memory)
 	for (uint64_t i = tid; i < n_loads; i += stride * UNROLL) {
 		uint64_t a[UNROLL], b[UNROLL], c[UNROLL], d[UNROLL];
 #pragma unroll
@@ -230,7 +230,7 @@ __global__ void k_index_gather(ProbeArrays A, uint64_t n_loads, uint64_t seed, u
 			uint64_t g = (uint64_t)(((unsigned __int128)s * total) >> 64);
 			const uint4 *bp = A.base[0]; uint64_t c0 = 0;          // (selects, not a run-time index into the parameter struct)
 #pragma unroll
-			for (int j = 1; j < 6; ++j) if (j < A.n && g >= A.cum[j]) { bp = A.base[j]; c0 = A.cum[j]; }
+			for (int j = 1; j < 6; ++j) if (g >= A.cum[j] && A.cum[j + 1] > A.cum[j]) { bp = A.base[j]; c0 = A.cum[j]; }
 			const uint4 *p = bp + 2 * (g - c0);
 			asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a[u]), "=l"(b[u]), "=l"(c[u]), "=l"(d[u]) : "l"(p));
 		}
@@ -310,6 +310,8 @@ extern "C" int cs_probe_index_gather(const cs_index_t *idx, uint64_t n_loads, in
 		if (I.text) add(I.text, ((I.seq_len + 31) / 32) * 8);
 		if (I.isa) add(I.isa, ((I.seq_len >> I.isa_shift) + 1) * 8);
 		if (I.kt) add(I.kt, (((1ull << (2 * (I.kt_depth + 1))) - 4) / 3) * 16);
+		for (int k = A.n; k < 6; ++k) { A.base[k] = A.base[0]; A.cum[k + 1] = A.cum[A.n]; }
+		A.total = A.cum[A.n];
 	}
 	CK(cudaMalloc(&d_sink, 8));
 	CK(cudaMemset(d_sink, 0, 8));

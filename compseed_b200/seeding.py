@@ -56,13 +56,33 @@ class _Result(C.Structure):
                 ("gather_requests", C.c_uint64 * 6), ("kernel_ms2", C.c_float * 4)]
 
 
+class _Block(C.Structure):
+    _fields_ = [("r0", C.c_uint64), ("r1", C.c_uint64), ("batch_reads", C.c_uint32), ("n_batches", C.c_uint32),
+                ("mem_base", C.POINTER(C.c_uint64)), ("seed_base", C.POINTER(C.c_uint64)),
+                ("mem_off", C.POINTER(C.c_uint32)), ("seed_off", C.POINTER(C.c_uint32)),
+                ("cmems", C.POINTER(C.c_uint32)), ("rbeg_lo", C.POINTER(C.c_uint32)), ("rbeg_hi", C.POINTER(C.c_uint8)),
+                ("device", C.c_int)]
+
+
+class _MultiResult(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_mems", C.c_uint64), ("n_seeds", C.c_uint64), ("n_blocks", C.c_int),
+                ("blocks", C.POINTER(_Block)), ("counters", _Counters), ("seconds", C.c_double)]
+
+
 class _IndexConfig(C.Structure):
     _fields_ = [("kmer_table_depth", C.c_int32), ("prune_k", C.c_int32), ("isa_intv", C.c_int32), ("reserved", C.c_int32)]
 
 
 class _CtxConfig(C.Structure):
     _fields_ = [("use_fast", C.c_int32), ("use_r3_fast", C.c_int32), ("defer_cap", C.c_int32), ("lit_ctas_per_sm", C.c_int32),
-                ("prefetch_results", C.c_int32), ("l2_persist_mb", C.c_int32), ("overlap_streams", C.c_int32), ("reserved", C.c_int32)]
+                ("prefetch_results", C.c_int32), ("l2_persist_mb", C.c_int32), ("overlap_streams", C.c_int32), ("compact_results", C.c_int32)]
+
+
+class _CompactResult(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_mems", C.c_uint64), ("n_seeds", C.c_uint64),
+                ("mem_off", C.POINTER(C.c_uint32)), ("cmems", C.POINTER(C.c_uint32)),
+                ("seed_off", C.POINTER(C.c_uint32)), ("rbeg_lo", C.POINTER(C.c_uint32)), ("rbeg_hi", C.POINTER(C.c_uint8)),
+                ("counters", _Counters)]
 
 
 @dataclass
@@ -86,10 +106,11 @@ class CtxConfig:
     prefetch_results: int = 0
     l2_persist_mb: int = 0
     overlap_streams: int = -1
+    compact_results: int = 0
 
     def _c(self) -> _CtxConfig:
         return _CtxConfig(self.use_fast, self.use_r3_fast, self.defer_cap, self.lit_ctas_per_sm, self.prefetch_results,
-                          self.l2_persist_mb, self.overlap_streams, 0)
+                          self.l2_persist_mb, self.overlap_streams, self.compact_results)
 
 
 _lib = None
@@ -105,6 +126,7 @@ def load_library():
                            "(nvcc, sm_100a).  compseed_b200 has no CPU fallback.")
     L = C.CDLL(LIB_PATH)
     L.cs_last_error.restype = C.c_char_p
+    L.cs_last_error_code.restype = C.c_int
     L.cs_device_count.restype = C.c_int
     L.cs_index_upload.restype = C.c_void_p
     L.cs_index_upload.argtypes = [C.POINTER(_BwtView), C.c_int, C.c_int]
@@ -124,6 +146,20 @@ def load_library():
     L.cs_ctx_create_ex.restype = C.c_void_p
     L.cs_ctx_create_ex.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(_CtxConfig)]
     L.cs_ctx_need.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.cs_seed_batch_wait_compact.argtypes = [C.c_void_p, C.c_int, C.POINTER(_CompactResult)]
+    L.cs_compact_expand.argtypes = [C.POINTER(_CompactResult), C.c_void_p, C.c_void_p, C.c_int]
+    L.cs_multi_create.restype = C.c_void_p
+    L.cs_multi_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(_CtxConfig)]
+    L.cs_multi_free.argtypes = [C.c_void_p]
+    L.cs_index_replicate.restype = C.c_void_p
+    L.cs_index_replicate.argtypes = [C.c_void_p, C.c_int]
+    L.cs_multi_submit.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(_SeedOpt)]
+    L.cs_multi_submit_packed.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SeedOpt)]
+    L.cs_multi_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(_MultiResult)]
+    L.cs_multi_gather.argtypes = [C.POINTER(_MultiResult), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.cs_pack_reads_host64.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.cs_multi_launches.restype = C.c_uint64
+    L.cs_multi_launches.argtypes = [C.c_void_p]
     L.cs_ctx_launches.restype = C.c_uint64
     L.cs_ctx_launches.argtypes = [C.c_void_p]
     L.cs_index_download.argtypes = [C.c_void_p, C.POINTER(_BwtView), C.c_void_p, C.c_void_p, C.c_int]
@@ -210,7 +246,7 @@ class FMIndex:
 
     def __init__(self, handle, device: int):
         if not handle:
-            raise CompSeedError(CS_E_CUDA, load_library().cs_last_error().decode())
+            raise CompSeedError(load_library().cs_last_error_code() or CS_E_CUDA, load_library().cs_last_error().decode())
         self.h = C.c_void_p(handle)
         self.device = device
         v = _BwtView()
@@ -325,7 +361,7 @@ class SeedContext:
         cfg = (config or CtxConfig())._c()
         h = load_library().cs_ctx_create_ex(index.h, max_reads, max_bases, max_read_len, max_mems, max_seeds, n_slots, C.byref(cfg))
         if not h:
-            raise CompSeedError(CS_E_CUDA, load_library().cs_last_error().decode())
+            raise CompSeedError(load_library().cs_last_error_code() or CS_E_CUDA, load_library().cs_last_error().decode())
         self.h = C.c_void_p(h)
 
     def close(self) -> None:
@@ -398,6 +434,27 @@ class SeedContext:
         _check(load_library().cs_seed_batch_wait(self.h, slot, C.byref(r)))
         return self._result(r, copy=copy)
 
+    def wait_compact(self, slot: int, expand_threads: int = 0):
+        """cs_seed_batch_wait_compact.  expand_threads == 0: the compact arrays as they arrived (views into the slot's
+        pinned buffers: mem_off, cmems u32[n_mems, 5], seed_off, rbeg_lo, rbeg_hi); > 0: a SeedResult expanded by
+        cs_compact_expand on that many host threads."""
+        r = _CompactResult()
+        _check(load_library().cs_seed_batch_wait_compact(self.h, slot, C.byref(r)))
+        n, nm, ns = int(r.n_reads), int(r.n_mems), int(r.n_seeds)
+        mem_off = np.ctypeslib.as_array(r.mem_off, shape=(n + 1,))
+        seed_off = np.ctypeslib.as_array(r.seed_off, shape=(n + 1,))
+        if expand_threads <= 0:
+            cm = np.ctypeslib.as_array(r.cmems, shape=(nm, 5)) if nm else np.empty((0, 5), dtype=np.uint32)
+            lo = np.ctypeslib.as_array(r.rbeg_lo, shape=(ns,)) if ns else np.empty(0, dtype=np.uint32)
+            hi = np.ctypeslib.as_array(r.rbeg_hi, shape=(ns,)) if ns else np.empty(0, dtype=np.uint8)
+            return mem_off, cm, seed_off, lo, hi
+        mems = np.empty((nm, 4), dtype=np.uint64)
+        rbeg = np.empty(ns, dtype=np.int64)
+        _check(load_library().cs_compact_expand(C.byref(r), _ptr(mems), _ptr(rbeg), expand_threads))
+        cnt = dict(ext_queries=int(r.counters.ext_queries), ext_calls=int(r.counters.ext_calls),
+                   sal_queries=int(r.counters.sal_queries), sal_calls=int(r.counters.sal_calls))
+        return SeedResult(mem_off.copy(), mems, seed_off.copy(), rbeg, cnt)
+
     @staticmethod
     def _result(r: _Result, copy: bool) -> SeedResult:
         n, nm, ns = int(r.n_reads), int(r.n_mems), int(r.n_seeds)
@@ -454,6 +511,91 @@ def pack_reads(bases: np.ndarray, off: np.ndarray):
     np.bitwise_or.at(keep, word, clear)
     nmask &= ~keep
     assert int((w0 + nw).max()) <= nw_tot
+    return packed, nmask
+
+
+class MultiSeeder:
+    """cs_multi_t: one index replica and one context per device, reads of a set split into contiguous blocks (multiples
+    of 512 reads, comp_seed.h:36) in input order, pipelined by one host thread per device; two sets may be in flight.
+    Replaces kt_for over the reads of a -K batch (bwamem.c:1343, comp_seed.cpp:2541-2548) for the seeding part."""
+
+    def __init__(self, indexes, batch_reads: int = 1 << 20, max_read_len: int = 256, n_slots: int = 3,
+                 mems_per_read: int = 0, seeds_per_read: int = 0, config: "CtxConfig | None" = None):
+        self.indexes = list(indexes)
+        arr = (C.c_void_p * len(self.indexes))(*[i.h for i in self.indexes])
+        cfg = (config or CtxConfig())._c()
+        h = load_library().cs_multi_create(arr, len(self.indexes), batch_reads, max_read_len, n_slots, mems_per_read, seeds_per_read, C.byref(cfg))
+        if not h:
+            raise CompSeedError(load_library().cs_last_error_code() or CS_E_CUDA, load_library().cs_last_error().decode())
+        self.h = C.c_void_p(h)
+        self._keep = {}
+
+    def close(self) -> None:
+        if self.h:
+            load_library().cs_multi_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(load_library().cs_multi_launches(self.h))
+
+    def submit(self, set_id: int, bases, off64, opt: SeedOpt) -> None:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        off64 = np.ascontiguousarray(off64, dtype=np.uint64)
+        self._keep[set_id] = (bases, off64)
+        o = opt._c()
+        _check(load_library().cs_multi_submit(self.h, set_id, off64.shape[0] - 1, _ptr(bases), _ptr(off64), C.byref(o)))
+
+    def submit_packed(self, set_id: int, packed, nmask, off64, opt: SeedOpt) -> None:
+        packed = np.ascontiguousarray(packed, dtype=np.uint64)
+        nmask = np.ascontiguousarray(nmask, dtype=np.uint32)
+        off64 = np.ascontiguousarray(off64, dtype=np.uint64)
+        self._keep[set_id] = (packed, nmask, off64)
+        o = opt._c()
+        _check(load_library().cs_multi_submit_packed(self.h, set_id, off64.shape[0] - 1, _ptr(packed), _ptr(nmask), _ptr(off64), C.byref(o)))
+
+    def wait(self, set_id: int, gather: bool = True, n_threads: int = 4):
+        """Waits for the set.  gather=True: a SeedResult with flat arrays in input order (cs_multi_gather; offsets as u64);
+        gather=False: dict(n_reads, n_mems, n_seeds, seconds, blocks=[(device, r0, r1)]) -- the results stay where the DMA put them."""
+        r = _MultiResult()
+        _check(load_library().cs_multi_wait(self.h, set_id, C.byref(r)))
+        self._keep.pop(set_id, None)
+        info = dict(n_reads=int(r.n_reads), n_mems=int(r.n_mems), n_seeds=int(r.n_seeds), seconds=float(r.seconds),
+                    blocks=[(int(r.blocks[k].device), int(r.blocks[k].r0), int(r.blocks[k].r1)) for k in range(r.n_blocks)],
+                    wire_bytes=8 * int(r.n_reads) + 20 * int(r.n_mems) + 5 * int(r.n_seeds))
+        if not gather:
+            return info
+        n = int(r.n_reads)
+        mem_off = np.empty(n + 1, dtype=np.uint64); seed_off = np.empty(n + 1, dtype=np.uint64)
+        mems = np.empty((int(r.n_mems), 4), dtype=np.uint64); rbeg = np.empty(int(r.n_seeds), dtype=np.int64)
+        _check(load_library().cs_multi_gather(C.byref(r), _ptr(mem_off), _ptr(mems), _ptr(seed_off), _ptr(rbeg), n_threads))
+        cnt = dict(ext_queries=int(r.counters.ext_queries), ext_calls=int(r.counters.ext_calls),
+                   sal_queries=int(r.counters.sal_queries), sal_calls=int(r.counters.sal_calls))
+        res = SeedResult(mem_off, mems, seed_off, rbeg, cnt)
+        res.info = info
+        return res
+
+
+def replicate_index(index: "FMIndex", device: int) -> "FMIndex":
+    """cs_index_replicate: a copy of the index on another device (device-to-device, over NVLink between peers)."""
+    return FMIndex(load_library().cs_index_replicate(index.h, device), device)
+
+
+def pack_reads_host64(bases: np.ndarray, off64: np.ndarray, n_threads: int = 1):
+    """cs_pack_reads_host64: the set-global packed layout cs_multi_submit_packed takes (64-bit offsets)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    off64 = np.ascontiguousarray(off64, dtype=np.uint64)
+    n = off64.shape[0] - 1
+    nw = (int(off64[-1]) >> 5) + 2 * n
+    packed = np.empty(nw, dtype=np.uint64)
+    nmask = np.empty(nw, dtype=np.uint32)
+    _check(load_library().cs_pack_reads_host64(n, _ptr(bases), _ptr(off64), _ptr(packed), _ptr(nmask), n_threads))
     return packed, nmask
 
 

@@ -106,6 +106,39 @@ typedef struct {
 	                              second stream: kernel_ms[5] is then only what is left of it after k_seed), [2] k_pack_reads, [3] unused */
 } cs_result_t;
 
+/* Compact wire format of the results (cs_ctx_config_t.compact_results): what crosses the device-to-host link is 20
+ * bytes per mem and 5 per seed position instead of 32 and 8 (on 150-bp reads 225 instead of 355 bytes per read; the link,
+ * not the GPU, bounds the host-buffer path).  Lossless: seq_len < 2^37 (cs_index_upload rejects more) and read positions
+ * < 2^16 (comp_seed.h:39).  A consumer expands one read at a time where it needs bwtintv_t (cs_cmem_unpack: the kt_for
+ * workers do it in parallel, in place of the memcpy they would do anyway), or all at once (cs_compact_expand). */
+typedef struct {
+	uint32_t x0, x1, x2;    /* low 32 bits of k, l, s */
+	uint32_t info;          /* start << 16 | end */
+	uint32_t hi;            /* bits 0-4: k >> 32, 5-9: l >> 32, 10-14: s >> 32 */
+} cs_cmem_t;
+
+static inline void cs_cmem_unpack(const cs_cmem_t *c, cs_mem_t *m)
+{
+	m->x[0] = (uint64_t)c->x0 | ((uint64_t)(c->hi & 31u) << 32);
+	m->x[1] = (uint64_t)c->x1 | ((uint64_t)((c->hi >> 5) & 31u) << 32);
+	m->x[2] = (uint64_t)c->x2 | ((uint64_t)((c->hi >> 10) & 31u) << 32);
+	m->info = ((uint64_t)(c->info >> 16) << 32) | (uint64_t)(c->info & 0xffffu);
+}
+/* seed position i: 40 bits, sign-extended (bwt_sa of row 0 is (uint64_t)-1, FM_index/bwt.c:83,93) */
+static inline int64_t cs_crbeg(const uint32_t *lo, const uint8_t *hi, uint64_t i)
+{ return (int64_t)(((uint64_t)lo[i] | ((uint64_t)hi[i] << 32)) << 24) >> 24; }
+
+typedef struct {
+	uint32_t n_reads;
+	uint64_t n_mems, n_seeds;
+	const uint32_t *mem_off;   /* [n_reads+1] */
+	const cs_cmem_t *cmems;    /* [n_mems] per read sorted ascending by info */
+	const uint32_t *seed_off;  /* [n_reads+1] */
+	const uint32_t *rbeg_lo;   /* [n_seeds] */
+	const uint8_t  *rbeg_hi;   /* [n_seeds] */
+	cs_counters_t counters;
+} cs_compact_result_t;
+
 typedef struct cs_index cs_index_t;
 typedef struct cs_ctx cs_ctx_t;
 
@@ -131,11 +164,12 @@ typedef struct {
 	int32_t l2_persist_mb;     /* > 0: an L2 access-policy window (persisting) of this many MB over the top of the K-mer table on
 	                              every slot stream (default 0: none; profiles/ has the measurement) */
 	int32_t overlap_streams;   /* 1 (default): kernels of one batch that do not depend on each other run on forked streams */
-	int32_t reserved;
+	int32_t compact_results;   /* 1: the batches also produce the compact wire format (cs_seed_batch_wait_compact); default 0 */
 } cs_ctx_config_t;
 void cs_ctx_config_default(cs_ctx_config_t *cfg);
 
 const char *cs_last_error(void);
+int cs_last_error_code(void);   /* the CS_E_* code that goes with it (for the calls that return a handle, not a code) */
 int cs_device_count(void);
 
 /* --- index ------------------------------------------------------------------------------------
@@ -213,6 +247,71 @@ int cs_seed_batch_submit_packed(cs_ctx_t *ctx, int slot, uint32_t n_reads, const
 /* Waits for the slot, copies the results to its pinned host buffers and fills *out. */
 int cs_seed_batch_wait(cs_ctx_t *ctx, int slot, cs_result_t *out);
 
+/* The same batch in the compact wire format (the ctx must have been created with compact_results = 1). */
+int cs_seed_batch_wait_compact(cs_ctx_t *ctx, int slot, cs_compact_result_t *out);
+/* Expands a compact result into plain arrays (mems: n_mems entries, rbeg: n_seeds) on n_threads host threads. */
+int cs_compact_expand(const cs_compact_result_t *res, cs_mem_t *mems, int64_t *rbeg, int n_threads);
+
+/* --- multi-device pipeline ----------------------------------------------------------------------
+ * Replaces kt_for(opt->n_threads, worker1 / seed_and_extend) over the reads of a -K batch for the seeding part
+ * (mapping/bwamem.c:1343, comp_seed.cpp:2541-2548), and -- with two read sets in flight -- the overlap kt_pipeline gives
+ * between batch i+1 and batch i (fastmap.c:76-140, kthread.c:95-107).  One index replica and one ctx per device; the reads
+ * of a set are split into one contiguous block per device, in input order, each a multiple of 512 reads (BATCH_SIZE,
+ * comp_seed.h:36); one host thread per device pipelines its block in batches through the slots of its ctx.  Results arrive
+ * in the compact wire format, by DMA, in page-locked arrays owned by the cs_multi_t; nothing is exchanged between devices
+ * and no host thread copies a result: gathering in input order is the accessor cs_multi_read. */
+#define CS_MULTI_MAX_DEV 16
+typedef struct cs_multi cs_multi_t;
+
+typedef struct {            /* the reads [r0, r1) of a set, seeded by one device in batches of batch_reads */
+	uint64_t r0, r1;
+	uint32_t batch_reads, n_batches;
+	const uint64_t *mem_base, *seed_base;   /* [n_batches+1] where a batch's mems / seeds start in the arrays below */
+	const uint32_t *mem_off, *seed_off;     /* [n_batches][batch_reads+1] offsets inside the batch */
+	const cs_cmem_t *cmems;                 /* mems of the block, reads in input order, per read sorted by info */
+	const uint32_t *rbeg_lo; const uint8_t *rbeg_hi;
+	int device;
+} cs_block_t;
+
+typedef struct {
+	uint64_t n_reads, n_mems, n_seeds;
+	int n_blocks;
+	const cs_block_t *blocks;   /* in input order; valid until the set is submitted again */
+	cs_counters_t counters;
+	double seconds;             /* submit to the last device finishing */
+} cs_multi_result_t;
+
+/* where read r of the set is: its mems cm[0..n_mems) and the index s0 of its first seed position in (lo, hi) */
+static inline void cs_multi_read(const cs_multi_result_t *res, uint64_t r, const cs_cmem_t **cm, uint32_t *n_mems,
+                                 const uint32_t **lo, const uint8_t **hi, uint64_t *s0, uint32_t *n_seeds)
+{
+	int k = 0;
+	while (k + 1 < res->n_blocks && r >= res->blocks[k].r1) ++k;
+	const cs_block_t *b = &res->blocks[k];
+	const uint64_t lr = r - b->r0, bi = lr / b->batch_reads, i = bi * (b->batch_reads + 1ull) + lr % b->batch_reads;
+	*cm = b->cmems + b->mem_base[bi] + b->mem_off[i]; *n_mems = b->mem_off[i + 1] - b->mem_off[i];
+	*lo = b->rbeg_lo; *hi = b->rbeg_hi; *s0 = b->seed_base[bi] + b->seed_off[i]; *n_seeds = b->seed_off[i + 1] - b->seed_off[i];
+}
+
+/* idx[k]: the index replica on the k-th device to use (cs_index_replicate copies one device-to-device over NVLink).
+ * mems_per_read / seeds_per_read: sizing estimates (0: 16 / 32); buffers grow when a batch needs more. */
+cs_multi_t *cs_multi_create(cs_index_t *const *idx, int n_dev, uint32_t batch_reads, uint32_t max_read_len, int n_slots,
+                            uint32_t mems_per_read, uint32_t seeds_per_read, const cs_ctx_config_t *cfg);
+void cs_multi_free(cs_multi_t *m);
+cs_index_t *cs_index_replicate(const cs_index_t *src, int device);
+/* Starts seeding a read set and returns at once.  set: 0 or 1 (two sets may be in flight: submit batch i+1 while the host
+ * consumes batch i).  offsets: n_reads+1, 64-bit.  bases (nt4 codes) / packed+nmask must stay valid until cs_multi_wait;
+ * page-locked memory (cs_host_register) is read by DMA without a staging copy.  The packed form is the set-global layout
+ * cs_pack_reads_host64 writes: read r owns the words [(offsets[r] >> 5) + 2r, ... + (len_r >> 5) + 2). */
+int cs_multi_submit(cs_multi_t *m, int set, uint64_t n_reads, const uint8_t *bases, const uint64_t *offsets, const cs_seed_opt_t *opt);
+int cs_multi_submit_packed(cs_multi_t *m, int set, uint64_t n_reads, const uint64_t *packed, const uint32_t *nmask,
+                           const uint64_t *offsets, const cs_seed_opt_t *opt);
+int cs_multi_wait(cs_multi_t *m, int set, cs_multi_result_t *out);
+int cs_pack_reads_host64(uint64_t n_reads, const uint8_t *bases, const uint64_t *offsets, uint64_t *packed, uint32_t *nmask, int n_threads);
+/* Flat arrays in input order from a multi result (mem_off / seed_off: n_reads+1 each; mems / rbeg may be NULL). */
+int cs_multi_gather(const cs_multi_result_t *res, uint64_t *mem_off, cs_mem_t *mems, uint64_t *seed_off, int64_t *rbeg, int n_threads);
+uint64_t cs_multi_launches(const cs_multi_t *m);
+
 /* Page-locks a caller-owned buffer (e.g. the read buffer of the batch loop).  cs_seed_batch_submit
  * then DMAs straight out of it instead of staging through the slot's pinned buffer; the caller must
  * leave the bases of a submitted batch untouched until the slot is waited on. */
@@ -241,7 +340,7 @@ int cs_probe_random_gather_ex(int device, uint64_t table_bytes, uint32_t granule
 int cs_probe_index_gather(const cs_index_t *idx, uint64_t n_loads, int iters, int unroll, double *gbytes_per_s, double *gloads_per_s);
 /* Raw device counters of the last finished run on a slot: [0] ext queries, [1] ext calls, [2] extends whose
  * k and l needed two sectors, [3] occurrence-filter probes, [4..19] event counters of a -DCS_STATS build (else 0), [20] reads the fast
- * kernel deferred to the literal kernel, [21] CTAs of k_seed_fast (0 = not available), [22] CTAs of k_seed,
+ * kernel deferred to the literal kernel, [21] CTAs of k_seed_fast (0 = not available), [22] CTAs of k_seed, [23] calls the literal kernel ran,
  * [24..39] event counters of k_seed_fast in a -DCS_STATS build. */
 int cs_debug_stats(cs_ctx_t *ctx, int slot, uint64_t out[40]);
 /* Writes a buffer larger than L2 (flush between timed iterations). */

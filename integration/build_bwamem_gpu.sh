@@ -1,7 +1,7 @@
 #!/bin/bash
 # Builds integration/_build/bwamem_gpu: the reference's bwamem with its seeding replaced by the
-# compseed_b200 C-ABI.  Host code stays unchanged: the five one-line edits below are applied to a
-# SCRATCH COPY of mapping/bwamem.c (never committed); every other file compiles straight from $REF.
+# compseed_b200 C-ABI.  Host code stays unchanged: the one-line edits below are applied to SCRATCH
+# COPIES of mapping/bwamem.c and mapping/fastmap.c (never committed); every other file compiles straight from $REF.
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"; ROOT="$(dirname "$HERE")"
 REF="${REF:-/root/reference}"; OUT="$HERE/_build"; OBJ="$ROOT/oracle/_ref/obj"
@@ -21,12 +21,21 @@ for pat in 'cs_shim.h' 'csgpu_fill_mems' 'csgpu_next_rbeg' 'csgpu_set_read(i);' 
   grep -q "$pat" "$OUT/bwamem_gpu.c" || { echo "patch site not found: $pat"; exit 1; }
 done
 diff -u "$REF/mapping/bwamem.c" "$OUT/bwamem_gpu.c" > "$OUT/bwamem_gpu.patch" || true
+# batch-ahead overlap: step 0 of process() (the reader, fastmap.c:76-103) hands the batch it just read to the GPUs
+sed -e 's|^#include "bwamem.h"|#include "bwamem.h"\n#include "cs_shim.h"|' \
+    -e 's|^\t\treturn ret;|\t\tcsgpu_prefetch_batch(aux->opt, aux->idx->bwt, ret->n_seqs, ret->seqs); /* added: seed batch i+1 while batch i is chained */\n\t\treturn ret;|' \
+    "$REF/mapping/fastmap.c" > "$OUT/fastmap_gpu.c"
+for pat in 'cs_shim.h' 'csgpu_prefetch_batch'; do
+  grep -q "$pat" "$OUT/fastmap_gpu.c" || { echo "patch site not found in fastmap.c: $pat"; exit 1; }
+done
+diff -u "$REF/mapping/fastmap.c" "$OUT/fastmap_gpu.c" >> "$OUT/bwamem_gpu.patch" || true
 CF="-O3 -g0 -fcommon -mavx2 -w -I$REF -I$REF/mapping -I$HERE -I$ROOT/include"
 gcc $CF -c "$OUT/bwamem_gpu.c" -o "$OUT/bwamem_gpu.o"
+gcc $CF -I"$REF/bwalib" -c "$OUT/fastmap_gpu.c" -o "$OUT/fastmap_gpu.o"
 gcc $CF -c "$HERE/cs_shim.c" -o "$OUT/cs_shim.o"
-gcc -o "$OUT/bwamem_gpu" "$OUT/bwamem_gpu.o" "$OUT/cs_shim.o" \
+gcc -o "$OUT/bwamem_gpu" "$OUT/bwamem_gpu.o" "$OUT/fastmap_gpu.o" "$OUT/cs_shim.o" \
     "$OBJ"/cstl/kstring.o "$OBJ"/cstl/kthread.o "$OBJ"/FM_index/{bntseq,bwt,bwt_gen,is,QSufSort,rle,rope}.o \
-    "$OBJ"/bwalib/{bwashm,bwa,kopen,ksw,utils}.o "$OBJ"/mapping/{bwamem_pair,bwamem_extra,fastmap}.o \
+    "$OBJ"/bwalib/{bwashm,bwa,kopen,ksw,utils}.o "$OBJ"/mapping/{bwamem_pair,bwamem_extra}.o \
     -L"$ROOT/compseed_b200/_lib" -lcompseed_b200 -Wl,-rpath,'$ORIGIN/../../compseed_b200/_lib' -Wl,-rpath,/usr/local/cuda/lib64 \
     -L/usr/local/cuda/lib64 -lcudart -lstdc++ -lm -lz -lpthread -lrt
 echo "built $OUT/bwamem_gpu"; grep -c '^[+-][^+-]' "$OUT/bwamem_gpu.patch" | sed 's/^/changed lines in bwamem.c: /'

@@ -1,5 +1,5 @@
 /* Reference-side binding of compseed_b200: the five calls a maintainer adds to mapping/bwamem.c
- * (integration/build_bwamem_gpu.sh applies them to a scratch copy). */
+ * (integration/build_bwamem_gpu.sh applies them to scratch copies of bwamem.c and fastmap.c). */
 #ifndef CS_SHIM_H
 #define CS_SHIM_H
 #include <stdint.h>
@@ -9,7 +9,10 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
-/* bwamem.c:1343, before kt_for(worker1): seed the whole -K batch on the GPU */
+/* fastmap.c:98, end of step 0 of process(): hand the batch just read to the GPUs and return at once (batch i+1 is seeded
+ * while the host chains / extends batch i) */
+void csgpu_prefetch_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const bseq1_t *seqs);
+/* bwamem.c:1343, before kt_for(worker1): wait for the batch's seeds (or seed it now if it was not prefetched) */
 void csgpu_seed_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const bseq1_t *seqs);
 /* bwamem.c:1299-1305, worker1: which read the calling thread is about to align */
 void csgpu_set_read(int i);

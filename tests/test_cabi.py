@@ -19,7 +19,8 @@ def lib_path():
 def _declared_symbols():
     txt = open(os.path.join(ROOT, "include", "compseed_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(cs_[a-z0-9_]+)\s*\(", txt)))
+    inline = set(re.findall(r"static inline [^(]*?\b(cs_[a-z0-9_]+)\s*\(", txt))   # accessors defined in the header itself
+    return sorted(set(re.findall(r"\b(cs_[a-z0-9_]+)\s*\(", txt)) - inline)
 
 
 def test_library_exports_every_declared_symbol(lib_path):
@@ -123,3 +124,33 @@ def test_library_reads_no_environment_switches():
     """Behaviour is configured through cs_index_config_t / cs_ctx_config_t, never through getenv inside the library."""
     for f in os.listdir(os.path.join(ROOT, "compseed_b200", "csrc")):
         assert "getenv" not in open(os.path.join(ROOT, "compseed_b200", "csrc", f)).read(), f
+
+
+def test_compact_wire_format_spec():
+    """cs_cmem_t / cs_crbeg as the header defines them, exercised through the host-side cs_compact_expand (no device):
+    20 bytes per mem (three low words, start << 16 | end, five high bits of each coordinate), 40-bit sign-extended positions."""
+    import ctypes as C
+    import compseed_b200 as cs
+    from compseed_b200 import seeding as S
+    L = cs.load_library()
+    rng = np.random.default_rng(1)
+    n_m, n_s = 5000, 7000
+    x = rng.integers(0, 1 << 37, (n_m, 3), dtype=np.uint64)
+    start = rng.integers(0, 1 << 16, n_m, dtype=np.uint64)
+    end = rng.integers(0, 1 << 16, n_m, dtype=np.uint64)
+    rbeg = rng.integers(0, 1 << 37, n_s, dtype=np.int64)
+    rbeg[:3] = [-1, 0, (1 << 37) - 1]
+    cm = np.zeros((n_m, 5), dtype=np.uint32)
+    cm[:, 0:3] = (x & np.uint64(0xffffffff)).astype(np.uint32)
+    cm[:, 3] = ((start << np.uint64(16)) | end).astype(np.uint32)
+    cm[:, 4] = ((x[:, 0] >> np.uint64(32)) | ((x[:, 1] >> np.uint64(32)) << np.uint64(5)) | ((x[:, 2] >> np.uint64(32)) << np.uint64(10))).astype(np.uint32)
+    lo = (rbeg & 0xffffffff).astype(np.uint32)
+    hi = ((rbeg >> 32) & 0xff).astype(np.uint8)
+    r = S._CompactResult()
+    r.n_reads, r.n_mems, r.n_seeds = 1, n_m, n_s
+    r.cmems = cm.ctypes.data_as(C.POINTER(C.c_uint32)); r.rbeg_lo = lo.ctypes.data_as(C.POINTER(C.c_uint32)); r.rbeg_hi = hi.ctypes.data_as(C.POINTER(C.c_uint8))
+    for threads in (1, 5):
+        mems = np.zeros((n_m, 4), dtype=np.uint64); out = np.zeros(n_s, dtype=np.int64)
+        assert L.cs_compact_expand(C.byref(r), mems.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), threads) == 0
+        assert np.array_equal(mems[:, :3], x) and np.array_equal(mems[:, 3], (start << np.uint64(32)) | end)
+        assert np.array_equal(out, rbeg)

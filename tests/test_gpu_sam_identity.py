@@ -52,9 +52,16 @@ def test_sam_is_byte_identical(cuda_lib, tmp_path, kind):
     # a different -K only moves batch boundaries: same SAM for single-end input
     got2 = _run(GPUBIN, ["-t", "2", "-K", "50000", idx, reads], os.path.join(d, "gpu2.sam"))
     assert got2 == want
-    # the shim sending the reads 2-bit packed (cs_seed_batch_submit_packed)
-    got3 = _run(GPUBIN, ["-t", "4", "-K", "200000", idx, reads], os.path.join(d, "gpu3.sam"), env={"CSGPU_PACKED": "1"})
+    # without the batch-ahead prefetch from the reader step (every batch seeded at the start of its own step 1), and with
+    # pipeline batches far smaller than the -K batch (many batches per set, several sets)
+    got3 = _run(GPUBIN, ["-t", "4", "-K", "200000", idx, reads], os.path.join(d, "gpu3.sam"), env={"CSGPU_NO_PREFETCH": "1"})
     assert got3 == want
+    got4 = _run(GPUBIN, ["-t", "3", "-K", "30000", idx, reads], os.path.join(d, "gpu4.sam"), env={"CSGPU_BATCH": "700"})
+    assert got4 == want
+    # every visible GPU (the index replicated device-to-device, one contiguous block of each batch per GPU) or just one
+    got5 = _run(GPUBIN, ["-t", "4", "-K", "100000", idx, reads], os.path.join(d, "gpu5.sam"), env={"CSGPU_DEVICES": "all", "CSGPU_BATCH": "1024"})
+    got6 = _run(GPUBIN, ["-t", "4", "-K", "100000", idx, reads], os.path.join(d, "gpu6.sam"), env={"CSGPU_DEVICES": "1"})
+    assert got5 == want and got6 == want
     # non-default seeding options travel through the shim
     a = _run(os.path.join(REFBIN, "bwamem"), ["-t", "4", "-k", "15", "-r", "1.0", "-y", "40", "-c", "50", idx, reads], os.path.join(d, "a.sam"))
     b = _run(GPUBIN, ["-t", "4", "-k", "15", "-r", "1.0", "-y", "40", "-c", "50", idx, reads], os.path.join(d, "b.sam"))
