@@ -48,8 +48,9 @@ def parse_args():
     ap.add_argument("--e2e-input", default="packed", choices=["packed", "bytes"],
                     help="what crosses the host-to-device link on the host-buffer path: 2-bit packed reads (cs_seed_batch_submit_packed) or nt4 bytes")
     ap.add_argument("--l2-persist-mb", type=int, default=0, help="cs_ctx_config_t.l2_persist_mb for the contexts of this run")
-    ap.add_argument("--no-overlap", action="store_true", help="cs_ctx_config_t.overlap_streams = 0")
-    ap.add_argument("--isa-intv", type=int, default=-1, help="cs_index_config_t.isa_intv (sampling of the inverse SA; -1 = default 4)")
+    ap.add_argument("--overlap", action="store_true", help="cs_ctx_config_t.overlap_streams = 1")
+    ap.add_argument("--e2e-only", action="store_true", help="experiments: only the host-buffer leg (prints its dict, not a bench line)")
+    ap.add_argument("--isa-intv", type=int, default=-1, help="cs_index_config_t.isa_intv (sampling of the inverse SA; -1 = default 2)")
     ap.add_argument("--lit-ctas", type=int, default=-1, help="cs_ctx_config_t.lit_ctas_per_sm")
     return ap.parse_args()
 
@@ -158,6 +159,40 @@ def work_counters(host_idx, bases, off, n_sample: int, threads: int):
     return {k: c[k] / n for k in c}, r, n
 
 
+def e2e_only(args, cs, idx, bases, off, opt, ccfg, threads):
+    """Experiments on the host-buffer path: one line per (input form) with where the pipeline's host thread spent its time."""
+    n_reads = off.shape[0] - 1
+    off64 = off.astype(np.uint64)
+    for packed_in in ((True, False) if args.e2e_input == "packed" else (False,)):
+        if packed_in:
+            pk, nm = cs.pack_reads_host64(bases, off64, threads)
+            cs.host_register(pk); cs.host_register(nm)
+        else:
+            cs.host_register(bases)
+        ms_ = cs.MultiSeeder([idx], batch_reads=min(args.e2e_batch, n_reads), max_read_len=args.read_len, n_slots=args.e2e_slots,
+                             mems_per_read=14, seeds_per_read=20, config=ccfg)
+        sub = (lambda s: ms_.submit_packed(s, pk, nm, off64, opt)) if packed_in else (lambda s: ms_.submit(s, bases, off64, opt))
+        for _ in range(2):
+            sub(0); sub(1); ms_.wait(0, gather=False); ms_.wait(1, gather=False)
+        t0 = time.perf_counter()
+        sub(0)
+        infos = []
+        for i in range(1, args.steps):
+            sub(i & 1)
+            infos.append(ms_.wait((i - 1) & 1, gather=False))
+        infos.append(ms_.wait((args.steps - 1) & 1, gather=False))
+        dt = time.perf_counter() - t0
+        hs = {k: float(np.mean([x["host_s"][k] for x in infos])) for k in infos[0]["host_s"]}
+        print(json.dumps({"e2e_reads_per_s": n_reads * args.steps / dt, "input": "packed" if packed_in else "bytes", "batch": args.e2e_batch, "slots": args.e2e_slots,
+                          "set_seconds": float(np.mean([x["seconds"] for x in infos])), "host_thread_s_per_set": hs, "wire_bytes": infos[-1]["wire_bytes"]}))
+        ms_.close()
+        if packed_in:
+            cs.host_unregister(pk); cs.host_unregister(nm)
+        else:
+            cs.host_unregister(bases)
+    return 0
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -242,7 +277,10 @@ def main():
                  "what": "independent uniformly random 32-byte sector loads, 1184 CTAs x 256 threads, measured in this run before the timed region: over this "
                          "index's own arrays (cs_probe_index_gather, each load picks an array in proportion to its size) and over one 16 GiB table "
                          "(cs_probe_random_gather); the roofline peak is the best of the four"}
-    ccfg = cs.CtxConfig(l2_persist_mb=args.l2_persist_mb, overlap_streams=0 if args.no_overlap else -1, lit_ctas_per_sm=args.lit_ctas)
+    ccfg = cs.CtxConfig(l2_persist_mb=args.l2_persist_mb, overlap_streams=1 if args.overlap else 0, lit_ctas_per_sm=args.lit_ctas)
+
+    if args.e2e_only:
+        return e2e_only(args, cs, idx, bases, off, opt, ccfg, threads)
 
     # (1) device-resident: all reads of the step staged in HBM once
     max_mems, max_seeds = n_reads * 14, n_reads * 20
@@ -438,7 +476,7 @@ def main():
                 "all_kernels": {k: {"ms_per_step": ms[n] / steps, "requests_per_read": req[i] / steps / n_reads if i is not None else None,
                                     "grequests_per_s": (req[i] / ms[n] / 1e6) if (i is not None and ms[n] > 0) else None}
                                 for k, n, i in (("k_pack_reads", "pack", None), ("k_seed_fast", "fast", 0), ("k_seed_walk", "walk", 1), ("k_seed", "lit", 2),
-                                                ("third pass (own stream, overlaps k_seed_walk / k_seed)", "r3", 3), ("collect", "collect", None), ("k_sa_resolve", "sa", 4))},
+                                                ("third pass", "r3", 3), ("collect", "collect", None), ("k_sa_resolve", "sa", 4))},
                 "kernel_share_of_step": {"k_pack_reads": ms["pack"] / dev_ms, "k_seed_fast": ms["fast"] / dev_ms, "k_seed_walk": ms["walk"] / dev_ms, "k_seed": ms["lit"] / dev_ms,
                                          "third_pass_not_hidden": ms["r3_tail"] / dev_ms, "collect": ms["collect"] / dev_ms, "k_sa_resolve": ms["sa"] / dev_ms},
                 "deferred_calls_per_read": counters.get("deferred_calls", 0) / n_reads}
@@ -462,7 +500,7 @@ def main():
                        "result_neutral_structures": "dense SA, top-of-search k-mer table (depth <= 13), 2-bit occurrence filter (K <= 19), "
                                                     "2-bit text + sampled inverse SA for unique matches (DESIGN.md section 5)",
                        "l2_policy": "inputs larger than L2 (index %.1f GB, reads %.1f GB per step)" % (idx.device_bytes / 1e9, bases.nbytes / 1e9),
-                       "l2_persist_mb": args.l2_persist_mb, "overlap_streams": not args.no_overlap, "isa_intv": args.isa_intv, "lit_ctas_per_sm": args.lit_ctas,
+                       "l2_persist_mb": args.l2_persist_mb, "overlap_streams": bool(args.overlap), "isa_intv": args.isa_intv, "lit_ctas_per_sm": args.lit_ctas,
                        "library_tag": os.environ.get("COMPSEED_LIB_TAG", ""),
                        "parallelism": f"index replicated x{world}, reads sharded in contiguous blocks, host gather, no collective"},
             "parity": parity, "index_verify": index_verify,

@@ -47,6 +47,7 @@ int cs_use_device(int device)
 	if (device < 0 || device >= n) return set_err(CS_E_ARG, "device %d out of range (%d visible)", device, n);
 	cudaError_t e = cudaSetDevice(device);
 	if (e != cudaSuccess) return set_err(CS_E_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+	cudaGetLastError();   // an error some earlier call of this thread left behind must not be blamed on the next launch
 	return CS_OK;
 }
 #define use_device cs_use_device
@@ -61,17 +62,17 @@ extern "C" void cs_ctx_config_default(cs_ctx_config_t *cfg)
 {
 	if (!cfg) return;
 	cfg->use_fast = -1; cfg->use_r3_fast = -1; cfg->defer_cap = -1; cfg->lit_ctas_per_sm = -1;
-	cfg->prefetch_results = 0; cfg->l2_persist_mb = 0; cfg->overlap_streams = -1; cfg->compact_results = 0;
+	cfg->prefetch_results = 0; cfg->l2_persist_mb = 0; cfg->overlap_streams = 0; cfg->compact_results = 0;
 }
 
 static uint64_t kt_offset_host(uint32_t d) { return ((1ull << (2 * d)) - 4) / 3; }   // entries of depths 1 .. d-1 (kt_offset, cs_device.cuh)
 static int log2_exact(uint64_t v) { int s = 0; while ((1ull << s) < v) ++s; return (1ull << s) == v ? s : -1; }
 
 // Unique-match fast path (cs_device.cuh): 2-bit text in read bit order + sampled inverse SA.  Only with a
-// dense SA.  cfg.isa_intv sets the ISA sampling (power of two, default 4; 0 disables the fast path).
+// dense SA.  cfg.isa_intv sets the ISA sampling (power of two, default 2; 0 disables the fast path).
 static int cs_internal_build_text(cs_index *idx, const uint64_t *W)
 {
-	int intv = idx->cfg.isa_intv < 0 ? 4 : idx->cfg.isa_intv, shift = 0;
+	int intv = idx->cfg.isa_intv < 0 ? 2 : idx->cfg.isa_intv, shift = 0;   // default 2: 4 more bytes per row than 4, 7 % off a cfg2 step (fewer LF steps after every inverse-SA lookup)
 	const uint64_t n = idx->d.seq_len;
 	idx->d.text = nullptr; idx->d.isa = nullptr; idx->d.isa_shift = 0; idx->d_text = nullptr; idx->d_isa = nullptr;
 	if (intv <= 0 || idx->d.sa_mask != 0 || !W) return CS_OK;
@@ -545,6 +546,7 @@ struct Slot {
 
 struct cs_ctx {
 	const cs_index *idx;
+	int device;           // (the ctx may outlive a careless caller's index handle: never read idx->device when freeing)
 	uint32_t max_reads, max_read_len;
 	uint64_t max_bases, max_mems, max_seeds;
 	int n_slots;
@@ -583,7 +585,7 @@ static void slot_free(Slot *s)
 extern "C" void cs_ctx_free(cs_ctx_t *ctx)
 {
 	if (!ctx) return;
-	cudaSetDevice(ctx->idx->device);
+	cudaSetDevice(ctx->device);
 	for (int i = 0; i < ctx->n_slots; ++i) slot_free(&ctx->slots[i]);
 	free(ctx->slots); free(ctx);
 }
@@ -617,7 +619,7 @@ extern "C" cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads,
 	ctx = (cs_ctx*)calloc(1, sizeof(cs_ctx));
 	if (!ctx) { set_err(CS_E_ARG, "out of host memory"); return nullptr; }
 	if (cfg) ctx->cfg = *cfg; else cs_ctx_config_default(&ctx->cfg);
-	ctx->idx = idx; ctx->max_reads = max_reads; ctx->max_bases = max_bases; ctx->max_read_len = max_read_len;
+	ctx->idx = idx; ctx->device = idx->device; ctx->max_reads = max_reads; ctx->max_bases = max_bases; ctx->max_read_len = max_read_len;
 	ctx->max_mems = max_mems ? max_mems : (uint64_t)max_reads * 16;
 	ctx->max_seeds = max_seeds ? max_seeds : (uint64_t)max_reads * 32;
 	if (ctx->max_mems >= (1ull << 32) || ctx->max_seeds >= (1ull << 32)) { set_err(CS_E_ARG, "result capacities must be < 2^32 per slot"); free(ctx); return nullptr; }
@@ -751,7 +753,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	SeedArgs a;
 	CollectArgs c;
 	const bool pass3 = opt->max_mem_intv > 0;
-	const bool overlap = ctx->cfg.overlap_streams != 0;
+	const bool overlap = ctx->cfg.overlap_streams > 0;
 	// The third pass depends on k_seed_fast alone (text-assisted: it reads the first-pass SMEMs k_seed_fast left in the
 	// pool) or on nothing (k_seed_r3): it runs on the slot's second stream, next to k_seed_walk / k_seed, whose few long
 	// tasks leave most of the GPU idle.

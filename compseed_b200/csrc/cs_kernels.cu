@@ -1089,9 +1089,9 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			cnt0 = 32; if ((uint32_t)cx < cnt0) cnt0 = (uint32_t)cx; if (tp0 < cnt0) cnt0 = (uint32_t)tp0;
 			if (cnt0) { bw0 = packed_window(I.text, tp0 - cnt0); n_req += 1u + (((tp0 - cnt0) & 31) != 0); }
 			uint64_t tpos = tp0 + (uint64_t)(i - cx);
-			// Up to CS_FWD_WIN windows of 32 bases are fetched at once (all their loads in flight together) instead of one
-			// per trip of a loop whose trip count differs from lane to lane: at 1 % substitutions a unique match runs on for
-			// ~100 bases, so most of the words are needed, and the warp no longer waits four times for its longest lane.
+			// CS_FWD_WIN windows of 32 bases are fetched per trip (all their loads in flight together).  More than one looked
+			// attractive (at 1 % substitutions a unique match runs on for ~100 bases, and the trip count differs from lane to
+			// lane) but measured slower: see CS_FWD_WIN in cs_kernels.cuh.
 			for (bool go = true; go; ) {
 				const uint64_t left = I.seq_len - tpos;
 				uint64_t room = (uint64_t)(len - i); if (left < room) room = left;            // bases that can still match

@@ -24,8 +24,8 @@
 #define CS_WALK_MAX 6           // short forward matches a call may have to be walked by k_seed_walk (else k_seed)
 #endif
 #ifndef CS_FWD_WIN
-#define CS_FWD_WIN 4            // 32-base text windows k_seed_fast fetches at once when it follows a unique match forward
-#endif
+#define CS_FWD_WIN 1            // 32-base text windows k_seed_fast fetches at once when it follows a unique match forward.  Measured on
+#endif                          // cfg2 (4 M reads, profiles/r02_variants.json): 1: 12.34 ms, 2: 12.52 ms, 4: 13.30 ms -- the extra loads and registers cost more than the shorter dependent chain saves
 #define CS_FAST_SMEM_BYTES ((size_t)CS_FAST_BLOCK * (CS_READ_SMEM * 12))
 
 struct SeedArgs {

@@ -52,6 +52,7 @@ struct Dev {
 	BlockBuf buf[2];
 	int rc[2]; char err[2][512];
 	uint64_t n_mems[2], n_seeds[2]; cs_counters_t cnt[2];
+	double host_s[2][3];               // seconds spent submitting / waiting for kernels / waiting for copies
 	bool done[2];
 };
 
@@ -112,6 +113,7 @@ int run_block(Dev *d, const Job &j)
 	memset(&b.pub, 0, sizeof b.pub);
 	b.pub.r0 = r0; b.pub.r1 = r1; b.pub.batch_reads = m->batch_reads; b.pub.n_batches = nb; b.pub.device = d->idx->device;
 	d->n_mems[j.set] = d->n_seeds[j.set] = 0; memset(&d->cnt[j.set], 0, sizeof(cs_counters_t));
+	d->host_s[j.set][0] = d->host_s[j.set][1] = d->host_s[j.set][2] = 0;
 	if (n == 0) return CS_OK;
 	if (cs_use_device(d->idx->device) != CS_OK) return CS_E_CUDA;
 	{
@@ -132,18 +134,33 @@ int run_block(Dev *d, const Job &j)
 	b.mem_base[0] = b.seed_base[0] = 0;
 	uint32_t next = 0, done = 0;       // batches submitted / completed (kernels finished and result copy enqueued)
 	uint32_t copied = 0;               // batches whose result copy has been waited for
+	double *hs = d->host_s[j.set];
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
 	auto submit = [&](uint32_t bi) -> int {
+		const auto t = now();
 		const uint64_t s = r0 + (uint64_t)bi * B, e = std::min<uint64_t>(r1, s + B);
-		return cs_i_submit(d->ctx, (int)(bi % m->n_slots), (uint32_t)(e - s), j.off, j.bases, j.packed, j.nmask, s, &j.opt);
+		const int rc_ = cs_i_submit(d->ctx, (int)(bi % m->n_slots), (uint32_t)(e - s), j.off, j.bases, j.packed, j.nmask, s, &j.opt);
+		hs[0] += since(t);
+		return rc_;
 	};
-	auto wait_copy = [&](uint32_t bi) -> int { return cs_i_fetch_wait(d->ctx, (int)(bi % m->n_slots), &d->cnt[j.set], nullptr); };
+	auto wait_copy = [&](uint32_t bi) -> int {
+		const auto t = now();
+		const int rc_ = cs_i_fetch_wait(d->ctx, (int)(bi % m->n_slots), &d->cnt[j.set], nullptr);
+		hs[2] += since(t);
+		return rc_;
+	};
 	while (done < nb) {
 		while (next < nb && next - copied < (uint32_t)m->n_slots) { // a slot is free once its previous batch's copy has landed
 			if ((rc = submit(next)) != CS_OK) return rc;
 			++next;
 		}
 		uint64_t nm = 0, ns = 0;
-		rc = cs_i_finish(d->ctx, (int)(done % m->n_slots), &nm, &ns);
+		{
+			const auto t = now();
+			rc = cs_i_finish(d->ctx, (int)(done % m->n_slots), &nm, &ns);
+			hs[1] += since(t);
+		}
 		if (rc == CS_E_OVERFLOW) { // this batch needs larger slot buffers: drain, re-create the ctx once with what it needs, resubmit from here
 			uint64_t need_m = 0, need_s = 0;
 			cs_ctx_need(d->ctx, (int)(done % m->n_slots), &need_m, &need_s);
@@ -289,6 +306,8 @@ extern "C" int cs_multi_wait(cs_multi_t *m, int set, cs_multi_result_t *out)
 		out->n_mems += d->n_mems[set]; out->n_seeds += d->n_seeds[set];
 		out->counters.ext_queries += d->cnt[set].ext_queries; out->counters.ext_calls += d->cnt[set].ext_calls;
 		out->counters.sal_queries += d->cnt[set].sal_queries; out->counters.sal_calls += d->cnt[set].sal_calls;
+		if (d->host_s[set][0] + d->host_s[set][1] + d->host_s[set][2] > out->host_s[0] + out->host_s[1] + out->host_s[2])
+			for (int q = 0; q < 3; ++q) out->host_s[q] = d->host_s[set][q];
 	}
 	m->busy[set] = false;
 	out->n_reads = m->n_reads[set]; out->n_blocks = m->n_dev; out->blocks = m->blocks[set];

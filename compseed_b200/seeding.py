@@ -66,7 +66,7 @@ class _Block(C.Structure):
 
 class _MultiResult(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_mems", C.c_uint64), ("n_seeds", C.c_uint64), ("n_blocks", C.c_int),
-                ("blocks", C.POINTER(_Block)), ("counters", _Counters), ("seconds", C.c_double)]
+                ("blocks", C.POINTER(_Block)), ("counters", _Counters), ("seconds", C.c_double), ("host_s", C.c_double * 3)]
 
 
 class _IndexConfig(C.Structure):
@@ -105,7 +105,7 @@ class CtxConfig:
     lit_ctas_per_sm: int = -1
     prefetch_results: int = 0
     l2_persist_mb: int = 0
-    overlap_streams: int = -1
+    overlap_streams: int = 0
     compact_results: int = 0
 
     def _c(self) -> _CtxConfig:
@@ -568,7 +568,8 @@ class MultiSeeder:
         self._keep.pop(set_id, None)
         info = dict(n_reads=int(r.n_reads), n_mems=int(r.n_mems), n_seeds=int(r.n_seeds), seconds=float(r.seconds),
                     blocks=[(int(r.blocks[k].device), int(r.blocks[k].r0), int(r.blocks[k].r1)) for k in range(r.n_blocks)],
-                    wire_bytes=8 * int(r.n_reads) + 20 * int(r.n_mems) + 5 * int(r.n_seeds))
+                    wire_bytes=8 * int(r.n_reads) + 20 * int(r.n_mems) + 5 * int(r.n_seeds),
+                    host_s=dict(submit=float(r.host_s[0]), kernel_wait=float(r.host_s[1]), copy_wait=float(r.host_s[2])))
         if not gather:
             return info
         n = int(r.n_reads)

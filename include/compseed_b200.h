@@ -147,7 +147,7 @@ typedef struct cs_ctx cs_ctx_t;
 typedef struct {
 	int32_t kmer_table_depth;  /* top-of-search table of every string of <= this many bases (default: up to 13); 0 = none */
 	int32_t prune_k;           /* K of the K-mer occurrence filter (default ceil(log4 seq_len)+2, at most 19); 0 = none */
-	int32_t isa_intv;          /* sampling of the inverse SA used by the unique-match paths (power of two, default 4); 0 = no
+	int32_t isa_intv;          /* sampling of the inverse SA used by the unique-match paths (power of two, default 2); 0 = no
 	                              2-bit text / inverse SA (the fast kernels are then not used) */
 	int32_t reserved;
 } cs_index_config_t;
@@ -163,7 +163,9 @@ typedef struct {
 	int32_t prefetch_results;  /* 1: result copies of finished slots are enqueued while the host waits on another (default 0) */
 	int32_t l2_persist_mb;     /* > 0: an L2 access-policy window (persisting) of this many MB over the top of the K-mer table on
 	                              every slot stream (default 0: none; profiles/ has the measurement) */
-	int32_t overlap_streams;   /* 1 (default): kernels of one batch that do not depend on each other run on forked streams */
+	int32_t overlap_streams;   /* 1: the third-pass kernel of a batch runs on a forked stream next to k_seed_walk / k_seed, on which it
+	                              does not depend.  Default 0: measured neutral on one B200 (every kernel of the batch fills the GPU: what
+	                              the third pass gains, k_seed loses; profiles/r02_variants.json), and serial kernels time cleanly */
 	int32_t compact_results;   /* 1: the batches also produce the compact wire format (cs_seed_batch_wait_compact); default 0 */
 } cs_ctx_config_t;
 void cs_ctx_config_default(cs_ctx_config_t *cfg);
@@ -279,6 +281,8 @@ typedef struct {
 	const cs_block_t *blocks;   /* in input order; valid until the set is submitted again */
 	cs_counters_t counters;
 	double seconds;             /* submit to the last device finishing */
+	double host_s[3];           /* where the slowest device's host thread spent that time: [0] submitting batches (offsets, enqueueing
+	                               copies and kernels), [1] waiting for kernels, [2] waiting for result copies */
 } cs_multi_result_t;
 
 /* where read r of the set is: its mems cm[0..n_mems) and the index s0 of its first seed position in (lo, hi) */

@@ -317,3 +317,56 @@ def bwaidx(fasta: str, prefix: str) -> None:
     """Run the reference's own index builder (oracle/_ref/bwaidx)."""
     subprocess.check_call([os.path.join(REF_BIN, "bwaidx"), "-p", prefix, fasta],
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+# ---------------------------------------------------------------------------------------------
+# Chains (SURVEY 8f-1): the reference's own mem_chain + mem_chain_flt on given mems / seeds
+# ---------------------------------------------------------------------------------------------
+class _ChainOpt(C.Structure):
+    _fields_ = [("w", C.c_int32), ("max_chain_gap", C.c_int32), ("min_chain_weight", C.c_int32), ("max_chain_extend", C.c_int32),
+                ("mask_level", C.c_float), ("drop_ratio", C.c_float)]
+
+
+@dataclass
+class ChainResult:
+    chain_off: np.ndarray   # u32 [n_reads+1]
+    pos: np.ndarray         # i64 [n_chains]
+    rid: np.ndarray         # i32
+    w: np.ndarray           # i32
+    kept: np.ndarray        # i32  kept | is_alt << 8
+    n: np.ndarray           # i32  seeds in the chain
+    s_rbeg: np.ndarray      # i64 [n_chain_seeds], chain after chain
+    s_qbeg: np.ndarray      # i32
+    s_len: np.ndarray       # i32
+    frac_rep: np.ndarray    # f32 [n_reads]
+
+
+def ref_chain(read_off, res: SeedResult, contig_lens, min_seed_len=19, split_factor=1.5, split_width=10, max_mem_intv=20, max_occ=500,
+              w=100, max_chain_gap=10000, min_chain_weight=0, max_chain_extend=1 << 30, mask_level=0.5, drop_ratio=0.5, is_alt=None) -> ChainResult:
+    """mem_chain + mem_chain_flt of the unmodified reference (comp_seed.cpp:241-354) on the mems / seeds of `res`.
+    contig_lens: lengths of the reference sequences (their sum is l_pac).  Defaults: mem_opt_init, comp_seed.cpp:26-61."""
+    L = ref_lib()
+    L.csref_chain.restype = C.c_void_p
+    L.csref_chain.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.POINTER(_RefOpt), C.POINTER(_ChainOpt), C.c_int, C.c_void_p, C.c_void_p]
+    L.csref_chains_n.restype = C.c_uint64; L.csref_chains_n.argtypes = [C.c_void_p]
+    L.csref_chains_n_seeds.restype = C.c_uint64; L.csref_chains_n_seeds.argtypes = [C.c_void_p]
+    L.csref_chains_copy.argtypes = [C.c_void_p] * 11
+    L.csref_chains_free.argtypes = [C.c_void_p]
+    read_off = np.ascontiguousarray(read_off, dtype=np.uint32)
+    mem_off = np.ascontiguousarray(res.mem_off, dtype=np.uint32); mems = np.ascontiguousarray(res.mems, dtype=np.uint64)
+    seed_off = np.ascontiguousarray(res.seed_off, dtype=np.uint32); rbeg = np.ascontiguousarray(res.rbeg, dtype=np.int64)
+    lens = np.ascontiguousarray(contig_lens, dtype=np.int32)
+    alt = np.ascontiguousarray(is_alt if is_alt is not None else np.zeros(lens.shape[0]), dtype=np.uint8)
+    n = read_off.shape[0] - 1
+    so = _RefOpt(min_seed_len, split_factor, split_width, max_mem_intv, max_occ)
+    co = _ChainOpt(w, max_chain_gap, min_chain_weight, max_chain_extend, mask_level, drop_ratio)
+    h = L.csref_chain(n, _ptr(read_off), _ptr(mem_off), _ptr(mems), _ptr(seed_off), _ptr(rbeg), C.byref(so), C.byref(co), lens.shape[0], _ptr(lens), _ptr(alt))
+    try:
+        nc, ns = int(L.csref_chains_n(h)), int(L.csref_chains_n_seeds(h))
+        out = ChainResult(np.empty(n + 1, np.uint32), np.empty(nc, np.int64), np.empty(nc, np.int32), np.empty(nc, np.int32), np.empty(nc, np.int32),
+                          np.empty(nc, np.int32), np.empty(ns, np.int64), np.empty(ns, np.int32), np.empty(ns, np.int32), np.empty(n, np.float32))
+        L.csref_chains_copy(h, _ptr(out.chain_off), _ptr(out.pos), _ptr(out.rid), _ptr(out.w), _ptr(out.kept), _ptr(out.n),
+                            _ptr(out.s_rbeg), _ptr(out.s_qbeg), _ptr(out.s_len), _ptr(out.frac_rep))
+    finally:
+        L.csref_chains_free(h)
+    return out

@@ -31,6 +31,10 @@ thread_aux_t tprof; // comp_seed.cpp:22 expects the driver to define it (main.cp
 
 extern int collect_mem_with_sst(const uint8_t *seq, int len, int pivot, int min_hits, thread_aux_t &aux);
 extern int tem_forward_sst(const mem_opt_t *opt, const uint8_t *seq, int len, int start, bwtintv_t *mem, thread_aux_t &aux);
+// chaining and chain filtering (mapping/comp_seed.cpp:241-354); mem_chain_v is private to that file (comp_seed.cpp:176)
+typedef struct { size_t n, m; mem_chain_t *a; } mem_chain_v;
+extern mem_chain_v mem_chain(const mem_opt_t *opt, const bntseq_t *bns, int len, const std::vector<bwtintv_t> &mem, const std::vector<mem_seed_t> &seed);
+extern int mem_chain_flt(const mem_opt_t *opt, int n_chn, mem_chain_t *a);
 
 extern "C" {
 
@@ -283,6 +287,85 @@ static void worker_compseed(const bwt_t *bwt, const csref_opt_t *o, const uint8_
 	delete auxp;
 	free(opt);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Chains: the reference's own mem_chain + mem_chain_flt (comp_seed.cpp:241-354) on given mems and seeds.
+// Contigs: n_seqs lengths (a bntseq_t with just the fields bns_intv2rid reads, bntseq.c:354-378).  Output, flat:
+//   chain_off[n_reads+1]; per chain pos, rid, w, kept | is_alt << 8, n seeds; seeds of all chains in chain order
+//   (rbeg, qbeg, len); per read frac_rep (float) of its chains (0 if it has none).
+// ---------------------------------------------------------------------------------------------
+typedef struct {
+	int32_t w, max_chain_gap, min_chain_weight, max_chain_extend;
+	float mask_level, drop_ratio;
+} csref_chain_opt_t;
+
+typedef struct {
+	std::vector<uint32_t> chain_off;
+	std::vector<int64_t> pos; std::vector<int32_t> rid, w, kept, n;
+	std::vector<int64_t> s_rbeg; std::vector<int32_t> s_qbeg, s_len;
+	std::vector<float> frac_rep;
+} csref_chains_t;
+
+void *csref_chain(int n_reads, const uint32_t *read_off, const uint32_t *mem_off, const uint64_t *mems /*n*4*/, const uint32_t *seed_off,
+                  const int64_t *rbeg, const csref_opt_t *so, const csref_chain_opt_t *co, int n_seqs, const int32_t *seq_len, const uint8_t *is_alt)
+{
+	bntseq_t bns; memset(&bns, 0, sizeof bns);
+	std::vector<bntann1_t> anns(n_seqs);
+	int64_t o = 0;
+	for (int i = 0; i < n_seqs; ++i) { memset(&anns[i], 0, sizeof(bntann1_t)); anns[i].offset = o; anns[i].len = seq_len[i]; anns[i].is_alt = is_alt ? is_alt[i] : 0; o += seq_len[i]; }
+	bns.l_pac = o; bns.n_seqs = n_seqs; bns.anns = anns.data();
+	mem_opt_t *opt = mem_opt_init();
+	opt->min_seed_len = so->min_seed_len; opt->split_factor = so->split_factor; opt->split_width = so->split_width;
+	opt->max_mem_intv = so->max_mem_intv; opt->max_occ = so->max_occ;
+	opt->w = co->w; opt->max_chain_gap = co->max_chain_gap; opt->min_chain_weight = co->min_chain_weight; opt->max_chain_extend = co->max_chain_extend;
+	opt->mask_level = co->mask_level; opt->drop_ratio = co->drop_ratio;
+	csref_chains_t *out = new csref_chains_t();
+	out->chain_off.assign(n_reads + 1, 0);
+	out->frac_rep.assign(n_reads, 0.f);
+	for (int r = 0; r < n_reads; ++r) {
+		std::vector<bwtintv_t> mem(mem_off[r + 1] - mem_off[r]);
+		for (size_t i = 0; i < mem.size(); ++i) { const uint64_t *p = mems + 4 * (size_t)(mem_off[r] + i); mem[i].x[0] = p[0]; mem[i].x[1] = p[1]; mem[i].x[2] = p[2]; mem[i].info = p[3]; }
+		std::vector<mem_seed_t> seed; // expanded exactly as comp_seed.cpp:2309-2326 does (then resolved: rbeg given)
+		size_t si = seed_off[r];
+		for (const auto &m : mem) {
+			uint64_t step = m.x[2] > (uint64_t)opt->max_occ ? m.x[2] / opt->max_occ : 1;
+			for (uint64_t k = 0, count = 0; k < m.x[2] && count < (uint64_t)opt->max_occ; k += step, count++) {
+				mem_seed_t sd; memset(&sd, 0, sizeof(sd));
+				sd.qbeg = m.info >> 32; sd.score = sd.len = (int)m.info - (int)(m.info >> 32); sd.rbeg = rbeg[si++];
+				seed.push_back(sd);
+			}
+		}
+		mem_chain_v chn = mem_chain(opt, &bns, (int)(read_off[r + 1] - read_off[r]), mem, seed);
+		chn.n = mem_chain_flt(opt, chn.n, chn.a);
+		for (size_t c = 0; c < chn.n; ++c) {
+			const mem_chain_t &ch = chn.a[c];
+			out->pos.push_back(ch.pos); out->rid.push_back(ch.rid); out->w.push_back((int32_t)ch.w);
+			out->kept.push_back((int32_t)ch.kept | ((int32_t)ch.is_alt << 8)); out->n.push_back(ch.n);
+			for (int j = 0; j < ch.n; ++j) { out->s_rbeg.push_back(ch.seeds[j].rbeg); out->s_qbeg.push_back(ch.seeds[j].qbeg); out->s_len.push_back(ch.seeds[j].len); }
+			out->frac_rep[r] = ch.frac_rep;
+			free(ch.seeds);
+		}
+		free(chn.a);
+		out->chain_off[r + 1] = (uint32_t)out->pos.size();
+	}
+	free(opt);
+	return out;
+}
+uint64_t csref_chains_n(void *h) { return ((csref_chains_t*)h)->pos.size(); }
+uint64_t csref_chains_n_seeds(void *h) { return ((csref_chains_t*)h)->s_rbeg.size(); }
+void csref_chains_copy(void *h, uint32_t *chain_off, int64_t *pos, int32_t *rid, int32_t *w, int32_t *kept, int32_t *n,
+                       int64_t *s_rbeg, int32_t *s_qbeg, int32_t *s_len, float *frac_rep)
+{
+	csref_chains_t *c = (csref_chains_t*)h;
+	memcpy(chain_off, c->chain_off.data(), c->chain_off.size() * 4);
+	if (!c->pos.empty()) {
+		memcpy(pos, c->pos.data(), c->pos.size() * 8); memcpy(rid, c->rid.data(), c->rid.size() * 4); memcpy(w, c->w.data(), c->w.size() * 4);
+		memcpy(kept, c->kept.data(), c->kept.size() * 4); memcpy(n, c->n.data(), c->n.size() * 4);
+	}
+	if (!c->s_rbeg.empty()) { memcpy(s_rbeg, c->s_rbeg.data(), c->s_rbeg.size() * 8); memcpy(s_qbeg, c->s_qbeg.data(), c->s_qbeg.size() * 4); memcpy(s_len, c->s_len.data(), c->s_len.size() * 4); }
+	memcpy(frac_rep, c->frac_rep.data(), c->frac_rep.size() * 4);
+}
+void csref_chains_free(void *h) { delete (csref_chains_t*)h; }
 
 // bases: nt4 codes (0..3, >3 ambiguous) concatenated; off: n_reads+1 offsets.
 void *csref_seed(void *hh, int mode, int n_threads, int n_reads, const uint8_t *bases, const uint32_t *off, const csref_opt_t *opt)

@@ -50,10 +50,12 @@ def test_compact_wire_format_equals_plain_results(cuda_lib, workload):
     assert np.array_equal(x0, want[1].mems[:, 0]) and np.array_equal(x2, want[1].mems[:, 2]) and np.array_equal(info, want[1].mems[:, 3])
     assert np.array_equal(lo.astype(np.int64) | (hi.astype(np.int64) << 32), want[1].rbeg)
     ctx.close()
+    c2 = cuda_lib.SeedContext(idx, n, int(off[-1]), 256, n * 64, n * 600, 1)
+    c2.submit(0, bases, off, cuda_lib.SeedOpt())
     with pytest.raises(cuda_lib.CompSeedError):                  # a ctx without compact_results has no compact copy to hand out
-        c2 = cuda_lib.SeedContext(idx, n, int(off[-1]), 256, n * 64, n * 600, 1)
-        c2.submit(0, bases, off, cuda_lib.SeedOpt())
         c2.wait_compact(0)
+    _same(c2.wait(0), want[1])
+    c2.close()
     idx.close()
 
 

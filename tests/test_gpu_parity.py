@@ -175,7 +175,7 @@ def test_fast_route_equals_literal_route_midsize(cuda_lib):
     assert a.counters["deferred_calls"] > 0 and b.counters["deferred_calls"] == 0
     _assert_same(a, b.mem_off, b.mems, b.seed_off, b.rbeg)
     # the third pass on its own stream next to the walk / literal kernels, or after them on the same stream: same answer
-    c = cuda_lib.seed_reads(idx, bases, off, batch_reads=150_001, n_slots=2, config=cuda_lib.CtxConfig(overlap_streams=0))
+    c = cuda_lib.seed_reads(idx, bases, off, batch_reads=150_001, n_slots=2, config=cuda_lib.CtxConfig(overlap_streams=1))
     _assert_same(c, a.mem_off, a.mems, a.seed_off, a.rbeg)
     idx.close()
 
@@ -276,7 +276,8 @@ def test_result_neutral_caches_can_be_switched_off(cuda_lib, oracle_lib):
             "text_isa32": (1, IC(kmer_table_depth=0, prune_k=0, isa_intv=32), CC()),
             "all_dense": (1, IC(), CC()), "all_dense_tiny_queue": (1, IC(), CC(defer_cap=7)), "all_dense_nofast": (1, IC(), CC(use_fast=0)),
             "all_dense_r3slow": (1, IC(), CC(use_r3_fast=0)), "all_dense_k12": (1, IC(prune_k=12, kmer_table_depth=9), CC()),
-            "all_dense_serial": (1, IC(), CC(overlap_streams=0)), "all_dense_r3slow_serial": (1, IC(), CC(use_r3_fast=0, overlap_streams=0)),
+            "all_dense_serial": (1, IC(), CC(overlap_streams=1)), "all_dense_r3slow_serial": (1, IC(), CC(use_r3_fast=0, overlap_streams=1)),
+            "all_dense_isa4": (1, IC(isa_intv=4), CC()),
             "all_dense_l2window": (1, IC(), CC(l2_persist_mb=16)), "all_dense_litcap": (1, IC(), CC(lit_ctas_per_sm=1)),
             "all_dense_prefetch": (1, IC(), CC(prefetch_results=1))}.items():
         idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv, dense_sa_intv=dense, config=icfg)
