@@ -353,7 +353,7 @@ def main():
     # library (cs_multi_*: one host thread per GPU submits batches through the slots of a ctx, results arrive by DMA in the
     # compact wire format in page-locked arrays).  Consecutive steps alternate between the two read sets the pipeline keeps
     # in flight, as a host does with batch i+1 and batch i.
-    def run_e2e(packed_in: bool, keep_head: bool):
+    def run_e2e(packed_in: bool, keep_head: bool, chains: bool = False):
         bs = min(args.e2e_batch, n_reads)
         off64 = off.astype(np.uint64)
         if packed_in:   # the host holds the reads 2-bit packed in page-locked memory (what a packing reader would leave)
@@ -362,6 +362,8 @@ def main():
         else:
             cs.host_register(bases)   # the reads sit in page-locked host memory, as the bench contract asks
         ms_ = cs.MultiSeeder([idx], batch_reads=bs, max_read_len=args.read_len, n_slots=args.e2e_slots, mems_per_read=14, seeds_per_read=20, config=ccfg)
+        if chains:      # mem_chain + mem_chain_flt on the GPU too: only the filtered chains come back
+            ms_.set_chaining([args.ref_len])
 
         def submit(set_id):
             if packed_in:
@@ -385,9 +387,16 @@ def main():
         barrier()
         e_ms = (time.perf_counter() - t0) * 1e3
         n_launch = ms_.launches - l0
-        assert info["n_mems"] == n_mems and info["n_seeds"] == n_seeds, "host-buffer path disagrees with the device-resident path"
+        assert chains or (info["n_mems"] == n_mems and info["n_seeds"] == n_seeds), "host-buffer path disagrees with the device-resident path"
         head = None
-        if keep_head:     # untimed: one more pass, expanded to flat arrays, for the comparison with the reference
+        if keep_head and chains:   # untimed: the chains of the first reads, flat, for the comparison with the reference's mem_chain_flt output
+            submit(0)
+            g = ms_.wait(0, gather=True)
+            nc_h, nk_h = int(g.chain_off[n_par]), int(g.cseed_off[n_par])
+            head = dict(chain_off=g.chain_off[:n_par + 1], rid=g.rid[:nc_h], w=g.w[:nc_h], kept=g.kept[:nc_h], n=g.n[:nc_h], l_rep=g.l_rep[:nc_h],
+                        s_rbeg=g.s_rbeg[:nk_h], s_qbeg=g.s_qbeg[:nk_h], s_len=g.s_len[:nk_h])
+            del g
+        elif keep_head:   # untimed: one more pass, expanded to flat arrays, for the comparison with the reference
             submit(0)
             g = ms_.wait(0, gather=True, n_threads=threads)
             nm_h, ns_h = int(g.mem_off[n_par]), int(g.seed_off[n_par])
@@ -402,8 +411,10 @@ def main():
                "batch_reads": bs, "slots": args.e2e_slots,
                "api": "cs_multi_submit%s / cs_multi_wait: the library's own pipeline (one host thread per GPU, no Python in the loop), two read sets in flight" % ("_packed" if packed_in else ""),
                "input": "2-bit packed reads + N mask in page-locked host memory, packed by the host outside the timed region (cs_pack_reads_host64)" if packed_in else "nt4 bytes in page-locked host memory",
-               "output": "compact wire format (20 B per mem, 5 B per seed position, 8 B of offsets per read) by DMA into page-locked host arrays; "
-                         "a consumer expands a read where it uses it (cs_cmem_unpack / cs_multi_read)",
+               "output": ("filtered chains (mem_chain + mem_chain_flt run on the GPU: 16 B per chain, 9 B per chain seed, 8 B of offsets per read) by DMA into "
+                          "page-locked host arrays (cs_multi_read_chains)") if chains else
+                         ("compact wire format (20 B per mem, 5 B per seed position, 8 B of offsets per read) by DMA into page-locked host arrays; "
+                          "a consumer expands a read where it uses it (cs_cmem_unpack / cs_multi_read)"),
                "timing": "host wall clock between device syncs"}
         ms_.close()
         if packed_in:
@@ -412,12 +423,48 @@ def main():
             cs.host_unregister(bases)
         return out, head, n_launch
 
-    e2e, e2e_head, e2e_launches = None, None, 0
+    e2e, e2e_head, e2e_launches, chain_head = None, None, 0, None
     if not args.no_e2e:
         e2e, e2e_head, e2e_launches = run_e2e(args.e2e_input == "packed", True)
+        # the same path with chaining + chain filtering on the GPU: what a host that takes chains would see
+        ch, chain_head, _ = run_e2e(args.e2e_input == "packed", True, chains=True)
+        e2e["with_chaining_on_the_gpu"] = {k: ch[k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "output")}
         if args.e2e_input == "packed":   # the same with nt4 bytes crossing the link, for comparison (not the headline)
             alt, _, _ = run_e2e(False, False)
             e2e["nt4_bytes_input_variant"] = {k: alt[k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "input")}
+
+    # (2b) what the host side of the box can move: every rank copies 1 GiB host-to-device and 1 GiB device-to-host at the
+    # same time (page-locked memory, two streams), all ranks together; the sum is the ceiling of the host-buffer path at
+    # this N (the GPUs of a box share the host's memory and PCIe fabric)
+    host_link = None
+    if not args.no_e2e:
+        nb = 1 << 30
+        hsrc = torch.empty(nb, dtype=torch.uint8).pin_memory(); hdst = torch.empty(nb, dtype=torch.uint8).pin_memory()
+        dsrc = torch.empty(nb, dtype=torch.uint8, device=device); ddst = torch.empty(nb, dtype=torch.uint8, device=device)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        best = None
+        for it in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s1):
+                ddst.copy_(hsrc, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hdst.copy_(dsrc, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if use_dist:
+                t = torch.tensor([dt], device=device, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t[0])
+            best = dt if best is None or dt < best else best
+        host_link = {"aggregate_h2d_plus_d2h_gb_per_s": 2 * nb * world / best / 1e9, "per_gpu_gb_per_s": 2 * nb / best / 1e9,
+                     "what": "%d rank(s), each 1 GiB host-to-device and 1 GiB device-to-host at once from page-locked memory, slowest rank, best of 3" % world}
+        if e2e is not None:
+            bytes_per_read = (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / (n_reads * world)
+            host_link["e2e_bytes_per_read"] = bytes_per_read
+            host_link["e2e_gb_per_s"] = e2e["value"] * bytes_per_read / 1e9
+            host_link["reads_per_s_this_link_allows"] = host_link["aggregate_h2d_plus_d2h_gb_per_s"] * 1e9 / bytes_per_read
+        del hsrc, hdst, dsrc, ddst
 
     if rank != 0:
         if use_dist:
@@ -444,7 +491,16 @@ def main():
                   "device_resident_equal": all(same_prefix(dev_head, w, n_cmp) for w in ref_res.values())}
         if e2e_head is not None:
             parity["e2e_equal"] = all(same_prefix(e2e_head, w, n_cmp) for w in ref_res.values())
-        parity["equal"] = bool(parity["device_resident_equal"] and parity.get("e2e_equal", True))
+        if chain_head is not None and cpu_baseline["kind"] == "reference":   # the reference's own mem_chain + mem_chain_flt on its own seeds
+            from oracle import oracle_py as O
+            want_c = O.ref_chain(off[:n_cmp + 1], first, [args.ref_len])
+            ce = bool(np.array_equal(chain_head["chain_off"], want_c.chain_off) and np.array_equal(chain_head["rid"], want_c.rid)
+                      and np.array_equal(chain_head["w"], want_c.w) and np.array_equal(chain_head["kept"], want_c.kept) and np.array_equal(chain_head["n"], want_c.n)
+                      and np.array_equal(chain_head["s_rbeg"], want_c.s_rbeg) and np.array_equal(chain_head["s_qbeg"], want_c.s_qbeg)
+                      and np.array_equal(chain_head["s_len"], want_c.s_len))
+            parity["chains"] = {"reads": n_cmp, "chains": int(want_c.chain_off[-1]), "chain_seeds": int(want_c.s_rbeg.shape[0]), "equal": ce,
+                                "against": "mem_chain + mem_chain_flt of the reference (comp_seed.cpp:241-354) on the reference's own seeds"}
+        parity["equal"] = bool(parity["device_resident_equal"] and parity.get("e2e_equal", True) and parity.get("chains", {}).get("equal", True))
         parity["rows_at_or_above_2^32_in_sample"] = int((first.mems[:, 0] >= np.uint64(1 << 32)).sum())
 
     # (4) roofline of the dominant kernel, k_seed_fast, from what it EXECUTES: memory requests counted in the kernel
@@ -508,7 +564,7 @@ def main():
             "occ_lookups_per_s_logical": ref_work["occ_lookups_per_s_logical"] if ref_work else None,
             "mems_per_read": n_mems / n_reads, "seeds_per_read": n_seeds / n_reads,
             "wall_ms_per_step": wall_ms_max / args.steps,
-            "e2e": e2e, "gpu_launches": int(dev_launches + e2e_launches),
+            "e2e": e2e, "host_link": host_link, "gpu_launches": int(dev_launches + e2e_launches),
             "gpu_launches_what": "kernel launches counted at the launch sites of the library (cs_ctx_launches): %d in the device-resident timed region "
                                  "(%d steps), %d in the host-buffer timed region" % (dev_launches, args.steps, e2e_launches),
             "clocks": clocks, "roofline": roofline, "reference_work_equivalent": ref_work, "cpu_baseline": cpu_baseline,

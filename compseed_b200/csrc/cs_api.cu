@@ -501,6 +501,8 @@ struct Ctrl { // zeroed before every run; copied back after it
 	unsigned long long tot12, tot3, tot_seeds;   // 64-bit batch totals: mems of passes 1-2, of pass 3, seeds
 	int error, pad1;
 	uint32_t n_mems, n_seeds;
+	unsigned long long chain_work;         // work counter of k_chain_build
+	uint32_t n_chains, n_cseeds, n_nodes, pad2;
 };
 
 struct Slot {
@@ -518,6 +520,11 @@ struct Slot {
 	cs_cmem_t *h_cmems; uint32_t *h_rlo; uint8_t *h_rhi;   // compact wire format (pinned, allocated on first use)
 	cs_cmem_t *d_cmems; uint32_t *d_rlo; uint8_t *d_rhi;   // ... on the device (cfg.compact_results)
 	bool fetched_compact;
+	// chaining (cs_ctx_set_chaining): scratch and results on the device, pinned results on first use
+	uint32_t *d_s_next, *d_s_qb_len, *d_order, *d_klist, *d_node_cnt, *d_node_off, *d_nodes, *d_n_chain, *d_n_cseed, *d_l_rep, *d_chain_off, *d_cseed_off;
+	ChainTmp *d_chain_tmp; cs_chain_t *d_chains; uint32_t *d_cs_lo; uint8_t *d_cs_hi; uint16_t *d_cs_qbeg, *d_cs_len;
+	uint32_t *h_chain_off, *h_cseed_off; cs_chain_t *h_chains; uint32_t *h_cs_lo; uint8_t *h_cs_hi; uint16_t *h_cs_qbeg, *h_cs_len;
+	bool chained;          // the batch in the slot was chained
 	Ctrl *h_ctrl;
 	// device
 	uint8_t *d_bases; uint32_t *d_off;
@@ -557,6 +564,11 @@ struct cs_ctx {
 	cs_ctx_config_t cfg;
 	uint64_t n_launch;    // kernels launched so far (counted at the launch sites)
 	uint64_t need_mems[16], need_seeds[16];   // per slot: what the last overflowing batch would have needed
+	// chaining (cs_ctx_set_chaining)
+	bool chaining;
+	cs_chain_opt_t copt;
+	int64_t l_pac; int32_t n_seqs; int64_t *d_c_off; uint8_t *d_c_alt;
+	uint64_t node_cap;    // B-tree nodes per slot
 	Slot *slots;
 };
 
@@ -574,6 +586,11 @@ static void slot_free(Slot *s)
 	cudaFreeHost(s->h_packed); cudaFreeHost(s->h_nmask);
 	cudaFreeHost(s->h_cmems); cudaFreeHost(s->h_rlo); cudaFreeHost(s->h_rhi);
 	cudaFree(s->d_cmems); cudaFree(s->d_rlo); cudaFree(s->d_rhi);
+	cudaFree(s->d_s_next); cudaFree(s->d_s_qb_len); cudaFree(s->d_order); cudaFree(s->d_klist); cudaFree(s->d_node_cnt); cudaFree(s->d_node_off); cudaFree(s->d_nodes);
+	cudaFree(s->d_n_chain); cudaFree(s->d_n_cseed); cudaFree(s->d_l_rep); cudaFree(s->d_chain_off); cudaFree(s->d_cseed_off); cudaFree(s->d_chain_tmp);
+	cudaFree(s->d_chains); cudaFree(s->d_cs_lo); cudaFree(s->d_cs_hi); cudaFree(s->d_cs_qbeg); cudaFree(s->d_cs_len);
+	cudaFreeHost(s->h_chain_off); cudaFreeHost(s->h_cseed_off); cudaFreeHost(s->h_chains); cudaFreeHost(s->h_cs_lo); cudaFreeHost(s->h_cs_hi);
+	cudaFreeHost(s->h_cs_qbeg); cudaFreeHost(s->h_cs_len);
 	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
 	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
 	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_defer_bits); cudaFree(s->d_lit_q); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
@@ -587,6 +604,7 @@ extern "C" void cs_ctx_free(cs_ctx_t *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	for (int i = 0; i < ctx->n_slots; ++i) slot_free(&ctx->slots[i]);
+	cudaFree(ctx->d_c_off); cudaFree(ctx->d_c_alt);
 	free(ctx->slots); free(ctx);
 }
 
@@ -878,6 +896,36 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	                                                    &s->d_ctrl->sa_work, &s->d_ctrl->lf_steps);
 	CK(cudaGetLastError()); ++ctx->n_launch;
 	CK(cudaEventRecord(s->ev[4], s->stream));
+	s->chained = false;
+	if (ctx->chaining) { // mem_chain + mem_chain_flt on the device (cs_chain.cu): node regions, build + filter, offsets, emit
+		ChainArgs ca;
+		const int g = std::min<int>(idx->n_sm * 8, (int)((n + 255) / 256));
+		k_chain_node_counts<<<g, 256, 0, s->stream>>>(s->d_read_n_seeds, n, s->d_node_cnt);
+		CK(cudaGetLastError()); ++ctx->n_launch;
+		CK(cudaMemsetAsync(s->d_node_cnt + n, 0, 4, s->stream));
+		CK(cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, s->scan_tmp_bytes, s->d_node_cnt, s->d_node_off, (int)n + 1, s->stream));
+		ctx->n_launch += 2;
+		CK(cudaMemcpyAsync(&s->d_ctrl->n_nodes, s->d_node_off + n, 4, cudaMemcpyDeviceToDevice, s->stream));
+		ca.n_reads = n; ca.opt = *opt; ca.copt = ctx->copt; ca.off = s->d_off; ca.mem_off = s->d_mem_off; ca.mems = s->d_mems;
+		ca.seed_off = s->d_seed_off; ca.rbeg = s->d_rows; ca.l_pac = ctx->l_pac; ca.n_seqs = ctx->n_seqs; ca.c_off = ctx->d_c_off; ca.c_alt = ctx->d_c_alt;
+		ca.s_next = s->d_s_next; ca.s_qb_len = s->d_s_qb_len; ca.chains = s->d_chain_tmp; ca.order = s->d_order; ca.klist = s->d_klist;
+		ca.node_off = s->d_node_off; ca.nodes = s->d_nodes; ca.node_cap = ctx->node_cap; ca.seed_cap = ctx->max_seeds; ca.mems_cap = ctx->max_mems;
+		ca.n_chain = s->d_n_chain; ca.n_cseed = s->d_n_cseed; ca.l_rep = s->d_l_rep;
+		ca.work = &s->d_ctrl->chain_work; ca.error = &s->d_ctrl->error;
+		k_chain_build<<<idx->n_sm * 16, 128, 0, s->stream>>>(ca);
+		CK(cudaGetLastError()); ++ctx->n_launch;
+		CK(cudaMemsetAsync(s->d_n_chain + n, 0, 4, s->stream));
+		CK(cudaMemsetAsync(s->d_n_cseed + n, 0, 4, s->stream));
+		CK(cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, s->scan_tmp_bytes, s->d_n_chain, s->d_chain_off, (int)n + 1, s->stream));
+		CK(cub::DeviceScan::ExclusiveSum(s->d_scan_tmp, s->scan_tmp_bytes, s->d_n_cseed, s->d_cseed_off, (int)n + 1, s->stream));
+		ctx->n_launch += 4;
+		k_chain_emit<<<(int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, s->stream>>>(
+			ca, s->d_chain_off, s->d_cseed_off, ctx->max_mems, ctx->max_seeds, s->d_chains, s->d_cs_lo, s->d_cs_hi, s->d_cs_qbeg, s->d_cs_len);
+		CK(cudaGetLastError()); ++ctx->n_launch;
+		CK(cudaMemcpyAsync(&s->d_ctrl->n_chains, s->d_chain_off + n, 4, cudaMemcpyDeviceToDevice, s->stream));
+		CK(cudaMemcpyAsync(&s->d_ctrl->n_cseeds, s->d_cseed_off + n, 4, cudaMemcpyDeviceToDevice, s->stream));
+		s->chained = true;
+	}
 	if (s->d_cmems) {
 		k_compact_results<<<idx->n_sm * 8, 256, 0, s->stream>>>(&s->d_ctrl->n_mems, ctx->max_mems, s->d_mems, s->d_cmems,
 		                                                         &s->d_ctrl->n_seeds, ctx->max_seeds, s->d_rows, s->d_rlo, s->d_rhi);
@@ -1137,8 +1185,33 @@ int cs_i_finish(cs_ctx *ctx, int slot, uint64_t *n_mems, uint64_t *n_seeds)
 	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
 	const int rc = finish_run(ctx, s);
 	if (rc != CS_OK) { s->state = 1; return rc; }
-	*n_mems = s->h_ctrl->n_mems; *n_seeds = s->h_ctrl->n_seeds;
+	if (s->chained) {
+		*n_mems = s->h_ctrl->n_chains; *n_seeds = s->h_ctrl->n_cseeds;
+		if (*n_mems > ctx->max_mems || *n_seeds > ctx->max_seeds) return set_err(CS_E_OVERFLOW, "chain buffers too small for this batch");
+	} else { *n_mems = s->h_ctrl->n_mems; *n_seeds = s->h_ctrl->n_seeds; }
 	return CS_OK;
+}
+
+int cs_i_fetch_chains_into(cs_ctx *ctx, int slot, uint32_t *chain_off, uint32_t *cseed_off, cs_chain_t *ch, uint32_t *lo, uint8_t *hi, uint16_t *qb, uint16_t *ln)
+{
+	Slot *s = &ctx->slots[slot];
+	const uint32_t n = s->n_reads;
+	if (s->state != 3 || !s->chained) return set_err(CS_E_STATE, "slot %d has no finished chained batch", slot);
+	CK(cudaMemcpyAsync(chain_off, s->d_chain_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaMemcpyAsync(cseed_off, s->d_cseed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+	if (s->h_ctrl->n_chains) CK(cudaMemcpyAsync(ch, s->d_chains, (size_t)s->h_ctrl->n_chains * sizeof(cs_chain_t), cudaMemcpyDeviceToHost, s->stream));
+	if (s->h_ctrl->n_cseeds) {
+		const size_t k = s->h_ctrl->n_cseeds;
+		CK(cudaMemcpyAsync(lo, s->d_cs_lo, k * 4, cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaMemcpyAsync(hi, s->d_cs_hi, k, cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaMemcpyAsync(qb, s->d_cs_qbeg, k * 2, cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaMemcpyAsync(ln, s->d_cs_len, k * 2, cudaMemcpyDeviceToHost, s->stream));
+	}
+	CK(cudaEventRecord(s->ev_done, s->stream));
+	s->state = 4;
+	return CS_OK;
+fail:
+	return CS_E_CUDA;
 }
 
 // enqueue the result copies of a finished slot (compact wire format) to caller-owned page-locked memory
@@ -1176,6 +1249,17 @@ int cs_i_fetch_wait(cs_ctx *ctx, int slot, cs_counters_t *cnt, float *slot_ms)
 	return CS_OK;
 fail:
 	return CS_E_CUDA;
+}
+
+// non-blocking: 1 if the kernels (state 2) / the result copies (state 4) of the slot have finished, 0 if not yet, < 0 on error
+int cs_i_poll(cs_ctx *ctx, int slot)
+{
+	Slot *s = &ctx->slots[slot];
+	if (s->state != 2 && s->state != 4) return set_err(CS_E_STATE, "slot %d has nothing in flight", slot);
+	const cudaError_t e = cudaEventQuery(s->state == 2 ? s->ev_kdone : s->ev_done);
+	if (e == cudaSuccess) return 1;
+	if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+	return set_err(CS_E_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
 }
 
 void cs_i_ctx_caps(const cs_ctx *ctx, uint64_t *max_mems, uint64_t *max_seeds) { *max_mems = ctx->max_mems; *max_seeds = ctx->max_seeds; }
@@ -1354,6 +1438,88 @@ extern "C" int cs_seed_batch_wait_compact(cs_ctx_t *ctx, int slot, cs_compact_re
 	out->counters.ext_queries = s->h_ctrl->counters[0]; out->counters.ext_calls = s->h_ctrl->counters[1];
 	out->counters.sal_queries = s->h_ctrl->n_seeds; out->counters.sal_calls = s->h_ctrl->lf_steps;
 	return CS_OK;
+}
+
+extern "C" int cs_ctx_set_chaining(cs_ctx_t *ctx, const cs_bns_view_t *bns, const cs_chain_opt_t *opt)
+{
+	if (!ctx) return set_err(CS_E_ARG, "null ctx");
+	{ const int rc_ = use_device(ctx->device); if (rc_ != CS_OK) return rc_; }
+	for (int i = 0; i < ctx->n_slots; ++i) if (ctx->slots[i].state == 2 || ctx->slots[i].state == 4) return set_err(CS_E_STATE, "slot %d is busy", i);
+	if (!bns) { ctx->chaining = false; return CS_OK; }
+	if (!opt || bns->n_seqs < 1 || !bns->offset || bns->l_pac <= 0 || (uint64_t)bns->l_pac * 2 != ctx->idx->d.seq_len)
+		return set_err(CS_E_ARG, "bad contig table (n_seqs %d, l_pac %lld; the index has %llu rows)", bns ? bns->n_seqs : 0, bns ? (long long)bns->l_pac : 0, (unsigned long long)ctx->idx->d.seq_len);
+	if (ctx->max_read_len > 65535) return set_err(CS_E_ARG, "chaining packs read positions in 16 bits");
+	cudaFree(ctx->d_c_off); cudaFree(ctx->d_c_alt); ctx->d_c_off = nullptr; ctx->d_c_alt = nullptr;
+	CK(cudaMalloc(&ctx->d_c_off, (size_t)bns->n_seqs * 8));
+	CK(cudaMemcpy(ctx->d_c_off, bns->offset, (size_t)bns->n_seqs * 8, cudaMemcpyHostToDevice));
+	if (bns->is_alt) {
+		CK(cudaMalloc(&ctx->d_c_alt, (size_t)bns->n_seqs));
+		CK(cudaMemcpy(ctx->d_c_alt, bns->is_alt, (size_t)bns->n_seqs, cudaMemcpyHostToDevice));
+	}
+	ctx->l_pac = bns->l_pac; ctx->n_seqs = bns->n_seqs; ctx->copt = *opt;
+	// most reads need one B-tree node (up to nine chains); the rest a third of their seeds (k_chain_node_counts)
+	ctx->node_cap = (uint64_t)ctx->max_reads + ctx->max_seeds / 3 + 4096;
+	for (int i = 0; i < ctx->n_slots; ++i) {
+		Slot *s = &ctx->slots[i];
+		if (s->d_s_next) continue;
+		const size_t ns = ctx->max_seeds, nr = (size_t)ctx->max_reads + 1;
+		CK(cudaMalloc(&s->d_s_next, ns * 4)); CK(cudaMalloc(&s->d_s_qb_len, ns * 4)); CK(cudaMalloc(&s->d_order, ns * 4)); CK(cudaMalloc(&s->d_klist, ns * 4));
+		CK(cudaMalloc(&s->d_chain_tmp, ns * sizeof(ChainTmp)));
+		CK(cudaMalloc(&s->d_node_cnt, nr * 4)); CK(cudaMalloc(&s->d_node_off, nr * 4));
+		CK(cudaMalloc(&s->d_nodes, ctx->node_cap * 24 * 4));
+		CK(cudaMalloc(&s->d_n_chain, nr * 4)); CK(cudaMalloc(&s->d_n_cseed, nr * 4)); CK(cudaMalloc(&s->d_l_rep, nr * 4));
+		CK(cudaMalloc(&s->d_chain_off, nr * 4)); CK(cudaMalloc(&s->d_cseed_off, nr * 4));
+		CK(cudaMalloc(&s->d_chains, ctx->max_mems * sizeof(cs_chain_t)));
+		CK(cudaMalloc(&s->d_cs_lo, ns * 4)); CK(cudaMalloc(&s->d_cs_hi, ns)); CK(cudaMalloc(&s->d_cs_qbeg, ns * 2)); CK(cudaMalloc(&s->d_cs_len, ns * 2));
+	}
+	ctx->chaining = true;
+	return CS_OK;
+fail:
+	ctx->chaining = false;
+	return CS_E_CUDA;
+}
+
+extern "C" int cs_seed_batch_wait_chains(cs_ctx_t *ctx, int slot, cs_chain_result_t *out)
+{
+	int rc;
+	if ((rc = check_slot(ctx, slot)) != CS_OK) return rc;
+	if (!out) return set_err(CS_E_ARG, "null result");
+	Slot *s = &ctx->slots[slot];
+	if (s->state != 2 && s->state != 3) return set_err(CS_E_STATE, "slot %d has no batch in flight or finished", slot);
+	if (!s->chained) return set_err(CS_E_STATE, "the batch in slot %d was not chained (cs_ctx_set_chaining)", slot);
+	{ const int rc_ = use_device(ctx->device); if (rc_ != CS_OK) return rc_; }
+	if (s->state == 2 && (rc = finish_run(ctx, s)) != CS_OK) { s->state = 1; return rc; }
+	{
+		const uint32_t n = s->n_reads;
+		const Ctrl *h = s->h_ctrl;
+		if (h->n_chains > ctx->max_mems || h->n_cseeds > ctx->max_seeds)
+			return set_err(CS_E_OVERFLOW, "chain buffers too small: %u chains of %llu, %u chain seeds of %llu", h->n_chains, (unsigned long long)ctx->max_mems, h->n_cseeds, (unsigned long long)ctx->max_seeds);
+		if (!s->h_chain_off) {
+			CK(cudaMallocHost(&s->h_chain_off, ((size_t)ctx->max_reads + 1) * 4)); CK(cudaMallocHost(&s->h_cseed_off, ((size_t)ctx->max_reads + 1) * 4));
+			CK(cudaMallocHost(&s->h_chains, ctx->max_mems * sizeof(cs_chain_t)));
+			CK(cudaMallocHost(&s->h_cs_lo, ctx->max_seeds * 4)); CK(cudaMallocHost(&s->h_cs_hi, ctx->max_seeds));
+			CK(cudaMallocHost(&s->h_cs_qbeg, ctx->max_seeds * 2)); CK(cudaMallocHost(&s->h_cs_len, ctx->max_seeds * 2));
+		}
+		CK(cudaMemcpyAsync(s->h_chain_off, s->d_chain_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaMemcpyAsync(s->h_cseed_off, s->d_cseed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+		if (h->n_chains) CK(cudaMemcpyAsync(s->h_chains, s->d_chains, (size_t)h->n_chains * sizeof(cs_chain_t), cudaMemcpyDeviceToHost, s->stream));
+		if (h->n_cseeds) {
+			CK(cudaMemcpyAsync(s->h_cs_lo, s->d_cs_lo, (size_t)h->n_cseeds * 4, cudaMemcpyDeviceToHost, s->stream));
+			CK(cudaMemcpyAsync(s->h_cs_hi, s->d_cs_hi, (size_t)h->n_cseeds, cudaMemcpyDeviceToHost, s->stream));
+			CK(cudaMemcpyAsync(s->h_cs_qbeg, s->d_cs_qbeg, (size_t)h->n_cseeds * 2, cudaMemcpyDeviceToHost, s->stream));
+			CK(cudaMemcpyAsync(s->h_cs_len, s->d_cs_len, (size_t)h->n_cseeds * 2, cudaMemcpyDeviceToHost, s->stream));
+		}
+		CK(cudaEventRecord(s->ev_done, s->stream));
+		CK(cudaEventSynchronize(s->ev_done));
+		s->state = 3;
+		memset(out, 0, sizeof *out);
+		out->n_reads = n; out->n_chains = h->n_chains; out->n_cseeds = h->n_cseeds;
+		out->chain_off = s->h_chain_off; out->cseed_off = s->h_cseed_off; out->chains = s->h_chains;
+		out->rbeg_lo = s->h_cs_lo; out->rbeg_hi = s->h_cs_hi; out->qbeg = s->h_cs_qbeg; out->len = s->h_cs_len;
+	}
+	return CS_OK;
+fail:
+	return CS_E_CUDA;
 }
 
 extern "C" int cs_compact_expand(const cs_compact_result_t *res, cs_mem_t *mems, int64_t *rbeg, int n_threads)

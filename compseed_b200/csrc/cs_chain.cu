@@ -15,7 +15,7 @@
 //      of equal weight come out in the order that algorithm leaves them;
 //   3. the pairwise overlap filter walks the kept chains in that order (bwamem.c:460-487).
 // One read per thread (the work of a read is a chain of dependent steps), reads handed out by a work counter.
-#include "cs_kernels.cuh"
+#include "cs_chain.cuh"
 
 #define KB_T 5                     // minimum degree: a node holds at most 2t - 1 = 9 keys and 10 children
 #define KB_MAXK (2 * KB_T - 1)
@@ -303,6 +303,8 @@ __global__ void __launch_bounds__(128) k_chain_build(ChainArgs a)
 		uint32_t n_out = 0, seeds_out = 0, l_rep = 0;
 		a.n_chain[r] = 0; a.n_cseed[r] = 0; a.l_rep[r] = 0;
 		if (len < a.opt.min_seed_len || S == 0) continue;           // bwamem.c:368: no match for a query shorter than the seed length
+		if ((uint64_t)a.seed_off[r + 1] > a.seed_cap || (uint64_t)a.mem_off[r + 1] > a.mems_cap) continue;   // the batch overflowed its buffers: reported by the collect pass
+		if ((uint64_t)a.node_off[r + 1] > a.node_cap) { atomicMin(a.error, CS_E_OVERFLOW); continue; }
 		{ // fraction of the read covered by repetitive seeds (bwamem.c:377-385)
 			int b = 0, e = 0, lr = 0;
 			for (uint32_t i = 0; i < n_mem; ++i) {
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(128) k_chain_build(ChainArgs a)
 			l_rep = (uint32_t)lr;
 		}
 		Tree T;
-		T.nodes = a.nodes + a.node_off[r] * NODE_WORDS; T.cap = (uint32_t)(a.node_off[r + 1] - a.node_off[r]);
+		T.nodes = a.nodes + (size_t)a.node_off[r] * NODE_WORDS; T.cap = a.node_off[r + 1] - a.node_off[r];
 		T.n_nodes = 0; T.overflow = false;
 		T.root = nd_new(T, false);
 		uint32_t n_ch = 0, j = 0;

@@ -28,8 +28,10 @@ int cs_use_device(int device);
 struct cs_ctx;
 int cs_i_submit(cs_ctx *ctx, int slot, uint32_t n, const uint64_t *off64, const uint8_t *bases, const uint64_t *packed, const uint32_t *nmask,
                 uint64_t r0, const cs_seed_opt_t *opt);
-int cs_i_finish(cs_ctx *ctx, int slot, uint64_t *n_mems, uint64_t *n_seeds);
+int cs_i_finish(cs_ctx *ctx, int slot, uint64_t *n_mems, uint64_t *n_seeds);   // (chains / chain seeds when the batch was chained)
+int cs_i_fetch_chains_into(cs_ctx *ctx, int slot, uint32_t *chain_off, uint32_t *cseed_off, cs_chain_t *ch, uint32_t *lo, uint8_t *hi, uint16_t *qb, uint16_t *ln);
 int cs_i_fetch_compact_into(cs_ctx *ctx, int slot, uint32_t *mem_off, uint32_t *seed_off, cs_cmem_t *cm, uint32_t *lo, uint8_t *hi);
 int cs_i_fetch_wait(cs_ctx *ctx, int slot, cs_counters_t *cnt, float *slot_ms);
+int cs_i_poll(cs_ctx *ctx, int slot);
 void cs_i_ctx_caps(const cs_ctx *ctx, uint64_t *max_mems, uint64_t *max_seeds);
 const cs_index *cs_i_ctx_index(const cs_ctx *ctx);

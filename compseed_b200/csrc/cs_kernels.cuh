@@ -92,6 +92,8 @@ struct CollectArgs {
 	int *error;
 };
 
+#include "cs_chain.cuh"
+
 __global__ void k_relayout(const uint32_t *src, uint64_t src_words, uint64_t seq_len, uint4 *dst, uint64_t n_buckets);
 __global__ void k_unlayout(const uint4 *src, uint64_t seq_len, uint32_t *dst, uint64_t dst_words);
 __global__ void k_resample_sa(DevIndex I, uint64_t *out, uint64_t n_out, uint32_t out_shift);

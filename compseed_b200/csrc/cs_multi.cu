@@ -33,6 +33,8 @@ struct BlockBuf { // page-locked result arrays of one (set, device)
 	uint32_t *mem_off = nullptr, *seed_off = nullptr; uint64_t cap_off = 0;
 	cs_cmem_t *cmems = nullptr; uint64_t cap_mems = 0;
 	uint32_t *rlo = nullptr; uint8_t *rhi = nullptr; uint64_t cap_seeds = 0;
+	cs_chain_t *chains = nullptr; uint64_t cap_chains = 0;              // chaining mode: chains instead of cmems ...
+	uint16_t *sq = nullptr, *sl = nullptr; uint64_t cap_sq = 0;          // ... and qbeg / len next to the positions
 };
 
 struct Job {
@@ -63,6 +65,8 @@ struct cs_multi {
 	uint32_t batch_reads, max_read_len; int n_slots;
 	uint32_t mems_per_read, seeds_per_read;
 	cs_ctx_config_t cfg;
+	bool chaining; cs_chain_opt_t copt;                     // cs_multi_set_chaining: contig table kept for ctx re-creation
+	int64_t l_pac; std::vector<int64_t> c_off; std::vector<uint8_t> c_alt;
 	std::vector<Dev*> dev;
 	cs_block_t blocks[2][CS_MULTI_MAX_DEV];
 	bool busy[2];
@@ -97,7 +101,12 @@ int make_ctx(Dev *d)
 	cfg.compact_results = 1;
 	if (d->ctx) { cs_ctx_free(d->ctx); d->ctx = nullptr; }
 	d->ctx = cs_ctx_create_ex(d->idx, m->batch_reads, (uint64_t)m->batch_reads * m->max_read_len, m->max_read_len, d->cap_mems, d->cap_seeds, m->n_slots, &cfg);
-	return d->ctx ? CS_OK : CS_E_CUDA;
+	if (!d->ctx) return CS_E_CUDA;
+	if (m->chaining) {
+		cs_bns_view_t v; v.l_pac = m->l_pac; v.n_seqs = (int32_t)m->c_off.size(); v.offset = m->c_off.data(); v.is_alt = m->c_alt.empty() ? nullptr : m->c_alt.data();
+		return cs_ctx_set_chaining(d->ctx, &v, &m->copt);
+	}
+	return CS_OK;
 }
 
 // one read set on one device: reads [r0, r1) in batches through the slots
@@ -126,7 +135,14 @@ int run_block(Dev *d, const Job &j)
 		co = b.cap_off; p = b.seed_off; if ((rc = pinned_grow(&p, &co, (uint64_t)nb * (B + 1), 4, 0)) != CS_OK) return rc; b.seed_off = (uint32_t*)p;
 		b.cap_off = co;
 		uint64_t cm = b.cap_mems, cs = b.cap_seeds;
+		if (m->chaining) {
+			uint64_t cc = b.cap_chains, cq = b.cap_sq;
+			p = b.chains; if ((rc = pinned_grow(&p, &cc, n * 4, sizeof(cs_chain_t), 0)) != CS_OK) return rc; b.chains = (cs_chain_t*)p; b.cap_chains = cc;
+			p = b.sq; if ((rc = pinned_grow(&p, &cq, n * m->seeds_per_read, 2, 0)) != CS_OK) return rc; b.sq = (uint16_t*)p;
+			cq = b.cap_sq; p = b.sl; if ((rc = pinned_grow(&p, &cq, n * m->seeds_per_read, 2, 0)) != CS_OK) return rc; b.sl = (uint16_t*)p; b.cap_sq = cq;
+		} else {
 		p = b.cmems; if ((rc = pinned_grow(&p, &cm, n * m->mems_per_read, sizeof(cs_cmem_t), 0)) != CS_OK) return rc; b.cmems = (cs_cmem_t*)p; b.cap_mems = cm;
+		}
 		p = b.rlo; if ((rc = pinned_grow(&p, &cs, n * m->seeds_per_read, 4, 0)) != CS_OK) return rc; b.rlo = (uint32_t*)p;
 		cs = b.cap_seeds; p = b.rhi; if ((rc = pinned_grow(&p, &cs, n * m->seeds_per_read, 1, 0)) != CS_OK) return rc; b.rhi = (uint8_t*)p;
 		b.cap_seeds = cs;
@@ -144,59 +160,91 @@ int run_block(Dev *d, const Job &j)
 		hs[0] += since(t);
 		return rc_;
 	};
-	auto wait_copy = [&](uint32_t bi) -> int {
+	auto wait_copy = [&](uint32_t bi) -> int { // blocking (only on the rare paths that must drain the slots)
 		const auto t = now();
 		const int rc_ = cs_i_fetch_wait(d->ctx, (int)(bi % m->n_slots), &d->cnt[j.set], nullptr);
 		hs[2] += since(t);
 		return rc_;
 	};
-	while (done < nb) {
+	// Event-driven: the thread never blocks on one thing while another is ready.  Whenever the kernels of the oldest
+	// unfinished batch are done, its result copy is enqueued at once (the copy engine must not wait for the host);
+	// whenever the oldest copy has landed, its slot is free for the next batch; otherwise the thread naps for 20 us.
+	while (copied < nb) {
+		bool progress = false;
 		while (next < nb && next - copied < (uint32_t)m->n_slots) { // a slot is free once its previous batch's copy has landed
 			if ((rc = submit(next)) != CS_OK) return rc;
-			++next;
+			++next; progress = true;
 		}
-		uint64_t nm = 0, ns = 0;
-		{
+		if (done < next) {
 			const auto t = now();
-			rc = cs_i_finish(d->ctx, (int)(done % m->n_slots), &nm, &ns);
+			const int pr = cs_i_poll(d->ctx, (int)(done % m->n_slots));
+			if (pr < 0) return pr;
+			if (pr == 1) {
+				uint64_t nm = 0, ns = 0;
+				rc = cs_i_finish(d->ctx, (int)(done % m->n_slots), &nm, &ns);
+				if (rc == CS_E_OVERFLOW) { // this batch needs larger slot buffers: drain, re-create the ctx once with what it needs, resubmit from here
+					uint64_t need_m = 0, need_s = 0;
+					cs_ctx_need(d->ctx, (int)(done % m->n_slots), &need_m, &need_s);
+					for (; copied < done; ++copied) if ((rc = wait_copy(copied)) != CS_OK) return rc;
+					if (need_m >= (1ull << 32) || need_s >= (1ull << 32)) return cs_set_err(CS_E_OVERFLOW, "a batch of %u reads needs more than 2^32 mems or seeds: use smaller batches", m->batch_reads);
+					if (need_m <= d->cap_mems && need_s <= d->cap_seeds) { need_m = d->cap_mems * 2; need_s = d->cap_seeds * 2; }   // (chain buffers: no exact figure)
+					d->cap_mems = std::max(d->cap_mems, need_m); d->cap_seeds = std::max(d->cap_seeds, need_s);
+					if ((rc = make_ctx(d)) != CS_OK) return rc;   // (frees the old ctx: its in-flight batches are dropped with it)
+					next = done;
+					continue;
+				}
+				if (rc != CS_OK) return rc;
+				{ // room for this batch in the block arrays (rare: the estimate per read was too low)
+					const uint64_t mb = b.mem_base[done], sb = b.seed_base[done];
+					const uint64_t cap1 = m->chaining ? b.cap_chains : b.cap_mems, cap2 = m->chaining ? std::min(b.cap_seeds, b.cap_sq) : b.cap_seeds;
+					if (mb + nm > cap1 || sb + ns > cap2) {
+						for (; copied < done; ++copied) if ((rc = wait_copy(copied)) != CS_OK) return rc;   // copies into the old arrays must have landed
+						void *p; uint64_t c;
+						if (m->chaining) {
+							p = b.chains; c = b.cap_chains;
+							if ((rc = pinned_grow(&p, &c, mb + nm, sizeof(cs_chain_t), mb)) != CS_OK) return rc;
+							b.chains = (cs_chain_t*)p; b.cap_chains = c;
+							p = b.sq; c = b.cap_sq;
+							if ((rc = pinned_grow(&p, &c, sb + ns, 2, sb)) != CS_OK) return rc;
+							b.sq = (uint16_t*)p;
+							p = b.sl; c = b.cap_sq;
+							if ((rc = pinned_grow(&p, &c, sb + ns, 2, sb)) != CS_OK) return rc;
+							b.sl = (uint16_t*)p; b.cap_sq = c;
+						} else {
+							p = b.cmems; c = b.cap_mems;
+							if ((rc = pinned_grow(&p, &c, mb + nm, sizeof(cs_cmem_t), mb)) != CS_OK) return rc;
+							b.cmems = (cs_cmem_t*)p; b.cap_mems = c;
+						}
+						p = b.rlo; c = b.cap_seeds;
+						if ((rc = pinned_grow(&p, &c, sb + ns, 4, sb)) != CS_OK) return rc;
+						b.rlo = (uint32_t*)p;
+						p = b.rhi; c = b.cap_seeds;
+						if ((rc = pinned_grow(&p, &c, sb + ns, 1, sb)) != CS_OK) return rc;
+						b.rhi = (uint8_t*)p; b.cap_seeds = c;
+					}
+					uint32_t *o1 = b.mem_off + (uint64_t)done * (B + 1), *o2 = b.seed_off + (uint64_t)done * (B + 1);
+					if (m->chaining) rc = cs_i_fetch_chains_into(d->ctx, (int)(done % m->n_slots), o1, o2, b.chains + mb, b.rlo + sb, b.rhi + sb, b.sq + sb, b.sl + sb);
+					else rc = cs_i_fetch_compact_into(d->ctx, (int)(done % m->n_slots), o1, o2, b.cmems + mb, b.rlo + sb, b.rhi + sb);
+					if (rc != CS_OK) return rc;
+					b.mem_base[done + 1] = mb + nm; b.seed_base[done + 1] = sb + ns;
+				}
+				++done; progress = true;
+			}
 			hs[1] += since(t);
 		}
-		if (rc == CS_E_OVERFLOW) { // this batch needs larger slot buffers: drain, re-create the ctx once with what it needs, resubmit from here
-			uint64_t need_m = 0, need_s = 0;
-			cs_ctx_need(d->ctx, (int)(done % m->n_slots), &need_m, &need_s);
-			for (; copied < done; ++copied) if ((rc = wait_copy(copied)) != CS_OK) return rc;
-			if (need_m >= (1ull << 32) || need_s >= (1ull << 32)) return cs_set_err(CS_E_OVERFLOW, "a batch of %u reads needs more than 2^32 mems or seeds: use smaller batches", m->batch_reads);
-			d->cap_mems = std::max(d->cap_mems, need_m); d->cap_seeds = std::max(d->cap_seeds, need_s);
-			if ((rc = make_ctx(d)) != CS_OK) return rc;   // (frees the old ctx: its in-flight batches are dropped with it)
-			next = done;
-			continue;
+		if (copied < done) {
+			const auto t = now();
+			const int pr = cs_i_poll(d->ctx, (int)(copied % m->n_slots));
+			if (pr < 0) return pr;
+			if (pr == 1) { if ((rc = cs_i_fetch_wait(d->ctx, (int)(copied % m->n_slots), &d->cnt[j.set], nullptr)) != CS_OK) return rc; ++copied; progress = true; }
+			hs[1] += since(t);
 		}
-		if (rc != CS_OK) return rc;
-		{ // room for this batch in the block arrays (rare: the estimate per read was too low)
-			const uint64_t mb = b.mem_base[done], sb = b.seed_base[done];
-			if (mb + nm > b.cap_mems || sb + ns > b.cap_seeds) {
-				for (; copied < done; ++copied) if ((rc = wait_copy(copied)) != CS_OK) return rc;   // copies into the old arrays must have landed
-				void *p = b.cmems; uint64_t c = b.cap_mems;
-				if ((rc = pinned_grow(&p, &c, mb + nm, sizeof(cs_cmem_t), mb)) != CS_OK) return rc;
-				b.cmems = (cs_cmem_t*)p; b.cap_mems = c;
-				p = b.rlo; c = b.cap_seeds;
-				if ((rc = pinned_grow(&p, &c, sb + ns, 4, sb)) != CS_OK) return rc;
-				b.rlo = (uint32_t*)p;
-				p = b.rhi; c = b.cap_seeds;
-				if ((rc = pinned_grow(&p, &c, sb + ns, 1, sb)) != CS_OK) return rc;
-				b.rhi = (uint8_t*)p; b.cap_seeds = c;
-			}
-			if ((rc = cs_i_fetch_compact_into(d->ctx, (int)(done % m->n_slots), b.mem_off + (uint64_t)done * (B + 1), b.seed_off + (uint64_t)done * (B + 1),
-			                                  b.cmems + mb, b.rlo + sb, b.rhi + sb)) != CS_OK) return rc;
-			b.mem_base[done + 1] = mb + nm; b.seed_base[done + 1] = sb + ns;
-		}
-		++done;
-		// keep the copy engine one batch behind: the slot of batch `copied` is needed for batch copied + n_slots
-		while (copied + 1 < done || (done == nb && copied < done)) { if ((rc = wait_copy(copied)) != CS_OK) return rc; ++copied; }
+		if (!progress) { const auto t = now(); std::this_thread::sleep_for(std::chrono::microseconds(20)); hs[2] += since(t); }
 	}
 	d->n_mems[j.set] = b.mem_base[nb]; d->n_seeds[j.set] = b.seed_base[nb];
 	b.pub.mem_base = b.mem_base; b.pub.seed_base = b.seed_base; b.pub.mem_off = b.mem_off; b.pub.seed_off = b.seed_off;
-	b.pub.cmems = b.cmems; b.pub.rbeg_lo = b.rlo; b.pub.rbeg_hi = b.rhi;
+	b.pub.cmems = m->chaining ? nullptr : b.cmems; b.pub.rbeg_lo = b.rlo; b.pub.rbeg_hi = b.rhi;
+	b.pub.chains = m->chaining ? b.chains : nullptr; b.pub.qbeg = m->chaining ? b.sq : nullptr; b.pub.len = m->chaining ? b.sl : nullptr;
 	return CS_OK;
 }
 
@@ -235,7 +283,7 @@ extern "C" cs_multi_t *cs_multi_create(cs_index_t *const *idx, int n_dev, uint32
 	m->n_dev = n_dev; m->batch_reads = batch_reads; m->max_read_len = max_read_len; m->n_slots = n_slots;
 	m->mems_per_read = mems_per_read ? mems_per_read : 16; m->seeds_per_read = seeds_per_read ? seeds_per_read : 32;
 	if (cfg) m->cfg = *cfg; else cs_ctx_config_default(&m->cfg);
-	m->busy[0] = m->busy[1] = false;
+	m->busy[0] = m->busy[1] = false; m->chaining = false; m->l_pac = 0;
 	for (int k = 0; k < n_dev; ++k) {
 		Dev *d = new Dev();
 		d->m = m; d->k = k; d->idx = idx[k]; d->ctx = nullptr;
@@ -262,7 +310,7 @@ extern "C" void cs_multi_free(cs_multi_t *m)
 		for (int s = 0; s < 2; ++s) {
 			BlockBuf &b = d->buf[s];
 			cudaFreeHost(b.mem_base); cudaFreeHost(b.seed_base); cudaFreeHost(b.mem_off); cudaFreeHost(b.seed_off);
-			cudaFreeHost(b.cmems); cudaFreeHost(b.rlo); cudaFreeHost(b.rhi);
+			cudaFreeHost(b.cmems); cudaFreeHost(b.rlo); cudaFreeHost(b.rhi); cudaFreeHost(b.chains); cudaFreeHost(b.sq); cudaFreeHost(b.sl);
 		}
 		delete d;
 	}
@@ -315,6 +363,26 @@ extern "C" int cs_multi_wait(cs_multi_t *m, int set, cs_multi_result_t *out)
 	return rc;
 }
 
+extern "C" int cs_multi_set_chaining(cs_multi_t *m, const cs_bns_view_t *bns, const cs_chain_opt_t *opt)
+{
+	if (!m) return cs_set_err(CS_E_ARG, "null argument");
+	if (m->busy[0] || m->busy[1]) return cs_set_err(CS_E_STATE, "a read set is in flight");
+	if (bns) {
+		if (!opt || bns->n_seqs < 1 || !bns->offset) return cs_set_err(CS_E_ARG, "bad contig table");
+		m->l_pac = bns->l_pac; m->copt = *opt;
+		m->c_off.assign(bns->offset, bns->offset + bns->n_seqs);
+		if (bns->is_alt) m->c_alt.assign(bns->is_alt, bns->is_alt + bns->n_seqs); else m->c_alt.clear();
+	}
+	m->chaining = bns != nullptr;
+	for (Dev *d : m->dev) {
+		std::lock_guard<std::mutex> lk(d->mu);     // (the worker is idle: no set in flight)
+		cs_bns_view_t v; v.l_pac = m->l_pac; v.n_seqs = (int32_t)m->c_off.size(); v.offset = m->c_off.data(); v.is_alt = m->c_alt.empty() ? nullptr : m->c_alt.data();
+		const int rc = cs_ctx_set_chaining(d->ctx, m->chaining ? &v : nullptr, &m->copt);
+		if (rc != CS_OK) { m->chaining = false; return rc; }
+	}
+	return CS_OK;
+}
+
 extern "C" uint64_t cs_multi_launches(const cs_multi_t *m)
 {
 	uint64_t n = 0;
@@ -325,6 +393,7 @@ extern "C" uint64_t cs_multi_launches(const cs_multi_t *m)
 extern "C" int cs_multi_gather(const cs_multi_result_t *res, uint64_t *mem_off, cs_mem_t *mems, uint64_t *seed_off, int64_t *rbeg, int n_threads)
 { // flat arrays in input order (tests, hosts that want them); plain host C++
 	if (!res || !mem_off || !seed_off) return cs_set_err(CS_E_ARG, "null argument");
+	if (res->n_blocks > 0 && res->blocks[0].chains) return cs_set_err(CS_E_STATE, "this result holds chains (cs_multi_read_chains), not mems");
 	if (n_threads < 1) n_threads = 1;
 	if (n_threads > 64) n_threads = 64;
 	uint64_t mb = 0, sb = 0;

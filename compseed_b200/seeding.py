@@ -61,12 +61,57 @@ class _Block(C.Structure):
                 ("mem_base", C.POINTER(C.c_uint64)), ("seed_base", C.POINTER(C.c_uint64)),
                 ("mem_off", C.POINTER(C.c_uint32)), ("seed_off", C.POINTER(C.c_uint32)),
                 ("cmems", C.POINTER(C.c_uint32)), ("rbeg_lo", C.POINTER(C.c_uint32)), ("rbeg_hi", C.POINTER(C.c_uint8)),
-                ("device", C.c_int)]
+                ("device", C.c_int), ("chains", C.POINTER(C.c_uint32)), ("qbeg", C.POINTER(C.c_uint16)), ("len", C.POINTER(C.c_uint16))]
 
 
 class _MultiResult(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_mems", C.c_uint64), ("n_seeds", C.c_uint64), ("n_blocks", C.c_int),
                 ("blocks", C.POINTER(_Block)), ("counters", _Counters), ("seconds", C.c_double), ("host_s", C.c_double * 3)]
+
+
+class _BnsView(C.Structure):
+    _fields_ = [("l_pac", C.c_int64), ("n_seqs", C.c_int32), ("offset", C.c_void_p), ("is_alt", C.c_void_p)]
+
+
+class _ChainOpt(C.Structure):
+    _fields_ = [("w", C.c_int32), ("max_chain_gap", C.c_int32), ("min_chain_weight", C.c_int32), ("max_chain_extend", C.c_int32),
+                ("mask_level", C.c_float), ("drop_ratio", C.c_float)]
+
+
+class _ChainResult(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_chains", C.c_uint64), ("n_cseeds", C.c_uint64),
+                ("chain_off", C.POINTER(C.c_uint32)), ("cseed_off", C.POINTER(C.c_uint32)), ("chains", C.POINTER(C.c_uint32)),
+                ("rbeg_lo", C.POINTER(C.c_uint32)), ("rbeg_hi", C.POINTER(C.c_uint8)), ("qbeg", C.POINTER(C.c_uint16)), ("len", C.POINTER(C.c_uint16))]
+
+
+@dataclass
+class ChainOpt:
+    """The chaining scalars of mem_opt_t with the defaults of mem_opt_init (comp_seed.cpp:26-61)."""
+    w: int = 100
+    max_chain_gap: int = 10000
+    min_chain_weight: int = 0
+    max_chain_extend: int = 1 << 30
+    mask_level: float = 0.5
+    drop_ratio: float = 0.5
+
+    def _c(self) -> _ChainOpt:
+        return _ChainOpt(self.w, self.max_chain_gap, self.min_chain_weight, self.max_chain_extend, self.mask_level, self.drop_ratio)
+
+
+@dataclass
+class ChainResult:
+    """What mem_chain + mem_chain_flt return for a batch (mem_chain_v per read, flattened)."""
+    chain_off: np.ndarray   # u32 [n+1]
+    cseed_off: np.ndarray   # u32 [n+1]
+    rid: np.ndarray         # i32 [n_chains]
+    w: np.ndarray           # i32
+    kept: np.ndarray        # i32  kept | is_alt << 8
+    n: np.ndarray           # i32  seeds per chain
+    l_rep: np.ndarray       # u32 per chain (frac_rep = l_rep / l_seq)
+    s_rbeg: np.ndarray      # i64 [n_cseeds]
+    s_qbeg: np.ndarray      # i32
+    s_len: np.ndarray       # i32
+    wire_bytes: int = 0
 
 
 class _IndexConfig(C.Structure):
@@ -158,8 +203,11 @@ def load_library():
     L.cs_multi_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(_MultiResult)]
     L.cs_multi_gather.argtypes = [C.POINTER(_MultiResult), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.cs_pack_reads_host64.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.cs_multi_set_chaining.argtypes = [C.c_void_p, C.POINTER(_BnsView), C.POINTER(_ChainOpt)]
     L.cs_multi_launches.restype = C.c_uint64
     L.cs_multi_launches.argtypes = [C.c_void_p]
+    L.cs_ctx_set_chaining.argtypes = [C.c_void_p, C.POINTER(_BnsView), C.POINTER(_ChainOpt)]
+    L.cs_seed_batch_wait_chains.argtypes = [C.c_void_p, C.c_int, C.POINTER(_ChainResult)]
     L.cs_ctx_launches.restype = C.c_uint64
     L.cs_ctx_launches.argtypes = [C.c_void_p]
     L.cs_index_download.argtypes = [C.c_void_p, C.POINTER(_BwtView), C.c_void_p, C.c_void_p, C.c_int]
@@ -434,6 +482,40 @@ class SeedContext:
         _check(load_library().cs_seed_batch_wait(self.h, slot, C.byref(r)))
         return self._result(r, copy=copy)
 
+    def set_chaining(self, contig_lens=None, opt: "ChainOpt | None" = None, is_alt=None) -> None:
+        """cs_ctx_set_chaining: batches submitted from now on are also chained on the device (mem_chain + mem_chain_flt).
+        contig_lens: lengths of the reference sequences in order (None switches chaining off)."""
+        if contig_lens is None:
+            _check(load_library().cs_ctx_set_chaining(self.h, None, None))
+            return
+        lens = np.asarray(contig_lens, dtype=np.int64)
+        offs = np.ascontiguousarray(np.concatenate([[0], np.cumsum(lens)[:-1]]), dtype=np.int64)
+        alt = np.ascontiguousarray(is_alt, dtype=np.uint8) if is_alt is not None else None
+        v = _BnsView(int(lens.sum()), lens.shape[0], _ptr(offs), _ptr(alt) if alt is not None else None)
+        o = (opt or ChainOpt())._c()
+        _check(load_library().cs_ctx_set_chaining(self.h, C.byref(v), C.byref(o)))
+
+    def wait_chains(self, slot: int) -> ChainResult:
+        """cs_seed_batch_wait_chains: only the filtered chains of the batch cross the link."""
+        r = _ChainResult()
+        _check(load_library().cs_seed_batch_wait_chains(self.h, slot, C.byref(r)))
+        n, nc, ns = int(r.n_reads), int(r.n_chains), int(r.n_cseeds)
+        chain_off = np.ctypeslib.as_array(r.chain_off, shape=(n + 1,)).copy()
+        cseed_off = np.ctypeslib.as_array(r.cseed_off, shape=(n + 1,)).copy()
+        ch = np.ctypeslib.as_array(r.chains, shape=(nc, 4)).copy() if nc else np.empty((0, 4), dtype=np.uint32)
+        if ns:
+            lo = np.ctypeslib.as_array(r.rbeg_lo, shape=(ns,)).astype(np.int64)
+            hi = np.ctypeslib.as_array(r.rbeg_hi, shape=(ns,)).astype(np.int64)
+            rb = ((lo | (hi << 32)) << 24) >> 24          # 40 bits, sign-extended (cs_crbeg)
+            qb = np.ctypeslib.as_array(r.qbeg, shape=(ns,)).astype(np.int32)
+            ln = np.ctypeslib.as_array(r.len, shape=(ns,)).astype(np.int32)
+        else:
+            rb, qb, ln = np.empty(0, np.int64), np.empty(0, np.int32), np.empty(0, np.int32)
+        wk = ch[:, 1]
+        return ChainResult(chain_off, cseed_off, ch[:, 0].astype(np.int32), (wk & 0x1fffffff).astype(np.int32),
+                           (((wk >> 29) & 3) | ((wk >> 31) << 8)).astype(np.int32), ch[:, 2].astype(np.int32), ch[:, 3].copy(), rb, qb, ln,
+                           wire_bytes=8 * (n + 1) + 16 * nc + 9 * ns)
+
     def wait_compact(self, slot: int, expand_threads: int = 0):
         """cs_seed_batch_wait_compact.  expand_threads == 0: the compact arrays as they arrived (views into the slot's
         pinned buffers: mem_off, cmems u32[n_mems, 5], seed_off, rbeg_lo, rbeg_hi); > 0: a SeedResult expanded by
@@ -560,6 +642,53 @@ class MultiSeeder:
         o = opt._c()
         _check(load_library().cs_multi_submit_packed(self.h, set_id, off64.shape[0] - 1, _ptr(packed), _ptr(nmask), _ptr(off64), C.byref(o)))
 
+    def set_chaining(self, contig_lens=None, opt: "ChainOpt | None" = None, is_alt=None) -> None:
+        """cs_multi_set_chaining: from the next set on the results are the filtered chains (None: mems + seed positions again)."""
+        if contig_lens is None:
+            _check(load_library().cs_multi_set_chaining(self.h, None, None))
+            self._chaining = False
+            return
+        lens = np.asarray(contig_lens, dtype=np.int64)
+        offs = np.ascontiguousarray(np.concatenate([[0], np.cumsum(lens)[:-1]]), dtype=np.int64)
+        alt = np.ascontiguousarray(is_alt, dtype=np.uint8) if is_alt is not None else None
+        v = _BnsView(int(lens.sum()), lens.shape[0], _ptr(offs), _ptr(alt) if alt is not None else None)
+        o = (opt or ChainOpt())._c()
+        _check(load_library().cs_multi_set_chaining(self.h, C.byref(v), C.byref(o)))
+        self._chaining = True
+
+    @staticmethod
+    def _gather_chains(r: "_MultiResult") -> ChainResult:
+        """Flat chains in input order from the blocks of a chained result (what cs_multi_read_chains walks), in numpy."""
+        offs_c, offs_s, recs, lo, hi, qb, ln = [np.zeros(1, np.int64)], [np.zeros(1, np.int64)], [], [], [], [], []
+        cb = sb = 0
+        for k in range(r.n_blocks):
+            b = r.blocks[k]
+            n = int(b.r1 - b.r0)
+            if n == 0:
+                continue
+            B, nb = int(b.batch_reads), int(b.n_batches)
+            cbase = np.ctypeslib.as_array(b.mem_base, shape=(nb + 1,)).astype(np.int64)
+            sbase = np.ctypeslib.as_array(b.seed_base, shape=(nb + 1,)).astype(np.int64)
+            co = np.ctypeslib.as_array(b.mem_off, shape=(nb, B + 1)).astype(np.int64)
+            so = np.ctypeslib.as_array(b.seed_off, shape=(nb, B + 1)).astype(np.int64)
+            for bi in range(nb):
+                m = min(B, n - bi * B)
+                offs_c.append(cb + cbase[bi] + co[bi, 1:m + 1]); offs_s.append(sb + sbase[bi] + so[bi, 1:m + 1])
+            nc, ns = int(cbase[nb]), int(sbase[nb])
+            if nc:
+                recs.append(np.ctypeslib.as_array(b.chains, shape=(nc, 4)).copy())
+            if ns:
+                lo.append(np.ctypeslib.as_array(b.rbeg_lo, shape=(ns,)).astype(np.int64)); hi.append(np.ctypeslib.as_array(b.rbeg_hi, shape=(ns,)).astype(np.int64))
+                qb.append(np.ctypeslib.as_array(b.qbeg, shape=(ns,)).astype(np.int32)); ln.append(np.ctypeslib.as_array(b.len, shape=(ns,)).astype(np.int32))
+            cb += nc; sb += ns
+        ch = np.concatenate(recs) if recs else np.empty((0, 4), np.uint32)
+        cat = lambda xs, dt: np.concatenate(xs) if xs else np.empty(0, dt)
+        rb = ((cat(lo, np.int64) | (cat(hi, np.int64) << 32)) << 24) >> 24
+        wk = ch[:, 1]
+        return ChainResult(np.concatenate(offs_c).astype(np.uint32), np.concatenate(offs_s).astype(np.uint32), ch[:, 0].astype(np.int32),
+                           (wk & 0x1fffffff).astype(np.int32), (((wk >> 29) & 3) | ((wk >> 31) << 8)).astype(np.int32), ch[:, 2].astype(np.int32),
+                           ch[:, 3].copy(), rb, cat(qb, np.int32), cat(ln, np.int32), wire_bytes=8 * int(r.n_reads) + 16 * ch.shape[0] + 9 * rb.shape[0])
+
     def wait(self, set_id: int, gather: bool = True, n_threads: int = 4):
         """Waits for the set.  gather=True: a SeedResult with flat arrays in input order (cs_multi_gather; offsets as u64);
         gather=False: dict(n_reads, n_mems, n_seeds, seconds, blocks=[(device, r0, r1)]) -- the results stay where the DMA put them."""
@@ -569,7 +698,14 @@ class MultiSeeder:
         info = dict(n_reads=int(r.n_reads), n_mems=int(r.n_mems), n_seeds=int(r.n_seeds), seconds=float(r.seconds),
                     blocks=[(int(r.blocks[k].device), int(r.blocks[k].r0), int(r.blocks[k].r1)) for k in range(r.n_blocks)],
                     wire_bytes=8 * int(r.n_reads) + 20 * int(r.n_mems) + 5 * int(r.n_seeds),
-                    host_s=dict(submit=float(r.host_s[0]), kernel_wait=float(r.host_s[1]), copy_wait=float(r.host_s[2])))
+                    host_s=dict(submit=float(r.host_s[0]), finish_and_enqueue=float(r.host_s[1]), idle=float(r.host_s[2])))
+        if getattr(self, "_chaining", False):      # n_mems / n_seeds count chains / chain seeds then
+            info["wire_bytes"] = 8 * int(r.n_reads) + 16 * int(r.n_mems) + 9 * int(r.n_seeds)
+            if not gather:
+                return info
+            res = self._gather_chains(r)
+            res.info = info
+            return res
         if not gather:
             return info
         n = int(r.n_reads)

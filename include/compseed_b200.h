@@ -254,6 +254,49 @@ int cs_seed_batch_wait_compact(cs_ctx_t *ctx, int slot, cs_compact_result_t *out
 /* Expands a compact result into plain arrays (mems: n_mems entries, rbeg: n_seeds) on n_threads host threads. */
 int cs_compact_expand(const cs_compact_result_t *res, cs_mem_t *mems, int64_t *rbeg, int n_threads);
 
+/* --- chaining on the device ---------------------------------------------------------------
+ * mem_chain + mem_chain_flt (mapping/bwamem.c:359-497 == mapping/comp_seed.cpp:241-354) run on the mems and seed positions
+ * of a batch where the seeding kernels left them, so that only the filtered chains cross the device-to-host link
+ * (about 45 bytes per 150-bp read instead of 225).  Bit-exact, including the order-dependent parts: the B-tree of chains
+ * (cstl/kbtree.h, t = 5), ks_introsort by weight (cstl/ksort.h) and the pairwise overlap filter. */
+typedef struct {             /* the fields of bntseq_t that bns_intv2rid reads (FM_index/bntseq.h:41-64, bntseq.c:354-378) */
+	int64_t l_pac;
+	int32_t n_seqs;
+	const int64_t *offset;   /* [n_seqs] anns[i].offset */
+	const uint8_t *is_alt;   /* [n_seqs] anns[i].is_alt != 0, or NULL */
+} cs_bns_view_t;
+
+typedef struct {             /* the chaining scalars of mem_opt_t (mapping/comp_seed.h:41-73); defaults of mem_opt_init in () */
+	int32_t w;                /* band width (100) */
+	int32_t max_chain_gap;    /* (10000) */
+	int32_t min_chain_weight; /* (0) */
+	int32_t max_chain_extend; /* (1 << 30) */
+	float mask_level;         /* (0.50) */
+	float drop_ratio;         /* (0.50) */
+} cs_chain_opt_t;
+
+typedef struct {
+	int32_t rid;              /* mem_chain_t.rid */
+	uint32_t w_kept;          /* w : 29 | kept : 2 | is_alt : 1, the bit-field of mem_chain_t (bwamem.c:286) */
+	uint32_t n;               /* seeds in the chain */
+	uint32_t l_rep;           /* bases of the read covered by repetitive seeds: frac_rep = (float)l_rep / l_seq (bwamem.c:377-385,424) */
+} cs_chain_t;                /* pos == rbeg of the chain's first seed */
+
+typedef struct {
+	uint32_t n_reads;
+	uint64_t n_chains, n_cseeds;
+	const uint32_t *chain_off;   /* [n_reads+1] the chains mem_chain_flt keeps, in its output order */
+	const uint32_t *cseed_off;   /* [n_reads+1] first chain seed of each read */
+	const cs_chain_t *chains;    /* [n_chains] */
+	const uint32_t *rbeg_lo; const uint8_t *rbeg_hi;   /* [n_cseeds] seeds of chain after chain, in chain order (cs_crbeg) */
+	const uint16_t *qbeg, *len;  /* [n_cseeds] mem_seed_t.qbeg / .len (score == len) */
+} cs_chain_result_t;
+
+/* Every batch submitted after this call is also chained (bns == NULL: switched off again).  Copies the contig table. */
+int cs_ctx_set_chaining(cs_ctx_t *ctx, const cs_bns_view_t *bns, const cs_chain_opt_t *opt);
+/* Waits for the slot and fetches ONLY the chains (the mems / seed positions stay on the device; cs_seed_batch_fetch still gets them). */
+int cs_seed_batch_wait_chains(cs_ctx_t *ctx, int slot, cs_chain_result_t *out);
+
 /* --- multi-device pipeline ----------------------------------------------------------------------
  * Replaces kt_for(opt->n_threads, worker1 / seed_and_extend) over the reads of a -K batch for the seeding part
  * (mapping/bwamem.c:1343, comp_seed.cpp:2541-2548), and -- with two read sets in flight -- the overlap kt_pipeline gives
@@ -273,6 +316,10 @@ typedef struct {            /* the reads [r0, r1) of a set, seeded by one device
 	const cs_cmem_t *cmems;                 /* mems of the block, reads in input order, per read sorted by info */
 	const uint32_t *rbeg_lo; const uint8_t *rbeg_hi;
 	int device;
+	/* with cs_multi_set_chaining the block holds CHAINS instead: mem_base / mem_off index chains[], seed_base / seed_off
+	 * index the chain seeds (rbeg_lo, rbeg_hi, qbeg, len); cmems is NULL */
+	const cs_chain_t *chains;
+	const uint16_t *qbeg, *len;
 } cs_block_t;
 
 typedef struct {
@@ -282,7 +329,8 @@ typedef struct {
 	cs_counters_t counters;
 	double seconds;             /* submit to the last device finishing */
 	double host_s[3];           /* where the slowest device's host thread spent that time: [0] submitting batches (offsets, enqueueing
-	                               copies and kernels), [1] waiting for kernels, [2] waiting for result copies */
+	                               copies and kernels), [1] polling, checking finished batches and enqueueing their result copies,
+	                               [2] idle (nothing was ready) */
 } cs_multi_result_t;
 
 /* where read r of the set is: its mems cm[0..n_mems) and the index s0 of its first seed position in (lo, hi) */
@@ -295,6 +343,18 @@ static inline void cs_multi_read(const cs_multi_result_t *res, uint64_t r, const
 	const uint64_t lr = r - b->r0, bi = lr / b->batch_reads, i = bi * (b->batch_reads + 1ull) + lr % b->batch_reads;
 	*cm = b->cmems + b->mem_base[bi] + b->mem_off[i]; *n_mems = b->mem_off[i + 1] - b->mem_off[i];
 	*lo = b->rbeg_lo; *hi = b->rbeg_hi; *s0 = b->seed_base[bi] + b->seed_off[i]; *n_seeds = b->seed_off[i + 1] - b->seed_off[i];
+}
+
+/* the chains of read r (after cs_multi_set_chaining): ch[0..n_chains), their seeds one chain after the other from index s0 */
+static inline void cs_multi_read_chains(const cs_multi_result_t *res, uint64_t r, const cs_chain_t **ch, uint32_t *n_chains,
+                                        const cs_block_t **blk, uint64_t *s0)
+{
+	int k = 0;
+	while (k + 1 < res->n_blocks && r >= res->blocks[k].r1) ++k;
+	const cs_block_t *b = &res->blocks[k];
+	const uint64_t lr = r - b->r0, bi = lr / b->batch_reads, i = bi * (b->batch_reads + 1ull) + lr % b->batch_reads;
+	*ch = b->chains + b->mem_base[bi] + b->mem_off[i]; *n_chains = b->mem_off[i + 1] - b->mem_off[i];
+	*blk = b; *s0 = b->seed_base[bi] + b->seed_off[i];
 }
 
 /* idx[k]: the index replica on the k-th device to use (cs_index_replicate copies one device-to-device over NVLink).
@@ -311,6 +371,9 @@ int cs_multi_submit(cs_multi_t *m, int set, uint64_t n_reads, const uint8_t *bas
 int cs_multi_submit_packed(cs_multi_t *m, int set, uint64_t n_reads, const uint64_t *packed, const uint32_t *nmask,
                            const uint64_t *offsets, const cs_seed_opt_t *opt);
 int cs_multi_wait(cs_multi_t *m, int set, cs_multi_result_t *out);
+/* From the next set on, the devices also chain (cs_ctx_set_chaining) and the results are chains (cs_multi_read_chains); bns ==
+ * NULL switches back to mems + seed positions.  No set may be in flight. */
+int cs_multi_set_chaining(cs_multi_t *m, const cs_bns_view_t *bns, const cs_chain_opt_t *opt);
 int cs_pack_reads_host64(uint64_t n_reads, const uint8_t *bases, const uint64_t *offsets, uint64_t *packed, uint32_t *nmask, int n_threads);
 /* Flat arrays in input order from a multi result (mem_off / seed_off: n_reads+1 each; mems / rbeg may be NULL). */
 int cs_multi_gather(const cs_multi_result_t *res, uint64_t *mem_off, cs_mem_t *mems, uint64_t *seed_off, int64_t *rbeg, int n_threads);

@@ -15,15 +15,18 @@ sed -e 's|^#include "bwamem.h"|#include "bwamem.h"\n#include "cs_shim.h"|' \
     -e 's|^\t\tw->regs\[i\] = mem_align1_core(|\t\tcsgpu_set_read(i); w->regs[i] = mem_align1_core(|' \
     -e 's|^\t\tw->regs\[i<<1\|0\] = mem_align1_core(|\t\tcsgpu_set_read(i<<1\|0); w->regs[i<<1\|0] = mem_align1_core(|' \
     -e 's|^\t\tw->regs\[i<<1\|1\] = mem_align1_core(|\t\tcsgpu_set_read(i<<1\|1); w->regs[i<<1\|1] = mem_align1_core(|' \
-    -e 's|^\tkt_for(opt->n_threads, worker1, &w, |\tcsgpu_seed_batch(opt, bwt, n, seqs);\n\tkt_for(opt->n_threads, worker1, \&w, |' \
+    -e 's|^\tkt_for(opt->n_threads, worker1, &w, |\tcsgpu_seed_batch(opt, bwt, bns, n, seqs);\n\tkt_for(opt->n_threads, worker1, \&w, |' \
+    -e 's|^mem_alnreg_v mem_align1_core(|#include "bwamem_chain_glue.c"\n\nmem_alnreg_v mem_align1_core(|' \
+    -e 's|^\tchn = mem_chain(opt, bwt, bns, l_seq, (uint8_t\*)seq, buf, tid);|\tchn = csgpu_chaining() ? csgpu_chains_of_read(l_seq) : mem_chain(opt, bwt, bns, l_seq, (uint8_t*)seq, buf, tid);|' \
+    -e 's|^\tchn.n = mem_chain_flt(opt, chn.n, chn.a);|\tif (!csgpu_chaining()) chn.n = mem_chain_flt(opt, chn.n, chn.a);|' \
     "$REF/mapping/bwamem.c" > "$OUT/bwamem_gpu.c"
-for pat in 'cs_shim.h' 'csgpu_fill_mems' 'csgpu_next_rbeg' 'csgpu_set_read(i);' 'csgpu_seed_batch'; do
+for pat in 'cs_shim.h' 'csgpu_fill_mems' 'csgpu_next_rbeg' 'csgpu_set_read(i);' 'csgpu_seed_batch' 'bwamem_chain_glue.c' 'csgpu_chains_of_read(l_seq)' 'if (!csgpu_chaining()) chn.n'; do
   grep -q "$pat" "$OUT/bwamem_gpu.c" || { echo "patch site not found: $pat"; exit 1; }
 done
 diff -u "$REF/mapping/bwamem.c" "$OUT/bwamem_gpu.c" > "$OUT/bwamem_gpu.patch" || true
 # batch-ahead overlap: step 0 of process() (the reader, fastmap.c:76-103) hands the batch it just read to the GPUs
 sed -e 's|^#include "bwamem.h"|#include "bwamem.h"\n#include "cs_shim.h"|' \
-    -e 's|^\t\treturn ret;|\t\tcsgpu_prefetch_batch(aux->opt, aux->idx->bwt, ret->n_seqs, ret->seqs); /* added: seed batch i+1 while batch i is chained */\n\t\treturn ret;|' \
+    -e 's|^\t\treturn ret;|\t\tcsgpu_prefetch_batch(aux->opt, aux->idx->bwt, aux->idx->bns, ret->n_seqs, ret->seqs); /* added: seed batch i+1 while batch i is chained */\n\t\treturn ret;|' \
     "$REF/mapping/fastmap.c" > "$OUT/fastmap_gpu.c"
 for pat in 'cs_shim.h' 'csgpu_prefetch_batch'; do
   grep -q "$pat" "$OUT/fastmap_gpu.c" || { echo "patch site not found in fastmap.c: $pat"; exit 1; }

@@ -39,6 +39,8 @@ static set_t g_set[N_SETS];
 static int g_next_set;
 static cs_multi_result_t g_res;     /* the batch the kt_for workers are reading */
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;   /* step 0 (prefetch) and step 1 (seed) of different batches run concurrently */
+static int g_chain = -1;            /* CSGPU_CHAIN=1: the GPUs also chain; the host takes chains instead of mems + seeds */
+static __thread const cs_chain_t *t_ch; static __thread uint32_t t_nch; static __thread const cs_block_t *t_blk; static __thread uint64_t t_cs0;
 static __thread const cs_cmem_t *t_cm; static __thread uint32_t t_nm;
 static __thread const uint32_t *t_lo; static __thread const uint8_t *t_hi; static __thread uint64_t t_cursor;
 
@@ -70,6 +72,22 @@ static void ensure_index(const bwt_t *bwt)
 
 /* (re)creates the pipeline for reads up to max_len bases.  Only step 1 may re-create (no kt_for worker is reading results
  * then); a set step 0 prefetched for the next batch is dropped and will be seeded again when its own step 1 comes. */
+static const bntseq_t *g_bns; static mem_opt_t g_chain_opt;
+
+static void apply_chaining(void)
+{ /* contig table (the fields bns_intv2rid reads) and the chaining scalars of mem_opt_t */
+	cs_bns_view_t v; cs_chain_opt_t co;
+	int64_t *off; uint8_t *alt; int i;
+	if (g_chain <= 0 || !g_bns) return;
+	off = (int64_t*)malloc(g_bns->n_seqs * 8); alt = (uint8_t*)malloc(g_bns->n_seqs);
+	for (i = 0; i < g_bns->n_seqs; ++i) { off[i] = g_bns->anns[i].offset; alt[i] = g_bns->anns[i].is_alt != 0; }
+	v.l_pac = g_bns->l_pac; v.n_seqs = g_bns->n_seqs; v.offset = off; v.is_alt = alt;
+	co.w = g_chain_opt.w; co.max_chain_gap = g_chain_opt.max_chain_gap; co.min_chain_weight = g_chain_opt.min_chain_weight;
+	co.max_chain_extend = g_chain_opt.max_chain_extend; co.mask_level = g_chain_opt.mask_level; co.drop_ratio = g_chain_opt.drop_ratio;
+	if (cs_multi_set_chaining(g_multi, &v, &co) != CS_OK) fatal("cs_multi_set_chaining");
+	free(off); free(alt);
+}
+
 static int ensure_multi(uint32_t max_len, int may_recreate)
 {
 	const char *b = getenv("CSGPU_BATCH");
@@ -84,6 +102,7 @@ static int ensure_multi(uint32_t max_len, int may_recreate)
 	g_multi_len = max_len < 256 ? 256 : max_len;
 	g_multi = cs_multi_create(g_idx, g_ndev, b && atoi(b) > 0 ? (uint32_t)atoi(b) : (1u << 18), g_multi_len, 3, 0, 0, NULL);
 	if (!g_multi) fatal("cs_multi_create");
+	apply_chaining();
 	return 1;
 }
 
@@ -120,13 +139,22 @@ static int submit_set(int s, const mem_opt_t *opt, int n, const bseq1_t *seqs, i
 	return 1;
 }
 
-void csgpu_prefetch_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const bseq1_t *seqs)
+static void note_chain_setup(const mem_opt_t *opt, const bntseq_t *bns)
+{
+	if (g_chain < 0) g_chain = getenv("CSGPU_CHAIN") != 0 && atoi(getenv("CSGPU_CHAIN")) != 0;
+	g_bns = bns; g_chain_opt = *opt;
+}
+
+int csgpu_chaining(void) { return g_chain > 0; }
+
+void csgpu_prefetch_batch(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, int n, const bseq1_t *seqs)
 {
 	static int off = -1;
 	int s;
 	if (off < 0) off = getenv("CSGPU_NO_PREFETCH") != 0;
 	if (n <= 0 || off) return;
 	pthread_mutex_lock(&g_mu);
+	note_chain_setup(opt, bns);
 	ensure_index(bwt);
 	s = g_next_set;
 	if (!g_set[s].submitted && submit_set(s, opt, n, seqs, 0)) g_next_set = (g_next_set + 1) % N_SETS;
@@ -134,11 +162,12 @@ void csgpu_prefetch_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const b
 	pthread_mutex_unlock(&g_mu);
 }
 
-void csgpu_seed_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const bseq1_t *seqs)
+void csgpu_seed_batch(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, int n, const bseq1_t *seqs)
 {
 	int s, found = -1;
 	if (n <= 0) return;
 	pthread_mutex_lock(&g_mu);
+	note_chain_setup(opt, bns);
 	ensure_index(bwt);
 	for (s = 0; s < N_SETS; ++s)
 		if (g_set[s].submitted == 1 && g_set[s].seqs == seqs && g_set[s].n == n) found = s;
@@ -160,7 +189,23 @@ void csgpu_seed_batch(const mem_opt_t *opt, const bwt_t *bwt, int n, const bseq1
 void csgpu_set_read(int i)
 {
 	uint32_t ns;
-	cs_multi_read(&g_res, (uint64_t)i, &t_cm, &t_nm, &t_lo, &t_hi, &t_cursor, &ns);
+	if (g_chain > 0) cs_multi_read_chains(&g_res, (uint64_t)i, &t_ch, &t_nch, &t_blk, &t_cs0);
+	else cs_multi_read(&g_res, (uint64_t)i, &t_cm, &t_nm, &t_lo, &t_hi, &t_cursor, &ns);
+}
+
+/* chains of the read in hand (CSGPU_CHAIN=1), for the glue in integration/bwamem_chain_glue.c */
+int csgpu_n_chains(void) { return (int)t_nch; }
+void csgpu_chain(int c, int *rid, int *w, int *kept, int *is_alt, int *n, int *l_rep, uint64_t *first_seed)
+{
+	const cs_chain_t *p = t_ch + c;
+	uint64_t s = t_cs0; int k;
+	for (k = 0; k < c; ++k) s += t_ch[k].n;
+	*rid = p->rid; *w = (int)(p->w_kept & 0x1fffffffu); *kept = (int)((p->w_kept >> 29) & 3); *is_alt = (int)(p->w_kept >> 31);
+	*n = (int)p->n; *l_rep = (int)p->l_rep; *first_seed = s;
+}
+void csgpu_chain_seed(uint64_t s, int64_t *rbeg, int *qbeg, int *len)
+{
+	*rbeg = cs_crbeg(t_blk->rbeg_lo, t_blk->rbeg_hi, s); *qbeg = t_blk->qbeg[s]; *len = t_blk->len[s];
 }
 
 void csgpu_fill_mems(bwtintv_v *mem)

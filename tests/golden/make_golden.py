@@ -74,6 +74,12 @@ def main():
                                            o.get("split_width", 10), o.get("max_mem_intv", 20), o.get("max_occ", 500)], dtype=np.int32)
                 out[f"mem_off{i}"], out[f"mems{i}"], out[f"seed_off{i}"], out[f"rbeg{i}"] = a.mem_off, a.mems, a.seed_off, a.rbeg
                 print(name, i, "reads", off.shape[0] - 1, "mems", a.mems.shape[0], "seeds", a.rbeg.shape[0], b.counters)
+                if i == 0:   # chains of the default option set: the reference's own mem_chain + mem_chain_flt (comp_seed.cpp:241-354)
+                    ch = O.ref_chain(off, a, [ref.shape[0]], **o)
+                    for k in ("pos", "rid", "w", "kept", "n", "s_rbeg", "s_qbeg", "s_len", "frac_rep"):
+                        out[f"chain_{k}0"] = getattr(ch, k)
+                    out["chain_off0"] = ch.chain_off
+                    print(name, "chains", ch.pos.shape[0], "chain seeds", ch.s_rbeg.shape[0])
             # extend probes: intervals taken from real mems plus the four 1-base intervals
             iv = [a.mems[:200, :3]]
             for c in range(4):

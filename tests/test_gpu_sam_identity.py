@@ -62,7 +62,16 @@ def test_sam_is_byte_identical(cuda_lib, tmp_path, kind):
     got5 = _run(GPUBIN, ["-t", "4", "-K", "100000", idx, reads], os.path.join(d, "gpu5.sam"), env={"CSGPU_DEVICES": "all", "CSGPU_BATCH": "1024"})
     got6 = _run(GPUBIN, ["-t", "4", "-K", "100000", idx, reads], os.path.join(d, "gpu6.sam"), env={"CSGPU_DEVICES": "1"})
     assert got5 == want and got6 == want
+    # chaining and chain filtering on the GPUs too: mem_align1_core takes the chains instead of running
+    # mem_chain / mem_chain_flt; only chains cross the device-to-host link
+    got7 = _run(GPUBIN, ["-t", "4", "-K", "200000", idx, reads], os.path.join(d, "gpu7.sam"), env={"CSGPU_CHAIN": "1"})
+    got8 = _run(GPUBIN, ["-t", "3", "-K", "40000", idx, reads], os.path.join(d, "gpu8.sam"), env={"CSGPU_CHAIN": "1", "CSGPU_BATCH": "900", "CSGPU_DEVICES": "all"})
+    assert got7 == want and got8 == want
     # non-default seeding options travel through the shim
     a = _run(os.path.join(REFBIN, "bwamem"), ["-t", "4", "-k", "15", "-r", "1.0", "-y", "40", "-c", "50", idx, reads], os.path.join(d, "a.sam"))
     b = _run(GPUBIN, ["-t", "4", "-k", "15", "-r", "1.0", "-y", "40", "-c", "50", idx, reads], os.path.join(d, "b.sam"))
     assert a == b
+    # ... and non-default chaining options (-w band width, -D drop ratio, -W min chain weight, -G max chain extend)
+    ca = _run(os.path.join(REFBIN, "bwamem"), ["-t", "4", "-w", "40", "-D", "0.7", "-W", "25", idx, reads], os.path.join(d, "ca.sam"))
+    cb = _run(GPUBIN, ["-t", "4", "-w", "40", "-D", "0.7", "-W", "25", idx, reads], os.path.join(d, "cb.sam"), env={"CSGPU_CHAIN": "1"})
+    assert ca == cb
