@@ -140,6 +140,14 @@ def cpu_seed_sample(host_idx, bases, off, n_sample: int, threads: int):
     return out, res, n
 
 
+def contig_lens(ref_len: int):
+    """The reference sequences the chaining stage sees: bntann1_t.len is int32 (bntseq.h:43), so the 3.1 Gbp reference is a
+    set of 25 equal contigs, human-chromosome sized; seeding never looks at contig boundaries."""
+    n = max(1, -(-ref_len // 124_000_000))
+    base = ref_len // n
+    return [base] * (n - 1) + [ref_len - base * (n - 1)]
+
+
 def same_prefix(got, want, n: int) -> bool:
     """The first n reads of `got` (mem_off, mems, seed_off, rbeg of a longer run) == `want` (exactly n reads), bit for bit."""
     nm, ns = int(want.mem_off[-1]), int(want.seed_off[-1])
@@ -183,6 +191,7 @@ def e2e_only(args, cs, idx, bases, off, opt, ccfg, threads):
         infos.append(ms_.wait((args.steps - 1) & 1, gather=False))
         dt = time.perf_counter() - t0
         hs = {k: float(np.mean([x["host_s"][k] for x in infos])) for k in infos[0]["host_s"]}
+        hs.update({"gpu_ms_" + k: float(np.mean([x["gpu_ms"][k] for x in infos])) for k in infos[0]["gpu_ms"]})
         print(json.dumps({"e2e_reads_per_s": n_reads * args.steps / dt, "input": "packed" if packed_in else "bytes", "batch": args.e2e_batch, "slots": args.e2e_slots,
                           "set_seconds": float(np.mean([x["seconds"] for x in infos])), "host_thread_s_per_set": hs, "wire_bytes": infos[-1]["wire_bytes"]}))
         ms_.close()
@@ -363,7 +372,7 @@ def main():
             cs.host_register(bases)   # the reads sit in page-locked host memory, as the bench contract asks
         ms_ = cs.MultiSeeder([idx], batch_reads=bs, max_read_len=args.read_len, n_slots=args.e2e_slots, mems_per_read=14, seeds_per_read=20, config=ccfg)
         if chains:      # mem_chain + mem_chain_flt on the GPU too: only the filtered chains come back
-            ms_.set_chaining([args.ref_len])
+            ms_.set_chaining(contig_lens(args.ref_len))
 
         def submit(set_id):
             if packed_in:
@@ -493,7 +502,7 @@ def main():
             parity["e2e_equal"] = all(same_prefix(e2e_head, w, n_cmp) for w in ref_res.values())
         if chain_head is not None and cpu_baseline["kind"] == "reference":   # the reference's own mem_chain + mem_chain_flt on its own seeds
             from oracle import oracle_py as O
-            want_c = O.ref_chain(off[:n_cmp + 1], first, [args.ref_len])
+            want_c = O.ref_chain(off[:n_cmp + 1], first, contig_lens(args.ref_len))
             ce = bool(np.array_equal(chain_head["chain_off"], want_c.chain_off) and np.array_equal(chain_head["rid"], want_c.rid)
                       and np.array_equal(chain_head["w"], want_c.w) and np.array_equal(chain_head["kept"], want_c.kept) and np.array_equal(chain_head["n"], want_c.n)
                       and np.array_equal(chain_head["s_rbeg"], want_c.s_rbeg) and np.array_equal(chain_head["s_qbeg"], want_c.s_qbeg)

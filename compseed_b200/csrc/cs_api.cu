@@ -510,6 +510,7 @@ struct Slot {
 	cudaStream_t stream2;  // the third-pass kernel runs here, next to k_seed_walk / k_seed (it depends on k_seed_fast only)
 	cudaEvent_t ev[8];   // slot start, seed start, seed end, collect end, sa end, k_seed end, k_seed_fast end, k_seed_walk end
 	cudaEvent_t ev_pack;   // k_pack_reads done
+	cudaEvent_t ev_kend;   // last kernel of the batch done (timed twin of ev_kdone)
 	cudaEvent_t ev_fork, ev_join, ev_r3[2];   // fork / join of stream2; start and end of the third-pass kernel on it
 	cudaEvent_t ev_done;
 	cudaEvent_t ev_kdone;  // kernels and the control block copy of the batch in flight are complete
@@ -578,6 +579,7 @@ static void slot_free(Slot *s)
 	if (s->stream2) cudaStreamDestroy(s->stream2);
 	for (int i = 0; i < 8; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
 	if (s->ev_pack) cudaEventDestroy(s->ev_pack);
+	if (s->ev_kend) cudaEventDestroy(s->ev_kend);
 	if (s->ev_fork) cudaEventDestroy(s->ev_fork);
 	if (s->ev_join) cudaEventDestroy(s->ev_join);
 	for (int i = 0; i < 2; ++i) if (s->ev_r3[i]) cudaEventDestroy(s->ev_r3[i]);
@@ -683,6 +685,7 @@ extern "C" cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads,
 		CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
 		for (int e = 0; e < 8; ++e) CK(cudaEventCreate(&s->ev[e]));
 		CK(cudaEventCreate(&s->ev_pack));
+		CK(cudaEventCreate(&s->ev_kend));
 		CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
 		for (int e = 0; e < 2; ++e) CK(cudaEventCreate(&s->ev_r3[e]));
@@ -931,6 +934,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 		                                                         &s->d_ctrl->n_seeds, ctx->max_seeds, s->d_rows, s->d_rlo, s->d_rhi);
 		CK(cudaGetLastError()); ++ctx->n_launch;
 	}
+	CK(cudaEventRecord(s->ev_kend, s->stream));
 	CK(cudaMemcpyAsync(s->h_ctrl, s->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaEventRecord(s->ev_kdone, s->stream));
 	s->state = 2;
@@ -1245,7 +1249,12 @@ int cs_i_fetch_wait(cs_ctx *ctx, int slot, cs_counters_t *cnt, float *slot_ms)
 		cnt->ext_queries += s->h_ctrl->counters[0]; cnt->ext_calls += s->h_ctrl->counters[1];
 		cnt->sal_queries += s->h_ctrl->n_seeds; cnt->sal_calls += s->h_ctrl->lf_steps;
 	}
-	if (slot_ms) cudaEventElapsedTime(slot_ms, s->ev[0], s->ev_done);
+	if (slot_ms) { // [0] submit -> kernels start (H2D and whatever ran before on the GPU), [1] seeding kernels, [2] collect + SA (+ chaining, compaction), [3] kernels end -> results on the host
+		cudaEventElapsedTime(slot_ms + 0, s->ev[0], s->ev[1]);
+		cudaEventElapsedTime(slot_ms + 1, s->ev[1], s->ev[2]);
+		cudaEventElapsedTime(slot_ms + 2, s->ev[2], s->ev_kend);
+		cudaEventElapsedTime(slot_ms + 3, s->ev_kend, s->ev_done);
+	}
 	return CS_OK;
 fail:
 	return CS_E_CUDA;

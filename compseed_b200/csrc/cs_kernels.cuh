@@ -5,15 +5,15 @@
 
 #define CS_SEED_BLOCK   256     // threads per CTA of the seeding kernel
 #ifndef CS_LIST_SMEM
-#define CS_LIST_SMEM    8       // interval-list entries per thread kept in shared memory
-#endif
+#define CS_LIST_SMEM    16      // interval-list entries per thread kept in shared memory (the rest spills to HBM).  16 entries and 2 CTAs per
+#endif                          // SM instead of 8 and 3: +10 % on the repeat-rich configuration, neutral on cfg2 (profiles/r02_variants.json)
 #ifndef CS_READ_SMEM
 #define CS_READ_SMEM    9       // 32-base words of the read in flight kept in shared memory (reads <= 256 bases + pad word)
 #endif
 // dynamic shared memory of k_seed: interval lists [entry][thread] + packed reads [word][thread] + N masks
 #define CS_SEED_SMEM_BYTES ((size_t)CS_SEED_BLOCK * (CS_LIST_SMEM * 16 + CS_READ_SMEM * 12))
 #ifndef CS_SEED_MINBLOCKS
-#define CS_SEED_MINBLOCKS 3     // CTAs per SM the register allocation of k_seed is tuned for
+#define CS_SEED_MINBLOCKS 2     // CTAs per SM the register allocation of k_seed is tuned for
 #endif
 
 #define CS_FAST_BLOCK   256     // threads per CTA of k_seed_fast

@@ -54,7 +54,8 @@ struct Dev {
 	BlockBuf buf[2];
 	int rc[2]; char err[2][512];
 	uint64_t n_mems[2], n_seeds[2]; cs_counters_t cnt[2];
-	double host_s[2][3];               // seconds spent submitting / waiting for kernels / waiting for copies
+	double host_s[2][3];               // seconds spent submitting / polling + enqueueing copies / idle
+	double gpu_ms[2][4];               // summed over the batches of a set: see cs_multi_result_t.gpu_ms
 	bool done[2];
 };
 
@@ -123,6 +124,7 @@ int run_block(Dev *d, const Job &j)
 	b.pub.r0 = r0; b.pub.r1 = r1; b.pub.batch_reads = m->batch_reads; b.pub.n_batches = nb; b.pub.device = d->idx->device;
 	d->n_mems[j.set] = d->n_seeds[j.set] = 0; memset(&d->cnt[j.set], 0, sizeof(cs_counters_t));
 	d->host_s[j.set][0] = d->host_s[j.set][1] = d->host_s[j.set][2] = 0;
+	for (int q = 0; q < 4; ++q) d->gpu_ms[j.set][q] = 0;
 	if (n == 0) return CS_OK;
 	if (cs_use_device(d->idx->device) != CS_OK) return CS_E_CUDA;
 	{
@@ -236,7 +238,12 @@ int run_block(Dev *d, const Job &j)
 			const auto t = now();
 			const int pr = cs_i_poll(d->ctx, (int)(copied % m->n_slots));
 			if (pr < 0) return pr;
-			if (pr == 1) { if ((rc = cs_i_fetch_wait(d->ctx, (int)(copied % m->n_slots), &d->cnt[j.set], nullptr)) != CS_OK) return rc; ++copied; progress = true; }
+			if (pr == 1) {
+				float ms4[4] = {0, 0, 0, 0};
+				if ((rc = cs_i_fetch_wait(d->ctx, (int)(copied % m->n_slots), &d->cnt[j.set], ms4)) != CS_OK) return rc;
+				for (int q = 0; q < 4; ++q) d->gpu_ms[j.set][q] += ms4[q];
+				++copied; progress = true;
+			}
 			hs[1] += since(t);
 		}
 		if (!progress) { const auto t = now(); std::this_thread::sleep_for(std::chrono::microseconds(20)); hs[2] += since(t); }
@@ -356,6 +363,7 @@ extern "C" int cs_multi_wait(cs_multi_t *m, int set, cs_multi_result_t *out)
 		out->counters.sal_queries += d->cnt[set].sal_queries; out->counters.sal_calls += d->cnt[set].sal_calls;
 		if (d->host_s[set][0] + d->host_s[set][1] + d->host_s[set][2] > out->host_s[0] + out->host_s[1] + out->host_s[2])
 			for (int q = 0; q < 3; ++q) out->host_s[q] = d->host_s[set][q];
+		for (int q = 0; q < 4; ++q) out->gpu_ms[q] = std::max(out->gpu_ms[q], d->gpu_ms[set][q]);
 	}
 	m->busy[set] = false;
 	out->n_reads = m->n_reads[set]; out->n_blocks = m->n_dev; out->blocks = m->blocks[set];
@@ -381,6 +389,12 @@ extern "C" int cs_multi_set_chaining(cs_multi_t *m, const cs_bns_view_t *bns, co
 		if (rc != CS_OK) { m->chaining = false; return rc; }
 	}
 	return CS_OK;
+}
+
+extern "C" void cs_multi_block_bounds(uint64_t n_reads, int n_dev, int k, uint64_t *r0, uint64_t *r1)
+{
+	if (n_dev < 1 || k < 0 || k >= n_dev || !r0 || !r1) { if (r0) *r0 = 0; if (r1) *r1 = 0; return; }
+	block_bounds(n_reads, n_dev, k, r0, r1);
 }
 
 extern "C" uint64_t cs_multi_launches(const cs_multi_t *m)

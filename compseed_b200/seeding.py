@@ -66,7 +66,7 @@ class _Block(C.Structure):
 
 class _MultiResult(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_mems", C.c_uint64), ("n_seeds", C.c_uint64), ("n_blocks", C.c_int),
-                ("blocks", C.POINTER(_Block)), ("counters", _Counters), ("seconds", C.c_double), ("host_s", C.c_double * 3)]
+                ("blocks", C.POINTER(_Block)), ("counters", _Counters), ("seconds", C.c_double), ("host_s", C.c_double * 3), ("gpu_ms", C.c_double * 4)]
 
 
 class _BnsView(C.Structure):
@@ -698,7 +698,8 @@ class MultiSeeder:
         info = dict(n_reads=int(r.n_reads), n_mems=int(r.n_mems), n_seeds=int(r.n_seeds), seconds=float(r.seconds),
                     blocks=[(int(r.blocks[k].device), int(r.blocks[k].r0), int(r.blocks[k].r1)) for k in range(r.n_blocks)],
                     wire_bytes=8 * int(r.n_reads) + 20 * int(r.n_mems) + 5 * int(r.n_seeds),
-                    host_s=dict(submit=float(r.host_s[0]), finish_and_enqueue=float(r.host_s[1]), idle=float(r.host_s[2])))
+                    host_s=dict(submit=float(r.host_s[0]), finish_and_enqueue=float(r.host_s[1]), idle=float(r.host_s[2])),
+                    gpu_ms=dict(before_kernels=float(r.gpu_ms[0]), seeding=float(r.gpu_ms[1]), collect_sa=float(r.gpu_ms[2]), results_to_host=float(r.gpu_ms[3])))
         if getattr(self, "_chaining", False):      # n_mems / n_seeds count chains / chain seeds then
             info["wire_bytes"] = 8 * int(r.n_reads) + 16 * int(r.n_mems) + 9 * int(r.n_seeds)
             if not gather:

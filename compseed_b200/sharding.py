@@ -1,22 +1,28 @@
-"""Multi-GPU read sharding: the index is replicated on every GPU, reads are
+"""Multi-GPU read sharding, host-side helpers around the split of cs_multi_*: the index is replicated on every GPU, reads are
 split in CONTIGUOUS blocks in input order (neighbouring reordered reads stay on one GPU), each block
 a whole multiple of the reference's reuse block (BATCH_SIZE 512, comp_seed.h:36), and results are
 concatenated on the host by block index.  There is no collective on the data path."""
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 
 REUSE_BLOCK = 512
 
 
-def shard_bounds(n_reads: int, world: int, block: int = REUSE_BLOCK) -> list[tuple[int, int]]:
-    """[start, end) of each rank's contiguous block; all but the last are multiples of `block`."""
-    n_blocks = (n_reads + block - 1) // block
+def shard_bounds(n_reads: int, world: int) -> list[tuple[int, int]]:
+    """[start, end) of each rank's contiguous block; all but the last are multiples of 512.  This IS the split the
+    library's multi-device pipeline applies (cs_multi_block_bounds, csrc/cs_multi.cu): host arithmetic inside the C-ABI."""
+    from .seeding import load_library
+    L = load_library()
+    L.cs_multi_block_bounds.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.cs_multi_block_bounds.restype = None
     out = []
     for r in range(world):
-        s = min(n_reads, (n_blocks * r // world) * block)
-        e = min(n_reads, (n_blocks * (r + 1) // world) * block)
-        out.append((s, e))
+        a, b = C.c_uint64(), C.c_uint64()
+        L.cs_multi_block_bounds(n_reads, world, r, C.byref(a), C.byref(b))
+        out.append((int(a.value), int(b.value)))
     return out
 
 

@@ -331,6 +331,9 @@ typedef struct {
 	double host_s[3];           /* where the slowest device's host thread spent that time: [0] submitting batches (offsets, enqueueing
 	                               copies and kernels), [1] polling, checking finished batches and enqueueing their result copies,
 	                               [2] idle (nothing was ready) */
+	double gpu_ms[4];           /* CUDA-event times summed over the batches of the busiest device (batches overlap, so the sum may
+	                               exceed `seconds`): [0] submit -> first kernel (input copy, and waiting for the GPU), [1] seeding kernels,
+	                               [2] collect + SA resolution (+ chaining, compaction), [3] last kernel -> results on the host */
 } cs_multi_result_t;
 
 /* where read r of the set is: its mems cm[0..n_mems) and the index s0 of its first seed position in (lo, hi) */
@@ -378,6 +381,9 @@ int cs_pack_reads_host64(uint64_t n_reads, const uint8_t *bases, const uint64_t 
 /* Flat arrays in input order from a multi result (mem_off / seed_off: n_reads+1 each; mems / rbeg may be NULL). */
 int cs_multi_gather(const cs_multi_result_t *res, uint64_t *mem_off, cs_mem_t *mems, uint64_t *seed_off, int64_t *rbeg, int n_threads);
 uint64_t cs_multi_launches(const cs_multi_t *m);
+/* The block of reads [*r0, *r1) the k-th of n_dev devices gets from a set of n_reads (what cs_multi_submit applies): contiguous,
+ * in input order, whole multiples of 512 reads (comp_seed.h:36) except the last.  Plain host arithmetic, no device involved. */
+void cs_multi_block_bounds(uint64_t n_reads, int n_dev, int k, uint64_t *r0, uint64_t *r1);
 
 /* Page-locks a caller-owned buffer (e.g. the read buffer of the batch loop).  cs_seed_batch_submit
  * then DMAs straight out of it instead of staging through the slot's pinned buffer; the caller must

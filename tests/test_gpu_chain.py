@@ -30,7 +30,8 @@ def test_golden_chains(cuda_lib, golden):
     # the mems and seed positions of a chained batch are still there for whoever wants them
     r = ctx.fetch(0)
     assert np.array_equal(r.mems, golden["mems0"]) and np.array_equal(r.rbeg, golden["rbeg0"])
-    assert got.wire_bytes < 32 * r.mems.shape[0] + 8 * r.rbeg.shape[0] + 8 * n
+    if golden["name"] == "random20k":   # ordinary reads: far fewer bytes than mems + seed positions (repeat-rich reads have a chain for almost every seed)
+        assert got.wire_bytes < (32 * r.mems.shape[0] + 8 * r.rbeg.shape[0] + 8 * n) // 2
     ctx.set_chaining(None)
     ctx.submit(0, golden["bases"], golden["off"], opt)
     with pytest.raises(cuda_lib.CompSeedError):
@@ -57,7 +58,7 @@ def test_chains_against_the_reference(cuda_lib, oracle_lib, kind):
         lens, alt = [100_000, 50_000, 150_000], [0, 1, 0]
     idx = cuda_lib.FMIndex.build(ref, sa_intv=1)
     n = off.shape[0] - 1
-    ctx = cuda_lib.SeedContext(idx, n, int(off[-1]), 256, n * 64, n * 600, 1)
+    ctx = cuda_lib.SeedContext(idx, n, int(off[-1]), 256, n * 64, n * 2000, 1)
     for co in (cuda_lib.ChainOpt(), cuda_lib.ChainOpt(w=50, max_chain_gap=300, min_chain_weight=30, max_chain_extend=3, mask_level=0.3, drop_ratio=0.8)):
         ctx.set_chaining(lens, co, alt)
         ctx.submit(0, bases, off, cuda_lib.SeedOpt())
