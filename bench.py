@@ -190,10 +190,14 @@ def e2e_only(args, cs, idx, bases, off, opt, ccfg, threads):
             infos.append(ms_.wait((i - 1) & 1, gather=False))
         infos.append(ms_.wait((args.steps - 1) & 1, gather=False))
         dt = time.perf_counter() - t0
+        tr = ms_.trace((args.steps - 1) & 1)   # timeline of the last set: ms relative to its first submit
+        tr0 = float(tr[:, 5].min()) if tr.size else 0.0
         hs = {k: float(np.mean([x["host_s"][k] for x in infos])) for k in infos[0]["host_s"]}
         hs.update({"gpu_ms_" + k: float(np.mean([x["gpu_ms"][k] for x in infos])) for k in infos[0]["gpu_ms"]})
         print(json.dumps({"e2e_reads_per_s": n_reads * args.steps / dt, "input": "packed" if packed_in else "bytes", "batch": args.e2e_batch, "slots": args.e2e_slots,
-                          "set_seconds": float(np.mean([x["seconds"] for x in infos])), "host_thread_s_per_set": hs, "wire_bytes": infos[-1]["wire_bytes"]}))
+                          "set_seconds": float(np.mean([x["seconds"] for x in infos])), "host_thread_s_per_set": hs, "wire_bytes": infos[-1]["wire_bytes"],
+                          "timeline_cols": "gpu: h2d_enqueued kernels_start kernels_end d2h_start d2h_end | host: submit kernels_seen results_seen",
+                          "timeline_ms": [[round(float(v) - tr0, 2) for v in row] for row in tr]}))
         ms_.close()
         if packed_in:
             cs.host_unregister(pk); cs.host_unregister(nm)

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cstdarg>
 #include <vector>
+#include <chrono>
 #include <thread>
 #include <algorithm>
 #include <time.h>
@@ -513,6 +514,7 @@ struct Slot {
 	cudaEvent_t ev_kend;   // last kernel of the batch done (timed twin of ev_kdone)
 	cudaEvent_t ev_fork, ev_join, ev_r3[2];   // fork / join of stream2; start and end of the third-pass kernel on it
 	cudaEvent_t ev_done;
+	cudaEvent_t ev_copy;   // result copies of the batch enqueued (cs_i_fetch_*_into): diagnostics timeline
 	cudaEvent_t ev_kdone;  // kernels and the control block copy of the batch in flight are complete
 	bool want_fetch;       // submitted through cs_seed_batch_submit: the host wants the results (see prefetch_ready)
 	// pinned host
@@ -570,6 +572,8 @@ struct cs_ctx {
 	cs_chain_opt_t copt;
 	int64_t l_pac; int32_t n_seqs; int64_t *d_c_off; uint8_t *d_c_alt;
 	uint64_t node_cap;    // B-tree nodes per slot
+	cudaEvent_t ev_base;  // recorded when the ctx was created: origin of the diagnostics timeline (cs_i_slot_times)
+	long long base_host_ns;
 	Slot *slots;
 };
 
@@ -584,6 +588,7 @@ static void slot_free(Slot *s)
 	if (s->ev_join) cudaEventDestroy(s->ev_join);
 	for (int i = 0; i < 2; ++i) if (s->ev_r3[i]) cudaEventDestroy(s->ev_r3[i]);
 	if (s->ev_done) cudaEventDestroy(s->ev_done);
+	if (s->ev_copy) cudaEventDestroy(s->ev_copy);
 	if (s->ev_kdone) cudaEventDestroy(s->ev_kdone);
 	cudaFreeHost(s->h_packed); cudaFreeHost(s->h_nmask);
 	cudaFreeHost(s->h_cmems); cudaFreeHost(s->h_rlo); cudaFreeHost(s->h_rhi);
@@ -607,6 +612,7 @@ extern "C" void cs_ctx_free(cs_ctx_t *ctx)
 	cudaSetDevice(ctx->device);
 	for (int i = 0; i < ctx->n_slots; ++i) slot_free(&ctx->slots[i]);
 	cudaFree(ctx->d_c_off); cudaFree(ctx->d_c_alt);
+	if (ctx->ev_base) cudaEventDestroy(ctx->ev_base);
 	free(ctx->slots); free(ctx);
 }
 
@@ -711,6 +717,7 @@ extern "C" cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads,
 			}
 		}
 		CK(cudaEventCreate(&s->ev_done));
+		CK(cudaEventCreate(&s->ev_copy));
 		CK(cudaEventCreateWithFlags(&s->ev_kdone, cudaEventDisableTiming));
 		CK(cudaMallocHost(&s->h_bases, max_bases));
 		CK(cudaMallocHost(&s->h_off, ((size_t)max_reads + 1) * 4));
@@ -750,6 +757,10 @@ extern "C" cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads,
 		CK(cub::DeviceScan::ExclusiveSum(nullptr, s->scan_tmp_bytes, s->d_read_n_mems, s->d_mem_off, (int)max_reads + 1, s->stream));
 		CK(cudaMalloc(&s->d_scan_tmp, s->scan_tmp_bytes + 256));
 	}
+	CK(cudaEventCreate(&ctx->ev_base));
+	CK(cudaEventRecord(ctx->ev_base, ctx->slots[0].stream));
+	CK(cudaEventSynchronize(ctx->ev_base));
+	ctx->base_host_ns = (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 	return ctx;
 fail:
 	cs_ctx_free(ctx);
@@ -952,6 +963,15 @@ static int run_status(cs_ctx *ctx, Slot *s)
 	if (h->error == CS_E_READ_OVERFLOW)
 		return set_err(CS_E_READ_OVERFLOW, "a read of this batch needs more than %u mems or %u interval-list entries: the per-read scratch follows "
 		               "max_read_len (%u); larger max_mems / max_seeds do not help", ctx->mem_cap, ctx->spill_cap + CS_LIST_SMEM, ctx->max_read_len);
+	if (s->chained && h->pool_used <= ctx->max_mems && tot_mems <= ctx->max_mems && h->tot_seeds <= ctx->max_seeds
+	    && (h->n_chains > ctx->max_mems || h->n_cseeds > ctx->max_seeds)) {
+		// the mems and seed positions fitted, the chains made of them did not (chain records share max_mems, chain seeds max_seeds)
+		ctx->need_mems[slot] = std::max<uint64_t>((uint64_t)h->n_chains + h->n_chains / 16 + 64, ctx->max_mems);
+		ctx->need_seeds[slot] = std::max<uint64_t>((uint64_t)h->n_cseeds + h->n_cseeds / 16 + 64, ctx->max_seeds);
+		return set_err(CS_E_OVERFLOW, "chain buffers too small for this batch: %u chains of %llu (max_mems), %u chain seeds of %llu (max_seeds); "
+		               "re-create the ctx with the capacities cs_ctx_need reports (%llu, %llu)", h->n_chains, (unsigned long long)ctx->max_mems,
+		               h->n_cseeds, (unsigned long long)ctx->max_seeds, (unsigned long long)ctx->need_mems[slot], (unsigned long long)ctx->need_seeds[slot]);
+	}
 	if (h->error != 0 || h->pool_used > ctx->max_mems || tot_mems > ctx->max_mems || h->tot_seeds > ctx->max_seeds) {
 		// passes 1-2 went through the pool (pool_used counts what was asked for, also past the capacity; tot12 misses the
 		// reads that did not fit); the seeds of reads whose mems did not fit in the pool are unknown: scale what is known
@@ -1201,6 +1221,7 @@ int cs_i_fetch_chains_into(cs_ctx *ctx, int slot, uint32_t *chain_off, uint32_t 
 	Slot *s = &ctx->slots[slot];
 	const uint32_t n = s->n_reads;
 	if (s->state != 3 || !s->chained) return set_err(CS_E_STATE, "slot %d has no finished chained batch", slot);
+	CK(cudaEventRecord(s->ev_copy, s->stream));
 	CK(cudaMemcpyAsync(chain_off, s->d_chain_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaMemcpyAsync(cseed_off, s->d_cseed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
 	if (s->h_ctrl->n_chains) CK(cudaMemcpyAsync(ch, s->d_chains, (size_t)s->h_ctrl->n_chains * sizeof(cs_chain_t), cudaMemcpyDeviceToHost, s->stream));
@@ -1224,6 +1245,7 @@ int cs_i_fetch_compact_into(cs_ctx *ctx, int slot, uint32_t *mem_off, uint32_t *
 	Slot *s = &ctx->slots[slot];
 	const uint32_t n = s->n_reads;
 	if (s->state != 3 || !s->d_cmems) return set_err(CS_E_STATE, "slot %d has no finished batch with compact results", slot);
+	CK(cudaEventRecord(s->ev_copy, s->stream));
 	CK(cudaMemcpyAsync(mem_off, s->d_mem_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaMemcpyAsync(seed_off, s->d_seed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
 	if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(cm, s->d_cmems, (size_t)s->h_ctrl->n_mems * sizeof(cs_cmem_t), cudaMemcpyDeviceToHost, s->stream));
@@ -1258,6 +1280,17 @@ int cs_i_fetch_wait(cs_ctx *ctx, int slot, cs_counters_t *cnt, float *slot_ms)
 	return CS_OK;
 fail:
 	return CS_E_CUDA;
+}
+
+// diagnostics timeline of the batch last fetched from the slot: ms since the ctx was created of [0] submit (input copy enqueued),
+// [1] first kernel, [2] last kernel done, [3] result copies enqueued, [4] results on the host; *base_host_ns = host clock at the origin
+int cs_i_slot_times(cs_ctx *ctx, int slot, float *t5, long long *base_host_ns)
+{
+	Slot *s = &ctx->slots[slot];
+	cudaEvent_t e[5] = { s->ev[0], s->ev[1], s->ev_kend, s->ev_copy, s->ev_done };
+	for (int k = 0; k < 5; ++k) if (cudaEventElapsedTime(t5 + k, ctx->ev_base, e[k]) != cudaSuccess) { cudaGetLastError(); t5[k] = -1.f; }
+	if (base_host_ns) *base_host_ns = ctx->base_host_ns;
+	return CS_OK;
 }
 
 // non-blocking: 1 if the kernels (state 2) / the result copies (state 4) of the slot have finished, 0 if not yet, < 0 on error
@@ -1467,7 +1500,7 @@ extern "C" int cs_ctx_set_chaining(cs_ctx_t *ctx, const cs_bns_view_t *bns, cons
 	}
 	ctx->l_pac = bns->l_pac; ctx->n_seqs = bns->n_seqs; ctx->copt = *opt;
 	// most reads need one B-tree node (up to nine chains); the rest a third of their seeds (k_chain_node_counts)
-	ctx->node_cap = (uint64_t)ctx->max_reads + ctx->max_seeds / 3 + 4096;
+	ctx->node_cap = 2 * (uint64_t)ctx->max_reads + ctx->max_seeds / 4 + 4096;   // see k_chain_node_counts
 	for (int i = 0; i < ctx->n_slots; ++i) {
 		Slot *s = &ctx->slots[i];
 		if (s->d_s_next) continue;

@@ -455,12 +455,13 @@ __global__ void k_chain_emit(ChainArgs a, const uint32_t *chain_off, const uint3
 	}
 }
 
-// node capacity of each read's B-tree region: a tree of K <= S keys with t = 5 has at most K / 4 leaves and a quarter of
-// that again in internal nodes once it has more than one node; nine keys fit in the root
+// node capacity of each read's B-tree region: nine keys fit in the root; beyond that every node but the root holds at least
+// t - 1 = 4 of the K <= S keys (splits leave exactly 4 on each side, kbtree.h:174-190), so there are at most (K - 1) / 4 + 1 nodes.
+// The sum over a batch is at most 2 * n_reads + n_seeds / 4: what cs_ctx_set_chaining allocates (node_cap).
 __global__ void k_chain_node_counts(const uint32_t *read_n_seeds, uint32_t n_reads, uint32_t *out)
 {
 	for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) {
 		const uint32_t S = read_n_seeds[r];
-		out[r] = S <= KB_MAXK ? 1u : S / 3 + 4;
+		out[r] = S <= KB_MAXK ? 1u : S / 4 + 2;
 	}
 }

@@ -33,5 +33,6 @@ int cs_i_fetch_chains_into(cs_ctx *ctx, int slot, uint32_t *chain_off, uint32_t 
 int cs_i_fetch_compact_into(cs_ctx *ctx, int slot, uint32_t *mem_off, uint32_t *seed_off, cs_cmem_t *cm, uint32_t *lo, uint8_t *hi);
 int cs_i_fetch_wait(cs_ctx *ctx, int slot, cs_counters_t *cnt, float *slot_ms);
 int cs_i_poll(cs_ctx *ctx, int slot);
+int cs_i_slot_times(cs_ctx *ctx, int slot, float *t5, long long *base_host_ns);
 void cs_i_ctx_caps(const cs_ctx *ctx, uint64_t *max_mems, uint64_t *max_seeds);
 const cs_index *cs_i_ctx_index(const cs_ctx *ctx);

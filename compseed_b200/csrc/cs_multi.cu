@@ -25,6 +25,8 @@
 #include <algorithm>
 #include "cs_internal.h"
 
+#define CS_TRACE_COLS 8
+
 namespace {
 
 struct BlockBuf { // page-locked result arrays of one (set, device)
@@ -57,6 +59,7 @@ struct Dev {
 	double host_s[2][3];               // seconds spent submitting / polling + enqueueing copies / idle
 	double gpu_ms[2][4];               // summed over the batches of a set: see cs_multi_result_t.gpu_ms
 	bool done[2];
+	std::vector<float> trace[2];       // diagnostics: CS_TRACE_COLS floats per batch of the last run of a set (cs_multi_trace)
 };
 
 } // namespace
@@ -125,6 +128,7 @@ int run_block(Dev *d, const Job &j)
 	d->n_mems[j.set] = d->n_seeds[j.set] = 0; memset(&d->cnt[j.set], 0, sizeof(cs_counters_t));
 	d->host_s[j.set][0] = d->host_s[j.set][1] = d->host_s[j.set][2] = 0;
 	for (int q = 0; q < 4; ++q) d->gpu_ms[j.set][q] = 0;
+	d->trace[j.set].assign((size_t)nb * CS_TRACE_COLS, 0.f);
 	if (n == 0) return CS_OK;
 	if (cs_use_device(d->idx->device) != CS_OK) return CS_E_CUDA;
 	{
@@ -155,8 +159,13 @@ int run_block(Dev *d, const Job &j)
 	double *hs = d->host_s[j.set];
 	auto now = [] { return std::chrono::steady_clock::now(); };
 	auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
+	long long base_ns = 0;
+	{ float t5[5]; cs_i_slot_times(d->ctx, 0, t5, &base_ns); }
+	auto host_ms = [&]() -> float { return (float)((std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() - base_ns) * 1e-6); };
+	float *tr = d->trace[j.set].data();
 	auto submit = [&](uint32_t bi) -> int {
 		const auto t = now();
+		tr[(size_t)bi * CS_TRACE_COLS + 5] = host_ms();
 		const uint64_t s = r0 + (uint64_t)bi * B, e = std::min<uint64_t>(r1, s + B);
 		const int rc_ = cs_i_submit(d->ctx, (int)(bi % m->n_slots), (uint32_t)(e - s), j.off, j.bases, j.packed, j.nmask, s, &j.opt);
 		hs[0] += since(t);
@@ -230,6 +239,7 @@ int run_block(Dev *d, const Job &j)
 					if (rc != CS_OK) return rc;
 					b.mem_base[done + 1] = mb + nm; b.seed_base[done + 1] = sb + ns;
 				}
+				tr[(size_t)done * CS_TRACE_COLS + 6] = host_ms();
 				++done; progress = true;
 			}
 			hs[1] += since(t);
@@ -242,6 +252,8 @@ int run_block(Dev *d, const Job &j)
 				float ms4[4] = {0, 0, 0, 0};
 				if ((rc = cs_i_fetch_wait(d->ctx, (int)(copied % m->n_slots), &d->cnt[j.set], ms4)) != CS_OK) return rc;
 				for (int q = 0; q < 4; ++q) d->gpu_ms[j.set][q] += ms4[q];
+				cs_i_slot_times(d->ctx, (int)(copied % m->n_slots), tr + (size_t)copied * CS_TRACE_COLS, nullptr);
+				tr[(size_t)copied * CS_TRACE_COLS + 7] = host_ms();
 				++copied; progress = true;
 			}
 			hs[1] += since(t);
@@ -395,6 +407,15 @@ extern "C" void cs_multi_block_bounds(uint64_t n_reads, int n_dev, int k, uint64
 {
 	if (n_dev < 1 || k < 0 || k >= n_dev || !r0 || !r1) { if (r0) *r0 = 0; if (r1) *r1 = 0; return; }
 	block_bounds(n_reads, n_dev, k, r0, r1);
+}
+
+extern "C" uint32_t cs_multi_trace(const cs_multi_t *m, int set, int k, float *out, uint32_t cap_batches)
+{ // diagnostics: the timeline of the batches device k ran for the last finished run of `set` (see compseed_b200.h)
+	if (!m || set < 0 || set > 1 || k < 0 || k >= m->n_dev) return 0;
+	const std::vector<float> &t = m->dev[k]->trace[set];
+	const uint32_t nb = (uint32_t)(t.size() / CS_TRACE_COLS);
+	if (out) memcpy(out, t.data(), (size_t)std::min(nb, cap_batches) * CS_TRACE_COLS * sizeof(float));
+	return nb;
 }
 
 extern "C" uint64_t cs_multi_launches(const cs_multi_t *m)

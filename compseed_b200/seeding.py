@@ -206,6 +206,8 @@ def load_library():
     L.cs_multi_set_chaining.argtypes = [C.c_void_p, C.POINTER(_BnsView), C.POINTER(_ChainOpt)]
     L.cs_multi_launches.restype = C.c_uint64
     L.cs_multi_launches.argtypes = [C.c_void_p]
+    L.cs_multi_trace.restype = C.c_uint32
+    L.cs_multi_trace.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
     L.cs_ctx_set_chaining.argtypes = [C.c_void_p, C.POINTER(_BnsView), C.POINTER(_ChainOpt)]
     L.cs_seed_batch_wait_chains.argtypes = [C.c_void_p, C.c_int, C.POINTER(_ChainResult)]
     L.cs_ctx_launches.restype = C.c_uint64
@@ -626,6 +628,15 @@ class MultiSeeder:
     @property
     def launches(self) -> int:
         return int(load_library().cs_multi_launches(self.h))
+
+    def trace(self, set_id: int, dev: int = 0) -> np.ndarray:
+        """Diagnostics timeline of the last finished run of a set on one device: [n_batches, 8] ms (cs_multi_trace)."""
+        L = load_library()
+        nb = int(L.cs_multi_trace(self.h, set_id, dev, None, 0))
+        out = np.zeros((nb, 8), dtype=np.float32)
+        if nb:
+            L.cs_multi_trace(self.h, set_id, dev, _ptr(out), nb)
+        return out
 
     def submit(self, set_id: int, bases, off64, opt: SeedOpt) -> None:
         bases = np.ascontiguousarray(bases, dtype=np.uint8)

@@ -381,6 +381,11 @@ int cs_pack_reads_host64(uint64_t n_reads, const uint8_t *bases, const uint64_t 
 /* Flat arrays in input order from a multi result (mem_off / seed_off: n_reads+1 each; mems / rbeg may be NULL). */
 int cs_multi_gather(const cs_multi_result_t *res, uint64_t *mem_off, cs_mem_t *mems, uint64_t *seed_off, int64_t *rbeg, int n_threads);
 uint64_t cs_multi_launches(const cs_multi_t *m);
+/* Diagnostics: the timeline of the batches device k ran for the last finished run of `set`, 8 floats per batch, milliseconds since the
+ * device's ctx was created: GPU clock [0] input copy enqueued, [1] first kernel starts, [2] last kernel done, [3] result copies start,
+ * [4] results on the host; host clock [5] submit call, [6] kernels seen finished (result copies enqueued), [7] results seen on the host.
+ * Returns the number of batches; at most cap_batches rows are written to out (may be NULL). */
+uint32_t cs_multi_trace(const cs_multi_t *m, int set, int k, float *out, uint32_t cap_batches);
 /* The block of reads [*r0, *r1) the k-th of n_dev devices gets from a set of n_reads (what cs_multi_submit applies): contiguous,
  * in input order, whole multiples of 512 reads (comp_seed.h:36) except the last.  Plain host arithmetic, no device involved. */
 void cs_multi_block_bounds(uint64_t n_reads, int n_dev, int k, uint64_t *r0, uint64_t *r1);

@@ -62,7 +62,19 @@ def test_chains_against_the_reference(cuda_lib, oracle_lib, kind):
     for co in (cuda_lib.ChainOpt(), cuda_lib.ChainOpt(w=50, max_chain_gap=300, min_chain_weight=30, max_chain_extend=3, mask_level=0.3, drop_ratio=0.8)):
         ctx.set_chaining(lens, co, alt)
         ctx.submit(0, bases, off, cuda_lib.SeedOpt())
-        got = ctx.wait_chains(0)
+        try:
+            got = ctx.wait_chains(0)
+        except cuda_lib.CompSeedError as e:
+            # repeat-rich reads: more chains than the mems the ctx was sized for (chain records share max_mems).  The library says
+            # what the batch needs; a caller re-creates the ctx once with that (what cs_multi_* and the shim do)
+            assert e.code == -3 and "chain buffers too small" in str(e), e
+            need_m, need_s = ctx.need(0)
+            assert need_m > n * 64 or need_s > n * 2000
+            ctx.close()
+            ctx = cuda_lib.SeedContext(idx, n, int(off[-1]), 256, need_m, need_s, 1)
+            ctx.set_chaining(lens, co, alt)
+            ctx.submit(0, bases, off, cuda_lib.SeedOpt())
+            got = ctx.wait_chains(0)
         seeds = ctx.fetch(0)
         want = oracle_lib.ref_chain(off, seeds, lens, w=co.w, max_chain_gap=co.max_chain_gap, min_chain_weight=co.min_chain_weight,
                                     max_chain_extend=co.max_chain_extend, mask_level=co.mask_level, drop_ratio=co.drop_ratio, is_alt=alt)
