@@ -25,6 +25,9 @@ from types import SimpleNamespace
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# one hardware queue per stream of the slot pipeline (the default of 8 makes slots wait for each other; see cs_api.cu); must be set
+# before the CUDA context exists, i.e. before torch touches the device
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, ROOT)
 
 

@@ -15,6 +15,14 @@
 
 #include "cs_internal.h"
 
+// Hardware work queues.  A CUDA context maps its streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8), round robin;
+// two streams that share a queue run one after the other.  Measured on the B200 box (scripts/micro/copy_overlap.cu): of 14 streams
+// with one kernel each, streams 8..13 start when streams 0..5 end -- and in the slot pipeline the input copy of one slot waited for
+// the kernels or the result copy of another (profiles/r02_pipeline_timeline.md).  The variable is read when the context is created,
+// so it is set when the library is loaded, unless the host has set it already; a host that creates its CUDA context before loading
+// this library sets it itself.
+namespace { struct QueueEnv { QueueEnv() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_queue_env; }
+
 static thread_local char g_err[512] = "";
 static thread_local int g_err_code = 0;
 
@@ -508,6 +516,11 @@ struct Ctrl { // zeroed before every run; copied back after it
 
 struct Slot {
 	cudaStream_t stream;
+	// Result copies (and the control block) go through a stream of their own.  Measured (scripts/micro/pipe_mimic.cu,
+	// profiles/r02_pipeline_timeline.md): a stream whose first copy was host-to-device keeps ALL its copies on that copy engine, so
+	// with one stream per slot every input and result copy of every slot queued up on one engine, in order of submission: the input
+	// copy of a resubmitted slot waited for the result copies of all other slots, and no kernel ran meanwhile.
+	cudaStream_t stream_out;
 	cudaStream_t stream2;  // the third-pass kernel runs here, next to k_seed_walk / k_seed (it depends on k_seed_fast only)
 	cudaEvent_t ev[8];   // slot start, seed start, seed end, collect end, sa end, k_seed end, k_seed_fast end, k_seed_walk end
 	cudaEvent_t ev_pack;   // k_pack_reads done
@@ -581,6 +594,7 @@ static void slot_free(Slot *s)
 {
 	if (s->stream) cudaStreamDestroy(s->stream);
 	if (s->stream2) cudaStreamDestroy(s->stream2);
+	if (s->stream_out) cudaStreamDestroy(s->stream_out);
 	for (int i = 0; i < 8; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
 	if (s->ev_pack) cudaEventDestroy(s->ev_pack);
 	if (s->ev_kend) cudaEventDestroy(s->ev_kend);
@@ -688,7 +702,8 @@ extern "C" cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads,
 		Slot *s = &ctx->slots[i];
 		const size_t nthreads = std::max((size_t)ctx->grid * CS_SEED_BLOCK, (size_t)ctx->grid_fast * CS_FAST_BLOCK);
 		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-		CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&s->stream_out, cudaStreamNonBlocking));
+		if (ctx->cfg.overlap_streams > 0) CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));   // (streams share the device's hardware queues: none is created idle)
 		for (int e = 0; e < 8; ++e) CK(cudaEventCreate(&s->ev[e]));
 		CK(cudaEventCreate(&s->ev_pack));
 		CK(cudaEventCreate(&s->ev_kend));
@@ -713,7 +728,7 @@ extern "C" cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads,
 				av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
 				av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
 				CK(cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av));
-				CK(cudaStreamSetAttribute(s->stream2, cudaStreamAttributeAccessPolicyWindow, &av));
+				if (s->stream2) CK(cudaStreamSetAttribute(s->stream2, cudaStreamAttributeAccessPolicyWindow, &av));
 			}
 		}
 		CK(cudaEventCreate(&s->ev_done));
@@ -946,8 +961,9 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 		CK(cudaGetLastError()); ++ctx->n_launch;
 	}
 	CK(cudaEventRecord(s->ev_kend, s->stream));
-	CK(cudaMemcpyAsync(s->h_ctrl, s->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
-	CK(cudaEventRecord(s->ev_kdone, s->stream));
+	CK(cudaStreamWaitEvent(s->stream_out, s->ev_kend, 0));   // everything that goes to the host goes through the slot's output stream
+	CK(cudaMemcpyAsync(s->h_ctrl, s->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream_out));
+	CK(cudaEventRecord(s->ev_kdone, s->stream_out));
 	s->state = 2;
 	return CS_OK;
 fail:
@@ -990,11 +1006,11 @@ static int run_status(cs_ctx *ctx, Slot *s)
 // wait for the device side of a run and check its status
 static int finish_run(cs_ctx *ctx, Slot *s)
 {
-	CK(cudaStreamSynchronize(s->stream));
+	CK(cudaStreamSynchronize(s->stream_out));   // (waits for the kernels on s->stream through ev_kend)
 	if (s->used_fast && s->h_ctrl->n_defer > ctx->defer_cap) { // more hard calls than the queue holds (repeat-rich batch): literal kernel alone
 		cs_seed_opt_t o = s->opt;
 		if (enqueue_run(ctx, s, &o, false) != CS_OK) return CS_E_CUDA;
-		CK(cudaStreamSynchronize(s->stream));
+		CK(cudaStreamSynchronize(s->stream_out));
 	}
 	s->state = 3;
 	return run_status(ctx, s);
@@ -1221,18 +1237,18 @@ int cs_i_fetch_chains_into(cs_ctx *ctx, int slot, uint32_t *chain_off, uint32_t 
 	Slot *s = &ctx->slots[slot];
 	const uint32_t n = s->n_reads;
 	if (s->state != 3 || !s->chained) return set_err(CS_E_STATE, "slot %d has no finished chained batch", slot);
-	CK(cudaEventRecord(s->ev_copy, s->stream));
-	CK(cudaMemcpyAsync(chain_off, s->d_chain_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
-	CK(cudaMemcpyAsync(cseed_off, s->d_cseed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
-	if (s->h_ctrl->n_chains) CK(cudaMemcpyAsync(ch, s->d_chains, (size_t)s->h_ctrl->n_chains * sizeof(cs_chain_t), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaEventRecord(s->ev_copy, s->stream_out));
+	CK(cudaMemcpyAsync(chain_off, s->d_chain_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream_out));
+	CK(cudaMemcpyAsync(cseed_off, s->d_cseed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream_out));
+	if (s->h_ctrl->n_chains) CK(cudaMemcpyAsync(ch, s->d_chains, (size_t)s->h_ctrl->n_chains * sizeof(cs_chain_t), cudaMemcpyDeviceToHost, s->stream_out));
 	if (s->h_ctrl->n_cseeds) {
 		const size_t k = s->h_ctrl->n_cseeds;
-		CK(cudaMemcpyAsync(lo, s->d_cs_lo, k * 4, cudaMemcpyDeviceToHost, s->stream));
-		CK(cudaMemcpyAsync(hi, s->d_cs_hi, k, cudaMemcpyDeviceToHost, s->stream));
-		CK(cudaMemcpyAsync(qb, s->d_cs_qbeg, k * 2, cudaMemcpyDeviceToHost, s->stream));
-		CK(cudaMemcpyAsync(ln, s->d_cs_len, k * 2, cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaMemcpyAsync(lo, s->d_cs_lo, k * 4, cudaMemcpyDeviceToHost, s->stream_out));
+		CK(cudaMemcpyAsync(hi, s->d_cs_hi, k, cudaMemcpyDeviceToHost, s->stream_out));
+		CK(cudaMemcpyAsync(qb, s->d_cs_qbeg, k * 2, cudaMemcpyDeviceToHost, s->stream_out));
+		CK(cudaMemcpyAsync(ln, s->d_cs_len, k * 2, cudaMemcpyDeviceToHost, s->stream_out));
 	}
-	CK(cudaEventRecord(s->ev_done, s->stream));
+	CK(cudaEventRecord(s->ev_done, s->stream_out));
 	s->state = 4;
 	return CS_OK;
 fail:
@@ -1245,15 +1261,15 @@ int cs_i_fetch_compact_into(cs_ctx *ctx, int slot, uint32_t *mem_off, uint32_t *
 	Slot *s = &ctx->slots[slot];
 	const uint32_t n = s->n_reads;
 	if (s->state != 3 || !s->d_cmems) return set_err(CS_E_STATE, "slot %d has no finished batch with compact results", slot);
-	CK(cudaEventRecord(s->ev_copy, s->stream));
-	CK(cudaMemcpyAsync(mem_off, s->d_mem_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
-	CK(cudaMemcpyAsync(seed_off, s->d_seed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
-	if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(cm, s->d_cmems, (size_t)s->h_ctrl->n_mems * sizeof(cs_cmem_t), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaEventRecord(s->ev_copy, s->stream_out));
+	CK(cudaMemcpyAsync(mem_off, s->d_mem_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream_out));
+	CK(cudaMemcpyAsync(seed_off, s->d_seed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream_out));
+	if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(cm, s->d_cmems, (size_t)s->h_ctrl->n_mems * sizeof(cs_cmem_t), cudaMemcpyDeviceToHost, s->stream_out));
 	if (s->h_ctrl->n_seeds) {
-		CK(cudaMemcpyAsync(lo, s->d_rlo, (size_t)s->h_ctrl->n_seeds * 4, cudaMemcpyDeviceToHost, s->stream));
-		CK(cudaMemcpyAsync(hi, s->d_rhi, (size_t)s->h_ctrl->n_seeds, cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaMemcpyAsync(lo, s->d_rlo, (size_t)s->h_ctrl->n_seeds * 4, cudaMemcpyDeviceToHost, s->stream_out));
+		CK(cudaMemcpyAsync(hi, s->d_rhi, (size_t)s->h_ctrl->n_seeds, cudaMemcpyDeviceToHost, s->stream_out));
 	}
-	CK(cudaEventRecord(s->ev_done, s->stream));
+	CK(cudaEventRecord(s->ev_done, s->stream_out));
 	s->state = 4;
 	return CS_OK;
 fail:
@@ -1351,7 +1367,7 @@ extern "C" int cs_seed_batch_wait_device(cs_ctx_t *ctx, int slot, cs_result_t *o
 	if (s->state != 2) return set_err(CS_E_STATE, "slot %d has no batch in flight", slot);
 	{ const int rc_ = use_device(ctx->idx->device); if (rc_ != CS_OK) return rc_; }
 	rc = finish_run(ctx, s);
-	cudaEventRecord(s->ev_done, s->stream);
+	cudaEventRecord(s->ev_done, s->stream_out);
 	cudaEventSynchronize(s->ev_done);
 	if (rc != CS_OK) { s->state = 1; return rc; }
 	fill_result(ctx, s, out, false);
@@ -1374,20 +1390,20 @@ static int fetch(cs_ctx *ctx, Slot *s, bool compact = false)
 		CK(cudaMallocHost(&s->h_rlo, ctx->max_seeds * 4));
 		CK(cudaMallocHost(&s->h_rhi, ctx->max_seeds));
 	}
-	CK(cudaMemcpyAsync(s->h_mem_off, s->d_mem_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
-	CK(cudaMemcpyAsync(s->h_seed_off, s->d_seed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaMemcpyAsync(s->h_mem_off, s->d_mem_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream_out));
+	CK(cudaMemcpyAsync(s->h_seed_off, s->d_seed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream_out));
 	if (!compact) {
-		if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(s->h_mems, s->d_mems, (size_t)s->h_ctrl->n_mems * sizeof(cs_mem_t), cudaMemcpyDeviceToHost, s->stream));
-		if (s->h_ctrl->n_seeds) CK(cudaMemcpyAsync(s->h_rbeg, s->d_rows, (size_t)s->h_ctrl->n_seeds * 8, cudaMemcpyDeviceToHost, s->stream));
+		if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(s->h_mems, s->d_mems, (size_t)s->h_ctrl->n_mems * sizeof(cs_mem_t), cudaMemcpyDeviceToHost, s->stream_out));
+		if (s->h_ctrl->n_seeds) CK(cudaMemcpyAsync(s->h_rbeg, s->d_rows, (size_t)s->h_ctrl->n_seeds * 8, cudaMemcpyDeviceToHost, s->stream_out));
 	} else {
-		if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(s->h_cmems, s->d_cmems, (size_t)s->h_ctrl->n_mems * sizeof(cs_cmem_t), cudaMemcpyDeviceToHost, s->stream));
+		if (s->h_ctrl->n_mems) CK(cudaMemcpyAsync(s->h_cmems, s->d_cmems, (size_t)s->h_ctrl->n_mems * sizeof(cs_cmem_t), cudaMemcpyDeviceToHost, s->stream_out));
 		if (s->h_ctrl->n_seeds) {
-			CK(cudaMemcpyAsync(s->h_rlo, s->d_rlo, (size_t)s->h_ctrl->n_seeds * 4, cudaMemcpyDeviceToHost, s->stream));
-			CK(cudaMemcpyAsync(s->h_rhi, s->d_rhi, (size_t)s->h_ctrl->n_seeds, cudaMemcpyDeviceToHost, s->stream));
+			CK(cudaMemcpyAsync(s->h_rlo, s->d_rlo, (size_t)s->h_ctrl->n_seeds * 4, cudaMemcpyDeviceToHost, s->stream_out));
+			CK(cudaMemcpyAsync(s->h_rhi, s->d_rhi, (size_t)s->h_ctrl->n_seeds, cudaMemcpyDeviceToHost, s->stream_out));
 		}
 	}
 	s->fetched_compact = compact;
-	CK(cudaEventRecord(s->ev_done, s->stream));
+	CK(cudaEventRecord(s->ev_done, s->stream_out));
 	return CS_OK;
 fail:
 	return CS_E_CUDA;
@@ -1542,16 +1558,16 @@ extern "C" int cs_seed_batch_wait_chains(cs_ctx_t *ctx, int slot, cs_chain_resul
 			CK(cudaMallocHost(&s->h_cs_lo, ctx->max_seeds * 4)); CK(cudaMallocHost(&s->h_cs_hi, ctx->max_seeds));
 			CK(cudaMallocHost(&s->h_cs_qbeg, ctx->max_seeds * 2)); CK(cudaMallocHost(&s->h_cs_len, ctx->max_seeds * 2));
 		}
-		CK(cudaMemcpyAsync(s->h_chain_off, s->d_chain_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
-		CK(cudaMemcpyAsync(s->h_cseed_off, s->d_cseed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
-		if (h->n_chains) CK(cudaMemcpyAsync(s->h_chains, s->d_chains, (size_t)h->n_chains * sizeof(cs_chain_t), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaMemcpyAsync(s->h_chain_off, s->d_chain_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream_out));
+		CK(cudaMemcpyAsync(s->h_cseed_off, s->d_cseed_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s->stream_out));
+		if (h->n_chains) CK(cudaMemcpyAsync(s->h_chains, s->d_chains, (size_t)h->n_chains * sizeof(cs_chain_t), cudaMemcpyDeviceToHost, s->stream_out));
 		if (h->n_cseeds) {
-			CK(cudaMemcpyAsync(s->h_cs_lo, s->d_cs_lo, (size_t)h->n_cseeds * 4, cudaMemcpyDeviceToHost, s->stream));
-			CK(cudaMemcpyAsync(s->h_cs_hi, s->d_cs_hi, (size_t)h->n_cseeds, cudaMemcpyDeviceToHost, s->stream));
-			CK(cudaMemcpyAsync(s->h_cs_qbeg, s->d_cs_qbeg, (size_t)h->n_cseeds * 2, cudaMemcpyDeviceToHost, s->stream));
-			CK(cudaMemcpyAsync(s->h_cs_len, s->d_cs_len, (size_t)h->n_cseeds * 2, cudaMemcpyDeviceToHost, s->stream));
+			CK(cudaMemcpyAsync(s->h_cs_lo, s->d_cs_lo, (size_t)h->n_cseeds * 4, cudaMemcpyDeviceToHost, s->stream_out));
+			CK(cudaMemcpyAsync(s->h_cs_hi, s->d_cs_hi, (size_t)h->n_cseeds, cudaMemcpyDeviceToHost, s->stream_out));
+			CK(cudaMemcpyAsync(s->h_cs_qbeg, s->d_cs_qbeg, (size_t)h->n_cseeds * 2, cudaMemcpyDeviceToHost, s->stream_out));
+			CK(cudaMemcpyAsync(s->h_cs_len, s->d_cs_len, (size_t)h->n_cseeds * 2, cudaMemcpyDeviceToHost, s->stream_out));
 		}
-		CK(cudaEventRecord(s->ev_done, s->stream));
+		CK(cudaEventRecord(s->ev_done, s->stream_out));
 		CK(cudaEventSynchronize(s->ev_done));
 		s->state = 3;
 		memset(out, 0, sizeof *out);
