@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--e2e-only", action="store_true", help="experiments: only the host-buffer leg (prints its dict, not a bench line)")
     ap.add_argument("--isa-intv", type=int, default=-1, help="cs_index_config_t.isa_intv (sampling of the inverse SA; -1 = default 2)")
     ap.add_argument("--lit-ctas", type=int, default=-1, help="cs_ctx_config_t.lit_ctas_per_sm")
+    ap.add_argument("--batch-order", type=int, default=-1, help="cs_ctx_config_t.batch_order")
     return ap.parse_args()
 
 
@@ -293,7 +294,7 @@ def main():
                  "what": "independent uniformly random 32-byte sector loads, 1184 CTAs x 256 threads, measured in this run before the timed region: over this "
                          "index's own arrays (cs_probe_index_gather, each load picks an array in proportion to its size) and over one 16 GiB table "
                          "(cs_probe_random_gather); the roofline peak is the best of the four"}
-    ccfg = cs.CtxConfig(l2_persist_mb=args.l2_persist_mb, overlap_streams=1 if args.overlap else 0, lit_ctas_per_sm=args.lit_ctas)
+    ccfg = cs.CtxConfig(l2_persist_mb=args.l2_persist_mb, overlap_streams=1 if args.overlap else 0, lit_ctas_per_sm=args.lit_ctas, batch_order=args.batch_order)
 
     if args.e2e_only:
         return e2e_only(args, cs, idx, bases, off, opt, ccfg, threads)

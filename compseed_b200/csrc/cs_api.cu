@@ -71,7 +71,7 @@ extern "C" void cs_ctx_config_default(cs_ctx_config_t *cfg)
 {
 	if (!cfg) return;
 	cfg->use_fast = -1; cfg->use_r3_fast = -1; cfg->defer_cap = -1; cfg->lit_ctas_per_sm = -1;
-	cfg->prefetch_results = 0; cfg->l2_persist_mb = 0; cfg->overlap_streams = 0; cfg->compact_results = 0;
+	cfg->prefetch_results = 0; cfg->l2_persist_mb = 0; cfg->overlap_streams = 0; cfg->compact_results = 0; cfg->batch_order = -1;
 }
 
 static uint64_t kt_offset_host(uint32_t d) { return ((1ull << (2 * d)) - 4) / 3; }   // entries of depths 1 .. d-1 (kt_offset, cs_device.cuh)
@@ -585,6 +585,7 @@ struct cs_ctx {
 	cs_chain_opt_t copt;
 	int64_t l_pac; int32_t n_seqs; int64_t *d_c_off; uint8_t *d_c_alt;
 	uint64_t node_cap;    // B-tree nodes per slot
+	cudaEvent_t ev_prev_kend;   // ev_kend of the batch enqueued last (cfg.batch_order): the next batch's kernels wait for it
 	cudaEvent_t ev_base;  // recorded when the ctx was created: origin of the diagnostics timeline (cs_i_slot_times)
 	long long base_host_ns;
 	Slot *slots;
@@ -843,6 +844,8 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 		}
 	}
 	CK(cudaMemsetAsync(s->d_ctrl, 0, sizeof(Ctrl), s->stream));
+	if (ctx->cfg.batch_order != 0 && ctx->ev_prev_kend && ctx->ev_prev_kend != s->ev_kend)   // (input copies above are not held back)
+		CK(cudaStreamWaitEvent(s->stream, ctx->ev_prev_kend, 0));
 	CK(cudaEventRecord(s->ev[1], s->stream));
 	if (!s->packed_input) {
 		k_pack_reads<<<(int)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)idx->n_sm * 16), 256, 0, s->stream>>>(
@@ -961,6 +964,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 		CK(cudaGetLastError()); ++ctx->n_launch;
 	}
 	CK(cudaEventRecord(s->ev_kend, s->stream));
+	ctx->ev_prev_kend = s->ev_kend;
 	CK(cudaStreamWaitEvent(s->stream_out, s->ev_kend, 0));   // everything that goes to the host goes through the slot's output stream
 	CK(cudaMemcpyAsync(s->h_ctrl, s->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream_out));
 	CK(cudaEventRecord(s->ev_kdone, s->stream_out));

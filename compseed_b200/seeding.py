@@ -120,7 +120,7 @@ class _IndexConfig(C.Structure):
 
 class _CtxConfig(C.Structure):
     _fields_ = [("use_fast", C.c_int32), ("use_r3_fast", C.c_int32), ("defer_cap", C.c_int32), ("lit_ctas_per_sm", C.c_int32),
-                ("prefetch_results", C.c_int32), ("l2_persist_mb", C.c_int32), ("overlap_streams", C.c_int32), ("compact_results", C.c_int32)]
+                ("prefetch_results", C.c_int32), ("l2_persist_mb", C.c_int32), ("overlap_streams", C.c_int32), ("compact_results", C.c_int32), ("batch_order", C.c_int32)]
 
 
 class _CompactResult(C.Structure):
@@ -152,10 +152,11 @@ class CtxConfig:
     l2_persist_mb: int = 0
     overlap_streams: int = 0
     compact_results: int = 0
+    batch_order: int = -1
 
     def _c(self) -> _CtxConfig:
         return _CtxConfig(self.use_fast, self.use_r3_fast, self.defer_cap, self.lit_ctas_per_sm, self.prefetch_results,
-                          self.l2_persist_mb, self.overlap_streams, self.compact_results)
+                          self.l2_persist_mb, self.overlap_streams, self.compact_results, self.batch_order)
 
 
 _lib = None

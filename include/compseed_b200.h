@@ -167,6 +167,11 @@ typedef struct {
 	                              does not depend.  Default 0: measured neutral on one B200 (every kernel of the batch fills the GPU: what
 	                              the third pass gains, k_seed loses; profiles/r02_variants.json), and serial kernels time cleanly */
 	int32_t compact_results;   /* 1: the batches also produce the compact wire format (cs_seed_batch_wait_compact); default 0 */
+	int32_t batch_order;       /* how the kernels of batches submitted to different slots of the ctx share the GPU.  1 (default -1 = 1): the
+	                              first kernel of a batch waits for the last kernel of the batch submitted before it, so batches finish one
+	                              after the other and the result copy of one overlaps the kernels of the next.  0: no ordering -- every
+	                              kernel fills the GPU, so the batches in flight take turns kernel by kernel, all finish together, their
+	                              result copies queue up and the GPU idles meanwhile (profiles/r02_pipeline_timeline.md) */
 } cs_ctx_config_t;
 void cs_ctx_config_default(cs_ctx_config_t *cfg);
 

@@ -112,8 +112,8 @@ def test_config_defaults_and_error_codes():
     L.cs_index_config_default(C.byref(ic)); L.cs_ctx_config_default(C.byref(cc))
     assert (ic.kmer_table_depth, ic.prune_k, ic.isa_intv) == (-1, -1, -1)
     d = cs.CtxConfig()
-    assert (cc.use_fast, cc.use_r3_fast, cc.defer_cap, cc.lit_ctas_per_sm, cc.prefetch_results, cc.l2_persist_mb, cc.overlap_streams) == \
-           (d.use_fast, d.use_r3_fast, d.defer_cap, d.lit_ctas_per_sm, d.prefetch_results, d.l2_persist_mb, d.overlap_streams)
+    assert (cc.use_fast, cc.use_r3_fast, cc.defer_cap, cc.lit_ctas_per_sm, cc.prefetch_results, cc.l2_persist_mb, cc.overlap_streams, cc.compact_results, cc.batch_order) == \
+           (d.use_fast, d.use_r3_fast, d.defer_cap, d.lit_ctas_per_sm, d.prefetch_results, d.l2_persist_mb, d.overlap_streams, d.compact_results, d.batch_order)
     hdr = open(os.path.join(ROOT, "include", "compseed_b200.h")).read()
     codes = dict(re.findall(r"#define (CS_E_[A-Z_]+)\s+(-\d+)", hdr))
     assert int(codes["CS_E_OVERFLOW"]) == S.CS_E_OVERFLOW and int(codes["CS_E_READ_OVERFLOW"]) == S.CS_E_READ_OVERFLOW
