@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--sa-intv", type=int, default=1, help="device SA sampling (1 = dense; 32 = the reference's on-disk sampling)")
-    ap.add_argument("--e2e-batch", type=int, default=1 << 20, help="reads per pipelined batch on the host-buffer path")
+    ap.add_argument("--e2e-batch", type=int, default=1 << 21, help="reads per pipelined batch on the host-buffer path")
     ap.add_argument("--e2e-slots", type=int, default=3, help="pipelined batches in flight on the host-buffer path")
     ap.add_argument("--cpu-sample", type=int, default=300_000, help="reads of the same workload timed on the host cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -113,18 +113,31 @@ int make_ctx(Dev *d)
 	return CS_OK;
 }
 
-// one read set on one device: reads [r0, r1) in batches through the slots
-int run_block(Dev *d, const Job &j)
+// One read set on one device: reads [r0, r1) in batches through the slots.  A Run is a set being pipelined; the worker keeps up to
+// two of them going at once, so that the first batches of set i+1 are copied in and seeded while the last batches of set i are on
+// their way out (otherwise the pipeline drains between sets: ~13 ms of 83 per 10 M-read set on the B200 box).
+struct Run {
+	Job j;
+	BlockBuf *b;
+	uint64_t r0 = 0, r1 = 0, n = 0; uint32_t nb = 0;
+	uint32_t next = 0, done = 0, copied = 0;   // batches submitted / kernels finished and result copy enqueued / results on the host
+	int rc = CS_OK;
+};
+struct Flight { Run *run; uint32_t bi; int slot; };
+
+int run_prepare(Dev *d, Run *r)
 {
 	cs_multi *m = d->m;
+	const Job &j = r->j;
 	BlockBuf &b = d->buf[j.set];
-	uint64_t r0, r1;
-	block_bounds(j.n_reads, m->n_dev, d->k, &r0, &r1);
-	const uint64_t n = r1 - r0, B = m->batch_reads;
+	r->b = &b;
+	block_bounds(j.n_reads, m->n_dev, d->k, &r->r0, &r->r1);
+	const uint64_t n = r->r1 - r->r0, B = m->batch_reads;
 	const uint32_t nb = (uint32_t)((n + B - 1) / B);
+	r->n = n; r->nb = nb;
 	int rc;
 	memset(&b.pub, 0, sizeof b.pub);
-	b.pub.r0 = r0; b.pub.r1 = r1; b.pub.batch_reads = m->batch_reads; b.pub.n_batches = nb; b.pub.device = d->idx->device;
+	b.pub.r0 = r->r0; b.pub.r1 = r->r1; b.pub.batch_reads = m->batch_reads; b.pub.n_batches = nb; b.pub.device = d->idx->device;
 	d->n_mems[j.set] = d->n_seeds[j.set] = 0; memset(&d->cnt[j.set], 0, sizeof(cs_counters_t));
 	d->host_s[j.set][0] = d->host_s[j.set][1] = d->host_s[j.set][2] = 0;
 	for (int q = 0; q < 4; ++q) d->gpu_ms[j.set][q] = 0;
@@ -147,144 +160,200 @@ int run_block(Dev *d, const Job &j)
 			p = b.sq; if ((rc = pinned_grow(&p, &cq, n * m->seeds_per_read, 2, 0)) != CS_OK) return rc; b.sq = (uint16_t*)p;
 			cq = b.cap_sq; p = b.sl; if ((rc = pinned_grow(&p, &cq, n * m->seeds_per_read, 2, 0)) != CS_OK) return rc; b.sl = (uint16_t*)p; b.cap_sq = cq;
 		} else {
-		p = b.cmems; if ((rc = pinned_grow(&p, &cm, n * m->mems_per_read, sizeof(cs_cmem_t), 0)) != CS_OK) return rc; b.cmems = (cs_cmem_t*)p; b.cap_mems = cm;
+			p = b.cmems; if ((rc = pinned_grow(&p, &cm, n * m->mems_per_read, sizeof(cs_cmem_t), 0)) != CS_OK) return rc; b.cmems = (cs_cmem_t*)p; b.cap_mems = cm;
 		}
 		p = b.rlo; if ((rc = pinned_grow(&p, &cs, n * m->seeds_per_read, 4, 0)) != CS_OK) return rc; b.rlo = (uint32_t*)p;
 		cs = b.cap_seeds; p = b.rhi; if ((rc = pinned_grow(&p, &cs, n * m->seeds_per_read, 1, 0)) != CS_OK) return rc; b.rhi = (uint8_t*)p;
 		b.cap_seeds = cs;
 	}
 	b.mem_base[0] = b.seed_base[0] = 0;
-	uint32_t next = 0, done = 0;       // batches submitted / completed (kernels finished and result copy enqueued)
-	uint32_t copied = 0;               // batches whose result copy has been waited for
-	double *hs = d->host_s[j.set];
-	auto now = [] { return std::chrono::steady_clock::now(); };
-	auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
-	long long base_ns = 0;
-	{ float t5[5]; cs_i_slot_times(d->ctx, 0, t5, &base_ns); }
-	auto host_ms = [&]() -> float { return (float)((std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() - base_ns) * 1e-6); };
-	float *tr = d->trace[j.set].data();
-	auto submit = [&](uint32_t bi) -> int {
-		const auto t = now();
-		tr[(size_t)bi * CS_TRACE_COLS + 5] = host_ms();
-		const uint64_t s = r0 + (uint64_t)bi * B, e = std::min<uint64_t>(r1, s + B);
-		const int rc_ = cs_i_submit(d->ctx, (int)(bi % m->n_slots), (uint32_t)(e - s), j.off, j.bases, j.packed, j.nmask, s, &j.opt);
-		hs[0] += since(t);
-		return rc_;
-	};
-	auto wait_copy = [&](uint32_t bi) -> int { // blocking (only on the rare paths that must drain the slots)
-		const auto t = now();
-		const int rc_ = cs_i_fetch_wait(d->ctx, (int)(bi % m->n_slots), &d->cnt[j.set], nullptr);
-		hs[2] += since(t);
-		return rc_;
-	};
-	// Event-driven: the thread never blocks on one thing while another is ready.  Whenever the kernels of the oldest
-	// unfinished batch are done, its result copy is enqueued at once (the copy engine must not wait for the host);
-	// whenever the oldest copy has landed, its slot is free for the next batch; otherwise the thread naps for 20 us.
-	while (copied < nb) {
-		bool progress = false;
-		while (next < nb && next - copied < (uint32_t)m->n_slots) { // a slot is free once its previous batch's copy has landed
-			if ((rc = submit(next)) != CS_OK) return rc;
-			++next; progress = true;
-		}
-		if (done < next) {
-			const auto t = now();
-			const int pr = cs_i_poll(d->ctx, (int)(done % m->n_slots));
-			if (pr < 0) return pr;
-			if (pr == 1) {
-				uint64_t nm = 0, ns = 0;
-				rc = cs_i_finish(d->ctx, (int)(done % m->n_slots), &nm, &ns);
-				if (rc == CS_E_OVERFLOW) { // this batch needs larger slot buffers: drain, re-create the ctx once with what it needs, resubmit from here
-					uint64_t need_m = 0, need_s = 0;
-					cs_ctx_need(d->ctx, (int)(done % m->n_slots), &need_m, &need_s);
-					for (; copied < done; ++copied) if ((rc = wait_copy(copied)) != CS_OK) return rc;
-					if (need_m >= (1ull << 32) || need_s >= (1ull << 32)) return cs_set_err(CS_E_OVERFLOW, "a batch of %u reads needs more than 2^32 mems or seeds: use smaller batches", m->batch_reads);
-					if (need_m <= d->cap_mems && need_s <= d->cap_seeds) { need_m = d->cap_mems * 2; need_s = d->cap_seeds * 2; }   // (chain buffers: no exact figure)
-					d->cap_mems = std::max(d->cap_mems, need_m); d->cap_seeds = std::max(d->cap_seeds, need_s);
-					if ((rc = make_ctx(d)) != CS_OK) return rc;   // (frees the old ctx: its in-flight batches are dropped with it)
-					next = done;
-					continue;
-				}
-				if (rc != CS_OK) return rc;
-				{ // room for this batch in the block arrays (rare: the estimate per read was too low)
-					const uint64_t mb = b.mem_base[done], sb = b.seed_base[done];
-					const uint64_t cap1 = m->chaining ? b.cap_chains : b.cap_mems, cap2 = m->chaining ? std::min(b.cap_seeds, b.cap_sq) : b.cap_seeds;
-					if (mb + nm > cap1 || sb + ns > cap2) {
-						for (; copied < done; ++copied) if ((rc = wait_copy(copied)) != CS_OK) return rc;   // copies into the old arrays must have landed
-						void *p; uint64_t c;
-						if (m->chaining) {
-							p = b.chains; c = b.cap_chains;
-							if ((rc = pinned_grow(&p, &c, mb + nm, sizeof(cs_chain_t), mb)) != CS_OK) return rc;
-							b.chains = (cs_chain_t*)p; b.cap_chains = c;
-							p = b.sq; c = b.cap_sq;
-							if ((rc = pinned_grow(&p, &c, sb + ns, 2, sb)) != CS_OK) return rc;
-							b.sq = (uint16_t*)p;
-							p = b.sl; c = b.cap_sq;
-							if ((rc = pinned_grow(&p, &c, sb + ns, 2, sb)) != CS_OK) return rc;
-							b.sl = (uint16_t*)p; b.cap_sq = c;
-						} else {
-							p = b.cmems; c = b.cap_mems;
-							if ((rc = pinned_grow(&p, &c, mb + nm, sizeof(cs_cmem_t), mb)) != CS_OK) return rc;
-							b.cmems = (cs_cmem_t*)p; b.cap_mems = c;
-						}
-						p = b.rlo; c = b.cap_seeds;
-						if ((rc = pinned_grow(&p, &c, sb + ns, 4, sb)) != CS_OK) return rc;
-						b.rlo = (uint32_t*)p;
-						p = b.rhi; c = b.cap_seeds;
-						if ((rc = pinned_grow(&p, &c, sb + ns, 1, sb)) != CS_OK) return rc;
-						b.rhi = (uint8_t*)p; b.cap_seeds = c;
-					}
-					uint32_t *o1 = b.mem_off + (uint64_t)done * (B + 1), *o2 = b.seed_off + (uint64_t)done * (B + 1);
-					if (m->chaining) rc = cs_i_fetch_chains_into(d->ctx, (int)(done % m->n_slots), o1, o2, b.chains + mb, b.rlo + sb, b.rhi + sb, b.sq + sb, b.sl + sb);
-					else rc = cs_i_fetch_compact_into(d->ctx, (int)(done % m->n_slots), o1, o2, b.cmems + mb, b.rlo + sb, b.rhi + sb);
-					if (rc != CS_OK) return rc;
-					b.mem_base[done + 1] = mb + nm; b.seed_base[done + 1] = sb + ns;
-				}
-				tr[(size_t)done * CS_TRACE_COLS + 6] = host_ms();
-				++done; progress = true;
-			}
-			hs[1] += since(t);
-		}
-		if (copied < done) {
-			const auto t = now();
-			const int pr = cs_i_poll(d->ctx, (int)(copied % m->n_slots));
-			if (pr < 0) return pr;
-			if (pr == 1) {
-				float ms4[4] = {0, 0, 0, 0};
-				if ((rc = cs_i_fetch_wait(d->ctx, (int)(copied % m->n_slots), &d->cnt[j.set], ms4)) != CS_OK) return rc;
-				for (int q = 0; q < 4; ++q) d->gpu_ms[j.set][q] += ms4[q];
-				cs_i_slot_times(d->ctx, (int)(copied % m->n_slots), tr + (size_t)copied * CS_TRACE_COLS, nullptr);
-				tr[(size_t)copied * CS_TRACE_COLS + 7] = host_ms();
-				++copied; progress = true;
-			}
-			hs[1] += since(t);
-		}
-		if (!progress) { const auto t = now(); std::this_thread::sleep_for(std::chrono::microseconds(20)); hs[2] += since(t); }
-	}
-	d->n_mems[j.set] = b.mem_base[nb]; d->n_seeds[j.set] = b.seed_base[nb];
-	b.pub.mem_base = b.mem_base; b.pub.seed_base = b.seed_base; b.pub.mem_off = b.mem_off; b.pub.seed_off = b.seed_off;
-	b.pub.cmems = m->chaining ? nullptr : b.cmems; b.pub.rbeg_lo = b.rlo; b.pub.rbeg_hi = b.rhi;
-	b.pub.chains = m->chaining ? b.chains : nullptr; b.pub.qbeg = m->chaining ? b.sq : nullptr; b.pub.len = m->chaining ? b.sl : nullptr;
 	return CS_OK;
 }
 
+void run_publish(Dev *d, Run *r)
+{
+	cs_multi *m = d->m;
+	BlockBuf &b = *r->b;
+	const int set = r->j.set;
+	if (r->rc == CS_OK && r->n) {
+		d->n_mems[set] = b.mem_base[r->nb]; d->n_seeds[set] = b.seed_base[r->nb];
+		b.pub.mem_base = b.mem_base; b.pub.seed_base = b.seed_base; b.pub.mem_off = b.mem_off; b.pub.seed_off = b.seed_off;
+		b.pub.cmems = m->chaining ? nullptr : b.cmems; b.pub.rbeg_lo = b.rlo; b.pub.rbeg_hi = b.rhi;
+		b.pub.chains = m->chaining ? b.chains : nullptr; b.pub.qbeg = m->chaining ? b.sq : nullptr; b.pub.len = m->chaining ? b.sl : nullptr;
+	}
+	{
+		std::lock_guard<std::mutex> lk(d->mu);
+		d->rc[set] = r->rc;
+		if (r->rc != CS_OK) { strncpy(d->err[set], cs_last_error(), sizeof d->err[set] - 1); d->err[set][sizeof d->err[set] - 1] = 0; }
+		d->done[set] = true;
+	}
+	d->cv.notify_all();
+}
+
+// Event-driven: the thread never blocks on one thing while another is ready.  Whenever the kernels of the oldest unfinished batch
+// are done, its result copy is enqueued at once (the copy engine must not wait for the host); whenever the oldest copy has landed,
+// its slot is free for the next batch -- of the same set or of the next one; otherwise the thread naps for 20 us.
 void worker(Dev *d)
 {
+	cs_multi *m = d->m;
+	std::deque<Run*> runs;          // sets being pipelined, oldest first
+	std::deque<Flight> fl;          // batches in flight in submission order; fl[0 .. enq) have their result copy enqueued
+	size_t enq = 0;
+	uint64_t seq = 0;               // batches submitted so far: batch number seq uses slot seq % n_slots
+	const uint64_t B = m->batch_reads;
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
+	long long base_ns = 0;
+	auto host_ms = [&]() -> float { return (float)((std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() - base_ns) * 1e-6); };
+	auto trace_row = [&](Run *r, uint32_t bi) -> float* { return d->trace[r->j.set].data() + (size_t)bi * CS_TRACE_COLS; };
+	auto retire = [&](Run *r) { // r is runs.front() and complete (or failed)
+		run_publish(d, r);
+		runs.pop_front();
+		delete r;
+	};
+	// a failure: everything in flight is waited for and every active set fails with that code
+	auto fail_all = [&](int rc) {
+		for (size_t i = 0; i < fl.size(); ++i) {
+			uint64_t a, b2;
+			if (i < enq) cs_i_fetch_wait(d->ctx, fl[i].slot, nullptr, nullptr); else cs_i_finish(d->ctx, fl[i].slot, &a, &b2);
+		}
+		fl.clear(); enq = 0;
+		while (!runs.empty()) { runs.front()->rc = rc; retire(runs.front()); }
+	};
+	// results of fl[0] have landed
+	auto complete_front = [&](bool blocking) -> int {
+		Flight f = fl.front();
+		Run *r = f.run;
+		const int set = r->j.set;
+		if (!blocking) {
+			const int pr = cs_i_poll(d->ctx, f.slot);
+			if (pr <= 0) return pr;
+		}
+		float ms4[4] = {0, 0, 0, 0};
+		const int rc = cs_i_fetch_wait(d->ctx, f.slot, &d->cnt[set], ms4);
+		if (rc != CS_OK) return rc;
+		for (int q = 0; q < 4; ++q) d->gpu_ms[set][q] += ms4[q];
+		cs_i_slot_times(d->ctx, f.slot, trace_row(r, f.bi), nullptr);
+		trace_row(r, f.bi)[7] = host_ms();
+		fl.pop_front(); --enq;
+		++r->copied;
+		return 1;
+	};
 	for (;;) {
-		Job j;
-		{
+		{ // new sets: wait for one when idle, otherwise just look
 			std::unique_lock<std::mutex> lk(d->mu);
-			d->cv.wait(lk, [&] { return d->stop || !d->q.empty(); });
-			if (d->q.empty()) return;   // stop
-			j = d->q.front(); d->q.pop_front();
+			if (runs.empty()) d->cv.wait(lk, [&] { return d->stop || !d->q.empty(); });
+			if (runs.empty() && d->q.empty()) return;   // stop
+			while (!d->q.empty() && runs.size() < 2) {
+				Run *r = new Run();
+				r->j = d->q.front(); d->q.pop_front();
+				runs.push_back(r);
+				lk.unlock();
+				r->rc = run_prepare(d, r);
+				if (base_ns == 0 && d->ctx) { float t5[5]; cs_i_slot_times(d->ctx, 0, t5, &base_ns); }
+				lk.lock();
+			}
 		}
-		const int rc = run_block(d, j);
-		{
-			std::lock_guard<std::mutex> lk(d->mu);
-			d->rc[j.set] = rc;
-			if (rc != CS_OK) { strncpy(d->err[j.set], cs_last_error(), sizeof d->err[j.set] - 1); d->err[j.set][sizeof d->err[j.set] - 1] = 0; }
-			d->done[j.set] = true;
+		while (!runs.empty() && (runs.front()->rc != CS_OK || runs.front()->copied == runs.front()->nb)) {
+			if (runs.front()->rc != CS_OK && !fl.empty()) { fail_all(runs.front()->rc); break; }
+			retire(runs.front());
 		}
-		d->cv.notify_all();
+		if (runs.empty()) continue;
+		bool progress = false;
+		int rc = CS_OK;
+		// ---- submit: a slot is free once the results of its previous batch have landed ----
+		while (fl.size() < (size_t)m->n_slots) {
+			Run *r = nullptr;
+			for (Run *c : runs) if (c->rc == CS_OK && c->next < c->nb) { r = c; break; }
+			if (!r) break;
+			const auto t = now();
+			const uint32_t bi = r->next;
+			const uint64_t s0 = r->r0 + (uint64_t)bi * B, e0 = std::min<uint64_t>(r->r1, s0 + B);
+			const int slot = (int)(seq % m->n_slots);
+			trace_row(r, bi)[5] = host_ms();
+			rc = cs_i_submit(d->ctx, slot, (uint32_t)(e0 - s0), r->j.off, r->j.bases, r->j.packed, r->j.nmask, s0, &r->j.opt);
+			d->host_s[r->j.set][0] += since(t);
+			if (rc != CS_OK) break;
+			fl.push_back(Flight{r, bi, slot}); ++seq; ++r->next; progress = true;
+		}
+		if (rc != CS_OK) { fail_all(rc); continue; }
+		// ---- kernels of the oldest unfinished batch done?  then its result copy goes out ----
+		if (enq < fl.size()) {
+			const auto t = now();
+			Flight f = fl[enq];
+			Run *r = f.run;
+			BlockBuf &b = *r->b;
+			const int pr = cs_i_poll(d->ctx, f.slot);
+			if (pr < 0) { fail_all(pr); continue; }
+			if (pr == 1) {
+				uint64_t nm = 0, ns = 0;
+				rc = cs_i_finish(d->ctx, f.slot, &nm, &ns);
+				if (rc == CS_E_OVERFLOW) { // this batch needs larger slot buffers: drain, re-create the ctx once with what it needs, resubmit from here
+					uint64_t need_m = 0, need_s = 0;
+					cs_ctx_need(d->ctx, f.slot, &need_m, &need_s);
+					rc = CS_OK;
+					while (enq > 0 && rc == CS_OK) { const int c = complete_front(true); rc = c < 0 ? c : CS_OK; }
+					if (rc != CS_OK) { fail_all(rc); continue; }
+					if (need_m >= (1ull << 32) || need_s >= (1ull << 32)) {
+						fail_all(cs_set_err(CS_E_OVERFLOW, "a batch of %u reads needs more than 2^32 mems or seeds: use smaller batches", m->batch_reads));
+						continue;
+					}
+					if (need_m <= d->cap_mems && need_s <= d->cap_seeds) { need_m = d->cap_mems * 2; need_s = d->cap_seeds * 2; }
+					d->cap_mems = std::max(d->cap_mems, need_m); d->cap_seeds = std::max(d->cap_seeds, need_s);
+					for (const Flight &g : fl) g.run->next = std::min(g.run->next, g.bi);   // the batches still in flight are dropped with the old ctx
+					fl.clear(); enq = 0;
+					if ((rc = make_ctx(d)) != CS_OK) { fail_all(rc); continue; }
+					{ float t5[5]; cs_i_slot_times(d->ctx, 0, t5, &base_ns); }
+					continue;
+				}
+				if (rc != CS_OK) { fail_all(rc); continue; }
+				{ // room for this batch in the block arrays (rare: the estimate per read was too low)
+					const uint64_t mb = b.mem_base[f.bi], sb = b.seed_base[f.bi];
+					const uint64_t cap1 = m->chaining ? b.cap_chains : b.cap_mems, cap2 = m->chaining ? std::min(b.cap_seeds, b.cap_sq) : b.cap_seeds;
+					if (mb + nm > cap1 || sb + ns > cap2) {
+						// copies into the old arrays must have landed (those of this set; an older set's go to its own arrays, but the order is kept)
+						rc = CS_OK;
+						while (enq > 0 && rc == CS_OK) { const int c = complete_front(true); rc = c < 0 ? c : CS_OK; }
+						if (rc != CS_OK) { fail_all(rc); continue; }
+						void *p; uint64_t c;
+						if (m->chaining) {
+							p = b.chains; c = b.cap_chains;
+							if ((rc = pinned_grow(&p, &c, mb + nm, sizeof(cs_chain_t), mb)) == CS_OK) { b.chains = (cs_chain_t*)p; b.cap_chains = c; }
+							p = b.sq; c = b.cap_sq;
+							if (rc == CS_OK && (rc = pinned_grow(&p, &c, sb + ns, 2, sb)) == CS_OK) b.sq = (uint16_t*)p;
+							p = b.sl; c = b.cap_sq;
+							if (rc == CS_OK && (rc = pinned_grow(&p, &c, sb + ns, 2, sb)) == CS_OK) { b.sl = (uint16_t*)p; b.cap_sq = c; }
+						} else {
+							p = b.cmems; c = b.cap_mems;
+							if ((rc = pinned_grow(&p, &c, mb + nm, sizeof(cs_cmem_t), mb)) == CS_OK) { b.cmems = (cs_cmem_t*)p; b.cap_mems = c; }
+						}
+						p = b.rlo; c = b.cap_seeds;
+						if (rc == CS_OK && (rc = pinned_grow(&p, &c, sb + ns, 4, sb)) == CS_OK) b.rlo = (uint32_t*)p;
+						p = b.rhi; c = b.cap_seeds;
+						if (rc == CS_OK && (rc = pinned_grow(&p, &c, sb + ns, 1, sb)) == CS_OK) { b.rhi = (uint8_t*)p; b.cap_seeds = c; }
+						if (rc != CS_OK) { fail_all(rc); continue; }
+					}
+					uint32_t *o1 = b.mem_off + (uint64_t)f.bi * (B + 1), *o2 = b.seed_off + (uint64_t)f.bi * (B + 1);
+					if (m->chaining) rc = cs_i_fetch_chains_into(d->ctx, f.slot, o1, o2, b.chains + mb, b.rlo + sb, b.rhi + sb, b.sq + sb, b.sl + sb);
+					else rc = cs_i_fetch_compact_into(d->ctx, f.slot, o1, o2, b.cmems + mb, b.rlo + sb, b.rhi + sb);
+					if (rc != CS_OK) { fail_all(rc); continue; }
+					b.mem_base[f.bi + 1] = mb + nm; b.seed_base[f.bi + 1] = sb + ns;
+				}
+				trace_row(r, f.bi)[6] = host_ms();
+				++enq; ++r->done; progress = true;
+			}
+			d->host_s[r->j.set][1] += since(t);
+		}
+		// ---- results of the oldest batch on the host? ----
+		if (enq > 0) {
+			const auto t = now();
+			Run *r = fl.front().run;
+			const int c = complete_front(false);
+			if (c < 0) { fail_all(c); continue; }
+			if (c == 1) progress = true;
+			d->host_s[r->j.set][1] += since(t);
+		}
+		if (!progress) { const auto t = now(); std::this_thread::sleep_for(std::chrono::microseconds(20)); d->host_s[runs.front()->j.set][2] += since(t); }
 	}
 }
 
