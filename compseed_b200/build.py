@@ -12,7 +12,7 @@ LIB_DIR = os.path.join(HERE, "_lib")
 TAG = os.environ.get("CS_TAG", "")
 EXTRA_DEFS = os.environ.get("CS_DEFS", "").split()
 LIB = os.path.join(LIB_DIR, f"libcompseed_b200{('_' + TAG) if TAG else ''}.so")
-SOURCES = ["cs_kernels.cu", "cs_api.cu", "cs_index_build.cu", "cs_verify.cu", "cs_multi.cu", "cs_chain.cu"]
+SOURCES = ["cs_kernels.cu", "cs_api.cu", "cs_index_build.cu", "cs_verify.cu", "cs_multi.cu", "cs_chain.cu", "cs_bsw.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr", "-rdc=false"]
 

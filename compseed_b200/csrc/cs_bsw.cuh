@@ -1,0 +1,117 @@
+// Device side of the banded Smith-Waterman extension (see cs_bsw.cu for what it reproduces and why it is laid out this way).
+// Kept in a header of its own so that tests/emul/bsw_emul.cpp can compile bsw_one_pair as plain C++ and run it on the CPU
+// against the reference (test infrastructure; the library has no CPU path).
+#pragma once
+#include <cstdint>
+#include <cstddef>
+
+struct PairIn { int32_t idr, idq, len1, len2, h0; };
+
+struct BswArgs {
+	const PairIn *in;
+	const uint32_t *order;      // pair indices sorted by query length
+	uint32_t n;
+	const uint8_t *ref, *qer;
+	int2 *eh; size_t eh_stride; // eh[j * eh_stride + thread]: {H(i-1, j-1), E(i, j)} of the row in progress
+	int32_t w, o_del, e_del, o_ins, e_ins, zdrop, end_bonus, max_mat;
+	int8_t mat[25];
+	int32_t *out;               // 6 per pair: score, tle, gtle, qle, gscore, max_off (the order of SeqPair)
+	unsigned int *work;
+	unsigned long long *cells;
+};
+
+// ksw_extend2 (bwalib/ksw.c:380-479) for pair pid; eh: this thread's DP row, column j at eh[j * st]; s_mat: the 5 x 5 scores.
+// Returns the number of cells computed.
+__device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uint32_t pid, int2 *eh, size_t st, const int *s_mat)
+{
+	const int o_del = a.o_del, e_del = a.e_del, o_ins = a.o_ins, e_ins = a.e_ins, oe_del = o_del + e_del, oe_ins = o_ins + e_ins, zdrop = a.zdrop;
+	unsigned long long cells = 0;
+	const PairIn p = a.in[pid];
+	const int qlen = p.len2, tlen = p.len1, h0 = p.h0;
+	const uint8_t *query = a.qer + p.idq, *target = a.ref + p.idr;
+	int i, j, beg, end, max, max_i, max_j, max_ie, gscore, max_off, w = a.w;
+	// first row (ksw.c:395-398): H(-1, j); everything else of the row array is zero (calloc)
+	{
+		int h = h0 > oe_ins ? h0 - oe_ins : 0;
+		eh[0] = make_int2(h0, 0);
+		eh[st] = make_int2(h, 0);
+		for (j = 2; j <= qlen; ++j) {
+			h = h > e_ins ? h - e_ins : 0;      // (once 0 <= e_ins the reference's loop stops and the rest stays 0)
+			eh[(size_t)j * st] = make_int2(h, 0);
+		}
+	}
+	// w no larger than what the scores allow (ksw.c:401-408)
+	{
+		int max_ins = (int)((double)(qlen * a.max_mat + a.end_bonus - o_ins) / e_ins + 1.);
+		max_ins = max_ins > 1 ? max_ins : 1;
+		w = w < max_ins ? w : max_ins;
+		int max_del = (int)((double)(qlen * a.max_mat + a.end_bonus - o_del) / e_del + 1.);
+		max_del = max_del > 1 ? max_del : 1;
+		w = w < max_del ? w : max_del;
+	}
+	max = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
+	beg = 0; end = qlen;
+	for (i = 0; i < tlen; ++i) {
+		int f = 0, h1, m = 0, mj = -1;
+		const int *q = s_mat + 5 * (int)target[i];
+		if (beg < i - w) beg = i - w;
+		if (end > i + w + 1) end = i + w + 1;
+		if (end > qlen) end = qlen;
+		if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
+		else h1 = 0;
+		int2 *pe = eh + (size_t)beg * st;
+		for (j = beg; j < end; ++j, pe += st) { // ksw.c:421-447
+			const int2 v = *pe;
+			int M = v.x, e = v.y, h, t;
+			M = M ? M + q[query[j]] : 0;
+			h = M > e ? M : e;
+			h = h > f ? h : f;
+			mj = m > h ? mj : j;
+			m = m > h ? m : h;
+			t = M - oe_del; t = t > 0 ? t : 0;
+			e -= e_del; e = e > t ? e : t;
+			*pe = make_int2(h1, e);
+			h1 = h;
+			t = M - oe_ins; t = t > 0 ? t : 0;
+			f -= e_ins; f = f > t ? f : t;
+		}
+		cells += (unsigned)(end > beg ? end - beg : 0);
+		eh[(size_t)end * st] = make_int2(h1, 0);   // (end, not where the loop stopped: the band can be empty, beg > end, once i - w passes the query)
+		if (j == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
+		if (m == 0) break;
+		if (m > max) {
+			max = m; max_i = i; max_j = mj;
+			const int off = mj > i ? mj - i : i - mj;
+			max_off = max_off > off ? max_off : off;
+		} else if (zdrop > 0) {
+			if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop) break; }
+			else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break; }
+		}
+		// the band of the next row: the non-zero cells of this one (ksw.c:463-468)
+		for (j = beg; j < end; ++j) { const int2 v = eh[(size_t)j * st]; if (v.x != 0 || v.y != 0) break; }
+		beg = j;
+		for (j = end; j >= beg; --j) { const int2 v = eh[(size_t)j * st]; if (v.x != 0 || v.y != 0) break; }
+		end = j + 2 < qlen ? j + 2 : qlen;
+	}
+	int32_t *o = a.out + 6 * (size_t)pid;
+	o[0] = max; o[1] = max_i + 1; o[2] = max_ie + 1; o[3] = max_j + 1; o[4] = gscore; o[5] = max_off;
+	return cells;
+}
+
+__global__ void __launch_bounds__(128) k_bsw_extend(BswArgs a)
+{
+	__shared__ int s_mat[25];
+	if (threadIdx.x < 25) s_mat[threadIdx.x] = a.mat[threadIdx.x];
+	__syncthreads();
+	const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	unsigned long long cells = 0;
+	for (;;) { // 32 pairs of similar query length per warp and trip
+		unsigned int base = 0;
+		if (lane == 0) base = atomicAdd(a.work, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= a.n) break;
+		if (base + lane < a.n) cells += bsw_one_pair(a, a.order[base + lane], a.eh + gtid, a.eh_stride, s_mat);
+	}
+	if (cells) atomicAdd(a.cells, cells);
+}

@@ -123,6 +123,11 @@ class _CtxConfig(C.Structure):
                 ("prefetch_results", C.c_int32), ("l2_persist_mb", C.c_int32), ("overlap_streams", C.c_int32), ("compact_results", C.c_int32), ("batch_order", C.c_int32)]
 
 
+class _BswOpt(C.Structure):
+    _fields_ = [("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32), ("e_ins", C.c_int32), ("zdrop", C.c_int32),
+                ("end_bonus", C.c_int32), ("mat", C.c_int8 * 25)]
+
+
 class _CompactResult(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_mems", C.c_uint64), ("n_seeds", C.c_uint64),
                 ("mem_off", C.POINTER(C.c_uint32)), ("cmems", C.POINTER(C.c_uint32)),
@@ -238,6 +243,15 @@ def load_library():
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.cs_flush_l2.argtypes = [C.c_int]
     L.cs_debug_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.cs_bsw_create.restype = C.c_void_p
+    L.cs_bsw_create.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32]
+    L.cs_bsw_free.argtypes = [C.c_void_p]
+    L.cs_bsw_extend.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(_BswOpt)]
+    L.cs_bsw_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32]
+    L.cs_bsw_run_staged.argtypes = [C.c_void_p, C.c_int32, C.POINTER(_BswOpt), C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    L.cs_bsw_fetch.argtypes = [C.c_void_p, C.c_void_p]
+    L.cs_bsw_launches.restype = C.c_uint64
+    L.cs_bsw_launches.argtypes = [C.c_void_p]
     L.cs_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.cs_host_unregister.argtypes = [C.c_void_p]
     _lib = L
@@ -856,3 +870,86 @@ def host_unregister(a: np.ndarray) -> None:
 
 def flush_l2(device: int = 0) -> None:
     _check(load_library().cs_flush_l2(device))
+
+
+# --- banded Smith-Waterman extension (cs_bsw_*: BandedPairWiseSW::scalarBandedSWAWrapper / getScores8 / getScores16) ---
+# A batch of pairs is an int32 array [n, 14] in the layout of the reference's SeqPair (bandedSWA.h:91-99):
+PAIR_IDR, PAIR_IDQ, PAIR_ID, PAIR_LEN1, PAIR_LEN2, PAIR_H0, PAIR_SEQID, PAIR_REGID, PAIR_SCORE, PAIR_TLE, PAIR_GTLE, PAIR_QLE, PAIR_GSCORE, PAIR_MAX_OFF = range(14)
+
+
+def bwa_fill_scmat(a: int = 1, b: int = 4, ambig: int = -1) -> np.ndarray:
+    """mem_opt_t.mat as bwa_fill_scmat builds it (bwalib/bwa.c:419-431): a on the diagonal, -b off it, `ambig` in the N row and column."""
+    m = np.full((5, 5), -b, dtype=np.int8)
+    np.fill_diagonal(m, a)
+    m[4, :] = ambig
+    m[:, 4] = ambig
+    return m.reshape(25)
+
+
+@dataclass
+class BswOpt:
+    """The constructor arguments of BandedPairWiseSW (bandedSWA.cpp:48-58); defaults of mem_opt_init (comp_seed.cpp:26-61)."""
+    o_del: int = 6
+    e_del: int = 1
+    o_ins: int = 6
+    e_ins: int = 1
+    zdrop: int = 100
+    end_bonus: int = 5
+    mat: np.ndarray | None = None
+
+    def _c(self) -> _BswOpt:
+        m = self.mat if self.mat is not None else bwa_fill_scmat()
+        return _BswOpt(self.o_del, self.e_del, self.o_ins, self.e_ins, self.zdrop, self.end_bonus, (C.c_int8 * 25)(*[int(x) for x in m]))
+
+
+class BswExtender:
+    """cs_bsw_t: batches of extension pairs on one device."""
+
+    def __init__(self, device: int = 0, max_pairs: int = 1 << 20, max_ref_bytes: int = 1 << 26, max_qer_bytes: int = 1 << 26, max_qlen: int = 256):
+        self.h = load_library().cs_bsw_create(device, max_pairs, max_ref_bytes, max_qer_bytes, max_qlen)
+        if not self.h:
+            raise CompSeedError(load_library().cs_last_error_code(), load_library().cs_last_error().decode())
+
+    def close(self) -> None:
+        if self.h:
+            load_library().cs_bsw_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(load_library().cs_bsw_launches(self.h))
+
+    @staticmethod
+    def _check_pairs(pairs):
+        if pairs.dtype != np.int32 or pairs.ndim != 2 or pairs.shape[1] != 14 or not pairs.flags.c_contiguous:
+            raise ValueError("pairs: C-contiguous int32 [n, 14] (SeqPair)")
+
+    def extend(self, pairs: np.ndarray, seq_buf_ref: np.ndarray, seq_buf_qer: np.ndarray, w: int = 100, opt: BswOpt | None = None) -> np.ndarray:
+        """scalarBandedSWAWrapper(pairs, seqBufRef, seqBufQer, n, 1, w): fills score .. max_off of `pairs` in place and returns it."""
+        self._check_pairs(pairs)
+        o = (opt or BswOpt())._c()
+        _check(load_library().cs_bsw_extend(self.h, _ptr(pairs), _ptr(seq_buf_ref), seq_buf_ref.nbytes, _ptr(seq_buf_qer), seq_buf_qer.nbytes,
+                                            pairs.shape[0], w, C.byref(o)))
+        return pairs
+
+    def stage(self, pairs: np.ndarray, seq_buf_ref: np.ndarray, seq_buf_qer: np.ndarray) -> None:
+        self._check_pairs(pairs)
+        _check(load_library().cs_bsw_stage(self.h, _ptr(pairs), _ptr(seq_buf_ref), seq_buf_ref.nbytes, _ptr(seq_buf_qer), seq_buf_qer.nbytes, pairs.shape[0]))
+
+    def run_staged(self, w: int = 100, opt: BswOpt | None = None):
+        """Returns (kernel_ms, cells)."""
+        o = (opt or BswOpt())._c()
+        ms, cells = C.c_float(), C.c_uint64()
+        _check(load_library().cs_bsw_run_staged(self.h, w, C.byref(o), C.byref(ms), C.byref(cells)))
+        return float(ms.value), int(cells.value)
+
+    def fetch(self, pairs: np.ndarray) -> np.ndarray:
+        self._check_pairs(pairs)
+        _check(load_library().cs_bsw_fetch(self.h, _ptr(pairs)))
+        return pairs

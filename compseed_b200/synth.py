@@ -212,3 +212,102 @@ def simulate_reads_torch(ref, n_reads: int, read_len: int, sub_rate: float, seed
         bases[s * read_len:e * read_len] = b.reshape(-1).cpu().numpy()
     off = (np.arange(n_reads + 1, dtype=np.int64) * read_len).astype(np.uint32)
     return bases, off, pos.cpu().numpy()
+
+
+def extension_pairs(n: int, seed: int, max_qlen: int = 150, sub_rate: float = 0.02, indel_rate: float = 0.004, n_rate: float = 0.002,
+                    unrelated_frac: float = 0.05, a: int = 1, w: int = 100, max_seed_len: int = 150, extra_gap: bool = True):
+    """Synthetic input of the extension stage in the shape mem_chain2aln_across_reads_V2 builds it (comp_seed.cpp:1480-1660): for each
+    pair a query of 1..max_qlen bases (the part of a read left or right of a seed), a target that is a mutated copy of it (substitutions,
+    short indels, a few Ns) followed by unrelated flank up to the length the caller fetches (query + cal_max_gap, bwamem.c:66-73, capped
+    at 2w), and h0 = seed length x a.  A fraction of the pairs has an unrelated target (extension dies at once / z-drop), some have an
+    empty or one-base target, some a long indel.  Returns (pairs int32 [n, 14] (SeqPair layout), seq_buf_ref u8, seq_buf_qer u8)."""
+    rng = np.random.default_rng(seed)
+    pairs = np.zeros((n, 14), dtype=np.int32)
+    refs, qers = [], []
+    ro = qo = 0
+    for i in range(n):
+        ql = int(rng.integers(1, max_qlen + 1))
+        q = rng.integers(0, 4, ql).astype(np.uint8)
+        kind = rng.random()
+        if kind < unrelated_frac:
+            t = rng.integers(0, 4, int(rng.integers(0, ql + 40))).astype(np.uint8)
+        else:
+            t = []
+            j = 0
+            long_indel = rng.random() < 0.03
+            at = int(rng.integers(0, ql)) if long_indel else -1
+            while j < ql:
+                if j == at:
+                    k = int(rng.integers(5, 40))
+                    if rng.random() < 0.5:
+                        t.extend(rng.integers(0, 4, k).tolist())      # deletion from the read = extra target bases
+                    else:
+                        j += k                                         # insertion in the read = target skips query bases
+                        continue
+                r = rng.random()
+                if r < indel_rate:
+                    t.append(int(rng.integers(0, 4)))
+                    continue
+                if r < 2 * indel_rate:
+                    j += 1
+                    continue
+                b = int(q[j])
+                if rng.random() < sub_rate:
+                    b = (b + int(rng.integers(1, 4))) & 3
+                t.append(b)
+                j += 1
+            # flank: what bns_fetch_seq returns beyond the end of the read (max gap for the rest of the query, capped at 2w)
+            gap = min(2 * w, max(1, int((ql * a - 6) / 1.0 + 1))) if extra_gap else 0
+            t.extend(rng.integers(0, 4, int(rng.integers(0, gap + 1))).tolist())
+            t = np.asarray(t, dtype=np.uint8)
+            if rng.random() < 0.01:
+                t = t[:int(rng.integers(0, 2))]
+        if n_rate > 0:
+            q = q.copy(); t = t.copy()
+            q[rng.random(q.shape[0]) < n_rate] = 4
+            t[rng.random(t.shape[0]) < n_rate] = 4
+        pairs[i, 0], pairs[i, 1], pairs[i, 2] = ro, qo, i
+        pairs[i, 3], pairs[i, 4] = t.shape[0], ql
+        pairs[i, 5] = int(rng.integers(19, max_seed_len + 1)) * a
+        pairs[i, 6], pairs[i, 7] = i // 3, i % 3
+        refs.append(t); qers.append(q)
+        ro += t.shape[0]; qo += ql
+    ref = np.concatenate(refs) if refs else np.zeros(0, np.uint8)
+    qer = np.concatenate(qers) if qers else np.zeros(0, np.uint8)
+    return pairs, np.ascontiguousarray(ref, dtype=np.uint8), np.ascontiguousarray(qer, dtype=np.uint8)
+
+
+def extension_pairs_fast(n: int, seed: int, max_qlen: int = 150, sub_rate: float = 0.02, indel_frac: float = 0.15, n_rate: float = 0.001,
+                         unrelated_frac: float = 0.03, a: int = 1, w: int = 100, max_seed_len: int = 150):
+    """Vectorised variant of extension_pairs for large batches (benchmarks, full-size tests): queries are slices of a random genome
+    with substitutions; the target of a pair is the same stretch of the genome plus the flank the caller would fetch (up to
+    min(2w, query length) more bases), for `indel_frac` of the pairs with one indel of 1..12 bases at a random position, for
+    `unrelated_frac` of them taken from somewhere else.  Same return value as extension_pairs."""
+    rng = np.random.default_rng(seed)
+    glen = 1 << 22
+    g = rng.integers(0, 4, glen + 4096, dtype=np.uint8)
+    ql = rng.integers(1, max_qlen + 1, n).astype(np.int64)
+    flank = (rng.random(n) * (np.minimum(2 * w, ql) + 1)).astype(np.int64)
+    d = np.where(rng.random(n) < indel_frac, rng.integers(-12, 13, n), 0).astype(np.int64)       # > 0: the target skips d genome bases
+    tl = np.maximum(ql + flank - np.maximum(d, 0) * 0, 0)
+    k1 = (rng.random(n) * ql).astype(np.int64)                                                 # where the indel sits
+    s = rng.integers(16, glen - 2 * max_qlen - 512, n).astype(np.int64)
+    ts = np.where(rng.random(n) < unrelated_frac, rng.integers(16, glen - 2 * max_qlen - 512, n), s)
+    qoff = np.zeros(n + 1, np.int64); qoff[1:] = np.cumsum(ql)
+    roff = np.zeros(n + 1, np.int64); roff[1:] = np.cumsum(tl)
+    qi = np.arange(qoff[-1], dtype=np.int64) - np.repeat(qoff[:-1], ql)
+    qer = g[np.repeat(s, ql) + qi].copy()
+    sub = rng.random(qer.shape[0]) < sub_rate
+    qer[sub] = (qer[sub] + rng.integers(1, 4, int(sub.sum())).astype(np.uint8)) & 3
+    ti = np.arange(roff[-1], dtype=np.int64) - np.repeat(roff[:-1], tl)
+    shift = np.where(ti >= np.repeat(k1, tl), np.repeat(d, tl), 0)
+    ref = g[np.clip(np.repeat(ts, tl) + ti + shift, 0, glen + 4095)].copy()
+    if n_rate > 0:
+        qer[rng.random(qer.shape[0]) < n_rate] = 4
+        ref[rng.random(ref.shape[0]) < n_rate] = 4
+    pairs = np.zeros((n, 14), dtype=np.int32)
+    pairs[:, 0] = roff[:-1]; pairs[:, 1] = qoff[:-1]; pairs[:, 2] = np.arange(n)
+    pairs[:, 3] = tl; pairs[:, 4] = ql
+    pairs[:, 5] = rng.integers(19, max_seed_len + 1, n) * a
+    pairs[:, 6] = np.arange(n) // 3; pairs[:, 7] = np.arange(n) % 3
+    return pairs, np.ascontiguousarray(ref), np.ascontiguousarray(qer)

@@ -18,6 +18,8 @@
  *     (mapping/comp_seed.cpp:2255-2302)
  *   seed expansion + bwt_sa                                 "        (rbeg[] == seed[r][*].rbeg, emission order)
  *     (mapping/bwamem.c:386-399, comp_seed.cpp:2306-2346)
+ *   BandedPairWiseSW::scalarBandedSWAWrapper / getScores8  cs_bsw_extend      (one ksw_extend2 per sequence pair)
+ *     / getScores16 (mapping/bandedSWA.cpp, ksw.c:380)
  *   kt_for workers over reads / 512-read blocks            slots of a cs_ctx_t (pinned buffers, one CUDA
  *     (mapping/bwamem.c:1343, comp_seed.cpp:2541-2548)       stream per slot; submit batch i+1 while waiting on i)
  *
@@ -301,6 +303,46 @@ typedef struct {
 int cs_ctx_set_chaining(cs_ctx_t *ctx, const cs_bns_view_t *bns, const cs_chain_opt_t *opt);
 /* Waits for the slot and fetches ONLY the chains (the mems / seed positions stay on the device; cs_seed_batch_fetch still gets them). */
 int cs_seed_batch_wait_chains(cs_ctx_t *ctx, int slot, cs_chain_result_t *out);
+
+/* --- banded Smith-Waterman extension ----------------------------------------------
+ * Replaces the batch calls of the reference's extension stage, BandedPairWiseSW::scalarBandedSWAWrapper / getScores8 / getScores16
+ * (mapping/bandedSWA.cpp:242-260 and the SIMD twins; called from mem_chain2aln_across_reads_V2, comp_seed.cpp:1722-2074), i.e. one
+ * ksw_extend2 (bwalib/ksw.c:380-479 == scalarBandedSWA, bandedSWA.cpp:118-237) per sequence pair: score, qle, tle, gtle, gscore,
+ * max_off, bit for bit -- including the band that follows the non-zero cells from row to row (ksw.c:463-468), the z-drop test
+ * (:456-462) and the cap on w (:401-408).  cs_seqpair_t IS the reference's SeqPair (bandedSWA.h:91-99): the caller fills idr / idq
+ * (offsets of the target / the query of the pair in seqBufRef / seqBufQer), len1 (target), len2 (query) and h0; the call fills
+ * score .. max_off and leaves the other fields alone.  Sequences are nt4 codes (0-3, 4 = N), one byte per base. */
+typedef struct {
+	int32_t idr, idq, id;
+	int32_t len1, len2;
+	int32_t h0;
+	int32_t seqid, regid;
+	int32_t score, tle, gtle, qle;
+	int32_t gscore, max_off;
+} cs_seqpair_t;
+
+typedef struct {              /* the constructor arguments of BandedPairWiseSW (bandedSWA.cpp:48-58) */
+	int32_t o_del, e_del, o_ins, e_ins;   /* mem_opt_t.o_del .. e_ins (6, 1, 6, 1) */
+	int32_t zdrop;                        /* mem_opt_t.zdrop (100) */
+	int32_t end_bonus;                    /* pen_clip5 for the left extensions, pen_clip3 for the right ones (5) */
+	int8_t mat[25];                       /* mem_opt_t.mat: 5 x 5 scores, mat[target * 5 + query] (bwa_fill_scmat, bwalib/bwa.c:419) */
+} cs_bsw_opt_t;
+
+typedef struct cs_bsw cs_bsw_t;
+/* Device buffers and page-locked staging for batches of up to max_pairs pairs whose sequences take up to max_ref_bytes /
+ * max_qer_bytes (grown on demand).  max_qlen: longest query the DP rows are sized for (also grown on demand). */
+cs_bsw_t *cs_bsw_create(int device, uint32_t max_pairs, uint64_t max_ref_bytes, uint64_t max_qer_bytes, uint32_t max_qlen);
+void cs_bsw_free(cs_bsw_t *b);
+/* scalarBandedSWAWrapper(pairs, seqBufRef, seqBufQer, n_pairs, nthreads, w): blocking; host buffers in, pairs[] updated in place.
+ * ref_bytes / qer_bytes: how much of the two buffers the pairs refer to (max over pairs of idr + len1 / idq + len2). */
+int cs_bsw_extend(cs_bsw_t *b, cs_seqpair_t *pairs, const uint8_t *seq_buf_ref, uint64_t ref_bytes, const uint8_t *seq_buf_qer, uint64_t qer_bytes,
+                  uint32_t n_pairs, int32_t w, const cs_bsw_opt_t *opt);
+/* The same on inputs already staged on the device by cs_bsw_stage (benchmarks: inputs resident in HBM); results stay on the device
+ * until cs_bsw_fetch.  *kernel_ms: CUDA-event time of the extension kernel; *cells: DP cells it computed. */
+int cs_bsw_stage(cs_bsw_t *b, const cs_seqpair_t *pairs, const uint8_t *seq_buf_ref, uint64_t ref_bytes, const uint8_t *seq_buf_qer, uint64_t qer_bytes, uint32_t n_pairs);
+int cs_bsw_run_staged(cs_bsw_t *b, int32_t w, const cs_bsw_opt_t *opt, float *kernel_ms, uint64_t *cells);
+int cs_bsw_fetch(cs_bsw_t *b, cs_seqpair_t *pairs);
+uint64_t cs_bsw_launches(const cs_bsw_t *b);
 
 /* --- multi-device pipeline ----------------------------------------------------------------------
  * Replaces kt_for(opt->n_threads, worker1 / seed_and_extend) over the reads of a -K batch for the seeding part

@@ -577,3 +577,111 @@ void cso_result_free(void *rr)
 	result_t *r = (result_t*)rr;
 	free(r->mem_off); free(r->seed_off); free(r->mems); free(r->rbeg); free(r);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Banded Smith-Waterman extension: ksw_extend2 (bwalib/ksw.c:380-479), which BandedPairWiseSW::scalarBandedSWA
+ * (mapping/bandedSWA.cpp:118-237) repeats with m = 5.  Written from the recurrences the reference documents at ksw.c:423-428:
+ *   H(i,j) = max{M(i,j), E(i,j), F(i,j)},  M(i,j) = H(i-1,j-1) ? H(i-1,j-1) + S(i,j) : 0
+ *   E(i+1,j) = max{M(i,j) - o_del - e_del, E(i,j) - e_del, 0},  F(i,j+1) = max{M(i,j) - o_ins - e_ins, F(i,j) - e_ins, 0}
+ * over a band that is re-cut to the non-zero cells after every row (ksw.c:463-468).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { int32_t h, e; } cso_eh_t;
+
+static int cso_bsw_one(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
+                       int w, int end_bonus, int zdrop, int h0, int *qle, int *tle, int *gtle, int *gscore_out, int *max_off_out, uint64_t *cells)
+{
+	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+	cso_eh_t *row = (cso_eh_t*)calloc((size_t)qlen + 1, sizeof(cso_eh_t));   /* row[j] = { H(i-1, j-1), E(i, j) } (ksw.c:393) */
+	int i, j, k, best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0, lo = 0, hi = qlen, mmax = 0;
+	uint64_t ncell = 0;
+	/* H(-1, j): the query consumed as an insertion (ksw.c:395-398) */
+	row[0].h = h0; row[1].h = h0 > oe_ins ? h0 - oe_ins : 0;
+	for (j = 2; j <= qlen && row[j - 1].h > e_ins; ++j) row[j].h = row[j - 1].h - e_ins;
+	/* the band cannot usefully be wider than the longest gap the best possible score pays for (ksw.c:400-408) */
+	for (k = 0; k < 25; ++k) mmax = mmax > mat[k] ? mmax : mat[k];
+	{
+		int gi = (int)((double)(qlen * mmax + end_bonus - o_ins) / e_ins + 1.), gd = (int)((double)(qlen * mmax + end_bonus - o_del) / e_del + 1.);
+		if (gi < 1) gi = 1;
+		if (gd < 1) gd = 1;
+		if (w > gi) w = gi;
+		if (w > gd) w = gd;
+	}
+	for (i = 0; i < tlen; ++i) {
+		const int8_t *s = mat + 5 * target[i];
+		int f = 0, left, rowmax = 0, rowmax_j = -1;
+		if (lo < i - w) lo = i - w;
+		if (hi > i + w + 1) hi = i + w + 1;
+		if (hi > qlen) hi = qlen;
+		left = 0;                                             /* H(i, lo-1): the target consumed as a deletion, only in column -1 (ksw.c:416-419) */
+		if (lo == 0) { left = h0 - (o_del + e_del * (i + 1)); if (left < 0) left = 0; }
+		for (j = lo; j < hi; ++j) {
+			const int diag = row[j].h, e = row[j].e;
+			const int M = diag ? diag + s[query[j]] : 0;       /* ksw.c:432 */
+			int h = M > e ? M : e, t;
+			if (f > h) h = f;
+			row[j].h = left; left = h;                        /* row[j].h becomes H(i, j-1) for the next row */
+			if (h >= rowmax) { rowmax = h; rowmax_j = j; }    /* the LAST column that reaches the row maximum (ksw.c:437-438) */
+			t = M - oe_del; if (t < 0) t = 0;
+			row[j].e = e - e_del > t ? e - e_del : t;
+			t = M - oe_ins; if (t < 0) t = 0;
+			f = f - e_ins > t ? f - e_ins : t;
+		}
+		if (hi > lo) ncell += (uint64_t)(hi - lo);
+		row[hi].h = left; row[hi].e = 0;
+		if (j == qlen) {                                     /* the row reached the end of the query (ksw.c:449-452): >= keeps the LAST such row */
+			if (left >= gscore) { best_ie = i; gscore = left; }
+		}
+		if (rowmax == 0) break;
+		if (rowmax > best) {
+			const int d = rowmax_j > i ? rowmax_j - i : i - rowmax_j;
+			best = rowmax; best_i = i; best_j = rowmax_j;
+			if (d > max_off) max_off = d;
+		} else if (zdrop > 0) {
+			const int di = i - best_i, dj = rowmax_j - best_j;
+			if (di > dj) { if (best - rowmax - (di - dj) * e_del > zdrop) break; }
+			else if (best - rowmax - (dj - di) * e_ins > zdrop) break;
+		}
+		for (j = lo; j < hi && row[j].h == 0 && row[j].e == 0; ++j) {}
+		lo = j;
+		for (j = hi; j >= lo && row[j].h == 0 && row[j].e == 0; --j) {}
+		hi = j + 2 < qlen ? j + 2 : qlen;
+	}
+	free(row);
+	*cells += ncell;
+	*qle = best_j + 1; *tle = best_i + 1; *gtle = best_ie + 1; *gscore_out = gscore; *max_off_out = max_off;
+	return best;
+}
+
+typedef struct { int32_t *pairs; const uint8_t *ref, *qer; int n, w, o_del, e_del, o_ins, e_ins, zdrop, end_bonus; const int8_t *mat; int t, nt; uint64_t cells; } cso_bsw_job_t;
+
+static void *cso_bsw_worker(void *arg)
+{
+	cso_bsw_job_t *J = (cso_bsw_job_t*)arg;
+	const int64_t a = (int64_t)J->n * J->t / J->nt, b = (int64_t)J->n * (J->t + 1) / J->nt;
+	for (int64_t i = a; i < b; ++i) {
+		int32_t *p = J->pairs + 14 * i;   /* SeqPair: idr idq id len1 len2 h0 seqid regid score tle gtle qle gscore max_off */
+		int qle, tle, gtle, gscore, max_off;
+		p[8] = cso_bsw_one(p[4], J->qer + p[1], p[3], J->ref + p[0], J->mat, J->o_del, J->e_del, J->o_ins, J->e_ins, J->w, J->end_bonus, J->zdrop, p[5],
+		                   &qle, &tle, &gtle, &gscore, &max_off, &J->cells);
+		p[9] = tle; p[10] = gtle; p[11] = qle; p[12] = gscore; p[13] = max_off;
+	}
+	return NULL;
+}
+
+uint64_t cso_bsw_extend(int32_t *pairs, const uint8_t *seq_buf_ref, const uint8_t *seq_buf_qer, int n_pairs, int w,
+                        int o_del, int e_del, int o_ins, int e_ins, int zdrop, int end_bonus, const int8_t *mat, int n_threads)
+{
+	if (n_threads < 1) n_threads = 1;
+	if (n_threads > 256) n_threads = 256;
+	cso_bsw_job_t *J = (cso_bsw_job_t*)calloc(n_threads, sizeof(cso_bsw_job_t));
+	pthread_t *th = (pthread_t*)calloc(n_threads, sizeof(pthread_t));
+	uint64_t cells = 0;
+	for (int t = 0; t < n_threads; ++t) {
+		cso_bsw_job_t j = { pairs, seq_buf_ref, seq_buf_qer, n_pairs, w, o_del, e_del, o_ins, e_ins, zdrop, end_bonus, mat, t, n_threads, 0 };
+		J[t] = j;
+		pthread_create(&th[t], NULL, cso_bsw_worker, &J[t]);
+	}
+	for (int t = 0; t < n_threads; ++t) { pthread_join(th[t], NULL); cells += J[t].cells; }
+	free(J); free(th);
+	return cells;
+}

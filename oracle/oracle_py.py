@@ -370,3 +370,54 @@ def ref_chain(read_off, res: SeedResult, contig_lens, min_seed_len=19, split_fac
     finally:
         L.csref_chains_free(h)
     return out
+
+
+# ---- banded Smith-Waterman extension ----
+def bsw_mat(a: int = 1, b: int = 4, ambig: int = -1) -> np.ndarray:
+    """bwa_fill_scmat (bwalib/bwa.c:419-431)."""
+    m = np.full((5, 5), -b, dtype=np.int8)
+    np.fill_diagonal(m, a)
+    m[4, :] = ambig
+    m[:, 4] = ambig
+    return np.ascontiguousarray(m.reshape(25))
+
+
+def oracle_bsw(pairs: np.ndarray, seq_buf_ref: np.ndarray, seq_buf_qer: np.ndarray, w: int = 100, o_del=6, e_del=1, o_ins=6, e_ins=1, zdrop=100,
+               end_bonus=5, mat: np.ndarray | None = None, n_threads: int = 1):
+    """Our C restatement of ksw_extend2 over a batch (oracle/cs_oracle.c: cso_bsw_extend).  Returns (pairs copy with results, cells)."""
+    L = lib()
+    L.cso_bsw_extend.restype = C.c_uint64
+    L.cso_bsw_extend.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_int] * 6 + [C.c_void_p, C.c_int]
+    out = np.ascontiguousarray(pairs, dtype=np.int32).copy()
+    m = np.ascontiguousarray(mat if mat is not None else bsw_mat(), dtype=np.int8)
+    ref = np.ascontiguousarray(seq_buf_ref, dtype=np.uint8); qer = np.ascontiguousarray(seq_buf_qer, dtype=np.uint8)
+    cells = L.cso_bsw_extend(_ptr(out), _ptr(ref), _ptr(qer), out.shape[0], w, o_del, e_del, o_ins, e_ins, zdrop, end_bonus, _ptr(m), n_threads)
+    return out, int(cells)
+
+
+def ref_bsw(pairs: np.ndarray, seq_buf_ref: np.ndarray, seq_buf_qer: np.ndarray, w: int = 100, o_del=6, e_del=1, o_ins=6, e_ins=1, zdrop=100,
+            end_bonus=5, a: int = 1, b: int = 4, mode: int = 0):
+    """The unmodified reference: BandedPairWiseSW::scalarBandedSWAWrapper (mode 0), getScores8 (1), getScores16 (2)
+    (mapping/bandedSWA.cpp).  Returns (pairs copy with results, seconds)."""
+    L = ref_lib()
+    L.csref_bsw.restype = C.c_double
+    L.csref_bsw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    out = np.ascontiguousarray(pairs, dtype=np.int32).copy()
+    m = bsw_mat(a, b)
+    ref = np.ascontiguousarray(seq_buf_ref, dtype=np.uint8); qer = np.ascontiguousarray(seq_buf_qer, dtype=np.uint8)
+    # the SIMD twins read whole vectors past the last base of a sequence: pad the buffers as the caller's are (comp_seed.h: seqBuf sizes)
+    ref = np.concatenate([ref, np.zeros(1024, np.uint8)]); qer = np.concatenate([qer, np.zeros(1024, np.uint8)])
+    sec = L.csref_bsw(_ptr(out), _ptr(ref), _ptr(qer), out.shape[0], w, o_del, e_del, o_ins, e_ins, zdrop, end_bonus, _ptr(m), a, b, mode)
+    return out, float(sec)
+
+
+def ref_ksw_extend2(query: np.ndarray, target: np.ndarray, h0: int, w: int = 100, o_del=6, e_del=1, o_ins=6, e_ins=1, zdrop=100, end_bonus=5, a=1, b=4):
+    """ksw_extend2 of the reference (bwalib/ksw.c:380) for one pair: (score, qle, tle, gtle, gscore, max_off)."""
+    L = ref_lib()
+    L.csref_ksw_extend2.restype = C.c_int
+    L.csref_ksw_extend2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]
+    out5 = np.zeros(5, np.int32)
+    m = bsw_mat(a, b)
+    q = np.ascontiguousarray(query, np.uint8); t = np.ascontiguousarray(np.concatenate([target, np.zeros(1, np.uint8)]), np.uint8)
+    sc = L.csref_ksw_extend2(q.shape[0], _ptr(q), target.shape[0], _ptr(t), _ptr(m), o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, _ptr(out5))
+    return (int(sc),) + tuple(int(x) for x in out5)

@@ -26,6 +26,10 @@
 #include "FM_index/bwt.h"
 #include "FM_index/bntseq.h"
 #include "mapping/comp_seed.h"
+#include "mapping/bandedSWA.h"
+extern "C" {
+#include "bwalib/ksw.h"
+}
 
 thread_aux_t tprof; // comp_seed.cpp:22 expects the driver to define it (main.cpp:15)
 
@@ -417,6 +421,35 @@ void csref_result_free(void *rr)
 {
 	csref_result_t *r = (csref_result_t*)rr;
 	delete r->mem_off; delete r->seed_off; delete r->mems; delete r->rbeg; delete r;
+}
+
+
+// ---- banded Smith-Waterman extension: the reference's own batch entry points (mapping/bandedSWA.cpp) ----
+// mode 0: scalarBandedSWAWrapper (:242-260, == ksw_extend2 per pair); mode 1: getScores8; mode 2: getScores16 (the SIMD twins
+// mem_chain2aln_across_reads_V2 calls, comp_seed.cpp:1790,1859; they write into pairs[n .. roundup(n, SIMD width)), so the
+// batch is copied into a padded array first, as the caller's arrays are over-allocated by MAX_LINE_LEN, comp_seed.cpp:1491).
+// pairs: 14 int32 each == SeqPair (bandedSWA.h:91-99).  Returns seconds spent inside the reference call.
+double csref_bsw(int32_t *pairs, const uint8_t *seq_buf_ref, const uint8_t *seq_buf_qer, int n_pairs, int w,
+                 int o_del, int e_del, int o_ins, int e_ins, int zdrop, int end_bonus, const int8_t *mat, int w_match, int w_mismatch, int mode)
+{
+	static_assert(sizeof(SeqPair) == 14 * sizeof(int32_t), "SeqPair layout");
+	BandedPairWiseSW bsw(o_del, e_del, o_ins, e_ins, zdrop, end_bonus, mat, (int8_t)w_match, (int8_t)w_mismatch, 1);
+	std::vector<SeqPair> buf((size_t)n_pairs + 2 * MAX_LINE_LEN);
+	memcpy(buf.data(), pairs, (size_t)n_pairs * sizeof(SeqPair));
+	const auto t0 = std::chrono::steady_clock::now();
+	if (mode == 0) bsw.scalarBandedSWAWrapper(buf.data(), (uint8_t*)seq_buf_ref, (uint8_t*)seq_buf_qer, n_pairs, 1, w);
+	else if (mode == 1) bsw.getScores8(buf.data(), (uint8_t*)seq_buf_ref, (uint8_t*)seq_buf_qer, n_pairs, 1, w);
+	else bsw.getScores16(buf.data(), (uint8_t*)seq_buf_ref, (uint8_t*)seq_buf_qer, n_pairs, 1, w);
+	const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	memcpy(pairs, buf.data(), (size_t)n_pairs * sizeof(SeqPair));
+	return sec;
+}
+
+// ksw_extend2 itself (bwalib/ksw.c:380), the call of bwamem's mem_chain2aln (mapping/bwamem.c:720,746), for one pair
+int csref_ksw_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
+                      int w, int end_bonus, int zdrop, int h0, int *out5 /* qle tle gtle gscore max_off */)
+{
+	return ksw_extend2(qlen, query, tlen, target, 5, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, out5, out5 + 1, out5 + 2, out5 + 3, out5 + 4);
 }
 
 } // extern "C"
