@@ -27,9 +27,19 @@
 
 namespace {
 
+// sort key: query length (the width of a row), then target length (the number of rows) in steps of 8 -- the 32 pairs of a warp
+// should have the same shape
+#define BSW_KEY_BITS 26
 __global__ void k_bsw_keys(const PairIn *in, uint32_t n, uint32_t *keys, uint32_t *idx)
 {
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { keys[i] = (uint32_t)in[i].len2; idx[i] = i; }
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t t = (uint32_t)in[i].len1 >> 3;
+#ifdef BSW_KEY_QLEN_ONLY
+		keys[i] = (uint32_t)in[i].len2 << 9; idx[i] = i; (void)t;
+#else
+		keys[i] = ((uint32_t)in[i].len2 << 9) | (t > 511u ? 511u : t); idx[i] = i;
+#endif
+	}
 }
 
 } // namespace
@@ -39,6 +49,9 @@ struct cs_bsw {
 	cudaStream_t stream;
 	cudaEvent_t ev0, ev1;
 	uint32_t cap_pairs, n_pairs, max_qlen_staged;
+	int64_t max_h0_staged;   // of the staged batch: decides whether a DP cell fits 32 bits (EhCell)
+	bool neg_h0_staged;
+	int ctas_per_sm;         // resident 128-thread CTAs of the extension kernel per SM (cs_bsw_set_ctas_per_sm)
 	uint64_t cap_ref, cap_qer;
 	PairIn *h_in, *d_in;
 	int32_t *h_out, *d_out;
@@ -67,7 +80,7 @@ static int bsw_alloc_pairs(cs_bsw *b, uint32_t cap)
 	CK(cudaMalloc(&b->d_in, (size_t)cap * sizeof(PairIn))); CK(cudaMalloc(&b->d_out, (size_t)cap * 24));
 	CK(cudaMalloc(&b->d_keys, (size_t)cap * 4)); CK(cudaMalloc(&b->d_keys2, (size_t)cap * 4)); CK(cudaMalloc(&b->d_idx, (size_t)cap * 4)); CK(cudaMalloc(&b->d_order, (size_t)cap * 4));
 	b->sort_tmp_bytes = 0;
-	CK(cub::DeviceRadixSort::SortPairs(nullptr, b->sort_tmp_bytes, b->d_keys, b->d_keys2, b->d_idx, b->d_order, (int)cap, 0, 17, b->stream));
+	CK(cub::DeviceRadixSort::SortPairs(nullptr, b->sort_tmp_bytes, b->d_keys, b->d_keys2, b->d_idx, b->d_order, (int)cap, 0, BSW_KEY_BITS, b->stream));
 	CK(cudaMalloc(&b->d_sort_tmp, b->sort_tmp_bytes + 256));
 	b->cap_pairs = cap;
 	return CS_OK;
@@ -112,10 +125,13 @@ extern "C" cs_bsw_t *cs_bsw_create(int device, uint32_t max_pairs, uint64_t max_
 	CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
 	CK(cudaEventCreate(&b->ev0)); CK(cudaEventCreate(&b->ev1));
 	CK(cudaMalloc(&b->d_work, 4)); CK(cudaMalloc(&b->d_cells, 8));
+	// the DP rows live in L1: all of it (the kernel uses 100 bytes of shared memory)
+	CK(cudaFuncSetAttribute(k_bsw_extend<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+	CK(cudaFuncSetAttribute(k_bsw_extend<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
 	if (bsw_alloc_pairs(b, max_pairs) != CS_OK) goto fail;
 	if (bsw_alloc_seq(&b->h_ref, &b->d_ref, &b->cap_ref, std::max<uint64_t>(max_ref_bytes, 4096)) != CS_OK) goto fail;
 	if (bsw_alloc_seq(&b->h_qer, &b->d_qer, &b->cap_qer, std::max<uint64_t>(max_qer_bytes, 4096)) != CS_OK) goto fail;
-	b->eh_qlen = 0; b->eh_threads = 0; b->max_qlen_staged = max_qlen;
+	b->eh_qlen = 0; b->eh_threads = 0; b->max_qlen_staged = max_qlen; b->ctas_per_sm = 8;
 	return b;
 fail:
 	cs_bsw_free(b);
@@ -123,6 +139,13 @@ fail:
 }
 
 extern "C" uint64_t cs_bsw_launches(const cs_bsw_t *b) { return b ? b->n_launch : 0; }
+
+extern "C" int cs_bsw_set_ctas_per_sm(cs_bsw_t *b, int ctas_per_sm)
+{
+	if (!b || ctas_per_sm < 1 || ctas_per_sm > 16) return cs_set_err(CS_E_ARG, "ctas_per_sm outside [1, 16]");
+	b->ctas_per_sm = ctas_per_sm;
+	return CS_OK;
+}
 
 extern "C" int cs_bsw_stage(cs_bsw_t *b, const cs_seqpair_t *pairs, const uint8_t *seq_buf_ref, uint64_t ref_bytes, const uint8_t *seq_buf_qer, uint64_t qer_bytes, uint32_t n_pairs)
 {
@@ -133,7 +156,7 @@ extern "C" int cs_bsw_stage(cs_bsw_t *b, const cs_seqpair_t *pairs, const uint8_
 	if (n_pairs > b->cap_pairs && bsw_alloc_pairs(b, n_pairs + n_pairs / 4) != CS_OK) return CS_E_CUDA;
 	if (ref_bytes > b->cap_ref && bsw_alloc_seq(&b->h_ref, &b->d_ref, &b->cap_ref, ref_bytes + ref_bytes / 4) != CS_OK) return CS_E_CUDA;
 	if (qer_bytes > b->cap_qer && bsw_alloc_seq(&b->h_qer, &b->d_qer, &b->cap_qer, qer_bytes + qer_bytes / 4) != CS_OK) return CS_E_CUDA;
-	uint32_t mq = 1;
+	uint32_t mq = 1; int64_t mh = 0; bool neg = false;
 	for (uint32_t i = 0; i < n_pairs; ++i) {
 		const cs_seqpair_t &p = pairs[i];
 		if (p.len2 < 1 || p.len1 < 0 || p.idr < 0 || p.idq < 0 || (uint64_t)p.idr + (uint64_t)p.len1 > ref_bytes || (uint64_t)p.idq + (uint64_t)p.len2 > qer_bytes)
@@ -141,9 +164,11 @@ extern "C" int cs_bsw_stage(cs_bsw_t *b, const cs_seqpair_t *pairs, const uint8_
 			                  i, p.idr, p.len1, p.idq, p.len2, (unsigned long long)ref_bytes, (unsigned long long)qer_bytes);
 		b->h_in[i].idr = p.idr; b->h_in[i].idq = p.idq; b->h_in[i].len1 = p.len1; b->h_in[i].len2 = p.len2; b->h_in[i].h0 = p.h0;
 		if ((uint32_t)p.len2 > mq) mq = (uint32_t)p.len2;
+		if (p.h0 > mh) mh = p.h0;
+		if (p.h0 < 0) neg = true;
 	}
 	if (mq >= (1u << 17)) return cs_set_err(CS_E_ARG, "query of %u bases: longer than a read can be (65535, comp_seed.h:39)", mq);
-	b->max_qlen_staged = mq;
+	b->max_qlen_staged = mq; b->max_h0_staged = mh; b->neg_h0_staged = neg;
 	{
 		auto pinned = [](const void *p) { cudaPointerAttributes pa; const bool ok = cudaPointerGetAttributes(&pa, p) == cudaSuccess && pa.type == cudaMemoryTypeHost; cudaGetLastError(); return ok; };
 		const uint8_t *sr = seq_buf_ref, *sq = seq_buf_qer;
@@ -169,7 +194,7 @@ extern "C" int cs_bsw_run_staged(cs_bsw_t *b, int32_t w, const cs_bsw_opt_t *opt
 	{ const int rc = cs_use_device(b->device); if (rc != CS_OK) return rc; }
 	const uint32_t n = b->n_pairs;
 	// DP rows: one per resident thread, max_qlen + 1 columns; fewer threads for very long queries (2 GiB of scratch at most)
-	int grid = b->n_sm * 8;
+	int grid = b->n_sm * b->ctas_per_sm;
 	{
 		const uint64_t cols = (uint64_t)b->max_qlen_staged + 1;
 		while (grid > b->n_sm && (uint64_t)grid * 128 * cols * 8 > (2ull << 30)) grid -= b->n_sm;
@@ -196,10 +221,19 @@ extern "C" int cs_bsw_run_staged(cs_bsw_t *b, int32_t w, const cs_bsw_opt_t *opt
 		CK(cudaMemsetAsync(b->d_work, 0, 4, b->stream)); CK(cudaMemsetAsync(b->d_cells, 0, 8, b->stream));
 		k_bsw_keys<<<std::min<int>(b->n_sm * 8, (int)((n + 255) / 256)), 256, 0, b->stream>>>(b->d_in, n, b->d_keys, b->d_idx);
 		CK(cudaGetLastError()); ++b->n_launch;
-		CK(cub::DeviceRadixSort::SortPairs(b->d_sort_tmp, b->sort_tmp_bytes, b->d_keys, b->d_keys2, b->d_idx, b->d_order, (int)n, 0, 17, b->stream));
-		b->n_launch += 3;   // cub: histogram + onesweep passes of a 17-bit key
+		CK(cub::DeviceRadixSort::SortPairs(b->d_sort_tmp, b->sort_tmp_bytes, b->d_keys, b->d_keys2, b->d_idx, b->d_order, (int)n, 0, BSW_KEY_BITS, b->stream));
+		b->n_launch += 5;   // cub: histogram + onesweep passes of a 26-bit key
 		CK(cudaEventRecord(b->ev0, b->stream));
-		k_bsw_extend<<<grid, 128, 0, b->stream>>>(a);
+		// a cell holds two values in [0, h0 + qlen * max(mat)]: 16 bits each when that allows (negative h0 never does)
+		{
+#ifdef BSW_FORCE_WIDE
+			const bool wide = true;
+#else
+			const bool wide = b->neg_h0_staged || b->max_h0_staged + (int64_t)b->max_qlen_staged * (mx > 0 ? mx : 0) >= 65536;
+#endif
+			if (wide) k_bsw_extend<true><<<grid, 128, 0, b->stream>>>(a);
+			else k_bsw_extend<false><<<grid, 128, 0, b->stream>>>(a);
+		}
 		CK(cudaGetLastError()); ++b->n_launch;
 		CK(cudaEventRecord(b->ev1, b->stream));
 		CK(cudaMemcpyAsync(&b->h_cells, b->d_cells, 8, cudaMemcpyDeviceToHost, b->stream));

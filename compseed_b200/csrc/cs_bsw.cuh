@@ -12,7 +12,7 @@ struct BswArgs {
 	const uint32_t *order;      // pair indices sorted by query length
 	uint32_t n;
 	const uint8_t *ref, *qer;
-	int2 *eh; size_t eh_stride; // eh[j * eh_stride + thread]: {H(i-1, j-1), E(i, j)} of the row in progress
+	void *eh; size_t eh_stride; // DP rows, column j of a thread's row at [j * eh_stride + thread] (EhCell: 8 or 4 bytes per cell)
 	int32_t w, o_del, e_del, o_ins, e_ins, zdrop, end_bonus, max_mat;
 	int8_t mat[25];
 	int32_t *out;               // 6 per pair: score, tle, gtle, qle, gscore, max_off (the order of SeqPair)
@@ -20,10 +20,23 @@ struct BswArgs {
 	unsigned long long *cells;
 };
 
+// The DP row of a thread: cell j = {H(i-1, j-1), E(i, j)}.  Both are >= 0 and at most h0 + qlen * max(mat), so when that fits 16 bits
+// for every pair of a batch (always, for reads: h0 <= 65535 would need a 64 kbp seed) a cell is ONE 32-bit word, H in the low half.
+template <bool WIDE> struct EhCell;
+template <> struct EhCell<true>  { typedef int2 T;     static __device__ __forceinline__ T pack(int h, int e) { return make_int2(h, e); }
+                                   static __device__ __forceinline__ int h(T v) { return v.x; } static __device__ __forceinline__ int e(T v) { return v.y; }
+                                   static __device__ __forceinline__ bool zero(T v) { return (v.x | v.y) == 0; } };
+template <> struct EhCell<false> { typedef uint32_t T; static __device__ __forceinline__ T pack(int h, int e) { return (uint32_t)h | ((uint32_t)e << 16); }
+                                   static __device__ __forceinline__ int h(T v) { return (int)(v & 0xffffu); } static __device__ __forceinline__ int e(T v) { return (int)(v >> 16); }
+                                   static __device__ __forceinline__ bool zero(T v) { return v == 0; } };
+
 // ksw_extend2 (bwalib/ksw.c:380-479) for pair pid; eh: this thread's DP row, column j at eh[j * st]; s_mat: the 5 x 5 scores.
 // Returns the number of cells computed.
-__device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uint32_t pid, int2 *eh, size_t st, const int *s_mat)
+template <bool WIDE>
+__device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uint32_t pid, typename EhCell<WIDE>::T *eh, size_t st, const int *s_mat)
 {
+	typedef EhCell<WIDE> Cell;
+	typedef typename Cell::T cell_t;
 	const int o_del = a.o_del, e_del = a.e_del, o_ins = a.o_ins, e_ins = a.e_ins, oe_del = o_del + e_del, oe_ins = o_ins + e_ins, zdrop = a.zdrop;
 	unsigned long long cells = 0;
 	const PairIn p = a.in[pid];
@@ -33,11 +46,11 @@ __device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uin
 	// first row (ksw.c:395-398): H(-1, j); everything else of the row array is zero (calloc)
 	{
 		int h = h0 > oe_ins ? h0 - oe_ins : 0;
-		eh[0] = make_int2(h0, 0);
-		eh[st] = make_int2(h, 0);
+		eh[0] = Cell::pack(h0, 0);
+		eh[st] = Cell::pack(h, 0);
 		for (j = 2; j <= qlen; ++j) {
 			h = h > e_ins ? h - e_ins : 0;      // (once 0 <= e_ins the reference's loop stops and the rest stays 0)
-			eh[(size_t)j * st] = make_int2(h, 0);
+			eh[(size_t)j * st] = Cell::pack(h, 0);
 		}
 	}
 	// w no larger than what the scores allow (ksw.c:401-408)
@@ -59,10 +72,11 @@ __device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uin
 		if (end > qlen) end = qlen;
 		if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
 		else h1 = 0;
-		int2 *pe = eh + (size_t)beg * st;
+		cell_t *pe = eh + (size_t)beg * st;
+		// (fetching the next column's cell ahead of this column's store was tried: 4 x slower, profiles/r02_bsw_variants.txt)
 		for (j = beg; j < end; ++j, pe += st) { // ksw.c:421-447
-			const int2 v = *pe;
-			int M = v.x, e = v.y, h, t;
+			const cell_t v = *pe;
+			int M = Cell::h(v), e = Cell::e(v), h, t;
 			M = M ? M + q[query[j]] : 0;
 			h = M > e ? M : e;
 			h = h > f ? h : f;
@@ -70,13 +84,13 @@ __device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uin
 			m = m > h ? m : h;
 			t = M - oe_del; t = t > 0 ? t : 0;
 			e -= e_del; e = e > t ? e : t;
-			*pe = make_int2(h1, e);
+			*pe = Cell::pack(h1, e);
 			h1 = h;
 			t = M - oe_ins; t = t > 0 ? t : 0;
 			f -= e_ins; f = f > t ? f : t;
 		}
 		cells += (unsigned)(end > beg ? end - beg : 0);
-		eh[(size_t)end * st] = make_int2(h1, 0);   // (end, not where the loop stopped: the band can be empty, beg > end, once i - w passes the query)
+		eh[(size_t)end * st] = Cell::pack(h1, 0);   // (end, not where the loop stopped: the band can be empty, beg > end, once i - w passes the query)
 		if (j == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
 		if (m == 0) break;
 		if (m > max) {
@@ -88,9 +102,9 @@ __device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uin
 			else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break; }
 		}
 		// the band of the next row: the non-zero cells of this one (ksw.c:463-468)
-		for (j = beg; j < end; ++j) { const int2 v = eh[(size_t)j * st]; if (v.x != 0 || v.y != 0) break; }
+		for (j = beg; j < end; ++j) if (!Cell::zero(eh[(size_t)j * st])) break;
 		beg = j;
-		for (j = end; j >= beg; --j) { const int2 v = eh[(size_t)j * st]; if (v.x != 0 || v.y != 0) break; }
+		for (j = end; j >= beg; --j) if (!Cell::zero(eh[(size_t)j * st])) break;
 		end = j + 2 < qlen ? j + 2 : qlen;
 	}
 	int32_t *o = a.out + 6 * (size_t)pid;
@@ -98,6 +112,7 @@ __device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uin
 	return cells;
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(128) k_bsw_extend(BswArgs a)
 {
 	__shared__ int s_mat[25];
@@ -105,13 +120,14 @@ __global__ void __launch_bounds__(128) k_bsw_extend(BswArgs a)
 	__syncthreads();
 	const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
+	typename EhCell<WIDE>::T *const eh = reinterpret_cast<typename EhCell<WIDE>::T*>(a.eh) + gtid;
 	unsigned long long cells = 0;
-	for (;;) { // 32 pairs of similar query length per warp and trip
+	for (;;) { // 32 pairs of similar shape per warp and trip
 		unsigned int base = 0;
 		if (lane == 0) base = atomicAdd(a.work, 32u);
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= a.n) break;
-		if (base + lane < a.n) cells += bsw_one_pair(a, a.order[base + lane], a.eh + gtid, a.eh_stride, s_mat);
+		if (base + lane < a.n) cells += bsw_one_pair<WIDE>(a, a.order[a.n - 1 - (base + lane)], eh, a.eh_stride, s_mat);   // largest shapes first
 	}
 	if (cells) atomicAdd(a.cells, cells);
 }

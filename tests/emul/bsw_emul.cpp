@@ -28,7 +28,7 @@ extern "C" {
 
 // pairs: 14 int32 each (SeqPair); eh_stride > 1 exercises the interleaved row layout of the kernel.  Returns the cells computed.
 unsigned long long bsw_emul(int32_t *pairs, const uint8_t *ref, const uint8_t *qer, uint32_t n, int w, int o_del, int e_del, int o_ins, int e_ins,
-                            int zdrop, int end_bonus, const int8_t *mat, uint32_t eh_stride)
+                            int zdrop, int end_bonus, const int8_t *mat, uint32_t eh_stride, int wide)
 {
 	std::vector<PairIn> in(n);
 	std::vector<int32_t> out((size_t)n * 6);
@@ -48,7 +48,9 @@ unsigned long long bsw_emul(int32_t *pairs, const uint8_t *ref, const uint8_t *q
 	for (int k = 0; k < 25; ++k) { a.mat[k] = mat[k]; s_mat[k] = mat[k]; mx = mx > mat[k] ? mx : mat[k]; }
 	a.max_mat = mx;
 	unsigned long long cells = 0;
-	for (uint32_t i = 0; i < n; ++i) cells += bsw_one_pair(a, i, eh.data() + (i % eh_stride), eh_stride, s_mat);
+	for (uint32_t i = 0; i < n; ++i)
+		cells += wide ? bsw_one_pair<true>(a, i, eh.data() + (i % eh_stride), eh_stride, s_mat)
+		              : bsw_one_pair<false>(a, i, reinterpret_cast<uint32_t*>(eh.data()) + (i % eh_stride), eh_stride, s_mat);
 	for (uint32_t i = 0; i < n; ++i) for (int k = 0; k < 6; ++k) pairs[14 * (size_t)i + 8 + k] = out[6 * (size_t)i + k];
 	return cells;
 }
