@@ -64,7 +64,7 @@ int cs_use_device(int device)
 extern "C" void cs_index_config_default(cs_index_config_t *cfg)
 {
 	if (!cfg) return;
-	cfg->kmer_table_depth = -1; cfg->prune_k = -1; cfg->isa_intv = -1; cfg->reserved = 0;
+	cfg->kmer_table_depth = -1; cfg->prune_k = -1; cfg->isa_intv = -1; cfg->repeat_lengths = -1;
 }
 
 extern "C" void cs_ctx_config_default(cs_ctx_config_t *cfg)
@@ -84,6 +84,7 @@ static int cs_internal_build_text(cs_index *idx, const uint64_t *W)
 	int intv = idx->cfg.isa_intv < 0 ? 2 : idx->cfg.isa_intv, shift = 0;   // default 2: 4 more bytes per row than 4, 7 % off a cfg2 step (fewer LF steps after every inverse-SA lookup)
 	const uint64_t n = idx->d.seq_len;
 	idx->d.text = nullptr; idx->d.isa = nullptr; idx->d.isa_shift = 0; idx->d_text = nullptr; idx->d_isa = nullptr;
+	idx->d.rep = nullptr; idx->d_rep = nullptr;
 	if (intv <= 0 || idx->d.sa_mask != 0 || !W) return CS_OK;
 	while ((1 << shift) < intv) ++shift;
 	{
@@ -99,10 +100,21 @@ static int cs_internal_build_text(cs_index *idx, const uint64_t *W)
 		CK(cudaDeviceSynchronize());
 		idx->d.text = idx->d_text; idx->d.isa = idx->d_isa; idx->d.isa_shift = (uint32_t)shift;
 		idx->bytes += n_words * 8 + n_isa * 8;
+		if (idx->cfg.repeat_lengths != 0) { // repeat lengths: the suffix array's neighbours compared through the text (cs_device.cuh)
+			const uint64_t n_rep = ((n + 63) & ~63ull) + 64;   // k_seed_fast reads whole 8-byte words around a position
+			CK(cudaMalloc(&idx->d_rep, n_rep));
+			CK(cudaMemset(idx->d_rep, 0, n_rep));
+			k_rep_build<<<grid, 256>>>(idx->d, idx->d_rep);
+			CK(cudaGetLastError());
+			CK(cudaDeviceSynchronize());
+			idx->d.rep = idx->d_rep;
+			idx->bytes += n_rep;
+		}
 	}
 	return CS_OK;
 fail:
-	cudaFree(idx->d_text); cudaFree(idx->d_isa); idx->d_text = idx->d_isa = nullptr;
+	cudaFree(idx->d_text); cudaFree(idx->d_isa); cudaFree(idx->d_rep); idx->d_text = idx->d_isa = nullptr; idx->d_rep = nullptr;
+	idx->d.text = nullptr; idx->d.isa = nullptr; idx->d.rep = nullptr;
 	return CS_E_CUDA;
 }
 
@@ -406,7 +418,7 @@ extern "C" void cs_index_free(cs_index_t *idx)
 {
 	if (!idx) return;
 	cudaSetDevice(idx->device);
-	cudaFree(idx->d_buckets); cudaFree(idx->d_sa); cudaFree(idx->d_kt); cudaFree(idx->d_pt); cudaFree(idx->d_text); cudaFree(idx->d_isa);
+	cudaFree(idx->d_buckets); cudaFree(idx->d_sa); cudaFree(idx->d_kt); cudaFree(idx->d_pt); cudaFree(idx->d_text); cudaFree(idx->d_isa); cudaFree(idx->d_rep);
 	free(idx);
 }
 

@@ -12,7 +12,9 @@
 //   assembling four 64-bit counts.  One occ lookup == one 256-bit load (LDG.E.256) == one 32-byte sector.
 #pragma once
 #include <cstdint>
+#ifndef CS_EMUL   // tests/emul/seed_emul.cpp compiles this file as plain C++ (test infrastructure; never part of the library)
 #include <cuda_runtime.h>
+#endif
 
 struct DevIndex {
 	const uint4 *buckets;   // 2 x uint4 per bucket
@@ -40,6 +42,12 @@ struct DevIndex {
 	const uint64_t *text;
 	const uint64_t *isa;
 	uint32_t isa_shift;
+	// Repeat lengths (k_rep_build): rep[p] = the largest d such that T[p, p+d) occurs at least twice in T (as a prefix of
+	// two suffixes), capped at 255 = "255 or more".  With it a bwt_smem1a call that starts at a KNOWN text position (the
+	// second-pass call in the middle of a one-occurrence SMEM, bwamem.c:238-249) needs neither the FM-index nor the
+	// occurrence filter: its forward match is rep[p] bases long, and the K-mer windows inside the SMEM occur twice iff
+	// their rep is >= K.  One byte per text position.  NULL: not built (needs the dense SA and the text).
+	const uint8_t *rep;
 };
 
 
@@ -47,15 +55,18 @@ struct DevIndex {
 // shows L2 filling about four sectors per such request by default (lts__t_sectors_srcunit_tex_op_read ~ 3.7 x
 // lts__t_requests); nothing else of the 128-byte line is ever used, so the prefetch size is capped at 64 bytes,
 // the smallest PTX offers.  -DCS_L2_DEFAULT restores plain __ldg.
-#ifdef CS_L2_DEFAULT
+#if defined(CS_L2_DEFAULT) || defined(CS_EMUL)
 __device__ __forceinline__ uint32_t gather_u32(const uint32_t *p) { return __ldg(p); }
 __device__ __forceinline__ uint64_t gather_u64(const uint64_t *p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t gather_u8(const uint8_t *p) { return __ldg(p); }
 __device__ __forceinline__ uint4 gather_u128(const uint4 *p) { return __ldg(p); }
 #else
 __device__ __forceinline__ uint32_t gather_u32(const uint32_t *p)
 { uint32_t v; asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 __device__ __forceinline__ uint64_t gather_u64(const uint64_t *p)
 { uint64_t v; asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t gather_u8(const uint8_t *p)
+{ uint32_t v; asm volatile("ld.global.nc.L2::64B.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 __device__ __forceinline__ uint4 gather_u128(const uint4 *p)
 { uint4 v; asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
 #endif
@@ -75,8 +86,12 @@ __device__ __forceinline__ Bucket load_bucket(const DevIndex &I, uint64_t b)
 {
 	Bucket r;
 	const uint4 *p = I.buckets + 2 * b;
+#ifdef CS_EMUL
+	r.w0 = p[0].x; r.w1 = p[0].y; r.w2 = p[0].z; r.w3 = p[0].w; r.p1 = p[1].x; r.p2 = p[1].y; r.p3 = p[1].z; r.hi = p[1].w;
+#else
 	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 	             : "=r"(r.w0), "=r"(r.w1), "=r"(r.w2), "=r"(r.w3), "=r"(r.p1), "=r"(r.p2), "=r"(r.p3), "=r"(r.hi) : "l"(p));
+#endif
 	return r;
 }
 

@@ -11,6 +11,7 @@ struct cs_index {
 	uint4 *d_kt;            // top-of-search table (depths 1..d.kt_depth)
 	uint32_t *d_pt;         // occurrence filter (2-bit counts of all d.pt_k-mers)
 	uint64_t *d_text, *d_isa; // unique-match fast path: 2-bit text and sampled inverse SA
+	uint8_t *d_rep;         // repeat lengths (one byte per text position)
 	uint64_t bytes;
 	uint64_t bwt_size_ref;  // words of the reference layout
 	int sa_intv;

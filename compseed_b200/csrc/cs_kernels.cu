@@ -215,6 +215,31 @@ __global__ void k_isa_sample(DevIndex I, uint64_t *isa, uint32_t shift)
 	}
 }
 
+// Repeat lengths (DevIndex::rep) from the dense SA and the 2-bit text: suffix r shares max(lcp(r-1, r), lcp(r, r+1)) bases with
+// some other suffix, and no more.
+__device__ __forceinline__ uint32_t text_lcp(const DevIndex &I, uint64_t p, uint64_t q)   // common prefix of the suffixes p and q of T, capped at 255
+{
+	uint64_t room = I.seq_len - (p > q ? p : q);
+	if (room > 255) room = 255;
+	uint32_t n = 0;
+	while (n < room) {
+		const uint64_t diff = packed_window(I.text, p + n) ^ packed_window(I.text, q + n);
+		const uint32_t m = diff ? (uint32_t)(__ffsll((long long)diff) - 1) >> 1 : 32u;
+		n += m;
+		if (m < 32) break;
+	}
+	return n < room ? n : (uint32_t)room;
+}
+__global__ void k_rep_build(DevIndex I, uint8_t *rep)
+{
+	for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x + 1; r <= I.seq_len; r += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t p = I.sa[r];
+		const uint32_t a = r > 1 ? text_lcp(I, p, I.sa[r - 1]) : 0u;
+		const uint32_t b = r < I.seq_len ? text_lcp(I, p, I.sa[r + 1]) : 0u;
+		rep[p] = (uint8_t)(a > b ? a : b);
+	}
+}
+
 #define PT_CHUNK 256
 __global__ void k_pt_count(const uint64_t *W, uint64_t n, uint32_t K, uint32_t *pt)
 {
@@ -850,6 +875,9 @@ __device__ __forceinline__ uint32_t warp_take(uint32_t *ctr, bool want)
 __device__ __forceinline__ unsigned long long warp_alloc(unsigned long long *ctr, uint32_t cnt)
 {
 	const int lane = threadIdx.x & 31;
+#ifdef CS_EMUL   // one-lane warps (tests/emul/seed_emul.cpp)
+	return cnt ? atomicAdd(ctr, (unsigned long long)cnt) : 0ull;
+#endif
 	uint32_t incl = cnt;
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
@@ -906,6 +934,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 	uint32_t rd = 0; int len = 0;
 	int round = 1, x = 0;
 	uint32_t nmem = 0, old_n = 0, r2k = 0;
+	uint64_t p2done = 0;                                  // bit m: the second-pass call of my[m] has been dealt with where the SMEM was found (repeat lengths)
 
 	auto rd_word = [&](uint32_t wi) -> uint64_t { return s_rd[wi * CS_FAST_BLOCK + t]; };
 	auto nm_word = [&](uint32_t wi) -> uint32_t { return s_nm[wi * CS_FAST_BLOCK + t]; };
@@ -983,7 +1012,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 						s_rd[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.packed + w0 + wi) : 0ull;
 						s_nm[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.nmask + w0 + wi) : 0xffffffffu;
 					}
-					nmem = 0; round = 1; x = 0; have = true; last_q = 0xffffffffu;
+					nmem = 0; round = 1; x = 0; have = true; last_q = 0xffffffffu; p2done = 0;
 				}
 			}
 			bool finished = false;
@@ -995,8 +1024,9 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 				}
 				if (!active) {
 					while (r2k < old_n) { // second pass, bwamem.c:238-249
-						const uint4 v = reinterpret_cast<const uint4*>(my + r2k)[1];
-						++r2k;
+						const uint32_t k2 = r2k++;
+						if (k2 < 64 && ((p2done >> k2) & 1)) continue;           // answered when the SMEM was found
+						const uint4 v = reinterpret_cast<const uint4*>(my + k2)[1];
 						const int s = (int)v.w, e = (int)v.z;
 						const uint64_t sz = (uint64_t)v.x | ((uint64_t)v.y << 32);
 						if (e - s < opt.split_len || sz > (uint64_t)opt.split_width) continue;
@@ -1187,6 +1217,26 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		n_ext += r_ext; n_call += r_call;
 		if (end - (bi + 1) < opt.min_seed_len) continue;            // bwamem.c:231-233,247
 		STAT(11);
+		// ---- the second-pass call of this SMEM (bwamem.c:238-249: pivot in its middle, min_intv 2), answered here from the repeat
+		//      lengths when it can be: the SMEM has ONE occurrence, at text position tb, so q == T there.  The call's forward
+		//      match is R = rep[pivot's text position] bases long if that ends inside the SMEM (its interval holds >= 2 rows up
+		//      to R bases, one row after); the K-mer windows that decide which shorter matches the literal pass would push
+		//      (probe_bits above) lie inside the SMEM too when the pivot is >= K-1 bases from its start, and occur twice iff their
+		//      own rep is >= K.  Neither the FM-index nor the filter is read.  The loads are issued now and used after the
+		//      inverse-SA lookups below. ----
+		bool p2_try = false; int cx2 = 0; uint32_t ro = 0;
+		uint64_t rw0 = 0, rw1 = 0, rw2 = 0, rw3 = 0;
+		if (I.rep && round == 1 && nmem < 64 && end - (bi + 1) >= opt.split_len && opt.split_width >= 1) {
+			cx2 = (bi + 1 + end) >> 1;
+			if (cx2 - (bi + 1) >= K - 1) {
+				const uint64_t lo = tb + (uint64_t)(cx2 - (bi + 1)) - (uint64_t)(K - 1);   // text position of the first window, q[cx2+1-K, cx2+1)
+				const uint64_t *rp = reinterpret_cast<const uint64_t*>(I.rep) + (lo >> 3);
+				ro = (uint32_t)lo & 7;                                                       // (K + 7 <= 32 bytes: four words always hold them)
+				rw0 = gather_u64(rp); rw1 = gather_u64(rp + 1); rw2 = gather_u64(rp + 2); rw3 = gather_u64(rp + 3);
+				n_req += 1u + ((((uint32_t)lo & 31) + (uint32_t)K > 32u) ? 1u : 0u);        // sectors
+				p2_try = true;
+			}
+		}
 		// ---- the coordinates that moved by text comparison: x[0] backward, x[1] forward ----
 		{
 			int w0 = 0, w1 = 0;
@@ -1196,6 +1246,26 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 				if (w0) { c0 = dev_lf(I, c0); --w0; ++n_req; }
 				if (w1) { c1 = dev_lf(I, c1); --w1; ++n_req; }
 			}
+		}
+		if (p2_try) {
+			const uint32_t Kq = (uint32_t)K * 0x01010101u;
+			auto ge_k = [&](uint64_t w) -> uint32_t {   // bit i: byte i of w >= K
+				const uint32_t lo = (__vcmpgeu4((uint32_t)w, Kq) >> 7) & 0x01010101u, hi = (__vcmpgeu4((uint32_t)(w >> 32), Kq) >> 7) & 0x01010101u;
+				return (((lo * 0x01020408u) >> 24) & 0xfu) | ((((hi * 0x01020408u) >> 24) & 0xfu) << 4);
+			};
+			const uint32_t flags = (ge_k(rw0) | (ge_k(rw1) << 8) | (ge_k(rw2) << 16) | (ge_k(rw3) << 24)) >> ro;   // bit j: the window of e = j + 1 occurs twice
+			const uint32_t ri = ro + (uint32_t)K - 1u;
+			const uint64_t rw = ri < 8 ? rw0 : ri < 16 ? rw1 : ri < 24 ? rw2 : rw3;
+			const int R = (int)((rw >> (8 * (ri & 7))) & 0xff);
+			if (R >= 1 && R < 255 && R < end - cx2) { // the forward match of the call is q[cx2, cx2+R), and it fails on a base of the read
+				const uint32_t km = R < K ? flags & ((1u << R) - 1u) : 0u;
+				bool done = true;
+				if (R < K && km == 0) { STAT(12); n_ext += (uint32_t)R; }              // nothing pushable: the call returns no SMEM
+				else if (pend_y != 0) done = false;                                     // (one call can wait to be queued: the regular path takes this one)
+				else if (R < K && __popc(km) <= CS_WALK_MAX) { STAT(13); pend_y = (uint32_t)cx2 | (2u << 16) | ((uint32_t)R << 18) | 0x80000000u; pend_z = 2u; pend_bits = km; }
+				else { STAT(14); pend_y = (uint32_t)cx2 | (2u << 16); pend_z = 2u; }
+				if (done) p2done |= 1ull << nmem;
+			} else STAT(15);
 		}
 		{
 			uint4 *p = reinterpret_cast<uint4*>(my + nmem);
@@ -1829,6 +1899,7 @@ __global__ void k_compact_results(const uint32_t *n_mems_ptr, uint64_t mems_cap,
 // ---------------------------------------------------------------------------------------------
 // Independent uniformly random granule-sized loads over a table: the random-sector roofline.
 // `unroll` independent loads are issued back to back per thread before any of them is consumed.
+#ifndef CS_EMUL
 template <int UNROLL>
 __device__ __forceinline__ void gather_body(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads,
                                             uint64_t seed, unsigned long long *sink)
@@ -1869,6 +1940,7 @@ __global__ void k_gather_probe(const uint4 *table, uint64_t n_granules, uint32_t
 __global__ void k_gather_probe4(const uint4 *table, uint64_t n_granules, uint32_t granule16, uint64_t n_loads, uint64_t seed,
                                 unsigned long long *sink)
 { gather_body<4>(table, n_granules, granule16, n_loads, seed, sink); }
+#endif
 
 __global__ void k_fill(uint4 *p, uint64_t n, uint32_t v)
 {

@@ -105,6 +105,8 @@ __global__ void k_kt_build(DevIndex I, uint4 *kt, uint32_t d);
 __global__ void k_text_from_index(DevIndex I, unsigned long long *W);
 __global__ void k_text_lsb(const uint64_t *W, uint64_t n_words, uint64_t *out);
 __global__ void k_isa_sample(DevIndex I, uint64_t *isa, uint32_t shift);
+#define CS_HAVE_REP 1
+__global__ void k_rep_build(DevIndex I, uint8_t *rep);
 __global__ void k_pt_count(const uint64_t *W, uint64_t n, uint32_t K, uint32_t *pt);
 __global__ void k_pack_reads(const uint8_t *bases, const uint32_t *off, uint32_t n_reads, uint64_t *packed, uint32_t *nmask);
 __global__ void k_unpack_reads(const uint64_t *packed, const uint32_t *nmask, const uint32_t *off, uint32_t n_reads, uint8_t *bases, uint32_t off_bias);

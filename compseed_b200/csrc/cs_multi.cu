@@ -563,7 +563,7 @@ extern "C" cs_index_t *cs_index_replicate(const cs_index_t *src, int device)
 	if (!idx) { cs_set_err(CS_E_ARG, "out of host memory"); return nullptr; }
 	*idx = *src;
 	idx->device = device;
-	idx->d_buckets = nullptr; idx->d_sa = nullptr; idx->d_kt = nullptr; idx->d_pt = nullptr; idx->d_text = nullptr; idx->d_isa = nullptr;
+	idx->d_buckets = nullptr; idx->d_sa = nullptr; idx->d_kt = nullptr; idx->d_pt = nullptr; idx->d_text = nullptr; idx->d_isa = nullptr; idx->d_rep = nullptr;
 	{
 		int can = 0;
 		if (device != src->device && cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
@@ -586,12 +586,14 @@ extern "C" cs_index_t *cs_index_replicate(const cs_index_t *src, int device)
 		CK(clone((void**)&idx->d_pt, S.pt, S.pt ? ((1ull << (2 * S.pt_k)) / 16) * 4 : 0));
 		CK(clone((void**)&idx->d_text, S.text, S.text ? ((S.seq_len + 31) / 32 + 2) * 8 : 0));
 		CK(clone((void**)&idx->d_isa, S.isa, S.isa ? ((S.seq_len >> S.isa_shift) + 2) * 8 : 0));
+		CK(clone((void**)&idx->d_rep, S.rep, S.rep ? ((S.seq_len + 63) & ~63ull) + 64 : 0));
 		CK(cudaDeviceSynchronize());
+		idx->d.rep = idx->d_rep;
 		idx->d.buckets = idx->d_buckets; idx->d.sa = idx->d_sa; idx->d.kt = idx->d_kt; idx->d.pt = idx->d_pt; idx->d.text = idx->d_text; idx->d.isa = idx->d_isa;
 	}
 	return idx;
 fail:
-	cudaFree(idx->d_buckets); cudaFree(idx->d_sa); cudaFree(idx->d_kt); cudaFree(idx->d_pt); cudaFree(idx->d_text); cudaFree(idx->d_isa);
+	cudaFree(idx->d_buckets); cudaFree(idx->d_sa); cudaFree(idx->d_kt); cudaFree(idx->d_pt); cudaFree(idx->d_text); cudaFree(idx->d_isa); cudaFree(idx->d_rep);
 	free(idx);
 	return nullptr;
 }

@@ -196,6 +196,37 @@ __global__ void k_verify_table(DevIndex I, uint64_t n_samples, unsigned long lon
 	if (bad) atomicAdd(out + 11, bad);
 }
 
+// repeat lengths by their definition, with the FM-index instead of the suffix array's neighbours: T[p, p+R) must have at
+// least two occurrences (backward search over its R bases), T[p, p+R+1) exactly one (unless R is the cap or the text ends)
+__global__ void k_verify_rep(DevIndex I, uint64_t n_samples, unsigned long long *out)
+{
+	unsigned long long n = 0, bad = 0;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_samples; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t h = mix64(i * 0xA24BAED4963EE407ull + 4242);
+		const uint64_t p = (uint64_t)(((unsigned __int128)h * I.seq_len) >> 64);
+		const uint32_t R = I.rep[p];
+		++n;
+		if (p + R > I.seq_len) { ++bad; continue; }
+		const bool more = R < 255 && p + R < I.seq_len;              // the string one base longer exists and is not capped
+		const uint32_t len = R + (more ? 1u : 0u);
+		if (len == 0) continue;
+		// backward search over T[p, p+len): occurrences of every suffix of it; the count of T[p, p+len) is the last one,
+		// that of T[p+1, ...) irrelevant -- so search the REVERSED roles: forward extension from T[p] (bwt.c:309)
+		int b = (int)text_base(I, p);
+		uint64_t x0 = l2_at(I, b) + 1, x1 = l2_at(I, 3 - b) + 1, x2 = l2_at(I, b + 1) - l2_at(I, b), at_R = R == 1 ? x2 : 0;
+		for (uint32_t j = 1; j < len && x2 > 0; ++j) {
+			uint64_t o0, o1, o2; uint32_t two;
+			dev_extend(I, x0, x1, x2, 3 - (int)text_base(I, p + j), 0, o0, o1, o2, two);
+			x0 = o0; x1 = o1; x2 = o2;
+			if (j + 1 == R) at_R = x2;
+		}
+		if (R >= 1 && at_R < 2) ++bad;
+		else if (more && x2 != 1) ++bad;
+	}
+	if (n) atomicAdd(out + 14, n);
+	if (bad) atomicAdd(out + 15, bad);
+}
+
 // a chunk of the forward strand as the caller holds it (nt4 bytes): T[p] == fwd[p], T[2 l_pac - 1 - p] == 3 - fwd[p]
 __global__ void k_verify_text(DevIndex I, const uint8_t *chunk, uint64_t p0, uint64_t n_chunk, uint64_t l_pac, unsigned long long *out)
 {
@@ -213,7 +244,7 @@ __global__ void k_verify_text(DevIndex I, const uint8_t *chunk, uint64_t p0, uin
 }
 
 // random 32-byte sectors over several arrays at once: load i picks array a with probability size_a / total
-struct ProbeArrays { const uint4 *base[6]; uint64_t cum[7]; uint64_t total; int n; };   // cum: cumulative sizes in 32-byte sectors
+struct ProbeArrays { const uint4 *base[7]; uint64_t cum[8]; uint64_t total; int n; };   // cum: cumulative sizes in 32-byte sectors
 
 template <int UNROLL>
 __global__ void k_index_gather(ProbeArrays A, uint64_t n_loads, uint64_t seed, unsigned long long *sink)
@@ -230,7 +261,7 @@ __global__ void k_index_gather(ProbeArrays A, uint64_t n_loads, uint64_t seed, u
 			uint64_t g = (uint64_t)(((unsigned __int128)s * total) >> 64);
 			const uint4 *bp = A.base[0]; uint64_t c0 = 0;          // (selects, not a run-time index into the parameter struct)
 #pragma unroll
-			for (int j = 1; j < 6; ++j) if (g >= A.cum[j] && A.cum[j + 1] > A.cum[j]) { bp = A.base[j]; c0 = A.cum[j]; }
+			for (int j = 1; j < 7; ++j) if (g >= A.cum[j] && A.cum[j + 1] > A.cum[j]) { bp = A.base[j]; c0 = A.cum[j]; }
 			const uint4 *p = bp + 2 * (g - c0);
 			asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a[u]), "=l"(b[u]), "=l"(c[u]), "=l"(d[u]) : "l"(p));
 		}
@@ -271,6 +302,7 @@ extern "C" int cs_index_verify(const cs_index_t *idx, const uint8_t *fwd, uint64
 			const uint64_t n_samples = std::max<uint64_t>(1u << 16, std::min<uint64_t>(I.seq_len / stride, 1ull << 24));
 			if (I.pt && I.pt_k >= 2 && I.seq_len > I.pt_k) { k_verify_filter<<<grid, 256>>>(I, n_samples, d_out); CK(cudaGetLastError()); }
 			if (I.kt && I.kt_depth >= 1 && I.seq_len > I.kt_depth) { k_verify_table<<<grid, 256>>>(I, n_samples, d_out); CK(cudaGetLastError()); }
+			if (I.rep) { k_verify_rep<<<grid, 256>>>(I, n_samples, d_out); CK(cudaGetLastError()); }
 		}
 		if (fwd) {
 			const uint64_t chunk = 256ull << 20;
@@ -310,7 +342,8 @@ extern "C" int cs_probe_index_gather(const cs_index_t *idx, uint64_t n_loads, in
 		if (I.text) add(I.text, ((I.seq_len + 31) / 32) * 8);
 		if (I.isa) add(I.isa, ((I.seq_len >> I.isa_shift) + 1) * 8);
 		if (I.kt) add(I.kt, (((1ull << (2 * (I.kt_depth + 1))) - 4) / 3) * 16);
-		for (int k = A.n; k < 6; ++k) { A.base[k] = A.base[0]; A.cum[k + 1] = A.cum[A.n]; }
+		if (I.rep) add(I.rep, I.seq_len & ~31ull);
+		for (int k = A.n; k < 7; ++k) { A.base[k] = A.base[0]; A.cum[k + 1] = A.cum[A.n]; }
 		A.total = A.cum[A.n];
 	}
 	CK(cudaMalloc(&d_sink, 8));

@@ -115,7 +115,7 @@ class ChainResult:
 
 
 class _IndexConfig(C.Structure):
-    _fields_ = [("kmer_table_depth", C.c_int32), ("prune_k", C.c_int32), ("isa_intv", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("kmer_table_depth", C.c_int32), ("prune_k", C.c_int32), ("isa_intv", C.c_int32), ("repeat_lengths", C.c_int32)]
 
 
 class _CtxConfig(C.Structure):
@@ -141,9 +141,10 @@ class IndexConfig:
     kmer_table_depth: int = -1
     prune_k: int = -1
     isa_intv: int = -1
+    repeat_lengths: int = -1
 
     def _c(self) -> _IndexConfig:
-        return _IndexConfig(self.kmer_table_depth, self.prune_k, self.isa_intv, 0)
+        return _IndexConfig(self.kmer_table_depth, self.prune_k, self.isa_intv, self.repeat_lengths)
 
 
 @dataclass
@@ -355,7 +356,7 @@ class FMIndex:
         _check(load_library().cs_index_write(self.h, prefix.encode(), sa_intv))
 
     VERIFY_FIELDS = ("order_rows", "order_bad", "bwt_rows", "bwt_bad", "perm_bad", "occ_bad", "isa_samples", "isa_bad",
-                     "filter_samples", "filter_bad", "table_samples", "table_bad", "text_bases", "text_bad")
+                     "filter_samples", "filter_bad", "table_samples", "table_bad", "text_bases", "text_bad", "rep_samples", "rep_bad")
 
     def verify(self, fwd: np.ndarray | None = None, stride: int = 1) -> dict:
         """cs_index_verify: the index checked against the definitions of its parts (needs the dense SA)."""

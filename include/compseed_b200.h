@@ -151,7 +151,9 @@ typedef struct {
 	int32_t prune_k;           /* K of the K-mer occurrence filter (default ceil(log4 seq_len)+2, at most 19); 0 = none */
 	int32_t isa_intv;          /* sampling of the inverse SA used by the unique-match paths (power of two, default 2); 0 = no
 	                              2-bit text / inverse SA (the fast kernels are then not used) */
-	int32_t reserved;
+	int32_t repeat_lengths;    /* 1 (default -1 = 1): one byte per text position, the length of the longest repeat starting there
+	                              (second-pass calls inside a one-occurrence SMEM then read neither the FM-index nor the filter); 0 = none.
+	                              Needs the 2-bit text (isa_intv > 0) */
 } cs_index_config_t;
 void cs_index_config_default(cs_index_config_t *cfg);
 
@@ -207,6 +209,7 @@ cs_index_t *cs_index_build_ex(const uint8_t *fwd, uint64_t l_pac, int device, in
  *   out[8] K-mers checked: filter count == min(3, occurrences by backward search), out[9] violations
  *   out[10] top-of-search entries checked against bwt_extend from scratch,        out[11] violations
  *   out[12] text bases compared with fwd / revcomp(fwd) (when fwd != NULL),        out[13] mismatches
+ *   out[14] repeat lengths checked (T[p, p+R) occurs twice, one base more once),  out[15] violations
  * Needs the dense SA and the 2-bit text.  stride: every stride-th row / sample (1 = all).  Returns CS_OK when it ran;
  * the caller looks at the violation counts. */
 int cs_index_verify(const cs_index_t *idx, const uint8_t *fwd, uint64_t l_pac, uint32_t stride, uint64_t out[16]);

@@ -395,6 +395,22 @@ static int smem1(work_t *w, int len, const uint8_t *q, int x, uint64_t min_intv)
 	return ret;
 }
 
+/* ONE bwt_smem1a call for test harnesses (tests/emul/seed_emul.cpp resolves the calls the device kernels defer with it):
+ * the SMEMs of the call, unfiltered, sorted by start, into out[cap]; returns their number (-1: cap too small), *ret = next pivot. */
+int cso_smem1_call(const cso_index_t *idx, int len, const uint8_t *q, int x, uint64_t min_intv, cso_mem_t *out, int cap, int *ret)
+{
+	work_t w;
+	int r, n;
+	memset(&w, 0, sizeof w);
+	w.idx = idx;
+	r = smem1(&w, len, q, x, min_intv);
+	if (ret) *ret = r;
+	n = (int)w.mem1.n;
+	if (n <= cap) memcpy(out, w.mem1.a, (size_t)n * sizeof(cso_mem_t)); else n = -1;
+	free(w.prev.a); free(w.curr.a); free(w.mem1.a);
+	return n;
+}
+
 /* bwt_seed_strategy1 (bwt.c:358-379) */
 static int seed_strategy1(work_t *w, int len, const uint8_t *q, int x, int min_len, int max_intv, cso_mem_t *mem)
 {

@@ -2,7 +2,7 @@
 # quick ncu counters of every kernel of one bench step (current build); usage: scripts/ncu_all.sh TAG [reads]
 M=smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum,gpu__time_duration.sum,dram__sectors_read.sum,dram__sectors_write.sum,lts__t_sector_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.per_cycle_active,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,launch__grid_size,launch__registers_per_thread
 TAG=$1; READS=${2:-2000000}
-CMD="python bench.py --reads $READS --steps 1 --warmup 1 --no-cpu --no-e2e"
+CMD="python bench.py --reads $READS --steps 1 --warmup 1 --no-cpu --no-e2e --no-probe --verify-stride 0"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 && ncu --metrics $M --clock-control none -k regex:'k_seed|k_collect|k_mem_counts|k_sa_resolve|k_pack|DeviceScan' -s 13 -c 13 --csv --log-file gpurun_out/q_$TAG.csv $CMD > gpurun_out/ncu_$TAG.log 2>&1
 python - "$TAG" "$READS" <<'PY'
 import csv, sys

@@ -277,7 +277,7 @@ def test_result_neutral_caches_can_be_switched_off(cuda_lib, oracle_lib):
             "all_dense": (1, IC(), CC()), "all_dense_tiny_queue": (1, IC(), CC(defer_cap=7)), "all_dense_nofast": (1, IC(), CC(use_fast=0)),
             "all_dense_r3slow": (1, IC(), CC(use_r3_fast=0)), "all_dense_k12": (1, IC(prune_k=12, kmer_table_depth=9), CC()),
             "all_dense_serial": (1, IC(), CC(overlap_streams=1)), "all_dense_r3slow_serial": (1, IC(), CC(use_r3_fast=0, overlap_streams=1)),
-            "all_dense_isa4": (1, IC(isa_intv=4), CC()),
+            "all_dense_isa4": (1, IC(isa_intv=4), CC()), "all_dense_norep": (1, IC(repeat_lengths=0), CC()),
             "all_dense_l2window": (1, IC(), CC(l2_persist_mb=16)), "all_dense_litcap": (1, IC(), CC(lit_ctas_per_sm=1)),
             "all_dense_prefetch": (1, IC(), CC(prefetch_results=1))}.items():
         idx = cuda_lib.FMIndex.upload(oi.primary, oi.L2, oi.seq_len, oi.bwt, oi.sa, oi.sa_intv, dense_sa_intv=dense, config=icfg)
@@ -298,3 +298,5 @@ def test_result_neutral_caches_can_be_switched_off(cuda_lib, oracle_lib):
     # a queue too small for the batch: rerun through the literal kernel alone, same answer (checked above)
     assert results["all_dense_tiny_queue"]["ext_queries"] == results["all_dense_nofast"]["ext_queries"]
     assert results["all_dense_serial"] == results["all_dense"]
+    # repeat lengths: second-pass calls inside one-occurrence SMEMs read neither the FM-index nor the filter
+    assert results["all_dense"]["ext_calls"] < results["all_dense_norep"]["ext_calls"]
