@@ -934,6 +934,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 	uint32_t rd = 0; int len = 0;
 	int round = 1, x = 0;
 	uint32_t nmem = 0, old_n = 0, r2k = 0;
+	long long diag = 0; bool have_diag = false; int junk_at = -1;   // diagonal of the last one-occurrence SMEM this lane stored for the read; where its forward match failed on a base
 	uint64_t p2done = 0;                                  // bit m: the second-pass call of my[m] has been dealt with where the SMEM was found (repeat lengths)
 
 	auto rd_word = [&](uint32_t wi) -> uint64_t { return s_rd[wi * CS_FAST_BLOCK + t]; };
@@ -1012,7 +1013,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 						s_rd[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.packed + w0 + wi) : 0ull;
 						s_nm[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.nmask + w0 + wi) : 0xffffffffu;
 					}
-					nmem = 0; round = 1; x = 0; have = true; last_q = 0xffffffffu; p2done = 0;
+					nmem = 0; round = 1; x = 0; have = true; last_q = 0xffffffffu; p2done = 0; have_diag = false; junk_at = -1;
 				}
 			}
 			bool finished = false;
@@ -1087,42 +1088,77 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		};
 
 		// ---- forward pass (bwt.c:304-321) without pushes: until the match is one occurrence, dies, or hits an N / the end ----
-		uint64_t c0, c1, c2;
-		{
-			const int b = base_at(cx);
-			c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);   // bwt_set_intv, bwt.h:82
-		}
+		uint64_t c0 = 0, c1 = 0, c2 = 1;
 		int i = cx + 1, udepth = 0;                                 // udepth: bases after which one occurrence was left
-		bool unique = false;
-		if (!has_n(cx, kd)) { // q[cx, cx+kd) is inside the read and unambiguous: its table entry directly
-			uint64_t o0, o1, o2;
-			kt_lookup(I, (uint32_t)kd, key_of(cx, kd), o0, o1, o2); ++n_req;
-			if (o2 >= cmin) { c0 = o0; c1 = o1; c2 = o2; i = cx + kd; r_ext += (uint32_t)(kd - 1); }
+		bool unique = false, spec = false, fwd_go = true;
+		uint64_t tp0 = 0, bw0 = 0, tpos = 0; int jf = 0; uint32_t cnt0 = 0;
+		// First-pass calls, speculatively: a read with substitutions continues on the DIAGONAL (text position minus read position)
+		// of its last one-occurrence match.  If q[cx, ..) equals the text there for more than R = rep[that position] bases, the
+		// match is one occurrence from R + 1 bases on -- at that very position -- and everything the FM-index would have been
+		// asked (table jump, extends down to one row, the SA gather) is known: three independent gathers (repeat length, text
+		// window, the window before it for the backward pass) instead of a chain of five to eight.  The rows of the SMEM come
+		// from the inverse SA at the end, as for every match followed through the text.  Not tried at the position where the
+		// last match failed on a base (q differs from the text there by construction).
+		if (CS_SPEC_DIAG && I.rep && cmin == 1 && have_diag && cx != junk_at) {
+			const long long pp = diag + cx;
+			if (pp >= 0 && (unsigned long long)pp < I.seq_len) {
+				const uint64_t p1 = (uint64_t)pp;
+				const uint32_t R = gather_u8(I.rep + p1);
+				const uint64_t win = packed_window(I.text, p1);
+				cnt0 = 32; if ((uint32_t)cx < cnt0) cnt0 = (uint32_t)cx; if (p1 < cnt0) cnt0 = (uint32_t)p1;
+				if (cnt0) bw0 = packed_window(I.text, p1 - cnt0);
+				n_req += 2u + ((p1 & 31) != 0) + (cnt0 ? 1u + (((p1 - cnt0) & 31) != 0) : 0u);
+				const uint64_t diff = read_window(cx) ^ win;
+				const uint32_t nmw = nmask_window(cx);
+				uint32_t m = diff ? (uint32_t)(__ffsll((long long)diff) - 1) >> 1 : 32u;
+				const uint32_t nn = nmw ? (uint32_t)__ffs((int)nmw) - 1u : 32u;
+				const uint64_t lft = I.seq_len - p1;
+				if (nn < m) m = nn;
+				if (lft < m) m = (uint32_t)lft;
+				if (R < 255u && m >= R + 1u) {
+					STAT(7);
+					spec = true; unique = true; udepth = (int)R + 1; tp0 = p1;
+					i = cx + (int)m; jf = (int)m; tpos = p1 + m; fwd_go = m == 32u;
+				} else STAT(9);
+			}
 		}
-		for (;;) {
-			if (c2 == 1 && cmin == 1) { unique = true; udepth = i - cx; break; }
-			const int b = i < len ? base_at(i) : 4;
-			if (b > 3) break;
-			const int new_len = i + 1 - cx;
-			uint64_t o0, o1, o2;
-			++r_ext;
-			if (new_len <= kd) { kt_lookup(I, (uint32_t)new_len, key_of(cx, new_len), o0, o1, o2); ++n_req; }
-			else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - b, 0, o0, o1, o2, two); ++r_call; n_two += two; n_req += 1u + two; }
-			if (o2 < cmin) break;                                   // bwt.c:313: this extension fails, the match ends at i
-			c0 = o0; c1 = o1; c2 = o2; ++i;
+		if (!spec) {
+			{
+				const int b = base_at(cx);
+				c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);   // bwt_set_intv, bwt.h:82
+			}
+			if (!has_n(cx, kd)) { // q[cx, cx+kd) is inside the read and unambiguous: its table entry directly
+				uint64_t o0, o1, o2;
+				kt_lookup(I, (uint32_t)kd, key_of(cx, kd), o0, o1, o2); ++n_req;
+				if (o2 >= cmin) { c0 = o0; c1 = o1; c2 = o2; i = cx + kd; r_ext += (uint32_t)(kd - 1); }
+			}
+			for (;;) {
+				if (c2 == 1 && cmin == 1) { unique = true; udepth = i - cx; break; }
+				const int b = i < len ? base_at(i) : 4;
+				if (b > 3) break;
+				const int new_len = i + 1 - cx;
+				uint64_t o0, o1, o2;
+				++r_ext;
+				if (new_len <= kd) { kt_lookup(I, (uint32_t)new_len, key_of(cx, new_len), o0, o1, o2); ++n_req; }
+				else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - b, 0, o0, o1, o2, two); ++r_call; n_two += two; n_req += 1u + two; }
+				if (o2 < cmin) break;                                   // bwt.c:313: this extension fails, the match ends at i
+				c0 = o0; c1 = o1; c2 = o2; ++i;
+			}
+			if (unique) {
+				tp0 = gather_u64(I.sa + c0); ++n_req;                        // text position of q[cx]
+				// the text before the occurrence is wanted by the backward pass below: fetch its first window together with the forward one
+				cnt0 = 32; if ((uint32_t)cx < cnt0) cnt0 = (uint32_t)cx; if (tp0 < cnt0) cnt0 = (uint32_t)tp0;
+				if (cnt0) { bw0 = packed_window(I.text, tp0 - cnt0); n_req += 1u + (((tp0 - cnt0) & 31) != 0); }
+				tpos = tp0 + (uint64_t)(i - cx);
+			}
 		}
 		// unique from here on: compare against the text at the occurrence, 32 bases per step
-		uint64_t tp0 = 0, bw0 = 0; int jf = 0; uint32_t cnt0 = 0;
+		int fail_at = -1;                                           // where the text comparison failed on a base of the read
 		if (unique) {
-			tp0 = gather_u64(I.sa + c0); ++n_req;                        // text position of q[cx]
-			// the text before the occurrence is wanted by the backward pass below: fetch its first window together with the forward one
-			cnt0 = 32; if ((uint32_t)cx < cnt0) cnt0 = (uint32_t)cx; if (tp0 < cnt0) cnt0 = (uint32_t)tp0;
-			if (cnt0) { bw0 = packed_window(I.text, tp0 - cnt0); n_req += 1u + (((tp0 - cnt0) & 31) != 0); }
-			uint64_t tpos = tp0 + (uint64_t)(i - cx);
 			// CS_FWD_WIN windows of 32 bases are fetched per trip (all their loads in flight together).  More than one looked
 			// attractive (at 1 % substitutions a unique match runs on for ~100 bases, and the trip count differs from lane to
 			// lane) but measured slower: see CS_FWD_WIN in cs_kernels.cuh.
-			for (bool go = true; go; ) {
+			for (bool go = fwd_go; go; ) {
 				const uint64_t left = I.seq_len - tpos;
 				uint64_t room = (uint64_t)(len - i); if (left < room) room = left;            // bases that can still match
 				const uint32_t nwin = room >= 32u * CS_FWD_WIN ? (uint32_t)CS_FWD_WIN : (uint32_t)((room + 31) >> 5);
@@ -1148,7 +1184,9 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 					if (m < 32) go = false;
 				}
 			}
-			r_ext += (uint32_t)jf + ((i < len && base_at(i) <= 3) ? 1u : 0u);
+			const bool on_base = i < len && base_at(i) <= 3;            // the match failed on a base of the read (not at an N / the read end)
+			r_ext += (uint32_t)jf + (on_base ? 1u : 0u) - (spec ? 1u : 0u);   // (speculative: the comparison started at the pivot itself)
+			if (on_base && tpos < I.seq_len) fail_at = i;
 		}
 		const int end = i, d = end - cx;                            // the longest forward match is L = [cx, end)
 		if (round == 1) x = end;                                    // next pivot (bwt.c:323, bwamem.c:228)
@@ -1217,6 +1255,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		n_ext += r_ext; n_call += r_call;
 		if (end - (bi + 1) < opt.min_seed_len) continue;            // bwamem.c:231-233,247
 		STAT(11);
+		diag = (long long)tb - (bi + 1); have_diag = true; junk_at = fail_at;   // hints for the speculation above: nothing else depends on them
 		// ---- the second-pass call of this SMEM (bwamem.c:238-249: pivot in its middle, min_intv 2), answered here from the repeat
 		//      lengths when it can be: the SMEM has ONE occurrence, at text position tb, so q == T there.  The call's forward
 		//      match is R = rep[pivot's text position] bases long if that ends inside the SMEM (its interval holds >= 2 rows up
@@ -1240,7 +1279,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		// ---- the coordinates that moved by text comparison: x[0] backward, x[1] forward ----
 		{
 			int w0 = 0, w1 = 0;
-			if (jb > 0) isa_near(tb, c0, w0);
+			if (jb > 0 || spec) isa_near(tb, c0, w0);
 			if (jf > 0) isa_near(I.seq_len - tb - (uint64_t)(end - bi - 1), c1, w1);
 			while (w0 | w1) {
 				if (w0) { c0 = dev_lf(I, c0); --w0; ++n_req; }

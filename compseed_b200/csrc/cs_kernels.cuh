@@ -26,6 +26,11 @@
 #ifndef CS_FWD_WIN
 #define CS_FWD_WIN 1            // 32-base text windows k_seed_fast fetches at once when it follows a unique match forward.  Measured on
 #endif                          // cfg2 (4 M reads, profiles/r02_variants.json): 1: 12.34 ms, 2: 12.52 ms, 4: 13.30 ms -- the extra loads and registers cost more than the shorter dependent chain saves
+#ifndef CS_SPEC_DIAG
+#define CS_SPEC_DIAG 0          // k_seed_fast: first-pass calls tried first on the diagonal of the read's last one-occurrence SMEM (needs the repeat lengths).
+#endif                          // Correct (tests/test_seed_emul.py runs it), but measured slower on cfg2 (4 M reads: 9.19 ms with, 8.70 ms without,
+                                // profiles/r02_variants.json): it is taken for 0.67 calls per read and fails for 0.28, and a failed try costs three gathers
+                                // and one more dependent round trip, which the 2.5 requests per read it saves do not pay for
 #define CS_FAST_SMEM_BYTES ((size_t)CS_FAST_BLOCK * (CS_READ_SMEM * 12))
 
 struct SeedArgs {

@@ -36,7 +36,8 @@ print("k_seed (literal, call mode):")
 for k, name in enumerate(NAMES):
     print(f"  {name:36s} {int(st[4 + k]):14d}  {st[4 + k] / n_reads:9.3f} / read   {st[4 + k] / max(1, st[23]):10.2f} / literal call")
 FAST = ["warp iterations", "calls", "pass-2 calls", "done: nothing pushable", "defer: pass-2 call with a list", "defer: L not pushed",
-        "defer: L not unique", "-", "K-mer present at the failing position", "-", "L resolved", "mems emitted"]
+        "defer: L not unique", "diagonal speculation: taken", "K-mer present at the failing position", "diagonal speculation: failed", "L resolved", "mems emitted",
+        "pass 2 answered at the SMEM: nothing", "pass 2 answered at the SMEM: walk task", "pass 2 answered at the SMEM: literal task", "pass 2 at the SMEM: not decidable"]
 print("k_seed_fast:")
 for k, name in enumerate(FAST):
     print(f"  {name:48s} {int(st[24 + k]):14d}  {st[24 + k] / n_reads:9.3f} / read")

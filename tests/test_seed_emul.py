@@ -20,12 +20,11 @@ class _SeedOpt(C.Structure):
     _fields_ = [("min_seed_len", C.c_int32), ("split_len", C.c_int32), ("split_width", C.c_int32), ("max_mem_intv", C.c_int32), ("max_occ", C.c_int32)]
 
 
-@pytest.fixture(scope="module")
-def emul(tmp_path_factory):
-    d = tmp_path_factory.mktemp("seed_emul")
+def _build(tmp_path_factory, name, defs):
+    d = tmp_path_factory.mktemp(name)
     obj, so = str(d / "oracle.o"), str(d / "libseed_emul.so")
     subprocess.check_call(["gcc", "-O2", "-fPIC", "-w", "-c", os.path.join(ROOT, "oracle", "cs_oracle.c"), "-o", obj])
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-DCS_STATS", "-o", so, os.path.join(ROOT, "tests", "emul", "seed_emul.cpp"), obj, "-lpthread"])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-DCS_STATS", *defs, "-o", so, os.path.join(ROOT, "tests", "emul", "seed_emul.cpp"), obj, "-lpthread"])
     L = C.CDLL(so)
     L.seed_emul_index.restype = C.c_void_p
     L.seed_emul_index.argtypes = [C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64] + [C.c_int] * 5
@@ -35,6 +34,17 @@ def emul(tmp_path_factory):
     L.seed_emul_rep.restype = C.c_void_p
     L.seed_emul_rep.argtypes = [C.c_void_p]
     return L
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    return _build(tmp_path_factory, "seed_emul", [])
+
+
+@pytest.fixture(scope="module")
+def emul_spec(tmp_path_factory):
+    """the build with the diagonal speculation of k_seed_fast switched on (CS_SPEC_DIAG, off in the product: measured slower)"""
+    return _build(tmp_path_factory, "seed_emul_spec", ["-DCS_SPEC_DIAG=1"])
 
 
 def _p(a):
@@ -100,6 +110,18 @@ def test_fast_and_walk_kernels_equal_the_oracle_with_and_without_repeat_lengths(
     assert req[1] < req[0]   # fewer executed gathers with the repeat lengths
     if name.startswith("random"):
         assert req[1] < 0.85 * req[0]
+
+
+@pytest.mark.parametrize("name,mk,rd", CASES, ids=[c[0] for c in CASES])
+def test_diagonal_speculation_build_equals_the_oracle(emul_spec, name, mk, rd):
+    so = (19, 28, 10, 0, 500)
+    ref = mk()
+    bases, off, _ = synth.simulate_reads(ref, rd["n"], rd["lens"], rd["err"], seed=12, n_rate=rd["n_rate"])
+    oi = O.OracleIndex.build(ref)
+    want = oi.seed(bases, off, min_seed_len=so[0], split_len=so[1], split_width=so[2], max_mem_intv=0, max_occ=so[4])
+    mem_off, mems, stats, _ = run_emul(emul_spec, oi, bases, off, so, 1)
+    assert np.array_equal(mem_off, want.mem_off) and np.array_equal(mems, want.mems)
+    assert int(stats[16 + 7]) > 0    # speculation taken
 
 
 def test_repeat_lengths_match_their_definition(emul):
