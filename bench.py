@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--isa-intv", type=int, default=-1, help="cs_index_config_t.isa_intv (sampling of the inverse SA; -1 = default 2)")
     ap.add_argument("--lit-ctas", type=int, default=-1, help="cs_ctx_config_t.lit_ctas_per_sm")
     ap.add_argument("--batch-order", type=int, default=-1, help="cs_ctx_config_t.batch_order")
+    ap.add_argument("--no-bsw", action="store_true", help="skip the extension-stage leg (SURVEY 8f-2: banded Smith-Waterman, reported next to the headline)")
+    ap.add_argument("--bsw-pairs", type=int, default=2_000_000, help="sequence pairs of the extension-stage leg")
     return ap.parse_args()
 
 
@@ -208,6 +210,71 @@ def e2e_only(args, cs, idx, bases, off, opt, ccfg, threads):
         else:
             cs.host_unregister(bases)
     return 0
+
+
+def bsw_leg(args, cs, device: int, threads: int):
+    """SURVEY 8f-2, measured to the same bar as the seeding path: cs_bsw_* (one ksw_extend2 per pair) on a synthetic batch of extension
+    pairs -- device-resident cells/s from the kernel's CUDA events, pairs/s through the C-ABI with host buffers, and the unmodified
+    reference's own batch routines on the host cores over a bounded sample of the same pairs, whose results are compared bit for bit."""
+    from compseed_b200 import synth
+    from oracle import oracle_py as O
+    from concurrent.futures import ThreadPoolExecutor
+    pairs, ref, qer = synth.extension_pairs_fast(args.bsw_pairs, seed=411)
+    n = pairs.shape[0]
+    ex = cs.BswExtender(device, n, ref.nbytes, qer.nbytes, 256)
+    ex.stage(pairs, ref, qer)
+    l0 = ex.launches
+    ms_best, cells = None, 0
+    for it in range(args.warmup + args.steps):
+        ms, cells = ex.run_staged()
+        if it >= args.warmup:
+            ms_best = ms if ms_best is None or ms < ms_best else ms_best
+    launches = ex.launches - l0
+    t0 = time.perf_counter()
+    got = ex.extend(pairs.copy(), ref, qer)
+    e2e_s = time.perf_counter() - t0
+    ex.close()
+    out = {"what": "banded Smith-Waterman extension (ksw_extend2, bwalib/ksw.c:380 == BandedPairWiseSW, mapping/bandedSWA.cpp), one pair per thread, 16-bit cells",
+           "pairs": n, "cells": int(cells), "kernel_ms": ms_best, "gcups": cells / ms_best / 1e6, "pairs_per_s": n / (ms_best * 1e-3),
+           "e2e_pairs_per_s": n / e2e_s, "e2e_what": "cs_bsw_extend with host buffers (SeqPair array + two sequence buffers in, scores out), wall clock",
+           "h2d_bytes": int(pairs.nbytes + ref.nbytes + qer.nbytes), "d2h_bytes": int(pairs.nbytes), "gpu_launches": int(launches),
+           "bound": "integer ALU / latency: one dependent chain of rows per thread; DP rows live in an interleaved HBM scratch that stays in L2 "
+                    "(profiles/r02_ncu_k_bsw_*.txt); not tensor-core work (max-plus recurrences)"}
+    if O.have_ref():   # the reference's own routines on the host cores, parallel chunks of a bounded sample of the same pairs
+        ns = min(n, 200_000)
+        sub = np.ascontiguousarray(pairs[:ns])
+
+        def run_ref(jobs):   # jobs: (mode, indices); returns (results in place of the pairs, seconds)
+            res_all = sub.copy()
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(threads) as tp:
+                res = list(tp.map(lambda j: O.ref_bsw(np.ascontiguousarray(sub[j[1]]), ref, qer, mode=j[0])[0], jobs))
+            dt = time.perf_counter() - t0
+            for (mode, c), r in zip(jobs, res):
+                res_all[c] = r
+            return res_all, dt
+
+        # (a) the parity target: scalarBandedSWA == ksw_extend2, the routine bwamem calls and the one the SIMD twins are written after
+        want0, sec0 = run_ref([(0, c) for c in np.array_split(np.arange(ns), threads) if c.size])
+        # (b) what CompSeed times: getScores8 on the pairs that fit 8-bit cells, getScores16 on the rest (comp_seed.cpp:1556-1564)
+        m8 = (sub[:, 3] < 128) & (sub[:, 4] < 128) & (sub[:, 5] + np.minimum(sub[:, 3], sub[:, 4]) < 128)
+        jobs = []
+        for mode, idx in ((1, np.flatnonzero(m8)), (2, np.flatnonzero(~m8))):
+            share = max(1, int(round(threads * idx.size / ns)))
+            jobs += [(mode, c) for c in np.array_split(idx, share) if c.size]
+        want_simd, cpu_s = run_ref(jobs)
+        cells_s = O.oracle_bsw(sub, ref, qer, n_threads=threads)[1]
+        out["cpu_baseline"] = {"kind": "reference", "cores": threads, "value": ns / cpu_s, "unit": "pairs/s", "gcups": cells_s / cpu_s / 1e9,
+                               "sample": "first %d pairs, BandedPairWiseSW::getScores8 / getScores16 (mapping/bandedSWA.cpp, AVX2 build) by size class, %d parallel chunks" % (ns, len(jobs)),
+                               "scalar_routine_pairs_per_s": ns / sec0}
+        simd_diff = int((want_simd[:, 8:] != want0[:, 8:]).any(axis=1).sum())
+        out["parity"] = {"pairs": ns, "against": "BandedPairWiseSW::scalarBandedSWAWrapper (== ksw_extend2, bwalib/ksw.c:380): score, tle, gtle, qle, gscore, max_off of every pair",
+                         "equal": bool(np.array_equal(got[:ns][:, 8:], want0[:, 8:])),
+                         "reference_simd_twins_differ_from_its_scalar_routine_on_pairs": simd_diff,
+                         "simd_note": "the reference's getScores8/16 are not bit-identical to its own scalar routine: on a few pairs whose extension ends at once "
+                                      "their gtle / gscore differ (and depend on which pairs share a SIMD batch); score, tle, qle and max_off agree",
+                         "equal_to_simd_twins_on_score_tle_qle_max_off": bool(np.array_equal(got[:ns][:, [8, 9, 11, 13]], want_simd[:, [8, 9, 11, 13]]))}
+    return out
 
 
 def main():
@@ -565,6 +632,12 @@ def main():
                     "extends_per_read": E, "two_bucket_ratio": e2_ratio, "lf_steps_per_read": S, "seeding_bytes_per_read": seed_bytes,
                     "whole_path_bytes_per_read": path_bytes, "work_equivalent_gb_per_s": path_bytes * value / 1e9,
                     "occ_lookups_per_read_logical": occ_logical, "occ_lookups_per_s_logical": occ_logical * value}
+    extension = None
+    if not args.no_bsw and world == 1 and not args.no_cpu:
+        try:
+            extension = bsw_leg(args, cs, local_rank, threads)
+        except Exception as e:   # the headline does not depend on this leg
+            extension = {"error": repr(e)}
     occ_exec_per_read = (2.0 * counters["ext_calls"] + counters["sal_calls"]) / n_reads
     line = {"metric": "smem_seeding_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
@@ -585,11 +658,13 @@ def main():
             "gpu_launches_what": "kernel launches counted at the launch sites of the library (cs_ctx_launches): %d in the device-resident timed region "
                                  "(%d steps), %d in the host-buffer timed region" % (dev_launches, args.steps, e2e_launches),
             "clocks": clocks, "roofline": roofline, "reference_work_equivalent": ref_work, "cpu_baseline": cpu_baseline,
-            "counters": counters, "setup_s": setup_s}
+            "extension_stage": extension, "counters": counters, "setup_s": setup_s}
     print(json.dumps(line))
     if use_dist:
         dist.destroy_process_group()
     bad = (parity is not None and not parity["equal"]) or (index_verify is not None and not index_verify["ok"])
+    if extension and "parity" in extension and not extension["parity"]["equal"]:
+        bad = True
     if bad:
         sys.stderr.write("PARITY / INDEX CHECK FAILED: %s %s\n" % (parity, index_verify))
     return 3 if bad else 0

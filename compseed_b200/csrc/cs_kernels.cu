@@ -975,6 +975,14 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 	auto defer_walk = [&](int pivot, uint64_t mi, int d, uint32_t bits) {
 		pend_y = (uint32_t)pivot | ((uint32_t)round << 16) | ((uint32_t)d << 18) | 0x80000000u; pend_z = (uint32_t)mi; pend_bits = bits;
 	};
+	// ... or, when the longest forward match L has K or more bases (so it is pushed) but is not one occurrence: L itself, with its
+	// interval (x2 == 0: not known, k_seed_walk extends to it), walked first; the K-mer probe at the position where it fails then
+	// decides about every other entry of the list (bit 27; d in bits 18-22 and 24-26)
+	uint4 pend_lx = make_uint4(0, 0, 0, 0);
+	auto defer_walk_l = [&](int pivot, int pass, uint64_t mi, int d, uint64_t x0, uint64_t x1, uint64_t x2) {
+		pend_y = (uint32_t)pivot | ((uint32_t)pass << 16) | (((uint32_t)d & 31u) << 18) | (1u << 23) | (((uint32_t)d >> 5) << 24) | (1u << 27) | 0x80000000u;
+		pend_z = (uint32_t)mi; pend_bits = 0; pend_lx = pack_entry(x0, x1, x2, 0);
+	};
 
 	for (;;) {
 		// ---- queue the calls deferred in the previous iteration (one atomic per warp) ----
@@ -985,6 +993,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 				if (q < a.defer_cap) {
 					a.defer_q[q] = make_uint4(rd, pend_y, pend_z, last_q);
 					if (pend_y >> 31) a.defer_bits[q] = pend_bits;
+					if ((pend_y >> 27) & 1) a.defer_lx[q] = pend_lx;
 					last_q = q;
 				}
 			}
@@ -1200,12 +1209,14 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		if (cmin != 1 || !(d >= K || ((kmask >> (d - 1)) & 1))) { // pass 2 with a list, or L itself not pushed
 			if (cmin != 1) STAT(4); else STAT(5);
 			if (d < K && __popc(kmask) <= CS_WALK_MAX && cmin < 0x80000000ull) defer_walk(cx, cmin, d, kmask);
+			else if (CS_WALK_L && d >= K && d < 256 && cmin < 0x80000000ull) defer_walk_l(cx, round, cmin, d, c0, c1, c2);
 			else defer_call(cx, cmin);
 			continue;
 		}
 		if (!unique) { // a short L that still has several occurrences (the next mismatch came before the match was unique): its
 			STAT(6);    // backward sweeps are bwt_extend steps like those of any other short match -- k_seed_walk does them
 			if (d < K) { defer_walk(cx, cmin, d, kmask); pend_y |= 1u << 23; }   // bit 23: L first, then the K-mer probe decides about the rest
+			else if (CS_WALK_L && d < 256) defer_walk_l(cx, round, cmin, d, c0, c1, c2);
 			else defer_call(cx, cmin);
 			continue;
 		}
@@ -1302,6 +1313,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 				if (R < K && km == 0) { STAT(12); n_ext += (uint32_t)R; }              // nothing pushable: the call returns no SMEM
 				else if (pend_y != 0) done = false;                                     // (one call can wait to be queued: the regular path takes this one)
 				else if (R < K && __popc(km) <= CS_WALK_MAX) { STAT(13); pend_y = (uint32_t)cx2 | (2u << 16) | ((uint32_t)R << 18) | 0x80000000u; pend_z = 2u; pend_bits = km; }
+				else if (CS_WALK_L && R >= K) { STAT(14); defer_walk_l(cx2, 2, 2, R, 0, 0, 0); }   // (its interval is not known here)
 				else { STAT(14); pend_y = (uint32_t)cx2 | (2u << 16); pend_z = 2u; }
 				if (done) p2done |= 1ull << nmem;
 			} else STAT(15);
@@ -1391,15 +1403,20 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 		}
 		if (__all_sync(0xffffffffu, !active)) break;
 		const uint32_t rd = item.x;
-		const int cx = (int)(item.y & 0xffff), round = (int)((item.y >> 16) & 3), d = (int)((item.y >> 18) & 31);
+		const int cx = (int)(item.y & 0xffff), round = (int)((item.y >> 16) & 3);
+		const int d = (int)(((item.y >> 18) & 31) | (((item.y >> 24) & 7) << 5));
 		bool lprobe = ((item.y >> 23) & 1) != 0;                    // the longest entry is L itself; see below
+		bool lfirst = active && ((item.y >> 27) & 1) != 0;          // ... and has K or more bases: not among the bits, its interval comes with the task
 		const uint64_t cmin = item.z;
 		uint32_t bits = active ? a.defer_bits[q] : 0u;
 		const int ls0 = (int)(bits >> 18);                          // 1 + start of the SMEM k_seed_fast already found for this call (0: none)
 		bits &= 0x3ffffu;
+		uint4 lx = make_uint4(0, 0, 0, 0);
+		if (lfirst) lx = a.defer_lx[q];
+		int len = 0;
 		if (active) {
 			const uint32_t o = a.off[rd];
-			const int len = (int)(a.off[rd + 1] - o);
+			len = (int)(a.off[rd + 1] - o);
 			const uint64_t w0 = (uint64_t)((o + a.off_bias) >> 5) + 2ull * rd;
 			const uint32_t nw = ((uint32_t)len >> 5) + 2;
 #pragma unroll
@@ -1413,12 +1430,26 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 		int last_start = ls0 - 1;
 		// The loops below are made warp-uniform with votes: left to themselves the lanes drift apart (their entries take
 		// the table or the FM-index at different steps) and the hardware ends up running them one after the other.
-		while (__any_sync(0xffffffffu, bits && !punt)) { // entries, longest first
-			const bool on = bits && !punt;
+		while (__any_sync(0xffffffffu, (bits || lfirst) && !punt)) { // entries, longest first
+			const bool on = (bits || lfirst) && !punt;
 			int e = 0;
 			uint64_t c0 = 0, c1 = 0, c2 = 0;
 			bool go = false;
-			if (on) {
+			if (on && lfirst) { // L = q[cx, cx+d), d >= K: always pushed (the forward pass's last interval, bwt.c:317,321)
+				lfirst = false;
+				e = d;
+				uint32_t dummy;
+				unpack_entry(lx, c0, c1, c2, dummy);
+				if (c2 == 0) { // interval not known (the call was answered from the repeat lengths): table, then forward bwt_extend steps
+					kt_lookup(I, (uint32_t)kd, key_of(cx, kd), c0, c1, c2); ++n_req;
+					for (int k = kd; k < e; ++k) {
+						uint64_t o0, o1, o2; uint32_t two;
+						dev_extend(I, c0, c1, c2, 3 - base_at(cx + k), 0, o0, o1, o2, two);
+						c0 = o0; c1 = o1; c2 = o2; ++t_call; n_two += two; n_req += 1u + two;
+					}
+				}
+				go = true;
+			} else if (on) {
 				e = 32 - __clz((int)bits);
 				bits &= ~(1u << (e - 1));
 				// the interval of q[cx, cx+e) ...
@@ -1468,11 +1499,12 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 			}
 			if (lprobe) { // that was L (k_seed_fast's argument): the other entries of >= K - (cx - bi) bases all start with q[bi, bi+K)
 				lprobe = false;                                     // once extended to bi; if that K-mer does not occur they all end there, contained in L
+				const bool lgiven = ((item.y >> 27) & 1) != 0;      // (the other entries of such a task are not known yet)
 				if (bi < 0 || base_at(bi) > 3) bits = 0;            // read start / N: every interval ends here (bwt.c:331)
 				else {
 					const int K = (int)I.pt_k, need_d = K - (cx - bi);
 					const uint32_t shallow = need_d > 1 ? bits & ((1u << (need_d - 1)) - 1u) : 0u;
-					if (bits != shallow) { // some entry is long enough for the probe to decide
+					if (bits != shallow || lgiven) { // some entry is (may be) long enough for the probe to decide
 						const uint32_t wi = (uint32_t)bi >> 5, sh = (uint32_t)bi & 31;
 						uint32_t nmw = nm_word(wi) >> sh;
 						if (sh) nmw |= nm_word(wi + 1) << (32 - sh);
@@ -1480,6 +1512,28 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 						const bool absent = !(nmw & ((1u << K) - 1u)) && ((gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) == 0;
 						++n_req;
 						if (absent) bits = shallow;                     // else every entry is walked
+						else if (lgiven) punt = true;                   // ... which the literal kernel does: this task does not know them
+					}
+					if (lgiven && !punt && need_d > 1) { // the shallow entries of such a task: the filter bits of e = 1 .. need_d - 1, as k_seed_fast's probe_bits
+						int nl = 0;                                     // N-free run left of the pivot, capped at 31 bases
+						{
+							const int s0 = cx >= 31 ? cx - 31 : 0, cl = cx - s0;
+							if (cl > 0) {
+								const uint32_t w2 = (uint32_t)s0 >> 5, s2 = (uint32_t)s0 & 31;
+								uint32_t m = nm_word(w2) >> s2;
+								if (s2) m |= nm_word(w2 + 1) << (32 - s2);
+								m = (m & ((1u << cl) - 1u)) << (32 - cl);
+								nl = m ? __clz((int)m) : cl;
+							}
+						}
+						const int e0 = K - nl < 1 ? 1 : K - nl;
+						const uint32_t omin = cmin > 3 ? 4u : (uint32_t)cmin;
+						for (int e2 = e0; e2 < need_d; ++e2) {
+							const uint64_t key = key_of(cx + e2 - K, K);
+							const uint32_t cnt = (gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3;
+							++n_req;
+							if (cnt == 3 || (cnt != 0 && cnt >= omin)) bits |= 1u << (e2 - 1);
+						}
 					}
 					if (__popc(bits) > CS_WALK_MAX) punt = true;        // too many for one lane: the literal kernel takes the call
 				}

@@ -26,6 +26,9 @@
 #ifndef CS_FWD_WIN
 #define CS_FWD_WIN 1            // 32-base text windows k_seed_fast fetches at once when it follows a unique match forward.  Measured on
 #endif                          // cfg2 (4 M reads, profiles/r02_variants.json): 1: 12.34 ms, 2: 12.52 ms, 4: 13.30 ms -- the extra loads and registers cost more than the shorter dependent chain saves
+#ifndef CS_WALK_L
+#define CS_WALK_L 1             // calls whose longest forward match has >= K bases but several occurrences go to k_seed_walk (L first), not to k_seed
+#endif
 #ifndef CS_SPEC_DIAG
 #define CS_SPEC_DIAG 0          // k_seed_fast: first-pass calls tried first on the diagonal of the read's last one-occurrence SMEM (needs the repeat lengths).
 #endif                          // Correct (tests/test_seed_emul.py runs it), but measured slower on cfg2 (4 M reads: 9.19 ms with, 8.70 ms without,
@@ -48,6 +51,7 @@ struct SeedArgs {
 	// the length d of its longest forward match; walk = 0: for k_seed.  NULL: k_seed runs in read mode and takes every read.
 	uint4 *defer_q;
 	uint32_t *defer_bits;
+	uint4 *defer_lx;            // walk tasks that start with L itself (bit 27 of .y): its packed interval (pack_entry; x2 == 0: not known)
 	uint32_t *lit_q, *n_lit;    // the walk = 0 entries of defer_q (indices), listed for k_seed
 	uint32_t defer_cap;
 	uint32_t *n_defer;

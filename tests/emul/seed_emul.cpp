@@ -150,14 +150,14 @@ int64_t seed_emul_run(void *e, uint32_t n_reads, const uint8_t *bases, const uin
 	unsigned long long pool_used = 0;
 	int error = 0;
 	uint32_t n_defer = 0, n_lit = 0, n_defer_fast = 0;
-	std::vector<uint4> defer_q(defer_cap);
+	std::vector<uint4> defer_q(defer_cap), defer_lx(defer_cap);
 	std::vector<uint32_t> defer_bits(defer_cap, 0), lit_q(defer_cap, 0), x_n(defer_cap, 0xffffffffu), read_last_q(n_reads + 1, 0xffffffffu), read_n_mems(n_reads + 1, 0);
 	std::vector<uint64_t> x_off(defer_cap, 0), read_pool_off(n_reads + 1, 0);
 	std::vector<cs_mem_t> thread_mems(mem_cap), pool(cap);
 	SeedArgs a;
 	memset(&a, 0, sizeof a);
 	a.bases = pb.data(); a.off = off; a.n_reads = n_reads; a.opt = *opt; a.packed = packed.data(); a.off_bias = 0; a.nmask = nmask.data();
-	a.next_read = ctrl.data(); a.defer_q = defer_q.data(); a.defer_bits = defer_bits.data(); a.lit_q = lit_q.data(); a.n_lit = &n_lit;
+	a.next_read = ctrl.data(); a.defer_q = defer_q.data(); a.defer_bits = defer_bits.data(); a.defer_lx = defer_lx.data(); a.lit_q = lit_q.data(); a.n_lit = &n_lit;
 	a.defer_cap = defer_cap; a.n_defer = &n_defer; a.n_defer_fast = &n_defer_fast; a.read_last_q = read_last_q.data();
 	a.x_off = x_off.data(); a.x_n = x_n.data(); a.thread_mems = thread_mems.data(); a.mem_cap = mem_cap;
 	a.pool = pool.data(); a.pool_cap = cap; a.pool_used = &pool_used; a.read_pool_off = read_pool_off.data(); a.read_n_mems = read_n_mems.data();
