@@ -558,7 +558,7 @@ struct Slot {
 	uint8_t *d_bases; uint32_t *d_off;
 	uint64_t *d_packed; uint32_t *d_nmask;   // 2-bit packed reads + ambiguity mask (k_pack_reads)
 	uint4 *d_defer_q;                         // calls the fast kernel hands to the literal kernel (SeedArgs::defer_q)
-	uint32_t *d_read_last_q, *d_x_n, *d_defer_bits, *d_lit_q; uint64_t *d_x_off; uint4 *d_defer_lx;
+	uint32_t *d_read_last_q, *d_x_n, *d_defer_bits, *d_lit_q; uint64_t *d_x_off; uint4 *d_defer_lx, *d_thread_lx;
 	cs_mem_t *d_stage;                        // collect: a read's sources gathered before the sort
 	bool used_fast;
 	bool packed_input;                        // the batch came through cs_seed_batch_submit_packed: d_packed / d_nmask are the input
@@ -627,7 +627,7 @@ static void slot_free(Slot *s)
 	cudaFreeHost(s->h_cs_qbeg); cudaFreeHost(s->h_cs_len);
 	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
 	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
-	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_defer_bits); cudaFree(s->d_defer_lx); cudaFree(s->d_lit_q); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
+	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_defer_bits); cudaFree(s->d_defer_lx); cudaFree(s->d_thread_lx); cudaFree(s->d_lit_q); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
 	cudaFree(s->d_pool); cudaFree(s->d_mems); cudaFree(s->d_read_pool_off); cudaFree(s->d_read_n_mems);
 	cudaFree(s->d_r3_mems); cudaFree(s->d_r3_n_mems); cudaFree(s->d_tot_n_mems);
 	cudaFree(s->d_mem_off); cudaFree(s->d_read_n_seeds); cudaFree(s->d_seed_off); cudaFree(s->d_rows); cudaFree(s->d_scan_tmp);
@@ -764,6 +764,7 @@ extern "C" cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads,
 		CK(cudaMalloc(&s->d_read_last_q, ((size_t)max_reads + 1) * 4));
 		CK(cudaMalloc(&s->d_stage, ctx->max_mems * sizeof(cs_mem_t)));
 		CK(cudaMalloc(&s->d_thread_mems, nthreads * ctx->mem_cap * sizeof(cs_mem_t)));
+		CK(cudaMalloc(&s->d_thread_lx, nthreads * sizeof(uint4)));
 		CK(cudaMalloc(&s->d_spill, nthreads * ctx->spill_cap * sizeof(uint4)));
 		CK(cudaMalloc(&s->d_pool, ctx->max_mems * sizeof(cs_mem_t)));
 		CK(cudaMalloc(&s->d_mems, ctx->max_mems * sizeof(cs_mem_t)));
@@ -870,7 +871,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	a.packed = s->d_packed; a.nmask = s->d_nmask; a.off_bias = s->packed_input ? s->off_bias : 0u;
 	a.next_read = s->d_ctrl->next_read;
 	a.defer_q = nullptr; a.defer_cap = ctx->defer_cap; a.n_defer = &s->d_ctrl->n_defer;
-	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n; a.defer_bits = s->d_defer_bits; a.defer_lx = s->d_defer_lx; a.lit_q = s->d_lit_q; a.n_lit = &s->d_ctrl->n_lit; a.n_defer_fast = &s->d_ctrl->n_defer_fast;
+	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n; a.defer_bits = s->d_defer_bits; a.defer_lx = s->d_defer_lx; a.thread_lx = s->d_thread_lx; a.lit_q = s->d_lit_q; a.n_lit = &s->d_ctrl->n_lit; a.n_defer_fast = &s->d_ctrl->n_defer_fast;
 	s->used_fast = false;
 	a.thread_mems = s->d_thread_mems; a.mem_cap = ctx->mem_cap;
 	a.spill = s->d_spill; a.spill_cap = ctx->spill_cap;

@@ -52,6 +52,7 @@ struct cs_bsw {
 	int64_t max_h0_staged;   // of the staged batch: decides whether a DP cell fits 32 bits (EhCell)
 	bool neg_h0_staged;
 	int ctas_per_sm;         // resident 128-thread CTAs of the extension kernel per SM (cs_bsw_set_ctas_per_sm)
+	int use_smem;            // -1 / 1: DP rows in shared memory when the longest query allows (k_bsw_extend_smem); 0: always the HBM scratch
 	uint64_t cap_ref, cap_qer;
 	PairIn *h_in, *d_in;
 	int32_t *h_out, *d_out;
@@ -131,7 +132,7 @@ extern "C" cs_bsw_t *cs_bsw_create(int device, uint32_t max_pairs, uint64_t max_
 	if (bsw_alloc_pairs(b, max_pairs) != CS_OK) goto fail;
 	if (bsw_alloc_seq(&b->h_ref, &b->d_ref, &b->cap_ref, std::max<uint64_t>(max_ref_bytes, 4096)) != CS_OK) goto fail;
 	if (bsw_alloc_seq(&b->h_qer, &b->d_qer, &b->cap_qer, std::max<uint64_t>(max_qer_bytes, 4096)) != CS_OK) goto fail;
-	b->eh_qlen = 0; b->eh_threads = 0; b->max_qlen_staged = max_qlen; b->ctas_per_sm = 8;
+	b->eh_qlen = 0; b->eh_threads = 0; b->max_qlen_staged = max_qlen; b->ctas_per_sm = 8; b->use_smem = -1;
 	return b;
 fail:
 	cs_bsw_free(b);
@@ -139,6 +140,13 @@ fail:
 }
 
 extern "C" uint64_t cs_bsw_launches(const cs_bsw_t *b) { return b ? b->n_launch : 0; }
+
+extern "C" int cs_bsw_set_rows_in_smem(cs_bsw_t *b, int on)
+{
+	if (!b) return cs_set_err(CS_E_ARG, "null argument");
+	b->use_smem = on ? 1 : 0;
+	return CS_OK;
+}
 
 extern "C" int cs_bsw_set_ctas_per_sm(cs_bsw_t *b, int ctas_per_sm)
 {
@@ -231,7 +239,21 @@ extern "C" int cs_bsw_run_staged(cs_bsw_t *b, int32_t w, const cs_bsw_opt_t *opt
 #else
 			const bool wide = b->neg_h0_staged || b->max_h0_staged + (int64_t)b->max_qlen_staged * (mx > 0 ? mx : 0) >= 65536;
 #endif
-			if (wide) k_bsw_extend<true><<<grid, 128, 0, b->stream>>>(a);
+			// rows in shared memory when two or more CTAs fit an SM with the longest query of the batch (b->use_smem: -1 auto)
+			const size_t smem = (size_t)CS_BSW_SMEM_BLOCK * (((size_t)b->max_qlen_staged + 2) * (wide ? 8 : 4) + ((size_t)b->max_qlen_staged / 8 + 2) * 4);
+			a.smem_cols = b->max_qlen_staged + 2;
+			int per_sm = 0;
+			if (b->use_smem != 0 && smem <= 100 * 1024) {
+				if (wide) { CK(cudaFuncSetAttribute(k_bsw_extend_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bsw_extend_smem<true>, CS_BSW_SMEM_BLOCK, smem)); }
+				else { CK(cudaFuncSetAttribute(k_bsw_extend_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bsw_extend_smem<false>, CS_BSW_SMEM_BLOCK, smem)); }
+			}
+			if (per_sm >= 2) {
+				const int g = std::max(1, std::min<int>(b->n_sm * per_sm, (int)((n + CS_BSW_SMEM_BLOCK - 1) / CS_BSW_SMEM_BLOCK)));
+				if (wide) k_bsw_extend_smem<true><<<g, CS_BSW_SMEM_BLOCK, smem, b->stream>>>(a);
+				else k_bsw_extend_smem<false><<<g, CS_BSW_SMEM_BLOCK, smem, b->stream>>>(a);
+			} else if (wide) k_bsw_extend<true><<<grid, 128, 0, b->stream>>>(a);
 			else k_bsw_extend<false><<<grid, 128, 0, b->stream>>>(a);
 		}
 		CK(cudaGetLastError()); ++b->n_launch;

@@ -12,6 +12,7 @@ struct BswArgs {
 	const uint32_t *order;      // pair indices sorted by query length
 	uint32_t n;
 	const uint8_t *ref, *qer;
+	uint32_t smem_cols;         // k_bsw_extend_smem: columns of a DP row in shared memory (longest query + 2); the packed queries follow the rows
 	void *eh; size_t eh_stride; // DP rows, column j of a thread's row at [j * eh_stride + thread] (EhCell: 8 or 4 bytes per cell)
 	int32_t w, o_del, e_del, o_ins, e_ins, zdrop, end_bonus, max_mat;
 	int8_t mat[25];
@@ -31,9 +32,11 @@ template <> struct EhCell<false> { typedef uint32_t T; static __device__ __force
                                    static __device__ __forceinline__ bool zero(T v) { return v == 0; } };
 
 // ksw_extend2 (bwalib/ksw.c:380-479) for pair pid; eh: this thread's DP row, column j at eh[j * st]; s_mat: the 5 x 5 scores.
-// Returns the number of cells computed.
-template <bool WIDE>
-__device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uint32_t pid, typename EhCell<WIDE>::T *eh, size_t st, const int *s_mat)
+// QPK: the query is first copied, 8 bases per word (4 bits each), to qpk (word k at qpk[k * st]) and read from there: every row of the
+// DP re-reads the whole query, and 32 lanes reading one byte each of 32 different queries cost the L1 32 sector look-ups per
+// instruction -- more than everything else a cell needs.  Returns the number of cells computed.
+template <bool WIDE, bool QPK>
+__device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uint32_t pid, typename EhCell<WIDE>::T *eh, size_t st, const int *s_mat, uint32_t *qpk = nullptr)
 {
 	typedef EhCell<WIDE> Cell;
 	typedef typename Cell::T cell_t;
@@ -43,6 +46,12 @@ __device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uin
 	const int qlen = p.len2, tlen = p.len1, h0 = p.h0;
 	const uint8_t *query = a.qer + p.idq, *target = a.ref + p.idr;
 	int i, j, beg, end, max, max_i, max_j, max_ie, gscore, max_off, w = a.w;
+	if (QPK)
+		for (j = 0; j < qlen; j += 8) {
+			uint32_t v = 0;
+			for (int k = 0; k < 8 && j + k < qlen; ++k) v |= (uint32_t)(query[j + k] & 15) << (4 * k);
+			qpk[(size_t)(j >> 3) * st] = v;
+		}
 	// first row (ksw.c:395-398): H(-1, j); everything else of the row array is zero (calloc)
 	{
 		int h = h0 > oe_ins ? h0 - oe_ins : 0;
@@ -77,7 +86,7 @@ __device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uin
 		for (j = beg; j < end; ++j, pe += st) { // ksw.c:421-447
 			const cell_t v = *pe;
 			int M = Cell::h(v), e = Cell::e(v), h, t;
-			M = M ? M + q[query[j]] : 0;
+			M = M ? M + q[QPK ? (int)((qpk[(size_t)(j >> 3) * st] >> (4 * (j & 7))) & 15u) : (int)query[j]] : 0;
 			h = M > e ? M : e;
 			h = h > f ? h : f;
 			mj = m > h ? mj : j;
@@ -112,6 +121,37 @@ __device__ __forceinline__ unsigned long long bsw_one_pair(const BswArgs &a, uin
 	return cells;
 }
 
+// The same with the DP rows in SHARED memory ([column][thread of the CTA], bank-conflict free): the row loads of k_bsw_extend below go
+// to an interleaved HBM scratch that only partly stays in L2 and leave the warps waiting on the long scoreboard (ncu: 18 % issue
+// active, 34 stalled warps per issue, profiles/r02_ncu_k_bsw_extend_2Mpairs.txt); a row of <= a few hundred cells per thread fits
+// shared memory for about ten warps per SM, and at shared-memory latency that many are enough.  Used when the longest query of
+// the batch allows at least two CTAs per SM; k_bsw_extend is the fallback for longer queries.
+#ifndef CS_BSW_SMEM_BLOCK
+#define CS_BSW_SMEM_BLOCK 32   // one warp per CTA: the finest granularity for shared memory (2 M pairs: 32: 412 GCUPS, 64: 399, 128: 334; profiles/r02_bsw_variants.txt)
+#endif
+#ifndef CS_BSW_EMUL   // (tests/emul/bsw_emul.cpp runs bsw_one_pair alone)
+template <bool WIDE>
+__global__ void __launch_bounds__(CS_BSW_SMEM_BLOCK) k_bsw_extend_smem(BswArgs a)
+{
+	extern __shared__ uint4 s_rows_raw[];
+	__shared__ int s_mat[25];
+	if (threadIdx.x < 25) s_mat[threadIdx.x] = a.mat[threadIdx.x];
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	typename EhCell<WIDE>::T *const eh = reinterpret_cast<typename EhCell<WIDE>::T*>(s_rows_raw) + threadIdx.x;
+	uint32_t *const qpk = reinterpret_cast<uint32_t*>(reinterpret_cast<typename EhCell<WIDE>::T*>(s_rows_raw) + (size_t)CS_BSW_SMEM_BLOCK * a.smem_cols) + threadIdx.x;
+	unsigned long long cells = 0;
+	for (;;) { // 32 pairs of similar shape per warp and trip
+		unsigned int base = 0;
+		if (lane == 0) base = atomicAdd(a.work, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= a.n) break;
+		if (base + lane < a.n) cells += bsw_one_pair<WIDE, true>(a, a.order[a.n - 1 - (base + lane)], eh, CS_BSW_SMEM_BLOCK, s_mat, qpk);   // largest shapes first
+	}
+	if (cells) atomicAdd(a.cells, cells);
+}
+#endif
+
 template <bool WIDE>
 __global__ void __launch_bounds__(128) k_bsw_extend(BswArgs a)
 {
@@ -127,7 +167,7 @@ __global__ void __launch_bounds__(128) k_bsw_extend(BswArgs a)
 		if (lane == 0) base = atomicAdd(a.work, 32u);
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= a.n) break;
-		if (base + lane < a.n) cells += bsw_one_pair<WIDE>(a, a.order[a.n - 1 - (base + lane)], eh, a.eh_stride, s_mat);   // largest shapes first
+		if (base + lane < a.n) cells += bsw_one_pair<WIDE, false>(a, a.order[a.n - 1 - (base + lane)], eh, a.eh_stride, s_mat);   // largest shapes first
 	}
 	if (cells) atomicAdd(a.cells, cells);
 }

@@ -978,10 +978,10 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 	// ... or, when the longest forward match L has K or more bases (so it is pushed) but is not one occurrence: L itself, with its
 	// interval (x2 == 0: not known, k_seed_walk extends to it), walked first; the K-mer probe at the position where it fails then
 	// decides about every other entry of the list (bit 27; d in bits 18-22 and 24-26)
-	uint4 pend_lx = make_uint4(0, 0, 0, 0);
+	// (the interval waits in this thread's slot of thread_lx, not in registers)
 	auto defer_walk_l = [&](int pivot, int pass, uint64_t mi, int d, uint64_t x0, uint64_t x1, uint64_t x2) {
 		pend_y = (uint32_t)pivot | ((uint32_t)pass << 16) | (((uint32_t)d & 31u) << 18) | (1u << 23) | (((uint32_t)d >> 5) << 24) | (1u << 27) | 0x80000000u;
-		pend_z = (uint32_t)mi; pend_bits = 0; pend_lx = pack_entry(x0, x1, x2, 0);
+		pend_z = (uint32_t)mi; pend_bits = 0; a.thread_lx[gtid] = pack_entry(x0, x1, x2, 0);
 	};
 
 	for (;;) {
@@ -993,7 +993,7 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 				if (q < a.defer_cap) {
 					a.defer_q[q] = make_uint4(rd, pend_y, pend_z, last_q);
 					if (pend_y >> 31) a.defer_bits[q] = pend_bits;
-					if ((pend_y >> 27) & 1) a.defer_lx[q] = pend_lx;
+					if ((pend_y >> 27) & 1) a.defer_lx[q] = a.thread_lx[gtid];
 					last_q = q;
 				}
 			}
@@ -1509,7 +1509,8 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 						uint32_t nmw = nm_word(wi) >> sh;
 						if (sh) nmw |= nm_word(wi + 1) << (32 - sh);
 						const uint64_t key = key_of(bi, K);
-						const bool absent = !(nmw & ((1u << K) - 1u)) && ((gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) == 0;
+						// "does not occur" for a call with min_intv = cmin: fewer than cmin occurrences (the filter counts up to 3)
+						const bool absent = !(nmw & ((1u << K) - 1u)) && ((gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) < (cmin > 3 ? 3u : (uint32_t)cmin);
 						++n_req;
 						if (absent) bits = shallow;                     // else every entry is walked
 						else if (lgiven) punt = true;                   // ... which the literal kernel does: this task does not know them

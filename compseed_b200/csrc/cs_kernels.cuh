@@ -51,6 +51,7 @@ struct SeedArgs {
 	// the length d of its longest forward match; walk = 0: for k_seed.  NULL: k_seed runs in read mode and takes every read.
 	uint4 *defer_q;
 	uint32_t *defer_bits;
+	uint4 *thread_lx;           // [n_threads] where k_seed_fast keeps such an interval until the task has its queue slot
 	uint4 *defer_lx;            // walk tasks that start with L itself (bit 27 of .y): its packed interval (pack_entry; x2 == 0: not known)
 	uint32_t *lit_q, *n_lit;    // the walk = 0 entries of defer_q (indices), listed for k_seed
 	uint32_t defer_cap;

@@ -254,6 +254,7 @@ def load_library():
     L.cs_bsw_launches.restype = C.c_uint64
     L.cs_bsw_launches.argtypes = [C.c_void_p]
     L.cs_bsw_set_ctas_per_sm.argtypes = [C.c_void_p, C.c_int]
+    L.cs_bsw_set_rows_in_smem.argtypes = [C.c_void_p, C.c_int]
     L.cs_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.cs_host_unregister.argtypes = [C.c_void_p]
     _lib = L
@@ -926,6 +927,9 @@ class BswExtender:
     @property
     def launches(self) -> int:
         return int(load_library().cs_bsw_launches(self.h))
+
+    def set_rows_in_smem(self, on: bool) -> None:
+        _check(load_library().cs_bsw_set_rows_in_smem(self.h, 1 if on else 0))
 
     def set_ctas_per_sm(self, n: int) -> None:
         _check(load_library().cs_bsw_set_ctas_per_sm(self.h, n))

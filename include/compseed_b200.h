@@ -346,8 +346,11 @@ int cs_bsw_stage(cs_bsw_t *b, const cs_seqpair_t *pairs, const uint8_t *seq_buf_
 int cs_bsw_run_staged(cs_bsw_t *b, int32_t w, const cs_bsw_opt_t *opt, float *kernel_ms, uint64_t *cells);
 int cs_bsw_fetch(cs_bsw_t *b, cs_seqpair_t *pairs);
 uint64_t cs_bsw_launches(const cs_bsw_t *b);
-/* Tuning: resident 128-thread CTAs of the extension kernel per SM (default 8); changes no result. */
+/* Tuning: resident 128-thread CTAs of the extension kernel per SM when its DP rows live in the HBM scratch (default 8); changes no result. */
 int cs_bsw_set_ctas_per_sm(cs_bsw_t *b, int ctas_per_sm);
+/* Tuning: 1 (default) keeps the DP rows in shared memory whenever the longest query of the batch lets two CTAs of 32 threads share an
+ * SM (queries up to ~700 bases with 16-bit cells); 0 always uses the HBM scratch.  Changes no result. */
+int cs_bsw_set_rows_in_smem(cs_bsw_t *b, int on);
 
 /* --- multi-device pipeline ----------------------------------------------------------------------
  * Replaces kt_for(opt->n_threads, worker1 / seed_and_extend) over the reads of a -K batch for the seeding part

@@ -9,6 +9,10 @@ ctas = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8]
 pairs, ref, qer = synth.extension_pairs_fast(n, seed=411)
 ex = cs.BswExtender(0, pairs.shape[0], ref.nbytes, qer.nbytes, 256)
 ex.stage(pairs, ref, qer)
+for it in range(3):
+    ms, cells = ex.run_staged()
+print("%s rows in shared memory: %.2f ms, %.1f Gcells, %.1f GCUPS, %.1f M pairs/s" % (os.environ.get("COMPSEED_LIB_TAG", "default"), ms, cells / 1e9, cells / ms / 1e6, n / ms / 1e3), flush=True)
+ex.set_rows_in_smem(False)
 for c in ctas:
     ex.set_ctas_per_sm(c)
     for it in range(3):

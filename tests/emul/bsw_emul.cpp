@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 
+#define CS_BSW_EMUL 1
 #define __global__
 #define __device__
 #define __host__
@@ -28,7 +29,7 @@ extern "C" {
 
 // pairs: 14 int32 each (SeqPair); eh_stride > 1 exercises the interleaved row layout of the kernel.  Returns the cells computed.
 unsigned long long bsw_emul(int32_t *pairs, const uint8_t *ref, const uint8_t *qer, uint32_t n, int w, int o_del, int e_del, int o_ins, int e_ins,
-                            int zdrop, int end_bonus, const int8_t *mat, uint32_t eh_stride, int wide)
+                            int zdrop, int end_bonus, const int8_t *mat, uint32_t eh_stride, int wide, int qpack)
 {
 	std::vector<PairIn> in(n);
 	std::vector<int32_t> out((size_t)n * 6);
@@ -48,9 +49,15 @@ unsigned long long bsw_emul(int32_t *pairs, const uint8_t *ref, const uint8_t *q
 	for (int k = 0; k < 25; ++k) { a.mat[k] = mat[k]; s_mat[k] = mat[k]; mx = mx > mat[k] ? mx : mat[k]; }
 	a.max_mat = mx;
 	unsigned long long cells = 0;
+	std::vector<uint32_t> qpk((size_t)(max_q / 8 + 2) * eh_stride, 0xdeadbeefu);
+	if (qpack) { // the variant the shared-memory kernel runs: query read from its 4-bit packed copy
+		for (uint32_t i = 0; i < n; ++i)
+			cells += wide ? bsw_one_pair<true, true>(a, i, eh.data() + (i % eh_stride), eh_stride, s_mat, qpk.data() + (i % eh_stride))
+			              : bsw_one_pair<false, true>(a, i, reinterpret_cast<uint32_t*>(eh.data()) + (i % eh_stride), eh_stride, s_mat, qpk.data() + (i % eh_stride));
+	} else
 	for (uint32_t i = 0; i < n; ++i)
-		cells += wide ? bsw_one_pair<true>(a, i, eh.data() + (i % eh_stride), eh_stride, s_mat)
-		              : bsw_one_pair<false>(a, i, reinterpret_cast<uint32_t*>(eh.data()) + (i % eh_stride), eh_stride, s_mat);
+		cells += wide ? bsw_one_pair<true, false>(a, i, eh.data() + (i % eh_stride), eh_stride, s_mat)
+		              : bsw_one_pair<false, false>(a, i, reinterpret_cast<uint32_t*>(eh.data()) + (i % eh_stride), eh_stride, s_mat);
 	for (uint32_t i = 0; i < n; ++i) for (int k = 0; k < 6; ++k) pairs[14 * (size_t)i + 8 + k] = out[6 * (size_t)i + k];
 	return cells;
 }

@@ -151,19 +151,21 @@ int64_t seed_emul_run(void *e, uint32_t n_reads, const uint8_t *bases, const uin
 	int error = 0;
 	uint32_t n_defer = 0, n_lit = 0, n_defer_fast = 0;
 	std::vector<uint4> defer_q(defer_cap), defer_lx(defer_cap);
+	uint4 thread_lx[1];
 	std::vector<uint32_t> defer_bits(defer_cap, 0), lit_q(defer_cap, 0), x_n(defer_cap, 0xffffffffu), read_last_q(n_reads + 1, 0xffffffffu), read_n_mems(n_reads + 1, 0);
 	std::vector<uint64_t> x_off(defer_cap, 0), read_pool_off(n_reads + 1, 0);
 	std::vector<cs_mem_t> thread_mems(mem_cap), pool(cap);
 	SeedArgs a;
 	memset(&a, 0, sizeof a);
 	a.bases = pb.data(); a.off = off; a.n_reads = n_reads; a.opt = *opt; a.packed = packed.data(); a.off_bias = 0; a.nmask = nmask.data();
-	a.next_read = ctrl.data(); a.defer_q = defer_q.data(); a.defer_bits = defer_bits.data(); a.defer_lx = defer_lx.data(); a.lit_q = lit_q.data(); a.n_lit = &n_lit;
+	a.next_read = ctrl.data(); a.defer_q = defer_q.data(); a.defer_bits = defer_bits.data(); a.defer_lx = defer_lx.data(); a.thread_lx = thread_lx; a.lit_q = lit_q.data(); a.n_lit = &n_lit;
 	a.defer_cap = defer_cap; a.n_defer = &n_defer; a.n_defer_fast = &n_defer_fast; a.read_last_q = read_last_q.data();
 	a.x_off = x_off.data(); a.x_n = x_n.data(); a.thread_mems = thread_mems.data(); a.mem_cap = mem_cap;
 	a.pool = pool.data(); a.pool_cap = cap; a.pool_used = &pool_used; a.read_pool_off = read_pool_off.data(); a.read_n_mems = read_n_mems.data();
 	a.counters = counters.data(); a.req = req.data(); a.error = &error;
 	k_seed_fast(d, a);
 	n_defer_fast = n_defer;
+	const uint32_t n_lit_fast = n_lit;
 	if (n_defer > defer_cap) return -102;
 	k_seed_walk(d, a);
 	if (error) return error;
@@ -176,10 +178,11 @@ int64_t seed_emul_run(void *e, uint32_t n_reads, const uint8_t *bases, const uin
 			for (uint32_t m = 0; m < x_n[q]; ++m) per[defer_q[q].x].push_back(pool[x_off[q] + m]);
 	// ... and the calls listed for the literal kernel, executed as k_seed's call mode defines them: the whole bwt_smem1a call
 	// (mems of >= min_seed_len bases), and for a first-pass call the second-pass calls of what it found (bwamem.c:238-249)
-	uint64_t n_oracle = 0;
+	uint64_t n_oracle = 0, n_punt = 0, n_follow = 0;
 	std::vector<cso_mem_t> tmp(4096), tmp2(4096);
 	for (uint32_t li = 0; li < n_lit; ++li) {
 		const uint4 it = defer_q[lit_q[li]];
+		if (li >= n_lit_fast) { if (lit_q[li] < n_defer_fast) ++n_punt; else ++n_follow; }
 		const uint32_t rd = it.x; const int pivot = (int)(it.y & 0xffff), pass = (int)((it.y >> 16) & 3);
 		const uint8_t *q = bases + off[rd]; const int len = (int)(off[rd + 1] - off[rd]);
 		int n1 = cso_smem1_call(&E->oidx, len, q, pivot, it.z, tmp.data(), (int)tmp.size(), nullptr);
@@ -208,6 +211,8 @@ int64_t seed_emul_run(void *e, uint32_t n_reads, const uint8_t *bases, const uin
 	if (stats) {
 		for (int k = 0; k < 4; ++k) stats[k] = counters[k];
 		stats[4] = req[0]; stats[5] = req[1]; stats[6] = n_defer; stats[7] = n_lit; stats[8] = n_oracle;
+		for (int k = 40; k < 48; ++k) stats[k] = counters[k];
+		stats[9] = n_lit_fast; stats[10] = n_punt; stats[11] = n_follow;   // literal tasks: straight from k_seed_fast, punted by k_seed_walk, second-pass follow-ups of what k_seed_walk found
 		for (int k = 0; k < 16; ++k) stats[16 + k] = counters[20 + k];
 	}
 	return (int64_t)n;

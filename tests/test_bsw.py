@@ -29,7 +29,7 @@ def emul(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-w", "-o", so, os.path.join(ROOT, "tests", "emul", "bsw_emul.cpp")])
     L = C.CDLL(so)
     L.bsw_emul.restype = C.c_uint64
-    L.bsw_emul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_int] * 7 + [C.c_void_p, C.c_uint32, C.c_int]
+    L.bsw_emul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_int] * 7 + [C.c_void_p, C.c_uint32, C.c_int, C.c_int]
     return L
 
 
@@ -39,11 +39,11 @@ def full_pairs(p8):
     return p
 
 
-def run_emul(L, pairs, ref, qer, w, o_del, e_del, o_ins, e_ins, zdrop, eb, mat, stride=1, wide=0):
+def run_emul(L, pairs, ref, qer, w, o_del, e_del, o_ins, e_ins, zdrop, eb, mat, stride=1, wide=0, qpack=0):
     out = np.ascontiguousarray(pairs, np.int32).copy()
     m = np.ascontiguousarray(mat, np.int8)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    cells = L.bsw_emul(p(out), p(ref), p(qer), out.shape[0], w, o_del, e_del, o_ins, e_ins, zdrop, eb, p(m), stride, wide)
+    cells = L.bsw_emul(p(out), p(ref), p(qer), out.shape[0], w, o_del, e_del, o_ins, e_ins, zdrop, eb, p(m), stride, wide, qpack)
     return out, int(cells)
 
 
@@ -56,12 +56,12 @@ def test_oracle_bsw_equals_golden(oracle_lib, bsw_golden):
         assert np.array_equal(got[:, :8], pairs[:, :8]) and cells > 0
 
 
-@pytest.mark.parametrize("stride,wide", [(1, 0), (5, 1), (3, 0)])
-def test_kernel_source_equals_golden(emul, oracle_lib, bsw_golden, stride, wide):
+@pytest.mark.parametrize("stride,wide,qpack", [(1, 0, 0), (5, 1, 0), (3, 0, 0), (4, 0, 1), (2, 1, 1)])
+def test_kernel_source_equals_golden(emul, oracle_lib, bsw_golden, stride, wide, qpack):
     g = bsw_golden
     pairs = full_pairs(g["pairs"])
     for k, (w, o_del, e_del, o_ins, e_ins, zdrop, eb, a, b) in enumerate(g["opts"].tolist()):
-        got, cells = run_emul(emul, pairs, g["seq_buf_ref"], g["seq_buf_qer"], w, o_del, e_del, o_ins, e_ins, zdrop, eb, oracle_lib.bsw_mat(a, b), stride, wide)
+        got, cells = run_emul(emul, pairs, g["seq_buf_ref"], g["seq_buf_qer"], w, o_del, e_del, o_ins, e_ins, zdrop, eb, oracle_lib.bsw_mat(a, b), stride, wide, qpack)
         assert np.array_equal(got[:, 8:], g["res%d" % k]), k
         _, ocells = oracle_lib.oracle_bsw(pairs, g["seq_buf_ref"], g["seq_buf_qer"], w, o_del, e_del, o_ins, e_ins, zdrop, eb, oracle_lib.bsw_mat(a, b))
         assert cells == ocells   # the same cells, not just the same answers
@@ -91,6 +91,8 @@ def test_oracle_and_kernel_source_equal_reference_bsw(emul, oracle_lib, case):
     assert np.array_equal(got2, want) and cells2 == cells
     got3, cells3 = run_emul(emul, pairs, ref, qer, kw["w"], kw["o_del"], kw["e_del"], kw["o_ins"], kw["e_ins"], kw["zdrop"], kw["end_bonus"], oracle_lib.bsw_mat(a, b), 2, 1)
     assert np.array_equal(got3, want) and cells3 == cells
+    got4, cells4 = run_emul(emul, pairs, ref, qer, kw["w"], kw["o_del"], kw["e_del"], kw["o_ins"], kw["e_ins"], kw["zdrop"], kw["end_bonus"], oracle_lib.bsw_mat(a, b), 4, 0, 1)
+    assert np.array_equal(got4, want) and cells4 == cells   # query read from its packed copy (the shared-memory kernel)
     if case in ("default", "clean"):   # what CompSeed really calls: the SIMD twins, each on its class of pairs (comp_seed.cpp:1556-1564)
         m8 = (pairs[:, 3] < 128) & (pairs[:, 4] < 128) & (pairs[:, 5] + np.minimum(pairs[:, 3], pairs[:, 4]) < 128)
         v8, _ = oracle_lib.ref_bsw(np.ascontiguousarray(pairs[m8]), ref, qer, mode=1, **kw)

@@ -58,6 +58,10 @@ def test_bsw_equals_oracle(cuda_lib, oracle_lib, case):
         ms, gcells = ex.run_staged(kw["w"], opt)
         assert gcells == cells and ms > 0
     assert np.array_equal(ex.fetch(pairs.copy()), want)
+    # the kernel with its DP rows in the HBM scratch instead of shared memory (what long queries fall back to): same answers
+    ex.set_rows_in_smem(False)
+    ms, gcells = ex.run_staged(kw["w"], opt)
+    assert gcells == cells and np.array_equal(ex.fetch(pairs.copy()), want)
     ex.close()
 
 
