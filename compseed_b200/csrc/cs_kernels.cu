@@ -382,8 +382,10 @@ enum { ST_FETCH = 0, ST_R1_PIVOT, ST_FILTER, ST_FWD, ST_BWD_INIT, ST_BWD_SWEEP, 
 #endif
 #ifdef CS_STATS   // diagnostics build: event counters (scripts/spec_stats.py)
 #define STAT(k) (++sst[k])
+#define STATG(k) atomicAdd(a.counters + (k), 1ull)   // where the tasks of the literal kernel come from: counters[9..14] (unused slots of k_seed's own)
 #else
 #define STAT(k) ((void)0)
+#define STATG(k) ((void)0)
 #endif
 #ifndef CS_SPEC
 #define CS_SPEC 1          // 0: never take the speculative unique-match path (literal sweeps only)
@@ -1208,16 +1210,16 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 		}
 		if (cmin != 1 || !(d >= K || ((kmask >> (d - 1)) & 1))) { // pass 2 with a list, or L itself not pushed
 			if (cmin != 1) STAT(4); else STAT(5);
-			if (d < K && __popc(kmask) <= CS_WALK_MAX && cmin < 0x80000000ull) defer_walk(cx, cmin, d, kmask);
+			if (d < K && cmin < 0x80000000ull) defer_walk(cx, cmin, d, kmask);   // (however many entries: k_seed_walk's K-mer probe after the longest one leaves few)
 			else if (CS_WALK_L && d >= K && d < 256 && cmin < 0x80000000ull) defer_walk_l(cx, round, cmin, d, c0, c1, c2);
-			else defer_call(cx, cmin);
+			else { defer_call(cx, cmin); STATG(9); }
 			continue;
 		}
 		if (!unique) { // a short L that still has several occurrences (the next mismatch came before the match was unique): its
 			STAT(6);    // backward sweeps are bwt_extend steps like those of any other short match -- k_seed_walk does them
 			if (d < K) { defer_walk(cx, cmin, d, kmask); pend_y |= 1u << 23; }   // bit 23: L first, then the K-mer probe decides about the rest
 			else if (CS_WALK_L && d < 256) defer_walk_l(cx, round, cmin, d, c0, c1, c2);
-			else defer_call(cx, cmin);
+			else { defer_call(cx, cmin); STATG(10); }
 			continue;
 		}
 
@@ -1252,15 +1254,15 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			if (!has_n(bi, K)) { absent = pt_count(key_of(bi, K)) == 0; ++n_probe; }
 			if (!absent) { // every pushed match has to be looked at.  Beyond K bases only size changes before the match was unique are pushed:
 				STAT(8);    // none if it was unique by then (otherwise the literal kernel takes the call)
-				if (udepth > K) { defer_call(cx, cmin); continue; }
+				if (udepth > K) { defer_call(cx, cmin); STATG(10); continue; }
 				rest = d < K ? kmask & ~(1u << (d - 1)) : probe_bits(1, K - 1);
 				if (udepth >= 1 && udepth < 32) rest &= (1u << (udepth - 1)) - 1u;   // from udepth on the size stays 1: not pushed (bwt.c:311)
 			}
 		}
 		STAT(10);
-		if (end - (bi + 1) >= opt.min_seed_len && nmem >= a.mem_cap) { defer_call(cx, cmin); continue; }   // scratch full: the literal kernel stores it
+		if (end - (bi + 1) >= opt.min_seed_len && nmem >= a.mem_cap) { defer_call(cx, cmin); STATG(11); continue; }   // scratch full: the literal kernel stores it
 		// (each entry is a walk of its own in one lane of k_seed_walk: calls with many of them would hold their warp up)
-		if (__popc(rest) > CS_WALK_MAX) { defer_call(cx, cmin); continue; }
+		if (__popc(rest) > CS_WALK_MAX) { defer_call(cx, cmin); STATG(11); continue; }
 		// they come after L in the sweep order: k_seed_walk starts its containment test from L's start
 		if (rest) defer_walk(cx, cmin, d < 31 ? d : 31, rest | ((uint32_t)(bi + 2) << 18));
 		n_ext += r_ext; n_call += r_call;
@@ -1312,9 +1314,9 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 				bool done = true;
 				if (R < K && km == 0) { STAT(12); n_ext += (uint32_t)R; }              // nothing pushable: the call returns no SMEM
 				else if (pend_y != 0) done = false;                                     // (one call can wait to be queued: the regular path takes this one)
-				else if (R < K && __popc(km) <= CS_WALK_MAX) { STAT(13); pend_y = (uint32_t)cx2 | (2u << 16) | ((uint32_t)R << 18) | 0x80000000u; pend_z = 2u; pend_bits = km; }
+				else if (R < K) { STAT(13); pend_y = (uint32_t)cx2 | (2u << 16) | ((uint32_t)R << 18) | 0x80000000u; pend_z = 2u; pend_bits = km; }
 				else if (CS_WALK_L && R >= K) { STAT(14); defer_walk_l(cx2, 2, 2, R, 0, 0, 0); }   // (its interval is not known here)
-				else { STAT(14); pend_y = (uint32_t)cx2 | (2u << 16); pend_z = 2u; }
+				else { STAT(14); STATG(14); pend_y = (uint32_t)cx2 | (2u << 16); pend_z = 2u; }
 				if (done) p2done |= 1ull << nmem;
 			} else STAT(15);
 		}
@@ -1359,7 +1361,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_fast(
 #ifndef CS_R3_QUORUM
 #define CS_R3_QUORUM 8
 #endif
-__global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(DevIndex I, SeedArgs a)
+__global__ void __launch_bounds__(CS_FAST_BLOCK, CS_WALK_MINBLOCKS) k_seed_walk(DevIndex I, SeedArgs a)
 {
 	constexpr int RW = CS_READ_SMEM;
 	extern __shared__ uint4 s_dyn[];
@@ -1369,7 +1371,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 	const size_t gtid = (size_t)blockIdx.x * CS_FAST_BLOCK + t;
 	cs_mem_t *const my = a.thread_mems + gtid * a.mem_cap;
 	const cs_seed_opt_t opt = a.opt;
-	const int kd = (int)I.kt_depth;
+	const int kd = (int)I.kt_depth, K = (int)I.pt_k;
 	uint32_t n_ext = 0, n_call = 0, n_two = 0, n_req = 0;   // n_req: executed gathers (Occ sectors, table entries, filter words)
 	bool exhausted = false;
 
@@ -1384,6 +1386,12 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 		uint64_t v = rd_word(wi) >> sh;
 		if (sh) v |= rd_word(wi + 1) << (64 - sh);
 		return v & ((1ull << (2 * cnt)) - 1);
+	};
+	auto nmask_window = [&](int pos) -> uint32_t { // bit j: q[pos + j] is ambiguous or past the end of the read
+		uint32_t wi = (uint32_t)pos >> 5, sh = (uint32_t)pos & 31;
+		uint32_t m = nm_word(wi) >> sh;
+		if (sh) m |= nm_word(wi + 1) << (32 - sh);
+		return m;
 	};
 
 	for (;;) {
@@ -1403,16 +1411,15 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 		}
 		if (__all_sync(0xffffffffu, !active)) break;
 		const uint32_t rd = item.x;
-		const int cx = (int)(item.y & 0xffff), round = (int)((item.y >> 16) & 3);
-		const int d = (int)(((item.y >> 18) & 31) | (((item.y >> 24) & 7) << 5));
-		bool lprobe = ((item.y >> 23) & 1) != 0;                    // the longest entry is L itself; see below
-		bool lfirst = active && ((item.y >> 27) & 1) != 0;          // ... and has K or more bases: not among the bits, its interval comes with the task
-		const uint64_t cmin = item.z;
-		uint32_t bits = active ? a.defer_bits[q] : 0u;
-		const int ls0 = (int)(bits >> 18);                          // 1 + start of the SMEM k_seed_fast already found for this call (0: none)
-		bits &= 0x3ffffu;
-		uint4 lx = make_uint4(0, 0, 0, 0);
-		if (lfirst) lx = a.defer_lx[q];
+		const int cx0 = (int)(item.y & 0xffff), round = (int)((item.y >> 16) & 3);
+		const int d0 = (int)(((item.y >> 18) & 31) | (((item.y >> 24) & 7) << 5));
+		const bool lfirst0 = active && ((item.y >> 27) & 1) != 0;   // the longest entry is L itself, K or more bases: not among the bits, its interval comes with the task
+		const uint64_t cmin0 = item.z;
+		uint32_t bits0 = active ? a.defer_bits[q] : 0u;
+		const int ls00 = (int)(bits0 >> 18);                        // 1 + start of the SMEM k_seed_fast already found for this call (0: none)
+		bits0 &= 0x3ffffu;
+		uint64_t lx0 = 0, lx1 = 0, lx2 = 0;
+		if (lfirst0) { uint32_t dummy; unpack_entry(a.defer_lx[q], lx0, lx1, lx2, dummy); }
 		int len = 0;
 		if (active) {
 			const uint32_t o = a.off[rd];
@@ -1426,139 +1433,211 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_walk(
 			}
 		}
 		uint32_t nm = 0, t_ext = 0, t_call = 0;
-		bool first = ls0 == 0, punt = false;
-		int last_start = ls0 - 1;
-		// The loops below are made warp-uniform with votes: left to themselves the lanes drift apart (their entries take
-		// the table or the FM-index at different steps) and the hardware ends up running them one after the other.
-		while (__any_sync(0xffffffffu, (bits || lfirst) && !punt)) { // entries, longest first
-			const bool on = (bits || lfirst) && !punt;
-			int e = 0;
-			uint64_t c0 = 0, c1 = 0, c2 = 0;
-			bool go = false;
-			if (on && lfirst) { // L = q[cx, cx+d), d >= K: always pushed (the forward pass's last interval, bwt.c:317,321)
-				lfirst = false;
-				e = d;
-				uint32_t dummy;
-				unpack_entry(lx, c0, c1, c2, dummy);
-				if (c2 == 0) { // interval not known (the call was answered from the repeat lengths): table, then forward bwt_extend steps
-					kt_lookup(I, (uint32_t)kd, key_of(cx, kd), c0, c1, c2); ++n_req;
-					for (int k = kd; k < e; ++k) {
+		// filter bits of the windows e = elo .. ehi of a call (pivot cx, min_intv cmin), as k_seed_fast's probe_bits: bit e-1 <=> the K-mer
+		// ending e bases after the pivot occurs >= min(cmin, 3) times; windows that reach into an N / before the read start have no bit
+		auto probe_bits_w = [&](int cx, uint64_t cmin, int elo, int ehi) -> uint32_t {
+			int nl = 0;                                             // N-free run left of the pivot, capped at 31 bases
+			{
+				const int s0 = cx >= 31 ? cx - 31 : 0, cl = cx - s0;
+				if (cl > 0) {
+					const uint32_t m = (nmask_window(s0) & ((1u << cl) - 1u)) << (32 - cl);
+					nl = m ? __clz((int)m) : cl;
+				}
+			}
+			const int e0 = K - nl < 1 ? 1 : K - nl;
+			const uint32_t omin = cmin > 3 ? 4u : (uint32_t)cmin;
+			uint32_t mask = 0;
+			if (elo < e0) elo = e0;
+			if (ehi > K - 1) ehi = K - 1;
+			for (int eb = 0; eb < 18; eb += 6) { // six independent gathers at a time
+				uint32_t cnt[6];
+#pragma unroll
+				for (int u = 0; u < 6; ++u) {
+					const int e = eb + u + 1;
+					cnt[u] = 0;
+					if (e >= elo && e <= ehi) { const uint64_t key = key_of(cx + e - K, K); cnt[u] = (gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3; ++n_req; }
+				}
+#pragma unroll
+				for (int u = 0; u < 6; ++u) if (cnt[u] == 3 || (cnt[u] != 0 && cnt[u] >= omin)) mask |= 1u << (eb + u);
+			}
+			return mask;
+		};
+		// ONE bwt_smem1a call whose forward pass is known (pivot cx, min_intv cmin, longest forward match of d bases): its list walked
+		// entry by entry, longest first; SMEMs of >= min_seed_len bases are appended to my[nm..].  on: this lane has such a call.
+		// Returns true if the call has to go to the literal kernel instead.
+		// The loops are made warp-uniform with votes: left to themselves the lanes drift apart (their entries take the table or the
+		// FM-index at different steps) and the hardware ends up running them one after the other.
+		auto run_list = [&](bool on_call, int cx, uint64_t cmin, int d, uint32_t bits, bool lfirst, uint64_t l0, uint64_t l1, uint64_t l2, int ls0) -> bool {
+			const bool lgiven = on_call && lfirst;                  // (the other entries of such a call are not known yet)
+			bool first = ls0 == 0, punt = false;
+			// After the LONGEST entry of a list has been walked to the position bi where it fails, every other entry of >= K - (cx - bi) bases,
+			// extended that far, starts with q[bi, bi+K): one probe of that K-mer decides about all of them (below).  k_seed_fast has
+			// already done that for the tasks that follow an SMEM of its own (ls0 != 0).
+			bool lprobe = on_call && ls0 == 0;
+			int last_start = ls0 - 1;
+			if (!on_call) { bits = 0; lfirst = false; }
+			while (__any_sync(0xffffffffu, (bits || lfirst) && !punt)) { // entries, longest first
+				const bool on = (bits || lfirst) && !punt;
+				int e = 0;
+				uint64_t c0 = 0, c1 = 0, c2 = 0;
+				bool go = false;
+				if (on && lfirst) { // L = q[cx, cx+d), d >= K: always pushed (the forward pass's last interval, bwt.c:317,321)
+					lfirst = false;
+					e = d;
+					c0 = l0; c1 = l1; c2 = l2;
+					if (c2 == 0) { // interval not known (the call was answered from the repeat lengths): table, then forward bwt_extend steps
+						kt_lookup(I, (uint32_t)kd, key_of(cx, kd), c0, c1, c2); ++n_req;
+						for (int k = kd; k < e; ++k) {
+							uint64_t o0, o1, o2; uint32_t two;
+							dev_extend(I, c0, c1, c2, 3 - base_at(cx + k), 0, o0, o1, o2, two);
+							c0 = o0; c1 = o1; c2 = o2; ++t_call; n_two += two; n_req += 1u + two;
+						}
+					}
+					go = true;
+				} else if (on) {
+					e = 32 - __clz((int)bits);
+					bits &= ~(1u << (e - 1));
+					// the interval of q[cx, cx+e) ...
+					kt_lookup(I, (uint32_t)(e < kd ? e : kd), key_of(cx, e < kd ? e : kd), c0, c1, c2); ++n_req;
+					for (int k = kd; k < e; ++k) { // ... deeper than the table: forward bwt_extend steps
 						uint64_t o0, o1, o2; uint32_t two;
 						dev_extend(I, c0, c1, c2, 3 - base_at(cx + k), 0, o0, o1, o2, two);
 						c0 = o0; c1 = o1; c2 = o2; ++t_call; n_two += two; n_req += 1u + two;
 					}
-				}
-				go = true;
-			} else if (on) {
-				e = 32 - __clz((int)bits);
-				bits &= ~(1u << (e - 1));
-				// the interval of q[cx, cx+e) ...
-				kt_lookup(I, (uint32_t)(e < kd ? e : kd), key_of(cx, e < kd ? e : kd), c0, c1, c2); ++n_req;
-				for (int k = kd; k < e; ++k) { // ... deeper than the table: forward bwt_extend steps
-					uint64_t o0, o1, o2; uint32_t two;
-					dev_extend(I, c0, c1, c2, 3 - base_at(cx + k), 0, o0, o1, o2, two);
-					c0 = o0; c1 = o1; c2 = o2; ++t_call; n_two += two; n_req += 1u + two;
-				}
-				go = true;
-				if (e < d) { // pushed only if the next forward step changed the size (bwt.c:311-312)
-					uint64_t o0, o1, o2;
-					if (e + 1 <= kd) { kt_lookup(I, (uint32_t)(e + 1), key_of(cx, e + 1), o0, o1, o2); ++n_req; }
-					else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - base_at(cx + e), 0, o0, o1, o2, two); ++t_call; n_two += two; n_req += 1u + two; }
-					if (o2 == c2) go = false;
-				}
-			}
-			const bool walked = go;
-			// backward sweeps of this entry alone (bwt.c:326-345)
-			int bi = cx - 1;
-			for (int steps = 0; __any_sync(0xffffffffu, go); ++steps) {
-				if (go) {
-					const int b = bi >= 0 ? base_at(bi) : 4;
-					if (b > 3) go = false;                              // read start / N: no bwt_extend (bwt.c:330)
-					else if (steps >= CS_WALK_STEPS && ls0 == 0) { punt = true; go = false; }   // (a task that follows an SMEM of k_seed_fast is finished here)
-					else {
-						const int new_len = cx + e - bi;
+					go = true;
+					if (e < d) { // pushed only if the next forward step changed the size (bwt.c:311-312)
 						uint64_t o0, o1, o2;
-						++t_ext;
-						if (new_len <= kd) { kt_lookup(I, (uint32_t)new_len, key_of(bi, new_len), o0, o1, o2); ++n_req; }
-						else { uint32_t two; dev_extend(I, c0, c1, c2, b, 1, o0, o1, o2, two); ++t_call; n_two += two; n_req += 1u + two; }
-						if (o2 < cmin) go = false;                      // bwt.c:331
-						else { c0 = o0; c1 = o1; c2 = o2; --bi; }
+						if (e + 1 <= kd) { kt_lookup(I, (uint32_t)(e + 1), key_of(cx, e + 1), o0, o1, o2); ++n_req; }
+						else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - base_at(cx + e), 0, o0, o1, o2, two); ++t_call; n_two += two; n_req += 1u + two; }
+						if (o2 == c2) go = false;
 					}
 				}
-			}
-			if (!walked || punt) continue;
-			if (first || bi + 1 < last_start) { // bwt.c:332-336
-				first = false; last_start = bi + 1;
-				if (cx + e - (bi + 1) >= opt.min_seed_len) { // bwamem.c:231-233,247
-					if (nm >= a.mem_cap) { punt = true; continue; }
-					uint4 *p = reinterpret_cast<uint4*>(my + nm);
-					p[0] = make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)c1, (uint32_t)(c1 >> 32));
-					p[1] = make_uint4((uint32_t)c2, (uint32_t)(c2 >> 32), (uint32_t)(cx + e), (uint32_t)(bi + 1));
-					++nm;
-				}
-			}
-			if (lprobe) { // that was L (k_seed_fast's argument): the other entries of >= K - (cx - bi) bases all start with q[bi, bi+K)
-				lprobe = false;                                     // once extended to bi; if that K-mer does not occur they all end there, contained in L
-				const bool lgiven = ((item.y >> 27) & 1) != 0;      // (the other entries of such a task are not known yet)
-				if (bi < 0 || base_at(bi) > 3) bits = 0;            // read start / N: every interval ends here (bwt.c:331)
-				else {
-					const int K = (int)I.pt_k, need_d = K - (cx - bi);
-					const uint32_t shallow = need_d > 1 ? bits & ((1u << (need_d - 1)) - 1u) : 0u;
-					if (bits != shallow || lgiven) { // some entry is (may be) long enough for the probe to decide
-						const uint32_t wi = (uint32_t)bi >> 5, sh = (uint32_t)bi & 31;
-						uint32_t nmw = nm_word(wi) >> sh;
-						if (sh) nmw |= nm_word(wi + 1) << (32 - sh);
-						const uint64_t key = key_of(bi, K);
-						// "does not occur" for a call with min_intv = cmin: fewer than cmin occurrences (the filter counts up to 3)
-						const bool absent = !(nmw & ((1u << K) - 1u)) && ((gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) < (cmin > 3 ? 3u : (uint32_t)cmin);
-						++n_req;
-						if (absent) bits = shallow;                     // else every entry is walked
-						else if (lgiven) punt = true;                   // ... which the literal kernel does: this task does not know them
-					}
-					if (lgiven && !punt && need_d > 1) { // the shallow entries of such a task: the filter bits of e = 1 .. need_d - 1, as k_seed_fast's probe_bits
-						int nl = 0;                                     // N-free run left of the pivot, capped at 31 bases
-						{
-							const int s0 = cx >= 31 ? cx - 31 : 0, cl = cx - s0;
-							if (cl > 0) {
-								const uint32_t w2 = (uint32_t)s0 >> 5, s2 = (uint32_t)s0 & 31;
-								uint32_t m = nm_word(w2) >> s2;
-								if (s2) m |= nm_word(w2 + 1) << (32 - s2);
-								m = (m & ((1u << cl) - 1u)) << (32 - cl);
-								nl = m ? __clz((int)m) : cl;
-							}
+				const bool walked = go;
+				// backward sweeps of this entry alone (bwt.c:326-345)
+				int bi = cx - 1;
+				for (int steps = 0; __any_sync(0xffffffffu, go); ++steps) {
+					if (go) {
+						const int b = bi >= 0 ? base_at(bi) : 4;
+						if (b > 3) go = false;                              // read start / N: no bwt_extend (bwt.c:330)
+						else if (steps >= CS_WALK_STEPS && ls0 == 0) { punt = true; go = false; }   // (a task that follows an SMEM of k_seed_fast is finished here)
+						else {
+							const int new_len = cx + e - bi;
+							uint64_t o0, o1, o2;
+							++t_ext;
+							if (new_len <= kd) { kt_lookup(I, (uint32_t)new_len, key_of(bi, new_len), o0, o1, o2); ++n_req; }
+							else { uint32_t two; dev_extend(I, c0, c1, c2, b, 1, o0, o1, o2, two); ++t_call; n_two += two; n_req += 1u + two; }
+							if (o2 < cmin) go = false;                      // bwt.c:331
+							else { c0 = o0; c1 = o1; c2 = o2; --bi; }
 						}
-						const int e0 = K - nl < 1 ? 1 : K - nl;
-						const uint32_t omin = cmin > 3 ? 4u : (uint32_t)cmin;
-						for (int e2 = e0; e2 < need_d; ++e2) {
-							const uint64_t key = key_of(cx + e2 - K, K);
-							const uint32_t cnt = (gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3;
+					}
+				}
+				if (!walked || punt) continue;
+				if (first || bi + 1 < last_start) { // bwt.c:332-336
+					first = false; last_start = bi + 1;
+					if (cx + e - (bi + 1) >= opt.min_seed_len) { // bwamem.c:231-233,247
+						if (nm >= a.mem_cap) { punt = true; continue; }
+						uint4 *p = reinterpret_cast<uint4*>(my + nm);
+						p[0] = make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)c1, (uint32_t)(c1 >> 32));
+						p[1] = make_uint4((uint32_t)c2, (uint32_t)(c2 >> 32), (uint32_t)(cx + e), (uint32_t)(bi + 1));
+						++nm;
+					}
+				}
+				if (lprobe) { // that was the longest entry: the K-mer probe at the position where it failed
+					lprobe = false;
+					if (bi < 0 || base_at(bi) > 3) bits = 0;            // read start / N: every interval ends here (bwt.c:331)
+					else {
+						const int need_d = K - (cx - bi);
+						const uint32_t shallow = need_d > 1 ? bits & ((1u << (need_d - 1)) - 1u) : 0u;
+						if (bits != shallow || lgiven) { // some entry is (may be) long enough for the probe to decide
+							const uint64_t key = key_of(bi, K);
+							// "does not occur" for a call with min_intv = cmin: fewer than cmin occurrences (the filter counts up to 3)
+							const bool absent = !(nmask_window(bi) & ((1u << K) - 1u)) && ((gather_u32(I.pt + (key >> 4)) >> (2 * ((uint32_t)key & 15))) & 3) < (cmin > 3 ? 3u : (uint32_t)cmin);
 							++n_req;
-							if (cnt == 3 || (cnt != 0 && cnt >= omin)) bits |= 1u << (e2 - 1);
+							if (absent) bits = shallow;                     // they all end at bi, contained in the SMEM just found; else every entry is walked
+							else if (lgiven) punt = true;                   // ... which the literal kernel does: this call does not know them
 						}
+						if (lgiven && !punt && need_d > 1) bits = probe_bits_w(cx, cmin, 1, need_d - 1);   // the shallow entries of such a call
+						if (__popc(bits) > CS_WALK_MAX) punt = true;        // too many for one lane: the literal kernel takes the call
 					}
-					if (__popc(bits) > CS_WALK_MAX) punt = true;        // too many for one lane: the literal kernel takes the call
 				}
 			}
-		}
+			return punt;
+		};
+		const bool punt = run_list(active, cx0, cmin0, d0, bits0, lfirst0, lx0, lx1, lx2, ls00);
 		if (punt) { // the literal kernel takes it (it runs after this one)
+			STATG(12);
 			a.defer_q[q].y = item.y & 0x7fffffffu;
 			a.lit_q[atomicAdd(a.n_lit, 1u)] = q;
 		}
 		const bool fin = active && !punt;
-		if (fin) { n_ext += t_ext; n_call += t_call; }
-		// second-pass calls of what a first-pass call found (bwamem.c:238-249): ordinary calls for the literal kernel
-		if (fin && round == 1)
-			for (uint32_t m = 0; m < nm; ++m) {
-				const uint4 v = reinterpret_cast<const uint4*>(my + m)[1];
-				const int s = (int)v.w, e = (int)v.z;
-				const uint64_t sz = (uint64_t)v.x | ((uint64_t)v.y << 32);
-				if (e - s < opt.split_len || sz > (uint64_t)opt.split_width) continue;
-				const uint32_t q2 = atomicAdd(a.n_defer, 1u);
-				if (q2 < a.defer_cap) {
-					a.defer_q[q2] = make_uint4(rd, (uint32_t)((s + e) >> 1) | (2u << 16), (uint32_t)(sz + 1), atomicExch(a.read_last_q + rd, q2));
-					a.lit_q[atomicAdd(a.n_lit, 1u)] = q2;
+		// second-pass calls of what a first-pass call found (bwamem.c:238-249): forward pass here (table jump, then bwt_extend steps until
+		// fewer than min_intv rows are left), then the list as above; the ones that do not fit go to the literal kernel as ordinary calls
+		{
+			const uint32_t nm_main = (fin && round == 1) ? nm : 0u;
+			uint32_t fu = 0;
+			bool fgo = nm_main > 0;
+			while (__any_sync(0xffffffffu, fgo)) {
+				int cx2 = 0; uint64_t cmin2 = 2; bool have = false;
+				if (fgo) {
+					while (fu < nm_main) {
+						const uint4 v = reinterpret_cast<const uint4*>(my + fu)[1];
+						++fu;
+						const int s = (int)v.w, e = (int)v.z;
+						const uint64_t sz = (uint64_t)v.x | ((uint64_t)v.y << 32);
+						if (e - s < opt.split_len || sz > (uint64_t)opt.split_width) continue;
+						cx2 = (s + e) >> 1; cmin2 = sz + 1; have = true;
+						break;
+					}
+					if (!have) fgo = false;
+				}
+				uint64_t c0 = 0, c1 = 0, c2 = 0;
+				int i = cx2 + 1;
+				bool go = have;
+				if (have) {
+					STATG(13);
+					const int b = base_at(cx2);
+					c0 = l2_at(I, b) + 1; c1 = l2_at(I, 3 - b) + 1; c2 = l2_at(I, b + 1) - l2_at(I, b);   // bwt_set_intv, bwt.h:82
+					if (!(nmask_window(cx2) & ((1u << kd) - 1u))) { // q[cx2, cx2+kd) is inside the read and unambiguous: its table entry directly
+						uint64_t o0, o1, o2;
+						kt_lookup(I, (uint32_t)kd, key_of(cx2, kd), o0, o1, o2); ++n_req;
+						if (o2 >= cmin2) { c0 = o0; c1 = o1; c2 = o2; i = cx2 + kd; t_ext += (uint32_t)(kd - 1); }
+					}
+				}
+				while (__any_sync(0xffffffffu, go)) { // bwt.c:304-321 without the pushes
+					if (go) {
+						const int b = i < len ? base_at(i) : 4;
+						if (b > 3) go = false;
+						else {
+							const int new_len = i + 1 - cx2;
+							uint64_t o0, o1, o2;
+							++t_ext;
+							if (new_len <= kd) { kt_lookup(I, (uint32_t)new_len, key_of(cx2, new_len), o0, o1, o2); ++n_req; }
+							else { uint32_t two; dev_extend(I, c0, c1, c2, 3 - b, 0, o0, o1, o2, two); ++t_call; n_two += two; n_req += 1u + two; }
+							if (o2 < cmin2) go = false;                     // bwt.c:313
+							else { c0 = o0; c1 = o1; c2 = o2; ++i; }
+						}
+					}
+				}
+				const int d2 = i - cx2;
+				uint32_t bits2 = 0;
+				bool lf2 = false, lit2 = false;
+				if (have) {
+					if (d2 >= K) { if (d2 < 256) lf2 = true; else lit2 = true; }
+					else bits2 = probe_bits_w(cx2, cmin2, 1, d2);
+				}
+				const uint32_t nm_before = nm;
+				const bool punt2 = run_list(have && !lit2, cx2, cmin2, d2, bits2, lf2, c0, c1, c2, 0);
+				if (have && (punt2 || lit2)) {
+					nm = nm_before;
+					const uint32_t q2 = atomicAdd(a.n_defer, 1u);
+					if (q2 < a.defer_cap) {
+						a.defer_q[q2] = make_uint4(rd, (uint32_t)cx2 | (2u << 16), (uint32_t)cmin2, atomicExch(a.read_last_q + rd, q2));
+						a.lit_q[atomicAdd(a.n_lit, 1u)] = q2;
+					}
 				}
 			}
+		}
+		if (fin) { n_ext += t_ext; n_call += t_call; }
 		{
 			uint32_t cnt = fin ? nm : 0;
 			const unsigned long long o = warp_alloc(a.pool_used, cnt);

@@ -20,6 +20,9 @@
 #ifndef CS_FAST_MINBLOCKS
 #define CS_FAST_MINBLOCKS 4
 #endif
+#ifndef CS_WALK_MINBLOCKS
+#define CS_WALK_MINBLOCKS CS_FAST_MINBLOCKS   // CTAs per SM the register allocation of k_seed_walk is tuned for
+#endif
 #ifndef CS_WALK_MAX
 #define CS_WALK_MAX 6           // short forward matches a call may have to be walked by k_seed_walk (else k_seed)
 #endif

@@ -12,8 +12,8 @@ import bench
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 ref_len = int(sys.argv[2]) if len(sys.argv) > 2 else 3_100_000_000
 repeat = len(sys.argv) > 3 and sys.argv[3] == "repeat"
-NAMES = ["warp trips", "lane kt lookups", "lane FM extends", "lane text-path trips", "calls", "spec calls", "spec success",
-         "spec stop (nothing pushable)", "spec abort: stop", "spec abort: K-mer present", "spec abort: probe not applicable",
+NAMES = ["warp trips", "lane kt lookups", "lane FM extends", "lane text-path trips", "calls", "literal tasks from k_seed_fast: list call with > 6 entries / d >= 256", "... L not unique with d >= 256 / unique deeper than K with the K-mer present",
+         "... scratch full / > 6 shallow entries", "literal tasks punted by k_seed_walk", "second-pass follow-ups of what k_seed_walk found", "pass-2 answered at the SMEM with > 6 entries",
          "lane LF trips", "lane bookkeeping entries", "filter requests", "jump rejects", "lane text-compare trips"]
 if repeat:
     ref = synth.repeat_rich_reference(ref_len, seed=41, n_segdup=2000, segdup_len=5000, n_tandem=600)

@@ -9,6 +9,7 @@
 #include <cstddef>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 #include <vector>
 #include <algorithm>
 
