@@ -514,13 +514,14 @@ struct Ctrl { // zeroed before every run; copied back after it
 	uint32_t n_defer;        // calls handed on by k_seed_fast (and k_seed_walk)
 	uint32_t n_lit;          // of those, for k_seed
 	uint32_t n_defer_fast;   // n_defer when k_seed_fast ended
-	uint32_t pad0;
+	uint32_t n_walk;         // walk tasks among them
 	unsigned long long pool_used;
 	unsigned long long counters[4 + 32];   // [4..19] k_seed, [20..35] k_seed_fast: event counters of a -DCS_STATS diagnostics build, else 0
 	unsigned long long sa_work, lf_steps;
 	unsigned long long req[6];             // executed memory requests per kernel (SeedArgs::req)
 	unsigned long long tot12, tot3, tot_seeds;   // 64-bit batch totals: mems of passes 1-2, of pass 3, seeds
 	int error, pad1;
+	uint32_t walk_hist[64], walk_cursor[64];   // counting sort of the walk tasks by expected length
 	uint32_t n_mems, n_seeds;
 	unsigned long long chain_work;         // work counter of k_chain_build
 	uint32_t n_chains, n_cseeds, n_nodes, pad2;
@@ -558,7 +559,7 @@ struct Slot {
 	uint8_t *d_bases; uint32_t *d_off;
 	uint64_t *d_packed; uint32_t *d_nmask;   // 2-bit packed reads + ambiguity mask (k_pack_reads)
 	uint4 *d_defer_q;                         // calls the fast kernel hands to the literal kernel (SeedArgs::defer_q)
-	uint32_t *d_read_last_q, *d_x_n, *d_defer_bits, *d_lit_q; uint64_t *d_x_off; uint4 *d_defer_lx, *d_thread_lx;
+	uint32_t *d_read_last_q, *d_x_n, *d_defer_bits, *d_lit_q; uint64_t *d_x_off; uint4 *d_defer_lx, *d_thread_lx; uint32_t *d_walk_order;
 	cs_mem_t *d_stage;                        // collect: a read's sources gathered before the sort
 	bool used_fast;
 	bool packed_input;                        // the batch came through cs_seed_batch_submit_packed: d_packed / d_nmask are the input
@@ -627,7 +628,7 @@ static void slot_free(Slot *s)
 	cudaFreeHost(s->h_cs_qbeg); cudaFreeHost(s->h_cs_len);
 	cudaFreeHost(s->h_bases); cudaFreeHost(s->h_off); cudaFreeHost(s->h_mem_off); cudaFreeHost(s->h_seed_off);
 	cudaFreeHost(s->h_mems); cudaFreeHost(s->h_rbeg); cudaFreeHost(s->h_ctrl);
-	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_defer_bits); cudaFree(s->d_defer_lx); cudaFree(s->d_thread_lx); cudaFree(s->d_lit_q); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
+	cudaFree(s->d_bases); cudaFree(s->d_off); cudaFree(s->d_packed); cudaFree(s->d_nmask); cudaFree(s->d_defer_q); cudaFree(s->d_read_last_q); cudaFree(s->d_x_n); cudaFree(s->d_defer_bits); cudaFree(s->d_defer_lx); cudaFree(s->d_thread_lx); cudaFree(s->d_walk_order); cudaFree(s->d_lit_q); cudaFree(s->d_x_off); cudaFree(s->d_stage); cudaFree(s->d_ctrl); cudaFree(s->d_thread_mems); cudaFree(s->d_spill);
 	cudaFree(s->d_pool); cudaFree(s->d_mems); cudaFree(s->d_read_pool_off); cudaFree(s->d_read_n_mems);
 	cudaFree(s->d_r3_mems); cudaFree(s->d_r3_n_mems); cudaFree(s->d_tot_n_mems);
 	cudaFree(s->d_mem_off); cudaFree(s->d_read_n_seeds); cudaFree(s->d_seed_off); cudaFree(s->d_rows); cudaFree(s->d_scan_tmp);
@@ -760,6 +761,7 @@ extern "C" cs_ctx_t *cs_ctx_create_ex(const cs_index_t *idx, uint32_t max_reads,
 		CK(cudaMalloc(&s->d_x_n, (size_t)ctx->defer_cap * 4));
 		CK(cudaMalloc(&s->d_defer_bits, (size_t)ctx->defer_cap * 4));
 		CK(cudaMalloc(&s->d_defer_lx, (size_t)ctx->defer_cap * sizeof(uint4)));
+		CK(cudaMalloc(&s->d_walk_order, (size_t)ctx->defer_cap * 4));
 		CK(cudaMalloc(&s->d_lit_q, (size_t)ctx->defer_cap * 4));
 		CK(cudaMalloc(&s->d_read_last_q, ((size_t)max_reads + 1) * 4));
 		CK(cudaMalloc(&s->d_stage, ctx->max_mems * sizeof(cs_mem_t)));
@@ -871,7 +873,7 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 	a.packed = s->d_packed; a.nmask = s->d_nmask; a.off_bias = s->packed_input ? s->off_bias : 0u;
 	a.next_read = s->d_ctrl->next_read;
 	a.defer_q = nullptr; a.defer_cap = ctx->defer_cap; a.n_defer = &s->d_ctrl->n_defer;
-	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n; a.defer_bits = s->d_defer_bits; a.defer_lx = s->d_defer_lx; a.thread_lx = s->d_thread_lx; a.lit_q = s->d_lit_q; a.n_lit = &s->d_ctrl->n_lit; a.n_defer_fast = &s->d_ctrl->n_defer_fast;
+	a.read_last_q = s->d_read_last_q; a.x_off = s->d_x_off; a.x_n = s->d_x_n; a.defer_bits = s->d_defer_bits; a.defer_lx = s->d_defer_lx; a.thread_lx = s->d_thread_lx; a.lit_q = s->d_lit_q; a.n_lit = &s->d_ctrl->n_lit; a.n_defer_fast = &s->d_ctrl->n_defer_fast; a.walk_order = s->d_walk_order; a.n_walk = &s->d_ctrl->n_walk;
 	s->used_fast = false;
 	a.thread_mems = s->d_thread_mems; a.mem_cap = ctx->mem_cap;
 	a.spill = s->d_spill; a.spill_cap = ctx->spill_cap;
@@ -890,6 +892,13 @@ static int enqueue_run(cs_ctx *ctx, Slot *s, const cs_seed_opt_t *opt, bool allo
 		CK(cudaEventRecord(s->ev[6], s->stream));
 		CK(cudaMemcpyAsync(&s->d_ctrl->n_defer_fast, &s->d_ctrl->n_defer, 4, cudaMemcpyDeviceToDevice, s->stream));
 		if (pass3 && overlap) CK(fork_r3(ctx->cfg.use_r3_fast != 0));
+		{ // the walk tasks, longest first (counting sort: count, scan, scatter)
+			const int go = std::max(1, std::min<int>(idx->n_sm * 8, (int)(((uint64_t)n + 2047) / 2048)));
+			k_walk_count<<<go, 256, 0, s->stream>>>(idx->d, a, s->d_ctrl->walk_hist);
+			k_walk_scan<<<1, 32, 0, s->stream>>>(s->d_ctrl->walk_hist, s->d_ctrl->walk_cursor, &s->d_ctrl->n_walk);
+			k_walk_scatter<<<go, 256, 0, s->stream>>>(idx->d, a, s->d_ctrl->walk_cursor, s->d_walk_order);
+			CK(cudaGetLastError()); ctx->n_launch += 3;
+		}
 		k_seed_walk<<<gf < 1 ? 1 : gf, CS_FAST_BLOCK, CS_FAST_SMEM_BYTES, s->stream>>>(idx->d, a);
 		CK(cudaGetLastError()); ++ctx->n_launch;
 		CK(cudaEventRecord(s->ev[7], s->stream));

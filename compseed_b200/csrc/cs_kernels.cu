@@ -1358,6 +1358,68 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_fast(
 // bases goes back to the literal kernel.
 // ---------------------------------------------------------------------------------------------
 #define CS_WALK_STEPS 96
+// The walk tasks of a batch in descending order of their expected length (counting sort over 64 classes: count, scan, scatter), so that
+// the 32 tasks a warp of k_seed_walk runs in lock step are of one size: left in queue order, a warp waits for its longest task with
+// 7 of 32 lanes busy (profiles/r02_ncu_all_kernels_base_*).  Expected length = extends of the longest entry (forward steps past the
+// table, the pushed test, >= K - e backward steps for a window that occurs) + a few per further entry; 24 for a list that starts with L.
+__device__ __forceinline__ uint32_t walk_cost_class(uint4 item, uint32_t bits, int K, int kd)
+{
+	uint32_t cost = ((item.y >> 27) & 1) ? 24u : 0u;
+	const uint32_t nb = bits & 0x3ffffu;
+	if (nb) {
+		const int e = 32 - __clz((int)nb);
+		cost += (uint32_t)((e > kd ? e - kd : 0) + 3 + (K > e ? K - e : 0)) + 4u * (uint32_t)(__popc(nb) - 1);
+	}
+	return cost < 63u ? cost : 63u;
+}
+__global__ void k_walk_count(DevIndex I, SeedArgs a, uint32_t *hist)
+{
+	__shared__ uint32_t s_h[64];
+	if (threadIdx.x < 64) s_h[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t nq = *a.n_defer_fast < a.defer_cap ? *a.n_defer_fast : a.defer_cap;
+	for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+		const uint4 item = a.defer_q[q];
+		if (item.y >> 31) atomicAdd(&s_h[walk_cost_class(item, a.defer_bits[q], (int)I.pt_k, (int)I.kt_depth)], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x < 64 && s_h[threadIdx.x]) atomicAdd(hist + threadIdx.x, s_h[threadIdx.x]);
+}
+__global__ void k_walk_scan(uint32_t *hist, uint32_t *cursor, uint32_t *n_walk)
+{ // one thread: 64 classes, the longest first
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		uint32_t acc = 0;
+		for (int c = 63; c >= 0; --c) { cursor[c] = acc; acc += hist[c]; }
+		*n_walk = acc;
+	}
+}
+__global__ void k_walk_scatter(DevIndex I, SeedArgs a, uint32_t *cursor, uint32_t *order)
+{
+	__shared__ uint32_t s_h[64], s_base[64];
+	const uint32_t nq = *a.n_defer_fast < a.defer_cap ? *a.n_defer_fast : a.defer_cap;
+	const uint32_t tile = blockDim.x * 8;
+	for (uint32_t t0 = blockIdx.x * tile; t0 < nq; t0 += gridDim.x * tile) { // a tile per CTA and trip: one global atomic per class and tile
+		if (threadIdx.x < 64) s_h[threadIdx.x] = 0;
+		__syncthreads();
+		uint32_t cls[8], pos[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const uint32_t q = t0 + k * blockDim.x + threadIdx.x;
+			cls[k] = 0xffffffffu;
+			if (q < nq) {
+				const uint4 item = a.defer_q[q];
+				if (item.y >> 31) { cls[k] = walk_cost_class(item, a.defer_bits[q], (int)I.pt_k, (int)I.kt_depth); pos[k] = atomicAdd(&s_h[cls[k]], 1u); }
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x < 64) s_base[threadIdx.x] = s_h[threadIdx.x] ? atomicAdd(cursor + threadIdx.x, s_h[threadIdx.x]) : 0u;
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < 8; ++k) if (cls[k] != 0xffffffffu) order[s_base[cls[k]] + pos[k]] = t0 + k * blockDim.x + threadIdx.x;
+		__syncthreads();
+	}
+}
+
 #ifndef CS_R3_QUORUM
 #define CS_R3_QUORUM 8
 #endif
@@ -1401,11 +1463,9 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_WALK_MINBLOCKS) k_seed_walk(
 		for (;;) { // queue slots for the whole warp at once; lanes that drew a task of the literal kernel draw again
 			const bool want = !exhausted && !active;
 			const uint32_t take = warp_take(a.next_read + 3, want);
-			if (want) {
-				const uint32_t nq = *a.n_defer_fast;             // the queue as k_seed_fast left it: entries appended by this kernel (second-pass
-				q = take;                                        // calls for k_seed) may still be in flight, over stale entries of an earlier batch
-				if (q >= (nq < a.defer_cap ? nq : a.defer_cap)) exhausted = true;
-				else { item = a.defer_q[q]; active = (item.y >> 31) != 0; }
+			if (want) { // the walk tasks k_seed_fast queued, longest first (k_walk_scatter); entries appended by this kernel are not among them
+				if (take >= *a.n_walk) exhausted = true;
+				else { q = a.walk_order[take]; item = a.defer_q[q]; active = true; }
 			}
 			if (!__any_sync(0xffffffffu, !exhausted && !active)) break;
 		}

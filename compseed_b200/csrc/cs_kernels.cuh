@@ -59,7 +59,9 @@ struct SeedArgs {
 	uint32_t *lit_q, *n_lit;    // the walk = 0 entries of defer_q (indices), listed for k_seed
 	uint32_t defer_cap;
 	uint32_t *n_defer;
-	const uint32_t *n_defer_fast; // n_defer as it stood when k_seed_fast ended (copied on the stream): what k_seed_walk scans
+	const uint32_t *n_defer_fast; // n_defer as it stood when k_seed_fast ended (copied on the stream): what the walk tasks are picked from
+	const uint32_t *walk_order;   // [n_walk] the walk tasks among them (indices into defer_q), longest first (k_walk_count / _scan / _scatter)
+	const uint32_t *n_walk;
 	uint32_t *read_last_q;      // [n_reads] last deferred call of each read (chain head), ~0 if none
 	uint64_t *x_off;            // [defer_cap] where the mems of a deferred call start in pool
 	uint32_t *x_n;              // [defer_cap]
@@ -127,6 +129,9 @@ __global__ void k_seed(DevIndex I, SeedArgs a);
 __global__ void k_seed_long(DevIndex I, SeedArgs a);
 __global__ void k_seed_fast(DevIndex I, SeedArgs a);
 __global__ void k_seed_walk(DevIndex I, SeedArgs a);
+__global__ void k_walk_count(DevIndex I, SeedArgs a, uint32_t *hist);
+__global__ void k_walk_scan(uint32_t *hist, uint32_t *cursor, uint32_t *n_walk);
+__global__ void k_walk_scatter(DevIndex I, SeedArgs a, uint32_t *cursor, uint32_t *order);
 __global__ void k_seed_r3_fast(DevIndex I, SeedArgs a);
 __global__ void k_seed_r3(DevIndex I, SeedArgs a);
 __global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, const uint32_t *read_last_q, const uint4 *defer_q, const uint32_t *x_n,

@@ -30,6 +30,7 @@ static inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; retu
 static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p |= v; return o; }
 static inline uint32_t atomicCAS(uint32_t *p, uint32_t cmp, uint32_t v) { uint32_t o = *p; if (o == cmp) *p = v; return o; }
 static inline uint32_t atomicExch(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
+static inline void __syncthreads() {}
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline bool __any_sync(unsigned, bool p) { return p; }
 static inline bool __all_sync(unsigned, bool p) { return p; }
@@ -167,6 +168,13 @@ int64_t seed_emul_run(void *e, uint32_t n_reads, const uint8_t *bases, const uin
 	k_seed_fast(d, a);
 	n_defer_fast = n_defer;
 	const uint32_t n_lit_fast = n_lit;
+	std::vector<uint32_t> walk_order(defer_cap, 0xffffffffu);
+	uint32_t hist[64] = {0}, cursor[64] = {0}, n_walk = 0;
+	a.walk_order = walk_order.data(); a.n_walk = &n_walk;
+	// (k_walk_count / k_walk_scatter use CTA-wide shared histograms and barriers: not emulated; the same counting sort with the kernels' cost function)
+	for (uint32_t qq = 0; qq < n_defer_fast; ++qq) if (defer_q[qq].y >> 31) ++hist[walk_cost_class(defer_q[qq], defer_bits[qq], (int)d.pt_k, (int)d.kt_depth)];
+	k_walk_scan(hist, cursor, &n_walk);
+	for (uint32_t qq = 0; qq < n_defer_fast; ++qq) if (defer_q[qq].y >> 31) walk_order[cursor[walk_cost_class(defer_q[qq], defer_bits[qq], (int)d.pt_k, (int)d.kt_depth)]++] = qq;
 	if (n_defer > defer_cap) return -102;
 	k_seed_walk(d, a);
 	if (error) return error;
