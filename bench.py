@@ -445,7 +445,10 @@ def main():
             cs.host_register(pk); cs.host_register(nm)
         else:
             cs.host_register(bases)   # the reads sit in page-locked host memory, as the bench contract asks
-        ms_ = cs.MultiSeeder([idx], batch_reads=bs, max_read_len=args.read_len, n_slots=args.e2e_slots, mems_per_read=14, seeds_per_read=20, config=ccfg)
+        # (with chaining two batches in flight: its per-seed scratch is 3 GB per slot, and next to the 155 GB index three slots do not fit)
+        n_slots = min(args.e2e_slots, 2) if chains else args.e2e_slots
+        torch.cuda.empty_cache()
+        ms_ = cs.MultiSeeder([idx], batch_reads=bs, max_read_len=args.read_len, n_slots=n_slots, mems_per_read=14, seeds_per_read=20, config=ccfg)
         if chains:      # mem_chain + mem_chain_flt on the GPU too: only the filtered chains come back
             ms_.set_chaining(contig_lens(args.ref_len))
 
@@ -492,7 +495,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t[0])
         out = {"value": total_reads / (e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": info["wire_bytes"] * world,
-               "batch_reads": bs, "slots": args.e2e_slots,
+               "batch_reads": bs, "slots": n_slots,
                "api": "cs_multi_submit%s / cs_multi_wait: the library's own pipeline (one host thread per GPU, no Python in the loop), two read sets in flight" % ("_packed" if packed_in else ""),
                "input": "2-bit packed reads + N mask in page-locked host memory, packed by the host outside the timed region (cs_pack_reads_host64)" if packed_in else "nt4 bytes in page-locked host memory",
                "output": ("filtered chains (mem_chain + mem_chain_flt run on the GPU: 16 B per chain, 9 B per chain seed, 8 B of offsets per read) by DMA into "
@@ -512,7 +515,7 @@ def main():
         e2e, e2e_head, e2e_launches = run_e2e(args.e2e_input == "packed", True)
         # the same path with chaining + chain filtering on the GPU: what a host that takes chains would see
         ch, chain_head, _ = run_e2e(args.e2e_input == "packed", True, chains=True)
-        e2e["with_chaining_on_the_gpu"] = {k: ch[k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "output")}
+        e2e["with_chaining_on_the_gpu"] = {k: ch[k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "slots", "output")}
         if args.e2e_input == "packed":   # the same with nt4 bytes crossing the link, for comparison (not the headline)
             alt, _, _ = run_e2e(False, False)
             e2e["nt4_bytes_input_variant"] = {k: alt[k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "input")}
