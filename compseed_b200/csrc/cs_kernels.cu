@@ -1341,21 +1341,35 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_fast(DevIndex I, SeedArgs a) { seed_fast_body<CS_READ_SMEM>(I, a); }
 
 // ---------------------------------------------------------------------------------------------
-// Walk kernel: the deferred calls whose interval list is SHORT forward matches only.
+// Walk kernel: the deferred calls whose interval list can be walked ENTRY BY ENTRY.
 //
-// k_seed_fast hands over, with their filter bits, the calls whose longest forward match L has fewer
-// than K bases and is either not pushable itself (first pass) or belongs to the second pass: the list
-// of the literal pass then holds at most K - 1 matches E_e = q[cx, cx+e), one per filter bit.
 // In bwt_smem1a's backward phase a list entry's fate does not depend on the others except through
 // the start of the last SMEM found: a longer entry is a right-extension of a shorter one, so it dies
-// no later; hence when E_e fails to extend no longer entry is alive (curr->n == 0, bwt.c:332), and
+// no later; hence when an entry fails to extend no longer entry is alive (curr->n == 0, bwt.c:332), and
 // duplicates dropped by the size test (bwt.c:338) would fail at the same base as the entry that
 // shadows them and be rejected as contained (bwt.c:333).  So each entry is walked backward alone,
 // longest first, with plain bwt_extend steps (table or FM-index), and the containment test is applied
 // in that order.  An entry is in the list only if the forward pass pushed it: the size changed at
 // the next base (bwt.c:311-312) or it is the forward pass's last interval (bwt.c:317,321).
-// One task per lane; all lanes run the same phases.  A walk that does not end within CS_WALK_STEPS
-// bases goes back to the literal kernel.
+//
+// What k_seed_fast hands over, with the filter bits of the entries E_e = q[cx, cx+e), e < K (one bit per
+// K-mer window that occurs often enough, §"Occurrence filter" at k_seed):
+//   - calls whose longest forward match L has fewer than K bases (L not pushable itself, L not yet one
+//     occurrence, or a second-pass call);
+//   - calls whose L has K or more bases but several occurrences: L comes first, with its interval
+//     (defer_lx; computed here when the call was answered from the repeat lengths), the other entries
+//     are looked for only if the probe below leaves any;
+//   - the shallow entries left over after k_seed_fast resolved L itself (ls0 != 0).
+// After the LONGEST entry has been walked to the position bi where it fails, every other entry of
+// >= K - (cx - bi) bases, extended that far, starts with q[bi, bi+K): if that K-mer occurs fewer than
+// min_intv times they all end there, contained in the SMEM just found -- one filter probe instead of
+// one walk per entry, which is what makes lists of any size acceptable (a call that starts in the
+// middle of an error-free stretch has one entry per K-mer of the stretch).
+// The second-pass calls of what a first-pass call finds here (bwamem.c:238-249) are run in place:
+// forward pass, then the list.  One task per lane; all lanes run the same phases; the tasks come in
+// descending order of their expected length (k_walk_*), so that a warp's 32 tasks are of one size.
+// What does not fit -- entries that survive the probe (> CS_WALK_MAX of them), a walk of more than
+// CS_WALK_STEPS bases, a full scratch -- goes to the literal kernel.
 // ---------------------------------------------------------------------------------------------
 #define CS_WALK_STEPS 96
 // The walk tasks of a batch in descending order of their expected length (counting sort over 64 classes: count, scan, scatter), so that
