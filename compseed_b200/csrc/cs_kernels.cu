@@ -2098,9 +2098,11 @@ __global__ void k_mem_counts(const uint32_t *n12, const uint32_t *n3, const uint
 }
 
 __global__ void k_collect_rows(CollectArgs a)
-{ // eight lanes per read
-	const uint32_t sub = threadIdx.x & 7;
+{ // eight lanes per read, one mem per lane and trip: a mem has one seed on ordinary data (x[2] == 1), up to max_occ on repeats
+	const uint32_t lane = threadIdx.x & 31, sub = lane & 7;
+	const unsigned gmask = 0xffu << (lane & 24);
 	const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
+	const uint64_t max_occ = (uint64_t)a.opt.max_occ;
 	for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < a.n_reads; r += ngroups) {
 		const uint32_t n = a.mem_off[r + 1] - a.mem_off[r];
 		const cs_mem_t *mem = a.mems + a.mem_off[r];
@@ -2109,12 +2111,32 @@ __global__ void k_collect_rows(CollectArgs a)
 			if (sub == 0) atomicMin(a.error, CS_E_OVERFLOW);
 			continue;
 		}
-		for (uint32_t m = 0; m < n; ++m) {
-			uint64_t x0 = mem[m].x[0], x2 = mem[m].x[2];
-			uint32_t cnt = seeds_of(x2, a.opt.max_occ);
-			uint64_t step = x2 > (uint64_t)a.opt.max_occ ? x2 / (uint64_t)a.opt.max_occ : 1;
-			for (uint32_t k = sub; k < cnt; k += 8) a.seed_rows[o + k] = x0 + (uint64_t)k * step;
-			o += cnt;
+		for (uint32_t m0 = 0; m0 < n; m0 += 8) {
+			const uint32_t m = m0 + sub;
+			uint64_t x0 = 0, step = 1;
+			uint32_t cnt = 0;
+			if (m < n) {
+				const uint4 v0 = reinterpret_cast<const uint4*>(mem + m)[0], v1 = reinterpret_cast<const uint4*>(mem + m)[1];
+				x0 = (uint64_t)v0.x | ((uint64_t)v0.y << 32);
+				const uint64_t x2 = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
+				cnt = seeds_of(x2, a.opt.max_occ);
+				if (x2 > max_occ) step = x2 / max_occ;           // (the division only where the occurrences are sampled, bwamem.c:391)
+			}
+			uint32_t incl = cnt;                                 // where each lane's seeds start: prefix sum over the eight lanes
+#pragma unroll
+			for (int d = 1; d < 8; d <<= 1) { const uint32_t v = __shfl_up_sync(gmask, incl, d, 8); if ((int)sub >= d) incl += v; }
+			const uint32_t total = __shfl_sync(gmask, incl, 7, 8);
+			const uint32_t big = __ballot_sync(gmask, cnt > 4) >> (lane & 24) & 0xffu;
+			if (!big) { // the usual case: every lane writes its own few seeds
+				for (uint32_t k = 0; k < cnt; ++k) a.seed_rows[o + (incl - cnt) + k] = x0 + (uint64_t)k * step;
+			} else { // repeats: the eight lanes share the seeds of one mem after the other
+				for (uint32_t j = 0; j < 8 && m0 + j < n; ++j) {
+					const uint64_t jx0 = __shfl_sync(gmask, x0, (int)j, 8), jstep = __shfl_sync(gmask, step, (int)j, 8);
+					const uint32_t jcnt = __shfl_sync(gmask, cnt, (int)j, 8), jo = __shfl_sync(gmask, incl - cnt, (int)j, 8);
+					for (uint32_t k = sub; k < jcnt; k += 8) a.seed_rows[o + jo + k] = jx0 + (uint64_t)k * jstep;
+				}
+			}
+			o += total;
 		}
 	}
 }
