@@ -20,6 +20,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <thread>
+#include <vector>
+#include <atomic>
 #include <cub/device/device_radix_sort.cuh>
 #include "cs_internal.h"
 
@@ -43,6 +46,23 @@ __global__ void k_bsw_keys(const PairIn *in, uint32_t n, uint32_t *keys, uint32_
 }
 
 } // namespace
+
+// Host loops over the pairs of a batch (conversion in, scores out) and the copies of the two sequence buffers into page-locked
+// memory, split over the host's threads: at 50 M pairs/s on the device one thread doing them would be the bottleneck.
+template <class F> static void host_par_for(uint64_t n, uint64_t grain, F fn)
+{
+	unsigned nt = std::thread::hardware_concurrency();
+	if (nt > 16) nt = 16;
+	if (nt < 2 || n < 2 * grain) { fn((uint64_t)0, n); return; }
+	if ((uint64_t)nt > n / grain) nt = (unsigned)(n / grain);
+	std::vector<std::thread> th;
+	const uint64_t per = (n + nt - 1) / nt;
+	for (unsigned k = 0; k < nt; ++k) {
+		const uint64_t lo = (uint64_t)k * per, hi = std::min<uint64_t>(n, lo + per);
+		if (lo < hi) th.emplace_back([=]() { fn(lo, hi); });
+	}
+	for (auto &t : th) t.join();
+}
 
 struct cs_bsw {
 	int device, n_sm;
@@ -165,23 +185,44 @@ extern "C" int cs_bsw_stage(cs_bsw_t *b, const cs_seqpair_t *pairs, const uint8_
 	if (ref_bytes > b->cap_ref && bsw_alloc_seq(&b->h_ref, &b->d_ref, &b->cap_ref, ref_bytes + ref_bytes / 4) != CS_OK) return CS_E_CUDA;
 	if (qer_bytes > b->cap_qer && bsw_alloc_seq(&b->h_qer, &b->d_qer, &b->cap_qer, qer_bytes + qer_bytes / 4) != CS_OK) return CS_E_CUDA;
 	uint32_t mq = 1; int64_t mh = 0; bool neg = false;
-	for (uint32_t i = 0; i < n_pairs; ++i) {
-		const cs_seqpair_t &p = pairs[i];
-		if (p.len2 < 1 || p.len1 < 0 || p.idr < 0 || p.idq < 0 || (uint64_t)p.idr + (uint64_t)p.len1 > ref_bytes || (uint64_t)p.idq + (uint64_t)p.len2 > qer_bytes)
+	{
+		std::atomic<uint32_t> a_mq(1), a_bad(0xffffffffu);
+		std::atomic<long long> a_mh(0);
+		std::atomic<bool> a_neg(false);
+		PairIn *h_in = b->h_in;
+		host_par_for(n_pairs, 1u << 16, [&, h_in](uint64_t lo, uint64_t hi) {
+			uint32_t lmq = 1, lbad = 0xffffffffu; long long lmh = 0; bool lneg = false;
+			for (uint64_t i = lo; i < hi; ++i) {
+				const cs_seqpair_t &p = pairs[i];
+				if (p.len2 < 1 || p.len1 < 0 || p.idr < 0 || p.idq < 0 || (uint64_t)p.idr + (uint64_t)p.len1 > ref_bytes || (uint64_t)p.idq + (uint64_t)p.len2 > qer_bytes) {
+					if ((uint32_t)i < lbad) lbad = (uint32_t)i;
+					continue;
+				}
+				h_in[i].idr = p.idr; h_in[i].idq = p.idq; h_in[i].len1 = p.len1; h_in[i].len2 = p.len2; h_in[i].h0 = p.h0;
+				if ((uint32_t)p.len2 > lmq) lmq = (uint32_t)p.len2;
+				if (p.h0 > lmh) lmh = p.h0;
+				if (p.h0 < 0) lneg = true;
+			}
+			uint32_t cur = a_mq.load(); while (lmq > cur && !a_mq.compare_exchange_weak(cur, lmq)) {}
+			long long ch = a_mh.load(); while (lmh > ch && !a_mh.compare_exchange_weak(ch, lmh)) {}
+			uint32_t cb = a_bad.load(); while (lbad < cb && !a_bad.compare_exchange_weak(cb, lbad)) {}
+			if (lneg) a_neg.store(true);
+		});
+		if (a_bad.load() != 0xffffffffu) {
+			const uint32_t i = a_bad.load();
+			const cs_seqpair_t &p = pairs[i];
 			return cs_set_err(CS_E_ARG, "pair %u: idr %d len1 %d / idq %d len2 %d do not fit the buffers (%llu, %llu bytes; a query has at least one base)",
 			                  i, p.idr, p.len1, p.idq, p.len2, (unsigned long long)ref_bytes, (unsigned long long)qer_bytes);
-		b->h_in[i].idr = p.idr; b->h_in[i].idq = p.idq; b->h_in[i].len1 = p.len1; b->h_in[i].len2 = p.len2; b->h_in[i].h0 = p.h0;
-		if ((uint32_t)p.len2 > mq) mq = (uint32_t)p.len2;
-		if (p.h0 > mh) mh = p.h0;
-		if (p.h0 < 0) neg = true;
+		}
+		mq = a_mq.load(); mh = a_mh.load(); neg = a_neg.load();
 	}
 	if (mq >= (1u << 17)) return cs_set_err(CS_E_ARG, "query of %u bases: longer than a read can be (65535, comp_seed.h:39)", mq);
 	b->max_qlen_staged = mq; b->max_h0_staged = mh; b->neg_h0_staged = neg;
 	{
 		auto pinned = [](const void *p) { cudaPointerAttributes pa; const bool ok = cudaPointerGetAttributes(&pa, p) == cudaSuccess && pa.type == cudaMemoryTypeHost; cudaGetLastError(); return ok; };
 		const uint8_t *sr = seq_buf_ref, *sq = seq_buf_qer;
-		if (!pinned(sr)) { memcpy(b->h_ref, sr, ref_bytes); sr = b->h_ref; }
-		if (!pinned(sq)) { memcpy(b->h_qer, sq, qer_bytes); sq = b->h_qer; }
+		if (!pinned(sr)) { uint8_t *dst = b->h_ref; host_par_for(ref_bytes, 4u << 20, [=](uint64_t lo, uint64_t hi) { memcpy(dst + lo, sr + lo, hi - lo); }); sr = b->h_ref; }
+		if (!pinned(sq)) { uint8_t *dst = b->h_qer; host_par_for(qer_bytes, 4u << 20, [=](uint64_t lo, uint64_t hi) { memcpy(dst + lo, sq + lo, hi - lo); }); sq = b->h_qer; }
 		CK(cudaMemcpyAsync(b->d_in, b->h_in, (size_t)n_pairs * sizeof(PairIn), cudaMemcpyHostToDevice, b->stream));
 		CK(cudaMemcpyAsync(b->d_ref, sr, ref_bytes, cudaMemcpyHostToDevice, b->stream));
 		CK(cudaMemcpyAsync(b->d_qer, sq, qer_bytes, cudaMemcpyHostToDevice, b->stream));
@@ -276,9 +317,14 @@ extern "C" int cs_bsw_fetch(cs_bsw_t *b, cs_seqpair_t *pairs)
 	{ const int rc = cs_use_device(b->device); if (rc != CS_OK) return rc; }
 	CK(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)b->n_pairs * 24, cudaMemcpyDeviceToHost, b->stream));
 	CK(cudaStreamSynchronize(b->stream));
-	for (uint32_t i = 0; i < b->n_pairs; ++i) {
-		const int32_t *o = b->h_out + 6 * (size_t)i;
-		pairs[i].score = o[0]; pairs[i].tle = o[1]; pairs[i].gtle = o[2]; pairs[i].qle = o[3]; pairs[i].gscore = o[4]; pairs[i].max_off = o[5];
+	{
+		const int32_t *h_out = b->h_out;
+		host_par_for(b->n_pairs, 1u << 16, [=](uint64_t lo, uint64_t hi) {
+			for (uint64_t i = lo; i < hi; ++i) {
+				const int32_t *o = h_out + 6 * (size_t)i;
+				pairs[i].score = o[0]; pairs[i].tle = o[1]; pairs[i].gtle = o[2]; pairs[i].qle = o[3]; pairs[i].gscore = o[4]; pairs[i].max_off = o[5];
+			}
+		});
 	}
 	return CS_OK;
 fail:
