@@ -34,9 +34,9 @@ static inline void __syncthreads() {}
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline bool __any_sync(unsigned, bool p) { return p; }
 static inline bool __all_sync(unsigned, bool p) { return p; }
-template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
-template <class T> static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int, int = 32) { return v; }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
