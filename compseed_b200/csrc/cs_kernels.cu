@@ -937,7 +937,6 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 	int round = 1, x = 0;
 	uint32_t nmem = 0, old_n = 0, r2k = 0;
 	long long diag = 0; bool have_diag = false; int junk_at = -1;   // diagonal of the last one-occurrence SMEM this lane stored for the read; where its forward match failed on a base
-	int next_junk = -1; bool held = false; int held_cx = 0, held_n = 0; uint64_t held_cmin = 1;   // CS_PHASE: see the phase selection below
 	uint64_t p2done = 0;                                  // bit m: the second-pass call of my[m] has been dealt with where the SMEM was found (repeat lengths)
 
 	auto rd_word = [&](uint32_t wi) -> uint64_t { return s_rd[wi * CS_FAST_BLOCK + t]; };
@@ -1025,12 +1024,11 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 						s_rd[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.packed + w0 + wi) : 0ull;
 						s_nm[wi * CS_FAST_BLOCK + t] = wi < nw ? __ldg(a.nmask + w0 + wi) : 0xffffffffu;
 					}
-					nmem = 0; round = 1; x = 0; have = true; last_q = 0xffffffffu; p2done = 0; have_diag = false; junk_at = -1; next_junk = -1;
+					nmem = 0; round = 1; x = 0; have = true; last_q = 0xffffffffu; p2done = 0; have_diag = false; junk_at = -1;
 				}
 			}
 			bool finished = false;
-			if (have && !active && held) { cx = held_cx; cmin = held_cmin; active = true; held = false; }   // the call this lane was holding back
-			else if (have && !active) {
+			if (have && !active) {
 				if (round == 1) { // first pass of mem_collect_intv, bwamem.c:226-236
 					while (x < len && base_at(x) > 3) ++x;
 					if (x < len) { cx = x; cmin = 1; active = true; }
@@ -1066,22 +1064,6 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			if (!__any_sync(0xffffffffu, finished && !exhausted)) break;   // nobody is waiting for another read
 		}
 		if (__all_sync(0xffffffffu, !active)) break;
-		// ---- phase selection.  The calls of a read alternate between two kinds: one that starts where the last one-occurrence match
-		//      failed on a base (the read differs from the text there: its forward match is a chance match of ~16 bases, and what follows
-		//      is a row of filter probes), and one that starts inside the next stretch the read shares with the text (table, extends, SA,
-		//      text comparison both ways, inverse SA).  A warp whose lanes are at both kinds at once runs both instruction streams with a
-		//      third of its lanes each; so the warp runs the kind most of its lanes are at and the others hold their call back for one
-		//      iteration -- after which they are in step, because every read alternates.  (A lane is never held three times in a row.) ----
-		if (CS_PHASE) {
-			const bool junk = active && cmin == 1 && cx == next_junk;
-			const unsigned mj = __ballot_sync(0xffffffffu, junk), mg = __ballot_sync(0xffffffffu, active && !junk);
-			const unsigned fj = __ballot_sync(0xffffffffu, junk && held_n >= 2), fg = __ballot_sync(0xffffffffu, active && !junk && held_n >= 2);
-			bool run_junk = __popc(mj) > __popc(mg);
-			if (fj && !fg) run_junk = true;
-			if (fg && !fj) run_junk = false;
-			if (active && junk != run_junk) { held = true; held_cx = cx; held_cmin = cmin; ++held_n; active = false; }
-			else held_n = 0;
-		}
 		if ((t & 31) == 0) STAT(0);
 		if (!active) continue;     // exhausted lanes wait at the vote above
 		STAT(1); if (cmin != 1) STAT(2);
@@ -1217,7 +1199,6 @@ __device__ __forceinline__ void seed_fast_body(const DevIndex &I, const SeedArgs
 			r_ext += (uint32_t)jf + (on_base ? 1u : 0u) - (spec ? 1u : 0u);   // (speculative: the comparison started at the pivot itself)
 			if (on_base && tpos < I.seq_len) fail_at = i;
 		}
-		next_junk = fail_at;                                        // (CS_PHASE: the call that starts there is of the other kind)
 		const int end = i, d = end - cx;                            // the longest forward match is L = [cx, end)
 		if (round == 1) x = end;                                    // next pivot (bwt.c:323, bwamem.c:228)
 

@@ -32,9 +32,6 @@
 #ifndef CS_WALK_L
 #define CS_WALK_L 1             // calls whose longest forward match has >= K bases but several occurrences go to k_seed_walk (L first), not to k_seed
 #endif
-#ifndef CS_PHASE
-#define CS_PHASE 1               // k_seed_fast: a warp runs one kind of call per iteration (see the phase selection in the kernel)
-#endif
 #ifndef CS_SPEC_DIAG
 #define CS_SPEC_DIAG 0          // k_seed_fast: first-pass calls tried first on the diagonal of the read's last one-occurrence SMEM (needs the repeat lengths).
 #endif                          // Correct (tests/test_seed_emul.py runs it), but measured slower on cfg2 (4 M reads: 9.19 ms with, 8.70 ms without,
