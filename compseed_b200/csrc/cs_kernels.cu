@@ -1371,7 +1371,9 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_fast(
 // What does not fit -- entries that survive the probe (> CS_WALK_MAX of them), a walk of more than
 // CS_WALK_STEPS bases, a full scratch -- goes to the literal kernel.
 // ---------------------------------------------------------------------------------------------
+#ifndef CS_WALK_STEPS
 #define CS_WALK_STEPS 96
+#endif
 // The walk tasks of a batch in descending order of their expected length (counting sort over 64 classes: count, scan, scatter), so that
 // the 32 tasks a warp of k_seed_walk runs in lock step are of one size: left in queue order, a warp waits for its longest task with
 // 7 of 32 lanes busy (profiles/r02_ncu_all_kernels_base_*).  Expected length = extends of the longest entry (forward steps past the
