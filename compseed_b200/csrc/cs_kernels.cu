@@ -1912,7 +1912,7 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 		if (__all_sync(0xffffffffu, !active && !parked)) break;
 
 		// ---- the chain that starts at x ----
-		bool walk = false, from_text = false;                       // needs the literal walk / is resolved through the text
+		bool walk = false, from_text = false, pre_text = false;     // needs the literal walk / is resolved through the text (pre_text: if its repeat length says so)
 		if (!active) ;
 		else if (W >= 32 || opt.max_mem_intv < 2) walk = true;      // the shortcuts below assume a 1-row interval ends the chain
 		else if (x + W > len || (nmask_window(x) & ((1u << W) - 1u))) {
@@ -1921,6 +1921,11 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 			while (i < len && base_at(i) <= 3) ++i;
 			n_ext += (uint32_t)(i - x - 1);
 			x = i < len ? i + 1 : len;
+		} else if (I.rep && ms <= x && x + W <= me) {
+			// W lies inside the one-occurrence SMEM of the previous chain, at text position P: its first K bases occur once iff the
+			// longest repeat that starts at P is shorter than K.  One byte at a known place instead of the filter probe -- so the two
+			// inverse-SA gathers below do not have to wait for it: all three are issued together (a repeat, rare, throws them away)
+			pre_text = true;
 		} else {
 			const uint32_t c19 = (gather_u32(I.pt + (key_of(x, K) >> 4)) >> (2 * ((uint32_t)key_of(x, K) & 15))) & 3;
 			++n_probe;
@@ -1946,10 +1951,16 @@ __global__ void __launch_bounds__(CS_FAST_BLOCK, CS_FAST_MINBLOCKS) k_seed_r3_fa
 		// LF steps together: the loop is controlled by a vote so that the warp does not drift apart)
 		{
 			uint64_t r0 = 0, r1 = 0; int w0 = 0, w1 = 0;
-			if (from_text) {
+			if (from_text || pre_text) {
 				const uint64_t P = mtb + (uint64_t)(x - ms);
+				uint32_t R = 0;
+				if (pre_text) { R = gather_u8(I.rep + P); ++n_req; }
 				isa_near(P, r0, w0);
 				isa_near(I.seq_len - P - (uint64_t)W, r1, w1);
+				if (pre_text) {
+					if (R < (uint32_t)K) from_text = true;
+					else { walk = true; w0 = w1 = 0; }
+				}
 			}
 			while (__any_sync(0xffffffffu, (w0 | w1) != 0)) {
 				if (w0) { r0 = dev_lf(I, r0); --w0; ++n_req; }

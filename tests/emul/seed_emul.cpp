@@ -178,8 +178,20 @@ int64_t seed_emul_run(void *e, uint32_t n_reads, const uint8_t *bases, const uin
 	if (n_defer > defer_cap) return -102;
 	k_seed_walk(d, a);
 	if (error) return error;
-	// per read: what the two kernels stored ...
+	// third pass (text-assisted kernel; reads the first-pass SMEMs k_seed_fast left in the pool), when the options ask for it
+	const uint32_t kp1 = (uint32_t)opt->min_seed_len + 1;
+	std::vector<cs_mem_t> r3_mems((size_t)n_bases / kp1 + n_reads + 2);
+	std::vector<uint32_t> r3_n(n_reads + 1, 0);
+	if (opt->max_mem_intv > 0) {
+		a.r3_mems = r3_mems.data(); a.r3_n_mems = r3_n.data();
+		k_seed_r3_fast(d, a);
+		if (error) return error;
+	}
+	// per read: what the kernels stored ...
 	std::vector<std::vector<cs_mem_t>> per(n_reads);
+	if (opt->max_mem_intv > 0)
+		for (uint32_t r = 0; r < n_reads; ++r)
+			for (uint32_t m = 0; m < r3_n[r]; ++m) per[r].push_back(r3_mems[(size_t)(off[r] / kp1) + r + m]);
 	for (uint32_t r = 0; r < n_reads; ++r)
 		for (uint32_t m = 0; m < read_n_mems[r]; ++m) per[r].push_back(pool[read_pool_off[r] + m]);
 	for (uint32_t q = 0; q < n_defer_fast; ++q)
@@ -219,6 +231,7 @@ int64_t seed_emul_run(void *e, uint32_t n_reads, const uint8_t *bases, const uin
 	}
 	if (stats) {
 		for (int k = 0; k < 4; ++k) stats[k] = counters[k];
+		stats[12] = req[3];   // executed requests of the third-pass kernel
 		stats[4] = req[0]; stats[5] = req[1]; stats[6] = n_defer; stats[7] = n_lit; stats[8] = n_oracle;
 		for (int k = 40; k < 48; ++k) stats[k] = counters[k];
 		stats[9] = n_lit_fast; stats[10] = n_punt; stats[11] = n_follow;   // literal tasks: straight from k_seed_fast, punted by k_seed_walk, second-pass follow-ups of what k_seed_walk found

@@ -124,6 +124,22 @@ def test_diagonal_speculation_build_equals_the_oracle(emul_spec, name, mk, rd):
     assert int(stats[16 + 7]) > 0    # speculation taken
 
 
+@pytest.mark.parametrize("name,mk,rd", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("so", [(19, 28, 10, 20, 500), (19, 28, 10, 40, 50)], ids=["y20", "y40c50"])
+def test_third_pass_kernel_equals_the_oracle(emul, name, mk, rd, so):
+    """all three passes: k_seed_fast + k_seed_walk + k_seed_r3_fast (the text-assisted third pass) against the oracle's mem_collect_intv"""
+    ref = mk()
+    bases, off, _ = synth.simulate_reads(ref, rd["n"], rd["lens"], rd["err"], seed=13, n_rate=rd["n_rate"])
+    oi = O.OracleIndex.build(ref)
+    want = oi.seed(bases, off, min_seed_len=so[0], split_len=so[1], split_width=so[2], max_mem_intv=so[3], max_occ=so[4])
+    req = {}
+    for use_rep in (0, 1):
+        mem_off, mems, stats, _ = run_emul(emul, oi, bases, off, so, use_rep)
+        assert np.array_equal(mem_off, want.mem_off) and np.array_equal(mems, want.mems), (name, so, use_rep)
+        req[use_rep] = int(stats[12])
+    assert req[0] > 0 and req[1] > 0
+
+
 def test_repeat_lengths_match_their_definition(emul):
     """rep[p] against a brute-force count of occurrences on a small repeat-rich text."""
     ref = synth.repeat_rich_reference(6_000, seed=5, n_segdup=6, segdup_len=300, n_tandem=4)
