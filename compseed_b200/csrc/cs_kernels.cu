@@ -902,11 +902,13 @@ __device__ __forceinline__ unsigned long long warp_alloc(unsigned long long *ctr
 // sampled inverse SA).  It never builds an interval list.  It relies on the argument spelled out at
 // "unique-match paths" in seed_body: the call's only SMEM is the backward extension of the longest
 // forward match L when L is one occurrence and the K-mer at the position where L fails does not
-// occur in the text; and a call whose forward pass could not push anything returns nothing.  Any
-// CALL that does not fit (a shorter match could survive, pass 2 needs a list, scratch overflow) is
-// queued as (read, pivot, min_intv, pass) for k_seed, which executes it literally -- and, for a
-// first-pass call, the second-pass calls of the SMEMs it finds (bwamem.c:238-249 depend only on
-// their own SMEM).  The first pass goes on here: the next pivot is the end of the longest forward
+// occur in the text; and a call whose forward pass could not push anything returns nothing.  The
+// second-pass call of a one-occurrence SMEM is answered where the SMEM is found, from the repeat
+// lengths at its text position (DevIndex::rep), without the FM-index or the filter.  Any CALL that
+// does not fit (a shorter match could survive, pass 2 needs a list, scratch overflow) is queued as
+// (read, pivot, min_intv, pass): for k_seed_walk when its list can be walked entry by entry (see
+// there), else for k_seed, which executes it literally -- and, for a first-pass call, the
+// second-pass calls of the SMEMs it finds (bwamem.c:238-249 depend only on their own SMEM).  The first pass goes on here: the next pivot is the end of the longest forward
 // match (bwt.c:323), which this kernel knows exactly.  The collect pass merges a read's chain of
 // deferred results with the ones written here.  Results are bit-identical by construction; only the
 // share of deferred calls depends on the data (about 0.6 per read on the i.i.d. 3.1 Gbp

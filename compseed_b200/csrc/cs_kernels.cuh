@@ -49,9 +49,12 @@ struct SeedArgs {
 	const uint32_t *nmask;      // ambiguity / end-of-read mask, same word indexing
 	// scratch
 	uint32_t *next_read;        // work counters: [0] k_seed, [1] k_seed_r3, [2] k_seed_fast, [3] k_seed_walk
-	// calls k_seed_fast hands on: {read, pivot | pass << 16 | d << 18 | walk << 31, min_intv, previous deferred call of
-	// the same read or ~0}; walk = 1: for k_seed_walk, with the filter bits of its short matches in defer_bits[] and
-	// the length d of its longest forward match; walk = 0: for k_seed.  NULL: k_seed runs in read mode and takes every read.
+	// calls k_seed_fast hands on: {read, y, min_intv, previous deferred call of the same read or ~0} with
+	// y = pivot (bits 0-15) | pass (16-17) | d low 5 bits (18-22) | d high 3 bits (24-26) | L-first (27) | walk (31);
+	// walk = 1: for k_seed_walk, with the filter bits of its short matches in defer_bits[] (bits 18+ there: 1 + start of the
+	// SMEM k_seed_fast already stored for the call) and the length d of its longest forward match; L-first: that match has K
+	// or more bases and is walked first, its interval in defer_lx[]; walk = 0: for k_seed.
+	// NULL: k_seed runs in read mode and takes every read.
 	uint4 *defer_q;
 	uint32_t *defer_bits;
 	uint4 *thread_lx;           // [n_threads] where k_seed_fast keeps such an interval until the task has its queue slot
