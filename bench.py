@@ -651,7 +651,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(args, world), "sa_intv_device": args.sa_intv, "index_bytes_per_gpu": idx.device_bytes,
                        "result_neutral_structures": "dense SA, top-of-search k-mer table (depth <= 13), 2-bit occurrence filter (K <= 19), "
-                                                    "2-bit text + sampled inverse SA for unique matches (DESIGN.md section 5)",
+                                                    "2-bit text + sampled inverse SA for unique matches, repeat lengths (one byte per text position) (DESIGN.md section 5)",
                        "l2_policy": "inputs larger than L2 (index %.1f GB, reads %.1f GB per step)" % (idx.device_bytes / 1e9, bases.nbytes / 1e9),
                        "l2_persist_mb": args.l2_persist_mb, "overlap_streams": bool(args.overlap), "isa_intv": args.isa_intv, "lit_ctas_per_sm": args.lit_ctas,
                        "library_tag": os.environ.get("COMPSEED_LIB_TAG", ""),
