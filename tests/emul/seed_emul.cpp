@@ -1,10 +1,13 @@
-// TEST INFRASTRUCTURE ONLY.  Compiles compseed_b200/csrc/cs_kernels.cu as plain C++ (CUDA qualifiers defined away, warps of ONE
-// lane: a vote is the lane's own predicate, a shuffle returns the lane's own value) and runs, serially on the CPU, the index
-// construction kernels (re-layout, dense SA, top-of-search table, 2-bit text, occurrence filter, inverse SA, repeat lengths) and
-// the lane-independent seeding kernels k_seed_fast and k_seed_walk.  The calls those two hand on to the literal kernel k_seed
-// (whose occurrence filter is served by 32 cooperating lanes and is not emulated) are resolved with the oracle's bwt_smem1a
-// restatement, exactly as k_seed's call mode defines them.  tests/test_seed_emul.py compares the outcome with the oracle.
-// The shipped library never contains or runs this build: there is no CPU path in the product.
+// TEST INFRASTRUCTURE ONLY.  Compiles compseed_b200/csrc/cs_kernels.cu as plain C++ (CUDA qualifiers defined away) and runs its kernels
+// on the CPU: the index construction kernels (re-layout, dense SA, top-of-search table, 2-bit text, occurrence filter, inverse SA,
+// repeat lengths) serially, and the seeding kernels in one of two ways --
+//   seed_emul_run:   warps of ONE lane (a vote is the lane's own predicate, a shuffle returns the lane's own value), one host thread:
+//                    k_seed_fast, k_seed_walk, k_seed_r3_fast; the calls handed on to the literal kernel are resolved with the oracle's
+//                    bwt_smem1a restatement, exactly as k_seed's call mode defines them;
+//   seed_emul_run32: REAL warps, one host thread per lane, every warp intrinsic a rendezvous of the 32: all seeding kernels, the literal
+//                    k_seed (call mode and read mode) and the general third pass k_seed_r3 included; nothing is resolved by the oracle.
+// tests/test_seed_emul.py compares the outcome with the oracle.  The shipped library never contains or runs this build: there is no
+// CPU path in the product.
 #include <cstdint>
 #include <cstddef>
 #include <cstring>
@@ -12,6 +15,8 @@
 #include <cstdio>
 #include <vector>
 #include <algorithm>
+#include <thread>
+#include <pthread.h>
 
 #define CS_EMUL 1
 #define __global__
@@ -21,23 +26,55 @@
 #define __launch_bounds__(...)
 #define __shared__
 struct emul_dim3 { unsigned x, y, z; };
-static emul_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+static thread_local emul_dim3 threadIdx = {0, 0, 0};
+static emul_dim3 blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 v = {x, y, z, w}; return v; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
-template <class T, class U> static inline T atomicAdd(T *p, U v) { T o = *p; *p += (T)v; return o; }
-static inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
-static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p |= v; return o; }
-static inline uint32_t atomicCAS(uint32_t *p, uint32_t cmp, uint32_t v) { uint32_t o = *p; if (o == cmp) *p = v; return o; }
-static inline uint32_t atomicExch(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
+template <class T, class U> static inline T atomicAdd(T *p, U v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_SEQ_CST); }
+static inline int atomicMin(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline uint32_t atomicCAS(uint32_t *p, uint32_t cmp, uint32_t v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+static inline uint32_t atomicExch(uint32_t *p, uint32_t v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 static inline void __syncthreads() {}
-static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
-static inline bool __any_sync(unsigned, bool p) { return p; }
-static inline bool __all_sync(unsigned, bool p) { return p; }
-template <class T> static inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
-template <class T> static inline T __shfl_up_sync(unsigned, T v, int, int = 32) { return v; }
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
+// Warp intrinsics.  g_lanes == 1: a warp of ONE lane (a vote is the lane's own predicate, a shuffle returns its own value) -- the
+// kernels then run in a single host thread.  g_lanes == 32: a real warp, one host thread per lane (emul_warp below); every intrinsic is a
+// rendezvous of the 32 threads (all masks in the seeding kernels are full), so the vote-controlled loops, the warp-aggregated
+// atomics and the cooperative occurrence filter of the literal kernel execute with their real semantics.
+static int g_lanes = 1;
+static pthread_barrier_t g_bar;
+static uint64_t g_slot[32];
+static inline void warp_rendezvous() { pthread_barrier_wait(&g_bar); }
+static inline unsigned __ballot_sync(unsigned, bool p)
+{
+	if (g_lanes == 1) return p ? 1u : 0u;
+	g_slot[threadIdx.x & 31] = p ? 1u : 0u;
+	warp_rendezvous();
+	unsigned m = 0;
+	for (int i = 0; i < 32; ++i) m |= (unsigned)(g_slot[i] & 1u) << i;
+	warp_rendezvous();
+	return m;
+}
+static inline bool __any_sync(unsigned mk, bool p) { return __ballot_sync(mk, p) != 0; }
+static inline bool __all_sync(unsigned mk, bool p) { return g_lanes == 1 ? p : __ballot_sync(mk, p) == 0xffffffffu; }
+template <class T> static inline T emul_exchange(T v, int src)
+{
+	static_assert(sizeof(T) <= 8, "shuffle of more than 8 bytes");
+	uint64_t raw = 0; memcpy(&raw, &v, sizeof v);
+	g_slot[threadIdx.x & 31] = raw;
+	warp_rendezvous();
+	raw = g_slot[src & 31];
+	warp_rendezvous();
+	T r; memcpy(&r, &raw, sizeof r);
+	return r;
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32)
+{ if (g_lanes == 1) return v; const int lane = threadIdx.x & 31; return emul_exchange(v, (lane & ~(width - 1)) | (src & (width - 1))); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d, int width = 32)
+{ if (g_lanes == 1) return v; const int lane = threadIdx.x & 31; const int src = (lane & (width - 1)) >= d ? lane - d : lane; return emul_exchange(v, src); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int d, int width = 32)
+{ if (g_lanes == 1) return v; const int lane = threadIdx.x & 31; return emul_exchange(v, lane ^ d); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { if (g_lanes != 1) warp_rendezvous(); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
@@ -68,6 +105,20 @@ struct Emul {
 	std::vector<uint8_t> rep;
 };
 void one_thread() { blockDim.x = 1; gridDim.x = 1; threadIdx.x = 0; blockIdx.x = 0; }
+}
+
+// one CTA of one real warp: 32 host threads, lane = threadIdx.x
+template <class K> static void emul_warp(K kernel)
+{
+	pthread_barrier_init(&g_bar, nullptr, 32);
+	g_lanes = 32;
+	blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
+	std::vector<std::thread> th;
+	for (unsigned lane = 0; lane < 32; ++lane) th.emplace_back([=]() { threadIdx.x = lane; kernel(); });
+	for (auto &t : th) t.join();
+	g_lanes = 1;
+	pthread_barrier_destroy(&g_bar);
+	one_thread();
 }
 
 extern "C" {
@@ -237,6 +288,92 @@ int64_t seed_emul_run(void *e, uint32_t n_reads, const uint8_t *bases, const uin
 		stats[9] = n_lit_fast; stats[10] = n_punt; stats[11] = n_follow;   // literal tasks: straight from k_seed_fast, punted by k_seed_walk, second-pass follow-ups of what k_seed_walk found
 		for (int k = 0; k < 16; ++k) stats[16 + k] = counters[20 + k];
 	}
+	return (int64_t)n;
+}
+
+// The same batch with REAL warps (32 host threads per warp, see emul_warp) and every seeding kernel of the library, the literal one
+// included; nothing is resolved by the oracle.  mode 0: k_seed_fast -> k_seed_walk -> k_seed in call mode -> k_seed_r3_fast (what a
+// batch runs with the dense SA); mode 1: k_seed alone in read mode -> k_seed_r3 (what it runs without the fast kernels).
+// Returns the number of mems (all passes the options ask for), or < 0.
+int64_t seed_emul_run32(void *e, uint32_t n_reads, const uint8_t *bases, const uint32_t *off, const cs_seed_opt_t *opt, int mode,
+                        cs_mem_t *out_mems, uint64_t cap, uint32_t *mem_off, uint64_t *stats)
+{
+	Emul *E = static_cast<Emul*>(e);
+	const DevIndex &d = E->d;
+	const uint64_t n_bases = off[n_reads];
+	uint32_t max_len = 0;
+	for (uint32_t r = 0; r < n_reads; ++r) max_len = std::max(max_len, off[r + 1] - off[r]);
+	if (max_len + 32 > 32 * CS_READ_SMEM) return -101;
+	std::vector<uint8_t> pb(bases, bases + n_bases); pb.resize(n_bases + 256, 0);
+	std::vector<uint64_t> packed((n_bases >> 5) + 2 * (size_t)n_reads + 8, 0);
+	std::vector<uint32_t> nmask(packed.size(), 0);
+	blockDim.x = 8; gridDim.x = 1; blockIdx.x = 0;
+	for (unsigned t = 0; t < 8; ++t) { threadIdx.x = t; k_pack_reads(pb.data(), off, n_reads, packed.data(), nmask.data()); }
+	one_thread();
+	const uint32_t mem_cap = std::min<uint32_t>(2 * max_len + 16, 4096), defer_cap = 8 * n_reads + 4096;
+	const uint32_t spill_cap = max_len > CS_LIST_SMEM ? max_len - CS_LIST_SMEM + 1 : 1;
+	const size_t nthreads = CS_SEED_BLOCK;                       // one CTA; its first warp runs
+	std::vector<uint32_t> ctrl(64, 0);
+	std::vector<unsigned long long> counters(64, 0), req(8, 0);
+	unsigned long long pool_used = 0;
+	int error = 0;
+	uint32_t n_defer = 0, n_lit = 0, n_defer_fast = 0, n_walk = 0;
+	std::vector<uint4> defer_q(defer_cap), defer_lx(defer_cap), thread_lx(nthreads), spill((size_t)spill_cap * nthreads);
+	std::vector<uint32_t> defer_bits(defer_cap, 0), lit_q(defer_cap, 0), x_n(defer_cap, 0xffffffffu), read_last_q(n_reads + 1, 0xffffffffu), read_n_mems(n_reads + 1, 0);
+	std::vector<uint32_t> walk_order(defer_cap, 0xffffffffu);
+	std::vector<uint64_t> x_off(defer_cap, 0), read_pool_off(n_reads + 1, 0);
+	std::vector<cs_mem_t> thread_mems((size_t)mem_cap * nthreads), pool(cap);
+	const uint32_t kp1 = (uint32_t)opt->min_seed_len + 1;
+	std::vector<cs_mem_t> r3_mems((size_t)n_bases / kp1 + n_reads + 2);
+	std::vector<uint32_t> r3_n(n_reads + 1, 0);
+	SeedArgs a;
+	memset(&a, 0, sizeof a);
+	a.bases = pb.data(); a.off = off; a.n_reads = n_reads; a.opt = *opt; a.packed = packed.data(); a.off_bias = 0; a.nmask = nmask.data();
+	a.next_read = ctrl.data(); a.defer_bits = defer_bits.data(); a.defer_lx = defer_lx.data(); a.thread_lx = thread_lx.data();
+	a.lit_q = lit_q.data(); a.n_lit = &n_lit; a.defer_cap = defer_cap; a.n_defer = &n_defer; a.n_defer_fast = &n_defer_fast;
+	a.walk_order = walk_order.data(); a.n_walk = &n_walk; a.read_last_q = read_last_q.data();
+	a.x_off = x_off.data(); a.x_n = x_n.data(); a.thread_mems = thread_mems.data(); a.mem_cap = mem_cap; a.spill = spill.data(); a.spill_cap = spill_cap;
+	a.pool = pool.data(); a.pool_cap = cap; a.pool_used = &pool_used; a.read_pool_off = read_pool_off.data(); a.read_n_mems = read_n_mems.data();
+	a.r3_mems = r3_mems.data(); a.r3_n_mems = r3_n.data();
+	a.counters = counters.data(); a.req = req.data(); a.error = &error;
+	const SeedArgs *pa = &a;
+	if (mode == 0) {
+		a.defer_q = defer_q.data();
+		emul_warp([&]() { k_seed_fast(d, *pa); });
+		n_defer_fast = n_defer;
+		if (n_defer > defer_cap) return -102;
+		uint32_t hist[64] = {0}, cursor[64] = {0};
+		for (uint32_t qq = 0; qq < n_defer_fast; ++qq) if (defer_q[qq].y >> 31) ++hist[walk_cost_class(defer_q[qq], defer_bits[qq], (int)d.pt_k, (int)d.kt_depth)];
+		k_walk_scan(hist, cursor, &n_walk);
+		for (uint32_t qq = 0; qq < n_defer_fast; ++qq) if (defer_q[qq].y >> 31) walk_order[cursor[walk_cost_class(defer_q[qq], defer_bits[qq], (int)d.pt_k, (int)d.kt_depth)]++] = qq;
+		emul_warp([&]() { k_seed_walk(d, *pa); });
+		emul_warp([&]() { k_seed(d, *pa); });                       // call mode: the tasks listed in lit_q
+		if (opt->max_mem_intv > 0) emul_warp([&]() { k_seed_r3_fast(d, *pa); });
+	} else {
+		a.defer_q = nullptr;
+		emul_warp([&]() { k_seed(d, *pa); });                       // read mode: every read, literally
+		if (opt->max_mem_intv > 0) emul_warp([&]() { k_seed_r3(d, *pa); });
+	}
+	if (error) return error;
+	std::vector<std::vector<cs_mem_t>> per(n_reads);
+	for (uint32_t r = 0; r < n_reads; ++r) {
+		for (uint32_t m = 0; m < read_n_mems[r]; ++m) per[r].push_back(pool[read_pool_off[r] + m]);
+		if (opt->max_mem_intv > 0) for (uint32_t m = 0; m < r3_n[r]; ++m) per[r].push_back(r3_mems[(size_t)(off[r] / kp1) + r + m]);
+	}
+	if (mode == 0)
+		for (uint32_t q = 0; q < n_defer && q < defer_cap; ++q) {
+			if (x_n[q] == 0xffffffffu) return -104;                  // a queued call nobody executed
+			for (uint32_t m = 0; m < x_n[q]; ++m) per[defer_q[q].x].push_back(pool[x_off[q] + m]);
+		}
+	uint64_t n = 0;
+	mem_off[0] = 0;
+	for (uint32_t r = 0; r < n_reads; ++r) {
+		std::stable_sort(per[r].begin(), per[r].end(), [](const cs_mem_t &x, const cs_mem_t &y) { return x.info < y.info; });
+		if (n + per[r].size() > cap) return -100;
+		for (const cs_mem_t &m : per[r]) out_mems[n++] = m;
+		mem_off[r + 1] = (uint32_t)n;
+	}
+	if (stats) { for (int k = 0; k < 4; ++k) stats[k] = counters[k]; stats[4] = req[0]; stats[5] = req[1]; stats[6] = n_defer; stats[7] = n_lit; stats[12] = req[3]; stats[13] = req[2]; }
 	return (int64_t)n;
 }
 

@@ -1,8 +1,9 @@
-"""k_seed_fast / k_seed_walk and the index-construction kernels of compseed_b200/csrc/cs_kernels.cu checked on the CPU: the same
-source compiled as plain C++ with one-lane warps (tests/emul/seed_emul.cpp) and run serially; the calls the two kernels hand
-on to the literal kernel are resolved with the oracle's bwt_smem1a.  Passes 1-2 of mem_collect_intv must equal the oracle's,
-with and without the repeat-length array (DevIndex::rep).  Test infrastructure only -- the shipped library has no CPU path;
-the GPU tests run the real kernels."""
+"""The seeding and index-construction kernels of compseed_b200/csrc/cs_kernels.cu checked on the CPU: the same source compiled as
+plain C++ (tests/emul/seed_emul.cpp) and run (a) with one-lane warps, serially -- k_seed_fast, k_seed_walk, k_seed_r3_fast, the calls
+handed on to the literal kernel resolved with the oracle's bwt_smem1a --, and (b) with REAL warps, one host thread per lane and every
+warp intrinsic a rendezvous of the 32 -- all seeding kernels, the literal k_seed (call mode and read mode) and the general third pass
+included, nothing resolved by the oracle.  The result must equal the oracle's mem_collect_intv, with and without the repeat-length
+array (DevIndex::rep).  Test infrastructure only -- the shipped library has no CPU path; the GPU tests run the real kernels."""
 import ctypes as C
 import os
 import subprocess
@@ -33,6 +34,8 @@ def _build(tmp_path_factory, name, defs):
     L.seed_emul_free.argtypes = [C.c_void_p]
     L.seed_emul_rep.restype = C.c_void_p
     L.seed_emul_rep.argtypes = [C.c_void_p]
+    L.seed_emul_run32.restype = C.c_int64
+    L.seed_emul_run32.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(_SeedOpt), C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -138,6 +141,34 @@ def test_third_pass_kernel_equals_the_oracle(emul, name, mk, rd, so):
         assert np.array_equal(mem_off, want.mem_off) and np.array_equal(mems, want.mems), (name, so, use_rep)
         req[use_rep] = int(stats[12])
     assert req[0] > 0 and req[1] > 0
+
+
+@pytest.mark.parametrize("name,mk,rd", CASES, ids=[c[0] for c in CASES])
+def test_real_warps_every_seeding_kernel_equals_the_oracle(emul, name, mk, rd):
+    """32 host threads per warp: k_seed_fast -> k_seed_walk -> k_seed (call mode) -> k_seed_r3_fast, and k_seed alone (read mode) ->
+    k_seed_r3; vote-controlled loops, warp-aggregated atomics and the literal kernel's cooperative filter with their real semantics."""
+    so = (19, 28, 10, 20, 500)
+    ref = mk()
+    n_reads = 500
+    bases, off, _ = synth.simulate_reads(ref, n_reads, rd["lens"], rd["err"], seed=14, n_rate=rd["n_rate"])
+    oi = O.OracleIndex.build(ref)
+    want = oi.seed(bases, off, min_seed_len=so[0], split_len=so[1], split_width=so[2], max_mem_intv=so[3], max_occ=so[4])
+    K, depth = default_k_depth(oi.seq_len)
+    L2 = np.ascontiguousarray(oi.L2, np.uint64)
+    E = emul.seed_emul_index(oi.primary, _p(L2), oi.seq_len, _p(oi.bwt), oi.bwt_size, _p(oi.sa), oi.n_sa, oi.sa_intv, min(K, so[0]), depth, 2, 1)
+    try:
+        for mode in (0, 1):
+            cap = n_reads * 64
+            mems = np.zeros((cap, 4), np.uint64)
+            mem_off = np.zeros(n_reads + 1, np.uint32)
+            stats = np.zeros(64, np.uint64)
+            rc = emul.seed_emul_run32(E, n_reads, _p(bases), _p(off), C.byref(_SeedOpt(*so)), mode, _p(mems), cap, _p(mem_off), _p(stats))
+            assert rc == want.mem_off[-1], (name, mode, rc)
+            assert np.array_equal(mem_off, want.mem_off) and np.array_equal(mems[:rc], want.mems), (name, mode)
+            if mode == 0:
+                assert int(stats[6]) > 0          # calls were handed on
+    finally:
+        emul.seed_emul_free(E)
 
 
 def test_repeat_lengths_match_their_definition(emul):
