@@ -171,6 +171,30 @@ def test_real_warps_every_seeding_kernel_equals_the_oracle(emul, name, mk, rd):
         emul.seed_emul_free(E)
 
 
+@pytest.mark.parametrize("so", [(19, 28, 10, 20, 500), (19, 19, 10, 40, 50)], ids=["default", "r1.0y40c50"])
+def test_real_warps_boundary_reads(emul, so):
+    """synth.boundary_reads (text ends of both strands, strand-bridging matches, substitutions and Ns at 32-base word edges, lengths
+    around multiples of 32 and 255/256) through every seeding kernel with real warps."""
+    ref = synth.random_reference(60_000, seed=51)
+    bases, off = synth.boundary_reads(ref)
+    n_reads = off.shape[0] - 1
+    oi = O.OracleIndex.build(ref)
+    want = oi.seed(bases, off, min_seed_len=so[0], split_len=so[1], split_width=so[2], max_mem_intv=so[3], max_occ=so[4])
+    K, depth = default_k_depth(oi.seq_len)
+    L2 = np.ascontiguousarray(oi.L2, np.uint64)
+    E = emul.seed_emul_index(oi.primary, _p(L2), oi.seq_len, _p(oi.bwt), oi.bwt_size, _p(oi.sa), oi.n_sa, oi.sa_intv, min(K, so[0]), depth, 2, 1)
+    try:
+        for mode in (0, 1):
+            cap = n_reads * 64
+            mems = np.zeros((cap, 4), np.uint64)
+            mem_off = np.zeros(n_reads + 1, np.uint32)
+            rc = emul.seed_emul_run32(E, n_reads, _p(bases), _p(off), C.byref(_SeedOpt(*so)), mode, _p(mems), cap, _p(mem_off), None)
+            assert rc == want.mem_off[-1], (mode, rc)
+            assert np.array_equal(mem_off, want.mem_off) and np.array_equal(mems[:rc], want.mems), mode
+    finally:
+        emul.seed_emul_free(E)
+
+
 def test_repeat_lengths_match_their_definition(emul):
     """rep[p] against a brute-force count of occurrences on a small repeat-rich text."""
     ref = synth.repeat_rich_reference(6_000, seed=5, n_segdup=6, segdup_len=300, n_tandem=4)
